@@ -1,0 +1,523 @@
+/*
+ * elfel_oracle.c -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+ *
+ * A plain-C, single-threaded restatement of the algorithm of Elfel.jl's assembly
+ * hot path: per-element quadrature loop -> LocalMatrixAssembler -> COO append in
+ * SysmatAssemblerSparse -> SparseArrays.sparse().  Only tests/, bench.py's
+ * cpu_baseline / --impl reference leg and __graft_entry__.smoke() may load it, and
+ * only as the checker / CPU baseline.  The product (libelfelgpu.so) never links it.
+ *
+ * Build: gcc -O2 -ffp-contract=off (no FMA contraction, so this file is the fixed
+ * point of the operation order written in the reference).
+ *
+ * Parity pin: validated against the reference's own golden values by
+ * tests/test_oracle_golden.py (test/test_assemblers.jl:27-34, test/test_heat.jl:110,
+ * test/test_stokes.jl:130,551-553,779, test/test_qpiterators.jl:21-61,
+ * test/test_refshapes.jl:26-29,45-48, test/test_feiterators.jl:58-64,154-172).
+ * Julia itself cannot run here (no julia binary, MeshCore/MeshSteward/StaticArrays are
+ * not vendored), so ULP-level operation order inside StaticArrays' 2x2 solve and
+ * SparseArrays.sparse is restated from their published algorithms (StaticArrays 1.0.1
+ * src/solve.jl, SparseArrays sparse!) and is "parity unpinned" below 1e-12.
+ *
+ * Every function cites the reference file:line it follows (paths relative to the
+ * Elfel.jl repository root).
+ *
+ * Array layouts are the reference's memory layouts, 1-based Int64 indices:
+ *   conn    : nen x nel   Int64 (node ids of element e at conn[e*nen + k])  -- MeshCore IncRel
+ *   xy      : 2 x nnodes  Float64                                          -- VecAttrib "geom"
+ *   dofnums : ncomp x nnodes Int64 (FEField.dofnums, src/FEFields.jl:15)
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+
+#define EFO_T3 3
+#define EFO_Q4 4
+#define EFO_T6 6
+
+enum {
+    EFO_FORM_HEAT = 1,            /* examples/heat/poisson/t3.jl:53-58, q4.jl:43-48 */
+    EFO_FORM_ELASTICITY = 2,      /* examples/elasticity/stretch/t6.jl:42-58 */
+    EFO_FORM_STOKES_GEN = 3,      /* examples/stokes/colliding_flow/ht_p2_p1_gen.jl:48-79 */
+    EFO_FORM_STOKES_REDDY = 4,    /* examples/stokes/colliding_flow/ht_p2_p1.jl:56-104 */
+    EFO_FORM_STOKES_VECLAP_ALT = 5, /* examples/stokes/colliding_flow/ht_p2_p1_veclap_alt.jl:61-90 */
+    EFO_FORM_STOKES_VECLAP = 6    /* examples/stokes/colliding_flow/ht_p2_p1_veclap.jl:55-97 */
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Quadrature rules.  src/RefShapes.jl:85-110 (_gauss1), :113-119 (_triangle),
+ * :301-323 (triangle rule), :333-366 (square tensor product, i outer / j inner).
+ * pc is npts x 2 row-major here (point p: pc[2p], pc[2p+1]).  Returns npts or -1.
+ * For triangles `rule` is npts (1 or 3); for squares `rule` is the Gauss order (1..5).
+ * ------------------------------------------------------------------------------------------ */
+static int gauss1(int order, double *pc, double *w) /* src/RefShapes.jl:91-106 */
+{
+    switch (order) {
+    case 1: pc[0] = 0.0; w[0] = 2.0; return 1;
+    case 2: pc[0] = -0.577350269189626; pc[1] = 0.577350269189626; w[0] = 1.0; w[1] = 1.0; return 2;
+    case 3: pc[0] = -0.774596669241483; pc[1] = 0.0; pc[2] = 0.774596669241483;
+            w[0] = 0.5555555555555556; w[1] = 0.8888888888888889; w[2] = 0.5555555555555556; return 3;
+    case 4: pc[0] = -0.86113631159405; pc[1] = -0.33998104358486; pc[2] = 0.33998104358486; pc[3] = 0.86113631159405;
+            w[0] = 0.34785484513745; w[1] = 0.65214515486255; w[2] = 0.65214515486255; w[3] = 0.34785484513745; return 4;
+    case 5: pc[0] = -0.906179845938664; pc[1] = -0.538469310105683; pc[2] = 0.000000000000000;
+            pc[3] = 0.538469310105683; pc[4] = 0.906179845938664;
+            w[0] = 0.236926885056189; w[1] = 0.478628670499367; w[2] = 0.568888888888889;
+            w[3] = 0.478628670499367; w[4] = 0.236926885056189; return 5;
+    default: return -1; /* order > 5 is Golub-Welsch in the reference: out of scope */
+    }
+}
+
+int efo_quadrature(int elemkind, int rule, double *pc, double *w)
+{
+    if (elemkind == EFO_T3 || elemkind == EFO_T6) {
+        if (rule == 1) { /* src/RefShapes.jl:114-116 */
+            pc[0] = 1.0 / 3.; pc[1] = 1.0 / 3.;
+            w[0] = 1.0 / 2.0;
+            return 1;
+        } else if (rule == 3) { /* src/RefShapes.jl:117-119 */
+            pc[0] = 2.0 / 3; pc[1] = 1.0 / 6;
+            pc[2] = 1.0 / 6; pc[3] = 2.0 / 3;
+            pc[4] = 1.0 / 6; pc[5] = 1.0 / 6;
+            w[0] = (1.0 / 3) / 2; w[1] = (1.0 / 3) / 2; w[2] = (1.0 / 3) / 2;
+            return 3;
+        }
+        return -1;
+    } else if (elemkind == EFO_Q4) { /* src/RefShapes.jl:350-362 */
+        double p1[5], w1[5];
+        int np = gauss1(rule, p1, w1);
+        if (np < 0) return -1;
+        int r = 0;
+        for (int i = 0; i < np; i++)
+            for (int j = 0; j < np; j++) {
+                pc[2 * r] = p1[i]; pc[2 * r + 1] = p1[j];
+                w[r] = w1[i] * w1[j];
+                r++;
+            }
+        return r;
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Basis functions and parametric gradients.
+ * T3: src/FElements.jl:239-246; T6: :264-288; Q4: :306-320.  g is nbf x 2 row-major.
+ * Julia evaluates `-3+4*r+4*s` as (-3 + 4r) + 4s, `4-8*r-4*s` as (4 - 8r) - 4s.
+ * ------------------------------------------------------------------------------------------ */
+int efo_nbf(int elemkind) { return elemkind; }
+
+void efo_bfun(int elemkind, double r, double s, double *N)
+{
+    if (elemkind == EFO_T3) {
+        N[0] = (1 - r - s); N[1] = r; N[2] = s;
+    } else if (elemkind == EFO_T6) {
+        double t = 1. - r - s;
+        N[0] = t * (t + t - 1);
+        N[1] = r * (r + r - 1);
+        N[2] = s * (s + s - 1);
+        N[3] = 4 * r * t;
+        N[4] = 4 * r * s;
+        N[5] = 4 * s * t;
+    } else if (elemkind == EFO_Q4) {
+        N[0] = 0.25 * (1. - r) * (1. - s);
+        N[1] = 0.25 * (1. + r) * (1. - s);
+        N[2] = 0.25 * (1. + r) * (1. + s);
+        N[3] = 0.25 * (1. - r) * (1. + s);
+    }
+}
+
+void efo_bfungradpar(int elemkind, double r, double s, double *g)
+{
+    if (elemkind == EFO_T3) {
+        g[0] = -1.; g[1] = -1.;
+        g[2] = +1.; g[3] = 0.;
+        g[4] = 0.;  g[5] = +1.;
+    } else if (elemkind == EFO_T6) {
+        g[0] = -3 + 4 * r + 4 * s; g[1] = -3 + 4 * r + 4 * s;
+        g[2] = 4 * r - 1;          g[3] = 0.0;
+        g[4] = 0.0;                g[5] = 4 * s - 1;
+        g[6] = 4 - 8 * r - 4 * s;  g[7] = -4 * r;
+        g[8] = 4 * s;              g[9] = 4 * r;
+        g[10] = -4 * s;            g[11] = 4 - 4 * r - 8 * s;
+    } else if (elemkind == EFO_Q4) {
+        g[0] = -(1. - s) * 0.25; g[1] = -(1. - r) * 0.25;
+        g[2] = (1. - s) * 0.25;  g[3] = -(1. + r) * 0.25;
+        g[4] = (1. + s) * 0.25;  g[5] = (1. + r) * 0.25;
+        g[6] = -(1. + s) * 0.25; g[7] = (1. - r) * 0.25;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Per-quadrature-point tables: QPIterator ctor / __bfundata, src/QPIterators.jl:14-50,79-84.
+ * ------------------------------------------------------------------------------------------ */
+#define MAXQP 25
+#define MAXBF 6
+typedef struct {
+    int kind, nbf, npts;
+    double w[MAXQP];
+    double N[MAXQP][MAXBF];        /* scalar basis functions       */
+    double gp[MAXQP][MAXBF][2];    /* scalar parametric gradients  */
+} qptab;
+
+static int qptab_init(qptab *t, int elemkind, int rule)
+{
+    double pc[2 * MAXQP];
+    t->kind = elemkind; t->nbf = efo_nbf(elemkind);
+    t->npts = efo_quadrature(elemkind, rule, pc, t->w);
+    if (t->npts < 0) return -1;
+    for (int q = 0; q < t->npts; q++) {
+        efo_bfun(elemkind, pc[2 * q], pc[2 * q + 1], t->N[q]);
+        efo_bfungradpar(elemkind, pc[2 * q], pc[2 * q + 1], &t->gp[q][0][0]);
+    }
+    return 0;
+}
+
+/* _jac: src/FElements.jl:148-156.  J = sum_n x_n (outer) gradNpar_n, summed in node order,
+ * first term assigned.  J[i][k] = sum_n x_n[i] * g_n[k].
+ * Jacobian(Val{2}): src/FElements.jl:120-129: J11*J22 - J21*J12. */
+static double jacjac(const double *xy, const int64_t *nodes, int nen, const double gp[][2], double J[2][2])
+{
+    const double *x = xy + 2 * (nodes[0] - 1);
+    J[0][0] = x[0] * gp[0][0]; J[0][1] = x[0] * gp[0][1];
+    J[1][0] = x[1] * gp[0][0]; J[1][1] = x[1] * gp[0][1];
+    for (int n = 1; n < nen; n++) {
+        x = xy + 2 * (nodes[n] - 1);
+        J[0][0] = J[0][0] + x[0] * gp[n][0]; J[0][1] = J[0][1] + x[0] * gp[n][1];
+        J[1][0] = J[1][0] + x[1] * gp[n][0]; J[1][1] = J[1][1] + x[1] * gp[n][1];
+    }
+    return J[0][0] * J[1][1] - J[1][0] * J[0][1];
+}
+
+/* bfungrad: src/QPIterators.jl:132-140.  gradpar[j] / Jac with Adjoint{SVector{2}} / SMatrix{2,2}
+ * = (Jac' \ g)' ; StaticArrays 1.0.1 2x2 solve: d = det(Jac'), x = ((a22 b1 - a12 b2)/d, (a11 b2 - a21 b1)/d)
+ * with a = Jac'.  Two true divisions by d. */
+static void bfungrad(int nbf, const double gp[][2], double J[2][2], double g[][2])
+{
+    double d = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+    for (int j = 0; j < nbf; j++) {
+        g[j][0] = (J[1][1] * gp[j][0] - J[1][0] * gp[j][1]) / d;
+        g[j][1] = (J[0][0] * gp[j][1] - J[0][1] * gp[j][0]) / d;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * COO buffer = SysmatAssemblerSparse (src/Assemblers.jl:19-24), caller-allocated.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct { int64_t *row, *col; double *val; int64_t n; } coo;
+
+/* assemble!(self, lma): src/Assemblers.jl:97-102 with init! ordering src/LocalAssemblers.jl:68-83:
+ * column-major, k = j*nr + i, row = rdofs[i], col = cdofs[j]. M is column-major nr x nc. */
+static void coo_append(coo *a, int nr, int nc, const int64_t *rdofs, const int64_t *cdofs, const double *M)
+{
+    for (int j = 0; j < nc; j++)
+        for (int i = 0; i < nr; i++) {
+            a->row[a->n] = rdofs[i]; a->col[a->n] = cdofs[j]; a->val[a->n] = M[j * nr + i];
+            a->n++;
+        }
+}
+/* assemble!(self, transpose(lma)): src/Assemblers.jl:109-114.  Iterating transpose(parent) in
+ * column-major order of the transposed view: outer = parent row i, inner = parent column j. */
+static void coo_append_T(coo *a, int nr, int nc, const int64_t *rdofs, const int64_t *cdofs, const double *M)
+{
+    for (int i = 0; i < nr; i++)
+        for (int j = 0; j < nc; j++) {
+            a->row[a->n] = cdofs[j]; a->col[a->n] = rdofs[i]; a->val[a->n] = M[j * nr + i];
+            a->n++;
+        }
+}
+
+/* _storedofs!: src/FEIterators.jl:161-171 -- node-major, component-minor. */
+static void eldofs(const int64_t *nodes, int nen, const int64_t *dofnums, int ncomp, int64_t *d)
+{
+    int p = 0;
+    for (int k = 0; k < nen; k++)
+        for (int i = 0; i < ncomp; i++)
+            d[p++] = dofnums[(nodes[k] - 1) * ncomp + i];
+}
+
+/* B(g,k): examples/elasticity/stretch/t6.jl:42 */
+static void Bmat(const double g[2], int k, double b[3])
+{
+    if (k == 1) { b[0] = g[0]; b[1] = 0; b[2] = g[1]; }
+    else        { b[0] = 0; b[1] = g[1]; b[2] = g[0]; }
+}
+/* D*b for SMatrix{3,3} (column-major storage Dcm[c*3+r]) times SVector{3}: StaticArrays unrolled
+ * row sums ((D[r,1] b1 + D[r,2] b2) + D[r,3] b3). */
+static void Dmul(const double *Dcm, const double b[3], double o[3])
+{
+    for (int r = 0; r < 3; r++)
+        o[r] = (Dcm[0 * 3 + r] * b[0] + Dcm[1 * 3 + r] * b[1]) + Dcm[2 * 3 + r] * b[2];
+}
+static double dot3(const double a[3], const double b[3]) { return (a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]; }
+static double dot2(const double a[2], const double b[2]) { return a[0] * b[0] + a[1] * b[1]; }
+
+/* Number of COO triplets each element appends for a form. */
+int64_t efo_triplets_per_element(int form, int vkind, int pkind)
+{
+    int64_t nu = vkind, np = pkind;
+    switch (form) {
+    case EFO_FORM_HEAT: return nu * nu;
+    case EFO_FORM_ELASTICITY: return 4 * nu * nu;
+    case EFO_FORM_STOKES_GEN:
+    case EFO_FORM_STOKES_VECLAP_ALT: return 4 * nu * nu + 2 * (2 * nu * np);
+    case EFO_FORM_STOKES_REDDY: return 4 * nu * nu + 4 * nu * np;
+    case EFO_FORM_STOKES_VECLAP: return 2 * nu * nu + 4 * nu * np;
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * The element loop (the user-written integrate! closures), appending COO triplets.
+ *
+ * mesh 0 (vconn/vkind/vxy): the mesh of space 0 (heat/elasticity: the only mesh; Stokes: velocity mesh).
+ * mesh 1 (pconn/pkind/pxy): Stokes pressure mesh (T6toT3), else NULL.
+ * dof0/dof1/dof2: FEField.dofnums of spaces 0..2; ncomp = components per node.
+ *   HEAT:        space0 scalar.          params = [kappa]
+ *   ELASTICITY:  space0 2 comps.         params = D (3x3 column-major, 9 doubles)
+ *   STOKES_GEN:  space0 = Uh (2 comps), space1 = Ph.             params = D (9)
+ *   STOKES_VECLAP_ALT: same spaces.                               params = [mu]
+ *   STOKES_REDDY / STOKES_VECLAP: space0 = ux, space1 = uy, space2 = p.  params = [mu]
+ * quad: triangle npts or square Gauss order (the QPIterator settings).
+ * Elements [e0, e1) are processed (0-based range) so the baseline can time a bounded sample.
+ * Returns number of triplets appended, or <0 on error.
+ * ------------------------------------------------------------------------------------------ */
+int64_t efo_assemble_coo(int form, int quad, int64_t e0, int64_t e1,
+                         const int64_t *vconn, int vkind, const double *vxy,
+                         const int64_t *pconn, int pkind, const double *pxy,
+                         const int64_t *dof0, const int64_t *dof1, const int64_t *dof2,
+                         const double *params,
+                         int64_t *row, int64_t *col, double *val)
+{
+    coo a = { row, col, val, 0 };
+    qptab vq, pq;
+    if (qptab_init(&vq, vkind, quad) < 0) return -1;
+    if (pconn && qptab_init(&pq, pkind, quad) < 0) return -1;
+    const int nu = vkind;
+    double J[2][2];
+    double g[MAXBF][2];
+
+    if (form == EFO_FORM_HEAT) { /* examples/heat/poisson/t3.jl:41-64 */
+        const double kappa = params[0];
+        int64_t d[MAXBF]; double ke[MAXBF * MAXBF];
+        for (int64_t e = e0; e < e1; e++) {
+            const int64_t *nodes = vconn + e * nu;
+            eldofs(nodes, nu, dof0, 1, d);
+            memset(ke, 0, sizeof ke);
+            for (int q = 0; q < vq.npts; q++) {
+                double Jd = jacjac(vxy, nodes, nu, vq.gp[q], J);
+                bfungrad(nu, vq.gp[q], J, g);
+                double JxW = Jd * vq.w[q];
+                for (int j = 0; j < nu; j++)
+                    for (int i = 0; i < nu; i++)
+                        ke[j * nu + i] = ke[j * nu + i] + dot2(g[i], g[j]) * (kappa * JxW);
+            }
+            coo_append(&a, nu, nu, d, d, ke);
+        }
+        return a.n;
+    }
+
+    if (form == EFO_FORM_ELASTICITY) { /* examples/elasticity/stretch/t6.jl:40-63 */
+        const int nd = 2 * nu;
+        int64_t d[2 * MAXBF]; double ke[4 * MAXBF * MAXBF];
+        for (int64_t e = e0; e < e1; e++) {
+            const int64_t *nodes = vconn + e * nu;
+            eldofs(nodes, nu, dof0, 2, d);
+            memset(ke, 0, sizeof ke);
+            for (int q = 0; q < vq.npts; q++) {
+                double Jd = jacjac(vxy, nodes, nu, vq.gp[q], J);
+                bfungrad(nu, vq.gp[q], J, g);
+                double JxW = Jd * vq.w[q];
+                for (int j = 0; j < nd; j++) {
+                    double Bj[3], DBj[3];
+                    Bmat(g[j / 2], j % 2 + 1, Bj); /* edofbfnum/edofcompnt: src/FESpaces.jl:87-105 */
+                    Dmul(params, Bj, DBj);
+                    for (int i = 0; i < nd; i++) {
+                        double Bi[3];
+                        Bmat(g[i / 2], i % 2 + 1, Bi);
+                        ke[j * nd + i] = ke[j * nd + i] + dot3(DBj, Bi) * JxW;
+                    }
+                }
+            }
+            coo_append(&a, nd, nd, d, d, ke);
+        }
+        return a.n;
+    }
+
+    if (form == EFO_FORM_STOKES_GEN || form == EFO_FORM_STOKES_VECLAP_ALT) {
+        /* gen: examples/stokes/colliding_flow/ht_p2_p1_gen.jl:46-90
+         * veclap_alt: ht_p2_p1_veclap_alt.jl:60-98, test/test_stokes.jl:629-668 */
+        const int nd = 2 * nu, np = pkind;
+        int64_t du[2 * MAXBF], dp[MAXBF];
+        double kuu[4 * MAXBF * MAXBF], kup[2 * MAXBF * MAXBF];
+        for (int64_t e = e0; e < e1; e++) {
+            const int64_t *unodes = vconn + e * nu, *pnodes = pconn + e * np;
+            eldofs(unodes, nu, dof0, 2, du);
+            eldofs(pnodes, np, dof1, 1, dp);
+            memset(kuu, 0, sizeof kuu); memset(kup, 0, sizeof kup);
+            for (int q = 0; q < vq.npts; q++) {
+                double Jd = jacjac(vxy, unodes, nu, vq.gp[q], J); /* velocity element Jacobian (:61) */
+                double JxW = Jd * vq.w[q];
+                bfungrad(nu, vq.gp[q], J, g);
+                const double *Np = pq.N[q];
+                if (form == EFO_FORM_STOKES_GEN) {
+                    for (int j = 0; j < nd; j++) {
+                        double Bj[3], DBj[3];
+                        Bmat(g[j / 2], j % 2 + 1, Bj);
+                        Dmul(params, Bj, DBj);
+                        for (int i = 0; i < nd; i++) {
+                            double Bi[3];
+                            Bmat(g[i / 2], i % 2 + 1, Bi);
+                            kuu[j * nd + i] = kuu[j * nd + i] + dot3(Bi, DBj) * (JxW);
+                        }
+                    }
+                } else {
+                    const double mu = params[0];
+                    for (int j = 0; j < nd; j++)
+                        for (int i = 0; i < nd; i++)
+                            if (i % 2 == j % 2)
+                                kuu[j * nd + i] = kuu[j * nd + i] + (mu * JxW) * (dot2(g[i / 2], g[j / 2]));
+                }
+                for (int j = 0; j < np; j++)
+                    for (int i = 0; i < nd; i++)
+                        kup[j * nd + i] = kup[j * nd + i] + (-JxW * Np[j]) * g[i / 2][i % 2];
+            }
+            coo_append(&a, nd, nd, du, du, kuu);
+            coo_append(&a, nd, np, du, dp, kup);
+            coo_append_T(&a, nd, np, du, dp, kup);
+        }
+        return a.n;
+    }
+
+    if (form == EFO_FORM_STOKES_REDDY || form == EFO_FORM_STOKES_VECLAP) {
+        /* Reddy: examples/stokes/colliding_flow/ht_p2_p1.jl:55-113, test/test_stokes.jl:374-422
+         * veclap: examples/stokes/colliding_flow/ht_p2_p1_veclap.jl:55-106 */
+        const int np = pkind;
+        const double mu = params[0];
+        int64_t dx[MAXBF], dy[MAXBF], dp[MAXBF];
+        double kxx[MAXBF * MAXBF], kyy[MAXBF * MAXBF], kxy[MAXBF * MAXBF], kxp[MAXBF * MAXBF], kyp[MAXBF * MAXBF];
+        double gp_[MAXBF][2];
+        for (int64_t e = e0; e < e1; e++) {
+            const int64_t *unodes = vconn + e * nu, *pnodes = pconn + e * np;
+            eldofs(unodes, nu, dof0, 1, dx);
+            eldofs(unodes, nu, dof1, 1, dy);
+            eldofs(pnodes, np, dof2, 1, dp);
+            memset(kxx, 0, sizeof kxx); memset(kyy, 0, sizeof kyy); memset(kxy, 0, sizeof kxy);
+            memset(kxp, 0, sizeof kxp); memset(kyp, 0, sizeof kyp);
+            for (int q = 0; q < vq.npts; q++) {
+                double Jd = jacjac(pxy, pnodes, np, pq.gp[q], J); /* PRESSURE element Jacobian (:72) */
+                double JxW = Jd * pq.w[q];
+                bfungrad(np, pq.gp[q], J, gp_); /* gradNp: computed, unused (:74) */
+                bfungrad(nu, vq.gp[q], J, g);   /* gradNux == gradNuy numerically */
+                const double *Np = pq.N[q];
+                if (form == EFO_FORM_STOKES_REDDY) {
+                    for (int j = 0; j < nu; j++)
+                        for (int i = 0; i < nu; i++)
+                            kxx[j * nu + i] = kxx[j * nu + i] + (mu * JxW) * (2 * g[i][0] * g[j][0] + g[i][1] * g[j][1]);
+                    for (int j = 0; j < nu; j++)
+                        for (int i = 0; i < nu; i++)
+                            kyy[j * nu + i] = kyy[j * nu + i] + (mu * JxW) * (g[i][0] * g[j][0] + 2 * g[i][1] * g[j][1]);
+                    for (int j = 0; j < nu; j++)
+                        for (int i = 0; i < nu; i++)
+                            kxy[j * nu + i] = kxy[j * nu + i] + (mu * JxW) * (g[i][0] * g[j][1]);
+                } else {
+                    for (int j = 0; j < nu; j++)
+                        for (int i = 0; i < nu; i++)
+                            kxx[j * nu + i] = kxx[j * nu + i] + (mu * JxW) * dot2(g[i], g[j]);
+                    for (int j = 0; j < nu; j++)
+                        for (int i = 0; i < nu; i++)
+                            kyy[j * nu + i] = kyy[j * nu + i] + (mu * JxW) * dot2(g[i], g[j]);
+                }
+                for (int j = 0; j < np; j++)
+                    for (int i = 0; i < nu; i++)
+                        kxp[j * nu + i] = kxp[j * nu + i] + (-JxW) * (g[i][0] * Np[j]);
+                for (int j = 0; j < np; j++)
+                    for (int i = 0; i < nu; i++)
+                        kyp[j * nu + i] = kyp[j * nu + i] + (-JxW) * (g[i][1] * Np[j]);
+            }
+            if (form == EFO_FORM_STOKES_REDDY) { /* ht_p2_p1.jl:94-101 */
+                coo_append(&a, nu, nu, dx, dx, kxx);
+                coo_append(&a, nu, nu, dx, dy, kxy);
+                coo_append_T(&a, nu, nu, dx, dy, kxy);
+                coo_append(&a, nu, nu, dy, dy, kyy);
+            } else {                             /* ht_p2_p1_veclap.jl:89-94 */
+                coo_append(&a, nu, nu, dx, dx, kxx);
+                coo_append(&a, nu, nu, dy, dy, kyy);
+            }
+            coo_append(&a, nu, np, dx, dp, kxp);
+            coo_append_T(&a, nu, np, dx, dp, kxp);
+            coo_append(&a, nu, np, dy, dp, kyp);
+            coo_append_T(&a, nu, np, dy, dp, kyp);
+        }
+        return a.n;
+    }
+    return -2;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * finish!: src/Assemblers.jl:121-123 -> SparseArrays.sparse(I, J, V, m, n) (Julia stdlib sparse!):
+ *  (1) counting sort of the triplets by row into CSR, preserving input order inside a row;
+ *  (2) per row, a later duplicate column is folded into the FIRST occurrence: v = v + dup
+ *      (left to right in input order); numerical zeros are NOT dropped;
+ *  (3) CSR -> CSC by counting sort on columns => row indices ascending within a column;
+ *  (4) colptr is Int64, 1-based, length n+1.
+ * Any index < 1 or > m / n is an ArgumentError in Julia: return -1 here.
+ * colptr: ncol+1; rowval/nzval: capacity ntrip.  Returns nnz.
+ * ------------------------------------------------------------------------------------------ */
+int64_t efo_sparse(int64_t nrow, int64_t ncol, int64_t ntrip,
+                   const int64_t *I, const int64_t *Jc, const double *V,
+                   int64_t *colptr, int64_t *rowval, double *nzval)
+{
+    int64_t *rowptr = (int64_t *)calloc((size_t)nrow + 2, sizeof(int64_t));
+    int64_t *ccol = (int64_t *)malloc((size_t)(ntrip > 0 ? ntrip : 1) * sizeof(int64_t));
+    double *cval = (double *)malloc((size_t)(ntrip > 0 ? ntrip : 1) * sizeof(double));
+    int64_t *last = (int64_t *)malloc((size_t)(ncol > 0 ? ncol : 1) * sizeof(int64_t));
+    if (!rowptr || !ccol || !cval || !last) { free(rowptr); free(ccol); free(cval); free(last); return -3; }
+    for (int64_t k = 0; k < ntrip; k++) {
+        if (I[k] < 1 || I[k] > nrow || Jc[k] < 1 || Jc[k] > ncol) { free(rowptr); free(ccol); free(cval); free(last); return -1; }
+        rowptr[I[k] + 1]++;
+    }
+    /* rowptr[i+1] = start of row i (1-based i) while filling */
+    for (int64_t i = 1; i <= nrow; i++) rowptr[i + 1] += rowptr[i];
+    /* now rowptr[i] = number of entries in rows < i ... shift: start(i) = rowptr[i] */
+    for (int64_t k = 0; k < ntrip; k++) {
+        int64_t p = rowptr[I[k]]++;
+        ccol[p] = Jc[k]; cval[p] = V[k];
+    }
+    /* after fill rowptr[i] = end of row i = start of row i+1; start of row 1 = 0 */
+    for (int64_t j = 0; j < ncol; j++) last[j] = -1;
+    for (int64_t j = 0; j <= ncol; j++) colptr[j] = 0;
+    int64_t w = 0, start = 0;
+    for (int64_t i = 1; i <= nrow; i++) {
+        int64_t end = rowptr[i];
+        int64_t wrow = w;
+        for (int64_t p = start; p < end; p++) {
+            int64_t j = ccol[p] - 1;
+            if (last[j] >= wrow) {
+                cval[last[j]] = cval[last[j]] + cval[p];
+            } else {
+                last[j] = w; ccol[w] = ccol[p]; cval[w] = cval[p]; w++;
+                colptr[j + 1]++;
+            }
+        }
+        start = end;
+        rowptr[i] = w; /* compacted end of row i */
+    }
+    int64_t nnz = w;
+    /* colptr: counts -> 1-based pointers */
+    colptr[0] = 1;
+    for (int64_t j = 0; j < ncol; j++) colptr[j + 1] += colptr[j];
+    /* transpose compacted CSR into CSC */
+    int64_t *next = last; /* reuse */
+    for (int64_t j = 0; j < ncol; j++) next[j] = colptr[j] - 1;
+    start = 0;
+    for (int64_t i = 1; i <= nrow; i++) {
+        int64_t end = rowptr[i];
+        for (int64_t p = start; p < end; p++) {
+            int64_t q = next[ccol[p] - 1]++;
+            rowval[q] = i; nzval[q] = cval[p];
+        }
+        start = end;
+    }
+    free(rowptr); free(ccol); free(cval); free(last);
+    return nnz;
+}

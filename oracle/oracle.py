@@ -1,0 +1,139 @@
+"""ctypes driver of the CPU oracle (oracle/elfel_oracle.c).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, bench.py's cpu_baseline / ``--impl reference`` leg and
+``__graft_entry__.smoke()`` may import this module; the product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import time
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libelfel_oracle.so")
+
+FORM_HEAT, FORM_ELASTICITY, FORM_STOKES_GEN, FORM_STOKES_REDDY, FORM_STOKES_VECLAP_ALT, FORM_STOKES_VECLAP = 1, 2, 3, 4, 5, 6
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "elfel_oracle.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        i64p, f64p = C.POINTER(C.c_int64), C.POINTER(C.c_double)
+        L.efo_quadrature.argtypes = [C.c_int, C.c_int, f64p, f64p]
+        L.efo_quadrature.restype = C.c_int
+        L.efo_bfun.argtypes = [C.c_int, C.c_double, C.c_double, f64p]
+        L.efo_bfungradpar.argtypes = [C.c_int, C.c_double, C.c_double, f64p]
+        L.efo_triplets_per_element.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.efo_triplets_per_element.restype = C.c_int64
+        L.efo_assemble_coo.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                       i64p, C.c_int, f64p, i64p, C.c_int, f64p,
+                                       i64p, i64p, i64p, f64p, i64p, i64p, f64p]
+        L.efo_assemble_coo.restype = C.c_int64
+        L.efo_sparse.argtypes = [C.c_int64, C.c_int64, C.c_int64, i64p, i64p, f64p, i64p, i64p, f64p]
+        L.efo_sparse.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _p(a, ty):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(ty))
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+def quadrature(kind, rule):
+    pc = np.zeros((25, 2))
+    w = np.zeros(25)
+    n = lib().efo_quadrature(kind, rule, _p(pc, C.c_double), _p(w, C.c_double))
+    if n < 0:
+        raise ValueError("quadrature rule not available")
+    return pc[:n].copy(), w[:n].copy()
+
+
+def bfun(kind, r, s):
+    N = np.zeros(kind)
+    lib().efo_bfun(kind, r, s, _p(N, C.c_double))
+    return N
+
+
+def bfungradpar(kind, r, s):
+    g = np.zeros((kind, 2))
+    lib().efo_bfungradpar(kind, r, s, _p(g, C.c_double))
+    return g
+
+
+def assemble_coo(form, quad, vmesh, pmesh, dofs, params, e0=0, e1=None):
+    """Element loop -> COO triplets (row, col, val), in the reference's append order.
+
+    vmesh/pmesh: objects with .kind, .conn (nel,nen) int64 1-based, .xy (nnodes,2);
+    dofs: list of up to three (nnodes, ncomp) int64 dofnums arrays; params: float64 vector."""
+    L = lib()
+    e1 = vmesh.conn.shape[0] if e1 is None else e1
+    pk = pmesh.kind if pmesh is not None else 0
+    tpe = L.efo_triplets_per_element(form, vmesh.kind, pk)
+    nt = tpe * (e1 - e0)
+    row = np.empty(nt, dtype=np.int64)
+    col = np.empty(nt, dtype=np.int64)
+    val = np.empty(nt, dtype=np.float64)
+    vconn = _c(vmesh.conn, np.int64)
+    vxy = _c(vmesh.xy, np.float64)
+    pconn = _c(pmesh.conn, np.int64) if pmesh is not None else None
+    pxy = _c(pmesh.xy, np.float64) if pmesh is not None else None
+    d = [_c(x, np.int64) for x in dofs] + [None] * (3 - len(dofs))
+    prm = _c(np.atleast_1d(params), np.float64)
+    n = L.efo_assemble_coo(form, quad, e0, e1, _p(vconn, C.c_int64), vmesh.kind, _p(vxy, C.c_double),
+                           _p(pconn, C.c_int64), pk, _p(pxy, C.c_double),
+                           _p(d[0], C.c_int64), _p(d[1], C.c_int64), _p(d[2], C.c_int64),
+                           _p(prm, C.c_double), _p(row, C.c_int64), _p(col, C.c_int64), _p(val, C.c_double))
+    if n != nt:
+        raise RuntimeError(f"oracle element loop failed (rc={n})")
+    return row, col, val
+
+
+def sparse(row, col, val, nrow, ncol):
+    """finish!: SparseArrays.sparse(I,J,V,m,n) -> (colptr, rowval, nzval), Int64 1-based."""
+    L = lib()
+    nt = len(row)
+    colptr = np.empty(ncol + 1, dtype=np.int64)
+    rowval = np.empty(max(nt, 1), dtype=np.int64)
+    nzval = np.empty(max(nt, 1), dtype=np.float64)
+    row = _c(row, np.int64); col = _c(col, np.int64); val = _c(val, np.float64)
+    nnz = L.efo_sparse(nrow, ncol, nt, _p(row, C.c_int64), _p(col, C.c_int64), _p(val, C.c_double),
+                       _p(colptr, C.c_int64), _p(rowval, C.c_int64), _p(nzval, C.c_double))
+    if nnz == -1:
+        raise ValueError("ArgumentError: row/column index out of range (dof number 0 or > nrow?)")
+    if nnz < 0:
+        raise MemoryError("oracle sparse(): allocation failed")
+    return colptr, rowval[:nnz].copy(), nzval[:nnz].copy()
+
+
+def assemble(form, quad, vmesh, pmesh, dofs, params, nrow, ncol, timing=None):
+    """start! / element loop / finish! -> CSC, exactly what the reference's assembleK returns."""
+    t0 = time.perf_counter()
+    row, col, val = assemble_coo(form, quad, vmesh, pmesh, dofs, params)
+    t1 = time.perf_counter()
+    out = sparse(row, col, val, nrow, ncol)
+    t2 = time.perf_counter()
+    if timing is not None:
+        timing["integrate_s"] = t1 - t0
+        timing["finish_s"] = t2 - t1
+    return out
