@@ -16,3 +16,10 @@ from .meshes import (Mesh, T3, Q4, T6, T3block, Q4block, T6block, T6block_fast, 
 from .fespaces import (FE, FEH1_T3, FEH1_T6, FEH1_Q4, FEField, FESpace, edofbfnum, edofcompnt,
                        ndofsperel, setebc, numberfreedofs, numberdatadofs, numberdofs, nunknowns,
                        ndofs, highestfreedofnum, highestdatadofnum, gathersysvec, scattersysvec)
+from . import _lib
+from ._lib import build, EfgError, ArgumentError
+from .assemblers import (FEIterator, QPIterator, HeatForm, ElasticityForm, StokesGenForm, StokesReddyForm,
+                         StokesVeclapAltForm, StokesVeclapForm, SparseMatrixCSC, Engine, SysmatAssemblerGPU,
+                         start, assemble, finish)
+from .problems import (Problem, heat_problem, elasticity_problem, stokes_problem, plane_stress_D, load_problem,
+                       oracle_args)

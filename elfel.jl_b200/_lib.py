@@ -1,0 +1,112 @@
+"""ctypes binding of include/elfel_gpu.h (libelfelgpu.so) -- the same C ABI a Julia shim would
+``ccall``.  No torch types cross this boundary: plain pointers and sizes.
+
+``build()`` compiles the CUDA library in-tree for sm_100a with nvcc (cross-compiles without a GPU).
+There is no CPU fallback: ``load()`` raises if the library is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+SO_PATH = os.path.join(_HERE, "libelfelgpu.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "elfel_gpu.h")
+
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
+
+# error codes / constants (mirror of the header)
+OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_INDEX, ERR_STATE, ERR_LIMIT = 0, -1, -2, -3, -4, -5, -6
+FORM_HEAT, FORM_ELASTICITY, FORM_STOKES_GEN, FORM_STOKES_REDDY, FORM_STOKES_VECLAP_ALT, FORM_STOKES_VECLAP = 1, 2, 3, 4, 5, 6
+OPT_PATH, OPT_STRICT_FP, OPT_TILE_ELEMS, OPT_SFC_ORDER = 1, 2, 3, 4
+PATH_AUTO, PATH_TWOPASS, PATH_TILED = 0, 1, 2
+(STAT_SYMBOLIC_MS, STAT_NUMERIC_MS, STAT_KERNEL_LAUNCHES, STAT_NUMERIC_LAUNCHES, STAT_DEVICE_BYTES,
+ STAT_NTILES, STAT_TILE_ELEMS, STAT_NUMERIC_BYTES, STAT_PATH) = range(1, 10)
+
+EXPORTS = ["efg_create", "efg_destroy", "efg_last_error", "efg_set_option", "efg_get_stat", "efg_get_stream",
+           "efg_synchronize", "efg_set_mesh", "efg_set_space", "efg_start", "efg_set_column_range",
+           "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version"]
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+
+
+def needs_build() -> bool:
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    return any(os.path.getmtime(s) > t for s in _sources() + [HEADER])
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo ... -> elfel.jl_b200/libelfelgpu.so"""
+    if not force and not needs_build():
+        return SO_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, os.path.join(CSRC, "elfel_gpu.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return SO_PATH
+
+
+_lib = None
+
+
+def load():
+    """Load libelfelgpu.so and declare the prototypes of include/elfel_gpu.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise RuntimeError(f"{SO_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the assembly path)")
+    L = C.CDLL(SO_PATH)
+    vp, i64, i64p, f64p, ci = C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_int
+    L.efg_version.restype = C.c_char_p
+    L.efg_create.argtypes = [ci, C.POINTER(vp)]
+    L.efg_destroy.argtypes = [vp]
+    L.efg_last_error.argtypes = [vp]
+    L.efg_last_error.restype = C.c_char_p
+    L.efg_set_option.argtypes = [vp, ci, i64]
+    L.efg_get_stat.argtypes = [vp, ci, f64p]
+    L.efg_get_stream.argtypes = [vp, C.POINTER(vp)]
+    L.efg_synchronize.argtypes = [vp]
+    L.efg_set_mesh.argtypes = [vp, ci, ci, i64, i64, vp, vp]
+    L.efg_set_space.argtypes = [vp, ci, ci, ci, i64, vp]
+    L.efg_start.argtypes = [vp, i64, i64]
+    L.efg_set_column_range.argtypes = [vp, i64, i64]
+    L.efg_symbolic.argtypes = [vp, ci, ci, i64p]
+    L.efg_numeric.argtypes = [vp, f64p, ci]
+    L.efg_assemble.argtypes = [vp, ci, ci, f64p, ci, i64p]
+    L.efg_fetch_csc.argtypes = [vp, vp, vp, vp]
+    L.efg_device_csc.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    for name in EXPORTS:
+        if name not in ("efg_version", "efg_last_error"):
+            getattr(L, name).restype = ci
+    _lib = L
+    return L
+
+
+class EfgError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libelfelgpu error {code}: {msg}")
+        self.code = code
+
+
+class ArgumentError(EfgError, ValueError):
+    """EFG_ERR_INDEX: what Julia's sparse() raises for an index < 1 or > m/n."""
+
+
+def check(ctx, rc):
+    if rc != OK:
+        L = load()
+        msg = L.efg_last_error(ctx).decode() if ctx else "no context (no CUDA device?)"
+        raise (ArgumentError if rc == ERR_INDEX else EfgError)(rc, msg)

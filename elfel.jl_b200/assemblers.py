@@ -1,0 +1,282 @@
+"""Host-side mirror of the reference's assembler interface for the accelerated path.
+
+Reference (Julia)                                   here (Python, same names without ``!``)
+--------------------------------------------------  ------------------------------------------------
+FEIterator(fesp)            src/FEIterators.jl:54   FEIterator(fesp)
+QPIterator(fesp, (kind=:default, npts=3))           QPIterator(fesp, kind="default", npts=3)
+                            src/QPIterators.jl:79   QPIterator(fesp, kind="Gauss", order=2)
+SysmatAssemblerSparse(0.0)  src/Assemblers.jl:58    SysmatAssemblerGPU(0.0)
+start!(ass, nrow, ncol)     src/Assemblers.jl:67    start(ass, nrow, ncol)
+for el in elit ... assemble!(ass, ke) end           assemble(ass, HeatForm(kappa), elit, qpit)
+                 (user closure, examples/*)         assemble(ass, ElasticityForm(D), elit, qpit)
+                                                    assemble(ass, StokesGenForm(D), (uel, pel), (uqp, pqp)) ...
+finish!(ass)                src/Assemblers.jl:121   finish(ass) -> SparseMatrixCSC(m, n, colptr, rowval, nzval)
+
+The element loop + COO append + sparse() of the reference collapse into one ``assemble`` call that
+runs on the GPU through the C ABI (include/elfel_gpu.h).  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .fespaces import FESpace
+from .meshes import Q4
+
+
+# ------------------------------------------------------------------------------------------------
+# iterators (thin: they only carry what the engine reads from them)
+# ------------------------------------------------------------------------------------------------
+class FEIterator:
+    """Caches the base incidence relation, geometry and the field of a space (src/FEIterators.jl:54-81)."""
+
+    def __init__(self, fesp: FESpace):
+        self.fesp = fesp
+        self._bir = fesp.mesh.conn        # element -> nodes, (nel, nen) int64 1-based
+        self._geom = fesp.mesh.xy         # (nnodes, 2)
+        self._fld0 = fesp.field
+
+    def __len__(self):
+        return self._bir.shape[0]
+
+
+class QPIterator:
+    """Quadrature settings of a space (src/QPIterators.jl:79-84, src/RefShapes.jl:301-323,333-366)."""
+
+    def __init__(self, fesp: FESpace, kind="default", npts=None, order=None):
+        self.fesp = fesp
+        if fesp.fe.kind == Q4:
+            if kind not in ("default", "Gauss"):
+                raise ValueError(f"Integration rule {kind} not available")
+            self.rule = 1 if order is None else int(order)
+        else:
+            if kind != "default":
+                raise ValueError(f"Integration rule {kind} not available")
+            self.rule = 1 if npts is None else int(npts)
+
+
+# ------------------------------------------------------------------------------------------------
+# weak forms = the integrate! closures of the reference's examples
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class HeatForm:           # examples/heat/poisson/t3.jl:53-58
+    kappa: float
+    form_id = _lib.FORM_HEAT
+
+    def params(self):
+        return np.array([self.kappa], dtype=np.float64)
+
+
+@dataclass
+class ElasticityForm:     # examples/elasticity/stretch/t6.jl:42-58 ; D is the 3x3 material matrix
+    D: np.ndarray
+    form_id = _lib.FORM_ELASTICITY
+
+    def params(self):
+        return np.asarray(self.D, dtype=np.float64).T.ravel().copy()   # column-major like SMatrix{3,3}
+
+
+@dataclass
+class StokesGenForm:      # examples/stokes/colliding_flow/ht_p2_p1_gen.jl:48-79 ; spaces (Uh, Ph)
+    D: np.ndarray
+    form_id = _lib.FORM_STOKES_GEN
+
+    def params(self):
+        return np.asarray(self.D, dtype=np.float64).T.ravel().copy()
+
+
+@dataclass
+class StokesReddyForm:    # examples/stokes/colliding_flow/ht_p2_p1.jl:56-104 ; spaces (ux, uy, p)
+    mu: float
+    form_id = _lib.FORM_STOKES_REDDY
+
+    def params(self):
+        return np.array([self.mu], dtype=np.float64)
+
+
+@dataclass
+class StokesVeclapAltForm:  # examples/stokes/colliding_flow/ht_p2_p1_veclap_alt.jl:61-90 ; spaces (u, p)
+    mu: float
+    form_id = _lib.FORM_STOKES_VECLAP_ALT
+
+    def params(self):
+        return np.array([self.mu], dtype=np.float64)
+
+
+@dataclass
+class StokesVeclapForm:   # examples/stokes/colliding_flow/ht_p2_p1_veclap.jl:56-97 ; spaces (ux, uy, p)
+    mu: float
+    form_id = _lib.FORM_STOKES_VECLAP
+
+    def params(self):
+        return np.array([self.mu], dtype=np.float64)
+
+
+@dataclass
+class SparseMatrixCSC:
+    """Julia's SparseMatrixCSC{Float64,Int64}: 1-based colptr / rowval."""
+    m: int
+    n: int
+    colptr: np.ndarray
+    rowval: np.ndarray
+    nzval: np.ndarray
+
+    def to_scipy(self):
+        import scipy.sparse as sp
+        return sp.csc_matrix((self.nzval, self.rowval - 1, self.colptr - 1), shape=(self.m, self.n))
+
+
+def _ptr(a):
+    """Raw address of a numpy array or a torch tensor (host or device)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()
+
+
+class Engine:
+    """One ``efg_ctx`` (one device, one stream).  Thin, 1:1 with the C ABI."""
+
+    def __init__(self, device: int = 0):
+        self.L = _lib.load()
+        h = C.c_void_p()
+        rc = self.L.efg_create(device, C.byref(h))
+        if rc != _lib.OK:
+            raise _lib.EfgError(rc, "efg_create failed: no usable CUDA device (there is no CPU fallback)")
+        self.h = h
+        self.ncols_local = 0
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.efg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _lib.check(self.h, rc)
+
+    def set_option(self, opt, value):
+        self._ck(self.L.efg_set_option(self.h, opt, int(value)))
+
+    def stat(self, which) -> float:
+        v = C.c_double()
+        self._ck(self.L.efg_get_stat(self.h, which, C.byref(v)))
+        return v.value
+
+    def stream(self) -> int:
+        s = C.c_void_p()
+        self._ck(self.L.efg_get_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def synchronize(self):
+        self._ck(self.L.efg_synchronize(self.h))
+
+    def set_mesh(self, slot, kind, conn, xy):
+        """conn: (nel, nen) int64 1-based, xy: (nnodes, 2) float64 -- numpy (host) or torch (host/device)."""
+        nel, nnodes = int(conn.shape[0]), int(xy.shape[0])
+        self._ck(self.L.efg_set_mesh(self.h, slot, kind, nel, nnodes, _ptr(conn), _ptr(xy)))
+
+    def set_space(self, slot, mesh_slot, dofnums):
+        """dofnums: (nnodes, ncomp) int64 1-based."""
+        nnodes, ncomp = int(dofnums.shape[0]), int(dofnums.shape[1])
+        self._ck(self.L.efg_set_space(self.h, slot, mesh_slot, ncomp, nnodes, _ptr(dofnums)))
+
+    def start(self, nrow, ncol):
+        self._ck(self.L.efg_start(self.h, int(nrow), int(ncol)))
+        self.nrow, self.ncol, self.ncols_local = int(nrow), int(ncol), int(ncol)
+
+    def set_column_range(self, first, last):
+        self._ck(self.L.efg_set_column_range(self.h, int(first), int(last)))
+        self.ncols_local = int(last) - int(first) + 1
+
+    def symbolic(self, form_id, quad) -> int:
+        nnz = C.c_int64()
+        self._ck(self.L.efg_symbolic(self.h, form_id, quad, C.byref(nnz)))
+        self.nnz = nnz.value
+        return nnz.value
+
+    def numeric(self, params):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._ck(self.L.efg_numeric(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), len(p)))
+
+    def assemble(self, form_id, quad, params) -> int:
+        nnz = C.c_int64()
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._ck(self.L.efg_assemble(self.h, form_id, quad, p.ctypes.data_as(C.POINTER(C.c_double)), len(p), C.byref(nnz)))
+        self.nnz = nnz.value
+        return nnz.value
+
+    def fetch_csc(self, colptr=None, rowval=None, nzval=None):
+        """Fill caller-allocated arrays (numpy or torch); allocates numpy arrays when all are None."""
+        if colptr is None and rowval is None and nzval is None:
+            colptr = np.empty(self.ncols_local + 1, dtype=np.int64)
+            rowval = np.empty(self.nnz, dtype=np.int64)
+            nzval = np.empty(self.nnz, dtype=np.float64)
+        self._ck(self.L.efg_fetch_csc(self.h, _ptr(colptr), _ptr(rowval), _ptr(nzval)))
+        return colptr, rowval, nzval
+
+
+class SysmatAssemblerGPU:
+    """Selected in place of SysmatAssemblerSparse; same start / assemble / finish life cycle."""
+
+    def __init__(self, zero: float = 0.0, device: int = 0):
+        if not isinstance(zero, float):
+            raise TypeError("only Float64 matrices are assembled")
+        self.engine = Engine(device)
+        self.nrow = self.ncol = 0
+        self._started = False
+        self._assembled = False
+
+    def set_option(self, opt, value):
+        self.engine.set_option(opt, value)
+        return self
+
+
+def start(ass: SysmatAssemblerGPU, nrow, ncol):
+    ass.engine.start(nrow, ncol)
+    ass.nrow, ass.ncol = int(nrow), int(ncol)
+    ass._started, ass._assembled = True, False
+    return ass
+
+
+def assemble(ass: SysmatAssemblerGPU, form, elits, qpits):
+    """One call replaces the reference's whole element loop for ``form``."""
+    if not ass._started:
+        raise _lib.EfgError(_lib.ERR_STATE, "assemble before start")
+    if isinstance(elits, FEIterator):
+        elits, qpits = (elits,), (qpits,)
+    if len({q.rule for q in qpits}) != 1:
+        raise ValueError("all spaces of a mixed form must use the same quadrature rule")
+    eng = ass.engine
+    meshes = []
+    for it in elits:
+        if not any(it.fesp.mesh is m for m in meshes):
+            meshes.append(it.fesp.mesh)
+    if len(meshes) > 2:
+        raise ValueError("at most two meshes (velocity, pressure)")
+    for slot, m in enumerate(meshes):
+        eng.set_mesh(slot, m.kind, np.ascontiguousarray(m.conn, dtype=np.int64), np.ascontiguousarray(m.xy, dtype=np.float64))
+    for slot, it in enumerate(elits):
+        mslot = [i for i, m in enumerate(meshes) if m is it.fesp.mesh][0]
+        eng.set_space(slot, mslot, np.ascontiguousarray(it._fld0.dofnums, dtype=np.int64))
+    eng.start(ass.nrow, ass.ncol)
+    eng.assemble(form.form_id, qpits[0].rule, form.params())
+    ass._assembled = True
+    return ass
+
+
+def finish(ass: SysmatAssemblerGPU) -> SparseMatrixCSC:
+    if not ass._assembled:
+        raise _lib.EfgError(_lib.ERR_STATE, "finish before assemble")
+    colptr, rowval, nzval = ass.engine.fetch_csc()
+    return SparseMatrixCSC(ass.nrow, ass.ncol, colptr, rowval, nzval)

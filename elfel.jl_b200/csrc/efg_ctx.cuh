@@ -1,0 +1,147 @@
+// efg_ctx.cuh -- the assembler context: device-resident mesh, dof maps, symbolic data, result.
+#pragma once
+#include "efg_common.cuh"
+#include "efg_forms.cuh"
+
+struct MeshDev {
+    int kind = 0;
+    int64_t nel = 0, nnodes = 0;
+    DevBuf<int32_t> conn;   // nen x nel, 0-based
+    DevBuf<double2> xy;     // nnodes
+};
+
+struct SpaceDev {
+    int mesh = -1, ncomp = 0;
+    int64_t nnodes = 0;
+    DevBuf<int32_t> dof;    // ncomp x nnodes, 0-based (-1 = dof number 0 = unnumbered)
+};
+
+// --- two-pass path (element matrices to HBM, then segmented gather) ---------------------------
+struct TwoPass {
+    DevBuf<uint32_t> perm;       // sorted triplet ids (valid ones first)
+    DevBuf<int64_t> seg_start;   // nnz+1 offsets into perm
+    DevBuf<double> Ke;           // NT x nel (entry k of element e at Ke[k*nel + e])
+    int64_t ntrip_valid = 0;
+};
+
+// --- tiled fused path ---------------------------------------------------------------------------
+struct TileDesc {               // one CTA work item
+    int64_t slot0;              // first tile-order slot of this tile
+    int64_t gidx0;              // first gather index of this tile
+    int32_t elem0, nelem;       // range in telem / lconn (tile elements incl. halo, ascending element id)
+    int32_t node0, nnode;       // range in tile_xy
+    int32_t nq;                 // staged columns
+    int32_t nslot;              // owned nonzeros
+    int32_t run0, nrun;         // range in runs
+    int32_t pad_[2];
+};
+struct TileRun {                // consecutive tile slots that are contiguous in nzval
+    int64_t nz0;                // destination in nzval
+    int32_t s0, len;            // tile-local first slot, length
+};
+struct Tiled {
+    int ntiles = 0;
+    int tile_elems = 0;          // TE used
+    int64_t sum_tile_elems = 0;  // incl. halo
+    int max_nq = 0, max_nnode = 0, max_nslot = 0, max_nelem = 0, max_nrun = 0;
+    DevBuf<TileDesc> tiles;
+    DevBuf<TileRun> runs;
+    DevBuf<uint16_t> lconn;      // GK per tile element: tile-local node index
+    DevBuf<uint32_t> emeta;      // per tile element: owned-column mask (low 16) | first staged column (high 16)
+    DevBuf<double2> txy;         // tile-local node coordinates
+    DevBuf<uint8_t> gcnt;        // contributions per tile slot
+    DevBuf<uint16_t> gidx;       // stage index of each contribution, by tile slot, reference order
+    int64_t numeric_bytes = 0;
+};
+
+struct efg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evn0 = nullptr, evn1 = nullptr;
+    std::string err;
+    DevPool pool;
+
+    MeshDev mesh[2];
+    SpaceDev space[3];
+
+    bool started = false;
+    int64_t nrow = 0, ncol = 0;
+    int64_t c0 = 0, c1 = 0;          // 0-based column range [c0, c1)
+    bool have_range = false;
+
+    // options
+    int opt_path = 0;
+    int opt_strict = 0;
+    int opt_tile_elems = 0;
+    int opt_sfc = 1;
+
+    // symbolic state
+    bool have_symbolic = false;
+    int form = 0, quad = 0, nq = 0, vkind = 0;
+    int path = 0;
+    int64_t nnz = 0;
+    DevBuf<int64_t> colptr;      // (c1-c0)+1, 1-based
+    DevBuf<int32_t> rowval;      // nnz, 0-based
+    DevBuf<double> nzval;        // nnz
+    bool have_values = false;
+    TwoPass tp;
+    Tiled tl;
+
+    // stats
+    double symbolic_ms = 0, numeric_ms = 0;
+    int64_t launches = 0, numeric_launches = 0;
+};
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
+    do {                                                                             \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);             \
+        (ctx)->launches++;                                                           \
+        CUDA_CHECK(cudaGetLastError());                                              \
+    } while (0)
+
+// (form, element kind, quadrature rule) -> template instantiation
+template <class Fn> inline bool dispatch_form(int form, int vkind, int nq, Fn &&fn)
+{
+    switch (form) {
+    case EFG_FORM_HEAT:
+        if (vkind == 3 && nq == 1) { fn(HeatForm<3, 1>{}); return true; }
+        if (vkind == 3 && nq == 3) { fn(HeatForm<3, 3>{}); return true; }
+        if (vkind == 6 && nq == 1) { fn(HeatForm<6, 1>{}); return true; }
+        if (vkind == 6 && nq == 3) { fn(HeatForm<6, 3>{}); return true; }
+        if (vkind == 4 && nq == 1) { fn(HeatForm<4, 1>{}); return true; }
+        if (vkind == 4 && nq == 4) { fn(HeatForm<4, 4>{}); return true; }
+        if (vkind == 4 && nq == 9) { fn(HeatForm<4, 9>{}); return true; }
+        return false;
+    case EFG_FORM_ELASTICITY:
+        if (vkind == 3 && nq == 1) { fn(ElasticityForm<3, 1>{}); return true; }
+        if (vkind == 3 && nq == 3) { fn(ElasticityForm<3, 3>{}); return true; }
+        if (vkind == 6 && nq == 3) { fn(ElasticityForm<6, 3>{}); return true; }
+        if (vkind == 4 && nq == 4) { fn(ElasticityForm<4, 4>{}); return true; }
+        return false;
+    case EFG_FORM_STOKES_GEN:
+        if (vkind == 6 && nq == 3) { fn(Stokes2Form<false>{}); return true; }
+        return false;
+    case EFG_FORM_STOKES_VECLAP_ALT:
+        if (vkind == 6 && nq == 3) { fn(Stokes2Form<true>{}); return true; }
+        return false;
+    case EFG_FORM_STOKES_REDDY:
+        if (vkind == 6 && nq == 3) { fn(Stokes3Form<false>{}); return true; }
+        return false;
+    case EFG_FORM_STOKES_VECLAP:
+        if (vkind == 6 && nq == 3) { fn(Stokes3Form<true>{}); return true; }
+        return false;
+    }
+    return false;
+}
+
+// load the coordinates of the geometry carrier's nodes of element e (global mesh arrays)
+template <int GK>
+__device__ __forceinline__ void load_xy(const int32_t *__restrict__ conn, const double2 *__restrict__ xy,
+                                        int64_t e, double (&X)[GK], double (&Y)[GK])
+{
+#pragma unroll
+    for (int a = 0; a < GK; a++) {
+        const double2 p = __ldg(&xy[conn[e * GK + a]]);
+        X[a] = p.x; Y[a] = p.y;
+    }
+}

@@ -1,0 +1,374 @@
+// efg_forms.cuh -- per-element arithmetic of the hot path, FP64, one thread per element.
+//
+// Everything a QPIterator precomputes (src/QPIterators.jl:14-50: N, dN/dxi per quadrature
+// point, weights) lives in __constant__ memory (c_tab); the element matrix is produced
+// column by column in registers.  The expressions follow the reference's operation order
+// (cited per function) so that the STRICT instantiation (no FMA contraction) is bit-identical
+// to the CPU oracle; the default instantiation lets nvcc contract a*b+c into DFMA.
+#pragma once
+#include <cstdint>
+#include <utility>
+
+#define EFG_MAXQ 9
+
+struct QTab {
+    double w[EFG_MAXQ];
+    double N[EFG_MAXQ][6];
+    double gp[EFG_MAXQ][6][2];
+};
+
+// slot 0: T3, 1: Q4, 2: T6 -- tables of the ACTIVE quadrature rule for each element kind
+// (the T3 table at the T6 rule's points is the pressure basis of the Taylor-Hood pair).
+__constant__ QTab c_tab[3];
+__constant__ double c_prm[16];
+
+__host__ __device__ constexpr int kind_slot(int kind) { return kind == 3 ? 0 : (kind == 4 ? 1 : 2); }
+
+// ---- arithmetic with or without contraction ---------------------------------------------------
+template <bool S> __device__ __forceinline__ double fmul(double a, double b) {
+    if constexpr (S) return __dmul_rn(a, b); else return a * b;
+}
+template <bool S> __device__ __forceinline__ double fadd(double a, double b) {
+    if constexpr (S) return __dadd_rn(a, b); else return a + b;
+}
+template <bool S> __device__ __forceinline__ double fsub(double a, double b) {
+    if constexpr (S) return __dsub_rn(a, b); else return a - b;
+}
+template <bool S> __device__ __forceinline__ double fdiv(double a, double b) {
+    if constexpr (S) return __ddiv_rn(a, b); else return a / b;
+}
+
+// ---- geometry: Jacobian, JxW and spatial gradients at every quadrature point -------------------
+// GK = kind of the geometry carrier (whose nodes X,Y are given), BK = kind whose basis gradients
+// are wanted (BK != GK only for the Reddy/veclap Stokes forms: T3 Jacobian applied to T6 gradients,
+// examples/stokes/colliding_flow/ht_p2_p1.jl:72-76).
+template <int BK, int NQ> struct Geo {
+    double gx[NQ][BK], gy[NQ][BK];
+    double JxW[NQ];
+};
+
+template <bool S, int GK, int BK, int NQ>
+__device__ __forceinline__ void geo_compute(const double (&X)[GK], const double (&Y)[GK], Geo<BK, NQ> &G)
+{
+    const QTab &tg = c_tab[kind_slot(GK)];
+    const QTab &tb = c_tab[kind_slot(BK)];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+        // _jac: src/FElements.jl:148-156 -- J = sum_n x_n (outer) dN_n/dxi, node order, first term assigned.
+        // ALWAYS evaluated without FMA contraction: the sum cancels from O(1) to O(h), so any other
+        // rounding sequence differs from the reference by O(eps/h) relative -- more than the 1e-12 /
+        // 1e-14 parity bar at h = 1/4000.  With identical J the rest is well conditioned.
+        double J00 = __dmul_rn(X[0], tg.gp[q][0][0]), J01 = __dmul_rn(X[0], tg.gp[q][0][1]);
+        double J10 = __dmul_rn(Y[0], tg.gp[q][0][0]), J11 = __dmul_rn(Y[0], tg.gp[q][0][1]);
+#pragma unroll
+        for (int n = 1; n < GK; n++) {
+            J00 = __dadd_rn(J00, __dmul_rn(X[n], tg.gp[q][n][0])); J01 = __dadd_rn(J01, __dmul_rn(X[n], tg.gp[q][n][1]));
+            J10 = __dadd_rn(J10, __dmul_rn(Y[n], tg.gp[q][n][0])); J11 = __dadd_rn(J11, __dmul_rn(Y[n], tg.gp[q][n][1]));
+        }
+        // Jacobian(Val{2}): src/FElements.jl:120-129
+        const double d = __dsub_rn(__dmul_rn(J00, J11), __dmul_rn(J10, J01));
+        G.JxW[q] = fmul<S>(d, tg.w[q]);                       // JxW = J * weight(qp)
+        // bfungrad: src/QPIterators.jl:132-140 -- gradpar / Jac == (Jac' \ g)', two true divisions
+#pragma unroll
+        for (int n = 0; n < BK; n++) {
+            G.gx[q][n] = fdiv<S>(fsub<S>(fmul<S>(J11, tb.gp[q][n][0]), fmul<S>(J10, tb.gp[q][n][1])), d);
+            G.gy[q][n] = fdiv<S>(fsub<S>(fmul<S>(J00, tb.gp[q][n][1]), fmul<S>(J01, tb.gp[q][n][0])), d);
+        }
+    }
+}
+
+// where the dof numbers of an element come from (symbolic phase only)
+struct DofSrc {
+    const int32_t *conn0, *conn1;          // 0-based node ids of mesh 0 / mesh 1
+    const int32_t *dof0, *dof1, *dof2;     // 0-based dof numbers (ncomp x nnodes), -1 = dof number 0
+};
+
+// A form provides:
+//   ND      local dofs of the combined element matrix (rows == columns)
+//   NT      COO triplets the reference appends per element
+//   GK,BK   geometry carrier kind / basis kind, GMESH = mesh slot of the geometry carrier
+//   mask(i,j)   is local entry (i,j) appended?       kidx(i,j)  its position in append order
+//   edofs()     combined element dof vector (0-based)
+//   column<S,J>()  column J of the element matrix, all quadrature points summed in order
+
+// B(g,k) and D*B of the elasticity / Stokes-gen kernels (examples/elasticity/stretch/t6.jl:42-58):
+// B(g,1) = (g1, 0, g2), B(g,2) = (0, g2, g1); the literal zero products are dropped (x + 0*D == x).
+template <bool S> __device__ __forceinline__ void DB(const double *D, int comp, double gx, double gy, double (&o)[3])
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+        o[r] = comp == 0 ? fadd<S>(fmul<S>(D[0 * 3 + r], gx), fmul<S>(D[2 * 3 + r], gy))
+                         : fadd<S>(fmul<S>(D[1 * 3 + r], gy), fmul<S>(D[2 * 3 + r], gx));
+}
+template <bool S> __device__ __forceinline__ double dotB(const double (&db)[3], int comp, double gx, double gy)
+{
+    return comp == 0 ? fadd<S>(fmul<S>(db[0], gx), fmul<S>(db[2], gy))
+                     : fadd<S>(fmul<S>(db[1], gy), fmul<S>(db[2], gx));
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1 heat: ke[i,j] += dot(gradN[i], gradN[j]) * (kappa * JxW)   examples/heat/poisson/t3.jl:53-58
+template <int VK, int NQ_> struct HeatForm {
+    static constexpr int ND = VK, NT = VK * VK, GK = VK, BK = VK, NQ = NQ_, GMESH = 0, NSPACES = 1;
+    __host__ __device__ static constexpr bool mask(int, int) { return true; }
+    __host__ __device__ static constexpr int kidx(int i, int j) { return j * ND + i; }
+    __device__ static void edofs(const DofSrc &s, int64_t e, int32_t (&d)[ND]) {
+#pragma unroll
+        for (int a = 0; a < VK; a++) d[a] = s.dof0[s.conn0[e * VK + a]];
+    }
+    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<BK, NQ> &G, double (&out)[ND]) {
+        const double kappa = c_prm[0];
+#pragma unroll
+        for (int i = 0; i < ND; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const double t = fmul<S>(fadd<S>(fmul<S>(G.gx[q][i], G.gx[q][J]), fmul<S>(G.gy[q][i], G.gy[q][J])),
+                                         fmul<S>(kappa, G.JxW[q]));
+                acc = q == 0 ? t : fadd<S>(acc, t);
+            }
+            out[i] = acc;
+        }
+    }
+};
+
+// K2 elasticity: ke[i,j] += dot(D*B_j, B_i) * JxW               examples/elasticity/stretch/t6.jl:52-58
+template <int VK, int NQ_> struct ElasticityForm {
+    static constexpr int ND = 2 * VK, NT = ND * ND, GK = VK, BK = VK, NQ = NQ_, GMESH = 0, NSPACES = 1;
+    __host__ __device__ static constexpr bool mask(int, int) { return true; }
+    __host__ __device__ static constexpr int kidx(int i, int j) { return j * ND + i; }
+    __device__ static void edofs(const DofSrc &s, int64_t e, int32_t (&d)[ND]) {
+#pragma unroll
+        for (int a = 0; a < VK; a++) {
+            const int64_t n = s.conn0[e * VK + a];
+            d[2 * a] = s.dof0[2 * n]; d[2 * a + 1] = s.dof0[2 * n + 1];
+        }
+    }
+    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<BK, NQ> &G, double (&out)[ND]) {
+        double db[NQ][3];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) DB<S>(c_prm, J % 2, G.gx[q][J / 2], G.gy[q][J / 2], db[q]);
+#pragma unroll
+        for (int i = 0; i < ND; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                const double t = fmul<S>(dotB<S>(db[q], i % 2, G.gx[q][i / 2], G.gy[q][i / 2]), G.JxW[q]);
+                acc = q == 0 ? t : fadd<S>(acc, t);
+            }
+            out[i] = acc;
+        }
+    }
+};
+
+// Taylor-Hood T6/T3 Stokes forms.  Combined local dofs of the "2-space" forms (gen, veclap_alt):
+// 0..11 = velocity (node-major, component-minor), 12..14 = pressure.  Of the "3-space" forms
+// (Reddy, veclap): 0..5 = ux, 6..11 = uy, 12..14 = p.  The p-p block is never appended.
+//
+// K3 gen: kuu += dot(B_i, D*B_j)*JxW; kup[i,j] += (-JxW*Np[j]) * gradNu[i][c[i]]; assemble kuu, kup, kup'
+//        examples/stokes/colliding_flow/ht_p2_p1_gen.jl:58-78
+// K5 veclap_alt: kuu[i,j] += (mu*JxW)*dot(g_i,g_j) only where c[i]==c[j] (others stay explicit zeros)
+//        examples/stokes/colliding_flow/ht_p2_p1_veclap_alt.jl:71-87
+template <bool VECLAP_ALT> struct Stokes2Form {
+    static constexpr int VK = 6, PK = 3, NQ = 3;
+    static constexpr int ND = 15, NT = 144 + 36 + 36, GK = 6, BK = 6, GMESH = 0, NSPACES = 2;
+    __host__ __device__ static constexpr bool mask(int i, int j) { return !(i >= 12 && j >= 12); }
+    __host__ __device__ static constexpr int kidx(int i, int j) {
+        return (i < 12 && j < 12) ? j * 12 + i                       // assemble!(ass, kuu)
+             : (i < 12)           ? 144 + (j - 12) * 12 + i          // assemble!(ass, kup)
+                                  : 180 + j * 3 + (i - 12);          // assemble!(ass, transpose(kup))
+    }
+    __device__ static void edofs(const DofSrc &s, int64_t e, int32_t (&d)[ND]) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            const int64_t n = s.conn0[e * 6 + a];
+            d[2 * a] = s.dof0[2 * n]; d[2 * a + 1] = s.dof0[2 * n + 1];
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) d[12 + m] = s.dof1[s.conn1[e * 3 + m]];
+    }
+    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<6, 3> &G, double (&out)[ND]) {
+        const QTab &tp = c_tab[kind_slot(3)];
+        if constexpr (J < 12) {
+            if constexpr (!VECLAP_ALT) {
+                double db[3][3];
+#pragma unroll
+                for (int q = 0; q < 3; q++) DB<S>(c_prm, J % 2, G.gx[q][J / 2], G.gy[q][J / 2], db[q]);
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        const double t = fmul<S>(dotB<S>(db[q], i % 2, G.gx[q][i / 2], G.gy[q][i / 2]), G.JxW[q]);
+                        acc = q == 0 ? t : fadd<S>(acc, t);
+                    }
+                    out[i] = acc;
+                }
+            } else {
+                const double mu = c_prm[0];
+#pragma unroll
+                for (int i = 0; i < 12; i++) {
+                    double acc = 0.0;
+                    if (i % 2 == J % 2) {
+#pragma unroll
+                        for (int q = 0; q < 3; q++) {
+                            const double t = fmul<S>(fmul<S>(mu, G.JxW[q]),
+                                                     fadd<S>(fmul<S>(G.gx[q][i / 2], G.gx[q][J / 2]),
+                                                             fmul<S>(G.gy[q][i / 2], G.gy[q][J / 2])));
+                            acc = q == 0 ? t : fadd<S>(acc, t);
+                        }
+                    }
+                    out[i] = acc;
+                }
+            }
+            // rows 12..14 = transpose(kup): value kup[J, m]
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double gj = (J % 2 == 0) ? G.gx[q][J / 2] : G.gy[q][J / 2];
+                    const double t = fmul<S>(fmul<S>(-G.JxW[q], tp.N[q][m]), gj);
+                    acc = q == 0 ? t : fadd<S>(acc, t);
+                }
+                out[12 + m] = acc;
+            }
+        } else {
+            constexpr int m = J - 12;
+#pragma unroll
+            for (int i = 0; i < 12; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double gi = (i % 2 == 0) ? G.gx[q][i / 2] : G.gy[q][i / 2];
+                    const double t = fmul<S>(fmul<S>(-G.JxW[q], tp.N[q][m]), gi);
+                    acc = q == 0 ? t : fadd<S>(acc, t);
+                }
+                out[i] = acc;
+            }
+            out[12] = out[13] = out[14] = 0.0;
+        }
+    }
+};
+
+// K4 Reddy: examples/stokes/colliding_flow/ht_p2_p1.jl:77-101 (Jacobian of the PRESSURE element);
+// veclap: examples/stokes/colliding_flow/ht_p2_p1_veclap.jl:75-94 (no ux-uy coupling blocks).
+template <bool VECLAP> struct Stokes3Form {
+    static constexpr int VK = 6, PK = 3, NQ = 3;
+    static constexpr int ND = 15, NT = VECLAP ? 144 : 216, GK = 3, BK = 6, GMESH = 1, NSPACES = 3;
+    __host__ __device__ static constexpr bool mask(int i, int j) {
+        if (i >= 12 && j >= 12) return false;
+        if (VECLAP && ((i < 6 && j >= 6 && j < 12) || (j < 6 && i >= 6 && i < 12))) return false;
+        return true;
+    }
+    __host__ __device__ static constexpr int kidx(int i, int j) {
+        if (!VECLAP) {
+            if (i < 6 && j < 6) return j * 6 + i;                              // kuxux
+            if (i < 6 && j < 12) return 36 + (j - 6) * 6 + i;                  // kuxuy
+            if (i < 12 && j < 6) return 72 + j * 6 + (i - 6);                  // transpose(kuxuy)
+            if (i < 12 && j < 12) return 108 + (j - 6) * 6 + (i - 6);          // kuyuy
+            if (i < 6) return 144 + (j - 12) * 6 + i;                          // kuxp
+            if (j < 6) return 162 + j * 3 + (i - 12);                          // transpose(kuxp)
+            if (i < 12) return 180 + (j - 12) * 6 + (i - 6);                   // kuyp
+            return 198 + (j - 6) * 3 + (i - 12);                               // transpose(kuyp)
+        } else {
+            if (i < 6 && j < 6) return j * 6 + i;                              // kuxux
+            if (i >= 6 && i < 12 && j >= 6 && j < 12) return 36 + (j - 6) * 6 + (i - 6); // kuyuy
+            if (i < 6) return 72 + (j - 12) * 6 + i;                           // kuxp
+            if (j < 6) return 90 + j * 3 + (i - 12);                           // transpose(kuxp)
+            if (i < 12) return 108 + (j - 12) * 6 + (i - 6);                   // kuyp
+            return 126 + (j - 6) * 3 + (i - 12);                               // transpose(kuyp)
+        }
+    }
+    __device__ static void edofs(const DofSrc &s, int64_t e, int32_t (&d)[ND]) {
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            const int64_t n = s.conn0[e * 6 + a];
+            d[a] = s.dof0[n]; d[6 + a] = s.dof1[n];
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) d[12 + m] = s.dof2[s.conn1[e * 3 + m]];
+    }
+    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<6, 3> &G, double (&out)[ND]) {
+        const QTab &tp = c_tab[kind_slot(3)];
+        const double mu = c_prm[0];
+#pragma unroll
+        for (int i = 0; i < 15; i++) out[i] = 0.0;
+        if constexpr (J < 6) {          // column of ux dof J
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                double a = 0.0, b = 0.0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double mJ = fmul<S>(mu, G.JxW[q]);
+                    double t;
+                    if constexpr (!VECLAP)   // (mu*JxW) * (2*gx_i*gx_j + gy_i*gy_j)
+                        t = fmul<S>(mJ, fadd<S>(fmul<S>(fmul<S>(2.0, G.gx[q][i]), G.gx[q][J]), fmul<S>(G.gy[q][i], G.gy[q][J])));
+                    else
+                        t = fmul<S>(mJ, fadd<S>(fmul<S>(G.gx[q][i], G.gx[q][J]), fmul<S>(G.gy[q][i], G.gy[q][J])));
+                    a = q == 0 ? t : fadd<S>(a, t);
+                    if constexpr (!VECLAP) { // transpose(kuxuy): value kuxuy[J, i] = (mu*JxW) * (gx_J * gy_i)
+                        const double u = fmul<S>(mJ, fmul<S>(G.gx[q][J], G.gy[q][i]));
+                        b = q == 0 ? u : fadd<S>(b, u);
+                    }
+                }
+                out[i] = a; out[6 + i] = b;
+            }
+#pragma unroll
+            for (int m = 0; m < 3; m++) {  // transpose(kuxp): kuxp[J, m] = (-JxW) * (gx_J * Np_m)
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double t = fmul<S>(-G.JxW[q], fmul<S>(G.gx[q][J], tp.N[q][m]));
+                    acc = q == 0 ? t : fadd<S>(acc, t);
+                }
+                out[12 + m] = acc;
+            }
+        } else if constexpr (J < 12) {  // column of uy dof b
+            constexpr int b_ = J - 6;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                double a = 0.0, c = 0.0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double mJ = fmul<S>(mu, G.JxW[q]);
+                    if constexpr (!VECLAP) { // kuxuy[i, b] = (mu*JxW) * (gx_i * gy_b)
+                        const double u = fmul<S>(mJ, fmul<S>(G.gx[q][i], G.gy[q][b_]));
+                        a = q == 0 ? u : fadd<S>(a, u);
+                    }
+                    double t;
+                    if constexpr (!VECLAP)   // (mu*JxW) * (gx_i*gx_b + 2*gy_i*gy_b)
+                        t = fmul<S>(mJ, fadd<S>(fmul<S>(G.gx[q][i], G.gx[q][b_]), fmul<S>(fmul<S>(2.0, G.gy[q][i]), G.gy[q][b_])));
+                    else
+                        t = fmul<S>(mJ, fadd<S>(fmul<S>(G.gx[q][i], G.gx[q][b_]), fmul<S>(G.gy[q][i], G.gy[q][b_])));
+                    c = q == 0 ? t : fadd<S>(c, t);
+                }
+                out[i] = a; out[6 + i] = c;
+            }
+#pragma unroll
+            for (int m = 0; m < 3; m++) {  // transpose(kuyp): kuyp[b, m] = (-JxW) * (gy_b * Np_m)
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double t = fmul<S>(-G.JxW[q], fmul<S>(G.gy[q][b_], tp.N[q][m]));
+                    acc = q == 0 ? t : fadd<S>(acc, t);
+                }
+                out[12 + m] = acc;
+            }
+        } else {                        // column of p dof m: kuxp[i, m], kuyp[i, m]
+            constexpr int m = J - 12;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                double a = 0.0, c = 0.0;
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const double t = fmul<S>(-G.JxW[q], fmul<S>(G.gx[q][i], tp.N[q][m]));
+                    const double u = fmul<S>(-G.JxW[q], fmul<S>(G.gy[q][i], tp.N[q][m]));
+                    a = q == 0 ? t : fadd<S>(a, t);
+                    c = q == 0 ? u : fadd<S>(c, u);
+                }
+                out[i] = a; out[6 + i] = c;
+            }
+        }
+    }
+};

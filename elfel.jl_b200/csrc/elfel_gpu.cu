@@ -1,0 +1,451 @@
+// elfel_gpu.cu -- libelfelgpu.so: C ABI (include/elfel_gpu.h) over the sm_100a kernels.
+// Single translation unit (the __constant__ tables are shared by all kernels).
+#include "efg_ctx.cuh"
+#include "efg_twopass.cuh"
+#include "efg_tiled.cuh"
+
+#include <cstring>
+#include <cmath>
+
+// ------------------------------------------------------------------------------------------------
+// quadrature + basis tables of the active rule (what QPIterator's ctor precomputes,
+// src/QPIterators.jl:14-50,79-84) -> __constant__ c_tab.  Host arithmetic is plain IEEE double
+// (compiled with -ffp-contract=off) in the reference's expression order.
+// ------------------------------------------------------------------------------------------------
+static int gauss1(int order, double *pc, double *w) // src/RefShapes.jl:91-106 (truncated literals kept)
+{
+    switch (order) {
+    case 1: pc[0] = 0.0; w[0] = 2.0; return 1;
+    case 2: pc[0] = -0.577350269189626; pc[1] = 0.577350269189626; w[0] = 1.0; w[1] = 1.0; return 2;
+    case 3: pc[0] = -0.774596669241483; pc[1] = 0.0; pc[2] = 0.774596669241483;
+            w[0] = 0.5555555555555556; w[1] = 0.8888888888888889; w[2] = 0.5555555555555556; return 3;
+    }
+    return -1;
+}
+
+// returns npts; pc is npts x 2
+static int quadrature_points(int kind, int rule, double (*pc)[2], double *w)
+{
+    if (kind == EFG_T3 || kind == EFG_T6) {
+        if (rule == 1) { // src/RefShapes.jl:114-116
+            pc[0][0] = 1.0 / 3.; pc[0][1] = 1.0 / 3.; w[0] = 1.0 / 2.0; return 1;
+        }
+        if (rule == 3) { // src/RefShapes.jl:117-119
+            pc[0][0] = 2.0 / 3; pc[0][1] = 1.0 / 6; pc[1][0] = 1.0 / 6; pc[1][1] = 2.0 / 3;
+            pc[2][0] = 1.0 / 6; pc[2][1] = 1.0 / 6;
+            w[0] = w[1] = w[2] = (1.0 / 3) / 2; return 3;
+        }
+        return -1;
+    }
+    if (kind == EFG_Q4) { // src/RefShapes.jl:350-362: i outer, j inner
+        double p1[3], w1[3];
+        const int np = gauss1(rule, p1, w1);
+        if (np < 0) return -1;
+        int r = 0;
+        for (int i = 0; i < np; i++)
+            for (int j = 0; j < np; j++) { pc[r][0] = p1[i]; pc[r][1] = p1[j]; w[r] = w1[i] * w1[j]; r++; }
+        return r;
+    }
+    return -1;
+}
+
+static void basis_tables(int kind, double r, double s, double *N, double (*g)[2])
+{
+    if (kind == EFG_T3) { // src/FElements.jl:239-246
+        N[0] = (1 - r - s); N[1] = r; N[2] = s;
+        g[0][0] = -1.; g[0][1] = -1.; g[1][0] = +1.; g[1][1] = 0.; g[2][0] = 0.; g[2][1] = +1.;
+    } else if (kind == EFG_T6) { // src/FElements.jl:264-288
+        const double t = 1. - r - s;
+        N[0] = t * (t + t - 1); N[1] = r * (r + r - 1); N[2] = s * (s + s - 1);
+        N[3] = 4 * r * t; N[4] = 4 * r * s; N[5] = 4 * s * t;
+        g[0][0] = -3 + 4 * r + 4 * s; g[0][1] = -3 + 4 * r + 4 * s;
+        g[1][0] = 4 * r - 1;          g[1][1] = 0.0;
+        g[2][0] = 0.0;                g[2][1] = 4 * s - 1;
+        g[3][0] = 4 - 8 * r - 4 * s;  g[3][1] = -4 * r;
+        g[4][0] = 4 * s;              g[4][1] = 4 * r;
+        g[5][0] = -4 * s;             g[5][1] = 4 - 4 * r - 8 * s;
+    } else { // Q4: src/FElements.jl:306-320
+        N[0] = 0.25 * (1. - r) * (1. - s); N[1] = 0.25 * (1. + r) * (1. - s);
+        N[2] = 0.25 * (1. + r) * (1. + s); N[3] = 0.25 * (1. - r) * (1. + s);
+        g[0][0] = -(1. - s) * 0.25; g[0][1] = -(1. - r) * 0.25;
+        g[1][0] = (1. - s) * 0.25;  g[1][1] = -(1. + r) * 0.25;
+        g[2][0] = (1. + s) * 0.25;  g[2][1] = (1. + r) * 0.25;
+        g[3][0] = -(1. + s) * 0.25; g[3][1] = (1. - r) * 0.25;
+    }
+}
+
+// Upload tables for the rule of element kind `vkind`; triangles share their rule between T3 and T6.
+static int upload_tables(efg_ctx *ctx, int vkind, int rule)
+{
+    QTab h[3];
+    memset(h, 0, sizeof h);
+    double pc[EFG_MAXQ][2], w[EFG_MAXQ];
+    const int npts = quadrature_points(vkind, rule, pc, w);
+    if (npts < 0 || npts > EFG_MAXQ) return -1;
+    const int kinds[3] = {EFG_T3, EFG_Q4, EFG_T6};
+    for (int k = 0; k < 3; k++) {
+        const bool tri = kinds[k] != EFG_Q4, vtri = vkind != EFG_Q4;
+        if (tri != vtri) continue;
+        for (int q = 0; q < npts; q++) {
+            h[k].w[q] = w[q];
+            basis_tables(kinds[k], pc[q][0], pc[q][1], h[k].N[q], h[k].gp[q]);
+        }
+    }
+    CUDA_CHECK(cudaMemcpyToSymbolAsync(c_tab, h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); // h is a stack buffer
+    return npts;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingestion: Int64 1-based host/device arrays -> Int32 0-based device arrays (validated)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_convert_index(const int64_t *__restrict__ in, int64_t n, int64_t lo, int64_t hi,
+                                int32_t *__restrict__ out, int *__restrict__ errflag)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int64_t v = in[i];
+        if (v < lo || v > hi) *errflag = 1;
+        out[i] = (int32_t)(v - 1);
+    }
+}
+
+// copy n Int64 from (host or device) src and convert; lo..hi = accepted 1-based range
+static void ingest_index(efg_ctx *ctx, const int64_t *src, int64_t n, int64_t lo, int64_t hi, int32_t *dst, const char *what)
+{
+    const int64_t CH = (int64_t)32 << 20; // 32 Mi entries = 256 MB staging
+    DevBuf<int64_t> stage;
+    DevBuf<int> errflag;
+    stage.alloc(ctx->pool, (size_t)(n < CH ? (n > 0 ? n : 1) : CH));
+    errflag.alloc(ctx->pool, 1);
+    CUDA_CHECK(cudaMemsetAsync(errflag.p, 0, sizeof(int), ctx->stream));
+    for (int64_t o = 0; o < n; o += CH) {
+        const int64_t m = (n - o < CH) ? n - o : CH;
+        CUDA_CHECK(cudaMemcpyAsync(stage.p, src + o, (size_t)m * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+        LAUNCH(ctx, k_convert_index, grid_for(m, 256), 256, 0, stage.p, m, lo, hi, dst + o, errflag.p);
+    }
+    int herr = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&herr, errflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    if (herr) efg_throw(EFG_ERR_INDEX, "%s: index out of range [%lld, %lld]", what, (long long)lo, (long long)hi);
+}
+
+static void invalidate(efg_ctx *ctx)
+{
+    ctx->have_symbolic = false;
+    ctx->have_values = false;
+    ctx->nnz = 0;
+    ctx->colptr.release(); ctx->rowval.release(); ctx->nzval.release();
+    ctx->tp.perm.release(); ctx->tp.seg_start.release(); ctx->tp.Ke.release();
+    tiled_release(ctx);
+}
+
+// ------------------------------------------------------------------------------------------------
+// output conversion: Int32 0-based -> Int64 1-based
+// ------------------------------------------------------------------------------------------------
+__global__ void k_rowval_out(const int32_t *__restrict__ in, int64_t n, int64_t *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (int64_t)in[i] + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+#define API_BEGIN(ctx)                                                          \
+    if (!(ctx)) return EFG_ERR_INVALID;                                         \
+    try {                                                                       \
+        cudaError_t sd__ = cudaSetDevice((ctx)->device);                        \
+        if (sd__ != cudaSuccess) efg_throw(EFG_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(sd__));
+#define API_END(ctx)                                                            \
+        return EFG_OK;                                                          \
+    } catch (const EfgError &e) {                                               \
+        (ctx)->err = e.msg;                                                     \
+        return e.code;                                                          \
+    } catch (const std::bad_alloc &) {                                          \
+        (ctx)->err = "host allocation failed";                                  \
+        return EFG_ERR_OOM;                                                     \
+    } catch (...) {                                                             \
+        (ctx)->err = "unknown error";                                           \
+        return EFG_ERR_CUDA;                                                    \
+    }
+
+extern "C" {
+
+const char *efg_version(void) { return "elfelgpu 0.1 (sm_100a, FP64, CUDA " __DATE__ ")"; }
+
+int efg_create(int device, efg_ctx **out)
+{
+    if (!out) return EFG_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return EFG_ERR_CUDA; }
+    if (device < 0 || device >= ndev) return EFG_ERR_INVALID;
+    efg_ctx *ctx = new (std::nothrow) efg_ctx();
+    if (!ctx) return EFG_ERR_OOM;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaEventCreate(&ctx->evn0) != cudaSuccess || cudaEventCreate(&ctx->evn1) != cudaSuccess) {
+        cudaGetLastError();
+        delete ctx;
+        return EFG_ERR_CUDA;
+    }
+    *out = ctx;
+    return EFG_OK;
+}
+
+int efg_destroy(efg_ctx *ctx)
+{
+    if (!ctx) return EFG_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    invalidate(ctx);
+    for (auto &m : ctx->mesh) { m.conn.release(); m.xy.release(); }
+    for (auto &s : ctx->space) s.dof.release();
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evn0); cudaEventDestroy(ctx->evn1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return EFG_OK;
+}
+
+const char *efg_last_error(const efg_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int efg_set_option(efg_ctx *ctx, int option, int64_t value)
+{
+    API_BEGIN(ctx)
+    switch (option) {
+    case EFG_OPT_PATH:
+        if (value < 0 || value > 2) efg_throw(EFG_ERR_INVALID, "EFG_OPT_PATH must be 0, 1 or 2");
+        if (ctx->opt_path != (int)value) { ctx->opt_path = (int)value; invalidate(ctx); }
+        break;
+    case EFG_OPT_STRICT_FP: ctx->opt_strict = value ? 1 : 0; ctx->have_values = false; break;
+    case EFG_OPT_TILE_ELEMS:
+        if (value < 0 || value > 4096) efg_throw(EFG_ERR_INVALID, "EFG_OPT_TILE_ELEMS out of range");
+        if (ctx->opt_tile_elems != (int)value) { ctx->opt_tile_elems = (int)value; invalidate(ctx); }
+        break;
+    case EFG_OPT_SFC_ORDER:
+        if (ctx->opt_sfc != (value ? 1 : 0)) { ctx->opt_sfc = value ? 1 : 0; invalidate(ctx); }
+        break;
+    default: efg_throw(EFG_ERR_INVALID, "unknown option %d", option);
+    }
+    API_END(ctx)
+}
+
+int efg_get_stat(efg_ctx *ctx, int which, double *out)
+{
+    API_BEGIN(ctx)
+    if (!out) efg_throw(EFG_ERR_INVALID, "null output");
+    switch (which) {
+    case EFG_STAT_SYMBOLIC_MS: *out = ctx->symbolic_ms; break;
+    case EFG_STAT_NUMERIC_MS:
+        if (ctx->have_values) {
+            float ms = 0;
+            CUDA_CHECK(cudaEventSynchronize(ctx->evn1));
+            CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->evn0, ctx->evn1));
+            ctx->numeric_ms = ms;
+        }
+        *out = ctx->numeric_ms;
+        break;
+    case EFG_STAT_KERNEL_LAUNCHES: *out = (double)ctx->launches; break;
+    case EFG_STAT_NUMERIC_LAUNCHES: *out = (double)ctx->numeric_launches; break;
+    case EFG_STAT_DEVICE_BYTES: *out = (double)ctx->pool.bytes; break;
+    case EFG_STAT_NTILES: *out = (double)ctx->tl.ntiles; break;
+    case EFG_STAT_TILE_ELEMS: *out = (double)ctx->tl.sum_tile_elems; break;
+    case EFG_STAT_NUMERIC_BYTES: *out = (double)ctx->tl.numeric_bytes; break;
+    case EFG_STAT_PATH: *out = (double)ctx->path; break;
+    default: efg_throw(EFG_ERR_INVALID, "unknown stat %d", which);
+    }
+    API_END(ctx)
+}
+
+int efg_get_stream(efg_ctx *ctx, void **stream_out)
+{
+    if (!ctx || !stream_out) return EFG_ERR_INVALID;
+    *stream_out = (void *)ctx->stream;
+    return EFG_OK;
+}
+
+int efg_synchronize(efg_ctx *ctx)
+{
+    API_BEGIN(ctx)
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+int efg_set_mesh(efg_ctx *ctx, int slot, int kind, int64_t nel, int64_t nnodes, const int64_t *conn, const double *xy)
+{
+    API_BEGIN(ctx)
+    if (slot < 0 || slot > 1) efg_throw(EFG_ERR_INVALID, "mesh_slot must be 0 or 1");
+    if (kind != EFG_T3 && kind != EFG_Q4 && kind != EFG_T6) efg_throw(EFG_ERR_INVALID, "unsupported element kind %d", kind);
+    if (nel < 0 || nnodes < 0 || (nel > 0 && (!conn || !xy))) efg_throw(EFG_ERR_INVALID, "bad mesh arguments");
+    if (nnodes >= ((int64_t)1 << 31) || nel >= ((int64_t)1 << 31)) efg_throw(EFG_ERR_LIMIT, "mesh too large for 32-bit device indices");
+    invalidate(ctx);
+    MeshDev &m = ctx->mesh[slot];
+    m.kind = kind; m.nel = nel; m.nnodes = nnodes;
+    m.conn.alloc(ctx->pool, (size_t)(nel * kind));
+    m.xy.alloc(ctx->pool, (size_t)nnodes);
+    if (nnodes > 0) CUDA_CHECK(cudaMemcpyAsync(m.xy.p, xy, (size_t)nnodes * sizeof(double2), cudaMemcpyDefault, ctx->stream));
+    ingest_index(ctx, conn, nel * kind, 1, nnodes, m.conn.p, "efg_set_mesh: node id");
+    API_END(ctx)
+}
+
+int efg_set_space(efg_ctx *ctx, int slot, int mesh_slot, int ncomp, int64_t nnodes, const int64_t *dofnums)
+{
+    API_BEGIN(ctx)
+    if (slot < 0 || slot > 2 || mesh_slot < 0 || mesh_slot > 1) efg_throw(EFG_ERR_INVALID, "bad space/mesh slot");
+    if (ncomp < 1 || ncomp > 2) efg_throw(EFG_ERR_INVALID, "ncomp must be 1 or 2");
+    if (nnodes != ctx->mesh[mesh_slot].nnodes) efg_throw(EFG_ERR_INVALID, "space has %lld terms, its mesh has %lld nodes", (long long)nnodes, (long long)ctx->mesh[mesh_slot].nnodes);
+    if (nnodes > 0 && !dofnums) efg_throw(EFG_ERR_INVALID, "null dofnums");
+    invalidate(ctx);
+    SpaceDev &s = ctx->space[slot];
+    s.mesh = mesh_slot; s.ncomp = ncomp; s.nnodes = nnodes;
+    s.dof.alloc(ctx->pool, (size_t)(nnodes * ncomp));
+    // dof number 0 (= not numbered) is accepted here and rejected by the symbolic phase, like sparse() does
+    ingest_index(ctx, dofnums, nnodes * ncomp, 0, ((int64_t)1 << 31) - 1, s.dof.p, "efg_set_space: dof number");
+    API_END(ctx)
+}
+
+int efg_start(efg_ctx *ctx, int64_t nrow, int64_t ncol)
+{
+    API_BEGIN(ctx)
+    if (nrow < 0 || ncol < 0) efg_throw(EFG_ERR_INVALID, "negative matrix size");
+    if (nrow >= ((int64_t)1 << 31) || ncol >= ((int64_t)1 << 31)) efg_throw(EFG_ERR_LIMIT, "matrix dimension exceeds 32-bit device indices");
+    const bool same = ctx->started && ctx->nrow == nrow && ctx->ncol == ncol && !ctx->have_range;
+    if (!same) invalidate(ctx);
+    ctx->nrow = nrow; ctx->ncol = ncol;
+    ctx->c0 = 0; ctx->c1 = ncol; ctx->have_range = false;
+    ctx->started = true;
+    ctx->have_values = false;
+    API_END(ctx)
+}
+
+int efg_set_column_range(efg_ctx *ctx, int64_t first, int64_t last)
+{
+    API_BEGIN(ctx)
+    if (!ctx->started) efg_throw(EFG_ERR_STATE, "efg_set_column_range before efg_start");
+    if (first < 1 || last > ctx->ncol || last < first - 1) efg_throw(EFG_ERR_INVALID, "bad column range");
+    if (ctx->c0 != first - 1 || ctx->c1 != last) invalidate(ctx);
+    ctx->c0 = first - 1; ctx->c1 = last; ctx->have_range = true;
+    API_END(ctx)
+}
+
+static void check_form_inputs(efg_ctx *ctx, int form)
+{
+    const MeshDev &m0 = ctx->mesh[0];
+    if (m0.kind == 0) efg_throw(EFG_ERR_STATE, "mesh 0 not set");
+    auto need_space = [&](int s, int mesh, int ncomp) {
+        const SpaceDev &sp = ctx->space[s];
+        if (sp.mesh != mesh || sp.ncomp != ncomp)
+            efg_throw(EFG_ERR_INVALID, "form %d needs space %d on mesh %d with %d component(s)", form, s, mesh, ncomp);
+    };
+    auto need_pmesh = [&]() {
+        const MeshDev &m1 = ctx->mesh[1];
+        if (m0.kind != EFG_T6 || m1.kind != EFG_T3 || m1.nel != m0.nel)
+            efg_throw(EFG_ERR_INVALID, "Stokes forms need a T6 velocity mesh (slot 0) and a T3 pressure mesh (slot 1) with equal element counts");
+    };
+    switch (form) {
+    case EFG_FORM_HEAT: need_space(0, 0, 1); break;
+    case EFG_FORM_ELASTICITY: need_space(0, 0, 2); break;
+    case EFG_FORM_STOKES_GEN:
+    case EFG_FORM_STOKES_VECLAP_ALT: need_pmesh(); need_space(0, 0, 2); need_space(1, 1, 1); break;
+    case EFG_FORM_STOKES_REDDY:
+    case EFG_FORM_STOKES_VECLAP: need_pmesh(); need_space(0, 0, 1); need_space(1, 0, 1); need_space(2, 1, 1); break;
+    default: efg_throw(EFG_ERR_INVALID, "unknown form %d", form);
+    }
+}
+
+int efg_symbolic(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
+{
+    API_BEGIN(ctx)
+    if (!ctx->started) efg_throw(EFG_ERR_STATE, "efg_symbolic before efg_start");
+    check_form_inputs(ctx, form);
+    if (!(ctx->have_symbolic && ctx->form == form && ctx->quad == quad)) {
+        invalidate(ctx);
+        const int vkind = ctx->mesh[0].kind;
+        const int npts = upload_tables(ctx, vkind, quad);
+        if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, vkind);
+        CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+        const int path = ctx->opt_path == 2 ? 2 : 1; // TODO auto -> tiled
+        const bool ok = dispatch_form(form, vkind, npts, [&](auto F) {
+            using Form = decltype(F);
+            if (path == 1) twopass_symbolic<Form>(ctx); else tiled_symbolic<Form>(ctx);
+        });
+        if (!ok) efg_throw(EFG_ERR_INVALID, "form %d is not available for element kind %d with rule %d", form, vkind, quad);
+        CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->symbolic_ms = ms;
+        ctx->form = form; ctx->quad = quad; ctx->nq = npts; ctx->vkind = vkind; ctx->path = path;
+        ctx->have_symbolic = true;
+    }
+    if (nnz_out) *nnz_out = ctx->nnz;
+    API_END(ctx)
+}
+
+int efg_numeric(efg_ctx *ctx, const double *params, int nparams)
+{
+    API_BEGIN(ctx)
+    if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_numeric before efg_symbolic");
+    const int need = (ctx->form == EFG_FORM_ELASTICITY || ctx->form == EFG_FORM_STOKES_GEN) ? 9 : 1;
+    if (!params || nparams != need) efg_throw(EFG_ERR_INVALID, "form %d takes %d parameter(s)", ctx->form, need);
+    double h[16] = {0};
+    for (int i = 0; i < need; i++) h[i] = params[i];
+    CUDA_CHECK(cudaMemcpyToSymbolAsync(c_prm, h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+    // the tables may have been overwritten by another ctx of this process: re-upload (cheap)
+    upload_tables(ctx, ctx->vkind, ctx->quad);
+    ctx->numeric_launches = 0;
+    CUDA_CHECK(cudaEventRecord(ctx->evn0, ctx->stream));
+    dispatch_form(ctx->form, ctx->vkind, ctx->nq, [&](auto F) {
+        using Form = decltype(F);
+        if (ctx->path == 1) twopass_numeric<Form>(ctx); else tiled_numeric<Form>(ctx);
+    });
+    CUDA_CHECK(cudaEventRecord(ctx->evn1, ctx->stream));
+    ctx->have_values = true;
+    API_END(ctx)
+}
+
+int efg_assemble(efg_ctx *ctx, int form, int quad, const double *params, int nparams, int64_t *nnz_out)
+{
+    int rc = efg_symbolic(ctx, form, quad, nnz_out);
+    if (rc != EFG_OK) return rc;
+    return efg_numeric(ctx, params, nparams);
+}
+
+int efg_fetch_csc(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval)
+{
+    API_BEGIN(ctx)
+    if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_fetch_csc before efg_symbolic");
+    if (nzval && !ctx->have_values) efg_throw(EFG_ERR_STATE, "efg_fetch_csc(nzval) before efg_numeric");
+    const int64_t ncl = ctx->c1 - ctx->c0;
+    if (colptr) CUDA_CHECK(cudaMemcpyAsync(colptr, ctx->colptr.p, (size_t)(ncl + 1) * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+    if (nzval && ctx->nnz > 0) CUDA_CHECK(cudaMemcpyAsync(nzval, ctx->nzval.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    if (rowval && ctx->nnz > 0) {
+        const int64_t CH = (int64_t)32 << 20;
+        DevBuf<int64_t> stage[2];
+        const int64_t cap = ctx->nnz < CH ? ctx->nnz : CH;
+        stage[0].alloc(ctx->pool, (size_t)cap); stage[1].alloc(ctx->pool, (size_t)cap);
+        int b = 0;
+        for (int64_t o = 0; o < ctx->nnz; o += CH, b ^= 1) {
+            const int64_t m = ctx->nnz - o < CH ? ctx->nnz - o : CH;
+            LAUNCH(ctx, k_rowval_out, grid_for(m, 256), 256, 0, ctx->rowval.p + o, m, stage[b].p);
+            CUDA_CHECK(cudaMemcpyAsync(rowval + o, stage[b].p, (size_t)m * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+int efg_device_csc(efg_ctx *ctx, const int64_t **colptr, const int32_t **rowval, const double **nzval)
+{
+    API_BEGIN(ctx)
+    if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_device_csc before efg_symbolic");
+    if (colptr) *colptr = ctx->colptr.p;
+    if (rowval) *rowval = ctx->rowval.p;
+    if (nzval) *nzval = ctx->nzval.p;
+    API_END(ctx)
+}
+
+} // extern "C"

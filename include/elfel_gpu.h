@@ -1,0 +1,137 @@
+/*
+ * elfel_gpu.h -- C ABI of libelfelgpu.so, the B200 (sm_100a) drop-in for Elfel.jl's assembly
+ * hot path.  This is exactly what a Julia `SysmatAssemblerGPU <: AbstractSysmatAssembler`
+ * binds with `ccall` (see INTEGRATION.md for the .jl shim); the same entry points are driven
+ * from Python ctypes in tests/ and bench.py because no Julia runtime exists in this image.
+ *
+ * Reference interface each entry point replaces (paths relative to the Elfel.jl tree):
+ *   efg_create / efg_destroy  SysmatAssemblerSparse(0.0) constructor     src/Assemblers.jl:58-60
+ *   efg_set_mesh              FEIterator ctor caching _bir and _geom     src/FEIterators.jl:54-56
+ *   efg_set_space             FEIterator's _fld0.dofnums (FEField)       src/FEIterators.jl:70, src/FEFields.jl:15
+ *   efg_start                 start!(ass, nrow, ncol)                    src/Assemblers.jl:67-78
+ *   efg_assemble              the user's integrate! loop: `for el in elit; init!(ke,...);
+ *                             for qp in qpit ... end; assemble!(ass, ke) end`
+ *                                                                        examples/heat/poisson/t3.jl:41-64,
+ *                                                                        examples/elasticity/stretch/t6.jl:40-63,
+ *                                                                        examples/stokes/colliding_flow/ht_p2_p1_gen.jl:46-90,
+ *                                                                        ht_p2_p1.jl:55-113, ht_p2_p1_veclap.jl:55-106,
+ *                                                                        ht_p2_p1_veclap_alt.jl:60-98
+ *                             + assemble!(ass, lma) / transpose(lma)     src/Assemblers.jl:97-114
+ *   efg_fetch_csc             finish!(ass) -> sparse(I,J,V,m,n)          src/Assemblers.jl:121-123
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  All index arrays are Int64 and 1-BASED, in the memory
+ *     layout Julia holds them: conn is nen x nel (node ids of element e at conn[e*nen + k]),
+ *     xy is 2 x nnodes, dofnums is ncomp x nnodes (Vector{SVector{ncomp,Int64}}).
+ *   - Input pointers may be host (pageable or pinned) or device pointers (unified addressing);
+ *     they are borrowed for the duration of the call only.
+ *   - Output arrays of efg_fetch_csc are allocated by the caller after nnz is known
+ *     (two-call pattern) so Julia wraps them in SparseMatrixCSC without a copy.
+ *   - Every function returns 0 on success or a negative EFG_ERR_* code; no exception crosses
+ *     the boundary.  efg_last_error() gives the message.  A dof number < 1 or > nrow/ncol gives
+ *     EFG_ERR_INDEX, mirroring sparse()'s ArgumentError (e.g. a space that was never
+ *     data-numbered holds dof number 0, src/FEFields.jl:148).
+ *   - One ctx = one device + one CUDA stream; not re-entrant.  Different ctx may be used from
+ *     different host threads.  Multi-GPU = one ctx (one process) per GPU, each assembling a
+ *     contiguous block of matrix columns (efg_set_column_range); no communication is needed.
+ *   - There is no CPU fallback: without a CUDA device efg_create fails with EFG_ERR_CUDA.
+ */
+#ifndef ELFEL_GPU_H
+#define ELFEL_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct efg_ctx efg_ctx;
+
+/* error codes */
+#define EFG_OK            0
+#define EFG_ERR_INVALID  -1  /* bad argument / unsupported element-form-rule combination */
+#define EFG_ERR_CUDA     -2  /* CUDA runtime error (incl. no device) */
+#define EFG_ERR_OOM      -3  /* device or host allocation failed */
+#define EFG_ERR_INDEX    -4  /* node / dof index out of range (sparse()'s ArgumentError) */
+#define EFG_ERR_STATE    -5  /* call order violated (e.g. assemble before start) */
+#define EFG_ERR_LIMIT    -6  /* an internal capacity was exceeded (message says which) */
+
+/* element kinds (= nodes per element): FEH1_T3, FEH1_Q4, FEH1_T6 (src/FElements.jl:225-320) */
+#define EFG_T3 3
+#define EFG_Q4 4
+#define EFG_T6 6
+
+/* weak forms (the integrate! closures of the reference's examples/tests) */
+#define EFG_FORM_HEAT               1 /* space 0: scalar.        params = [kappa]                  */
+#define EFG_FORM_ELASTICITY         2 /* space 0: 2 components.  params = D 3x3 column-major (9)   */
+#define EFG_FORM_STOKES_GEN         3 /* space 0: u (T6,2), 1: p (T3).  params = D (9)             */
+#define EFG_FORM_STOKES_REDDY       4 /* space 0: ux, 1: uy (T6), 2: p (T3).  params = [mu]        */
+#define EFG_FORM_STOKES_VECLAP_ALT  5 /* space 0: u (T6,2), 1: p (T3).  params = [mu]              */
+#define EFG_FORM_STOKES_VECLAP      6 /* space 0: ux, 1: uy (T6), 2: p (T3).  params = [mu]        */
+
+/* options for efg_set_option */
+#define EFG_OPT_PATH        1 /* 0 = auto (tiled fused kernel), 1 = two-pass (element matrices to HBM,
+                                 then segmented gather), 2 = tiled fused kernel */
+#define EFG_OPT_STRICT_FP   2 /* 1 = no FMA contraction: operation order and rounding of the
+                                 reference's expressions (bit-identical to the CPU oracle) */
+#define EFG_OPT_TILE_ELEMS  3 /* elements per tile of the fused kernel (0 = automatic) */
+#define EFG_OPT_SFC_ORDER   4 /* 1 (default) = tiles follow a space-filling-curve order of the
+                                 elements, 0 = tiles follow the given element order */
+
+/* statistics for efg_get_stat (milliseconds are device times from CUDA events on the ctx stream) */
+#define EFG_STAT_SYMBOLIC_MS      1
+#define EFG_STAT_NUMERIC_MS       2
+#define EFG_STAT_KERNEL_LAUNCHES  3 /* kernels launched by the library so far (all phases) */
+#define EFG_STAT_NUMERIC_LAUNCHES 4 /* kernels launched by the last efg_numeric call */
+#define EFG_STAT_DEVICE_BYTES     5 /* device memory currently held by the ctx */
+#define EFG_STAT_NTILES           6
+#define EFG_STAT_TILE_ELEMS       7 /* sum over tiles of elements processed (incl. halo) */
+#define EFG_STAT_NUMERIC_BYTES    8 /* bytes the numeric kernel is designed to move per call */
+#define EFG_STAT_PATH             9 /* path used by the last symbolic phase (1 or 2) */
+
+int efg_create(int device, efg_ctx **out);
+int efg_destroy(efg_ctx *ctx);
+const char *efg_last_error(const efg_ctx *ctx);
+int efg_set_option(efg_ctx *ctx, int option, int64_t value);
+int efg_get_stat(efg_ctx *ctx, int which, double *out);
+/* the CUDA stream (cudaStream_t) all work of this ctx is issued on */
+int efg_get_stream(efg_ctx *ctx, void **stream_out);
+int efg_synchronize(efg_ctx *ctx);
+
+/* mesh_slot 0: the mesh of space 0 (Stokes: velocity mesh); mesh_slot 1: Stokes pressure mesh. */
+int efg_set_mesh(efg_ctx *ctx, int mesh_slot, int elemkind, int64_t nel, int64_t nnodes,
+                 const int64_t *conn, const double *xy);
+/* space_slot 0..2, living on mesh_slot; dofnums is ncomp x nnodes. */
+int efg_set_space(efg_ctx *ctx, int space_slot, int mesh_slot, int ncomp, int64_t nnodes,
+                  const int64_t *dofnums);
+
+/* start!(ass, nrow, ncol): resets the assembler; mesh/space data are kept. */
+int efg_start(efg_ctx *ctx, int64_t nrow, int64_t ncol);
+/* Owner-computes sharding: assemble only columns col_first..col_last (1-based, inclusive).
+ * Triplets of other columns are dropped; colptr then has (col_last-col_first+2) entries, rebased
+ * to start at 1.  Concatenating the blocks of consecutive ranges gives the global matrix. */
+int efg_set_column_range(efg_ctx *ctx, int64_t col_first, int64_t col_last);
+
+/* Symbolic phase: CSC pattern + scatter maps on the device.  quad_rule: triangles npts (1|3),
+ * squares Gauss order (1..3).  Cached until mesh/space/start/range/options change. */
+int efg_symbolic(efg_ctx *ctx, int form_id, int quad_rule, int64_t *nnz_out);
+/* Numeric phase: element quadrature loop fused with the deterministic scatter -> nzval (device). */
+int efg_numeric(efg_ctx *ctx, const double *params, int nparams);
+/* symbolic (if not cached) + numeric. */
+int efg_assemble(efg_ctx *ctx, int form_id, int quad_rule, const double *params, int nparams,
+                 int64_t *nnz_out);
+
+/* finish!: copy out the SparseMatrixCSC fields (Int64 1-based colptr/rowval, Float64 nzval).
+ * Any pointer may be NULL to skip that array.  Destination may be host or device memory. */
+int efg_fetch_csc(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval);
+/* Device-resident result for a consumer that stays on the GPU (colptr: Int64 1-based,
+ * rowval: Int32 0-based, nzval: Float64); valid until the next start/symbolic/destroy. */
+int efg_device_csc(efg_ctx *ctx, const int64_t **colptr, const int32_t **rowval, const double **nzval);
+
+/* library / build information, e.g. "elfelgpu 0.1 sm_100a" */
+const char *efg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELFEL_GPU_H */

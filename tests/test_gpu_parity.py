@@ -1,0 +1,152 @@
+"""GPU parity: libelfelgpu.so (through the C ABI) vs the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): colptr/rowval bit-exact; nzval within 1e-12 relative / 1e-14 absolute.
+With EFG_OPT_STRICT_FP the GPU result must additionally be numerically IDENTICAL to the oracle
+(== on every value; only the sign of a zero may differ)."""
+import numpy as np
+import pytest
+
+import elfel_jl_b200 as efg
+from elfel_jl_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL = 1e-12, 1e-14     # tolerance stated by BASELINE.json north_star
+
+
+def _cases():
+    c = []
+    for perturb in (False, True):
+        c += [("heat_t3", lambda p=perturb: efg.heat_problem(efg.T3, 37, p)),
+              ("heat_t3_3pt", lambda p=perturb: efg.heat_problem(efg.T3, 20, p, quad=3)),
+              ("heat_t6", lambda p=perturb: efg.heat_problem(efg.T6, 33, p)),
+              ("heat_q4", lambda p=perturb: efg.heat_problem(efg.Q4, 41, p)),
+              ("heat_q4_o3", lambda p=perturb: efg.heat_problem(efg.Q4, 17, p, quad=3)),
+              ("elast_t6", lambda p=perturb: efg.elasticity_problem(29, efg.T6, p)),
+              ("elast_t3", lambda p=perturb: efg.elasticity_problem(31, efg.T3, p)),
+              ("elast_q4", lambda p=perturb: efg.elasticity_problem(23, efg.Q4, p)),
+              ("stokes_gen", lambda p=perturb: efg.stokes_problem(21, "gen", p)),
+              ("stokes_reddy", lambda p=perturb: efg.stokes_problem(19, "reddy", p)),
+              ("stokes_veclap_alt", lambda p=perturb: efg.stokes_problem(18, "veclap_alt", p)),
+              ("stokes_veclap", lambda p=perturb: efg.stokes_problem(17, "veclap", p))]
+    return c
+
+
+CASES = _cases()
+IDS = [f"{n}{'_jit' if i >= len(CASES) // 2 else ''}" for i, (n, _) in enumerate(CASES)]
+
+
+def _gpu(prob, path, strict):
+    eng = efg.Engine(0)
+    eng.set_option(_lib.OPT_PATH, path)
+    eng.set_option(_lib.OPT_STRICT_FP, strict)
+    efg.load_problem(eng, prob)
+    eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+    out = eng.fetch_csc()
+    assert int(eng.stat(_lib.STAT_PATH)) == path
+    eng.close()
+    return out
+
+
+@pytest.mark.parametrize("path", [_lib.PATH_TWOPASS, _lib.PATH_TILED], ids=["twopass", "tiled"])
+@pytest.mark.parametrize("case", CASES, ids=IDS)
+def test_parity_vs_oracle(oracle, case, path):
+    prob = case[1]()
+    ocp, orv, onz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    for strict in (1, 0):
+        cp, rv, nz = _gpu(prob, path, strict)
+        assert np.array_equal(cp, ocp), "colptr not bit-exact"
+        assert np.array_equal(rv, orv), "rowval not bit-exact"
+        if strict:
+            assert np.array_equal(nz, onz), f"strict mode differs from the oracle: max |d| = {np.abs(nz - onz).max()}"
+        else:
+            assert np.all(np.abs(nz - onz) <= ATOL + RTOL * np.abs(onz)), f"max |d| = {np.abs(nz - onz).max()}"
+
+
+@pytest.mark.parametrize("path", [_lib.PATH_TWOPASS, _lib.PATH_TILED], ids=["twopass", "tiled"])
+def test_reference_api_heat_t3_n100(oracle, path):
+    """BASELINE config 1 through the mirror of the reference's assembler API."""
+    prob = efg.heat_problem(efg.T3, 100)
+    fesp = prob.spaces[0]
+    elit = efg.FEIterator(fesp)
+    qpit = efg.QPIterator(fesp, kind="default")
+    ass = efg.SysmatAssemblerGPU(0.0).set_option(_lib.OPT_PATH, path)
+    efg.start(ass, efg.ndofs(fesp), efg.ndofs(fesp))
+    efg.assemble(ass, efg.HeatForm(1.0), elit, qpit)
+    K = efg.finish(ass)
+    assert K.colptr.dtype == np.int64 and K.rowval.dtype == np.int64 and K.nzval.dtype == np.float64
+    assert len(K.nzval) == 7 * 100 ** 2 + 6 * 100 + 1 == 70601
+    ocp, orv, onz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    assert np.array_equal(K.colptr, ocp) and np.array_equal(K.rowval, orv)
+    assert np.all(np.abs(K.nzval - onz) <= ATOL + RTOL * np.abs(onz))
+
+
+@pytest.mark.parametrize("path", [_lib.PATH_TWOPASS, _lib.PATH_TILED], ids=["twopass", "tiled"])
+def test_column_range_blocks_concatenate(oracle, path):
+    """Owner-computes column blocks (multi-GPU sharding): concatenation == the global matrix."""
+    prob = efg.heat_problem(efg.T6, 24, True)
+    ocp, orv, onz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    n = prob.ndofs
+    cuts = [0, n // 3, n // 3 + 1, (2 * n) // 3, n]
+    cps, rvs, nzs = [], [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        eng = efg.Engine(0)
+        eng.set_option(_lib.OPT_PATH, path)
+        efg.load_problem(eng, prob, column_range=(a + 1, b))
+        eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+        cp, rv, nz = eng.fetch_csc()
+        eng.close()
+        assert len(cp) == b - a + 1 and cp[0] == 1
+        cps.append(cp); rvs.append(rv); nzs.append(nz)
+    off, full = 0, [np.array([1], dtype=np.int64)]
+    for cp in cps:
+        full.append(cp[1:] + off)
+        off += cp[-1] - 1
+    assert np.array_equal(np.concatenate(full), ocp)
+    assert np.array_equal(np.concatenate(rvs), orv)
+    nz = np.concatenate(nzs)
+    assert np.all(np.abs(nz - onz) <= ATOL + RTOL * np.abs(onz))
+
+
+def test_unnumbered_dofs_raise_argument_error():
+    """A space that was never data-numbered holds dof number 0 -> sparse() ArgumentError (src/FEFields.jl:148)."""
+    prob = efg.heat_problem(efg.T3, 8)
+    efg.numberfreedofs(prob.spaces[0])          # zeroes the data dofs again, no numberdatadofs!
+    eng = efg.Engine(0)
+    eng.set_option(_lib.OPT_PATH, _lib.PATH_TWOPASS)
+    efg.load_problem(eng, prob)
+    with pytest.raises(efg.ArgumentError):
+        eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+    eng.close()
+
+
+def test_call_order_and_bad_arguments():
+    eng = efg.Engine(0)
+    with pytest.raises(efg.EfgError):
+        eng.symbolic(_lib.FORM_HEAT, 1)          # before start
+    prob = efg.heat_problem(efg.T3, 4)
+    efg.load_problem(eng, prob)
+    with pytest.raises(efg.EfgError):
+        eng.assemble(_lib.FORM_HEAT, 7, [1.0])   # no such triangle rule
+    with pytest.raises(efg.EfgError):
+        eng.assemble(_lib.FORM_ELASTICITY, 1, [1.0] * 9)   # space has 1 component
+    bad = prob.meshes[0].conn.copy(); bad[0, 0] = 10 ** 6
+    with pytest.raises(efg.ArgumentError):
+        eng.set_mesh(0, efg.T3, bad, prob.meshes[0].xy)
+    eng.close()
+
+
+def test_numeric_phase_is_deterministic_and_reusable():
+    prob = efg.elasticity_problem(40, efg.T6, True)
+    eng = efg.Engine(0)
+    efg.load_problem(eng, prob)
+    eng.symbolic(prob.form.form_id, prob.quad)
+    eng.numeric(prob.form.params())
+    _, _, a = eng.fetch_csc()
+    eng.numeric(prob.form.params())
+    _, _, b = eng.fetch_csc()
+    assert a.tobytes() == b.tobytes()
+    eng.numeric(2.0 * prob.form.params())        # linearity in D
+    _, _, c = eng.fetch_csc()
+    assert np.allclose(c, 2.0 * a, rtol=1e-14, atol=0)
+    eng.close()
