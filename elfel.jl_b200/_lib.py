@@ -17,7 +17,8 @@ SO_PATH = os.path.join(_HERE, "libelfelgpu.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "elfel_gpu.h")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared"]
+              "-Xcompiler", "-fPIC,-ffp-contract=off,-Wno-deprecated-declarations",
+              "-Wno-deprecated-declarations", "-shared"]
 
 # error codes / constants (mirror of the header)
 OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_INDEX, ERR_STATE, ERR_LIMIT = 0, -1, -2, -3, -4, -5, -6

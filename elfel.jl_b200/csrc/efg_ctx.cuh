@@ -24,33 +24,16 @@ struct TwoPass {
     int64_t ntrip_valid = 0;
 };
 
-// --- tiled fused path ---------------------------------------------------------------------------
-struct TileDesc {               // one CTA work item
-    int64_t slot0;              // first tile-order slot of this tile
-    int64_t gidx0;              // first gather index of this tile
-    int32_t elem0, nelem;       // range in telem / lconn (tile elements incl. halo, ascending element id)
-    int32_t node0, nnode;       // range in tile_xy
-    int32_t nq;                 // staged columns
-    int32_t nslot;              // owned nonzeros
-    int32_t run0, nrun;         // range in runs
-    int32_t pad_[2];
-};
+// --- tiled fused path (data lives in efg_tiled.cuh's TiledData behind tl_opaque) -------------------
 struct TileRun {                // consecutive tile slots that are contiguous in nzval
     int64_t nz0;                // destination in nzval
     int32_t s0, len;            // tile-local first slot, length
 };
 struct Tiled {
     int ntiles = 0;
-    int tile_elems = 0;          // TE used
-    int64_t sum_tile_elems = 0;  // incl. halo
-    int max_nq = 0, max_nnode = 0, max_nslot = 0, max_nelem = 0, max_nrun = 0;
-    DevBuf<TileDesc> tiles;
-    DevBuf<TileRun> runs;
-    DevBuf<uint16_t> lconn;      // GK per tile element: tile-local node index
-    DevBuf<uint32_t> emeta;      // per tile element: owned-column mask (low 16) | first staged column (high 16)
-    DevBuf<double2> txy;         // tile-local node coordinates
-    DevBuf<uint8_t> gcnt;        // contributions per tile slot
-    DevBuf<uint16_t> gidx;       // stage index of each contribution, by tile slot, reference order
+    int tile_elems = 0;          // elements per tile
+    int64_t sum_tile_elems = 0;  // tile elements incl. halo, summed over tiles
+    int max_nq = 0, max_nslot = 0, max_nelem = 0, max_nrun = 0;
     int64_t numeric_bytes = 0;
 };
 
@@ -86,6 +69,7 @@ struct efg_ctx {
     bool have_values = false;
     TwoPass tp;
     Tiled tl;
+    void *tl_opaque = nullptr;
 
     // stats
     double symbolic_ms = 0, numeric_ms = 0;

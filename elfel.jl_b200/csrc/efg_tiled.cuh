@@ -1,6 +1,784 @@
-// efg_tiled.cuh -- tiled fused path (placeholder while the two-pass path is brought up)
+// efg_tiled.cuh -- the fused path: owner-computes tiles, element matrices never leave the SM.
+//
+// Data layout in HBM (built once by the symbolic phase, all on the GPU):
+//   tiles[T]   TileDesc: one CTA work item = a compact group of elements (contiguous in a space-
+//              filling-curve order of the mesh) + the halo elements that touch the matrix columns
+//              the tile OWNS (owner of a column = lowest tile among the elements containing its dof).
+//   tconn      geometry connectivity of every tile element (incl. halo), tile order, int32
+//   tmask      which local columns of that element the tile owns, uint16
+//   gcnt/gidx  for every owned nonzero ("slot"), in (column,row) order: number of contributions
+//              (uint8) and where each one sits in the CTA's shared-memory stage (uint16), listed in
+//              the reference's append order (ascending element, column-major inside an element)
+//   runs       maximal groups of owned columns that are contiguous in nzval
+// Numeric kernel, per tile: (1) one thread per tile element: coordinates -> Jacobian/gradients ->
+// the owned columns of the element matrix, in registers -> shared-memory stage, (2) one thread per
+// owned nonzero: left-to-right sum of its contributions from the stage (deterministic, no atomics),
+// (3) coalesced store of nzval.  Every nonzero is written exactly once; nothing else is written.
 #pragma once
+#include <cub/cub.cuh>
+#include <climits>
 #include "efg_ctx.cuh"
-inline void tiled_release(efg_ctx *) {}
-template <class F> void tiled_symbolic(efg_ctx *) { efg_throw(EFG_ERR_INVALID, "tiled path not built yet"); }
-template <class F> void tiled_numeric(efg_ctx *) { efg_throw(EFG_ERR_INVALID, "tiled path not built yet"); }
+
+#define TL_CAP 96          // max distinct rows in one matrix column (tiled path)
+#define TL_MAXND 16
+
+struct TileDescFull {
+    int64_t slot0;          // first tile-order slot
+    int64_t gidx0;          // first gather index
+    int64_t elem0;          // first tile element (index into tconn/tmask)
+    int32_t nelem;          // tile elements incl. halo
+    int32_t nslot;          // owned nonzeros
+    int32_t run0, nrun;     // runs
+    int32_t nq;             // staged columns (= stage row stride)
+    int32_t pad_;
+    uint16_t qbase[TL_MAXND + 1]; // qbase[r] = first staged column of "r-th owned column of an element"
+    uint16_t pad2_[3];
+};
+
+static_assert(sizeof(TileDescFull) % 8 == 0, "TileDescFull is copied as 8-byte words");
+
+struct TiledData {
+    DevBuf<TileDescFull> tiles;
+    DevBuf<TileRun> runs;
+    DevBuf<int32_t> tconn;
+    DevBuf<uint16_t> tmask;
+    DevBuf<uint8_t> gcnt;
+    DevBuf<uint16_t> gidx;
+    int64_t ntelem = 0, ncontrib = 0, nruns = 0;
+    int smem_bytes = 0;
+    int block = 256;
+};
+
+static inline TiledData *&tiled_data(efg_ctx *ctx)
+{
+    static_assert(sizeof(void *) == 8, "");
+    return *reinterpret_cast<TiledData **>(&ctx->tl_opaque);
+}
+
+inline void tiled_release(efg_ctx *ctx)
+{
+    TiledData *&d = tiled_data(ctx);
+    delete d;
+    d = nullptr;
+    ctx->tl.ntiles = 0;
+}
+
+// ---- CUB helpers ---------------------------------------------------------------------------------
+template <class K, class V>
+static void tl_sort_pairs(efg_ctx *ctx, const K *kin, K *kout, const V *vin, V *vout, int64_t n, int end_bit)
+{
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, kin, kout, vin, vout, n, 0, end_bit, ctx->stream);
+    DevBuf<char> tmp;
+    tmp.alloc(ctx->pool, tb);
+    CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kin, kout, vin, vout, n, 0, end_bit, ctx->stream));
+    ctx->launches += (end_bit + 7) / 8 + 2;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+template <class K> static void tl_sort_keys(efg_ctx *ctx, const K *kin, K *kout, int64_t n, int end_bit)
+{
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, tb, kin, kout, n, 0, end_bit, ctx->stream);
+    DevBuf<char> tmp;
+    tmp.alloc(ctx->pool, tb);
+    CUDA_CHECK(cub::DeviceRadixSort::SortKeys(tmp.p, tb, kin, kout, n, 0, end_bit, ctx->stream));
+    ctx->launches += (end_bit + 7) / 8 + 2;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+template <class In, class Out> static void tl_excl_scan(efg_ctx *ctx, In in, Out out, int64_t n)
+{
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tb, in, out, n, ctx->stream);
+    DevBuf<char> tmp;
+    tmp.alloc(ctx->pool, tb);
+    CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, n, ctx->stream));
+    ctx->launches += 2;
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+}
+static inline int bits_for(int64_t maxval)
+{
+    int b = 1;
+    while (((int64_t)1 << b) <= maxval) b++;
+    return b;
+}
+template <class T> static T tl_read(efg_ctx *ctx, const T *dptr)
+{
+    T h;
+    CUDA_CHECK(cudaMemcpyAsync(&h, dptr, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    return h;
+}
+
+#define GRID_STRIDE(i, n) \
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride__ = (int64_t)gridDim.x * blockDim.x; i < (n); i += stride__)
+
+// ---- symbolic kernels ------------------------------------------------------------------------------
+template <class F>
+__global__ void k_tl_edofs(DofSrc src, int64_t nel, int64_t nrow, int64_t ncol, int32_t *__restrict__ edof, int *__restrict__ err)
+{
+    GRID_STRIDE(e, nel) {
+        int32_t d[F::ND];
+        F::edofs(src, e, d);
+        bool bad = false;
+#pragma unroll
+        for (int a = 0; a < F::ND; a++) {
+            bad |= d[a] < 0 || d[a] >= nrow || d[a] >= ncol;
+            edof[e * F::ND + a] = d[a];
+        }
+        if (bad) *err = 1;
+    }
+}
+
+struct BBox { double x0, y0, x1, y1; };
+struct BBoxOp {
+    __device__ __forceinline__ BBox operator()(const BBox &a, const BBox &b) const
+    {
+        return BBox{fmin(a.x0, b.x0), fmin(a.y0, b.y0), fmax(a.x1, b.x1), fmax(a.y1, b.y1)};
+    }
+};
+struct XYToBBox {
+    __device__ __forceinline__ BBox operator()(const double2 &p) const { return BBox{p.x, p.y, p.x, p.y}; }
+};
+
+__device__ __forceinline__ uint32_t spread16(uint32_t v)
+{
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+// Morton key of the element centroid (first 3 nodes), 16 bits per axis
+__global__ void k_tl_morton(const int32_t *__restrict__ gconn, int gk, const double2 *__restrict__ xy, int64_t nel,
+                            const BBox *__restrict__ bb, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const BBox b = *bb;
+    const double sx = (b.x1 > b.x0) ? 65535.0 / (b.x1 - b.x0) : 0.0, sy = (b.y1 > b.y0) ? 65535.0 / (b.y1 - b.y0) : 0.0;
+    GRID_STRIDE(e, nel) {
+        double cx = 0, cy = 0;
+        for (int a = 0; a < 3; a++) { const double2 p = xy[gconn[e * gk + a]]; cx += p.x; cy += p.y; }
+        cx *= (1.0 / 3); cy *= (1.0 / 3);
+        const uint32_t qx = (uint32_t)fmin(fmax((cx - b.x0) * sx, 0.0), 65535.0);
+        const uint32_t qy = (uint32_t)fmin(fmax((cy - b.y0) * sy, 0.0), 65535.0);
+        keys[e] = spread16(qx) | (spread16(qy) << 1);
+        vals[e] = (uint32_t)e;
+    }
+}
+__global__ void k_tl_etile_from_order(const uint32_t *__restrict__ eorder, int64_t nel, int te, int32_t *__restrict__ etile)
+{
+    GRID_STRIDE(p, nel) etile[eorder[p]] = (int32_t)(p / te);
+}
+__global__ void k_tl_etile_identity(int64_t nel, int te, int32_t *__restrict__ etile)
+{
+    GRID_STRIDE(e, nel) etile[e] = (int32_t)(e / te);
+}
+__global__ void k_tl_fill_i32(int32_t *p, int64_t n, int32_t v) { GRID_STRIDE(i, n) p[i] = v; }
+
+// owner tile of every column in range + adjacency pair generation
+template <int ND>
+__global__ void k_tl_owner_pairs(const int32_t *__restrict__ edof, const int32_t *__restrict__ etile, int64_t nel,
+                                 int64_t c0, int64_t c1, int32_t *__restrict__ owner, uint32_t *__restrict__ adjcnt,
+                                 uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const uint32_t ncl = (uint32_t)(c1 - c0);
+    GRID_STRIDE(t, nel * ND) {
+        const int64_t e = t / ND;
+        const int32_t c = edof[t];
+        if (c >= c0 && c < c1) {
+            const uint32_t cl = (uint32_t)(c - c0);
+            atomicMin(&owner[cl], etile[e]);
+            atomicAdd(&adjcnt[cl], 1u);
+            keys[t] = cl;
+        } else {
+            keys[t] = ncl;
+        }
+        vals[t] = (uint32_t)t;
+    }
+}
+
+// sorted, de-duplicated row list of one column (candidates enumerated from the adjacency)
+template <class F>
+__device__ __forceinline__ int tl_column_rows(const uint32_t *__restrict__ adj, uint32_t a0, uint32_t a1,
+                                              const int32_t *__restrict__ edof, int32_t (&rows)[TL_CAP], int &ncontrib)
+{
+    int n = 0;
+    ncontrib = 0;
+    for (uint32_t p = a0; p < a1; p++) {
+        const uint32_t t = adj[p];
+        const uint32_t e = t / F::ND;
+        const int lj = (int)(t % F::ND);
+        for (int i = 0; i < F::ND; i++) {
+            if (!F::mask(i, lj)) continue;
+            ncontrib++;
+            const int32_t r = edof[(int64_t)e * F::ND + i];
+            int lo = 0, hi = n;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (rows[mid] < r) lo = mid + 1; else hi = mid; }
+            if (lo < n && rows[lo] == r) continue;
+            if (n == TL_CAP) return -1;
+            for (int k = n; k > lo; k--) rows[k] = rows[k - 1];
+            rows[lo] = r;
+            n++;
+        }
+    }
+    return n;
+}
+
+template <class F>
+__global__ void k_tl_col_count(const uint32_t *__restrict__ adjptr, const uint32_t *__restrict__ adj, const int32_t *__restrict__ edof,
+                               int64_t ncl, uint8_t *__restrict__ colcnt, uint16_t *__restrict__ ccnt, int *__restrict__ err)
+{
+    GRID_STRIDE(cl, ncl) {
+        int32_t rows[TL_CAP];
+        int nc;
+        const int n = tl_column_rows<F>(adj, adjptr[cl], adjptr[cl + 1], edof, rows, nc);
+        if (n < 0 || nc > 65535) { *err = 2; colcnt[cl] = 0; ccnt[cl] = 0; continue; }
+        colcnt[cl] = (uint8_t)n;
+        ccnt[cl] = (uint16_t)nc;
+    }
+}
+template <class F>
+__global__ void k_tl_col_fill(const uint32_t *__restrict__ adjptr, const uint32_t *__restrict__ adj, const int32_t *__restrict__ edof,
+                              int64_t ncl, const int64_t *__restrict__ colptr0, int32_t *__restrict__ rowval, int64_t *__restrict__ colptr1)
+{
+    GRID_STRIDE(cl, ncl + 1) {
+        colptr1[cl] = colptr0[cl] + 1;
+        if (cl == ncl) continue;
+        int32_t rows[TL_CAP];
+        int nc;
+        const int n = tl_column_rows<F>(adj, adjptr[cl], adjptr[cl + 1], edof, rows, nc);
+        const int64_t o = colptr0[cl];
+        for (int k = 0; k < n; k++) rowval[o + k] = rows[k];
+    }
+}
+
+__global__ void k_tl_tilecol_keys(const int32_t *__restrict__ owner, int64_t ncl, int ntiles, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    GRID_STRIDE(cl, ncl) {
+        const int32_t o = owner[cl];
+        keys[cl] = (o == INT_MAX) ? (uint32_t)ntiles : (uint32_t)o;
+        vals[cl] = (uint32_t)cl;
+    }
+}
+// lower_bound of every tile id in a sorted key array
+template <class K> __global__ void k_tl_lower_bounds(const K *__restrict__ keys, int64_t n, int ntiles, int shift, int64_t *__restrict__ ptr)
+{
+    GRID_STRIDE(T, (int64_t)ntiles + 1) {
+        int64_t lo = 0, hi = n;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)(keys[mid] >> shift) < T) lo = mid + 1; else hi = mid; }
+        ptr[T] = lo;
+    }
+}
+struct GatherU8 {
+    const uint8_t *v; const uint32_t *idx; int64_t n;
+    __device__ __forceinline__ int64_t operator()(int64_t k) const { return k < n ? (int64_t)v[idx[k]] : 0; }
+};
+struct GatherU16 {
+    const uint16_t *v; const uint32_t *idx; int64_t n;
+    __device__ __forceinline__ int64_t operator()(int64_t k) const { return k < n ? (int64_t)v[idx[k]] : 0; }
+};
+// run heads among the owned tile columns
+__global__ void k_tl_run_flags(const uint32_t *__restrict__ tkeys, const uint32_t *__restrict__ tcols, int64_t nowned, int32_t *__restrict__ flag)
+{
+    GRID_STRIDE(k, nowned) flag[k] = (k == 0 || tkeys[k] != tkeys[k - 1] || tcols[k] != tcols[k - 1] + 1) ? 1 : 0;
+}
+__global__ void k_tl_run_fill(const int32_t *__restrict__ flag, const int64_t *__restrict__ runidx, const uint32_t *__restrict__ tkeys,
+                              const uint32_t *__restrict__ tcols, int64_t nowned, const int64_t *__restrict__ tcol_slot,
+                              const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ colptr0, TileRun *__restrict__ runs,
+                              int64_t *__restrict__ run_firstk)
+{
+    GRID_STRIDE(k, nowned) if (flag[k]) {
+        const int64_t r = runidx[k];
+        const uint32_t T = tkeys[k];
+        runs[r].nz0 = colptr0[tcols[k]];
+        runs[r].s0 = (int32_t)(tcol_slot[k] - tcol_slot[tcol_ptr[T]]);
+        run_firstk[r] = k;
+    }
+}
+__global__ void k_tl_run_len(const int64_t *__restrict__ run_firstk, int64_t nruns, int64_t nowned, const int64_t *__restrict__ tcol_slot, TileRun *__restrict__ runs)
+{
+    GRID_STRIDE(r, nruns) {
+        const int64_t k0 = run_firstk[r], k1 = (r + 1 < nruns) ? run_firstk[r + 1] : nowned;
+        runs[r].len = (int32_t)(tcol_slot[k1] - tcol_slot[k0]);
+    }
+}
+
+// tile-element keys: (T << 36) | (e << 4) | lj for every (e, lj) whose column is owned
+template <int ND>
+__global__ void k_tl_telem_keys(const int32_t *__restrict__ edof, int64_t nel, int64_t c0, int64_t c1, const int32_t *__restrict__ owner,
+                                int ntiles, uint64_t *__restrict__ keys)
+{
+    GRID_STRIDE(t, nel * ND) {
+        const int64_t e = t / ND;
+        const int lj = (int)(t % ND);
+        const int32_t c = edof[t];
+        const uint64_t T = (c >= c0 && c < c1) ? (uint64_t)(uint32_t)owner[c - c0] : (uint64_t)ntiles;
+        keys[t] = (T << 36) | ((uint64_t)e << 4) | (uint64_t)lj;
+    }
+}
+__global__ void k_tl_head_flags64(const uint64_t *__restrict__ keys, int64_t n, int shift, int32_t *__restrict__ flag)
+{
+    GRID_STRIDE(p, n) flag[p] = (p == 0 || (keys[p] >> shift) != (keys[p - 1] >> shift)) ? 1 : 0;
+}
+// unique (T,e) entries with their owned-column masks
+__global__ void k_tl_telem_fill(const uint64_t *__restrict__ keys, int64_t n, const int32_t *__restrict__ flag, const int64_t *__restrict__ gidx_of,
+                                uint64_t *__restrict__ telem_key, uint16_t *__restrict__ mask, uint32_t *__restrict__ key2, uint32_t *__restrict__ val2,
+                                uint32_t *__restrict__ pc_hist /* ntiles x 17 */)
+{
+    GRID_STRIDE(p, n) if (flag[p]) {
+        const uint64_t ke = keys[p] >> 4;
+        uint32_t m = 0;
+        for (int64_t q = p; q < n && (keys[q] >> 4) == ke; q++) m |= 1u << (uint32_t)(keys[q] & 15u);
+        const int64_t g = gidx_of[p];
+        telem_key[g] = ke;
+        mask[g] = (uint16_t)m;
+        const uint32_t T = (uint32_t)(ke >> 32);
+        const int pc = __popc(m);
+        key2[g] = (T << 5) | (uint32_t)(16 - pc);   // popcount descending inside a tile
+        val2[g] = (uint32_t)g;
+        atomicAdd(&pc_hist[(int64_t)T * 17 + pc], 1u);
+    }
+}
+__global__ void k_tl_invert(const uint32_t *__restrict__ order, int64_t n, uint32_t *__restrict__ newpos)
+{
+    GRID_STRIDE(p, n) newpos[order[p]] = (uint32_t)p;
+}
+template <int GK>
+__global__ void k_tl_tconn(const uint32_t *__restrict__ order, int64_t n, const uint64_t *__restrict__ telem_key, const uint16_t *__restrict__ mask,
+                           const int32_t *__restrict__ gconn, int32_t *__restrict__ tconn, uint16_t *__restrict__ tmask)
+{
+    GRID_STRIDE(p, n) {
+        const uint32_t g = order[p];
+        const int64_t e = (int64_t)(telem_key[g] & 0xffffffffu);
+#pragma unroll
+        for (int a = 0; a < GK; a++) tconn[p * GK + a] = gconn[e * GK + a];
+        tmask[p] = mask[g];
+    }
+}
+
+// per owned tile column: contribution counts per slot + stage indices in append order
+template <class F>
+__global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint32_t *__restrict__ tcols, int64_t nowned,
+                                  const uint32_t *__restrict__ adjptr, const uint32_t *__restrict__ adj, const int32_t *__restrict__ edof,
+                                  const int64_t *__restrict__ colptr0, const int32_t *__restrict__ rowval,
+                                  const uint64_t *__restrict__ telem_key, const int64_t *__restrict__ telem_ptr,
+                                  const uint16_t *__restrict__ mask, const uint32_t *__restrict__ newpos,
+                                  const TileDescFull *__restrict__ tiles, const int64_t *__restrict__ tcol_slot, const int64_t *__restrict__ tcol_gidx,
+                                  uint8_t *__restrict__ gcnt, uint16_t *__restrict__ gidx, int *__restrict__ err)
+{
+    GRID_STRIDE(k, nowned) {
+        const uint32_t T = tkeys[k], cl = tcols[k];
+        const int64_t r0 = colptr0[cl];
+        const int nr = (int)(colptr0[cl + 1] - r0);
+        const TileDescFull &td = tiles[T];
+        const int64_t g0 = telem_ptr[T], g1 = telem_ptr[T + 1];
+        uint16_t off[TL_CAP];
+        for (int t = 0; t < nr; t++) off[t] = 0;
+        const uint32_t a0 = adjptr[cl], a1 = adjptr[cl + 1];
+        // pass A: contributions per slot
+        for (uint32_t p = a0; p < a1; p++) {
+            const uint32_t t = adj[p];
+            const uint32_t e = t / F::ND;
+            const int lj = (int)(t % F::ND);
+            for (int i = 0; i < F::ND; i++) {
+                if (!F::mask(i, lj)) continue;
+                const int32_t r = edof[(int64_t)e * F::ND + i];
+                int lo = 0, hi = nr;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (rowval[r0 + mid] < r) lo = mid + 1; else hi = mid; }
+                off[lo]++;
+            }
+        }
+        const int64_t sbase = tcol_slot[k];
+        int run = 0;
+        for (int t = 0; t < nr; t++) {
+            const int c = off[t];
+            if (c > 255) *err = 3;
+            gcnt[sbase + t] = (uint8_t)c;
+            off[t] = (uint16_t)run;
+            run += c;
+        }
+        // pass B: stage indices, append order
+        const int64_t gb = tcol_gidx[k];
+        for (uint32_t p = a0; p < a1; p++) {
+            const uint32_t t = adj[p];
+            const uint32_t e = t / F::ND;
+            const int lj = (int)(t % F::ND);
+            // tile element (T, e)
+            const uint64_t want = ((uint64_t)T << 32) | e;
+            int64_t lo = g0, hi = g1;
+            while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (telem_key[mid] < want) lo = mid + 1; else hi = mid; }
+            const uint32_t m = mask[lo];
+            const int rnk = __popc(m & ((1u << lj) - 1u));
+            const uint32_t le = newpos[lo] - (uint32_t)td.elem0;
+            const uint32_t q = td.qbase[rnk] + le;
+            for (int i = 0; i < F::ND; i++) {
+                if (!F::mask(i, lj)) continue;
+                const int32_t r = edof[(int64_t)e * F::ND + i];
+                int l2 = 0, h2 = nr;
+                while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (rowval[r0 + mid] < r) l2 = mid + 1; else h2 = mid; }
+                const uint32_t sidx = (uint32_t)i * (uint32_t)td.nq + q;
+                if (sidx > 65535u) *err = 4;
+                gidx[gb + off[l2]] = (uint16_t)sidx;
+                off[l2]++;
+            }
+        }
+    }
+}
+
+__global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ tcol_slot,
+                                const int64_t *__restrict__ tcol_gidx, const int64_t *__restrict__ telem_ptr,
+                                const int64_t *__restrict__ run_of_k /* inclusive-run index per k: exclusive scan of flags */,
+                                int64_t nowned, int64_t nruns, const uint32_t *__restrict__ pc_hist, TileDescFull *__restrict__ tiles,
+                                int32_t *__restrict__ maxima /* nq, nslot, nelem, nrun */)
+{
+    GRID_STRIDE(T, ntiles) {
+        TileDescFull d;
+        const int64_t k0 = tcol_ptr[T], k1 = tcol_ptr[T + 1];
+        d.slot0 = tcol_slot[k0];
+        d.nslot = (int32_t)(tcol_slot[k1] - tcol_slot[k0]);
+        d.gidx0 = tcol_gidx[k0];
+        d.elem0 = telem_ptr[T];
+        d.nelem = (int32_t)(telem_ptr[T + 1] - telem_ptr[T]);
+        const int64_t r0 = (k0 < nowned) ? run_of_k[k0] : nruns, r1 = (k1 < nowned) ? run_of_k[k1] : nruns;
+        d.run0 = (int32_t)r0;
+        d.nrun = (int32_t)(r1 - r0);
+        // qbase[r] = sum_{r' < r} (#elements with popcount > r')
+        uint32_t above[TL_MAXND + 2];
+        uint32_t acc = 0;
+        for (int pc = 16; pc >= 0; pc--) { above[pc] = acc; acc += pc_hist[(int64_t)T * 17 + pc]; } // above[pc] = #elements with popcount > pc
+        uint32_t q = 0;
+        for (int r = 0; r <= TL_MAXND; r++) { d.qbase[r] = (uint16_t)q; if (r < TL_MAXND) q += above[r]; }
+        d.nq = (int32_t)d.qbase[nd];
+        d.pad_ = 0; d.pad2_[0] = d.pad2_[1] = d.pad2_[2] = 0;
+        tiles[T] = d;
+        atomicMax(&maxima[0], d.nq); atomicMax(&maxima[1], d.nslot); atomicMax(&maxima[2], d.nelem); atomicMax(&maxima[3], d.nrun);
+    }
+}
+
+// ---- numeric kernel ---------------------------------------------------------------------------------
+template <class F, bool S, int J>
+__device__ __forceinline__ void tl_stage_column(const Geo<F::BK, F::NQ> &G, uint32_t m, const uint16_t *__restrict__ qbase, uint32_t le, int nq,
+                                                double *__restrict__ stage)
+{
+    if (m & (1u << J)) {
+        double out[F::ND];
+        F::template column<S, J>(G, out);
+        const uint32_t q = qbase[__popc(m & ((1u << J) - 1u))] + le;
+#pragma unroll
+        for (int i = 0; i < F::ND; i++)
+            if (F::mask(i, J)) stage[i * nq + q] = out[i];
+    }
+}
+template <class F, bool S, int... Js>
+__device__ __forceinline__ void tl_stage_all(std::integer_sequence<int, Js...>, const Geo<F::BK, F::NQ> &G, uint32_t m,
+                                             const uint16_t *__restrict__ qbase, uint32_t le, int nq, double *__restrict__ stage)
+{
+    (tl_stage_column<F, S, Js>(G, m, qbase, le, nq, stage), ...);
+}
+
+template <class F, bool S, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_tl_numeric(const TileDescFull *__restrict__ tiles, const TileRun *__restrict__ runs,
+                                                      const int32_t *__restrict__ tconn, const uint16_t *__restrict__ tmask,
+                                                      const double2 *__restrict__ xy, const uint8_t *__restrict__ gcnt,
+                                                      const uint16_t *__restrict__ gidx, double *__restrict__ nzval)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ TileDescFull td;
+    __shared__ int warp_tot[BLOCK / 32];
+    const int tid = threadIdx.x;
+    if (tid < (int)(sizeof(TileDescFull) / 8)) reinterpret_cast<int64_t *>(&td)[tid] = reinterpret_cast<const int64_t *>(&tiles[blockIdx.x])[tid];
+    __syncthreads();
+    double *stage = reinterpret_cast<double *>(smem_raw);
+    const int nq = td.nq;
+    TileRun *srun = reinterpret_cast<TileRun *>(stage + (size_t)F::ND * nq);
+    for (int r = tid; r < td.nrun; r += BLOCK) srun[r] = runs[td.run0 + r];
+
+    // phase 1: element matrices of the owned columns -> stage
+    for (int le = tid; le < td.nelem; le += BLOCK) {
+        const int64_t g = td.elem0 + le;
+        double X[F::GK], Y[F::GK];
+#pragma unroll
+        for (int a = 0; a < F::GK; a++) {
+            const double2 p = __ldg(&xy[tconn[g * F::GK + a]]);
+            X[a] = p.x; Y[a] = p.y;
+        }
+        const uint32_t m = tmask[g];
+        Geo<F::BK, F::NQ> G;
+        geo_compute<S, F::GK, F::BK, F::NQ>(X, Y, G);
+        tl_stage_all<F, S>(std::make_integer_sequence<int, F::ND>{}, G, m, td.qbase, (uint32_t)le, nq, stage);
+    }
+    __syncthreads();
+
+    // phase 2: every owned nonzero = left-to-right sum of its contributions (append order)
+    const int lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = BLOCK / 32;
+    const int nslot = td.nslot;
+    const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // slots per warp, multiple of 32
+    const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
+    const uint8_t *cnt = gcnt + td.slot0;
+    int tot = 0;
+    for (int s = w0 + lane; s < w1; s += 32) tot += cnt[s];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) warp_tot[warp] = tot;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < warp; w++) wbase += warp_tot[w];
+    const uint16_t *gi = gidx + td.gidx0;
+    int rcur = 0;
+    for (int s0 = w0; s0 < w1; s0 += 32) {
+        const int s = s0 + lane;
+        const int c = (s < w1) ? cnt[s] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const int off = wbase + incl - c;
+        wbase += __shfl_sync(0xffffffffu, incl, 31);
+        if (s < w1) {
+            double acc = 0.0;
+            if (c > 0) {
+                acc = stage[gi[off]];
+                for (int k = 1; k < c; k++) acc = __dadd_rn(acc, stage[gi[off + k]]);
+            }
+            // destination: run containing tile slot s
+            if (!(s >= srun[rcur].s0 && s < srun[rcur].s0 + srun[rcur].len)) {
+                int lo = 0, hi = td.nrun - 1;
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
+                rcur = lo;
+            }
+            nzval[srun[rcur].nz0 + (s - srun[rcur].s0)] = acc;
+        }
+    }
+}
+
+// ---- host: symbolic ---------------------------------------------------------------------------------
+template <class F> static int tl_default_tile_elems()
+{
+    // stage bytes per owned element-equivalent = ND*ND*8; aim at ~72 KB of stage per CTA
+    int te = (72 * 1024) / (F::ND * F::ND * 8);
+    if (te > 512) te = 512;
+    if (te < 32) te = 32;
+    return te & ~7;
+}
+
+template <class F> void tiled_symbolic(efg_ctx *ctx)
+{
+    static_assert(F::ND <= TL_MAXND, "");
+    constexpr int ND = F::ND;
+    const MeshDev &m0 = ctx->mesh[0];
+    const MeshDev &gm = ctx->mesh[F::GMESH];
+    const int64_t nel = m0.nel;
+    const int64_t ncl = ctx->c1 - ctx->c0;
+    if (nel * ND >= ((int64_t)1 << 32)) efg_throw(EFG_ERR_LIMIT, "tiled path: nel*ND exceeds 2^32; shard the mesh (efg_set_column_range)");
+    cudaStream_t st = ctx->stream;
+    DevPool &pool = ctx->pool;
+    TiledData *td = new TiledData();
+    tiled_data(ctx) = td;
+
+    DevBuf<int> err;
+    err.alloc(pool, 1);
+    CUDA_CHECK(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+
+    // T0: combined element dof table
+    DevBuf<int32_t> edof;
+    edof.alloc(pool, (size_t)(nel * ND));
+    DofSrc src{m0.conn.p, ctx->mesh[1].conn.p, ctx->space[0].dof.p, ctx->space[1].dof.p, ctx->space[2].dof.p};
+    LAUNCH(ctx, k_tl_edofs<F>, grid_for(nel, 256), 256, 0, src, nel, ctx->nrow, ctx->ncol, edof.p, err.p);
+    if (tl_read(ctx, err.p))
+        efg_throw(EFG_ERR_INDEX, "ArgumentError: a dof number is < 1 or exceeds nrow/ncol (was every space numbered, incl. data dofs?)");
+
+    // T1: element order -> tile of each element
+    int te = ctx->opt_tile_elems > 0 ? ctx->opt_tile_elems : tl_default_tile_elems<F>();
+    const int ntiles = (int)((nel + te - 1) / te);
+    DevBuf<int32_t> etile;
+    etile.alloc(pool, (size_t)nel);
+    if (ctx->opt_sfc && nel > te) {
+        DevBuf<BBox> bb;
+        bb.alloc(pool, 1);
+        cub::TransformInputIterator<BBox, XYToBBox, const double2 *> it(gm.xy.p, XYToBBox());
+        const BBox init{1e300, 1e300, -1e300, -1e300};
+        size_t tb = 0;
+        cub::DeviceReduce::Reduce(nullptr, tb, it, bb.p, gm.nnodes, BBoxOp(), init, st);
+        DevBuf<char> tmp;
+        tmp.alloc(pool, tb);
+        CUDA_CHECK(cub::DeviceReduce::Reduce(tmp.p, tb, it, bb.p, gm.nnodes, BBoxOp(), init, st));
+        ctx->launches += 2;
+        DevBuf<uint32_t> k1, k2, v1, v2;
+        k1.alloc(pool, (size_t)nel); k2.alloc(pool, (size_t)nel); v1.alloc(pool, (size_t)nel); v2.alloc(pool, (size_t)nel);
+        LAUNCH(ctx, k_tl_morton, grid_for(nel, 256), 256, 0, gm.conn.p, gm.kind, gm.xy.p, nel, bb.p, k1.p, v1.p);
+        tl_sort_pairs(ctx, k1.p, k2.p, v1.p, v2.p, nel, 32);
+        LAUNCH(ctx, k_tl_etile_from_order, grid_for(nel, 256), 256, 0, v2.p, nel, te, etile.p);
+    } else {
+        LAUNCH(ctx, k_tl_etile_identity, grid_for(nel, 256), 256, 0, nel, te, etile.p);
+    }
+
+    // T2/T3: column owners + adjacency (column -> (element, local column)), ascending element
+    DevBuf<int32_t> owner;
+    DevBuf<uint32_t> adjcnt, adjptr, adj;
+    owner.alloc(pool, (size_t)ncl + 1);
+    adjcnt.alloc(pool, (size_t)ncl + 2); adjptr.alloc(pool, (size_t)ncl + 2);
+    LAUNCH(ctx, k_tl_fill_i32, grid_for(ncl + 1, 256), 256, 0, owner.p, ncl + 1, INT_MAX);
+    CUDA_CHECK(cudaMemsetAsync(adjcnt.p, 0, (size_t)(ncl + 2) * sizeof(uint32_t), st));
+    adj.alloc(pool, (size_t)(nel * ND));
+    {
+        DevBuf<uint32_t> k1, k2, v1;
+        k1.alloc(pool, (size_t)(nel * ND)); k2.alloc(pool, (size_t)(nel * ND)); v1.alloc(pool, (size_t)(nel * ND));
+        LAUNCH(ctx, k_tl_owner_pairs<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, etile.p, nel, ctx->c0, ctx->c1, owner.p, adjcnt.p, k1.p, v1.p);
+        tl_sort_pairs(ctx, k1.p, k2.p, v1.p, adj.p, nel * ND, bits_for(ncl));
+    }
+    tl_excl_scan(ctx, adjcnt.p, adjptr.p, ncl + 1);
+    const int64_t npairs = (int64_t)tl_read(ctx, adjptr.p + ncl);
+
+    // T4: CSC pattern
+    DevBuf<uint8_t> colcnt;
+    DevBuf<uint16_t> ccnt;
+    DevBuf<int64_t> colptr0;
+    colcnt.alloc(pool, (size_t)ncl + 1); ccnt.alloc(pool, (size_t)ncl + 1); colptr0.alloc(pool, (size_t)ncl + 1);
+    CUDA_CHECK(cudaMemsetAsync(colcnt.p, 0, (size_t)ncl + 1, st));
+    CUDA_CHECK(cudaMemsetAsync(ccnt.p, 0, ((size_t)ncl + 1) * 2, st));
+    LAUNCH(ctx, k_tl_col_count<F>, grid_for(ncl, 128), 128, 0, adjptr.p, adj.p, edof.p, ncl, colcnt.p, ccnt.p, err.p);
+    if (tl_read(ctx, err.p))
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a matrix column has more than %d distinct rows (node valence too high); use EFG_OPT_PATH=1", TL_CAP);
+    {
+        cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const uint8_t *> it(colcnt.p, cub::CastOp<int64_t>());
+        tl_excl_scan(ctx, it, colptr0.p, ncl + 1);
+    }
+    const int64_t nnz = tl_read(ctx, colptr0.p + ncl);
+    ctx->nnz = nnz;
+    ctx->rowval.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
+    ctx->colptr.alloc(pool, (size_t)ncl + 1);
+    LAUNCH(ctx, k_tl_col_fill<F>, grid_for(ncl + 1, 128), 128, 0, adjptr.p, adj.p, edof.p, ncl, colptr0.p, ctx->rowval.p, ctx->colptr.p);
+
+    // T5: tile column lists, tile-order slot / gather offsets, runs
+    DevBuf<uint32_t> tkeys, tcols;
+    tkeys.alloc(pool, (size_t)ncl + 1); tcols.alloc(pool, (size_t)ncl + 1);
+    {
+        DevBuf<uint32_t> k1, v1;
+        k1.alloc(pool, (size_t)ncl + 1); v1.alloc(pool, (size_t)ncl + 1);
+        LAUNCH(ctx, k_tl_tilecol_keys, grid_for(ncl, 256), 256, 0, owner.p, ncl, ntiles, k1.p, v1.p);
+        tl_sort_pairs(ctx, k1.p, tkeys.p, v1.p, tcols.p, ncl, bits_for(ntiles));
+    }
+    DevBuf<int64_t> tcol_ptr, tcol_slot, tcol_gidx;
+    tcol_ptr.alloc(pool, (size_t)ntiles + 1); tcol_slot.alloc(pool, (size_t)ncl + 2); tcol_gidx.alloc(pool, (size_t)ncl + 2);
+    LAUNCH(ctx, k_tl_lower_bounds<uint32_t>, grid_for(ntiles + 1, 256), 256, 0, tkeys.p, ncl, ntiles, 0, tcol_ptr.p);
+    const int64_t nowned = tl_read(ctx, tcol_ptr.p + ntiles);
+    {
+        cub::CountingInputIterator<int64_t> cnt_it(0);
+        cub::TransformInputIterator<int64_t, GatherU8, cub::CountingInputIterator<int64_t>> it8(cnt_it, GatherU8{colcnt.p, tcols.p, nowned});
+        tl_excl_scan(ctx, it8, tcol_slot.p, nowned + 1);
+        cub::TransformInputIterator<int64_t, GatherU16, cub::CountingInputIterator<int64_t>> it16(cnt_it, GatherU16{ccnt.p, tcols.p, nowned});
+        tl_excl_scan(ctx, it16, tcol_gidx.p, nowned + 1);
+    }
+    const int64_t ncontrib = tl_read(ctx, tcol_gidx.p + nowned);
+    td->ncontrib = ncontrib;
+
+    DevBuf<int32_t> rflag;
+    DevBuf<int64_t> runidx, run_firstk;
+    rflag.alloc(pool, (size_t)nowned + 1); runidx.alloc(pool, (size_t)nowned + 1);
+    CUDA_CHECK(cudaMemsetAsync(rflag.p, 0, ((size_t)nowned + 1) * sizeof(int32_t), st));
+    LAUNCH(ctx, k_tl_run_flags, grid_for(nowned, 256), 256, 0, tkeys.p, tcols.p, nowned, rflag.p);
+    {
+        cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *> it(rflag.p, cub::CastOp<int64_t>());
+        tl_excl_scan(ctx, it, runidx.p, nowned + 1);
+    }
+    const int64_t nruns = tl_read(ctx, runidx.p + nowned);
+    td->nruns = nruns;
+    td->runs.alloc(pool, (size_t)(nruns > 0 ? nruns : 1));
+    run_firstk.alloc(pool, (size_t)(nruns > 0 ? nruns : 1));
+    LAUNCH(ctx, k_tl_run_fill, grid_for(nowned, 256), 256, 0, rflag.p, runidx.p, tkeys.p, tcols.p, nowned, tcol_slot.p, tcol_ptr.p, colptr0.p, td->runs.p, run_firstk.p);
+    LAUNCH(ctx, k_tl_run_len, grid_for(nruns, 256), 256, 0, run_firstk.p, nruns, nowned, tcol_slot.p, td->runs.p);
+
+    // T6: tile element lists (own + halo), masks, popcount-descending order inside a tile
+    DevBuf<uint64_t> ek2;
+    {
+        DevBuf<uint64_t> ek1;
+        ek1.alloc(pool, (size_t)(nel * ND)); ek2.alloc(pool, (size_t)(nel * ND));
+        LAUNCH(ctx, k_tl_telem_keys<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, nel, ctx->c0, ctx->c1, owner.p, ntiles, ek1.p);
+        tl_sort_keys(ctx, ek1.p, ek2.p, nel * ND, 36 + bits_for(ntiles));   // out-of-range pairs carry tile id ntiles: they sort last
+    }
+    DevBuf<int32_t> eflag;
+    DevBuf<int64_t> eidx;
+    eflag.alloc(pool, (size_t)npairs + 1); eidx.alloc(pool, (size_t)npairs + 1);
+    CUDA_CHECK(cudaMemsetAsync(eflag.p, 0, ((size_t)npairs + 1) * sizeof(int32_t), st));
+    LAUNCH(ctx, k_tl_head_flags64, grid_for(npairs, 256), 256, 0, ek2.p, npairs, 4, eflag.p);
+    {
+        cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *> it(eflag.p, cub::CastOp<int64_t>());
+        tl_excl_scan(ctx, it, eidx.p, npairs + 1);
+    }
+    const int64_t ntelem = tl_read(ctx, eidx.p + npairs);
+    td->ntelem = ntelem;
+    if (ntelem >= ((int64_t)1 << 32)) efg_throw(EFG_ERR_LIMIT, "tiled path: too many tile elements");
+    DevBuf<uint64_t> telem_key;
+    DevBuf<uint16_t> emask;
+    DevBuf<uint32_t> key2, val2, key2s, order2, newpos, pc_hist;
+    telem_key.alloc(pool, (size_t)ntelem + 1); emask.alloc(pool, (size_t)ntelem + 1);
+    key2.alloc(pool, (size_t)ntelem + 1); val2.alloc(pool, (size_t)ntelem + 1);
+    key2s.alloc(pool, (size_t)ntelem + 1); order2.alloc(pool, (size_t)ntelem + 1); newpos.alloc(pool, (size_t)ntelem + 1);
+    pc_hist.alloc(pool, (size_t)ntiles * 17);
+    CUDA_CHECK(cudaMemsetAsync(pc_hist.p, 0, (size_t)ntiles * 17 * sizeof(uint32_t), st));
+    LAUNCH(ctx, k_tl_telem_fill, grid_for(npairs, 256), 256, 0, ek2.p, npairs, eflag.p, eidx.p, telem_key.p, emask.p, key2.p, val2.p, pc_hist.p);
+    ek2.release(); eflag.release(); eidx.release();
+    tl_sort_pairs(ctx, key2.p, key2s.p, val2.p, order2.p, ntelem, 5 + bits_for(ntiles));
+    LAUNCH(ctx, k_tl_invert, grid_for(ntelem, 256), 256, 0, order2.p, ntelem, newpos.p);
+    DevBuf<int64_t> telem_ptr;
+    telem_ptr.alloc(pool, (size_t)ntiles + 1);
+    LAUNCH(ctx, k_tl_lower_bounds<uint64_t>, grid_for(ntiles + 1, 256), 256, 0, telem_key.p, ntelem, ntiles, 32, telem_ptr.p);
+    td->tconn.alloc(pool, (size_t)(ntelem * F::GK + 1));
+    td->tmask.alloc(pool, (size_t)ntelem + 1);
+    LAUNCH(ctx, k_tl_tconn<F::GK>, grid_for(ntelem, 256), 256, 0, order2.p, ntelem, telem_key.p, emask.p, gm.conn.p, td->tconn.p, td->tmask.p);
+
+    // tile descriptors
+    DevBuf<int32_t> maxima;
+    maxima.alloc(pool, 4);
+    CUDA_CHECK(cudaMemsetAsync(maxima.p, 0, 4 * sizeof(int32_t), st));
+    td->tiles.alloc(pool, (size_t)ntiles);
+    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tcol_ptr.p, tcol_slot.p, tcol_gidx.p, telem_ptr.p, runidx.p,
+           nowned, nruns, pc_hist.p, td->tiles.p, maxima.p);
+    int32_t hmax[4];
+    CUDA_CHECK(cudaMemcpyAsync(hmax, maxima.p, sizeof hmax, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    ctx->tl.max_nq = hmax[0]; ctx->tl.max_nslot = hmax[1]; ctx->tl.max_nelem = hmax[2]; ctx->tl.max_nrun = hmax[3];
+    if ((int64_t)hmax[0] * ND > 65535)
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile stages %d columns x %d rows > 65535 entries; lower EFG_OPT_TILE_ELEMS", hmax[0], ND);
+    const size_t smem = (size_t)hmax[0] * ND * sizeof(double) + (size_t)hmax[3] * sizeof(TileRun);
+    if (smem > 220 * 1024)
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile needs %zu bytes of shared memory; lower EFG_OPT_TILE_ELEMS", smem);
+    td->smem_bytes = (int)smem;
+
+    // T8: gather lists
+    td->gcnt.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
+    td->gidx.alloc(pool, (size_t)(ncontrib > 0 ? ncontrib : 1));
+    LAUNCH(ctx, k_tl_gather_build<F>, grid_for(nowned, 128), 128, 0, tkeys.p, tcols.p, nowned, adjptr.p, adj.p, edof.p, colptr0.p, ctx->rowval.p,
+           telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, tcol_slot.p, tcol_gidx.p, td->gcnt.p, td->gidx.p, err.p);
+    const int e2 = tl_read(ctx, err.p);
+    if (e2 == 3) efg_throw(EFG_ERR_LIMIT, "tiled path: a nonzero has more than 255 contributions; use EFG_OPT_PATH=1");
+    if (e2) efg_throw(EFG_ERR_LIMIT, "tiled path: internal stage index overflow (%d)", e2);
+
+    ctx->nzval.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
+    ctx->tl.ntiles = ntiles;
+    ctx->tl.tile_elems = te;
+    ctx->tl.sum_tile_elems = ntelem;
+    ctx->tl.numeric_bytes = ntelem * (F::GK * 4 + 2) + gm.nnodes * 16 + nnz * (1 + 8) + ncontrib * 2 + (int64_t)ntiles * sizeof(TileDescFull) + nruns * sizeof(TileRun);
+}
+
+template <class F, bool S> static void tl_launch_numeric(efg_ctx *ctx)
+{
+    TiledData *td = tiled_data(ctx);
+    const MeshDev &gm = ctx->mesh[F::GMESH];
+    constexpr int BLOCK = 256;
+    auto kern = k_tl_numeric<F, S, BLOCK>;
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
+    if (ctx->tl.ntiles > 0)
+        LAUNCH(ctx, kern, (unsigned)ctx->tl.ntiles, BLOCK, (size_t)td->smem_bytes, td->tiles.p, td->runs.p, td->tconn.p, td->tmask.p, gm.xy.p,
+               td->gcnt.p, td->gidx.p, ctx->nzval.p);
+    ctx->numeric_launches += 1;
+}
+
+template <class F> void tiled_numeric(efg_ctx *ctx)
+{
+    if (ctx->opt_strict) tl_launch_numeric<F, true>(ctx); else tl_launch_numeric<F, false>(ctx);
+}

@@ -366,7 +366,7 @@ int efg_symbolic(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
         const int npts = upload_tables(ctx, vkind, quad);
         if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, vkind);
         CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-        const int path = ctx->opt_path == 2 ? 2 : 1; // TODO auto -> tiled
+        const int path = ctx->opt_path == 1 ? 1 : 2;
         const bool ok = dispatch_form(form, vkind, npts, [&](auto F) {
             using Form = decltype(F);
             if (path == 1) twopass_symbolic<Form>(ctx); else tiled_symbolic<Form>(ctx);
