@@ -38,10 +38,53 @@ template <bool S> __device__ __forceinline__ double fdiv(double a, double b) {
     if constexpr (S) return __ddiv_rn(a, b); else return a / b;
 }
 
-// ---- geometry: Jacobian, JxW and spatial gradients at every quadrature point -------------------
+// Quotients n/d with a shared divisor.  STRICT: the IEEE division the reference performs.
+// Default: one IEEE reciprocal per divisor, then q = n*inv refined by one FMA residual step
+// (Markstein: q' = q + inv*(n - q*d) is the correctly rounded quotient when inv = RN(1/d), up to
+// the divisor-significand-all-ones corner case) -- 3 DFMA-pipe ops instead of a ~25-instruction
+// division sequence, and still (almost always) the same bits as the true division.
+template <bool S> struct SharedDivisor {
+    double d, inv;
+    __device__ __forceinline__ explicit SharedDivisor(double d_) : d(d_), inv(0.0) { if constexpr (!S) inv = 1.0 / d_; }
+    __device__ __forceinline__ double operator()(double n) const {
+        if constexpr (S) return __ddiv_rn(n, d);
+        else { const double q = n * inv; const double r = fma(-q, d, n); return fma(r, inv, q); }
+    }
+};
+
+// ---- geometry: Jacobian, JxW and spatial gradients at one quadrature point ---------------------
 // GK = kind of the geometry carrier (whose nodes X,Y are given), BK = kind whose basis gradients
 // are wanted (BK != GK only for the Reddy/veclap Stokes forms: T3 Jacobian applied to T6 gradients,
 // examples/stokes/colliding_flow/ht_p2_p1.jl:72-76).
+template <bool S, int GK, int BK>
+__device__ __forceinline__ void geo_qp(const double (&X)[GK], const double (&Y)[GK], int q,
+                                       double (&gx)[BK], double (&gy)[BK], double &JxW)
+{
+    const QTab &tg = c_tab[kind_slot(GK)];
+    const QTab &tb = c_tab[kind_slot(BK)];
+    // _jac: src/FElements.jl:148-156 -- J = sum_n x_n (outer) dN_n/dxi, node order, first term assigned.
+    // ALWAYS evaluated without FMA contraction: the sum cancels from O(1) to O(h), so any other
+    // rounding sequence differs from the reference by O(eps/h) relative -- more than the 1e-12 /
+    // 1e-14 parity bar at h = 1/4000.  With identical J the rest is well conditioned.
+    double J00 = __dmul_rn(X[0], tg.gp[q][0][0]), J01 = __dmul_rn(X[0], tg.gp[q][0][1]);
+    double J10 = __dmul_rn(Y[0], tg.gp[q][0][0]), J11 = __dmul_rn(Y[0], tg.gp[q][0][1]);
+#pragma unroll
+    for (int n = 1; n < GK; n++) {
+        J00 = __dadd_rn(J00, __dmul_rn(X[n], tg.gp[q][n][0])); J01 = __dadd_rn(J01, __dmul_rn(X[n], tg.gp[q][n][1]));
+        J10 = __dadd_rn(J10, __dmul_rn(Y[n], tg.gp[q][n][0])); J11 = __dadd_rn(J11, __dmul_rn(Y[n], tg.gp[q][n][1]));
+    }
+    // Jacobian(Val{2}): src/FElements.jl:120-129
+    const double d = __dsub_rn(__dmul_rn(J00, J11), __dmul_rn(J10, J01));
+    JxW = fmul<S>(d, tg.w[q]);                                // JxW = J * weight(qp)
+    // bfungrad: src/QPIterators.jl:132-140 -- gradpar / Jac == (Jac' \ g)', two quotients by det per basis function
+    const SharedDivisor<S> div(d);
+#pragma unroll
+    for (int n = 0; n < BK; n++) {
+        gx[n] = div(fsub<S>(fmul<S>(J11, tb.gp[q][n][0]), fmul<S>(J10, tb.gp[q][n][1])));
+        gy[n] = div(fsub<S>(fmul<S>(J00, tb.gp[q][n][1]), fmul<S>(J01, tb.gp[q][n][0])));
+    }
+}
+
 template <int BK, int NQ> struct Geo {
     double gx[NQ][BK], gy[NQ][BK];
     double JxW[NQ];
@@ -50,31 +93,32 @@ template <int BK, int NQ> struct Geo {
 template <bool S, int GK, int BK, int NQ>
 __device__ __forceinline__ void geo_compute(const double (&X)[GK], const double (&Y)[GK], Geo<BK, NQ> &G)
 {
-    const QTab &tg = c_tab[kind_slot(GK)];
-    const QTab &tb = c_tab[kind_slot(BK)];
 #pragma unroll
-    for (int q = 0; q < NQ; q++) {
-        // _jac: src/FElements.jl:148-156 -- J = sum_n x_n (outer) dN_n/dxi, node order, first term assigned.
-        // ALWAYS evaluated without FMA contraction: the sum cancels from O(1) to O(h), so any other
-        // rounding sequence differs from the reference by O(eps/h) relative -- more than the 1e-12 /
-        // 1e-14 parity bar at h = 1/4000.  With identical J the rest is well conditioned.
-        double J00 = __dmul_rn(X[0], tg.gp[q][0][0]), J01 = __dmul_rn(X[0], tg.gp[q][0][1]);
-        double J10 = __dmul_rn(Y[0], tg.gp[q][0][0]), J11 = __dmul_rn(Y[0], tg.gp[q][0][1]);
-#pragma unroll
-        for (int n = 1; n < GK; n++) {
-            J00 = __dadd_rn(J00, __dmul_rn(X[n], tg.gp[q][n][0])); J01 = __dadd_rn(J01, __dmul_rn(X[n], tg.gp[q][n][1]));
-            J10 = __dadd_rn(J10, __dmul_rn(Y[n], tg.gp[q][n][0])); J11 = __dadd_rn(J11, __dmul_rn(Y[n], tg.gp[q][n][1]));
-        }
-        // Jacobian(Val{2}): src/FElements.jl:120-129
-        const double d = __dsub_rn(__dmul_rn(J00, J11), __dmul_rn(J10, J01));
-        G.JxW[q] = fmul<S>(d, tg.w[q]);                       // JxW = J * weight(qp)
-        // bfungrad: src/QPIterators.jl:132-140 -- gradpar / Jac == (Jac' \ g)', two true divisions
-#pragma unroll
-        for (int n = 0; n < BK; n++) {
-            G.gx[q][n] = fdiv<S>(fsub<S>(fmul<S>(J11, tb.gp[q][n][0]), fmul<S>(J10, tb.gp[q][n][1])), d);
-            G.gy[q][n] = fdiv<S>(fsub<S>(fmul<S>(J00, tb.gp[q][n][1]), fmul<S>(J01, tb.gp[q][n][0])), d);
-        }
+    for (int q = 0; q < NQ; q++) geo_qp<S, GK, BK>(X, Y, q, G.gx[q], G.gy[q], G.JxW[q]);
+}
+
+// Generic element driver: all quadrature points' gradients in registers, then the owned columns one
+// by one.  emit.template col<J>(out) receives column J of the element matrix.
+template <class F, bool S, class Emit, int J>
+__device__ __forceinline__ void element_column(const Geo<F::BK, F::NQ> &G, uint32_t m, Emit &emit)
+{
+    if (m & (1u << J)) {
+        double out[F::ND];
+        F::template column<S, J>(G, out);
+        emit.template col<J>(out);
     }
+}
+template <class F, bool S, class Emit, int... Js>
+__device__ __forceinline__ void element_columns(std::integer_sequence<int, Js...>, const Geo<F::BK, F::NQ> &G, uint32_t m, Emit &emit)
+{
+    (element_column<F, S, Emit, Js>(G, m, emit), ...);
+}
+template <class F, bool S, class Emit>
+__device__ __forceinline__ void element_generic(const double (&X)[F::GK], const double (&Y)[F::GK], uint32_t m, Emit &emit)
+{
+    Geo<F::BK, F::NQ> G;
+    geo_compute<S, F::GK, F::BK, F::NQ>(X, Y, G);
+    element_columns<F, S, Emit>(std::make_integer_sequence<int, F::ND>{}, G, m, emit);
 }
 
 // where the dof numbers of an element come from (symbolic phase only)
@@ -90,6 +134,7 @@ struct DofSrc {
 //   mask(i,j)   is local entry (i,j) appended?       kidx(i,j)  its position in append order
 //   edofs()     combined element dof vector (0-based)
 //   column<S,J>()  column J of the element matrix, all quadrature points summed in order
+//   element<S>(X, Y, mask, emit)  whole element: emits the columns whose mask bit is set
 
 // B(g,k) and D*B of the elasticity / Stokes-gen kernels (examples/elasticity/stretch/t6.jl:42-58):
 // B(g,1) = (g1, 0, g2), B(g,2) = (0, g2, g1); the literal zero products are dropped (x + 0*D == x).
@@ -116,25 +161,48 @@ template <int VK, int NQ_> struct HeatForm {
 #pragma unroll
         for (int a = 0; a < VK; a++) d[a] = s.dof0[s.conn0[e * VK + a]];
     }
-    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<BK, NQ> &G, double (&out)[ND]) {
-        const double kappa = c_prm[0];
+    // The element matrix is bitwise symmetric (g_i.g_j: the two products commute, same sum order), so
+    // only the upper triangle is accumulated, quadrature point by quadrature point like the reference's
+    // loop; gradients of one point at a time keep the register footprint small.
+    template <class Emit, int J> __device__ __forceinline__ static void emit_col(const double (&K)[ND][ND], uint32_t m, Emit &emit) {
+        if (m & (1u << J)) {
+            double out[ND];
 #pragma unroll
-        for (int i = 0; i < ND; i++) {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-                const double t = fmul<S>(fadd<S>(fmul<S>(G.gx[q][i], G.gx[q][J]), fmul<S>(G.gy[q][i], G.gy[q][J])),
-                                         fmul<S>(kappa, G.JxW[q]));
-                acc = q == 0 ? t : fadd<S>(acc, t);
-            }
-            out[i] = acc;
+            for (int i = 0; i < ND; i++) out[i] = (i <= J) ? K[i][J] : K[J][i];
+            emit.template col<J>(out);
         }
+    }
+    template <class Emit, int... Js> __device__ __forceinline__ static void emit_cols(std::integer_sequence<int, Js...>, const double (&K)[ND][ND], uint32_t m, Emit &emit) {
+        (emit_col<Emit, Js>(K, m, emit), ...);
+    }
+    template <bool S, class Emit>
+    __device__ __forceinline__ static void element(const double (&X)[GK], const double (&Y)[GK], uint32_t m, Emit &emit) {
+        const double kappa = c_prm[0];
+        double K[ND][ND];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            double gx[BK], gy[BK], JxW;
+            geo_qp<S, GK, BK>(X, Y, q, gx, gy, JxW);
+            const double kJ = fmul<S>(kappa, JxW);
+#pragma unroll
+            for (int j = 0; j < ND; j++)
+#pragma unroll
+                for (int i = 0; i <= j; i++) {
+                    const double t = fmul<S>(fadd<S>(fmul<S>(gx[i], gx[j]), fmul<S>(gy[i], gy[j])), kJ);
+                    K[i][j] = q == 0 ? t : fadd<S>(K[i][j], t);
+                }
+        }
+        emit_cols<Emit>(std::make_integer_sequence<int, ND>{}, K, m, emit);
     }
 };
 
 // K2 elasticity: ke[i,j] += dot(D*B_j, B_i) * JxW               examples/elasticity/stretch/t6.jl:52-58
 template <int VK, int NQ_> struct ElasticityForm {
     static constexpr int ND = 2 * VK, NT = ND * ND, GK = VK, BK = VK, NQ = NQ_, GMESH = 0, NSPACES = 1;
+    template <bool S, class Emit>
+    __device__ __forceinline__ static void element(const double (&X)[GK], const double (&Y)[GK], uint32_t m, Emit &emit) {
+        element_generic<ElasticityForm<VK, NQ_>, S, Emit>(X, Y, m, emit);
+    }
     __host__ __device__ static constexpr bool mask(int, int) { return true; }
     __host__ __device__ static constexpr int kidx(int i, int j) { return j * ND + i; }
     __device__ static void edofs(const DofSrc &s, int64_t e, int32_t (&d)[ND]) {
@@ -172,6 +240,10 @@ template <int VK, int NQ_> struct ElasticityForm {
 template <bool VECLAP_ALT> struct Stokes2Form {
     static constexpr int VK = 6, PK = 3, NQ = 3;
     static constexpr int ND = 15, NT = 144 + 36 + 36, GK = 6, BK = 6, GMESH = 0, NSPACES = 2;
+    template <bool S, class Emit>
+    __device__ __forceinline__ static void element(const double (&X)[GK], const double (&Y)[GK], uint32_t m, Emit &emit) {
+        element_generic<Stokes2Form<VECLAP_ALT>, S, Emit>(X, Y, m, emit);
+    }
     __host__ __device__ static constexpr bool mask(int i, int j) { return !(i >= 12 && j >= 12); }
     __host__ __device__ static constexpr int kidx(int i, int j) {
         return (i < 12 && j < 12) ? j * 12 + i                       // assemble!(ass, kuu)
@@ -256,6 +328,10 @@ template <bool VECLAP_ALT> struct Stokes2Form {
 template <bool VECLAP> struct Stokes3Form {
     static constexpr int VK = 6, PK = 3, NQ = 3;
     static constexpr int ND = 15, NT = VECLAP ? 144 : 216, GK = 3, BK = 6, GMESH = 1, NSPACES = 3;
+    template <bool S, class Emit>
+    __device__ __forceinline__ static void element(const double (&X)[GK], const double (&Y)[GK], uint32_t m, Emit &emit) {
+        element_generic<Stokes3Form<VECLAP>, S, Emit>(X, Y, m, emit);
+    }
     __host__ __device__ static constexpr bool mask(int i, int j) {
         if (i >= 12 && j >= 12) return false;
         if (VECLAP && ((i < 6 && j >= 6 && j < 12) || (j < 6 && i >= 6 && i < 12))) return false;

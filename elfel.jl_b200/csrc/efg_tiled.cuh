@@ -23,28 +23,34 @@
 #define TL_MAXND 16
 
 struct TileDescFull {
-    int64_t slot0;          // first tile-order slot
-    int64_t gidx0;          // first gather index
+    int64_t slot0;          // first tile-order slot            (symbolic phase only)
+    int64_t gidx0;          // first tile-order contribution    (symbolic phase only)
     int64_t elem0;          // first tile element (index into tconn/tmask)
+    int64_t meta0;          // byte offset of the tile's metadata block (16-byte aligned)
     int32_t nelem;          // tile elements incl. halo
     int32_t nslot;          // owned nonzeros
-    int32_t run0, nrun;     // runs
+    int32_t nrun;           // runs of nonzeros contiguous in nzval
     int32_t nq;             // staged columns (= stage row stride)
+    int32_t ncontrib;       // contributions to the owned nonzeros
+    int32_t meta_bytes;     // size of the metadata block (multiple of 16)
+    int32_t run0;           // first run (symbolic phase only)
     int32_t pad_;
     uint16_t qbase[TL_MAXND + 1]; // qbase[r] = first staged column of "r-th owned column of an element"
     uint16_t pad2_[3];
 };
-
 static_assert(sizeof(TileDescFull) % 8 == 0, "TileDescFull is copied as 8-byte words");
+
+// metadata block of a tile: [goff: u16 x (nslot+1)] [gidx: u16 x ncontrib] [runs: TileRun x nrun], each part 16-byte aligned
+__host__ __device__ static inline int tl_align16(int b) { return (b + 15) & ~15; }
+__host__ __device__ static inline int tl_meta_goff_bytes(int nslot) { return tl_align16(2 * (nslot + 1)); }
+__host__ __device__ static inline int tl_meta_gidx_bytes(int nc) { return tl_align16(2 * nc); }
 
 struct TiledData {
     DevBuf<TileDescFull> tiles;
-    DevBuf<TileRun> runs;
     DevBuf<int32_t> tconn;
     DevBuf<uint16_t> tmask;
-    DevBuf<uint8_t> gcnt;
-    DevBuf<uint16_t> gidx;
-    int64_t ntelem = 0, ncontrib = 0, nruns = 0;
+    DevBuf<unsigned char> meta;  // per-tile metadata blocks (bulk-copied to shared memory by the numeric kernel)
+    int64_t ntelem = 0, ncontrib = 0, nruns = 0, meta_bytes = 0;
     int smem_bytes = 0;
     int block = 256;
 };
@@ -357,7 +363,8 @@ __global__ void k_tl_tconn(const uint32_t *__restrict__ order, int64_t n, const 
     }
 }
 
-// per owned tile column: contribution counts per slot + stage indices in append order
+// per owned tile column: start offset of every slot's contributions (goff) + the stage index of
+// every contribution in append order (gidx), written into the owning tile's metadata block
 template <class F>
 __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint32_t *__restrict__ tcols, int64_t nowned,
                                   const uint32_t *__restrict__ adjptr, const uint32_t *__restrict__ adj, const int32_t *__restrict__ edof,
@@ -365,7 +372,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                                   const uint64_t *__restrict__ telem_key, const int64_t *__restrict__ telem_ptr,
                                   const uint16_t *__restrict__ mask, const uint32_t *__restrict__ newpos,
                                   const TileDescFull *__restrict__ tiles, const int64_t *__restrict__ tcol_slot, const int64_t *__restrict__ tcol_gidx,
-                                  uint8_t *__restrict__ gcnt, uint16_t *__restrict__ gidx, int *__restrict__ err)
+                                  unsigned char *__restrict__ meta, int *__restrict__ err)
 {
     GRID_STRIDE(k, nowned) {
         const uint32_t T = tkeys[k], cl = tcols[k];
@@ -373,6 +380,9 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
         const int nr = (int)(colptr0[cl + 1] - r0);
         const TileDescFull &td = tiles[T];
         const int64_t g0 = telem_ptr[T], g1 = telem_ptr[T + 1];
+        uint16_t *__restrict__ goff = reinterpret_cast<uint16_t *>(meta + td.meta0) + (tcol_slot[k] - td.slot0);
+        uint16_t *__restrict__ gidx = reinterpret_cast<uint16_t *>(meta + td.meta0 + tl_meta_goff_bytes(td.nslot));
+        const uint32_t gbase = (uint32_t)(tcol_gidx[k] - td.gidx0);
         uint16_t off[TL_CAP];
         for (int t = 0; t < nr; t++) off[t] = 0;
         const uint32_t a0 = adjptr[cl], a1 = adjptr[cl + 1];
@@ -389,22 +399,19 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                 off[lo]++;
             }
         }
-        const int64_t sbase = tcol_slot[k];
-        int run = 0;
+        uint32_t run = gbase;
         for (int t = 0; t < nr; t++) {
-            const int c = off[t];
-            if (c > 255) *err = 3;
-            gcnt[sbase + t] = (uint8_t)c;
+            const uint32_t c = off[t];
+            if (run + c > 65535u) *err = 3;
+            goff[t] = (uint16_t)run;
             off[t] = (uint16_t)run;
             run += c;
         }
-        // pass B: stage indices, append order
-        const int64_t gb = tcol_gidx[k];
+        // pass B: stage indices, append order (ascending element, column-major inside an element)
         for (uint32_t p = a0; p < a1; p++) {
             const uint32_t t = adj[p];
             const uint32_t e = t / F::ND;
             const int lj = (int)(t % F::ND);
-            // tile element (T, e)
             const uint64_t want = ((uint64_t)T << 32) | e;
             int64_t lo = g0, hi = g1;
             while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (telem_key[mid] < want) lo = mid + 1; else hi = mid; }
@@ -419,18 +426,34 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                 while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (rowval[r0 + mid] < r) l2 = mid + 1; else h2 = mid; }
                 const uint32_t sidx = (uint32_t)i * (uint32_t)td.nq + q;
                 if (sidx > 65535u) *err = 4;
-                gidx[gb + off[l2]] = (uint16_t)sidx;
+                gidx[off[l2]] = (uint16_t)sidx;
                 off[l2]++;
             }
         }
     }
 }
 
+// terminal goff entry + the tile's runs into its metadata block
+__global__ void k_tl_meta_finish(int ntiles, const TileDescFull *__restrict__ tiles, const TileRun *__restrict__ runs, unsigned char *__restrict__ meta)
+{
+    GRID_STRIDE(T, ntiles) {
+        const TileDescFull &td = tiles[T];
+        if (td.meta_bytes == 0) continue;
+        reinterpret_cast<uint16_t *>(meta + td.meta0)[td.nslot] = (uint16_t)td.ncontrib;
+        TileRun *dst = reinterpret_cast<TileRun *>(meta + td.meta0 + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
+        for (int r = 0; r < td.nrun; r++) dst[r] = runs[td.run0 + r];
+    }
+}
+__global__ void k_tl_tiles_meta0(int ntiles, const int64_t *__restrict__ meta_off, TileDescFull *__restrict__ tiles)
+{
+    GRID_STRIDE(T, ntiles) tiles[T].meta0 = meta_off[T];
+}
+
 __global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ tcol_slot,
                                 const int64_t *__restrict__ tcol_gidx, const int64_t *__restrict__ telem_ptr,
-                                const int64_t *__restrict__ run_of_k /* inclusive-run index per k: exclusive scan of flags */,
+                                const int64_t *__restrict__ run_of_k /* exclusive scan of run-head flags */,
                                 int64_t nowned, int64_t nruns, const uint32_t *__restrict__ pc_hist, TileDescFull *__restrict__ tiles,
-                                int32_t *__restrict__ maxima /* nq, nslot, nelem, nrun */)
+                                int64_t *__restrict__ meta_bytes, int32_t *__restrict__ maxima /* smem, nq*nd, ncontrib, nelem */)
 {
     GRID_STRIDE(T, ntiles) {
         TileDescFull d;
@@ -438,6 +461,8 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ 
         d.slot0 = tcol_slot[k0];
         d.nslot = (int32_t)(tcol_slot[k1] - tcol_slot[k0]);
         d.gidx0 = tcol_gidx[k0];
+        const int64_t nc = tcol_gidx[k1] - tcol_gidx[k0];
+        d.ncontrib = (int32_t)(nc > 0x7fffffff ? 0x7fffffff : nc);
         d.elem0 = telem_ptr[T];
         d.nelem = (int32_t)(telem_ptr[T + 1] - telem_ptr[T]);
         const int64_t r0 = (k0 < nowned) ? run_of_k[k0] : nruns, r1 = (k1 < nowned) ? run_of_k[k1] : nruns;
@@ -448,53 +473,64 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ 
         uint32_t acc = 0;
         for (int pc = 16; pc >= 0; pc--) { above[pc] = acc; acc += pc_hist[(int64_t)T * 17 + pc]; } // above[pc] = #elements with popcount > pc
         uint32_t q = 0;
-        for (int r = 0; r <= TL_MAXND; r++) { d.qbase[r] = (uint16_t)q; if (r < TL_MAXND) q += above[r]; }
-        d.nq = (int32_t)d.qbase[nd];
+        for (int r = 0; r <= TL_MAXND; r++) { d.qbase[r] = (uint16_t)(q > 65535u ? 65535u : q); if (r < TL_MAXND) q += above[r]; }
+        d.nq = (int32_t)q;
+        d.meta_bytes = d.nslot > 0 ? tl_meta_goff_bytes(d.nslot) + tl_meta_gidx_bytes(d.ncontrib) + d.nrun * (int)sizeof(TileRun) : 0;
+        d.meta0 = 0;
         d.pad_ = 0; d.pad2_[0] = d.pad2_[1] = d.pad2_[2] = 0;
         tiles[T] = d;
-        atomicMax(&maxima[0], d.nq); atomicMax(&maxima[1], d.nslot); atomicMax(&maxima[2], d.nelem); atomicMax(&maxima[3], d.nrun);
+        meta_bytes[T] = d.meta_bytes;
+        const int64_t smem = (int64_t)tl_align16(d.nq * nd * 8) + d.meta_bytes;
+        atomicMax(&maxima[0], (int32_t)(smem > 0x7fffffff ? 0x7fffffff : smem));
+        atomicMax(&maxima[1], (int32_t)((int64_t)d.nq * nd > 0x7fffffff ? 0x7fffffff : d.nq * nd));
+        atomicMax(&maxima[2], d.ncontrib); atomicMax(&maxima[3], d.nelem);
     }
 }
 
 // ---- numeric kernel ---------------------------------------------------------------------------------
-template <class F, bool S, int J>
-__device__ __forceinline__ void tl_stage_column(const Geo<F::BK, F::NQ> &G, uint32_t m, const uint16_t *__restrict__ qbase, uint32_t le, int nq,
-                                                double *__restrict__ stage)
-{
-    if (m & (1u << J)) {
-        double out[F::ND];
-        F::template column<S, J>(G, out);
+__device__ __forceinline__ uint32_t tl_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <class F> struct StageEmit {
+    double *__restrict__ stage;
+    const uint16_t *__restrict__ qbase;
+    uint32_t m, le;
+    int nq;
+    template <int J> __device__ __forceinline__ void col(const double (&out)[F::ND]) {
         const uint32_t q = qbase[__popc(m & ((1u << J) - 1u))] + le;
 #pragma unroll
         for (int i = 0; i < F::ND; i++)
             if (F::mask(i, J)) stage[i * nq + q] = out[i];
     }
-}
-template <class F, bool S, int... Js>
-__device__ __forceinline__ void tl_stage_all(std::integer_sequence<int, Js...>, const Geo<F::BK, F::NQ> &G, uint32_t m,
-                                             const uint16_t *__restrict__ qbase, uint32_t le, int nq, double *__restrict__ stage)
-{
-    (tl_stage_column<F, S, Js>(G, m, qbase, le, nq, stage), ...);
-}
+};
 
 template <class F, bool S, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_tl_numeric(const TileDescFull *__restrict__ tiles, const TileRun *__restrict__ runs,
-                                                      const int32_t *__restrict__ tconn, const uint16_t *__restrict__ tmask,
-                                                      const double2 *__restrict__ xy, const uint8_t *__restrict__ gcnt,
-                                                      const uint16_t *__restrict__ gidx, double *__restrict__ nzval)
+__global__ void __launch_bounds__(BLOCK, 2) k_tl_numeric(const TileDescFull *__restrict__ tiles, const int32_t *__restrict__ tconn,
+                                                         const uint16_t *__restrict__ tmask, const double2 *__restrict__ xy,
+                                                         const unsigned char *__restrict__ meta, double *__restrict__ nzval)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDescFull td;
-    __shared__ int warp_tot[BLOCK / 32];
+    __shared__ __align__(8) unsigned long long bar;
     const int tid = threadIdx.x;
     if (tid < (int)(sizeof(TileDescFull) / 8)) reinterpret_cast<int64_t *>(&td)[tid] = reinterpret_cast<const int64_t *>(&tiles[blockIdx.x])[tid];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tl_smem_addr(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
-    double *stage = reinterpret_cast<double *>(smem_raw);
+    if (td.nslot == 0) return;
     const int nq = td.nq;
-    TileRun *srun = reinterpret_cast<TileRun *>(stage + (size_t)F::ND * nq);
-    for (int r = tid; r < td.nrun; r += BLOCK) srun[r] = runs[td.run0 + r];
+    double *stage = reinterpret_cast<double *>(smem_raw);
+    unsigned char *smeta = smem_raw + tl_align16(F::ND * nq * 8);
+    // TMA bulk copy of the tile's gather metadata; it lands while phase 1 computes
+    if (tid == 0) {
+        const uint32_t b = tl_smem_addr(&bar);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((uint32_t)td.meta_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(tl_smem_addr(smeta)), "l"(meta + td.meta0), "r"((uint32_t)td.meta_bytes), "r"(b) : "memory");
+    }
 
-    // phase 1: element matrices of the owned columns -> stage
+    // phase 1: one thread per tile element: owned columns of the element matrix -> stage
     for (int le = tid; le < td.nelem; le += BLOCK) {
         const int64_t g = td.elem0 + le;
         double X[F::GK], Y[F::GK];
@@ -503,63 +539,53 @@ __global__ void __launch_bounds__(BLOCK) k_tl_numeric(const TileDescFull *__rest
             const double2 p = __ldg(&xy[tconn[g * F::GK + a]]);
             X[a] = p.x; Y[a] = p.y;
         }
-        const uint32_t m = tmask[g];
-        Geo<F::BK, F::NQ> G;
-        geo_compute<S, F::GK, F::BK, F::NQ>(X, Y, G);
-        tl_stage_all<F, S>(std::make_integer_sequence<int, F::ND>{}, G, m, td.qbase, (uint32_t)le, nq, stage);
+        StageEmit<F> emit{stage, td.qbase, (uint32_t)tmask[g], (uint32_t)le, nq};
+        F::template element<S>(X, Y, emit.m, emit);
     }
     __syncthreads();
+    {   // metadata has landed?
+        const uint32_t b = tl_smem_addr(&bar);
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(b) : "memory");
+    }
 
-    // phase 2: every owned nonzero = left-to-right sum of its contributions (append order)
+    // phase 2: every owned nonzero = left-to-right sum of its contributions (append order), stored once
+    const uint16_t *goff = reinterpret_cast<const uint16_t *>(smeta);
+    const uint16_t *gi = reinterpret_cast<const uint16_t *>(smeta + tl_meta_goff_bytes(td.nslot));
+    const TileRun *srun = reinterpret_cast<const TileRun *>(smeta + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
     const int lane = tid & 31, warp = tid >> 5;
     constexpr int NW = BLOCK / 32;
     const int nslot = td.nslot;
-    const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // slots per warp, multiple of 32
+    const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // contiguous slots per warp, multiple of 32
     const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
-    const uint8_t *cnt = gcnt + td.slot0;
-    int tot = 0;
-    for (int s = w0 + lane; s < w1; s += 32) tot += cnt[s];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) warp_tot[warp] = tot;
-    __syncthreads();
-    int wbase = 0;
-    for (int w = 0; w < warp; w++) wbase += warp_tot[w];
-    const uint16_t *gi = gidx + td.gidx0;
-    int rcur = 0;
-    for (int s0 = w0; s0 < w1; s0 += 32) {
-        const int s = s0 + lane;
-        const int c = (s < w1) ? cnt[s] : 0;
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+    if (w0 >= w1) return;
+    int r = 0;
+    {   // run containing slot w0 (same search in every lane)
+        int lo = 0, hi = td.nrun - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= w0) lo = mid; else hi = mid - 1; }
+        r = lo;
+    }
+    int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
+    int64_t rnz = srun[r].nz0;
+    for (int s = w0 + lane; s < w1; s += 32) {
+        const int o0 = goff[s], o1 = goff[s + 1];
+        double acc = 0.0;
+        if (o1 > o0) {
+            acc = stage[gi[o0]];
+            for (int k = o0 + 1; k < o1; k++) acc = __dadd_rn(acc, stage[gi[k]]);
         }
-        const int off = wbase + incl - c;
-        wbase += __shfl_sync(0xffffffffu, incl, 31);
-        if (s < w1) {
-            double acc = 0.0;
-            if (c > 0) {
-                acc = stage[gi[off]];
-                for (int k = 1; k < c; k++) acc = __dadd_rn(acc, stage[gi[off + k]]);
-            }
-            // destination: run containing tile slot s
-            if (!(s >= srun[rcur].s0 && s < srun[rcur].s0 + srun[rcur].len)) {
-                int lo = 0, hi = td.nrun - 1;
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
-                rcur = lo;
-            }
-            nzval[srun[rcur].nz0 + (s - srun[rcur].s0)] = acc;
-        }
+        while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
+        nzval[rnz + (s - rs0)] = acc;
     }
 }
 
 // ---- host: symbolic ---------------------------------------------------------------------------------
 template <class F> static int tl_default_tile_elems()
 {
-    // stage bytes per owned element-equivalent = ND*ND*8; aim at ~72 KB of stage per CTA
-    int te = (72 * 1024) / (F::ND * F::ND * 8);
+    // shared memory per owned element-equivalent: stage ND*ND*8 + gather metadata ~ NT*2 + 3*ND*ND;
+    // aim at ~96 KB per CTA so two CTAs share an SM
+    int te = (96 * 1024) / (F::ND * F::ND * 8 + F::NT * 2 + 3 * F::ND * F::ND);
     if (te > 512) te = 512;
     if (te < 32) te = 32;
     return te & ~7;
@@ -687,10 +713,11 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     }
     const int64_t nruns = tl_read(ctx, runidx.p + nowned);
     td->nruns = nruns;
-    td->runs.alloc(pool, (size_t)(nruns > 0 ? nruns : 1));
+    DevBuf<TileRun> runs;
+    runs.alloc(pool, (size_t)(nruns > 0 ? nruns : 1));
     run_firstk.alloc(pool, (size_t)(nruns > 0 ? nruns : 1));
-    LAUNCH(ctx, k_tl_run_fill, grid_for(nowned, 256), 256, 0, rflag.p, runidx.p, tkeys.p, tcols.p, nowned, tcol_slot.p, tcol_ptr.p, colptr0.p, td->runs.p, run_firstk.p);
-    LAUNCH(ctx, k_tl_run_len, grid_for(nruns, 256), 256, 0, run_firstk.p, nruns, nowned, tcol_slot.p, td->runs.p);
+    LAUNCH(ctx, k_tl_run_fill, grid_for(nowned, 256), 256, 0, rflag.p, runidx.p, tkeys.p, tcols.p, nowned, tcol_slot.p, tcol_ptr.p, colptr0.p, runs.p, run_firstk.p);
+    LAUNCH(ctx, k_tl_run_len, grid_for(nruns, 256), 256, 0, run_firstk.p, nruns, nowned, tcol_slot.p, runs.p);
 
     // T6: tile element lists (own + halo), masks, popcount-descending order inside a tile
     DevBuf<uint64_t> ek2;
@@ -731,38 +758,45 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     td->tmask.alloc(pool, (size_t)ntelem + 1);
     LAUNCH(ctx, k_tl_tconn<F::GK>, grid_for(ntelem, 256), 256, 0, order2.p, ntelem, telem_key.p, emask.p, gm.conn.p, td->tconn.p, td->tmask.p);
 
-    // tile descriptors
+    // tile descriptors + metadata block layout
     DevBuf<int32_t> maxima;
+    DevBuf<int64_t> mbytes, moff;
     maxima.alloc(pool, 4);
+    mbytes.alloc(pool, (size_t)ntiles + 1); moff.alloc(pool, (size_t)ntiles + 1);
     CUDA_CHECK(cudaMemsetAsync(maxima.p, 0, 4 * sizeof(int32_t), st));
+    CUDA_CHECK(cudaMemsetAsync(mbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     td->tiles.alloc(pool, (size_t)ntiles);
     LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tcol_ptr.p, tcol_slot.p, tcol_gidx.p, telem_ptr.p, runidx.p,
-           nowned, nruns, pc_hist.p, td->tiles.p, maxima.p);
+           nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
+    tl_excl_scan(ctx, mbytes.p, moff.p, (int64_t)ntiles + 1);
+    const int64_t meta_total = tl_read(ctx, moff.p + ntiles);
+    LAUNCH(ctx, k_tl_tiles_meta0, grid_for(ntiles, 256), 256, 0, ntiles, moff.p, td->tiles.p);
     int32_t hmax[4];
     CUDA_CHECK(cudaMemcpyAsync(hmax, maxima.p, sizeof hmax, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    ctx->tl.max_nq = hmax[0]; ctx->tl.max_nslot = hmax[1]; ctx->tl.max_nelem = hmax[2]; ctx->tl.max_nrun = hmax[3];
-    if ((int64_t)hmax[0] * ND > 65535)
-        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile stages %d columns x %d rows > 65535 entries; lower EFG_OPT_TILE_ELEMS", hmax[0], ND);
-    const size_t smem = (size_t)hmax[0] * ND * sizeof(double) + (size_t)hmax[3] * sizeof(TileRun);
-    if (smem > 220 * 1024)
-        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile needs %zu bytes of shared memory; lower EFG_OPT_TILE_ELEMS", smem);
-    td->smem_bytes = (int)smem;
+    ctx->tl.max_nq = hmax[1] / ND; ctx->tl.max_nslot = 0; ctx->tl.max_nelem = hmax[3]; ctx->tl.max_nrun = 0;
+    if (hmax[1] > 65535)
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile stages %d element-matrix entries (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[1]);
+    if (hmax[2] > 65535)
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile gathers %d contributions (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[2]);
+    if (hmax[0] > 225 * 1024)
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile needs %d bytes of shared memory; lower EFG_OPT_TILE_ELEMS", hmax[0]);
+    td->smem_bytes = hmax[0];
+    td->meta_bytes = meta_total;
 
-    // T8: gather lists
-    td->gcnt.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
-    td->gidx.alloc(pool, (size_t)(ncontrib > 0 ? ncontrib : 1));
+    // T8: gather lists into the metadata blocks
+    td->meta.alloc(pool, (size_t)(meta_total > 0 ? meta_total : 16));
     LAUNCH(ctx, k_tl_gather_build<F>, grid_for(nowned, 128), 128, 0, tkeys.p, tcols.p, nowned, adjptr.p, adj.p, edof.p, colptr0.p, ctx->rowval.p,
-           telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, tcol_slot.p, tcol_gidx.p, td->gcnt.p, td->gidx.p, err.p);
+           telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, tcol_slot.p, tcol_gidx.p, td->meta.p, err.p);
+    LAUNCH(ctx, k_tl_meta_finish, grid_for(ntiles, 128), 128, 0, ntiles, td->tiles.p, runs.p, td->meta.p);
     const int e2 = tl_read(ctx, err.p);
-    if (e2 == 3) efg_throw(EFG_ERR_LIMIT, "tiled path: a nonzero has more than 255 contributions; use EFG_OPT_PATH=1");
-    if (e2) efg_throw(EFG_ERR_LIMIT, "tiled path: internal stage index overflow (%d)", e2);
+    if (e2) efg_throw(EFG_ERR_LIMIT, "tiled path: a tile's gather list exceeds 16-bit offsets (%d); lower EFG_OPT_TILE_ELEMS", e2);
 
     ctx->nzval.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
     ctx->tl.ntiles = ntiles;
     ctx->tl.tile_elems = te;
     ctx->tl.sum_tile_elems = ntelem;
-    ctx->tl.numeric_bytes = ntelem * (F::GK * 4 + 2) + gm.nnodes * 16 + nnz * (1 + 8) + ncontrib * 2 + (int64_t)ntiles * sizeof(TileDescFull) + nruns * sizeof(TileRun);
+    ctx->tl.numeric_bytes = ntelem * (F::GK * 4 + 2) + gm.nnodes * 16 + meta_total + nnz * 8 + (int64_t)ntiles * sizeof(TileDescFull);
 }
 
 template <class F, bool S> static void tl_launch_numeric(efg_ctx *ctx)
@@ -773,8 +807,8 @@ template <class F, bool S> static void tl_launch_numeric(efg_ctx *ctx)
     auto kern = k_tl_numeric<F, S, BLOCK>;
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
     if (ctx->tl.ntiles > 0)
-        LAUNCH(ctx, kern, (unsigned)ctx->tl.ntiles, BLOCK, (size_t)td->smem_bytes, td->tiles.p, td->runs.p, td->tconn.p, td->tmask.p, gm.xy.p,
-               td->gcnt.p, td->gidx.p, ctx->nzval.p);
+        LAUNCH(ctx, kern, (unsigned)ctx->tl.ntiles, BLOCK, (size_t)td->smem_bytes, td->tiles.p, td->tconn.p, td->tmask.p, gm.xy.p,
+               td->meta.p, ctx->nzval.p);
     ctx->numeric_launches += 1;
 }
 

@@ -188,24 +188,15 @@ template <class F> void twopass_symbolic(efg_ctx *ctx)
 }
 
 // numeric kernel 1: all element matrices, Ke[k*nel + e] (coalesced across elements)
-template <class F, bool S>
-__global__ void __launch_bounds__(128) k_tp_elem_matrices(const int32_t *__restrict__ gconn, const double2 *__restrict__ gxy,
-                                                          int64_t nel, double *__restrict__ Ke);
-
-template <class F, bool S, int J>
-__device__ __forceinline__ void tp_store_column(const Geo<F::BK, F::NQ> &G, int64_t e, int64_t nel, double *__restrict__ Ke)
-{
-    double out[F::ND];
-    F::template column<S, J>(G, out);
+template <class F> struct KeEmit {
+    double *__restrict__ Ke;
+    int64_t e, nel;
+    template <int J> __device__ __forceinline__ void col(const double (&out)[F::ND]) {
 #pragma unroll
-    for (int i = 0; i < F::ND; i++)
-        if (F::mask(i, J)) Ke[(int64_t)F::kidx(i, J) * nel + e] = out[i];
-}
-template <class F, bool S, int... Js>
-__device__ __forceinline__ void tp_store_all(std::integer_sequence<int, Js...>, const Geo<F::BK, F::NQ> &G, int64_t e, int64_t nel, double *__restrict__ Ke)
-{
-    (tp_store_column<F, S, Js>(G, e, nel, Ke), ...);
-}
+        for (int i = 0; i < F::ND; i++)
+            if (F::mask(i, J)) Ke[(int64_t)F::kidx(i, J) * nel + e] = out[i];
+    }
+};
 
 template <class F, bool S>
 __global__ void __launch_bounds__(128) k_tp_elem_matrices(const int32_t *__restrict__ gconn, const double2 *__restrict__ gxy,
@@ -215,9 +206,8 @@ __global__ void __launch_bounds__(128) k_tp_elem_matrices(const int32_t *__restr
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < nel; e += stride) {
         double X[F::GK], Y[F::GK];
         load_xy<F::GK>(gconn, gxy, e, X, Y);
-        Geo<F::BK, F::NQ> G;
-        geo_compute<S, F::GK, F::BK, F::NQ>(X, Y, G);
-        tp_store_all<F, S>(std::make_integer_sequence<int, F::ND>{}, G, e, nel, Ke);
+        KeEmit<F> emit{Ke, e, nel};
+        F::template element<S>(X, Y, 0xffffffffu, emit);
     }
 }
 
