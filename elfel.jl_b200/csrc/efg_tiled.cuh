@@ -34,13 +34,15 @@ struct TileDescFull {
     int32_t ncontrib;       // contributions to the owned nonzeros
     int32_t meta_bytes;     // size of the metadata block (multiple of 16)
     int32_t run0;           // first run (symbolic phase only)
-    int32_t pad_;
+    int32_t nheavy;         // owned nonzeros with more than TL_LIGHT contributions
+    int64_t heavy0;         // first heavy entry in tile order (symbolic phase only)
     uint16_t qbase[TL_MAXND + 1]; // qbase[r] = first staged column of "r-th owned column of an element"
     uint16_t pad2_[3];
 };
 static_assert(sizeof(TileDescFull) % 8 == 0, "TileDescFull is copied as 8-byte words");
 
-// metadata block of a tile: [goff: u16 x (nslot+1)] [gidx: u16 x ncontrib] [runs: TileRun x nrun], each part 16-byte aligned
+// metadata block of a tile: [goff: u16 x (nslot+1)] [gidx: u16 x ncontrib] [runs: TileRun x nrun] [heavy: u16 x nheavy],
+// each part 16-byte aligned
 __host__ __device__ static inline int tl_align16(int b) { return (b + 15) & ~15; }
 __host__ __device__ static inline int tl_meta_goff_bytes(int nslot) { return tl_align16(2 * (nslot + 1)); }
 __host__ __device__ static inline int tl_meta_gidx_bytes(int nc) { return tl_align16(2 * nc); }
@@ -204,10 +206,11 @@ __global__ void k_tl_owner_pairs(const int32_t *__restrict__ edof, const int32_t
     }
 }
 
-// sorted, de-duplicated row list of one column (candidates enumerated from the adjacency)
-template <class F>
+// sorted, de-duplicated row list of one column (candidates enumerated from the adjacency);
+// COUNT additionally keeps the number of contributions of every row
+template <class F, bool COUNT>
 __device__ __forceinline__ int tl_column_rows(const uint32_t *__restrict__ adj, uint32_t a0, uint32_t a1,
-                                              const int32_t *__restrict__ edof, int32_t (&rows)[TL_CAP], int &ncontrib)
+                                              const int32_t *__restrict__ edof, int32_t (&rows)[TL_CAP], uint16_t *cnt, int &ncontrib)
 {
     int n = 0;
     ncontrib = 0;
@@ -221,27 +224,35 @@ __device__ __forceinline__ int tl_column_rows(const uint32_t *__restrict__ adj, 
             const int32_t r = edof[(int64_t)e * F::ND + i];
             int lo = 0, hi = n;
             while (lo < hi) { const int mid = (lo + hi) >> 1; if (rows[mid] < r) lo = mid + 1; else hi = mid; }
-            if (lo < n && rows[lo] == r) continue;
+            if (lo < n && rows[lo] == r) { if (COUNT) cnt[lo]++; continue; }
             if (n == TL_CAP) return -1;
-            for (int k = n; k > lo; k--) rows[k] = rows[k - 1];
+            for (int k = n; k > lo; k--) { rows[k] = rows[k - 1]; if (COUNT) cnt[k] = cnt[k - 1]; }
             rows[lo] = r;
+            if (COUNT) cnt[lo] = 1;
             n++;
         }
     }
     return n;
 }
 
+#define TL_LIGHT 2   // nonzeros with at most this many contributions take the straight-line gather path
+
 template <class F>
 __global__ void k_tl_col_count(const uint32_t *__restrict__ adjptr, const uint32_t *__restrict__ adj, const int32_t *__restrict__ edof,
-                               int64_t ncl, uint8_t *__restrict__ colcnt, uint16_t *__restrict__ ccnt, int *__restrict__ err)
+                               int64_t ncl, uint8_t *__restrict__ colcnt, uint16_t *__restrict__ ccnt, uint8_t *__restrict__ hcnt,
+                               int *__restrict__ err)
 {
     GRID_STRIDE(cl, ncl) {
         int32_t rows[TL_CAP];
+        uint16_t cnt[TL_CAP];
         int nc;
-        const int n = tl_column_rows<F>(adj, adjptr[cl], adjptr[cl + 1], edof, rows, nc);
-        if (n < 0 || nc > 65535) { *err = 2; colcnt[cl] = 0; ccnt[cl] = 0; continue; }
+        const int n = tl_column_rows<F, true>(adj, adjptr[cl], adjptr[cl + 1], edof, rows, cnt, nc);
+        if (n < 0 || nc > 65535) { *err = 2; colcnt[cl] = 0; ccnt[cl] = 0; hcnt[cl] = 0; continue; }
+        int h = 0;
+        for (int t = 0; t < n; t++) h += cnt[t] > TL_LIGHT;
         colcnt[cl] = (uint8_t)n;
         ccnt[cl] = (uint16_t)nc;
+        hcnt[cl] = (uint8_t)h;
     }
 }
 template <class F>
@@ -253,7 +264,7 @@ __global__ void k_tl_col_fill(const uint32_t *__restrict__ adjptr, const uint32_
         if (cl == ncl) continue;
         int32_t rows[TL_CAP];
         int nc;
-        const int n = tl_column_rows<F>(adj, adjptr[cl], adjptr[cl + 1], edof, rows, nc);
+        const int n = tl_column_rows<F, false>(adj, adjptr[cl], adjptr[cl + 1], edof, rows, nullptr, nc);
         const int64_t o = colptr0[cl];
         for (int k = 0; k < n; k++) rowval[o + k] = rows[k];
     }
@@ -372,7 +383,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                                   const uint64_t *__restrict__ telem_key, const int64_t *__restrict__ telem_ptr,
                                   const uint16_t *__restrict__ mask, const uint32_t *__restrict__ newpos,
                                   const TileDescFull *__restrict__ tiles, const int64_t *__restrict__ tcol_slot, const int64_t *__restrict__ tcol_gidx,
-                                  unsigned char *__restrict__ meta, int *__restrict__ err)
+                                  const int64_t *__restrict__ tcol_heavy, unsigned char *__restrict__ meta, int *__restrict__ err)
 {
     GRID_STRIDE(k, nowned) {
         const uint32_t T = tkeys[k], cl = tcols[k];
@@ -399,10 +410,15 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                 off[lo]++;
             }
         }
+        uint16_t *__restrict__ heavy = reinterpret_cast<uint16_t *>(meta + td.meta0 + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib) +
+                                                                   td.nrun * (int)sizeof(TileRun)) + (tcol_heavy[k] - td.heavy0);
+        const uint32_t sloc = (uint32_t)(tcol_slot[k] - td.slot0);
         uint32_t run = gbase;
+        int nh = 0;
         for (int t = 0; t < nr; t++) {
             const uint32_t c = off[t];
             if (run + c > 65535u) *err = 3;
+            if (c > TL_LIGHT) heavy[nh++] = (uint16_t)(sloc + t);
             goff[t] = (uint16_t)run;
             off[t] = (uint16_t)run;
             run += c;
@@ -450,7 +466,7 @@ __global__ void k_tl_tiles_meta0(int ntiles, const int64_t *__restrict__ meta_of
 }
 
 __global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ tcol_slot,
-                                const int64_t *__restrict__ tcol_gidx, const int64_t *__restrict__ telem_ptr,
+                                const int64_t *__restrict__ tcol_gidx, const int64_t *__restrict__ tcol_heavy, const int64_t *__restrict__ telem_ptr,
                                 const int64_t *__restrict__ run_of_k /* exclusive scan of run-head flags */,
                                 int64_t nowned, int64_t nruns, const uint32_t *__restrict__ pc_hist, TileDescFull *__restrict__ tiles,
                                 int64_t *__restrict__ meta_bytes, int32_t *__restrict__ maxima /* smem, nq*nd, ncontrib, nelem */)
@@ -463,6 +479,8 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ 
         d.gidx0 = tcol_gidx[k0];
         const int64_t nc = tcol_gidx[k1] - tcol_gidx[k0];
         d.ncontrib = (int32_t)(nc > 0x7fffffff ? 0x7fffffff : nc);
+        d.heavy0 = tcol_heavy[k0];
+        d.nheavy = (int32_t)(tcol_heavy[k1] - tcol_heavy[k0]);
         d.elem0 = telem_ptr[T];
         d.nelem = (int32_t)(telem_ptr[T + 1] - telem_ptr[T]);
         const int64_t r0 = (k0 < nowned) ? run_of_k[k0] : nruns, r1 = (k1 < nowned) ? run_of_k[k1] : nruns;
@@ -475,9 +493,9 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ 
         uint32_t q = 0;
         for (int r = 0; r <= TL_MAXND; r++) { d.qbase[r] = (uint16_t)(q > 65535u ? 65535u : q); if (r < TL_MAXND) q += above[r]; }
         d.nq = (int32_t)q;
-        d.meta_bytes = d.nslot > 0 ? tl_meta_goff_bytes(d.nslot) + tl_meta_gidx_bytes(d.ncontrib) + d.nrun * (int)sizeof(TileRun) : 0;
+        d.meta_bytes = d.nslot > 0 ? tl_meta_goff_bytes(d.nslot) + tl_meta_gidx_bytes(d.ncontrib) + d.nrun * (int)sizeof(TileRun) + tl_align16(2 * d.nheavy) : 0;
         d.meta0 = 0;
-        d.pad_ = 0; d.pad2_[0] = d.pad2_[1] = d.pad2_[2] = 0;
+        d.pad2_[0] = d.pad2_[1] = d.pad2_[2] = 0;
         tiles[T] = d;
         meta_bytes[T] = d.meta_bytes;
         const int64_t smem = (int64_t)tl_align16(d.nq * nd * 8) + d.meta_bytes;
@@ -559,7 +577,6 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tl_numeric(const TileDescFull *__r
     const int nslot = td.nslot;
     const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // contiguous slots per warp, multiple of 32
     const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
-    if (w0 >= w1) return;
     int r = 0;
     {   // run containing slot w0 (same search in every lane)
         int lo = 0, hi = td.nrun - 1;
@@ -568,15 +585,45 @@ __global__ void __launch_bounds__(BLOCK, 2) k_tl_numeric(const TileDescFull *__r
     }
     int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
     int64_t rnz = srun[r].nz0;
-    for (int s = w0 + lane; s < w1; s += 32) {
-        const int o0 = goff[s], o1 = goff[s + 1];
-        double acc = 0.0;
-        if (o1 > o0) {
-            acc = stage[gi[o0]];
-            for (int k = o0 + 1; k < o1; k++) acc = __dadd_rn(acc, stage[gi[k]]);
+    // light nonzeros (<= TL_LIGHT contributions: all but the matrix diagonals of node patches): straight-line
+    // code, 4 independent slots in flight per lane to cover the shared-memory latency chain goff -> gidx -> stage
+    constexpr int U = 4;
+    for (int sb = w0; sb < w1; sb += 32 * U) {
+        int o0[U], c[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int s = sb + u * 32 + lane;
+            o0[u] = 0; c[u] = 0;
+            if (s < w1) { o0[u] = goff[s]; c[u] = (int)goff[s + 1] - o0[u]; }
         }
-        while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
-        nzval[rnz + (s - rs0)] = acc;
+        double acc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            acc[u] = 0.0;
+            if (c[u] >= 1 && c[u] <= TL_LIGHT) acc[u] = stage[gi[o0[u]]];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (c[u] == 2) acc[u] = __dadd_rn(acc[u], stage[gi[o0[u] + 1]]);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int s = sb + u * 32 + lane;
+            if (s < w1) {
+                while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
+                if (c[u] <= TL_LIGHT) nzval[rnz + (s - rs0)] = acc[u];
+            }
+        }
+    }
+    // heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum
+    const uint16_t *heavy = reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(srun) + td.nrun * (int)sizeof(TileRun));
+    for (int h = tid; h < td.nheavy; h += BLOCK) {
+        const int s = heavy[h];
+        const int o0 = goff[s], o1 = goff[s + 1];
+        double acc = stage[gi[o0]];
+        for (int k = o0 + 1; k < o1; k++) acc = __dadd_rn(acc, stage[gi[k]]);
+        int lo = 0, hi = td.nrun - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
+        nzval[srun[lo].nz0 + (s - srun[lo].s0)] = acc;
     }
 }
 
@@ -660,13 +707,14 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     const int64_t npairs = (int64_t)tl_read(ctx, adjptr.p + ncl);
 
     // T4: CSC pattern
-    DevBuf<uint8_t> colcnt;
+    DevBuf<uint8_t> colcnt, hcnt;
     DevBuf<uint16_t> ccnt;
     DevBuf<int64_t> colptr0;
-    colcnt.alloc(pool, (size_t)ncl + 1); ccnt.alloc(pool, (size_t)ncl + 1); colptr0.alloc(pool, (size_t)ncl + 1);
+    colcnt.alloc(pool, (size_t)ncl + 1); hcnt.alloc(pool, (size_t)ncl + 1); ccnt.alloc(pool, (size_t)ncl + 1); colptr0.alloc(pool, (size_t)ncl + 1);
     CUDA_CHECK(cudaMemsetAsync(colcnt.p, 0, (size_t)ncl + 1, st));
+    CUDA_CHECK(cudaMemsetAsync(hcnt.p, 0, (size_t)ncl + 1, st));
     CUDA_CHECK(cudaMemsetAsync(ccnt.p, 0, ((size_t)ncl + 1) * 2, st));
-    LAUNCH(ctx, k_tl_col_count<F>, grid_for(ncl, 128), 128, 0, adjptr.p, adj.p, edof.p, ncl, colcnt.p, ccnt.p, err.p);
+    LAUNCH(ctx, k_tl_col_count<F>, grid_for(ncl, 128), 128, 0, adjptr.p, adj.p, edof.p, ncl, colcnt.p, ccnt.p, hcnt.p, err.p);
     if (tl_read(ctx, err.p))
         efg_throw(EFG_ERR_LIMIT, "tiled path: a matrix column has more than %d distinct rows (node valence too high); use EFG_OPT_PATH=1", TL_CAP);
     {
@@ -688,8 +736,8 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
         LAUNCH(ctx, k_tl_tilecol_keys, grid_for(ncl, 256), 256, 0, owner.p, ncl, ntiles, k1.p, v1.p);
         tl_sort_pairs(ctx, k1.p, tkeys.p, v1.p, tcols.p, ncl, bits_for(ntiles));
     }
-    DevBuf<int64_t> tcol_ptr, tcol_slot, tcol_gidx;
-    tcol_ptr.alloc(pool, (size_t)ntiles + 1); tcol_slot.alloc(pool, (size_t)ncl + 2); tcol_gidx.alloc(pool, (size_t)ncl + 2);
+    DevBuf<int64_t> tcol_ptr, tcol_slot, tcol_gidx, tcol_heavy;
+    tcol_ptr.alloc(pool, (size_t)ntiles + 1); tcol_slot.alloc(pool, (size_t)ncl + 2); tcol_gidx.alloc(pool, (size_t)ncl + 2); tcol_heavy.alloc(pool, (size_t)ncl + 2);
     LAUNCH(ctx, k_tl_lower_bounds<uint32_t>, grid_for(ntiles + 1, 256), 256, 0, tkeys.p, ncl, ntiles, 0, tcol_ptr.p);
     const int64_t nowned = tl_read(ctx, tcol_ptr.p + ntiles);
     {
@@ -698,6 +746,8 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
         tl_excl_scan(ctx, it8, tcol_slot.p, nowned + 1);
         cub::TransformInputIterator<int64_t, GatherU16, cub::CountingInputIterator<int64_t>> it16(cnt_it, GatherU16{ccnt.p, tcols.p, nowned});
         tl_excl_scan(ctx, it16, tcol_gidx.p, nowned + 1);
+        cub::TransformInputIterator<int64_t, GatherU8, cub::CountingInputIterator<int64_t>> ith(cnt_it, GatherU8{hcnt.p, tcols.p, nowned});
+        tl_excl_scan(ctx, ith, tcol_heavy.p, nowned + 1);
     }
     const int64_t ncontrib = tl_read(ctx, tcol_gidx.p + nowned);
     td->ncontrib = ncontrib;
@@ -766,7 +816,7 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     CUDA_CHECK(cudaMemsetAsync(maxima.p, 0, 4 * sizeof(int32_t), st));
     CUDA_CHECK(cudaMemsetAsync(mbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     td->tiles.alloc(pool, (size_t)ntiles);
-    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tcol_ptr.p, tcol_slot.p, tcol_gidx.p, telem_ptr.p, runidx.p,
+    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tcol_ptr.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
            nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
     tl_excl_scan(ctx, mbytes.p, moff.p, (int64_t)ntiles + 1);
     const int64_t meta_total = tl_read(ctx, moff.p + ntiles);
@@ -787,7 +837,7 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     // T8: gather lists into the metadata blocks
     td->meta.alloc(pool, (size_t)(meta_total > 0 ? meta_total : 16));
     LAUNCH(ctx, k_tl_gather_build<F>, grid_for(nowned, 128), 128, 0, tkeys.p, tcols.p, nowned, adjptr.p, adj.p, edof.p, colptr0.p, ctx->rowval.p,
-           telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, tcol_slot.p, tcol_gidx.p, td->meta.p, err.p);
+           telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, td->meta.p, err.p);
     LAUNCH(ctx, k_tl_meta_finish, grid_for(ntiles, 128), 128, 0, ntiles, td->tiles.p, runs.p, td->meta.p);
     const int e2 = tl_read(ctx, err.p);
     if (e2) efg_throw(EFG_ERR_LIMIT, "tiled path: a tile's gather list exceeds 16-bit offsets (%d); lower EFG_OPT_TILE_ELEMS", e2);
