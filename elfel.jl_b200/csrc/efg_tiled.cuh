@@ -521,109 +521,184 @@ template <class F> struct StageEmit {
     }
 };
 
-template <class F, bool S, int BLOCK>
-__global__ void __launch_bounds__(BLOCK, 2) k_tl_numeric(const TileDescFull *__restrict__ tiles, const int32_t *__restrict__ tconn,
-                                                         const uint16_t *__restrict__ tmask, const double2 *__restrict__ xy,
-                                                         const unsigned char *__restrict__ meta, double *__restrict__ nzval)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// Persistent CTAs (gridDim.x = CTAs resident on the device), tile t handled by CTA t mod gridDim.x.
+// Software pipeline across tiles: the descriptor is fetched two tiles ahead, the connectivity of the
+// next tile's element is loaded into registers before the mid-tile barrier and its coordinates during
+// the gather phase, so phase 1 never waits on a dependent global load; the gather metadata of the
+// current tile arrives by TMA bulk copy while phase 1 computes.
+template <class F, bool S, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *__restrict__ tiles, int ntiles,
+                                                            const int32_t *__restrict__ tconn, const uint16_t *__restrict__ tmask,
+                                                            const double2 *__restrict__ xy, const unsigned char *__restrict__ meta,
+                                                            double *__restrict__ nzval)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ TileDescFull td;
+    __shared__ TileDescFull tds[3];
     __shared__ __align__(8) unsigned long long bar;
-    const int tid = threadIdx.x;
-    if (tid < (int)(sizeof(TileDescFull) / 8)) reinterpret_cast<int64_t *>(&td)[tid] = reinterpret_cast<const int64_t *>(&tiles[blockIdx.x])[tid];
+    constexpr int DW = (int)(sizeof(TileDescFull) / 8);
+    constexpr int GK = F::GK;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x;
+    int t = blockIdx.x;
+    if (t >= ntiles) return;
+    if (tid < DW) reinterpret_cast<int64_t *>(&tds[0])[tid] = reinterpret_cast<const int64_t *>(&tiles[t])[tid];
+    if (tid >= 32 && tid < 32 + DW && t + G < ntiles)
+        reinterpret_cast<int64_t *>(&tds[1])[tid - 32] = reinterpret_cast<const int64_t *>(&tiles[t + G])[tid - 32];
+    const uint32_t barA = tl_smem_addr(&bar);
     if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tl_smem_addr(&bar)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (td.nslot == 0) return;
-    const int nq = td.nq;
-    double *stage = reinterpret_cast<double *>(smem_raw);
-    unsigned char *smeta = smem_raw + tl_align16(F::ND * nq * 8);
-    // TMA bulk copy of the tile's gather metadata; it lands while phase 1 computes
-    if (tid == 0) {
-        const uint32_t b = tl_smem_addr(&bar);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"((uint32_t)td.meta_bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(tl_smem_addr(smeta)), "l"(meta + td.meta0), "r"((uint32_t)td.meta_bytes), "r"(b) : "memory");
+
+    // coordinates + column mask of this thread's first-round element of the current tile
+    double PX[GK], PY[GK];
+    uint32_t pm = 0;
+    if (tid < tds[0].nelem) {
+        const int64_t g = tds[0].elem0 + tid;
+#pragma unroll
+        for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); PX[a] = p.x; PY[a] = p.y; }
+        pm = tmask[g];
     }
 
-    // phase 1: one thread per tile element: owned columns of the element matrix -> stage
-    for (int le = tid; le < td.nelem; le += BLOCK) {
-        const int64_t g = td.elem0 + le;
-        double X[F::GK], Y[F::GK];
-#pragma unroll
-        for (int a = 0; a < F::GK; a++) {
-            const double2 p = __ldg(&xy[tconn[g * F::GK + a]]);
-            X[a] = p.x; Y[a] = p.y;
+    for (int it = 0; t < ntiles; it++, t += G) {
+        const TileDescFull &td = tds[it % 3];
+        const bool active = td.nslot > 0;
+        // descriptor two tiles ahead: load now, park in shared memory before the mid-tile barrier
+        int64_t dword = 0;
+        const bool fetch_desc = (t + 2 * G < ntiles) && warp == BLOCK / 32 - 1 && lane < DW;
+        if (fetch_desc) dword = reinterpret_cast<const int64_t *>(&tiles[t + 2 * G])[lane];
+        const int nq = td.nq;
+        double *stage = reinterpret_cast<double *>(smem_raw);
+        unsigned char *smeta = smem_raw + tl_align16(F::ND * nq * 8);
+        if (tid == 0 && active) {   // TMA bulk copy of the tile's gather metadata; lands while phase 1 computes
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barA), "r"((uint32_t)td.meta_bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(tl_smem_addr(smeta)), "l"(meta + td.meta0), "r"((uint32_t)td.meta_bytes), "r"(barA) : "memory");
         }
-        StageEmit<F> emit{stage, td.qbase, (uint32_t)tmask[g], (uint32_t)le, nq};
-        F::template element<S>(X, Y, emit.m, emit);
-    }
-    __syncthreads();
-    {   // metadata has landed?
-        const uint32_t b = tl_smem_addr(&bar);
-        uint32_t done = 0;
-        while (!done)
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(b) : "memory");
-    }
 
-    // phase 2: every owned nonzero = left-to-right sum of its contributions (append order), stored once
-    const uint16_t *goff = reinterpret_cast<const uint16_t *>(smeta);
-    const uint16_t *gi = reinterpret_cast<const uint16_t *>(smeta + tl_meta_goff_bytes(td.nslot));
-    const TileRun *srun = reinterpret_cast<const TileRun *>(smeta + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
-    const int lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = BLOCK / 32;
-    const int nslot = td.nslot;
-    const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // contiguous slots per warp, multiple of 32
-    const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
-    int r = 0;
-    {   // run containing slot w0 (same search in every lane)
-        int lo = 0, hi = td.nrun - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= w0) lo = mid; else hi = mid - 1; }
-        r = lo;
-    }
-    int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
-    int64_t rnz = srun[r].nz0;
-    // light nonzeros (<= TL_LIGHT contributions: all but the matrix diagonals of node patches): straight-line
-    // code, 4 independent slots in flight per lane to cover the shared-memory latency chain goff -> gidx -> stage
-    constexpr int U = 4;
-    for (int sb = w0; sb < w1; sb += 32 * U) {
-        int o0[U], c[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int s = sb + u * 32 + lane;
-            o0[u] = 0; c[u] = 0;
-            if (s < w1) { o0[u] = goff[s]; c[u] = (int)goff[s + 1] - o0[u]; }
+        // phase 1: one thread per tile element: owned columns of the element matrix -> stage
+        if (tid < td.nelem) {
+            StageEmit<F> emit{stage, td.qbase, pm, (uint32_t)tid, nq};
+            F::template element<S>(PX, PY, pm, emit);
         }
-        double acc[U];
+        for (int le = tid + BLOCK; le < td.nelem; le += BLOCK) {    // rare: tiles with more elements than threads
+            const int64_t g = td.elem0 + le;
+            double X[GK], Y[GK];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            acc[u] = 0.0;
-            if (c[u] >= 1 && c[u] <= TL_LIGHT) acc[u] = stage[gi[o0[u]]];
+            for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
+            StageEmit<F> emit{stage, td.qbase, (uint32_t)tmask[g], (uint32_t)le, nq};
+            F::template element<S>(X, Y, emit.m, emit);
         }
+        // next tile: connectivity of this thread's element into registers (coordinates follow in phase 2)
+        int32_t nc[GK];
+        uint32_t nm = 0;
+        bool have_next = false;
+        if (t + G < ntiles) {
+            const TileDescFull &dn = tds[(it + 1) % 3];
+            if (tid < dn.nelem) {
+                const int64_t g = dn.elem0 + tid;
 #pragma unroll
-        for (int u = 0; u < U; u++)
-            if (c[u] == 2) acc[u] = __dadd_rn(acc[u], stage[gi[o0[u] + 1]]);
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int s = sb + u * 32 + lane;
-            if (s < w1) {
-                while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
-                if (c[u] <= TL_LIGHT) nzval[rnz + (s - rs0)] = acc[u];
+                for (int a = 0; a < GK; a++) nc[a] = tconn[g * GK + a];
+                nm = tmask[g];
+                have_next = true;
             }
         }
-    }
-    // heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum
-    const uint16_t *heavy = reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(srun) + td.nrun * (int)sizeof(TileRun));
-    for (int h = tid; h < td.nheavy; h += BLOCK) {
-        const int s = heavy[h];
-        const int o0 = goff[s], o1 = goff[s + 1];
-        double acc = stage[gi[o0]];
-        for (int k = o0 + 1; k < o1; k++) acc = __dadd_rn(acc, stage[gi[k]]);
-        int lo = 0, hi = td.nrun - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
-        nzval[srun[lo].nz0 + (s - srun[lo].s0)] = acc;
+        if (fetch_desc) reinterpret_cast<int64_t *>(&tds[(it + 2) % 3])[lane] = dword;
+        __syncthreads();
+
+        if (active) {
+            {   // metadata has landed?
+                uint32_t done = 0;
+                const uint32_t parity = (uint32_t)(it & 1);
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(done) : "r"(barA), "r"(parity) : "memory");
+            }
+            // phase 2: every owned nonzero = left-to-right sum of its contributions (append order), stored once
+            const uint32_t stageA = tl_smem_addr(stage);
+            const uint32_t goffA = tl_smem_addr(smeta);
+            const uint32_t giA = goffA + tl_meta_goff_bytes(td.nslot);
+            const TileRun *srun = reinterpret_cast<const TileRun *>(smeta + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
+            constexpr int NW = BLOCK / 32;
+            const int nslot = td.nslot;
+            const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // contiguous slots per warp, multiple of 32
+            const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
+            int r = 0;
+            {   // run containing slot w0 (same search in every lane)
+                int lo = 0, hi = td.nrun - 1;
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= w0) lo = mid; else hi = mid - 1; }
+                r = lo;
+            }
+            int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
+            int64_t rnz = srun[r].nz0;
+            // light nonzeros (<= TL_LIGHT contributions: all but the matrix diagonals of node patches): straight-line
+            // code, 4 independent slots in flight per lane to cover the latency chain goff -> gidx -> stage
+            constexpr int U = 4;
+            const int wmid = w0 + (((w1 - w0) / 2 + 32 * U - 1) / (32 * U)) * (32 * U);
+            for (int half = 0; half < 2; half++) {
+                const int h0 = half == 0 ? w0 : min(wmid, w1), h1 = half == 0 ? min(wmid, w1) : w1;
+                for (int sb = h0; sb < h1; sb += 32 * U) {
+                    int o0[U], c[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int s = sb + u * 32 + lane;
+                        o0[u] = 0; c[u] = 0;
+                        if (s < h1) { o0[u] = (int)lds_u16(goffA + 2 * s); c[u] = (int)lds_u16(goffA + 2 * s + 2) - o0[u]; }
+                    }
+                    double acc[U];
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        acc[u] = 0.0;
+                        if (c[u] >= 1 && c[u] <= TL_LIGHT) acc[u] = lds_f64(stageA + 8 * lds_u16(giA + 2 * o0[u]));
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; u++)
+                        if (c[u] == 2) acc[u] = __dadd_rn(acc[u], lds_f64(stageA + 8 * lds_u16(giA + 2 * o0[u] + 2)));
+#pragma unroll
+                    for (int u = 0; u < U; u++) {
+                        const int s = sb + u * 32 + lane;
+                        if (s < h1) {
+                            while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
+                            if (c[u] <= TL_LIGHT) nzval[rnz + (s - rs0)] = acc[u];
+                        }
+                    }
+                }
+                if (half == 0 && have_next) {   // coordinates of the next tile's element: in flight during the second half
+#pragma unroll
+                    for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[nc[a]]); PX[a] = p.x; PY[a] = p.y; }
+                }
+            }
+            // heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum
+            const uint32_t heavyA = tl_smem_addr(srun) + td.nrun * (int)sizeof(TileRun);
+            for (int h = tid; h < td.nheavy; h += BLOCK) {
+                const int s = (int)lds_u16(heavyA + 2 * h);
+                const int o0 = (int)lds_u16(goffA + 2 * s), o1 = (int)lds_u16(goffA + 2 * s + 2);
+                double acc = lds_f64(stageA + 8 * lds_u16(giA + 2 * o0));
+                for (int k = o0 + 1; k < o1; k++) acc = __dadd_rn(acc, lds_f64(stageA + 8 * lds_u16(giA + 2 * k)));
+                int lo = 0, hi = td.nrun - 1;
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
+                nzval[srun[lo].nz0 + (s - srun[lo].s0)] = acc;
+            }
+        } else if (have_next) {
+#pragma unroll
+            for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[nc[a]]); PX[a] = p.x; PY[a] = p.y; }
+        }
+        pm = nm;
+        __syncthreads();    // stage, metadata and tds[it % 3] are free again
     }
 }
 
@@ -849,17 +924,26 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     ctx->tl.numeric_bytes = ntelem * (F::GK * 4 + 2) + gm.nnodes * 16 + meta_total + nnz * 8 + (int64_t)ntiles * sizeof(TileDescFull);
 }
 
-template <class F, bool S> static void tl_launch_numeric(efg_ctx *ctx)
+template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(efg_ctx *ctx)
 {
     TiledData *td = tiled_data(ctx);
     const MeshDev &gm = ctx->mesh[F::GMESH];
-    constexpr int BLOCK = 256;
-    auto kern = k_tl_numeric<F, S, BLOCK>;
+    auto kern = k_tl_numeric<F, S, BLOCK, MINB>;
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
-    if (ctx->tl.ntiles > 0)
-        LAUNCH(ctx, kern, (unsigned)ctx->tl.ntiles, BLOCK, (size_t)td->smem_bytes, td->tiles.p, td->tconn.p, td->tmask.p, gm.xy.p,
+    int per_sm = 0, nsm = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
+    CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+    if (per_sm < 1) efg_throw(EFG_ERR_LIMIT, "tiled path: the numeric kernel does not fit on an SM (%d bytes of shared memory)", td->smem_bytes);
+    int grid = per_sm * nsm;                      // persistent: one CTA per resident slot
+    if (grid > ctx->tl.ntiles) grid = ctx->tl.ntiles;
+    if (grid > 0)
+        LAUNCH(ctx, kern, (unsigned)grid, BLOCK, (size_t)td->smem_bytes, td->tiles.p, ctx->tl.ntiles, td->tconn.p, td->tmask.p, gm.xy.p,
                td->meta.p, ctx->nzval.p);
     ctx->numeric_launches += 1;
+}
+template <class F, bool S> static void tl_launch_numeric(efg_ctx *ctx)
+{
+    tl_launch_numeric_b<F, S, 256, 2>(ctx);
 }
 
 template <class F> void tiled_numeric(efg_ctx *ctx)
