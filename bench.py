@@ -68,10 +68,10 @@ def algorithmic_bytes(prob, nnz):
     indices: 4*nen*nel + 16*nnodes + 4*ndofs + 4*ntriplets + 8*nnz (pressure mesh connectivity added for Stokes)."""
     b = 0
     for m in prob.meshes:
-        b += 4 * m.kind * m.nel
-    b += 16 * prob.meshes[0].nnodes
+        b += 4 * m.kind * m.nel_
+    b += 16 * prob.meshes[0].nnodes_
     b += 4 * prob.ndofs
-    b += 4 * triplets_per_element(prob) * prob.nel
+    b += 4 * triplets_per_element(prob) * prob.meshes[0].nel_
     b += 8 * nnz
     return b
 
@@ -200,6 +200,8 @@ def main():
 
     n = args.n or WORKLOADS[args.workload][0]
     if world > 1:
+        # weak scaling: a mesh `world` units tall, rank r owns the dofs of horizontal band r (a set of column
+        # ranges), halo elements replicated; generated on the GPU (elfel.jl_b200/sharding.py)
         from elfel_jl_b200.sharding import shard_problem
         prob, col_range, nel_global = shard_problem(efg, args.workload, n, rank, world)
     else:
@@ -216,10 +218,18 @@ def main():
 
     # host buffers (pinned) of the reference-facing call
     def pin(a):
-        t = torch.from_numpy(np.ascontiguousarray(a))
+        t = a.detach().cpu().contiguous() if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
         return t.pin_memory()
-    h_mesh = [(m.kind, pin(m.conn.astype(np.int64)), pin(m.xy.astype(np.float64))) for m in prob.meshes]
-    h_dofs = [pin(s.field.dofnums.astype(np.int64)) for s in prob.spaces]
+    h_mesh = [(m.kind, pin(m.conn), pin(m.xy)) for m in prob.meshes]
+    h_dofs = [pin(s.field.dofnums) for s in prob.spaces]
+    for m in prob.meshes:           # the host copies are the inputs from here on
+        m.conn_shape, m.nnodes_, m.nel_ = tuple(m.conn.shape), int(m.xy.shape[0]), int(m.conn.shape[0])
+    if world > 1:
+        for m in prob.meshes:
+            m.conn = m.xy = None
+        for sp in prob.spaces:
+            sp.field.dofnums = None
+        torch.cuda.empty_cache()
     h2d = sum(c.numel() * 8 + x.numel() * 8 for _, c, x in h_mesh) + sum(d.numel() * 8 for d in h_dofs)
 
     def load():
@@ -229,7 +239,7 @@ def main():
             eng.set_space(slot, ms, d)
         eng.start(prob.ndofs, prob.ndofs)
         if col_range is not None:
-            eng.set_column_range(*col_range)
+            eng.set_column_ranges(*col_range)
 
     # ---- e2e through the C ABI with host buffers -------------------------------------------------------
     e2e = None
@@ -303,7 +313,7 @@ def main():
     value = nel_global / (ms_step / 1e3)
 
     path = int(eng.stat(_lib.STAT_PATH))
-    alg = algorithmic_bytes(prob, nnz)     # this rank's launch
+    alg = algorithmic_bytes(prob, nnz)     # this rank's launch (its sub-mesh incl. replicated halo elements)
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_file):
         peak, peak_src = json.load(open(peaks_file))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
@@ -317,7 +327,7 @@ def main():
         traffic = json.load(open(tf)).get(f"{args.workload}_N{n}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(alg),
-                "algorithmic_bytes_per_element": alg / prob.nel,
+                "algorithmic_bytes_per_element": alg / prob.meshes[0].nel_,
                 "designed_bytes_per_launch": int(eng.stat(_lib.STAT_NUMERIC_BYTES)),
                 "frac_of_nominal_8TBps": achieved / 8000.0,
                 "kernel": "k_tl_numeric" if path == 2 else "k_tp_elem_matrices+k_tp_gather"}
@@ -331,7 +341,8 @@ def main():
                    "path": {1: "two-pass", 2: "tiled-fused"}[path], "strict_fp": args.strict,
                    "tile_elems": int(eng.stat(_lib.STAT_TILE_ELEMS) and args.tile_elems), "sfc_order": args.sfc,
                    "tiles": int(eng.stat(_lib.STAT_NTILES)),
-                   "halo_factor": eng.stat(_lib.STAT_TILE_ELEMS) / max(prob.nel, 1)},
+                   "halo_factor": eng.stat(_lib.STAT_TILE_ELEMS) / max(prob.meshes[0].nel_, 1),
+                   "rank_elements_incl_shard_halo": int(prob.meshes[0].nel_)},
         "roofline": roofline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
         "phases": {"symbolic_ms": sym_ms, "numeric_ms": ms_step,
                    "value_with_symbolic": nel_global / ((ms_step + sym_ms) / 1e3)},

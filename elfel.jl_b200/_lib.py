@@ -30,7 +30,7 @@ PATH_AUTO, PATH_TWOPASS, PATH_TILED = 0, 1, 2
 
 EXPORTS = ["efg_create", "efg_destroy", "efg_last_error", "efg_set_option", "efg_get_stat", "efg_get_stream",
            "efg_synchronize", "efg_set_mesh", "efg_set_space", "efg_start", "efg_set_column_range",
-           "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version"]
+           "efg_set_column_ranges", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version"]
 
 
 def _sources():
@@ -84,6 +84,7 @@ def load():
     L.efg_set_space.argtypes = [vp, ci, ci, ci, i64, vp]
     L.efg_start.argtypes = [vp, i64, i64]
     L.efg_set_column_range.argtypes = [vp, i64, i64]
+    L.efg_set_column_ranges.argtypes = [vp, i64, i64p, i64p]
     L.efg_symbolic.argtypes = [vp, ci, ci, i64p]
     L.efg_numeric.argtypes = [vp, f64p, ci]
     L.efg_assemble.argtypes = [vp, ci, ci, f64p, ci, i64p]

@@ -199,6 +199,13 @@ class Engine:
         self._ck(self.L.efg_set_column_range(self.h, int(first), int(last)))
         self.ncols_local = int(last) - int(first) + 1
 
+    def set_column_ranges(self, firsts, lasts):
+        f = np.ascontiguousarray(firsts, dtype=np.int64)
+        l = np.ascontiguousarray(lasts, dtype=np.int64)
+        self._ck(self.L.efg_set_column_ranges(self.h, len(f), f.ctypes.data_as(C.POINTER(C.c_int64)),
+                                              l.ctypes.data_as(C.POINTER(C.c_int64))))
+        self.ncols_local = int((l - f + 1).sum())
+
     def symbolic(self, form_id, quad) -> int:
         nnz = C.c_int64()
         self._ck(self.L.efg_symbolic(self.h, form_id, quad, C.byref(nnz)))

@@ -3,6 +3,21 @@
 #include "efg_common.cuh"
 #include "efg_forms.cuh"
 
+// global column -> local column of this ctx (owner-computes sharding), -1 if not owned
+struct ColMap {
+    int64_t c0, c1;
+    int nr;
+    const int32_t *first, *last1, *off;
+    __device__ __forceinline__ int64_t local(int64_t c) const
+    {
+        if (nr == 0) return (c >= c0 && c < c1) ? c - c0 : -1;
+        int lo = 0, hi = nr - 1;
+        if (c < first[0]) return -1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (first[mid] <= c) lo = mid; else hi = mid - 1; }
+        return c < last1[lo] ? (int64_t)off[lo] + (c - first[lo]) : -1;
+    }
+};
+
 struct MeshDev {
     int kind = 0;
     int64_t nel = 0, nnodes = 0;
@@ -49,8 +64,12 @@ struct efg_ctx {
 
     bool started = false;
     int64_t nrow = 0, ncol = 0;
-    int64_t c0 = 0, c1 = 0;          // 0-based column range [c0, c1)
+    // owned matrix columns: one range [c0, c1) (0-based) or a sorted list of disjoint ranges
+    int64_t c0 = 0, c1 = 0;
+    int64_t ncl = 0;                 // number of owned (local) columns
     bool have_range = false;
+    int nranges = 0;                 // 0 = single range
+    DevBuf<int32_t> rfirst, rlast1, roff;
 
     // options
     int opt_path = 0;
@@ -63,7 +82,7 @@ struct efg_ctx {
     int form = 0, quad = 0, nq = 0, vkind = 0;
     int path = 0;
     int64_t nnz = 0;
-    DevBuf<int64_t> colptr;      // (c1-c0)+1, 1-based
+    DevBuf<int64_t> colptr;      // ncl+1, 1-based
     DevBuf<int32_t> rowval;      // nnz, 0-based
     DevBuf<double> nzval;        // nnz
     bool have_values = false;
@@ -75,6 +94,8 @@ struct efg_ctx {
     double symbolic_ms = 0, numeric_ms = 0;
     int64_t launches = 0, numeric_launches = 0;
 };
+
+#define COLMAP(ctx) ColMap{(ctx)->c0, (ctx)->c1, (ctx)->nranges, (ctx)->rfirst.p, (ctx)->rlast1.p, (ctx)->roff.p}
 
 #define LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
     do {                                                                             \

@@ -187,15 +187,14 @@ __global__ void k_tl_fill_i32(int32_t *p, int64_t n, int32_t v) { GRID_STRIDE(i,
 // owner tile of every column in range + adjacency pair generation
 template <int ND>
 __global__ void k_tl_owner_pairs(const int32_t *__restrict__ edof, const int32_t *__restrict__ etile, int64_t nel,
-                                 int64_t c0, int64_t c1, int32_t *__restrict__ owner, uint32_t *__restrict__ adjcnt,
+                                 ColMap cm, uint32_t ncl, int32_t *__restrict__ owner, uint32_t *__restrict__ adjcnt,
                                  uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
-    const uint32_t ncl = (uint32_t)(c1 - c0);
     GRID_STRIDE(t, nel * ND) {
         const int64_t e = t / ND;
-        const int32_t c = edof[t];
-        if (c >= c0 && c < c1) {
-            const uint32_t cl = (uint32_t)(c - c0);
+        const int64_t lc = cm.local(edof[t]);
+        if (lc >= 0) {
+            const uint32_t cl = (uint32_t)lc;
             atomicMin(&owner[cl], etile[e]);
             atomicAdd(&adjcnt[cl], 1u);
             keys[t] = cl;
@@ -323,14 +322,14 @@ __global__ void k_tl_run_len(const int64_t *__restrict__ run_firstk, int64_t nru
 
 // tile-element keys: (T << 36) | (e << 4) | lj for every (e, lj) whose column is owned
 template <int ND>
-__global__ void k_tl_telem_keys(const int32_t *__restrict__ edof, int64_t nel, int64_t c0, int64_t c1, const int32_t *__restrict__ owner,
+__global__ void k_tl_telem_keys(const int32_t *__restrict__ edof, int64_t nel, ColMap cm, const int32_t *__restrict__ owner,
                                 int ntiles, uint64_t *__restrict__ keys)
 {
     GRID_STRIDE(t, nel * ND) {
         const int64_t e = t / ND;
         const int lj = (int)(t % ND);
-        const int32_t c = edof[t];
-        const uint64_t T = (c >= c0 && c < c1) ? (uint64_t)(uint32_t)owner[c - c0] : (uint64_t)ntiles;
+        const int64_t lc = cm.local(edof[t]);
+        const uint64_t T = lc >= 0 ? (uint64_t)(uint32_t)owner[lc] : (uint64_t)ntiles;
         keys[t] = (T << 36) | ((uint64_t)e << 4) | (uint64_t)lj;
     }
 }
@@ -720,7 +719,7 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     const MeshDev &m0 = ctx->mesh[0];
     const MeshDev &gm = ctx->mesh[F::GMESH];
     const int64_t nel = m0.nel;
-    const int64_t ncl = ctx->c1 - ctx->c0;
+    const int64_t ncl = ctx->ncl;
     if (nel * ND >= ((int64_t)1 << 32)) efg_throw(EFG_ERR_LIMIT, "tiled path: nel*ND exceeds 2^32; shard the mesh (efg_set_column_range)");
     cudaStream_t st = ctx->stream;
     DevPool &pool = ctx->pool;
@@ -775,7 +774,7 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     {
         DevBuf<uint32_t> k1, k2, v1;
         k1.alloc(pool, (size_t)(nel * ND)); k2.alloc(pool, (size_t)(nel * ND)); v1.alloc(pool, (size_t)(nel * ND));
-        LAUNCH(ctx, k_tl_owner_pairs<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, etile.p, nel, ctx->c0, ctx->c1, owner.p, adjcnt.p, k1.p, v1.p);
+        LAUNCH(ctx, k_tl_owner_pairs<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, etile.p, nel, COLMAP(ctx), (uint32_t)ncl, owner.p, adjcnt.p, k1.p, v1.p);
         tl_sort_pairs(ctx, k1.p, k2.p, v1.p, adj.p, nel * ND, bits_for(ncl));
     }
     tl_excl_scan(ctx, adjcnt.p, adjptr.p, ncl + 1);
@@ -849,7 +848,7 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     {
         DevBuf<uint64_t> ek1;
         ek1.alloc(pool, (size_t)(nel * ND)); ek2.alloc(pool, (size_t)(nel * ND));
-        LAUNCH(ctx, k_tl_telem_keys<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, nel, ctx->c0, ctx->c1, owner.p, ntiles, ek1.p);
+        LAUNCH(ctx, k_tl_telem_keys<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, nel, COLMAP(ctx), owner.p, ntiles, ek1.p);
         tl_sort_keys(ctx, ek1.p, ek2.p, nel * ND, 36 + bits_for(ntiles));   // out-of-range pairs carry tile id ntiles: they sort last
     }
     DevBuf<int32_t> eflag;

@@ -13,7 +13,7 @@
 #include "efg_ctx.cuh"
 
 template <class F>
-__global__ void k_tp_keys(DofSrc src, int64_t nel, int64_t nrow, int64_t ncol, int64_t c0, int64_t c1,
+__global__ void k_tp_keys(DofSrc src, int64_t nel, int64_t nrow, int64_t ncol, ColMap cm, int64_t ncl,
                           uint64_t *__restrict__ keys, uint32_t *__restrict__ vals, int *__restrict__ errflag)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -30,8 +30,8 @@ __global__ void k_tp_keys(DofSrc src, int64_t nel, int64_t nrow, int64_t ncol, i
                 if (F::mask(i, j)) {
                     bad |= (d[i] >= nrow) || (d[j] >= ncol);
                     const int64_t t = e * F::NT + F::kidx(i, j);
-                    const int64_t c = d[j];
-                    const uint64_t cl = (c >= c0 && c < c1) ? (uint64_t)(c - c0) : (uint64_t)(c1 - c0);
+                    const int64_t lc = (d[j] >= 0) ? cm.local(d[j]) : -1;
+                    const uint64_t cl = lc >= 0 ? (uint64_t)lc : (uint64_t)ncl;
                     keys[t] = (cl << 32) | (uint32_t)d[i];
                     vals[t] = (uint32_t)t;
                 }
@@ -112,7 +112,7 @@ template <class F> void twopass_symbolic(efg_ctx *ctx)
     const int64_t ntrip = nel * F::NT;
     if (ntrip >= (int64_t)1 << 32)
         efg_throw(EFG_ERR_LIMIT, "two-pass path: %lld triplets exceed the 2^32 limit; shard the mesh (efg_set_column_range)", (long long)ntrip);
-    const int64_t ncl = ctx->c1 - ctx->c0;
+    const int64_t ncl = ctx->ncl;
     DofSrc src{m0.conn.p, ctx->mesh[1].conn.p, ctx->space[0].dof.p, ctx->space[1].dof.p, ctx->space[2].dof.p};
 
     DevBuf<uint64_t> keys, keys2;
@@ -122,7 +122,7 @@ template <class F> void twopass_symbolic(efg_ctx *ctx)
     vals.alloc(ctx->pool, ntrip); ctx->tp.perm.alloc(ctx->pool, ntrip);
     errflag.alloc(ctx->pool, 1);
     CUDA_CHECK(cudaMemsetAsync(errflag.p, 0, sizeof(int), ctx->stream));
-    LAUNCH(ctx, k_tp_keys<F>, grid_for(nel, 256), 256, 0, src, nel, ctx->nrow, ctx->ncol, ctx->c0, ctx->c1, keys.p, vals.p, errflag.p);
+    LAUNCH(ctx, k_tp_keys<F>, grid_for(nel, 256), 256, 0, src, nel, ctx->nrow, ctx->ncol, COLMAP(ctx), ncl, keys.p, vals.p, errflag.p);
     int herr = 0;
     CUDA_CHECK(cudaMemcpyAsync(&herr, errflag.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -314,7 +314,7 @@ int efg_start(efg_ctx *ctx, int64_t nrow, int64_t ncol)
     const bool same = ctx->started && ctx->nrow == nrow && ctx->ncol == ncol && !ctx->have_range;
     if (!same) invalidate(ctx);
     ctx->nrow = nrow; ctx->ncol = ncol;
-    ctx->c0 = 0; ctx->c1 = ncol; ctx->have_range = false;
+    ctx->c0 = 0; ctx->c1 = ncol; ctx->ncl = ncol; ctx->have_range = false; ctx->nranges = 0;
     ctx->started = true;
     ctx->have_values = false;
     API_END(ctx)
@@ -325,8 +325,32 @@ int efg_set_column_range(efg_ctx *ctx, int64_t first, int64_t last)
     API_BEGIN(ctx)
     if (!ctx->started) efg_throw(EFG_ERR_STATE, "efg_set_column_range before efg_start");
     if (first < 1 || last > ctx->ncol || last < first - 1) efg_throw(EFG_ERR_INVALID, "bad column range");
-    if (ctx->c0 != first - 1 || ctx->c1 != last) invalidate(ctx);
-    ctx->c0 = first - 1; ctx->c1 = last; ctx->have_range = true;
+    invalidate(ctx);
+    ctx->c0 = first - 1; ctx->c1 = last; ctx->ncl = last - first + 1; ctx->have_range = true; ctx->nranges = 0;
+    API_END(ctx)
+}
+
+int efg_set_column_ranges(efg_ctx *ctx, int64_t nranges, const int64_t *firsts, const int64_t *lasts)
+{
+    API_BEGIN(ctx)
+    if (!ctx->started) efg_throw(EFG_ERR_STATE, "efg_set_column_ranges before efg_start");
+    if (nranges < 1 || nranges > (1 << 24) || !firsts || !lasts) efg_throw(EFG_ERR_INVALID, "bad column range list");
+    std::vector<int32_t> f((size_t)nranges), l((size_t)nranges), o((size_t)nranges);
+    int64_t tot = 0, prev = 0;
+    for (int64_t i = 0; i < nranges; i++) {
+        if (firsts[i] < 1 || lasts[i] > ctx->ncol || lasts[i] < firsts[i] || firsts[i] <= prev)
+            efg_throw(EFG_ERR_INVALID, "column ranges must be non-empty, ascending and disjoint (range %lld)", (long long)i);
+        f[(size_t)i] = (int32_t)(firsts[i] - 1); l[(size_t)i] = (int32_t)lasts[i]; o[(size_t)i] = (int32_t)tot;
+        tot += lasts[i] - firsts[i] + 1;
+        prev = lasts[i];
+    }
+    invalidate(ctx);
+    ctx->rfirst.alloc(ctx->pool, (size_t)nranges); ctx->rlast1.alloc(ctx->pool, (size_t)nranges); ctx->roff.alloc(ctx->pool, (size_t)nranges);
+    CUDA_CHECK(cudaMemcpyAsync(ctx->rfirst.p, f.data(), (size_t)nranges * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->rlast1.p, l.data(), (size_t)nranges * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaMemcpyAsync(ctx->roff.p, o.data(), (size_t)nranges * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->c0 = firsts[0] - 1; ctx->c1 = lasts[nranges - 1]; ctx->ncl = tot; ctx->have_range = true; ctx->nranges = (int)nranges;
     API_END(ctx)
 }
 
@@ -418,7 +442,7 @@ int efg_fetch_csc(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval)
     API_BEGIN(ctx)
     if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_fetch_csc before efg_symbolic");
     if (nzval && !ctx->have_values) efg_throw(EFG_ERR_STATE, "efg_fetch_csc(nzval) before efg_numeric");
-    const int64_t ncl = ctx->c1 - ctx->c0;
+    const int64_t ncl = ctx->ncl;
     if (colptr) CUDA_CHECK(cudaMemcpyAsync(colptr, ctx->colptr.p, (size_t)(ncl + 1) * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
     if (nzval && ctx->nnz > 0) CUDA_CHECK(cudaMemcpyAsync(nzval, ctx->nzval.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDefault, ctx->stream));
     if (rowval && ctx->nnz > 0) {

@@ -24,7 +24,8 @@
  *     layout Julia holds them: conn is nen x nel (node ids of element e at conn[e*nen + k]),
  *     xy is 2 x nnodes, dofnums is ncomp x nnodes (Vector{SVector{ncomp,Int64}}).
  *   - Input pointers may be host (pageable or pinned) or device pointers (unified addressing);
- *     they are borrowed for the duration of the call only.
+ *     they are borrowed for the duration of the call only.  Device inputs are read on the ctx's own
+ *     stream: the work that produced them must have completed (synchronize the producer first).
  *   - Output arrays of efg_fetch_csc are allocated by the caller after nnz is known
  *     (two-call pattern) so Julia wraps them in SparseMatrixCSC without a copy.
  *   - Every function returns 0 on success or a negative EFG_ERR_* code; no exception crosses
@@ -111,6 +112,10 @@ int efg_start(efg_ctx *ctx, int64_t nrow, int64_t ncol);
  * Triplets of other columns are dropped; colptr then has (col_last-col_first+2) entries, rebased
  * to start at 1.  Concatenating the blocks of consecutive ranges gives the global matrix. */
 int efg_set_column_range(efg_ctx *ctx, int64_t col_first, int64_t col_last);
+/* Same, for an owner that holds several disjoint column ranges (ascending, 1-based inclusive), e.g. the
+ * vertex-dof rows and the mid-side-dof runs of one horizontal band of a T6 mesh.  The output holds the owned
+ * columns in ascending order: colptr has (number of owned columns + 1) entries. */
+int efg_set_column_ranges(efg_ctx *ctx, int64_t nranges, const int64_t *col_firsts, const int64_t *col_lasts);
 
 /* Symbolic phase: CSC pattern + scatter maps on the device.  quad_rule: triangles npts (1|3),
  * squares Gauss order (1..3).  Cached until mesh/space/start/range/options change. */

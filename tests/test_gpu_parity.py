@@ -150,3 +150,37 @@ def test_numeric_phase_is_deterministic_and_reusable():
     _, _, c = eng.fetch_csc()
     assert np.allclose(c, 2.0 * a, rtol=1e-14, atol=0)
     eng.close()
+
+
+@pytest.mark.parametrize("path", [_lib.PATH_TWOPASS, _lib.PATH_TILED], ids=["twopass", "tiled"])
+@pytest.mark.parametrize("workload,n,world", [("heat_t6", 9, 3), ("heat_q4", 12, 2), ("elasticity_t6", 7, 2)])
+def test_multirange_band_shards_merge_to_global(oracle, workload, n, world, path):
+    """The multi-GPU decomposition on one GPU: every rank's band (a set of column ranges, halo elements
+    replicated) is assembled by the engine; the interleaved blocks equal the oracle's global matrix."""
+    import torch
+    from elfel_jl_b200 import sharding as sh
+    kind, conn, xy, dofnums, band, form, quad = sh.build_global(workload, n, world, "cpu")
+    nd = dofnums.numel()
+    ocp, orv, onz = oracle.assemble(form.form_id, quad, efg.Mesh(kind, conn.numpy(), xy.numpy()), None, [dofnums.numpy()],
+                                    form.params(), nd, nd)
+    blocks = []
+    for r in range(world):
+        # shard built on the CPU (same coordinates, bit for bit, as the oracle's mesh), handed over as DEVICE arrays
+        s, (firsts, lasts), _ = sh.shard_problem(efg, workload, n, r, world, dev="cpu")
+        s.meshes[0].conn, s.meshes[0].xy = s.meshes[0].conn.cuda(), s.meshes[0].xy.cuda()
+        s.spaces[0].field.dofnums = s.spaces[0].field.dofnums.cuda()
+        torch.cuda.synchronize()    # the ctx copies on its own stream: producer work must be complete
+        eng = efg.Engine(0)
+        eng.set_option(_lib.OPT_PATH, path)
+        eng.set_option(_lib.OPT_STRICT_FP, 1)
+        eng.set_mesh(0, s.meshes[0].kind, s.meshes[0].conn, s.meshes[0].xy)
+        eng.set_space(0, 0, s.spaces[0].field.dofnums)
+        eng.start(s.ndofs, s.ndofs)
+        eng.set_column_ranges(firsts, lasts)
+        eng.assemble(s.form.form_id, s.quad, s.form.params())
+        cp, rv, nz = eng.fetch_csc()
+        eng.close()
+        blocks.append((firsts, lasts, cp, rv, nz))
+    cp, rv, nz = sh.merge_blocks(nd, blocks)
+    assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+    assert np.array_equal(nz, onz)
