@@ -13,7 +13,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-SO_PATH = os.path.join(_HERE, "libelfelgpu.so")
+SO_PATH = os.environ.get("EFG_LIB") or os.path.join(_HERE, "libelfelgpu.so")   # EFG_LIB: A/B kernel variants while tuning
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "elfel_gpu.h")
 
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -84,14 +84,15 @@ def load():
     L.efg_set_space.argtypes = [vp, ci, ci, ci, i64, vp]
     L.efg_start.argtypes = [vp, i64, i64]
     L.efg_set_column_range.argtypes = [vp, i64, i64]
-    L.efg_set_column_ranges.argtypes = [vp, i64, i64p, i64p]
+    if hasattr(L, "efg_set_column_ranges"):
+        L.efg_set_column_ranges.argtypes = [vp, i64, i64p, i64p]
     L.efg_symbolic.argtypes = [vp, ci, ci, i64p]
     L.efg_numeric.argtypes = [vp, f64p, ci]
     L.efg_assemble.argtypes = [vp, ci, ci, f64p, ci, i64p]
     L.efg_fetch_csc.argtypes = [vp, vp, vp, vp]
     L.efg_device_csc.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     for name in EXPORTS:
-        if name not in ("efg_version", "efg_last_error"):
+        if name not in ("efg_version", "efg_last_error") and hasattr(L, name):
             getattr(L, name).restype = ci
     _lib = L
     return L

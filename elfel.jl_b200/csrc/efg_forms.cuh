@@ -39,13 +39,26 @@ template <bool S> __device__ __forceinline__ double fdiv(double a, double b) {
 }
 
 // Quotients n/d with a shared divisor.  STRICT: the IEEE division the reference performs.
-// Default: one IEEE reciprocal per divisor, then q = n*inv refined by one FMA residual step
-// (Markstein: q' = q + inv*(n - q*d) is the correctly rounded quotient when inv = RN(1/d), up to
-// the divisor-significand-all-ones corner case) -- 3 DFMA-pipe ops instead of a ~25-instruction
-// division sequence, and still (almost always) the same bits as the true division.
+// Default: one ~1-ulp reciprocal per divisor, then q = n*inv refined by one FMA residual step
+// (Markstein: q' = q + inv*(n - q*d) with the residual exact in the FMA) -- 3 DFMA-pipe ops per quotient
+// instead of a ~25-instruction IEEE division sequence; q' is the correctly rounded quotient except in
+// rare near-tie cases (then 1 ulp off), far inside the 1e-12 parity bar.
 template <bool S> struct SharedDivisor {
     double d, inv;
-    __device__ __forceinline__ explicit SharedDivisor(double d_) : d(d_), inv(0.0) { if constexpr (!S) inv = 1.0 / d_; }
+    __device__ __forceinline__ explicit SharedDivisor(double d_) : d(d_), inv(0.0) {
+#if defined(TL_FAST_RCP) && !TL_FAST_RCP
+        if constexpr (!S) inv = 1.0 / d_;
+#else
+        if constexpr (!S) {   // MUFU.RCP64H seed (>= 20 good bits) + two Newton steps -> ~1 ulp reciprocal
+            double r;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d_));
+            double e = fma(-d_, r, 1.0);
+            r = fma(r, e, r);
+            e = fma(-d_, r, 1.0);
+            inv = fma(r, e, r);
+        }
+#endif
+    }
     __device__ __forceinline__ double operator()(double n) const {
         if constexpr (S) return __ddiv_rn(n, d);
         else { const double q = n * inv; const double r = fma(-q, d, n); return fma(r, inv, q); }

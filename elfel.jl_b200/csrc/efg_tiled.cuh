@@ -53,7 +53,7 @@ struct TiledData {
     DevBuf<uint16_t> tmask;
     DevBuf<unsigned char> meta;  // per-tile metadata blocks (bulk-copied to shared memory by the numeric kernel)
     int64_t ntelem = 0, ncontrib = 0, nruns = 0, meta_bytes = 0;
-    int smem_bytes = 0;
+    int smem_bytes = 0, stage_bytes = 0, meta_max = 0;
     int block = 256;
 };
 
@@ -390,8 +390,9 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
         const int nr = (int)(colptr0[cl + 1] - r0);
         const TileDescFull &td = tiles[T];
         const int64_t g0 = telem_ptr[T], g1 = telem_ptr[T + 1];
-        uint16_t *__restrict__ goff = reinterpret_cast<uint16_t *>(meta + td.meta0) + (tcol_slot[k] - td.slot0);
-        uint16_t *__restrict__ gidx = reinterpret_cast<uint16_t *>(meta + td.meta0 + tl_meta_goff_bytes(td.nslot));
+        unsigned char *__restrict__ mb = meta + td.meta0;
+        uint16_t *__restrict__ goff = reinterpret_cast<uint16_t *>(mb) + (tcol_slot[k] - td.slot0);
+        uint16_t *__restrict__ gidx = reinterpret_cast<uint16_t *>(mb + tl_meta_goff_bytes(td.nslot));
         const uint32_t gbase = (uint32_t)(tcol_gidx[k] - td.gidx0);
         uint16_t off[TL_CAP];
         for (int t = 0; t < nr; t++) off[t] = 0;
@@ -409,7 +410,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                 off[lo]++;
             }
         }
-        uint16_t *__restrict__ heavy = reinterpret_cast<uint16_t *>(meta + td.meta0 + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib) +
+        uint16_t *__restrict__ heavy = reinterpret_cast<uint16_t *>(mb + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib) +
                                                                    td.nrun * (int)sizeof(TileRun)) + (tcol_heavy[k] - td.heavy0);
         const uint32_t sloc = (uint32_t)(tcol_slot[k] - td.slot0);
         uint32_t run = gbase;
@@ -454,9 +455,10 @@ __global__ void k_tl_meta_finish(int ntiles, const TileDescFull *__restrict__ ti
     GRID_STRIDE(T, ntiles) {
         const TileDescFull &td = tiles[T];
         if (td.meta_bytes == 0) continue;
-        reinterpret_cast<uint16_t *>(meta + td.meta0)[td.nslot] = (uint16_t)td.ncontrib;
-        TileRun *dst = reinterpret_cast<TileRun *>(meta + td.meta0 + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
-        for (int r = 0; r < td.nrun; r++) dst[r] = runs[td.run0 + r];
+        unsigned char *mb = meta + td.meta0;
+        reinterpret_cast<uint16_t *>(mb)[td.nslot] = (uint16_t)td.ncontrib;
+        TileRun *dst = reinterpret_cast<TileRun *>(mb + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
+        for (int rr = 0; rr < td.nrun; rr++) dst[rr] = runs[td.run0 + rr];
     }
 }
 __global__ void k_tl_tiles_meta0(int ntiles, const int64_t *__restrict__ meta_off, TileDescFull *__restrict__ tiles)
@@ -468,7 +470,7 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ 
                                 const int64_t *__restrict__ tcol_gidx, const int64_t *__restrict__ tcol_heavy, const int64_t *__restrict__ telem_ptr,
                                 const int64_t *__restrict__ run_of_k /* exclusive scan of run-head flags */,
                                 int64_t nowned, int64_t nruns, const uint32_t *__restrict__ pc_hist, TileDescFull *__restrict__ tiles,
-                                int64_t *__restrict__ meta_bytes, int32_t *__restrict__ maxima /* smem, nq*nd, ncontrib, nelem */)
+                                int64_t *__restrict__ meta_bytes, int32_t *__restrict__ maxima /* stage+meta bytes, nq*nd, ncontrib, nelem */)
 {
     GRID_STRIDE(T, ntiles) {
         TileDescFull d;
@@ -497,8 +499,7 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ 
         d.pad2_[0] = d.pad2_[1] = d.pad2_[2] = 0;
         tiles[T] = d;
         meta_bytes[T] = d.meta_bytes;
-        const int64_t smem = (int64_t)tl_align16(d.nq * nd * 8) + d.meta_bytes;
-        atomicMax(&maxima[0], (int32_t)(smem > 0x7fffffff ? 0x7fffffff : smem));
+        atomicMax(&maxima[0], tl_align16(d.nq * nd * 8) + d.meta_bytes);
         atomicMax(&maxima[1], (int32_t)((int64_t)d.nq * nd > 0x7fffffff ? 0x7fffffff : d.nq * nd));
         atomicMax(&maxima[2], d.ncontrib); atomicMax(&maxima[3], d.nelem);
     }
@@ -520,199 +521,157 @@ template <class F> struct StageEmit {
     }
 };
 
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+__device__ __forceinline__ uint32_t tl_mbar_wait(uint32_t barA, uint32_t parity)
 {
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-    return v;
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(barA), "r"(parity) : "memory");
+    return done;
 }
-__device__ __forceinline__ double lds_f64(uint32_t addr)
+__device__ __forceinline__ void tl_bulk_load(uint32_t dstA, const void *src, uint32_t bytes, uint32_t barA)
 {
-    double v;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
-    return v;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barA), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dstA), "l"(src), "r"(bytes), "r"(barA) : "memory");
 }
 
-// Persistent CTAs (gridDim.x = CTAs resident on the device), tile t handled by CTA t mod gridDim.x.
-// Software pipeline across tiles: the descriptor is fetched two tiles ahead, the connectivity of the
-// next tile's element is loaded into registers before the mid-tile barrier and its coordinates during
-// the gather phase, so phase 1 never waits on a dependent global load; the gather metadata of the
-// current tile arrives by TMA bulk copy while phase 1 computes.
+// One CTA per tile.  Per tile: (0) a TMA bulk copy brings the tile's gather metadata into shared memory
+// while (1) one thread per tile element computes the owned columns of its element matrix into the stage,
+// (2) one thread per owned nonzero sums its contributions from the stage left to right and stores nzval.
+// Overlap between the compute phase of one tile and the gather/store phase of another comes from the
+// CTAs co-resident on an SM.
 template <class F, bool S, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *__restrict__ tiles, int ntiles,
                                                             const int32_t *__restrict__ tconn, const uint16_t *__restrict__ tmask,
                                                             const double2 *__restrict__ xy, const unsigned char *__restrict__ meta,
-                                                            double *__restrict__ nzval)
+                                                            double *__restrict__ nzval, int stage_bytes, int meta_max)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ TileDescFull tds[3];
+    __shared__ TileDescFull td;
     __shared__ __align__(8) unsigned long long bar;
     constexpr int DW = (int)(sizeof(TileDescFull) / 8);
     constexpr int GK = F::GK;
+    constexpr int NW = BLOCK / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x;
-    int t = blockIdx.x;
-    if (t >= ntiles) return;
-    if (tid < DW) reinterpret_cast<int64_t *>(&tds[0])[tid] = reinterpret_cast<const int64_t *>(&tiles[t])[tid];
-    if (tid >= 32 && tid < 32 + DW && t + G < ntiles)
-        reinterpret_cast<int64_t *>(&tds[1])[tid - 32] = reinterpret_cast<const int64_t *>(&tiles[t + G])[tid - 32];
+    if (tid < DW) reinterpret_cast<int64_t *>(&td)[tid] = reinterpret_cast<const int64_t *>(&tiles[blockIdx.x])[tid];
     const uint32_t barA = tl_smem_addr(&bar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    if (td.nslot == 0) return;
+    double *stage = reinterpret_cast<double *>(smem_raw);
+    unsigned char *smeta = smem_raw + tl_align16(F::ND * td.nq * 8);
+    if (tid == 0) tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
+    const int nq = td.nq;
 
-    // coordinates + column mask of this thread's first-round element of the current tile
-    double PX[GK], PY[GK];
-    uint32_t pm = 0;
-    if (tid < tds[0].nelem) {
-        const int64_t g = tds[0].elem0 + tid;
+    // phase 1: one thread per tile element: owned columns of the element matrix -> stage
+    for (int le = tid; le < td.nelem; le += BLOCK) {
+        const int64_t g = td.elem0 + le;
+        double X[GK], Y[GK];
 #pragma unroll
-        for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); PX[a] = p.x; PY[a] = p.y; }
-        pm = tmask[g];
+        for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
+        StageEmit<F> emit{stage, td.qbase, (uint32_t)tmask[g], (uint32_t)le, nq};
+        F::template element<S>(X, Y, emit.m, emit);
     }
+    __syncthreads();
+    tl_mbar_wait(barA, 0);
 
-    for (int it = 0; t < ntiles; it++, t += G) {
-        const TileDescFull &td = tds[it % 3];
-        const bool active = td.nslot > 0;
-        // descriptor two tiles ahead: load now, park in shared memory before the mid-tile barrier
-        int64_t dword = 0;
-        const bool fetch_desc = (t + 2 * G < ntiles) && warp == BLOCK / 32 - 1 && lane < DW;
-        if (fetch_desc) dword = reinterpret_cast<const int64_t *>(&tiles[t + 2 * G])[lane];
-        const int nq = td.nq;
-        double *stage = reinterpret_cast<double *>(smem_raw);
-        unsigned char *smeta = smem_raw + tl_align16(F::ND * nq * 8);
-        if (tid == 0 && active) {   // TMA bulk copy of the tile's gather metadata; lands while phase 1 computes
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barA), "r"((uint32_t)td.meta_bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(tl_smem_addr(smeta)), "l"(meta + td.meta0), "r"((uint32_t)td.meta_bytes), "r"(barA) : "memory");
-        }
-
-        // phase 1: one thread per tile element: owned columns of the element matrix -> stage
-        if (tid < td.nelem) {
-            StageEmit<F> emit{stage, td.qbase, pm, (uint32_t)tid, nq};
-            F::template element<S>(PX, PY, pm, emit);
-        }
-        for (int le = tid + BLOCK; le < td.nelem; le += BLOCK) {    // rare: tiles with more elements than threads
-            const int64_t g = td.elem0 + le;
-            double X[GK], Y[GK];
+    // phase 2: every owned nonzero = left-to-right sum of its contributions (append order), stored once
+    {
+    const uint16_t *goff = reinterpret_cast<const uint16_t *>(smeta);
+    const uint16_t *gi = reinterpret_cast<const uint16_t *>(smeta + tl_meta_goff_bytes(td.nslot));
+    const TileRun *srun = reinterpret_cast<const TileRun *>(reinterpret_cast<const unsigned char *>(gi) + tl_meta_gidx_bytes(td.ncontrib));
+    const int nslot = td.nslot;
+    const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;
+    const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
+    int r = 0;
+    {
+        int lo = 0, hi = td.nrun - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= w0) lo = mid; else hi = mid - 1; }
+        r = lo;
+    }
+    int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
+    int64_t rnz = srun[r].nz0;
+    constexpr int U = 4;
+    for (int sb = w0; sb < w1; sb += 32 * U) {
+        int o0[U], c[U];
 #pragma unroll
-            for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
-            StageEmit<F> emit{stage, td.qbase, (uint32_t)tmask[g], (uint32_t)le, nq};
-            F::template element<S>(X, Y, emit.m, emit);
+        for (int u = 0; u < U; u++) {
+            const int s = sb + u * 32 + lane;
+            o0[u] = 0; c[u] = 0;
+            if (s < w1) { o0[u] = goff[s]; c[u] = (int)goff[s + 1] - o0[u]; }
         }
-        // next tile: connectivity of this thread's element into registers (coordinates follow in phase 2)
-        int32_t nc[GK];
-        uint32_t nm = 0;
-        bool have_next = false;
-        if (t + G < ntiles) {
-            const TileDescFull &dn = tds[(it + 1) % 3];
-            if (tid < dn.nelem) {
-                const int64_t g = dn.elem0 + tid;
+        double acc[U];
 #pragma unroll
-                for (int a = 0; a < GK; a++) nc[a] = tconn[g * GK + a];
-                nm = tmask[g];
-                have_next = true;
+        for (int u = 0; u < U; u++) {
+            acc[u] = 0.0;
+            if (c[u] >= 1 && c[u] <= TL_LIGHT) acc[u] = stage[gi[o0[u]]];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++)
+            if (c[u] == 2) acc[u] = __dadd_rn(acc[u], stage[gi[o0[u] + 1]]);
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int s = sb + u * 32 + lane;
+            if (s < w1) {
+                while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
+                if (c[u] <= TL_LIGHT) nzval[rnz + (s - rs0)] = acc[u];
             }
         }
-        if (fetch_desc) reinterpret_cast<int64_t *>(&tds[(it + 2) % 3])[lane] = dword;
-        __syncthreads();
-
-        if (active) {
-            {   // metadata has landed?
-                uint32_t done = 0;
-                const uint32_t parity = (uint32_t)(it & 1);
-                while (!done)
-                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                                 : "=r"(done) : "r"(barA), "r"(parity) : "memory");
-            }
-            // phase 2: every owned nonzero = left-to-right sum of its contributions (append order), stored once
-            const uint32_t stageA = tl_smem_addr(stage);
-            const uint32_t goffA = tl_smem_addr(smeta);
-            const uint32_t giA = goffA + tl_meta_goff_bytes(td.nslot);
-            const TileRun *srun = reinterpret_cast<const TileRun *>(smeta + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
-            constexpr int NW = BLOCK / 32;
-            const int nslot = td.nslot;
-            const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // contiguous slots per warp, multiple of 32
-            const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
-            int r = 0;
-            {   // run containing slot w0 (same search in every lane)
-                int lo = 0, hi = td.nrun - 1;
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= w0) lo = mid; else hi = mid - 1; }
-                r = lo;
-            }
-            int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
-            int64_t rnz = srun[r].nz0;
-            // light nonzeros (<= TL_LIGHT contributions: all but the matrix diagonals of node patches): straight-line
-            // code, 4 independent slots in flight per lane to cover the latency chain goff -> gidx -> stage
-            constexpr int U = 4;
-            const int wmid = w0 + (((w1 - w0) / 2 + 32 * U - 1) / (32 * U)) * (32 * U);
-            for (int half = 0; half < 2; half++) {
-                const int h0 = half == 0 ? w0 : min(wmid, w1), h1 = half == 0 ? min(wmid, w1) : w1;
-                for (int sb = h0; sb < h1; sb += 32 * U) {
-                    int o0[U], c[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int s = sb + u * 32 + lane;
-                        o0[u] = 0; c[u] = 0;
-                        if (s < h1) { o0[u] = (int)lds_u16(goffA + 2 * s); c[u] = (int)lds_u16(goffA + 2 * s + 2) - o0[u]; }
-                    }
-                    double acc[U];
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        acc[u] = 0.0;
-                        if (c[u] >= 1 && c[u] <= TL_LIGHT) acc[u] = lds_f64(stageA + 8 * lds_u16(giA + 2 * o0[u]));
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; u++)
-                        if (c[u] == 2) acc[u] = __dadd_rn(acc[u], lds_f64(stageA + 8 * lds_u16(giA + 2 * o0[u] + 2)));
-#pragma unroll
-                    for (int u = 0; u < U; u++) {
-                        const int s = sb + u * 32 + lane;
-                        if (s < h1) {
-                            while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
-                            if (c[u] <= TL_LIGHT) nzval[rnz + (s - rs0)] = acc[u];
-                        }
-                    }
-                }
-                if (half == 0 && have_next) {   // coordinates of the next tile's element: in flight during the second half
-#pragma unroll
-                    for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[nc[a]]); PX[a] = p.x; PY[a] = p.y; }
-                }
-            }
-            // heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum
-            const uint32_t heavyA = tl_smem_addr(srun) + td.nrun * (int)sizeof(TileRun);
-            for (int h = tid; h < td.nheavy; h += BLOCK) {
-                const int s = (int)lds_u16(heavyA + 2 * h);
-                const int o0 = (int)lds_u16(goffA + 2 * s), o1 = (int)lds_u16(goffA + 2 * s + 2);
-                double acc = lds_f64(stageA + 8 * lds_u16(giA + 2 * o0));
-                for (int k = o0 + 1; k < o1; k++) acc = __dadd_rn(acc, lds_f64(stageA + 8 * lds_u16(giA + 2 * k)));
-                int lo = 0, hi = td.nrun - 1;
-                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
-                nzval[srun[lo].nz0 + (s - srun[lo].s0)] = acc;
-            }
-        } else if (have_next) {
-#pragma unroll
-            for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[nc[a]]); PX[a] = p.x; PY[a] = p.y; }
-        }
-        pm = nm;
-        __syncthreads();    // stage, metadata and tds[it % 3] are free again
+    }
+    const uint16_t *heavy = reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(srun) + td.nrun * (int)sizeof(TileRun));
+    for (int h = tid; h < td.nheavy; h += BLOCK) {
+        const int s = heavy[h];
+        const int o0 = goff[s], o1 = goff[s + 1];
+        double acc = stage[gi[o0]];
+        for (int k = o0 + 1; k < o1; k++) acc = __dadd_rn(acc, stage[gi[k]]);
+        int lo = 0, hi = td.nrun - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
+        nzval[srun[lo].nz0 + (s - srun[lo].s0)] = acc;
+    }
     }
 }
 
 // ---- host: symbolic ---------------------------------------------------------------------------------
+// Tile sizes tried in turn (largest first): powers of two and 3*2^k keep space-filling-curve tiles compact
+// (a 256-element T6 tile is a 16 x 8 block of cells).  The first size whose shared-memory footprint lets two
+// CTAs share an SM is used.
+static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 48, 32};
+#define TL_SMEM_TWO_CTAS (114 * 1024 + 512)
 template <class F> static int tl_default_tile_elems()
 {
-    // shared memory per owned element-equivalent: stage ND*ND*8 + gather metadata ~ NT*2 + 3*ND*ND;
-    // aim at ~96 KB per CTA so two CTAs share an SM
-    int te = (96 * 1024) / (F::ND * F::ND * 8 + F::NT * 2 + 3 * F::ND * F::ND);
-    if (te > 512) te = 512;
-    if (te < 32) te = 32;
-    return te & ~7;
+    // shared memory per owned element-equivalent ~ stage ND*ND*8 + gather metadata NT*2 + ~2.7*ND*ND
+    const double per_elem = F::ND * F::ND * 10.7 + F::NT * 2.0;
+    for (int te : TL_TILE_SIZES)
+        if (te * per_elem <= 118.0 * 1024) return te;
+    return 32;
 }
 
+template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te);
+
 template <class F> void tiled_symbolic(efg_ctx *ctx)
+{
+    if (ctx->opt_tile_elems > 0) { tiled_symbolic_te<F>(ctx, ctx->opt_tile_elems); return; }
+    int te = tl_default_tile_elems<F>();
+    for (;;) {
+        try {
+            tiled_symbolic_te<F>(ctx, te);
+            if (tiled_data(ctx)->smem_bytes <= TL_SMEM_TWO_CTAS || te <= 32) return;
+        } catch (const EfgError &e) {
+            if (e.code != EFG_ERR_LIMIT || te <= 32) throw;
+        }
+        int next = 32;
+        for (int c : TL_TILE_SIZES) if (c < te) { next = c; break; }
+        te = next;
+        tiled_release(ctx);
+        ctx->rowval.release(); ctx->colptr.release(); ctx->nzval.release();
+    }
+}
+
+template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
 {
     static_assert(F::ND <= TL_MAXND, "");
     constexpr int ND = F::ND;
@@ -739,7 +698,6 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
         efg_throw(EFG_ERR_INDEX, "ArgumentError: a dof number is < 1 or exceeds nrow/ncol (was every space numbered, incl. data dofs?)");
 
     // T1: element order -> tile of each element
-    int te = ctx->opt_tile_elems > 0 ? ctx->opt_tile_elems : tl_default_tile_elems<F>();
     const int ntiles = (int)((nel + te - 1) / te);
     DevBuf<int32_t> etile;
     etile.alloc(pool, (size_t)nel);
@@ -903,9 +861,11 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
         efg_throw(EFG_ERR_LIMIT, "tiled path: a tile stages %d element-matrix entries (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[1]);
     if (hmax[2] > 65535)
         efg_throw(EFG_ERR_LIMIT, "tiled path: a tile gathers %d contributions (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[2]);
-    if (hmax[0] > 225 * 1024)
-        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile needs %d bytes of shared memory; lower EFG_OPT_TILE_ELEMS", hmax[0]);
-    td->smem_bytes = hmax[0];
+    td->stage_bytes = 0;
+    td->meta_max = 0;
+    td->smem_bytes = hmax[0];                                  // max over tiles of (stage + gather metadata)
+    if (td->smem_bytes > 225 * 1024)
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile needs %d bytes of shared memory; lower EFG_OPT_TILE_ELEMS", td->smem_bytes);
     td->meta_bytes = meta_total;
 
     // T8: gather lists into the metadata blocks
@@ -933,11 +893,11 @@ template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
     CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
     if (per_sm < 1) efg_throw(EFG_ERR_LIMIT, "tiled path: the numeric kernel does not fit on an SM (%d bytes of shared memory)", td->smem_bytes);
-    int grid = per_sm * nsm;                      // persistent: one CTA per resident slot
-    if (grid > ctx->tl.ntiles) grid = ctx->tl.ntiles;
+    (void)nsm;
+    int grid = ctx->tl.ntiles;                    // one CTA per tile
     if (grid > 0)
         LAUNCH(ctx, kern, (unsigned)grid, BLOCK, (size_t)td->smem_bytes, td->tiles.p, ctx->tl.ntiles, td->tconn.p, td->tmask.p, gm.xy.p,
-               td->meta.p, ctx->nzval.p);
+               td->meta.p, ctx->nzval.p, td->stage_bytes, td->meta_max);
     ctx->numeric_launches += 1;
 }
 template <class F, bool S> static void tl_launch_numeric(efg_ctx *ctx)
