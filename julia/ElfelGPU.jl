@@ -1,0 +1,108 @@
+# ElfelGPU.jl -- Julia-side shim selecting the B200 assembler in place of SysmatAssemblerSparse.
+#
+# SHIPPED UNEXECUTED: no Julia runtime exists in the build/test image, so this file has never been run.
+# It binds exactly the C ABI of include/elfel_gpu.h, which IS exercised (through Python ctypes) by tests/
+# and bench.py.  Drop it next to a checkout of Elfel.jl and `include("ElfelGPU.jl")`.
+module ElfelGPU
+
+using SparseArrays: SparseMatrixCSC
+using Elfel.Assemblers: AbstractSysmatAssembler
+import Elfel.Assemblers: start!, assemble!, finish!
+using Elfel.FEIterators: FEIterator
+using Elfel.QPIterators: QPIterator
+using Elfel.RefShapes: npts
+
+const LIB = get(ENV, "ELFELGPU_LIB", "libelfelgpu.so")
+
+# weak forms = the integrate! closures of the examples
+struct HeatForm;            kappa::Float64; end                 # examples/heat/poisson/t3.jl:53-58
+struct ElasticityForm;      D::Matrix{Float64}; end             # examples/elasticity/stretch/t6.jl:42-58
+struct StokesGenForm;       D::Matrix{Float64}; end             # examples/stokes/colliding_flow/ht_p2_p1_gen.jl
+struct StokesReddyForm;     mu::Float64; end                    # .../ht_p2_p1.jl
+struct StokesVeclapAltForm; mu::Float64; end                    # .../ht_p2_p1_veclap_alt.jl
+struct StokesVeclapForm;    mu::Float64; end                    # .../ht_p2_p1_veclap.jl
+formid(::HeatForm) = 1; formid(::ElasticityForm) = 2; formid(::StokesGenForm) = 3
+formid(::StokesReddyForm) = 4; formid(::StokesVeclapAltForm) = 5; formid(::StokesVeclapForm) = 6
+params(f::HeatForm) = [f.kappa]
+params(f::Union{ElasticityForm,StokesGenForm}) = vec(collect(Float64, f.D))     # column-major 3x3
+params(f::Union{StokesReddyForm,StokesVeclapAltForm,StokesVeclapForm}) = [f.mu]
+
+mutable struct SysmatAssemblerGPU <: AbstractSysmatAssembler
+    ctx::Ptr{Cvoid}
+    nrow::Int64
+    ncol::Int64
+    nnz::Int64
+    function SysmatAssemblerGPU(zero::Float64 = 0.0; device::Integer = 0)
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:efg_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r)
+        rc == 0 || error("efg_create failed ($rc): no usable CUDA device (there is no CPU fallback)")
+        a = new(r[], 0, 0, 0)
+        finalizer(x -> ccall((:efg_destroy, LIB), Cint, (Ptr{Cvoid},), x.ctx), a)
+        return a
+    end
+end
+
+function _check(a::SysmatAssemblerGPU, rc)
+    rc == 0 && return
+    msg = unsafe_string(ccall((:efg_last_error, LIB), Cstring, (Ptr{Cvoid},), a.ctx))
+    rc == -4 ? throw(ArgumentError(msg)) : error("libelfelgpu error $rc: $msg")
+end
+
+"start!(ass, nrow, ncol) -- src/Assemblers.jl:67-78"
+function start!(a::SysmatAssemblerGPU, nrow, ncol)
+    a.nrow, a.ncol = nrow, ncol
+    _check(a, ccall((:efg_start, LIB), Cint, (Ptr{Cvoid}, Int64, Int64), a.ctx, nrow, ncol))
+    return a
+end
+
+_kind(it::FEIterator) = length(it._nodes)            # 3 = T3, 4 = Q4, 6 = T6
+_rule(q::QPIterator, kind) = kind == 4 ? isqrt(npts(q._quadr)) : npts(q._quadr)
+
+"""
+    assemble!(ass, form, elits, qpits)
+
+Replaces the whole `for el in elit ... assemble!(ass, ke) end` loop of the examples.  `elits`/`qpits` are
+one iterator (heat, elasticity) or a tuple in space order (Stokes: (uel, pel) or (uxel, uyel, pel)).
+"""
+function assemble!(a::SysmatAssemblerGPU, form, elits, qpits)
+    elits isa FEIterator && (elits = (elits,); qpits = (qpits,))
+    meshes = Any[]
+    for it in elits
+        any(m -> m === it._bir, meshes) || push!(meshes, it._bir)
+    end
+    GC.@preserve elits begin
+        for (slot, it) in enumerate(elits)
+            mslot = findfirst(m -> m === it._bir, meshes)
+            if count(j -> elits[j]._bir === it._bir, 1:slot) == 1      # first space on this mesh: send the mesh
+                conn = reinterpret(Int64, it._bir._v)                  # nen x nel, contiguous SVector storage
+                xy = reinterpret(Float64, it._geom.v)                  # 2 x nnodes
+                _check(a, ccall((:efg_set_mesh, LIB), Cint,
+                                (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Int64}, Ptr{Float64}),
+                                a.ctx, mslot - 1, _kind(it), length(it), length(it._geom), conn, xy))
+            end
+            dof = reinterpret(Int64, it._fld0.dofnums)                 # ncomp x nnodes
+            ncomp = length(eltype(it._fld0.dofnums))
+            _check(a, ccall((:efg_set_space, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Int64, Ptr{Int64}),
+                            a.ctx, slot - 1, mslot - 1, ncomp, length(it._fld0.dofnums), dof))
+        end
+        _check(a, ccall((:efg_start, LIB), Cint, (Ptr{Cvoid}, Int64, Int64), a.ctx, a.nrow, a.ncol))
+        p = params(form)
+        nnz = Ref{Int64}(0)
+        _check(a, ccall((:efg_assemble, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Cint, Ref{Int64}),
+                        a.ctx, formid(form), _rule(qpits[1], _kind(elits[1])), p, length(p), nnz))
+        a.nnz = nnz[]
+    end
+    return a
+end
+
+"finish!(ass) -- src/Assemblers.jl:121-123: the arrays are allocated here and filled by the library (no copy)."
+function finish!(a::SysmatAssemblerGPU)
+    colptr = Vector{Int64}(undef, a.ncol + 1)
+    rowval = Vector{Int64}(undef, a.nnz)
+    nzval = Vector{Float64}(undef, a.nnz)
+    _check(a, ccall((:efg_fetch_csc, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                    a.ctx, colptr, rowval, nzval))
+    return SparseMatrixCSC(a.nrow, a.ncol, colptr, rowval, nzval)
+end
+
+end # module
