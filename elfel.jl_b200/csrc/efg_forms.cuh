@@ -168,6 +168,7 @@ template <bool S> __device__ __forceinline__ double dotB(const double (&db)[3], 
 // K1 heat: ke[i,j] += dot(gradN[i], gradN[j]) * (kappa * JxW)   examples/heat/poisson/t3.jl:53-58
 template <int VK, int NQ_> struct HeatForm {
     static constexpr int ND = VK, NT = VK * VK, GK = VK, BK = VK, NQ = NQ_, GMESH = 0, NSPACES = 1;
+    static constexpr bool SPLIT = false;
     __host__ __device__ static constexpr bool mask(int, int) { return true; }
     __host__ __device__ static constexpr int kidx(int i, int j) { return j * ND + i; }
     __device__ static void edofs(const DofSrc &s, int64_t e, int32_t (&d)[ND]) {
@@ -225,10 +226,17 @@ template <int VK, int NQ_> struct ElasticityForm {
             d[2 * a] = s.dof0[2 * n]; d[2 * a + 1] = s.dof0[2 * n + 1];
         }
     }
-    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<BK, NQ> &G, double (&out)[ND]) {
+    // SPLIT forms: phase 1 runs as (a) one thread per element: geometry -> shared memory, (b) one thread per
+    // staged column: column_rt() with the column index known only at run time (gjx/gjy = gradients of the
+    // column's node).  column<S,J>() is the same arithmetic with J known at compile time.
+    static constexpr bool SPLIT = true;
+    __device__ __forceinline__ static int colnode(int J) { return J >> 1; }
+    template <bool S> __device__ __forceinline__ static void column_rt(const Geo<BK, NQ> &G, int J, const double (&gjx)[NQ],
+                                                                        const double (&gjy)[NQ], double (&out)[ND]) {
+        const int cj = J & 1;
         double db[NQ][3];
 #pragma unroll
-        for (int q = 0; q < NQ; q++) DB<S>(c_prm, J % 2, G.gx[q][J / 2], G.gy[q][J / 2], db[q]);
+        for (int q = 0; q < NQ; q++) DB<S>(c_prm, cj, gjx[q], gjy[q], db[q]);
 #pragma unroll
         for (int i = 0; i < ND; i++) {
             double acc = 0.0;
@@ -239,6 +247,12 @@ template <int VK, int NQ_> struct ElasticityForm {
             }
             out[i] = acc;
         }
+    }
+    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<BK, NQ> &G, double (&out)[ND]) {
+        double gjx[NQ], gjy[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) { gjx[q] = G.gx[q][J / 2]; gjy[q] = G.gy[q][J / 2]; }
+        column_rt<S>(G, J, gjx, gjy, out);
     }
 };
 
@@ -272,13 +286,17 @@ template <bool VECLAP_ALT> struct Stokes2Form {
 #pragma unroll
         for (int m = 0; m < 3; m++) d[12 + m] = s.dof1[s.conn1[e * 3 + m]];
     }
-    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<6, 3> &G, double (&out)[ND]) {
+    static constexpr bool SPLIT = true;
+    __device__ __forceinline__ static int colnode(int J) { return J < 12 ? (J >> 1) : 0; }
+    template <bool S> __device__ __forceinline__ static void column_rt(const Geo<6, 3> &G, int J, const double (&gjx)[3],
+                                                                        const double (&gjy)[3], double (&out)[ND]) {
         const QTab &tp = c_tab[kind_slot(3)];
-        if constexpr (J < 12) {
+        if (J < 12) {
+            const int cj = J & 1;
             if constexpr (!VECLAP_ALT) {
                 double db[3][3];
 #pragma unroll
-                for (int q = 0; q < 3; q++) DB<S>(c_prm, J % 2, G.gx[q][J / 2], G.gy[q][J / 2], db[q]);
+                for (int q = 0; q < 3; q++) DB<S>(c_prm, cj, gjx[q], gjy[q], db[q]);
 #pragma unroll
                 for (int i = 0; i < 12; i++) {
                     double acc = 0.0;
@@ -294,12 +312,11 @@ template <bool VECLAP_ALT> struct Stokes2Form {
 #pragma unroll
                 for (int i = 0; i < 12; i++) {
                     double acc = 0.0;
-                    if (i % 2 == J % 2) {
+                    if (i % 2 == cj) {
 #pragma unroll
                         for (int q = 0; q < 3; q++) {
                             const double t = fmul<S>(fmul<S>(mu, G.JxW[q]),
-                                                     fadd<S>(fmul<S>(G.gx[q][i / 2], G.gx[q][J / 2]),
-                                                             fmul<S>(G.gy[q][i / 2], G.gy[q][J / 2])));
+                                                     fadd<S>(fmul<S>(G.gx[q][i / 2], gjx[q]), fmul<S>(G.gy[q][i / 2], gjy[q])));
                             acc = q == 0 ? t : fadd<S>(acc, t);
                         }
                     }
@@ -312,14 +329,14 @@ template <bool VECLAP_ALT> struct Stokes2Form {
                 double acc = 0.0;
 #pragma unroll
                 for (int q = 0; q < 3; q++) {
-                    const double gj = (J % 2 == 0) ? G.gx[q][J / 2] : G.gy[q][J / 2];
+                    const double gj = (cj == 0) ? gjx[q] : gjy[q];
                     const double t = fmul<S>(fmul<S>(-G.JxW[q], tp.N[q][m]), gj);
                     acc = q == 0 ? t : fadd<S>(acc, t);
                 }
                 out[12 + m] = acc;
             }
         } else {
-            constexpr int m = J - 12;
+            const int m = J - 12;
 #pragma unroll
             for (int i = 0; i < 12; i++) {
                 double acc = 0.0;
@@ -334,6 +351,12 @@ template <bool VECLAP_ALT> struct Stokes2Form {
             out[12] = out[13] = out[14] = 0.0;
         }
     }
+    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<6, 3> &G, double (&out)[ND]) {
+        double gjx[3], gjy[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) { gjx[q] = G.gx[q][J < 12 ? J / 2 : 0]; gjy[q] = G.gy[q][J < 12 ? J / 2 : 0]; }
+        column_rt<S>(G, J, gjx, gjy, out);
+    }
 };
 
 // K4 Reddy: examples/stokes/colliding_flow/ht_p2_p1.jl:77-101 (Jacobian of the PRESSURE element);
@@ -341,6 +364,7 @@ template <bool VECLAP_ALT> struct Stokes2Form {
 template <bool VECLAP> struct Stokes3Form {
     static constexpr int VK = 6, PK = 3, NQ = 3;
     static constexpr int ND = 15, NT = VECLAP ? 144 : 216, GK = 3, BK = 6, GMESH = 1, NSPACES = 3;
+    static constexpr bool SPLIT = false;
     template <bool S, class Emit>
     __device__ __forceinline__ static void element(const double (&X)[GK], const double (&Y)[GK], uint32_t m, Emit &emit) {
         element_generic<Stokes3Form<VECLAP>, S, Emit>(X, Y, m, emit);

@@ -44,6 +44,10 @@ static_assert(sizeof(TileDescFull) % 8 == 0, "TileDescFull is copied as 8-byte w
 // metadata block of a tile: [goff: u16 x (nslot+1)] [gidx: u16 x ncontrib] [runs: TileRun x nrun] [heavy: u16 x nheavy],
 // each part 16-byte aligned
 __host__ __device__ static inline int tl_align16(int b) { return (b + 15) & ~15; }
+// SPLIT forms keep per-element geometry (gradients + JxW at every quadrature point, SoA) and the column masks in
+// shared memory between the two steps of phase 1
+template <class F> __host__ __device__ constexpr int tl_gsz() { return F::SPLIT ? F::NQ * (2 * F::BK + 1) : 0; }
+__host__ __device__ static inline int tl_geo_bytes(int gsz, int nelem) { return gsz ? tl_align16(nelem * (gsz * 8 + 2)) : 0; }
 __host__ __device__ static inline int tl_meta_goff_bytes(int nslot) { return tl_align16(2 * (nslot + 1)); }
 __host__ __device__ static inline int tl_meta_gidx_bytes(int nc) { return tl_align16(2 * nc); }
 
@@ -466,7 +470,7 @@ __global__ void k_tl_tiles_meta0(int ntiles, const int64_t *__restrict__ meta_of
     GRID_STRIDE(T, ntiles) tiles[T].meta0 = meta_off[T];
 }
 
-__global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ tcol_slot,
+__global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ tcol_slot,
                                 const int64_t *__restrict__ tcol_gidx, const int64_t *__restrict__ tcol_heavy, const int64_t *__restrict__ telem_ptr,
                                 const int64_t *__restrict__ run_of_k /* exclusive scan of run-head flags */,
                                 int64_t nowned, int64_t nruns, const uint32_t *__restrict__ pc_hist, TileDescFull *__restrict__ tiles,
@@ -499,7 +503,7 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, const int64_t *__restrict__ 
         d.pad2_[0] = d.pad2_[1] = d.pad2_[2] = 0;
         tiles[T] = d;
         meta_bytes[T] = d.meta_bytes;
-        atomicMax(&maxima[0], tl_align16(d.nq * nd * 8) + d.meta_bytes);
+        atomicMax(&maxima[0], tl_align16(d.nq * nd * 8) + max(tl_geo_bytes(gsz, d.nelem), d.meta_bytes));
         atomicMax(&maxima[1], (int32_t)((int64_t)d.nq * nd > 0x7fffffff ? 0x7fffffff : d.nq * nd));
         atomicMax(&maxima[2], d.ncontrib); atomicMax(&maxima[3], d.nelem);
     }
@@ -563,20 +567,82 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     __syncthreads();
     if (td.nslot == 0) return;
     double *stage = reinterpret_cast<double *>(smem_raw);
+    constexpr int GSZ = tl_gsz<F>();
+    // SPLIT forms: the per-element geometry of phase 1 and the gather metadata of phase 2 share the same shared-memory
+    // area, so the TMA copy is issued after phase 1; otherwise it is issued now and lands while phase 1 computes
     unsigned char *smeta = smem_raw + tl_align16(F::ND * td.nq * 8);
-    if (tid == 0) tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
+    if (!F::SPLIT && tid == 0) tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
     const int nq = td.nq;
 
-    // phase 1: one thread per tile element: owned columns of the element matrix -> stage
-    for (int le = tid; le < td.nelem; le += BLOCK) {
-        const int64_t g = td.elem0 + le;
-        double X[GK], Y[GK];
+    if constexpr (!F::SPLIT) {
+        // phase 1: one thread per tile element: owned columns of the element matrix -> stage
+        for (int le = tid; le < td.nelem; le += BLOCK) {
+            const int64_t g = td.elem0 + le;
+            double X[GK], Y[GK];
 #pragma unroll
-        for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
-        StageEmit<F> emit{stage, td.qbase, (uint32_t)tmask[g], (uint32_t)le, nq};
-        F::template element<S>(X, Y, emit.m, emit);
+            for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
+            StageEmit<F> emit{stage, td.qbase, (uint32_t)tmask[g], (uint32_t)le, nq};
+            F::template element<S>(X, Y, emit.m, emit);
+        }
+    } else {
+        // phase 1a: one thread per tile element: Jacobian / JxW / gradients at every quadrature point -> shared memory
+        constexpr int NQ = F::NQ, BK = F::BK;
+        const int ne = td.nelem;
+        double *Gs = reinterpret_cast<double *>(smem_raw + tl_align16(F::ND * nq * 8));   // SoA: Gs[k * ne + le]
+        uint16_t *smask = reinterpret_cast<uint16_t *>(Gs + GSZ * ne);
+        for (int le = tid; le < ne; le += BLOCK) {
+            const int64_t g = td.elem0 + le;
+            double X[GK], Y[GK];
+#pragma unroll
+            for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
+            Geo<BK, NQ> G;
+            geo_compute<S, GK, BK, NQ>(X, Y, G);
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+#pragma unroll
+                for (int n = 0; n < BK; n++) {
+                    Gs[(q * BK + n) * ne + le] = G.gx[q][n];
+                    Gs[(NQ * BK + q * BK + n) * ne + le] = G.gy[q][n];
+                }
+                Gs[(2 * NQ * BK + q) * ne + le] = G.JxW[q];
+            }
+            smask[le] = tmask[g];
+        }
+        __syncthreads();
+        // phase 1b: one thread per staged column (tile element, owned local column) -> stage
+        for (int qc = tid; qc < nq; qc += BLOCK) {
+            int r = 0;
+            while (r + 1 < F::ND && (int)td.qbase[r + 1] <= qc) r++;
+            const int le = qc - (int)td.qbase[r];
+            uint32_t mm = smask[le];
+            for (int t = 0; t < r; t++) mm &= mm - 1;
+            const int J = __ffs(mm) - 1;
+            Geo<BK, NQ> G;
+            double gjx[NQ], gjy[NQ];
+            const int nj = F::colnode(J);
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+#pragma unroll
+                for (int n = 0; n < BK; n++) {
+                    G.gx[q][n] = Gs[(q * BK + n) * ne + le];
+                    G.gy[q][n] = Gs[(NQ * BK + q * BK + n) * ne + le];
+                }
+                G.JxW[q] = Gs[(2 * NQ * BK + q) * ne + le];
+                gjx[q] = Gs[(q * BK + nj) * ne + le];
+                gjy[q] = Gs[(NQ * BK + q * BK + nj) * ne + le];
+            }
+            double out[F::ND];
+            F::template column_rt<S>(G, J, gjx, gjy, out);
+#pragma unroll
+            for (int i = 0; i < F::ND; i++)
+                if (F::mask(i, J)) stage[i * nq + qc] = out[i];
+        }
     }
     __syncthreads();
+    if (F::SPLIT && tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the area are done (barrier above)
+        tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
+    }
     tl_mbar_wait(barA, 0);
 
     // phase 2: every owned nonzero = left-to-right sum of its contributions (append order), stored once
@@ -644,7 +710,7 @@ static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 48, 32};
 template <class F> static int tl_default_tile_elems()
 {
     // shared memory per owned element-equivalent ~ stage ND*ND*8 + gather metadata NT*2 + ~2.7*ND*ND
-    const double per_elem = F::ND * F::ND * 10.7 + F::NT * 2.0;
+    const double per_elem = F::ND * F::ND * 10.7 + F::NT * 2.0;   // (SPLIT forms: the geometry area aliases the metadata area)
     for (int te : TL_TILE_SIZES)
         if (te * per_elem <= 118.0 * 1024) return te;
     return 32;
@@ -848,7 +914,7 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     CUDA_CHECK(cudaMemsetAsync(maxima.p, 0, 4 * sizeof(int32_t), st));
     CUDA_CHECK(cudaMemsetAsync(mbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     td->tiles.alloc(pool, (size_t)ntiles);
-    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tcol_ptr.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
+    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tl_gsz<F>(), tcol_ptr.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
            nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
     tl_excl_scan(ctx, mbytes.p, moff.p, (int64_t)ntiles + 1);
     const int64_t meta_total = tl_read(ctx, moff.p + ntiles);
