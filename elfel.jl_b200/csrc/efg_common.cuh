@@ -33,21 +33,25 @@ struct EfgError {
                       "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
     } while (0)
 
-// Device allocation owned by a ctx; tracks the total held.
+// Device allocations owned by a ctx, stream-ordered (cudaMallocAsync / cudaFreeAsync on the ctx stream with a
+// never-trimmed pool): the symbolic phase allocates and frees many multi-GB temporaries and plain
+// cudaMalloc/cudaFree (device-synchronising, unmapping) made its time vary by 10x.
 struct DevPool {
     int64_t bytes = 0;
+    cudaStream_t stream = nullptr;
     void *alloc(size_t n)
     {
         void *p = nullptr;
         if (n == 0) n = 8;
-        cudaError_t e = cudaMalloc(&p, n);
+        cudaError_t e = cudaMallocAsync(&p, n, stream);
         if (e != cudaSuccess) {
             cudaGetLastError();
-            efg_throw(EFG_ERR_OOM, "cudaMalloc of %zu bytes failed: %s", n, cudaGetErrorString(e));
+            efg_throw(EFG_ERR_OOM, "cudaMallocAsync of %zu bytes failed: %s", n, cudaGetErrorString(e));
         }
         bytes += (int64_t)n;
         return p;
     }
+    void free(void *p) { cudaFreeAsync(p, stream); }
 };
 
 template <class T> struct DevBuf {
@@ -71,8 +75,7 @@ template <class T> struct DevBuf {
     void release()
     {
         if (p) {
-            cudaFree(p);
-            if (pool) pool->bytes -= held;
+            if (pool) { pool->free(p); pool->bytes -= held; } else cudaFree(p);
         }
         p = nullptr; n = 0; held = 0;
     }

@@ -37,7 +37,8 @@ struct TileDescFull {
     int32_t nheavy;         // owned nonzeros with more than TL_LIGHT contributions
     int64_t heavy0;         // first heavy entry in tile order (symbolic phase only)
     uint16_t qbase[TL_MAXND + 1]; // qbase[r] = first staged column of "r-th owned column of an element"
-    uint16_t pad2_[3];
+    uint16_t nqs;           // stage row stride: nq rounded up to an odd number (rows i of one staged column fall in distinct banks)
+    uint16_t pad2_[2];
 };
 static_assert(sizeof(TileDescFull) % 8 == 0, "TileDescFull is copied as 8-byte words");
 
@@ -49,7 +50,7 @@ __host__ __device__ static inline int tl_align16(int b) { return (b + 15) & ~15;
 template <class F> __host__ __device__ constexpr int tl_gsz() { return F::SPLIT ? F::NQ * (2 * F::BK + 1) : 0; }
 __host__ __device__ static inline int tl_geo_bytes(int gsz, int nelem) { return gsz ? tl_align16(nelem * (gsz * 8 + 2)) : 0; }
 __host__ __device__ static inline int tl_meta_goff_bytes(int nslot) { return tl_align16(2 * (nslot + 1)); }
-__host__ __device__ static inline int tl_meta_gidx_bytes(int nc) { return tl_align16(2 * nc); }
+__host__ __device__ static inline int tl_meta_gidx_bytes(int nc) { return tl_align16(2 * (nc + 1)); }   // one zero pad entry
 
 struct TiledData {
     DevBuf<TileDescFull> tiles;
@@ -85,8 +86,7 @@ static void tl_sort_pairs(efg_ctx *ctx, const K *kin, K *kout, const V *vin, V *
     tmp.alloc(ctx->pool, tb);
     CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp.p, tb, kin, kout, vin, vout, n, 0, end_bit, ctx->stream));
     ctx->launches += (end_bit + 7) / 8 + 2;
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-}
+}   // temporaries are freed stream-ordered: no synchronisation needed
 template <class K> static void tl_sort_keys(efg_ctx *ctx, const K *kin, K *kout, int64_t n, int end_bit)
 {
     size_t tb = 0;
@@ -95,8 +95,7 @@ template <class K> static void tl_sort_keys(efg_ctx *ctx, const K *kin, K *kout,
     tmp.alloc(ctx->pool, tb);
     CUDA_CHECK(cub::DeviceRadixSort::SortKeys(tmp.p, tb, kin, kout, n, 0, end_bit, ctx->stream));
     ctx->launches += (end_bit + 7) / 8 + 2;
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-}
+}   // temporaries are freed stream-ordered: no synchronisation needed
 template <class In, class Out> static void tl_excl_scan(efg_ctx *ctx, In in, Out out, int64_t n)
 {
     size_t tb = 0;
@@ -105,7 +104,6 @@ template <class In, class Out> static void tl_excl_scan(efg_ctx *ctx, In in, Out
     tmp.alloc(ctx->pool, tb);
     CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, n, ctx->stream));
     ctx->launches += 2;
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
 }
 static inline int bits_for(int64_t maxval)
 {
@@ -444,7 +442,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                 const int32_t r = edof[(int64_t)e * F::ND + i];
                 int l2 = 0, h2 = nr;
                 while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (rowval[r0 + mid] < r) l2 = mid + 1; else h2 = mid; }
-                const uint32_t sidx = (uint32_t)i * (uint32_t)td.nq + q;
+                const uint32_t sidx = (uint32_t)i * (uint32_t)td.nqs + q;
                 if (sidx > 65535u) *err = 4;
                 gidx[off[l2]] = (uint16_t)sidx;
                 off[l2]++;
@@ -498,13 +496,14 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, const int64_t *__re
         uint32_t q = 0;
         for (int r = 0; r <= TL_MAXND; r++) { d.qbase[r] = (uint16_t)(q > 65535u ? 65535u : q); if (r < TL_MAXND) q += above[r]; }
         d.nq = (int32_t)q;
+        d.nqs = (uint16_t)((q | 1u) > 65535u ? 65535u : (q | 1u));
         d.meta_bytes = d.nslot > 0 ? tl_meta_goff_bytes(d.nslot) + tl_meta_gidx_bytes(d.ncontrib) + d.nrun * (int)sizeof(TileRun) + tl_align16(2 * d.nheavy) : 0;
         d.meta0 = 0;
-        d.pad2_[0] = d.pad2_[1] = d.pad2_[2] = 0;
+        d.pad2_[0] = d.pad2_[1] = 0;
         tiles[T] = d;
         meta_bytes[T] = d.meta_bytes;
-        atomicMax(&maxima[0], tl_align16(d.nq * nd * 8) + max(tl_geo_bytes(gsz, d.nelem), d.meta_bytes));
-        atomicMax(&maxima[1], (int32_t)((int64_t)d.nq * nd > 0x7fffffff ? 0x7fffffff : d.nq * nd));
+        atomicMax(&maxima[0], tl_align16(d.nqs * nd * 8) + max(tl_geo_bytes(gsz, d.nelem), d.meta_bytes));
+        atomicMax(&maxima[1], (int32_t)(((int64_t)q | 1) * nd > 0x7fffffff ? 0x7fffffff : ((int64_t)q | 1) * nd));
         atomicMax(&maxima[2], d.ncontrib); atomicMax(&maxima[3], d.nelem);
     }
 }
@@ -558,6 +557,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     constexpr int GK = F::GK;
     constexpr int NW = BLOCK / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#if defined(TL_EARLY) && TL_EARLY
+    // this thread's first element: start the dependent connectivity -> coordinate loads straight from the global
+    // descriptor, before the descriptor is staged in shared memory and the block synchronises
+    double EX[GK], EY[GK];
+    uint32_t em = 0;
+    if (!F::SPLIT) {
+        const int64_t e0g = tiles[blockIdx.x].elem0;
+        if (tid < tiles[blockIdx.x].nelem) {
+            const int64_t g = e0g + tid;
+#pragma unroll
+            for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); EX[a] = p.x; EY[a] = p.y; }
+            em = tmask[g];
+        }
+    }
+#endif
     if (tid < DW) reinterpret_cast<int64_t *>(&td)[tid] = reinterpret_cast<const int64_t *>(&tiles[blockIdx.x])[tid];
     const uint32_t barA = tl_smem_addr(&bar);
     if (tid == 0) {
@@ -570,13 +584,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     constexpr int GSZ = tl_gsz<F>();
     // SPLIT forms: the per-element geometry of phase 1 and the gather metadata of phase 2 share the same shared-memory
     // area, so the TMA copy is issued after phase 1; otherwise it is issued now and lands while phase 1 computes
-    unsigned char *smeta = smem_raw + tl_align16(F::ND * td.nq * 8);
+    unsigned char *smeta = smem_raw + tl_align16(F::ND * td.nqs * 8);
     if (!F::SPLIT && tid == 0) tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
-    const int nq = td.nq;
+    const int nq = td.nqs;      // stage row stride (odd)
+    const int ncols = td.nq;    // staged columns
 
     if constexpr (!F::SPLIT) {
         // phase 1: one thread per tile element: owned columns of the element matrix -> stage
+#if defined(TL_EARLY) && TL_EARLY
+        if (tid < td.nelem) {
+            StageEmit<F> emit{stage, td.qbase, em, (uint32_t)tid, nq};
+            F::template element<S>(EX, EY, em, emit);
+        }
+        for (int le = tid + BLOCK; le < td.nelem; le += BLOCK) {
+#else
         for (int le = tid; le < td.nelem; le += BLOCK) {
+#endif
             const int64_t g = td.elem0 + le;
             double X[GK], Y[GK];
 #pragma unroll
@@ -610,7 +633,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
         }
         __syncthreads();
         // phase 1b: one thread per staged column (tile element, owned local column) -> stage
-        for (int qc = tid; qc < nq; qc += BLOCK) {
+        for (int qc = tid; qc < ncols; qc += BLOCK) {
             int r = 0;
             while (r + 1 < F::ND && (int)td.qbase[r + 1] <= qc) r++;
             const int le = qc - (int)td.qbase[r];
@@ -661,7 +684,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     }
     int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
     int64_t rnz = srun[r].nz0;
-    constexpr int U = 4;
+#ifndef TL_U
+#define TL_U 4
+#endif
+    constexpr int U = TL_U;
     for (int sb = w0; sb < w1; sb += 32 * U) {
         int o0[U], c[U];
 #pragma unroll
@@ -671,6 +697,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
             if (s < w1) { o0[u] = goff[s]; c[u] = (int)goff[s + 1] - o0[u]; }
         }
         double acc[U];
+#if defined(TL_P2_BRANCHLESS) && TL_P2_BRANCHLESS
+        // unconditional loads (gidx is padded, index 0 of the stage is always valid), selects instead of predicated blocks
+        uint32_t i0[U], i1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { i0[u] = gi[o0[u]]; i1[u] = gi[o0[u] + 1]; }
+        double v0[U], v1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) { v0[u] = stage[i0[u]]; v1[u] = stage[i1[u]]; }
+#pragma unroll
+        for (int u = 0; u < U; u++) acc[u] = (c[u] == 2) ? __dadd_rn(v0[u], v1[u]) : (c[u] == 1 ? v0[u] : 0.0);
+#else
 #pragma unroll
         for (int u = 0; u < U; u++) {
             acc[u] = 0.0;
@@ -679,6 +716,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
 #pragma unroll
         for (int u = 0; u < U; u++)
             if (c[u] == 2) acc[u] = __dadd_rn(acc[u], stage[gi[o0[u] + 1]]);
+#endif
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int s = sb + u * 32 + lane;
@@ -705,7 +743,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
 // Tile sizes tried in turn (largest first): powers of two and 3*2^k keep space-filling-curve tiles compact
 // (a 256-element T6 tile is a 16 x 8 block of cells).  The first size whose shared-memory footprint lets two
 // CTAs share an SM is used.
-static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 48, 32};
+static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32};
 #define TL_SMEM_TWO_CTAS (114 * 1024 + 512)
 template <class F> static int tl_default_tile_elems()
 {
@@ -936,6 +974,7 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
 
     // T8: gather lists into the metadata blocks
     td->meta.alloc(pool, (size_t)(meta_total > 0 ? meta_total : 16));
+    CUDA_CHECK(cudaMemsetAsync(td->meta.p, 0, (size_t)(meta_total > 0 ? meta_total : 16), st));
     LAUNCH(ctx, k_tl_gather_build<F>, grid_for(nowned, 128), 128, 0, tkeys.p, tcols.p, nowned, adjptr.p, adj.p, edof.p, colptr0.p, ctx->rowval.p,
            telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, td->meta.p, err.p);
     LAUNCH(ctx, k_tl_meta_finish, grid_for(ntiles, 128), 128, 0, ntiles, td->tiles.p, runs.p, td->meta.p);

@@ -191,6 +191,15 @@ int efg_create(int device, efg_ctx **out)
         delete ctx;
         return EFG_ERR_CUDA;
     }
+    ctx->pool.stream = ctx->stream;
+    {   // keep freed blocks in the device's default memory pool instead of returning them to the OS at every sync
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        cudaGetLastError();
+    }
     *out = ctx;
     return EFG_OK;
 }
@@ -203,6 +212,13 @@ int efg_destroy(efg_ctx *ctx)
     invalidate(ctx);
     for (auto &m : ctx->mesh) { m.conn.release(); m.xy.release(); }
     for (auto &s : ctx->space) s.dof.release();
+    ctx->rfirst.release(); ctx->rlast1.release(); ctx->roff.release();
+    cudaStreamSynchronize(ctx->stream);
+    {
+        cudaMemPool_t mp;
+        if (cudaDeviceGetDefaultMemPool(&mp, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
+        cudaGetLastError();
+    }
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evn0); cudaEventDestroy(ctx->evn1);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
