@@ -743,15 +743,32 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
 // Tile sizes tried in turn (largest first): powers of two and 3*2^k keep space-filling-curve tiles compact
 // (a 256-element T6 tile is a 16 x 8 block of cells).  The first size whose shared-memory footprint lets two
 // CTAs share an SM is used.
+// Threads per CTA (two CTAs per SM): 320 for the one-thread-per-element forms (96 registers/thread, 20 warps/SM:
+// measured faster than 256 x 128 registers for T3/T6/Q4 heat), 256 for the SPLIT forms (measured).
+template <class F> __host__ __device__ constexpr int tl_block() { return (F::SPLIT || F::ND > 8) ? 256 : 320; }
+
 static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32};
 #define TL_SMEM_TWO_CTAS (114 * 1024 + 512)
 template <class F> static int tl_default_tile_elems()
 {
     // shared memory per owned element-equivalent ~ stage ND*ND*8 + gather metadata NT*2 + ~2.7*ND*ND
     const double per_elem = F::ND * F::ND * 10.7 + F::NT * 2.0;   // (SPLIT forms: the geometry area aliases the metadata area)
-    for (int te : TL_TILE_SIZES)
-        if (te * per_elem <= 118.0 * 1024) return te;
-    return 32;
+    int te = 32;
+    for (int c : TL_TILE_SIZES)
+        if (c * per_elem <= 118.0 * 1024) { te = c; break; }
+    if (!F::SPLIT) {
+        // phase 1 runs in rounds of tl_block() elements; a tile whose element count (own + halo) barely exceeds a
+        // whole number of rounds leaves the last round almost empty.  Halo model for compact tiles: 1 + x/sqrt(te).
+        const double x = F::GK == 6 ? 4.6 : (F::GK == 3 ? 4.0 : 2.9);
+        const double halo = 1.0 + x / sqrt((double)te);
+        const double rounds = te * halo / tl_block<F>();
+        const double whole = floor(rounds);
+        if (whole >= 1.0 && rounds - whole > 0.0 && rounds - whole < 0.5) {
+            const int t2 = (int)(whole * tl_block<F>() * 0.98 / halo) & ~7;
+            if (t2 >= 32) te = t2;
+        }
+    }
+    return te;
 }
 
 template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te);
@@ -1007,7 +1024,7 @@ template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(
 }
 template <class F, bool S> static void tl_launch_numeric(efg_ctx *ctx)
 {
-    tl_launch_numeric_b<F, S, 256, 2>(ctx);
+    tl_launch_numeric_b<F, S, tl_block<F>(), 2>(ctx);
 }
 
 template <class F> void tiled_numeric(efg_ctx *ctx)
