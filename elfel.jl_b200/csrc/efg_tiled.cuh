@@ -24,14 +24,14 @@
 
 struct TileDescFull {
     int64_t slot0;          // first tile-order slot            (symbolic phase only)
-    int64_t gidx0;          // first tile-order contribution    (symbolic phase only)
+    int64_t gidx0;          // first tile-order heavy contribution (symbolic phase only)
     int64_t elem0;          // first tile element (index into tconn/tmask)
     int64_t meta0;          // byte offset of the tile's metadata block (16-byte aligned)
     int32_t nelem;          // tile elements incl. halo
     int32_t nslot;          // owned nonzeros
     int32_t nrun;           // runs of nonzeros contiguous in nzval
     int32_t nq;             // staged columns (= stage row stride)
-    int32_t ncontrib;       // contributions to the owned nonzeros
+    int32_t ncontrib;       // contributions to the HEAVY owned nonzeros (entries of hidx)
     int32_t meta_bytes;     // size of the metadata block (multiple of 16)
     int32_t run0;           // first run (symbolic phase only)
     int32_t nheavy;         // owned nonzeros with more than TL_LIGHT contributions
@@ -42,15 +42,21 @@ struct TileDescFull {
 };
 static_assert(sizeof(TileDescFull) % 8 == 0, "TileDescFull is copied as 8-byte words");
 
-// metadata block of a tile: [goff: u16 x (nslot+1)] [gidx: u16 x ncontrib] [runs: TileRun x nrun] [heavy: u16 x nheavy],
-// each part 16-byte aligned
+// metadata block of a tile, each part 16-byte aligned:
+//   [pk: u32 x nslot]      per owned nonzero: stage index of its 1st | 2nd << 16 contribution (0xFFFF = none);
+//                          0xFFFEFFFE marks a "heavy" nonzero (> TL_LIGHT contributions)
+//   [hidx: u16 x ncontrib] stage indices of the contributions of the heavy nonzeros, append order
+//   [runs: TileRun x nrun] [heavy: TileHeavy x nheavy]
 __host__ __device__ static inline int tl_align16(int b) { return (b + 15) & ~15; }
 // SPLIT forms keep per-element geometry (gradients + JxW at every quadrature point, SoA) and the column masks in
 // shared memory between the two steps of phase 1
 template <class F> __host__ __device__ constexpr int tl_gsz() { return F::SPLIT ? F::NQ * (2 * F::BK + 1) : 0; }
 __host__ __device__ static inline int tl_geo_bytes(int gsz, int nelem) { return gsz ? tl_align16(nelem * (gsz * 8 + 2)) : 0; }
-__host__ __device__ static inline int tl_meta_goff_bytes(int nslot) { return tl_align16(2 * (nslot + 1)); }
-__host__ __device__ static inline int tl_meta_gidx_bytes(int nc) { return tl_align16(2 * (nc + 1)); }   // one zero pad entry
+__host__ __device__ static inline int tl_meta_goff_bytes(int nslot) { return tl_align16(4 * nslot); }          // pk
+__host__ __device__ static inline int tl_meta_gidx_bytes(int nc) { return tl_align16(2 * nc); }              // hidx
+struct TileHeavy { uint16_t s, o, c, pad; };   // tile slot, first entry in hidx, number of contributions
+#define TL_PK_NONE 0xFFFFu
+#define TL_PK_HEAVY 0xFFFEFFFEu
 
 struct TiledData {
     DevBuf<TileDescFull> tiles;
@@ -249,10 +255,10 @@ __global__ void k_tl_col_count(const uint32_t *__restrict__ adjptr, const uint32
         int nc;
         const int n = tl_column_rows<F, true>(adj, adjptr[cl], adjptr[cl + 1], edof, rows, cnt, nc);
         if (n < 0 || nc > 65535) { *err = 2; colcnt[cl] = 0; ccnt[cl] = 0; hcnt[cl] = 0; continue; }
-        int h = 0;
-        for (int t = 0; t < n; t++) h += cnt[t] > TL_LIGHT;
+        int h = 0, hc = 0;
+        for (int t = 0; t < n; t++) if (cnt[t] > TL_LIGHT) { h++; hc += cnt[t]; }
         colcnt[cl] = (uint8_t)n;
-        ccnt[cl] = (uint16_t)nc;
+        ccnt[cl] = (uint16_t)hc;      // contributions to heavy nonzeros only
         hcnt[cl] = (uint8_t)h;
     }
 }
@@ -393,11 +399,13 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
         const TileDescFull &td = tiles[T];
         const int64_t g0 = telem_ptr[T], g1 = telem_ptr[T + 1];
         unsigned char *__restrict__ mb = meta + td.meta0;
-        uint16_t *__restrict__ goff = reinterpret_cast<uint16_t *>(mb) + (tcol_slot[k] - td.slot0);
-        uint16_t *__restrict__ gidx = reinterpret_cast<uint16_t *>(mb + tl_meta_goff_bytes(td.nslot));
-        const uint32_t gbase = (uint32_t)(tcol_gidx[k] - td.gidx0);
-        uint16_t off[TL_CAP];
-        for (int t = 0; t < nr; t++) off[t] = 0;
+        const uint32_t sloc = (uint32_t)(tcol_slot[k] - td.slot0);
+        uint32_t *__restrict__ pk = reinterpret_cast<uint32_t *>(mb) + sloc;
+        uint16_t *__restrict__ hidx = reinterpret_cast<uint16_t *>(mb + tl_meta_goff_bytes(td.nslot));
+        TileHeavy *__restrict__ heavy = reinterpret_cast<TileHeavy *>(mb + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib) +
+                                                                     td.nrun * (int)sizeof(TileRun)) + (tcol_heavy[k] - td.heavy0);
+        uint16_t cnt[TL_CAP], off[TL_CAP], first[TL_CAP], second[TL_CAP];
+        for (int t = 0; t < nr; t++) cnt[t] = 0;
         const uint32_t a0 = adjptr[cl], a1 = adjptr[cl + 1];
         // pass A: contributions per slot
         for (uint32_t p = a0; p < a1; p++) {
@@ -409,21 +417,20 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                 const int32_t r = edof[(int64_t)e * F::ND + i];
                 int lo = 0, hi = nr;
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (rowval[r0 + mid] < r) lo = mid + 1; else hi = mid; }
-                off[lo]++;
+                cnt[lo]++;
             }
         }
-        uint16_t *__restrict__ heavy = reinterpret_cast<uint16_t *>(mb + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib) +
-                                                                   td.nrun * (int)sizeof(TileRun)) + (tcol_heavy[k] - td.heavy0);
-        const uint32_t sloc = (uint32_t)(tcol_slot[k] - td.slot0);
-        uint32_t run = gbase;
+        uint32_t run = (uint32_t)(tcol_gidx[k] - td.gidx0);      // heavy contributions of the tile before this column
         int nh = 0;
         for (int t = 0; t < nr; t++) {
-            const uint32_t c = off[t];
-            if (run + c > 65535u) *err = 3;
-            if (c > TL_LIGHT) heavy[nh++] = (uint16_t)(sloc + t);
-            goff[t] = (uint16_t)run;
-            off[t] = (uint16_t)run;
-            run += c;
+            first[t] = second[t] = TL_PK_NONE;
+            off[t] = 0;
+            if (cnt[t] > TL_LIGHT) {
+                if (run + cnt[t] > 65535u) *err = 3;
+                heavy[nh++] = TileHeavy{(uint16_t)(sloc + t), (uint16_t)run, cnt[t], 0};
+                off[t] = (uint16_t)run;
+                run += cnt[t];
+            }
         }
         // pass B: stage indices, append order (ascending element, column-major inside an element)
         for (uint32_t p = a0; p < a1; p++) {
@@ -443,23 +450,24 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                 int l2 = 0, h2 = nr;
                 while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (rowval[r0 + mid] < r) l2 = mid + 1; else h2 = mid; }
                 const uint32_t sidx = (uint32_t)i * (uint32_t)td.nqs + q;
-                if (sidx > 65535u) *err = 4;
-                gidx[off[l2]] = (uint16_t)sidx;
-                off[l2]++;
+                if (sidx >= 0xFFFEu) *err = 4;
+                if (cnt[l2] > TL_LIGHT) { hidx[off[l2]] = (uint16_t)sidx; off[l2]++; }
+                else if (off[l2]++ == 0) first[l2] = (uint16_t)sidx;
+                else second[l2] = (uint16_t)sidx;
             }
         }
+        for (int t = 0; t < nr; t++)
+            pk[t] = cnt[t] > TL_LIGHT ? TL_PK_HEAVY : ((uint32_t)first[t] | ((uint32_t)second[t] << 16));
     }
 }
 
-// terminal goff entry + the tile's runs into its metadata block
+// the tile's runs into its metadata block
 __global__ void k_tl_meta_finish(int ntiles, const TileDescFull *__restrict__ tiles, const TileRun *__restrict__ runs, unsigned char *__restrict__ meta)
 {
     GRID_STRIDE(T, ntiles) {
         const TileDescFull &td = tiles[T];
         if (td.meta_bytes == 0) continue;
-        unsigned char *mb = meta + td.meta0;
-        reinterpret_cast<uint16_t *>(mb)[td.nslot] = (uint16_t)td.ncontrib;
-        TileRun *dst = reinterpret_cast<TileRun *>(mb + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
+        TileRun *dst = reinterpret_cast<TileRun *>(meta + td.meta0 + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
         for (int rr = 0; rr < td.nrun; rr++) dst[rr] = runs[td.run0 + rr];
     }
 }
@@ -497,7 +505,7 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, const int64_t *__re
         for (int r = 0; r <= TL_MAXND; r++) { d.qbase[r] = (uint16_t)(q > 65535u ? 65535u : q); if (r < TL_MAXND) q += above[r]; }
         d.nq = (int32_t)q;
         d.nqs = (uint16_t)((q | 1u) > 65535u ? 65535u : (q | 1u));
-        d.meta_bytes = d.nslot > 0 ? tl_meta_goff_bytes(d.nslot) + tl_meta_gidx_bytes(d.ncontrib) + d.nrun * (int)sizeof(TileRun) + tl_align16(2 * d.nheavy) : 0;
+        d.meta_bytes = d.nslot > 0 ? tl_meta_goff_bytes(d.nslot) + tl_meta_gidx_bytes(d.ncontrib) + d.nrun * (int)sizeof(TileRun) + tl_align16((int)sizeof(TileHeavy) * d.nheavy) : 0;
         d.meta0 = 0;
         d.pad2_[0] = d.pad2_[1] = 0;
         tiles[T] = d;
@@ -544,11 +552,72 @@ __device__ __forceinline__ void tl_bulk_load(uint32_t dstA, const void *src, uin
 // (2) one thread per owned nonzero sums its contributions from the stage left to right and stores nzval.
 // Overlap between the compute phase of one tile and the gather/store phase of another comes from the
 // CTAs co-resident on an SM.
+// Phase-1 worker of the one-thread-per-element forms, kept out of line so that its register allocation does not
+// depend on the code of the gather phase (the kernel-wide allocation otherwise shifts spills into this hot code).
+template <class F, bool S>
+__device__ __noinline__ void tl_element_to_stage(int64_t g, uint32_t le, const int32_t *__restrict__ tconn, const uint16_t *__restrict__ tmask,
+                                                 const double2 *__restrict__ xy, double *__restrict__ stage, const uint16_t *__restrict__ qbase, int nq)
+{
+    constexpr int GK = F::GK;
+    double X[GK], Y[GK];
+#pragma unroll
+    for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
+    StageEmit<F> emit{stage, qbase, (uint32_t)tmask[g], le, nq};
+    F::template element<S>(X, Y, emit.m, emit);
+}
+
+// SPLIT forms, phase 1a / 1b workers (inlined: out of line measured 4% slower here)
+template <class F, bool S>
+__device__ __forceinline__ void tl_geometry_to_smem(int64_t g, int le, int ne, const int32_t *__restrict__ tconn, const uint16_t *__restrict__ tmask,
+                                                 const double2 *__restrict__ xy, double *__restrict__ Gs, uint16_t *__restrict__ smask)
+{
+    constexpr int GK = F::GK, NQ = F::NQ, BK = F::BK;
+    double X[GK], Y[GK];
+#pragma unroll
+    for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
+    Geo<BK, NQ> G;
+    geo_compute<S, GK, BK, NQ>(X, Y, G);
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+#pragma unroll
+        for (int n = 0; n < BK; n++) {
+            Gs[(q * BK + n) * ne + le] = G.gx[q][n];
+            Gs[(NQ * BK + q * BK + n) * ne + le] = G.gy[q][n];
+        }
+        Gs[(2 * NQ * BK + q) * ne + le] = G.JxW[q];
+    }
+    smask[le] = tmask[g];
+}
+template <class F, bool S>
+__device__ __forceinline__ void tl_column_to_stage(int qc, int le, int J, int ne, int nq, const double *__restrict__ Gs, double *__restrict__ stage)
+{
+    constexpr int NQ = F::NQ, BK = F::BK;
+    Geo<BK, NQ> G;
+    double gjx[NQ], gjy[NQ];
+    const int nj = F::colnode(J);
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+#pragma unroll
+        for (int n = 0; n < BK; n++) {
+            G.gx[q][n] = Gs[(q * BK + n) * ne + le];
+            G.gy[q][n] = Gs[(NQ * BK + q * BK + n) * ne + le];
+        }
+        G.JxW[q] = Gs[(2 * NQ * BK + q) * ne + le];
+        gjx[q] = Gs[(q * BK + nj) * ne + le];
+        gjy[q] = Gs[(NQ * BK + q * BK + nj) * ne + le];
+    }
+    double out[F::ND];
+    F::template column_rt<S>(G, J, gjx, gjy, out);
+#pragma unroll
+    for (int i = 0; i < F::ND; i++)
+        if (F::mask(i, J)) stage[i * nq + qc] = out[i];
+}
+
 template <class F, bool S, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *__restrict__ tiles, int ntiles,
                                                             const int32_t *__restrict__ tconn, const uint16_t *__restrict__ tmask,
                                                             const double2 *__restrict__ xy, const unsigned char *__restrict__ meta,
-                                                            double *__restrict__ nzval, int stage_bytes, int meta_max)
+                                                            double *__restrict__ nzval, int pf_dist, int unused_)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDescFull td;
@@ -557,22 +626,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     constexpr int GK = F::GK;
     constexpr int NW = BLOCK / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#if defined(TL_EARLY) && TL_EARLY
-    // this thread's first element: start the dependent connectivity -> coordinate loads straight from the global
-    // descriptor, before the descriptor is staged in shared memory and the block synchronises
-    double EX[GK], EY[GK];
-    uint32_t em = 0;
-    if (!F::SPLIT) {
-        const int64_t e0g = tiles[blockIdx.x].elem0;
-        if (tid < tiles[blockIdx.x].nelem) {
-            const int64_t g = e0g + tid;
-#pragma unroll
-            for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); EX[a] = p.x; EY[a] = p.y; }
-            em = tmask[g];
-        }
-    }
-#endif
     if (tid < DW) reinterpret_cast<int64_t *>(&td)[tid] = reinterpret_cast<const int64_t *>(&tiles[blockIdx.x])[tid];
+    // the tile that will occupy a CTA slot about one wave later (pf_dist = CTAs resident on the device): its
+    // connectivity is pulled into L2 at the end of this CTA, so that tile's first dependent load is an L2 hit
+    const int tpf = blockIdx.x + pf_dist;
+    int64_t pf_elem0 = 0; int pf_nelem = 0;
+    if (tpf < ntiles) { pf_elem0 = tiles[tpf].elem0; pf_nelem = tiles[tpf].nelem; }
     const uint32_t barA = tl_smem_addr(&bar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
@@ -591,46 +650,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
 
     if constexpr (!F::SPLIT) {
         // phase 1: one thread per tile element: owned columns of the element matrix -> stage
-#if defined(TL_EARLY) && TL_EARLY
-        if (tid < td.nelem) {
-            StageEmit<F> emit{stage, td.qbase, em, (uint32_t)tid, nq};
-            F::template element<S>(EX, EY, em, emit);
-        }
-        for (int le = tid + BLOCK; le < td.nelem; le += BLOCK) {
-#else
         for (int le = tid; le < td.nelem; le += BLOCK) {
-#endif
-            const int64_t g = td.elem0 + le;
-            double X[GK], Y[GK];
+            if constexpr (F::GK >= 4) {    // out of line: measured 4.47 -> 3.96 ms on config 2 (no spills in the hot code)
+                tl_element_to_stage<F, S>(td.elem0 + le, (uint32_t)le, tconn, tmask, xy, stage, td.qbase, nq);
+            } else {
+                const int64_t g = td.elem0 + le;
+                double X[GK], Y[GK];
 #pragma unroll
-            for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
-            StageEmit<F> emit{stage, td.qbase, (uint32_t)tmask[g], (uint32_t)le, nq};
-            F::template element<S>(X, Y, emit.m, emit);
+                for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
+                StageEmit<F> emit{stage, td.qbase, (uint32_t)tmask[g], (uint32_t)le, nq};
+                F::template element<S>(X, Y, emit.m, emit);
+            }
         }
     } else {
         // phase 1a: one thread per tile element: Jacobian / JxW / gradients at every quadrature point -> shared memory
-        constexpr int NQ = F::NQ, BK = F::BK;
         const int ne = td.nelem;
         double *Gs = reinterpret_cast<double *>(smem_raw + tl_align16(F::ND * nq * 8));   // SoA: Gs[k * ne + le]
         uint16_t *smask = reinterpret_cast<uint16_t *>(Gs + GSZ * ne);
-        for (int le = tid; le < ne; le += BLOCK) {
-            const int64_t g = td.elem0 + le;
-            double X[GK], Y[GK];
-#pragma unroll
-            for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
-            Geo<BK, NQ> G;
-            geo_compute<S, GK, BK, NQ>(X, Y, G);
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-#pragma unroll
-                for (int n = 0; n < BK; n++) {
-                    Gs[(q * BK + n) * ne + le] = G.gx[q][n];
-                    Gs[(NQ * BK + q * BK + n) * ne + le] = G.gy[q][n];
-                }
-                Gs[(2 * NQ * BK + q) * ne + le] = G.JxW[q];
-            }
-            smask[le] = tmask[g];
-        }
+        for (int le = tid; le < ne; le += BLOCK)
+            tl_geometry_to_smem<F, S>(td.elem0 + le, le, ne, tconn, tmask, xy, Gs, smask);
         __syncthreads();
         // phase 1b: one thread per staged column (tile element, owned local column) -> stage
         for (int qc = tid; qc < ncols; qc += BLOCK) {
@@ -640,25 +678,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
             uint32_t mm = smask[le];
             for (int t = 0; t < r; t++) mm &= mm - 1;
             const int J = __ffs(mm) - 1;
-            Geo<BK, NQ> G;
-            double gjx[NQ], gjy[NQ];
-            const int nj = F::colnode(J);
-#pragma unroll
-            for (int q = 0; q < NQ; q++) {
-#pragma unroll
-                for (int n = 0; n < BK; n++) {
-                    G.gx[q][n] = Gs[(q * BK + n) * ne + le];
-                    G.gy[q][n] = Gs[(NQ * BK + q * BK + n) * ne + le];
-                }
-                G.JxW[q] = Gs[(2 * NQ * BK + q) * ne + le];
-                gjx[q] = Gs[(q * BK + nj) * ne + le];
-                gjy[q] = Gs[(NQ * BK + q * BK + nj) * ne + le];
-            }
-            double out[F::ND];
-            F::template column_rt<S>(G, J, gjx, gjy, out);
-#pragma unroll
-            for (int i = 0; i < F::ND; i++)
-                if (F::mask(i, J)) stage[i * nq + qc] = out[i];
+            tl_column_to_stage<F, S>(qc, le, J, ne, nq, Gs, stage);
         }
     }
     __syncthreads();
@@ -670,11 +690,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
 
     // phase 2: every owned nonzero = left-to-right sum of its contributions (append order), stored once
     {
-    const uint16_t *goff = reinterpret_cast<const uint16_t *>(smeta);
-    const uint16_t *gi = reinterpret_cast<const uint16_t *>(smeta + tl_meta_goff_bytes(td.nslot));
-    const TileRun *srun = reinterpret_cast<const TileRun *>(reinterpret_cast<const unsigned char *>(gi) + tl_meta_gidx_bytes(td.ncontrib));
+    const uint32_t *spk = reinterpret_cast<const uint32_t *>(smeta);
+    const uint16_t *hidx = reinterpret_cast<const uint16_t *>(smeta + tl_meta_goff_bytes(td.nslot));
+    const TileRun *srun = reinterpret_cast<const TileRun *>(reinterpret_cast<const unsigned char *>(hidx) + tl_meta_gidx_bytes(td.ncontrib));
+    const TileHeavy *heavy = reinterpret_cast<const TileHeavy *>(reinterpret_cast<const unsigned char *>(srun) + td.nrun * (int)sizeof(TileRun));
     const int nslot = td.nslot;
-    const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;
+    const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // contiguous slots per warp
     const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
     int r = 0;
     {
@@ -684,54 +705,68 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     }
     int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
     int64_t rnz = srun[r].nz0;
+    // light nonzeros (1 or 2 contributions: all but the matrix diagonals of node patches): one packed word per
+    // nonzero names both stage entries; four nonzeros in flight per lane
 #ifndef TL_U
 #define TL_U 4
 #endif
     constexpr int U = TL_U;
     for (int sb = w0; sb < w1; sb += 32 * U) {
-        int o0[U], c[U];
+        uint32_t pk[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int s = sb + u * 32 + lane;
-            o0[u] = 0; c[u] = 0;
-            if (s < w1) { o0[u] = goff[s]; c[u] = (int)goff[s + 1] - o0[u]; }
+            pk[u] = (s < w1) ? spk[s] : 0xFFFFFFFFu;
         }
         double acc[U];
-#if defined(TL_P2_BRANCHLESS) && TL_P2_BRANCHLESS
-        // unconditional loads (gidx is padded, index 0 of the stage is always valid), selects instead of predicated blocks
-        uint32_t i0[U], i1[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) { i0[u] = gi[o0[u]]; i1[u] = gi[o0[u] + 1]; }
-        double v0[U], v1[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) { v0[u] = stage[i0[u]]; v1[u] = stage[i1[u]]; }
-#pragma unroll
-        for (int u = 0; u < U; u++) acc[u] = (c[u] == 2) ? __dadd_rn(v0[u], v1[u]) : (c[u] == 1 ? v0[u] : 0.0);
-#else
+#if !defined(TL_P2SPLIT) || !TL_P2SPLIT
 #pragma unroll
         for (int u = 0; u < U; u++) {
+            const uint32_t i0 = pk[u] & 0xFFFFu, i1 = pk[u] >> 16;
             acc[u] = 0.0;
-            if (c[u] >= 1 && c[u] <= TL_LIGHT) acc[u] = stage[gi[o0[u]]];
+            if (i0 < 0xFFFEu) acc[u] = stage[i0];
+            if (i1 < 0xFFFEu) acc[u] = __dadd_rn(acc[u], stage[i1]);
+        }
+#else
+        double v1[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i0 = pk[u] & 0xFFFFu;
+            acc[u] = 0.0;
+            if (i0 < 0xFFFEu) acc[u] = stage[i0];
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i1 = pk[u] >> 16;
+            v1[u] = 0.0;
+            if (i1 < 0xFFFEu) v1[u] = stage[i1];
         }
 #pragma unroll
         for (int u = 0; u < U; u++)
-            if (c[u] == 2) acc[u] = __dadd_rn(acc[u], stage[gi[o0[u] + 1]]);
+            if ((pk[u] >> 16) < 0xFFFEu) acc[u] = __dadd_rn(acc[u], v1[u]);
 #endif
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int s = sb + u * 32 + lane;
             if (s < w1) {
                 while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
-                if (c[u] <= TL_LIGHT) nzval[rnz + (s - rs0)] = acc[u];
+                if (pk[u] != TL_PK_HEAVY) nzval[rnz + (s - rs0)] = acc[u];
             }
         }
     }
-    const uint16_t *heavy = reinterpret_cast<const uint16_t *>(reinterpret_cast<const unsigned char *>(srun) + td.nrun * (int)sizeof(TileRun));
+    {   // pull the connectivity of the tile one wave ahead into L2
+        const char *p0 = reinterpret_cast<const char *>(tconn + pf_elem0 * GK);
+        const int nbytes = pf_nelem * GK * 4;
+        for (int o = tid * 128; o < nbytes; o += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+        const char *p1 = reinterpret_cast<const char *>(tmask + pf_elem0);
+        for (int o = tid * 128; o < pf_nelem * 2; o += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + o));
+    }
+    // heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum
     for (int h = tid; h < td.nheavy; h += BLOCK) {
-        const int s = heavy[h];
-        const int o0 = goff[s], o1 = goff[s + 1];
-        double acc = stage[gi[o0]];
-        for (int k = o0 + 1; k < o1; k++) acc = __dadd_rn(acc, stage[gi[k]]);
+        const TileHeavy e = heavy[h];
+        double acc = stage[hidx[e.o]];
+        for (int k = 1; k < (int)e.c; k++) acc = __dadd_rn(acc, stage[hidx[e.o + k]]);
+        const int s = e.s;
         int lo = 0, hi = td.nrun - 1;
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
         nzval[srun[lo].nz0 + (s - srun[lo].s0)] = acc;
@@ -745,7 +780,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
 // CTAs share an SM is used.
 // Threads per CTA (two CTAs per SM): 320 for the one-thread-per-element forms (96 registers/thread, 20 warps/SM:
 // measured faster than 256 x 128 registers for T3/T6/Q4 heat), 256 for the SPLIT forms (measured).
-template <class F> __host__ __device__ constexpr int tl_block() { return (F::SPLIT || F::ND > 8) ? 256 : 320; }
+#ifndef TL_BLOCK_NS
+#define TL_BLOCK_NS 320
+#endif
+template <class F> __host__ __device__ constexpr int tl_block() { return (F::SPLIT || F::ND > 8) ? 256 : TL_BLOCK_NS; }
 
 static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32};
 #define TL_SMEM_TWO_CTAS (114 * 1024 + 512)
@@ -756,6 +794,14 @@ template <class F> static int tl_default_tile_elems()
     int te = 32;
     for (int c : TL_TILE_SIZES)
         if (c * per_elem <= 118.0 * 1024) { te = c; break; }
+    if (F::SPLIT) {
+        // phase 1b runs in rounds of tl_block() staged columns (te*ND on average): avoid a nearly empty last round
+        for (int c : TL_TILE_SIZES) {
+            if (c > te) continue;
+            const double rounds = (double)c * F::ND / tl_block<F>();
+            if (rounds / ceil(rounds) >= 0.85) { te = c; break; }
+        }
+    }
     if (!F::SPLIT) {
         // phase 1 runs in rounds of tl_block() elements; a tile whose element count (own + halo) barely exceeds a
         // whole number of rounds leaves the last round almost empty.  Halo model for compact tiles: 1 + x/sqrt(te).
@@ -785,7 +831,12 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
             if (e.code != EFG_ERR_LIMIT || te <= 32) throw;
         }
         int next = 32;
-        for (int c : TL_TILE_SIZES) if (c < te) { next = c; break; }
+        for (int c : TL_TILE_SIZES) {
+            if (c >= te) continue;
+            if (F::SPLIT) { const double rounds = (double)c * F::ND / tl_block<F>(); if (rounds / ceil(rounds) < 0.85 && c > 32) continue; }
+            next = c;
+            break;
+        }
         te = next;
         tiled_release(ctx);
         ctx->rowval.release(); ctx->colptr.release(); ctx->nzval.release();
@@ -978,10 +1029,10 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     CUDA_CHECK(cudaMemcpyAsync(hmax, maxima.p, sizeof hmax, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     ctx->tl.max_nq = hmax[1] / ND; ctx->tl.max_nslot = 0; ctx->tl.max_nelem = hmax[3]; ctx->tl.max_nrun = 0;
-    if (hmax[1] > 65535)
+    if (hmax[1] > 65533)
         efg_throw(EFG_ERR_LIMIT, "tiled path: a tile stages %d element-matrix entries (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[1]);
     if (hmax[2] > 65535)
-        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile gathers %d contributions (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[2]);
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile gathers %d heavy contributions (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[2]);
     td->stage_bytes = 0;
     td->meta_max = 0;
     td->smem_bytes = hmax[0];                                  // max over tiles of (stage + gather metadata)
@@ -1015,11 +1066,10 @@ template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
     CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
     if (per_sm < 1) efg_throw(EFG_ERR_LIMIT, "tiled path: the numeric kernel does not fit on an SM (%d bytes of shared memory)", td->smem_bytes);
-    (void)nsm;
     int grid = ctx->tl.ntiles;                    // one CTA per tile
     if (grid > 0)
         LAUNCH(ctx, kern, (unsigned)grid, BLOCK, (size_t)td->smem_bytes, td->tiles.p, ctx->tl.ntiles, td->tconn.p, td->tmask.p, gm.xy.p,
-               td->meta.p, ctx->nzval.p, td->stage_bytes, td->meta_max);
+               td->meta.p, ctx->nzval.p, per_sm * nsm, 0);
     ctx->numeric_launches += 1;
 }
 template <class F, bool S> static void tl_launch_numeric(efg_ctx *ctx)
