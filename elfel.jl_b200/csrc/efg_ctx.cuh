@@ -89,6 +89,8 @@ struct efg_ctx {
     TwoPass tp;
     Tiled tl;
     void *tl_opaque = nullptr;
+    DevBuf<char> scratch;        // persistent scratch for the largest symbolic temporaries (kept across calls: the
+                                 // multi-GB sort buffers made cudaMallocAsync stall for 0.1-2.5 s when re-allocated every call)
 
     // stats
     double symbolic_ms = 0, numeric_ms = 0;

@@ -111,6 +111,11 @@ template <class In, class Out> static void tl_excl_scan(efg_ctx *ctx, In in, Out
     CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, out, n, ctx->stream));
     ctx->launches += 2;
 }
+static inline char *tl_scratch(efg_ctx *ctx, size_t bytes)
+{
+    if (ctx->scratch.n < bytes) ctx->scratch.alloc(ctx->pool, bytes + bytes / 8);
+    return ctx->scratch.p;
+}
 static inline int bits_for(int64_t maxval)
 {
     int b = 1;
@@ -124,6 +129,21 @@ template <class T> static T tl_read(efg_ctx *ctx, const T *dptr)
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     return h;
 }
+
+// EFG_TRACE=1: wall-clock per symbolic step on stderr (synchronises; for diagnosing host-side stalls)
+#include <chrono>
+#include <cstdlib>
+struct TlTrace {
+    bool on; std::chrono::steady_clock::time_point t; efg_ctx *ctx;
+    explicit TlTrace(efg_ctx *c) : on(getenv("EFG_TRACE") != nullptr), t(std::chrono::steady_clock::now()), ctx(c) {}
+    void mark(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(ctx->stream);
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[efg trace] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
 
 #define GRID_STRIDE(i, n) \
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride__ = (int64_t)gridDim.x * blockDim.x; i < (n); i += stride__)
@@ -856,11 +876,13 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     DevPool &pool = ctx->pool;
     TiledData *td = new TiledData();
     tiled_data(ctx) = td;
+    TlTrace trace(ctx);
 
     DevBuf<int> err;
     err.alloc(pool, 1);
     CUDA_CHECK(cudaMemsetAsync(err.p, 0, sizeof(int), st));
 
+    trace.mark("start");
     // T0: combined element dof table
     DevBuf<int32_t> edof;
     edof.alloc(pool, (size_t)(nel * ND));
@@ -869,6 +891,7 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     if (tl_read(ctx, err.p))
         efg_throw(EFG_ERR_INDEX, "ArgumentError: a dof number is < 1 or exceeds nrow/ncol (was every space numbered, incl. data dofs?)");
 
+    trace.mark("T0 edofs");
     // T1: element order -> tile of each element
     const int ntiles = (int)((nel + te - 1) / te);
     DevBuf<int32_t> etile;
@@ -893,6 +916,7 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
         LAUNCH(ctx, k_tl_etile_identity, grid_for(nel, 256), 256, 0, nel, te, etile.p);
     }
 
+    trace.mark("T1 morton order");
     // T2/T3: column owners + adjacency (column -> (element, local column)), ascending element
     DevBuf<int32_t> owner;
     DevBuf<uint32_t> adjcnt, adjptr, adj;
@@ -902,14 +926,15 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     CUDA_CHECK(cudaMemsetAsync(adjcnt.p, 0, (size_t)(ncl + 2) * sizeof(uint32_t), st));
     adj.alloc(pool, (size_t)(nel * ND));
     {
-        DevBuf<uint32_t> k1, k2, v1;
-        k1.alloc(pool, (size_t)(nel * ND)); k2.alloc(pool, (size_t)(nel * ND)); v1.alloc(pool, (size_t)(nel * ND));
-        LAUNCH(ctx, k_tl_owner_pairs<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, etile.p, nel, COLMAP(ctx), (uint32_t)ncl, owner.p, adjcnt.p, k1.p, v1.p);
-        tl_sort_pairs(ctx, k1.p, k2.p, v1.p, adj.p, nel * ND, bits_for(ncl));
+        const size_t np = (size_t)(nel * ND);
+        uint32_t *k1 = reinterpret_cast<uint32_t *>(tl_scratch(ctx, 3 * np * sizeof(uint32_t))), *k2 = k1 + np, *v1 = k2 + np;
+        LAUNCH(ctx, k_tl_owner_pairs<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, etile.p, nel, COLMAP(ctx), (uint32_t)ncl, owner.p, adjcnt.p, k1, v1);
+        tl_sort_pairs(ctx, k1, k2, v1, adj.p, nel * ND, bits_for(ncl));
     }
     tl_excl_scan(ctx, adjcnt.p, adjptr.p, ncl + 1);
     const int64_t npairs = (int64_t)tl_read(ctx, adjptr.p + ncl);
 
+    trace.mark("T2/T3 owners+adjacency");
     // T4: CSC pattern
     DevBuf<uint8_t> colcnt, hcnt;
     DevBuf<uint16_t> ccnt;
@@ -931,6 +956,7 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     ctx->colptr.alloc(pool, (size_t)ncl + 1);
     LAUNCH(ctx, k_tl_col_fill<F>, grid_for(ncl + 1, 128), 128, 0, adjptr.p, adj.p, edof.p, ncl, colptr0.p, ctx->rowval.p, ctx->colptr.p);
 
+    trace.mark("T4 pattern");
     // T5: tile column lists, tile-order slot / gather offsets, runs
     DevBuf<uint32_t> tkeys, tcols;
     tkeys.alloc(pool, (size_t)ncl + 1); tcols.alloc(pool, (size_t)ncl + 1);
@@ -973,24 +999,25 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     LAUNCH(ctx, k_tl_run_fill, grid_for(nowned, 256), 256, 0, rflag.p, runidx.p, tkeys.p, tcols.p, nowned, tcol_slot.p, tcol_ptr.p, colptr0.p, runs.p, run_firstk.p);
     LAUNCH(ctx, k_tl_run_len, grid_for(nruns, 256), 256, 0, run_firstk.p, nruns, nowned, tcol_slot.p, runs.p);
 
+    trace.mark("T5 tile columns/runs");
     // T6: tile element lists (own + halo), masks, popcount-descending order inside a tile
-    DevBuf<uint64_t> ek2;
+    // scratch layout: [ek1 (later: eflag) | ek2 | eidx], each nel*ND 8-byte words
+    const size_t npk = (size_t)(nel * ND) + 2;
+    uint64_t *ek1 = reinterpret_cast<uint64_t *>(tl_scratch(ctx, 3 * npk * sizeof(uint64_t)));
+    uint64_t *ek2 = ek1 + npk;
+    int64_t *eidx = reinterpret_cast<int64_t *>(ek2 + npk);
+    int32_t *eflag = reinterpret_cast<int32_t *>(ek1);       // ek1 is dead once sorted into ek2
+    LAUNCH(ctx, k_tl_telem_keys<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, nel, COLMAP(ctx), owner.p, ntiles, ek1);
+    tl_sort_keys(ctx, ek1, ek2, nel * ND, 36 + bits_for(ntiles));   // out-of-range pairs carry tile id ntiles: they sort last
+    trace.mark("  T6a keys+sort64");
+    CUDA_CHECK(cudaMemsetAsync(eflag, 0, ((size_t)npairs + 1) * sizeof(int32_t), st));
+    LAUNCH(ctx, k_tl_head_flags64, grid_for(npairs, 256), 256, 0, ek2, npairs, 4, eflag);
     {
-        DevBuf<uint64_t> ek1;
-        ek1.alloc(pool, (size_t)(nel * ND)); ek2.alloc(pool, (size_t)(nel * ND));
-        LAUNCH(ctx, k_tl_telem_keys<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, nel, COLMAP(ctx), owner.p, ntiles, ek1.p);
-        tl_sort_keys(ctx, ek1.p, ek2.p, nel * ND, 36 + bits_for(ntiles));   // out-of-range pairs carry tile id ntiles: they sort last
+        cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *> it(eflag, cub::CastOp<int64_t>());
+        tl_excl_scan(ctx, it, eidx, npairs + 1);
     }
-    DevBuf<int32_t> eflag;
-    DevBuf<int64_t> eidx;
-    eflag.alloc(pool, (size_t)npairs + 1); eidx.alloc(pool, (size_t)npairs + 1);
-    CUDA_CHECK(cudaMemsetAsync(eflag.p, 0, ((size_t)npairs + 1) * sizeof(int32_t), st));
-    LAUNCH(ctx, k_tl_head_flags64, grid_for(npairs, 256), 256, 0, ek2.p, npairs, 4, eflag.p);
-    {
-        cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const int32_t *> it(eflag.p, cub::CastOp<int64_t>());
-        tl_excl_scan(ctx, it, eidx.p, npairs + 1);
-    }
-    const int64_t ntelem = tl_read(ctx, eidx.p + npairs);
+    const int64_t ntelem = tl_read(ctx, eidx + npairs);
+    trace.mark("  T6b flags+scan");
     td->ntelem = ntelem;
     if (ntelem >= ((int64_t)1 << 32)) efg_throw(EFG_ERR_LIMIT, "tiled path: too many tile elements");
     DevBuf<uint64_t> telem_key;
@@ -1001,17 +1028,21 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     key2s.alloc(pool, (size_t)ntelem + 1); order2.alloc(pool, (size_t)ntelem + 1); newpos.alloc(pool, (size_t)ntelem + 1);
     pc_hist.alloc(pool, (size_t)ntiles * 17);
     CUDA_CHECK(cudaMemsetAsync(pc_hist.p, 0, (size_t)ntiles * 17 * sizeof(uint32_t), st));
-    LAUNCH(ctx, k_tl_telem_fill, grid_for(npairs, 256), 256, 0, ek2.p, npairs, eflag.p, eidx.p, telem_key.p, emask.p, key2.p, val2.p, pc_hist.p);
-    ek2.release(); eflag.release(); eidx.release();
+    LAUNCH(ctx, k_tl_telem_fill, grid_for(npairs, 256), 256, 0, ek2, npairs, eflag, eidx, telem_key.p, emask.p, key2.p, val2.p, pc_hist.p);
+    trace.mark("  T6c alloc+telem_fill");
+    trace.mark("  T6d release");
     tl_sort_pairs(ctx, key2.p, key2s.p, val2.p, order2.p, ntelem, 5 + bits_for(ntiles));
+    trace.mark("  T6e sort popcount");
     LAUNCH(ctx, k_tl_invert, grid_for(ntelem, 256), 256, 0, order2.p, ntelem, newpos.p);
     DevBuf<int64_t> telem_ptr;
     telem_ptr.alloc(pool, (size_t)ntiles + 1);
     LAUNCH(ctx, k_tl_lower_bounds<uint64_t>, grid_for(ntiles + 1, 256), 256, 0, telem_key.p, ntelem, ntiles, 32, telem_ptr.p);
+    trace.mark("  T6f invert+bounds");
     td->tconn.alloc(pool, (size_t)(ntelem * F::GK + 1));
     td->tmask.alloc(pool, (size_t)ntelem + 1);
     LAUNCH(ctx, k_tl_tconn<F::GK>, grid_for(ntelem, 256), 256, 0, order2.p, ntelem, telem_key.p, emask.p, gm.conn.p, td->tconn.p, td->tmask.p);
 
+    trace.mark("T6 tile elements");
     // tile descriptors + metadata block layout
     DevBuf<int32_t> maxima;
     DevBuf<int64_t> mbytes, moff;
@@ -1040,6 +1071,7 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
         efg_throw(EFG_ERR_LIMIT, "tiled path: a tile needs %d bytes of shared memory; lower EFG_OPT_TILE_ELEMS", td->smem_bytes);
     td->meta_bytes = meta_total;
 
+    trace.mark("tile descriptors");
     // T8: gather lists into the metadata blocks
     td->meta.alloc(pool, (size_t)(meta_total > 0 ? meta_total : 16));
     CUDA_CHECK(cudaMemsetAsync(td->meta.p, 0, (size_t)(meta_total > 0 ? meta_total : 16), st));
@@ -1049,6 +1081,7 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     const int e2 = tl_read(ctx, err.p);
     if (e2) efg_throw(EFG_ERR_LIMIT, "tiled path: a tile's gather list exceeds 16-bit offsets (%d); lower EFG_OPT_TILE_ELEMS", e2);
 
+    trace.mark("T8 gather build");
     ctx->nzval.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
     ctx->tl.ntiles = ntiles;
     ctx->tl.tile_elems = te;

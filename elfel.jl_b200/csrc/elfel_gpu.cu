@@ -212,7 +212,7 @@ int efg_destroy(efg_ctx *ctx)
     invalidate(ctx);
     for (auto &m : ctx->mesh) { m.conn.release(); m.xy.release(); }
     for (auto &s : ctx->space) s.dof.release();
-    ctx->rfirst.release(); ctx->rlast1.release(); ctx->roff.release();
+    ctx->rfirst.release(); ctx->rlast1.release(); ctx->roff.release(); ctx->scratch.release();
     cudaStreamSynchronize(ctx->stream);
     {
         cudaMemPool_t mp;
