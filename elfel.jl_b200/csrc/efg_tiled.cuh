@@ -665,6 +665,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     // area, so the TMA copy is issued after phase 1; otherwise it is issued now and lands while phase 1 computes
     unsigned char *smeta = smem_raw + tl_align16(F::ND * td.nqs * 8);
     if (!F::SPLIT && tid == 0) tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
+    if (F::SPLIT) {   // the TMA copy is issued after phase 1 (shared area): pull the block into L2 meanwhile
+        const char *mp = reinterpret_cast<const char *>(meta + td.meta0);
+        for (int o = tid * 128; o < td.meta_bytes; o += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + o));
+    }
     const int nq = td.nqs;      // stage row stride (odd)
     const int ncols = td.nq;    // staged columns
 
@@ -830,7 +834,7 @@ template <class F> static int tl_default_tile_elems()
         const double rounds = te * halo / tl_block<F>();
         const double whole = floor(rounds);
         if (whole >= 1.0 && rounds - whole > 0.0 && rounds - whole < 0.5) {
-            const int t2 = (int)(whole * tl_block<F>() * 0.98 / halo) & ~7;
+            const int t2 = (int)(whole * tl_block<F>() * 0.95 / halo) & ~7;
             if (t2 >= 32) te = t2;
         }
     }
