@@ -6,9 +6,9 @@
 //              the tile OWNS (owner of a column = lowest tile among the elements containing its dof).
 //   tconn      geometry connectivity of every tile element (incl. halo), tile order, int32
 //   tmask      which local columns of that element the tile owns, uint16
-//   gcnt/gidx  for every owned nonzero ("slot"), in (column,row) order: number of contributions
-//              (uint8) and where each one sits in the CTA's shared-memory stage (uint16), listed in
-//              the reference's append order (ascending element, column-major inside an element)
+//   pk         for every owned nonzero ("slot"), in (column,row) order: one 32-bit word naming where its first
+//              and second contribution sit in the CTA's shared-memory stage (reference append order: ascending
+//              element, column-major inside an element); hidx/heavy: lists for nonzeros with more contributions
 //   runs       maximal groups of owned columns that are contiguous in nzval
 // Numeric kernel, per tile: (1) one thread per tile element: coordinates -> Jacobian/gradients ->
 // the owned columns of the element matrix, in registers -> shared-memory stage, (2) one thread per

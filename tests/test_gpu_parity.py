@@ -184,3 +184,50 @@ def test_multirange_band_shards_merge_to_global(oracle, workload, n, world, path
     cp, rv, nz = sh.merge_blocks(nd, blocks)
     assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
     assert np.array_equal(nz, onz)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# larger meshes: closed-form pattern counts, tiled vs two-pass cross-check, properties
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,make,nnz_formula", [
+    ("heat_t3", lambda: efg.heat_problem(efg.T3, 500), lambda N: 7 * N * N + 6 * N + 1),
+    ("heat_t6", lambda: efg.heat_problem(efg.T6, 400), lambda N: 46 * N * N + 16 * N + 1),
+    ("heat_q4", lambda: efg.heat_problem(efg.Q4, 700), lambda N: (3 * N + 1) ** 2),
+    ("elasticity_t6", lambda: efg.elasticity_problem(250, efg.T6), lambda N: 4 * (46 * N * N + 16 * N + 1)),
+    ("stokes_gen", lambda: efg.stokes_problem(200, "gen"), lambda N: 260 * N * N + 104 * N + 8),
+])
+def test_large_mesh_pattern_counts_and_path_agreement(name, make, nnz_formula):
+    prob = make()
+    N = int(prob.name.split("_N")[1])
+    res = {}
+    for path in (_lib.PATH_TILED, _lib.PATH_TWOPASS):
+        cp, rv, nz = _gpu(prob, path, 1)
+        res[path] = (cp, rv, nz)
+        assert len(nz) == nnz_formula(N)
+        assert cp[0] == 1 and cp[-1] == len(nz) + 1 and np.all(np.diff(cp) >= 0)
+    a, b = res[_lib.PATH_TILED], res[_lib.PATH_TWOPASS]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(a[2], b[2]), "strict mode: the two independent GPU paths must agree bit for bit"
+    cp, rv, nz = a
+    import scipy.sparse as sp
+    K = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(prob.ndofs, prob.ndofs))
+    # rows ascending inside every column (sparse()'s CSC invariant)
+    d = np.diff(rv)
+    col_start = np.zeros(len(rv), dtype=bool); col_start[(cp[1:-1] - 1)[cp[1:-1] - 1 < len(rv)]] = True
+    assert np.all((d > 0) | col_start[1:])
+    if name.startswith("heat"):
+        # constants are in the null space of the (unconstrained) conductivity matrix; it is symmetric bit for bit
+        assert np.abs(K @ np.ones(prob.ndofs)).max() < 1e-10
+        assert (K - K.T).nnz == 0
+    if name == "elasticity_t6":
+        # rigid-body translations are in the null space
+        ux = np.zeros(prob.ndofs); ux[prob.spaces[0].field.dofnums[:, 0] - 1] = 1.0
+        assert np.abs(K @ ux).max() < 1e-10
+
+
+def test_fast_mode_vs_strict_mode_large():
+    """Default (FMA, shared reciprocal) vs strict arithmetic on a 1.3 M-element jittered T6 mesh: inside the parity bar."""
+    prob = efg.heat_problem(efg.T6, 800, True)
+    _, _, strict = _gpu(prob, _lib.PATH_TILED, 1)
+    _, _, fast = _gpu(prob, _lib.PATH_TILED, 0)
+    assert np.all(np.abs(fast - strict) <= ATOL + RTOL * np.abs(strict)), np.abs(fast - strict).max()
