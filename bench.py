@@ -70,7 +70,7 @@ def algorithmic_bytes(prob, nnz):
     for m in prob.meshes:
         b += 4 * m.kind * m.nel_
     b += 16 * prob.meshes[0].nnodes_
-    b += 4 * prob.ndofs
+    b += 4 * getattr(prob, "ndofs_local_", prob.ndofs)     # dof map entries of this rank's sub-mesh
     b += 4 * triplets_per_element(prob) * prob.meshes[0].nel_
     b += 8 * nnz
     return b
@@ -232,6 +232,7 @@ def main():
             sp.field.dofnums = None
         torch.cuda.empty_cache()
     h2d = sum(c.numel() * 8 + x.numel() * 8 for _, c, x in h_mesh) + sum(d.numel() * 8 for d in h_dofs)
+    prob.ndofs_local_ = int(sum(d.numel() for d in h_dofs))
 
     def load():
         for slot, (kind, c, x) in enumerate(h_mesh):
