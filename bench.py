@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--ref-n", type=int, default=500)
     ap.add_argument("--cpu-n", type=int, default=1000)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--e2e-warmup", type=int, default=2, help="untimed e2e calls (device memory pool reaches steady state after two)")
+    ap.add_argument("--e2e-warmup", type=int, default=4, help="untimed e2e calls (the device memory pool needs a few calls to reach steady state)")
     ap.add_argument("--tile-elems", type=int, default=0)
     ap.add_argument("--sfc", type=int, default=1)
     ap.add_argument("--strict", type=int, default=0)

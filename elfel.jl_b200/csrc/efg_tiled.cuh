@@ -731,10 +731,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     int64_t rnz = srun[r].nz0;
     // light nonzeros (1 or 2 contributions: all but the matrix diagonals of node patches): one packed word per
     // nonzero names both stage entries; four nonzeros in flight per lane
-#ifndef TL_U
-#define TL_U 4
-#endif
-    constexpr int U = TL_U;
+    constexpr int U = 4;
     for (int sb = w0; sb < w1; sb += 32 * U) {
         uint32_t pk[U];
 #pragma unroll
@@ -743,7 +740,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
             pk[u] = (s < w1) ? spk[s] : 0xFFFFFFFFu;
         }
         double acc[U];
-#if !defined(TL_P2SPLIT) || !TL_P2SPLIT
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t i0 = pk[u] & 0xFFFFu, i1 = pk[u] >> 16;
@@ -751,24 +747,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
             if (i0 < 0xFFFEu) acc[u] = stage[i0];
             if (i1 < 0xFFFEu) acc[u] = __dadd_rn(acc[u], stage[i1]);
         }
-#else
-        double v1[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i0 = pk[u] & 0xFFFFu;
-            acc[u] = 0.0;
-            if (i0 < 0xFFFEu) acc[u] = stage[i0];
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i1 = pk[u] >> 16;
-            v1[u] = 0.0;
-            if (i1 < 0xFFFEu) v1[u] = stage[i1];
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++)
-            if ((pk[u] >> 16) < 0xFFFEu) acc[u] = __dadd_rn(acc[u], v1[u]);
-#endif
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int s = sb + u * 32 + lane;
@@ -807,7 +785,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
 #ifndef TL_BLOCK_NS
 #define TL_BLOCK_NS 320
 #endif
-template <class F> __host__ __device__ constexpr int tl_block() { return (F::SPLIT || F::ND > 8) ? 256 : TL_BLOCK_NS; }
+#ifndef TL_BLOCK_SPLIT
+#define TL_BLOCK_SPLIT 256
+#endif
+template <class F> __host__ __device__ constexpr int tl_block() { return F::SPLIT ? TL_BLOCK_SPLIT : (F::ND > 8 ? 256 : TL_BLOCK_NS); }
 
 static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32};
 #define TL_SMEM_TWO_CTAS (114 * 1024 + 512)
