@@ -406,10 +406,20 @@ int efg_symbolic(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
         const int npts = upload_tables(ctx, vkind, quad);
         if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, vkind);
         CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-        const int path = ctx->opt_path == 1 ? 1 : 2;
+        int path = ctx->opt_path == 1 ? 1 : 2;
         const bool ok = dispatch_form(form, vkind, npts, [&](auto F) {
             using Form = decltype(F);
-            if (path == 1) twopass_symbolic<Form>(ctx); else tiled_symbolic<Form>(ctx);
+            if (path == 2) {
+                try {
+                    tiled_symbolic<Form>(ctx);
+                } catch (const EfgError &e) {
+                    // auto mode: a mesh beyond the tiled path's limits (node valence, ...) takes the general two-pass path
+                    if (e.code != EFG_ERR_LIMIT || ctx->opt_path == 2) throw;
+                    invalidate(ctx);
+                    path = 1;
+                }
+            }
+            if (path == 1) twopass_symbolic<Form>(ctx);
         });
         if (!ok) efg_throw(EFG_ERR_INVALID, "form %d is not available for element kind %d with rule %d", form, vkind, quad);
         CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));

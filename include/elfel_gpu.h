@@ -35,6 +35,8 @@
  *   - One ctx = one device + one CUDA stream; not re-entrant.  Different ctx may be used from
  *     different host threads.  Multi-GPU = one ctx (one process) per GPU, each assembling a
  *     contiguous block of matrix columns (efg_set_column_range); no communication is needed.
+ *   - The quadrature tables and form parameters live in __constant__ memory of the library: within one process
+ *     run the numeric phase of one ctx at a time (multi-GPU = one process per GPU, as in bench.py).
  *   - There is no CPU fallback: without a CUDA device efg_create fails with EFG_ERR_CUDA.
  */
 #ifndef ELFEL_GPU_H
@@ -71,8 +73,9 @@ typedef struct efg_ctx efg_ctx;
 #define EFG_FORM_STOKES_VECLAP      6 /* space 0: ux, 1: uy (T6), 2: p (T3).  params = [mu]        */
 
 /* options for efg_set_option */
-#define EFG_OPT_PATH        1 /* 0 = auto (tiled fused kernel), 1 = two-pass (element matrices to HBM,
-                                 then segmented gather), 2 = tiled fused kernel */
+#define EFG_OPT_PATH        1 /* 0 = auto (tiled fused kernel; meshes beyond its limits, e.g. a node shared by
+                                 > 90 elements, fall back to the two-pass CUDA path), 1 = two-pass (element
+                                 matrices to HBM, then segmented gather), 2 = tiled fused kernel only */
 #define EFG_OPT_STRICT_FP   2 /* 1 = no FMA contraction: operation order and rounding of the
                                  reference's expressions (bit-identical to the CPU oracle) */
 #define EFG_OPT_TILE_ELEMS  3 /* elements per tile of the fused kernel (0 = automatic) */

@@ -231,3 +231,32 @@ def test_fast_mode_vs_strict_mode_large():
     _, _, strict = _gpu(prob, _lib.PATH_TILED, 1)
     _, _, fast = _gpu(prob, _lib.PATH_TILED, 0)
     assert np.all(np.abs(fast - strict) <= ATOL + RTOL * np.abs(strict)), np.abs(fast - strict).max()
+
+
+def test_auto_path_falls_back_for_high_valence_mesh(oracle):
+    """A fan of 150 triangles around one node: that node's matrix column has 151 rows, beyond the tiled path's
+    per-column limit -> EFG_OPT_PATH=2 reports EFG_ERR_LIMIT, auto mode silently takes the two-pass CUDA path."""
+    nf = 150
+    ang = 2 * np.pi * np.arange(nf) / nf
+    xy = np.concatenate([[[0.0, 0.0]], np.stack([np.cos(ang), np.sin(ang)], axis=1)])
+    conn = np.stack([np.ones(nf, dtype=np.int64), 2 + np.arange(nf), 2 + (np.arange(nf) + 1) % nf], axis=1)
+    mesh = efg.Mesh(efg.T3, conn.astype(np.int64), xy)
+    fesp = efg.FESpace(mesh, efg.FEH1_T3())
+    efg.numberdofs(fesp)
+    n = efg.ndofs(fesp)
+    ocp, orv, onz = oracle.assemble(oracle.FORM_HEAT, 1, mesh, None, [fesp.field.dofnums], [1.0], n, n)
+    for path, expect_fail in ((_lib.PATH_TILED, True), (_lib.PATH_AUTO, False)):
+        eng = efg.Engine(0)
+        eng.set_option(_lib.OPT_PATH, path)
+        eng.set_option(_lib.OPT_STRICT_FP, 1)
+        eng.set_mesh(0, efg.T3, mesh.conn, mesh.xy); eng.set_space(0, 0, fesp.field.dofnums); eng.start(n, n)
+        if expect_fail:
+            with pytest.raises(efg.EfgError) as ei:
+                eng.assemble(_lib.FORM_HEAT, 1, [1.0])
+            assert ei.value.code == _lib.ERR_LIMIT
+        else:
+            eng.assemble(_lib.FORM_HEAT, 1, [1.0])
+            assert int(eng.stat(_lib.STAT_PATH)) == _lib.PATH_TWOPASS
+            cp, rv, nz = eng.fetch_csc()
+            assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz)
+        eng.close()
