@@ -279,7 +279,7 @@ def _errors(oracle, vmesh, pmesh, ux, uy, p):
     return np.sqrt(Ep), np.sqrt(Ev)
 
 
-def _run_stokes(oracle, form, N, three_spaces):
+def _run_stokes(oracle, form, N, three_spaces, assemble=None):
     vmesh, pmesh = _stokes_meshes(N)
     if three_spaces:
         U = [efg.FESpace(vmesh, efg.FEH1_T6(), 1), efg.FESpace(vmesh, efg.FEH1_T6(), 1)]
@@ -293,8 +293,11 @@ def _run_stokes(oracle, form, N, three_spaces):
     tndof = sum(efg.ndofs(s) for s in spaces)
     tnunk = sum(efg.nunknowns(s) for s in spaces)
     params = np.array([2.0, 0, 0, 0, 2.0, 0, 0, 0, 1.0]) if form == oracle.FORM_STOKES_GEN else np.array([1.0])
-    colptr, rowval, nzval = oracle.assemble(form, 3, vmesh, pmesh, [s.field.dofnums for s in spaces],
-                                            params, tndof, tndof)
+    if assemble is None:
+        colptr, rowval, nzval = oracle.assemble(form, 3, vmesh, pmesh, [s.field.dofnums for s in spaces],
+                                                params, tndof, tndof)
+    else:
+        colptr, rowval, nzval = assemble(form, spaces, params, tndof)
     K = _csc(colptr, rowval, nzval, tndof)
     Uv = _solve(K, efg.gathersysvec(spaces, tndof), np.zeros(tndof), tnunk)
     efg.scattersysvec(spaces, Uv)
