@@ -26,11 +26,13 @@ FORM_HEAT, FORM_ELASTICITY, FORM_STOKES_GEN, FORM_STOKES_REDDY, FORM_STOKES_VECL
 OPT_PATH, OPT_STRICT_FP, OPT_TILE_ELEMS, OPT_SFC_ORDER = 1, 2, 3, 4
 PATH_AUTO, PATH_TWOPASS, PATH_TILED = 0, 1, 2
 (STAT_SYMBOLIC_MS, STAT_NUMERIC_MS, STAT_KERNEL_LAUNCHES, STAT_NUMERIC_LAUNCHES, STAT_DEVICE_BYTES,
- STAT_NTILES, STAT_TILE_ELEMS, STAT_NUMERIC_BYTES, STAT_PATH) = range(1, 10)
+ STAT_NTILES, STAT_TILE_ELEMS, STAT_NUMERIC_BYTES, STAT_PATH, STAT_VEC_MS, STAT_SPMV_MS) = range(1, 12)
+VFORM_HEAT_LOAD = 1
 
 EXPORTS = ["efg_create", "efg_destroy", "efg_last_error", "efg_set_option", "efg_get_stat", "efg_get_stream",
            "efg_synchronize", "efg_set_mesh", "efg_set_space", "efg_start", "efg_set_column_range",
-           "efg_set_column_ranges", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version"]
+           "efg_set_column_ranges", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version",
+           "efg_vec_assemble", "efg_fetch_vec", "efg_device_vec", "efg_spmv", "efg_block_nnz", "efg_fetch_block"]
 
 
 def _sources():
@@ -91,6 +93,12 @@ def load():
     L.efg_assemble.argtypes = [vp, ci, ci, f64p, ci, i64p]
     L.efg_fetch_csc.argtypes = [vp, vp, vp, vp]
     L.efg_device_csc.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.efg_vec_assemble.argtypes = [vp, ci, ci, f64p, ci, i64]
+    L.efg_fetch_vec.argtypes = [vp, vp]
+    L.efg_device_vec.argtypes = [vp, C.POINTER(vp), i64p]
+    L.efg_spmv.argtypes = [vp, vp, vp]
+    L.efg_block_nnz.argtypes = [vp, i64, i64, i64, i64, i64p]
+    L.efg_fetch_block.argtypes = [vp, vp, vp, vp]
     for name in EXPORTS:
         if name not in ("efg_version", "efg_last_error") and hasattr(L, name):
             getattr(L, name).restype = ci

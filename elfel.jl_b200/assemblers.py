@@ -11,6 +11,13 @@ for el in elit ... assemble!(ass, ke) end           assemble(ass, HeatForm(kappa
                  (user closure, examples/*)         assemble(ass, ElasticityForm(D), elit, qpit)
                                                     assemble(ass, StokesGenForm(D), (uel, pel), (uqp, pqp)) ...
 finish!(ass)                src/Assemblers.jl:121   finish(ass) -> SparseMatrixCSC(m, n, colptr, rowval, nzval)
+SysvecAssembler(0.0)        src/Assemblers.jl:183   SysvecAssemblerGPU(0.0, like=am)   (shares am's device context)
+start!(av, nrow)            src/Assemblers.jl:196   start(av, nrow)
+init!(fe, eldofs(el)); fe[j] += N[j]*Q*JxW;         assemble(av, HeatLoadForm(Q), elit, qpit)
+  assemble!(av, fe)         examples/heat/.../t3.jl:44-61
+finish!(av)                 src/Assemblers.jl:230   finish(av) -> numpy vector
+KT = K * T                  examples/heat/.../t3.jl:78   mul(am, T)              (on the device, Julia's summation order)
+K[1:nu, 1:nu]               examples/heat/.../t3.jl:79   block(am, 1, nu, 1, nu) (sliced on the device)
 
 The element loop + COO append + sparse() of the reference collapse into one ``assemble`` call that
 runs on the GPU through the C ABI (include/elfel_gpu.h).  There is no CPU fallback.
@@ -68,6 +75,15 @@ class HeatForm:           # examples/heat/poisson/t3.jl:53-58
 
     def params(self):
         return np.array([self.kappa], dtype=np.float64)
+
+
+@dataclass
+class HeatLoadForm:       # examples/heat/poisson/t3.jl:57  fe[j] += N[j] * Q * JxW   (vector form)
+    Q: float = 0.0
+    vform_id = _lib.VFORM_HEAT_LOAD
+
+    def params(self):
+        return np.array([self.Q], dtype=np.float64)
 
 
 @dataclass
@@ -233,6 +249,40 @@ class Engine:
         return colptr, rowval, nzval
 
 
+    # ---- SURVEY 8f rows f1 / f2 -------------------------------------------------------------------
+    def vec_assemble(self, vform_id, quad, params, nrow):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._ck(self.L.efg_vec_assemble(self.h, vform_id, quad, p.ctypes.data_as(C.POINTER(C.c_double)), len(p), int(nrow)))
+        n = C.c_int64()
+        self._ck(self.L.efg_device_vec(self.h, None, C.byref(n)))
+        self.nvec = n.value
+
+    def fetch_vec(self, out=None):
+        if out is None:
+            out = np.empty(self.nvec, dtype=np.float64)
+        self._ck(self.L.efg_fetch_vec(self.h, _ptr(out)))
+        return out
+
+    def spmv(self, x, y=None):
+        """y = K*x in SparseArrays' accumulation order; x, y numpy (host) or torch (host/device) float64."""
+        if isinstance(x, np.ndarray):
+            x = np.ascontiguousarray(x, dtype=np.float64)
+        if y is None:
+            y = np.empty(self.nrow, dtype=np.float64)
+        self._ck(self.L.efg_spmv(self.h, _ptr(x), _ptr(y)))
+        return y
+
+    def block(self, r0, r1, c0, c1):
+        """K[r0:r1, c0:c1] (1-based inclusive) -> (colptr, rowval, nzval) of the block, sliced on the device."""
+        nnz = C.c_int64()
+        self._ck(self.L.efg_block_nnz(self.h, int(r0), int(r1), int(c0), int(c1), C.byref(nnz)))
+        colptr = np.empty(int(c1) - int(c0) + 2, dtype=np.int64)
+        rowval = np.empty(nnz.value, dtype=np.int64)
+        nzval = np.empty(nnz.value, dtype=np.float64)
+        self._ck(self.L.efg_fetch_block(self.h, _ptr(colptr), _ptr(rowval), _ptr(nzval)))
+        return colptr, rowval, nzval
+
+
 class SysmatAssemblerGPU:
     """Selected in place of SysmatAssemblerSparse; same start / assemble / finish life cycle."""
 
@@ -249,7 +299,45 @@ class SysmatAssemblerGPU:
         return self
 
 
-def start(ass: SysmatAssemblerGPU, nrow, ncol):
+class SysvecAssemblerGPU:
+    """Selected in place of SysvecAssembler (src/Assemblers.jl:170-232).  ``like=am`` shares the device context of a
+    SysmatAssemblerGPU, so the mesh and dof maps uploaded for the matrix are reused for the vector."""
+
+    def __init__(self, zero: float = 0.0, device: int = 0, like: "SysmatAssemblerGPU | None" = None):
+        if not isinstance(zero, float):
+            raise TypeError("only Float64 vectors are assembled")
+        self.engine = like.engine if like is not None else Engine(device)
+        self.ndofs = 0
+        self._started = False
+        self._assembled = False
+
+
+def _load_spaces(eng, elits, reuse=False):
+    """Upload meshes + dof maps.  ``reuse``: skip the upload when this engine was last loaded from exactly these
+    objects (the vector half of one integrate! call that follows the matrix half on a shared context)."""
+    token = tuple((id(it.fesp.mesh), id(it._fld0.dofnums)) for it in elits)
+    if reuse and getattr(eng, "_loaded", None) == token:
+        return
+    meshes = []
+    for it in elits:
+        if not any(it.fesp.mesh is m for m in meshes):
+            meshes.append(it.fesp.mesh)
+    if len(meshes) > 2:
+        raise ValueError("at most two meshes (velocity, pressure)")
+    for slot, m in enumerate(meshes):
+        eng.set_mesh(slot, m.kind, np.ascontiguousarray(m.conn, dtype=np.int64), np.ascontiguousarray(m.xy, dtype=np.float64))
+    for slot, it in enumerate(elits):
+        mslot = [i for i, m in enumerate(meshes) if m is it.fesp.mesh][0]
+        eng.set_space(slot, mslot, np.ascontiguousarray(it._fld0.dofnums, dtype=np.int64))
+    eng._loaded = token
+    eng._keep = [it for it in elits]      # the ids in the token stay valid while these are alive
+
+
+def start(ass, nrow, ncol=None):
+    if isinstance(ass, SysvecAssemblerGPU):   # start!(av, nrow): src/Assemblers.jl:196-200
+        ass.ndofs = int(nrow)
+        ass._started, ass._assembled = True, False
+        return ass
     ass.engine.start(nrow, ncol)
     ass.nrow, ass.ncol = int(nrow), int(ncol)
     ass._started, ass._assembled = True, False
@@ -265,25 +353,36 @@ def assemble(ass: SysmatAssemblerGPU, form, elits, qpits):
     if len({q.rule for q in qpits}) != 1:
         raise ValueError("all spaces of a mixed form must use the same quadrature rule")
     eng = ass.engine
-    meshes = []
-    for it in elits:
-        if not any(it.fesp.mesh is m for m in meshes):
-            meshes.append(it.fesp.mesh)
-    if len(meshes) > 2:
-        raise ValueError("at most two meshes (velocity, pressure)")
-    for slot, m in enumerate(meshes):
-        eng.set_mesh(slot, m.kind, np.ascontiguousarray(m.conn, dtype=np.int64), np.ascontiguousarray(m.xy, dtype=np.float64))
-    for slot, it in enumerate(elits):
-        mslot = [i for i, m in enumerate(meshes) if m is it.fesp.mesh][0]
-        eng.set_space(slot, mslot, np.ascontiguousarray(it._fld0.dofnums, dtype=np.int64))
+    _load_spaces(eng, elits, reuse=isinstance(ass, SysvecAssemblerGPU))
+    if isinstance(ass, SysvecAssemblerGPU):
+        eng.vec_assemble(form.vform_id, qpits[0].rule, form.params(), ass.ndofs)
+        ass._assembled = True
+        return ass
     eng.start(ass.nrow, ass.ncol)
     eng.assemble(form.form_id, qpits[0].rule, form.params())
     ass._assembled = True
     return ass
 
 
-def finish(ass: SysmatAssemblerGPU) -> SparseMatrixCSC:
+def finish(ass):
     if not ass._assembled:
         raise _lib.EfgError(_lib.ERR_STATE, "finish before assemble")
+    if isinstance(ass, SysvecAssemblerGPU):   # finish!(av): src/Assemblers.jl:230-232
+        return ass.engine.fetch_vec()
     colptr, rowval, nzval = ass.engine.fetch_csc()
     return SparseMatrixCSC(ass.nrow, ass.ncol, colptr, rowval, nzval)
+
+
+def mul(ass: SysmatAssemblerGPU, x):
+    """``K * x`` (examples/heat/poisson/t3.jl:78) on the device, without fetching K."""
+    if not ass._assembled:
+        raise _lib.EfgError(_lib.ERR_STATE, "mul before assemble")
+    return ass.engine.spmv(x)
+
+
+def block(ass: SysmatAssemblerGPU, r0, r1, c0, c1) -> SparseMatrixCSC:
+    """``K[r0:r1, c0:c1]`` (1-based inclusive; examples/heat/poisson/t3.jl:79) sliced on the device."""
+    if not ass._assembled:
+        raise _lib.EfgError(_lib.ERR_STATE, "block before assemble")
+    colptr, rowval, nzval = ass.engine.block(r0, r1, c0, c1)
+    return SparseMatrixCSC(int(r1) - int(r0) + 1, int(c1) - int(c0) + 1, colptr, rowval, nzval)

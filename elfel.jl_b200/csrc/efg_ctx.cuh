@@ -89,6 +89,7 @@ struct efg_ctx {
     TwoPass tp;
     Tiled tl;
     void *tl_opaque = nullptr;
+    void *vec_opaque = nullptr;  // efg_vector.cuh: system-vector assembly, K*x, sub-blocks
     DevBuf<char> scratch;        // persistent scratch for the largest symbolic temporaries (kept across calls: the
                                  // multi-GB sort buffers made cudaMallocAsync stall for 0.1-2.5 s when re-allocated every call)
 

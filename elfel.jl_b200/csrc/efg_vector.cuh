@@ -1,0 +1,232 @@
+// efg_vector.cuh -- the callers either side of the matrix path, all on the device:
+//   f1  system VECTOR assembly: SysvecAssembler start!/assemble!/finish! fed by a LocalVectorAssembler
+//       (src/Assemblers.jl:196-232, src/LocalAssemblers.jl:95-152) for the load term of the heat examples,
+//       `fe[j] += N[j]*Q*JxW` (examples/heat/poisson/t3.jl:57, q4.jl:47);
+//   f2  what the examples do with K right after finish!: `KT = K*T` (examples/heat/poisson/t3.jl:78) and the
+//       partition K[1:nu,1:nu], K[1:nu,nu+1:end] (t3.jl:79, examples/stokes/colliding_flow/ht_p2_p1_gen.jl solve!),
+//       so a 10 GB matrix is not copied to the host just to be sliced.
+//
+// Determinism / parity: the reference adds contributions to val[gi] element by element (ascending element, local
+// index ascending), and SparseArrays' K*x accumulates y[r] column by column.  Both orders are reproduced exactly:
+// a stable radix sort groups contributions by destination keeping their original order, one thread then sums a
+// destination left to right.  No atomics.  All arithmetic here uses explicitly rounded operations (no FMA
+// contraction) -- these kernels are memory-bound, so the results are bit-identical to the CPU oracle in every mode.
+#pragma once
+#include "efg_tiled.cuh"
+
+struct VecData {
+    // f1: dof -> contributions (t = e*NEN + local index), grouped by local row, original order kept
+    DevBuf<uint32_t> adjptr, adj;
+    DevBuf<double> fe;          // NEN x nel, SoA: fe[j*nel + e]
+    DevBuf<double> val;         // owned rows
+    int64_t nrl = 0;            // owned rows (= nrow, or the ctx's column ranges when sharded)
+    int64_t nrow = 0;
+    bool have_sym = false, have_val = false;
+    // f2: row-major view of the CSC result
+    DevBuf<int64_t> rowptr;     // nrow+1
+    DevBuf<uint32_t> tperm;     // row-major position -> CSC position
+    DevBuf<int32_t> tcol;       // row-major position -> local column
+    bool have_csr = false;
+    // f2: last extracted block
+    DevBuf<int64_t> bcolptr;
+    DevBuf<int64_t> bfirst;     // first CSC position of each block column
+    int64_t bnnz = 0, br0 = 0, bc0 = 0, bncol = 0;
+    bool have_block = false;
+    double vec_ms = 0, spmv_ms = 0;
+};
+
+static inline VecData *&vec_data(efg_ctx *ctx) { return *reinterpret_cast<VecData **>(&ctx->vec_opaque); }
+inline void vec_release(efg_ctx *ctx)
+{
+    VecData *&d = vec_data(ctx);
+    delete d;
+    d = nullptr;
+}
+static inline VecData *vec_get(efg_ctx *ctx)
+{
+    VecData *&d = vec_data(ctx);
+    if (!d) d = new VecData();
+    return d;
+}
+// ---- f1: vector assembly ------------------------------------------------------------------------------
+template <int NEN>
+__global__ void k_vec_keys(const int32_t *__restrict__ conn, const int32_t *__restrict__ dof, int64_t nel, int64_t nrow, ColMap cm,
+                           uint32_t nrl, uint32_t *__restrict__ cnt, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, int *__restrict__ err)
+{
+    GRID_STRIDE(t, nel * NEN) {
+        const int32_t d = dof[conn[t]];
+        if (d < 0 || d >= nrow) *err = 1;                 // Julia: BoundsError on val[gi]
+        const int64_t l = (d < 0 || d >= nrow) ? -1 : cm.local(d);
+        if (l >= 0) { atomicAdd(&cnt[l], 1u); keys[t] = (uint32_t)l; } else keys[t] = nrl;
+        vals[t] = (uint32_t)t;
+    }
+}
+
+// one thread per element: fe[j] = sum_q (N[j]*Q)*JxW, quadrature points in order, starting from 0.0
+template <int NEN, int NQ>
+__global__ void __launch_bounds__(256) k_vec_heat_load(const int32_t *__restrict__ conn, const double2 *__restrict__ xy, int64_t nel,
+                                                       double Q, double *__restrict__ fe)
+{
+    const QTab &tg = c_tab[kind_slot(NEN)];
+    GRID_STRIDE(e, nel) {
+        double X[NEN], Y[NEN];
+        load_xy<NEN>(conn, xy, e, X, Y);
+        double f[NEN];
+#pragma unroll
+        for (int j = 0; j < NEN; j++) f[j] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            // _jac + Jacobian(Val{2}): src/FElements.jl:148-156,120-129 (node-order sum, first term assigned)
+            double J00 = __dmul_rn(X[0], tg.gp[q][0][0]), J01 = __dmul_rn(X[0], tg.gp[q][0][1]);
+            double J10 = __dmul_rn(Y[0], tg.gp[q][0][0]), J11 = __dmul_rn(Y[0], tg.gp[q][0][1]);
+#pragma unroll
+            for (int n = 1; n < NEN; n++) {
+                J00 = __dadd_rn(J00, __dmul_rn(X[n], tg.gp[q][n][0])); J01 = __dadd_rn(J01, __dmul_rn(X[n], tg.gp[q][n][1]));
+                J10 = __dadd_rn(J10, __dmul_rn(Y[n], tg.gp[q][n][0])); J11 = __dadd_rn(J11, __dmul_rn(Y[n], tg.gp[q][n][1]));
+            }
+            const double JxW = __dmul_rn(__dsub_rn(__dmul_rn(J00, J11), __dmul_rn(J10, J01)), tg.w[q]);
+#pragma unroll
+            for (int j = 0; j < NEN; j++) f[j] = __dadd_rn(f[j], __dmul_rn(__dmul_rn(tg.N[q][j], Q), JxW));
+        }
+#pragma unroll
+        for (int j = 0; j < NEN; j++) fe[(int64_t)j * nel + e] = f[j];
+    }
+}
+
+// one thread per owned row: val = ((0.0 + c1) + c2) + ... in the reference's order
+template <int NEN>
+__global__ void k_vec_gather(const uint32_t *__restrict__ adjptr, const uint32_t *__restrict__ adj, const double *__restrict__ fe,
+                             int64_t nel, int64_t nrl, double *__restrict__ val)
+{
+    GRID_STRIDE(r, nrl) {
+        double acc = 0.0;
+        const uint32_t a1 = adjptr[r + 1];
+        for (uint32_t p = adjptr[r]; p < a1; p++) {
+            const uint32_t t = adj[p];
+            acc = __dadd_rn(acc, fe[(int64_t)(t % NEN) * nel + (t / NEN)]);
+        }
+        val[r] = acc;
+    }
+}
+
+template <int NEN> static void vec_symbolic(efg_ctx *ctx, VecData *vd, int64_t nrow)
+{
+    const MeshDev &m = ctx->mesh[0];
+    const int64_t nel = m.nel, np = nel * NEN;
+    if (np >= ((int64_t)1 << 32)) efg_throw(EFG_ERR_LIMIT, "vector assembly: nel*nen exceeds 2^32; shard the mesh");
+    // owned rows: the ctx's column ranges when the owner-computes sharding is active for an nrow x nrow system
+    const bool sharded = ctx->started && ctx->have_range && ctx->ncol == nrow;
+    ColMap cm = sharded ? COLMAP(ctx) : ColMap{0, nrow, 0, nullptr, nullptr, nullptr};
+    const int64_t nrl = sharded ? ctx->ncl : nrow;
+    DevBuf<int> err;
+    err.alloc(ctx->pool, 1);
+    CUDA_CHECK(cudaMemsetAsync(err.p, 0, sizeof(int), ctx->stream));
+    DevBuf<uint32_t> cnt;
+    cnt.alloc(ctx->pool, (size_t)nrl + 2);
+    CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, ((size_t)nrl + 2) * sizeof(uint32_t), ctx->stream));
+    vd->adjptr.alloc(ctx->pool, (size_t)nrl + 2);
+    vd->adj.alloc(ctx->pool, (size_t)(np > 0 ? np : 1));
+    {
+        const size_t n = (size_t)(np > 0 ? np : 1);
+        uint32_t *k1 = reinterpret_cast<uint32_t *>(tl_scratch(ctx, 3 * n * sizeof(uint32_t))), *k2 = k1 + n, *v1 = k2 + n;
+        LAUNCH(ctx, k_vec_keys<NEN>, grid_for(np, 256), 256, 0, m.conn.p, ctx->space[0].dof.p, nel, nrow, cm, (uint32_t)nrl, cnt.p, k1, v1, err.p);
+        if (tl_read(ctx, err.p))
+            efg_throw(EFG_ERR_INDEX, "BoundsError: a dof number is < 1 or exceeds nrow (was the space numbered, incl. data dofs?)");
+        if (np > 0) tl_sort_pairs(ctx, k1, k2, v1, vd->adj.p, np, bits_for(nrl));
+    }
+    tl_excl_scan(ctx, cnt.p, vd->adjptr.p, nrl + 1);
+    vd->fe.alloc(ctx->pool, (size_t)(np > 0 ? np : 1));
+    vd->val.alloc(ctx->pool, (size_t)(nrl > 0 ? nrl : 1));
+    vd->nrl = nrl; vd->nrow = nrow;
+    vd->have_sym = true;
+}
+
+template <int NEN, int NQ> static void vec_numeric_heat(efg_ctx *ctx, VecData *vd, double Q)
+{
+    const MeshDev &m = ctx->mesh[0];
+    LAUNCH(ctx, (k_vec_heat_load<NEN, NQ>), grid_for(m.nel, 256, (int64_t)148 * 32), 256, 0, m.conn.p, m.xy.p, m.nel, Q, vd->fe.p);
+    LAUNCH(ctx, k_vec_gather<NEN>, grid_for(vd->nrl, 256, (int64_t)148 * 32), 256, 0, vd->adjptr.p, vd->adj.p, vd->fe.p, m.nel, vd->nrl, vd->val.p);
+}
+
+// ---- f2: K*x in SparseArrays' accumulation order, and sub-blocks of K -------------------------------------
+__global__ void k_csr_keys(const int64_t *__restrict__ colptr, int64_t ncl, const int32_t *__restrict__ rowval,
+                           uint32_t *__restrict__ keys, uint32_t *__restrict__ vals, int32_t *__restrict__ colof, uint32_t *__restrict__ rowcnt)
+{
+    GRID_STRIDE(c, ncl) {
+        const int64_t p1 = colptr[c + 1] - 1;
+        for (int64_t p = colptr[c] - 1; p < p1; p++) {
+            const int32_t r = rowval[p];
+            keys[p] = (uint32_t)r; vals[p] = (uint32_t)p; colof[p] = (int32_t)c;
+            atomicAdd(&rowcnt[r], 1u);
+        }
+    }
+}
+__global__ void k_csr_cols(const uint32_t *__restrict__ tperm, const int32_t *__restrict__ colof, int64_t nnz, int32_t *__restrict__ tcol)
+{
+    GRID_STRIDE(q, nnz) tcol[q] = colof[tperm[q]];
+}
+// y[r] = ((0.0 + a_rc1*x_c1) + a_rc2*x_c2) + ... , columns ascending, product and sum rounded separately
+__global__ void k_spmv_rows(const int64_t *__restrict__ rowptr, const uint32_t *__restrict__ tperm, const int32_t *__restrict__ tcol,
+                            const double *__restrict__ nzval, const double *__restrict__ x, int64_t nrow, double *__restrict__ y)
+{
+    GRID_STRIDE(r, nrow) {
+        double acc = 0.0;
+        const int64_t q1 = rowptr[r + 1];
+        for (int64_t q = rowptr[r]; q < q1; q++) acc = __dadd_rn(acc, __dmul_rn(nzval[tperm[q]], __ldg(&x[tcol[q]])));
+        y[r] = acc;
+    }
+}
+
+static void vec_build_csr(efg_ctx *ctx, VecData *vd)
+{
+    const int64_t nnz = ctx->nnz, nrow = ctx->nrow, ncl = ctx->ncl;
+    if (nnz >= ((int64_t)1 << 32)) efg_throw(EFG_ERR_LIMIT, "efg_spmv: nnz exceeds 2^32");
+    const size_t n = (size_t)(nnz > 0 ? nnz : 1);
+    DevBuf<uint32_t> rowcnt;
+    rowcnt.alloc(ctx->pool, (size_t)nrow + 2);
+    CUDA_CHECK(cudaMemsetAsync(rowcnt.p, 0, ((size_t)nrow + 2) * sizeof(uint32_t), ctx->stream));
+    vd->rowptr.alloc(ctx->pool, (size_t)nrow + 2);
+    vd->tperm.alloc(ctx->pool, n);
+    vd->tcol.alloc(ctx->pool, n);
+    uint32_t *k1 = reinterpret_cast<uint32_t *>(tl_scratch(ctx, 4 * n * sizeof(uint32_t))), *k2 = k1 + n, *v1 = k2 + n;
+    int32_t *colof = reinterpret_cast<int32_t *>(v1 + n);
+    LAUNCH(ctx, k_csr_keys, grid_for(ncl, 128), 128, 0, ctx->colptr.p, ncl, ctx->rowval.p, k1, v1, colof, rowcnt.p);
+    if (nnz > 0) tl_sort_pairs(ctx, k1, k2, v1, vd->tperm.p, nnz, bits_for(nrow));     // stable: columns stay ascending inside a row
+    LAUNCH(ctx, k_csr_cols, grid_for(nnz, 256), 256, 0, vd->tperm.p, colof, nnz, vd->tcol.p);
+    {
+        cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const uint32_t *> it(rowcnt.p, cub::CastOp<int64_t>());
+        tl_excl_scan(ctx, it, vd->rowptr.p, nrow + 1);
+    }
+    vd->have_csr = true;
+}
+
+// entries of column c (local) with r0 <= row < r1: rows are ascending inside a column
+__global__ void k_block_count(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowval, int64_t bc0, int64_t bncol,
+                              int32_t r0, int32_t r1, int64_t *__restrict__ cnt, int64_t *__restrict__ first)
+{
+    GRID_STRIDE(j, bncol) {
+        const int64_t p0 = colptr[bc0 + j] - 1, p1 = colptr[bc0 + j + 1] - 1;
+        int64_t lo = p0, hi = p1;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < r0) lo = mid + 1; else hi = mid; }
+        const int64_t a = lo;
+        hi = p1;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (rowval[mid] < r1) lo = mid + 1; else hi = mid; }
+        cnt[j] = lo - a;
+        first[j] = a;
+    }
+}
+__global__ void k_block_colptr_out(const int64_t *__restrict__ in, int64_t n, int64_t *__restrict__ out) { GRID_STRIDE(i, n) out[i] = in[i] + 1; }
+// one warp per block column: copy its entries (rows rebased to the block, 1-based Int64)
+__global__ void k_block_copy(const int64_t *__restrict__ bcolptr, const int64_t *__restrict__ first, int64_t bncol, const int32_t *__restrict__ rowval,
+                             const double *__restrict__ nzval, int64_t r0, int64_t *__restrict__ orow, double *__restrict__ oval)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t j = w; j < bncol; j += nw) {
+        const int64_t o = bcolptr[j], n = bcolptr[j + 1] - o, a = first[j];
+        for (int64_t k = lane; k < n; k += 32) {
+            if (orow) orow[o + k] = (int64_t)rowval[a + k] - r0 + 1;
+            if (oval) oval[o + k] = nzval[a + k];
+        }
+    }
+}

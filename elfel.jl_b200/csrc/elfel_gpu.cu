@@ -3,6 +3,7 @@
 #include "efg_ctx.cuh"
 #include "efg_twopass.cuh"
 #include "efg_tiled.cuh"
+#include "efg_vector.cuh"
 
 #include <cstring>
 #include <cmath>
@@ -138,6 +139,7 @@ static void invalidate(efg_ctx *ctx)
     ctx->colptr.release(); ctx->rowval.release(); ctx->nzval.release();
     ctx->tp.perm.release(); ctx->tp.seg_start.release(); ctx->tp.Ke.release();
     tiled_release(ctx);
+    vec_release(ctx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -270,6 +272,8 @@ int efg_get_stat(efg_ctx *ctx, int which, double *out)
     case EFG_STAT_TILE_ELEMS: *out = (double)ctx->tl.sum_tile_elems; break;
     case EFG_STAT_NUMERIC_BYTES: *out = (double)ctx->tl.numeric_bytes; break;
     case EFG_STAT_PATH: *out = (double)ctx->path; break;
+    case EFG_STAT_VEC_MS: *out = vec_data(ctx) ? vec_data(ctx)->vec_ms : 0.0; break;
+    case EFG_STAT_SPMV_MS: *out = vec_data(ctx) ? vec_data(ctx)->spmv_ms : 0.0; break;
     default: efg_throw(EFG_ERR_INVALID, "unknown stat %d", which);
     }
     API_END(ctx)
@@ -495,6 +499,160 @@ int efg_device_csc(efg_ctx *ctx, const int64_t **colptr, const int32_t **rowval,
     if (colptr) *colptr = ctx->colptr.p;
     if (rowval) *rowval = ctx->rowval.p;
     if (nzval) *nzval = ctx->nzval.p;
+    API_END(ctx)
+}
+
+// ---- SURVEY 8f rows f1 / f2 (efg_vector.cuh) ----------------------------------------------------------
+static bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+static float elapsed_sync(efg_ctx *ctx)
+{
+    float ms = 0;
+    CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    return ms;
+}
+
+int efg_vec_assemble(efg_ctx *ctx, int vform, int quad, const double *params, int nparams, int64_t nrow)
+{
+    API_BEGIN(ctx)
+    if (vform != EFG_VFORM_HEAT_LOAD) efg_throw(EFG_ERR_INVALID, "unknown vector form %d", vform);
+    const MeshDev &m0 = ctx->mesh[0];
+    if (m0.kind == 0) efg_throw(EFG_ERR_STATE, "mesh 0 not set");
+    if (ctx->space[0].mesh != 0 || ctx->space[0].ncomp != 1) efg_throw(EFG_ERR_INVALID, "the heat load vector needs space 0 on mesh 0 with 1 component");
+    if (!params || nparams != 1) efg_throw(EFG_ERR_INVALID, "vector form %d takes 1 parameter (Q)", vform);
+    if (nrow < 0 || nrow >= ((int64_t)1 << 31)) efg_throw(EFG_ERR_INVALID, "bad vector length");
+    const int npts = upload_tables(ctx, m0.kind, quad);
+    if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, m0.kind);
+    VecData *vd = vec_get(ctx);
+    if (!(vd->have_sym && vd->nrow == nrow)) {
+        vd->have_sym = false; vd->have_val = false;
+        switch (m0.kind) {
+        case EFG_T3: vec_symbolic<3>(ctx, vd, nrow); break;
+        case EFG_Q4: vec_symbolic<4>(ctx, vd, nrow); break;
+        default: vec_symbolic<6>(ctx, vd, nrow); break;
+        }
+    }
+    const double Q = params[0];
+    CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    const int key = m0.kind * 100 + npts;
+    switch (key) {
+    case 301: vec_numeric_heat<3, 1>(ctx, vd, Q); break;
+    case 303: vec_numeric_heat<3, 3>(ctx, vd, Q); break;
+    case 601: vec_numeric_heat<6, 1>(ctx, vd, Q); break;
+    case 603: vec_numeric_heat<6, 3>(ctx, vd, Q); break;
+    case 401: vec_numeric_heat<4, 1>(ctx, vd, Q); break;
+    case 404: vec_numeric_heat<4, 4>(ctx, vd, Q); break;
+    case 409: vec_numeric_heat<4, 9>(ctx, vd, Q); break;
+    default: efg_throw(EFG_ERR_INVALID, "the heat load vector is not available for element kind %d with rule %d", m0.kind, quad);
+    }
+    CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    vd->vec_ms = elapsed_sync(ctx);
+    vd->have_val = true;
+    API_END(ctx)
+}
+
+int efg_fetch_vec(efg_ctx *ctx, double *out)
+{
+    API_BEGIN(ctx)
+    VecData *vd = vec_data(ctx);
+    if (!vd || !vd->have_val) efg_throw(EFG_ERR_STATE, "efg_fetch_vec before efg_vec_assemble");
+    if (!out) efg_throw(EFG_ERR_INVALID, "null output");
+    if (vd->nrl > 0) CUDA_CHECK(cudaMemcpyAsync(out, vd->val.p, (size_t)vd->nrl * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
+}
+
+int efg_device_vec(efg_ctx *ctx, const double **val, int64_t *n)
+{
+    API_BEGIN(ctx)
+    VecData *vd = vec_data(ctx);
+    if (!vd || !vd->have_val) efg_throw(EFG_ERR_STATE, "efg_device_vec before efg_vec_assemble");
+    if (val) *val = vd->val.p;
+    if (n) *n = vd->nrl;
+    API_END(ctx)
+}
+
+int efg_spmv(efg_ctx *ctx, const double *x, double *y)
+{
+    API_BEGIN(ctx)
+    if (!ctx->have_symbolic || !ctx->have_values) efg_throw(EFG_ERR_STATE, "efg_spmv before efg_numeric");
+    if (ctx->have_range) efg_throw(EFG_ERR_STATE, "efg_spmv needs the whole matrix on this ctx (no column range)");
+    if (!x || !y) efg_throw(EFG_ERR_INVALID, "null vector");
+    VecData *vd = vec_get(ctx);
+    if (!vd->have_csr) vec_build_csr(ctx, vd);
+    DevBuf<double> xs, ys;
+    const double *xd = x;
+    double *yd = y;
+    if (!is_device_ptr(x)) {
+        xs.alloc(ctx->pool, (size_t)ctx->ncol + 1);
+        CUDA_CHECK(cudaMemcpyAsync(xs.p, x, (size_t)ctx->ncol * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        xd = xs.p;
+    }
+    if (!is_device_ptr(y)) { ys.alloc(ctx->pool, (size_t)ctx->nrow + 1); yd = ys.p; }
+    CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    LAUNCH(ctx, k_spmv_rows, grid_for(ctx->nrow, 256, (int64_t)148 * 32), 256, 0, vd->rowptr.p, vd->tperm.p, vd->tcol.p, ctx->nzval.p, xd, ctx->nrow, yd);
+    CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (yd != y) CUDA_CHECK(cudaMemcpyAsync(y, yd, (size_t)ctx->nrow * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    vd->spmv_ms = elapsed_sync(ctx);
+    API_END(ctx)
+}
+
+int efg_block_nnz(efg_ctx *ctx, int64_t row_first, int64_t row_last, int64_t col_first, int64_t col_last, int64_t *nnz_out)
+{
+    API_BEGIN(ctx)
+    if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_block_nnz before efg_symbolic");
+    if (ctx->have_range) efg_throw(EFG_ERR_STATE, "efg_block_nnz needs the whole matrix on this ctx (no column range)");
+    if (row_first < 1 || row_last > ctx->nrow || row_last < row_first - 1 || col_first < 1 || col_last > ctx->ncol || col_last < col_first - 1)
+        efg_throw(EFG_ERR_INDEX, "BoundsError: block [%lld:%lld, %lld:%lld] of a %lld x %lld matrix", (long long)row_first, (long long)row_last,
+                  (long long)col_first, (long long)col_last, (long long)ctx->nrow, (long long)ctx->ncol);
+    VecData *vd = vec_get(ctx);
+    const int64_t bncol = col_last - col_first + 1;
+    DevBuf<int64_t> cnt;
+    cnt.alloc(ctx->pool, (size_t)bncol + 2);
+    CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, ((size_t)bncol + 2) * sizeof(int64_t), ctx->stream));
+    vd->bcolptr.alloc(ctx->pool, (size_t)bncol + 2);
+    vd->bfirst.alloc(ctx->pool, (size_t)bncol + 2);
+    LAUNCH(ctx, k_block_count, grid_for(bncol, 256), 256, 0, ctx->colptr.p, ctx->rowval.p, col_first - 1, bncol, (int32_t)(row_first - 1), (int32_t)row_last, cnt.p, vd->bfirst.p);
+    tl_excl_scan(ctx, cnt.p, vd->bcolptr.p, bncol + 1);
+    vd->bnnz = tl_read(ctx, vd->bcolptr.p + bncol);
+    vd->br0 = row_first - 1; vd->bc0 = col_first - 1; vd->bncol = bncol;
+    vd->have_block = true;
+    if (nnz_out) *nnz_out = vd->bnnz;
+    API_END(ctx)
+}
+
+int efg_fetch_block(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval)
+{
+    API_BEGIN(ctx)
+    VecData *vd = vec_data(ctx);
+    if (!vd || !vd->have_block || !ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_fetch_block before efg_block_nnz");
+    if (nzval && !ctx->have_values) efg_throw(EFG_ERR_STATE, "efg_fetch_block(nzval) before efg_numeric");
+    const int64_t n = vd->bnnz, bncol = vd->bncol;
+    if (colptr) {
+        DevBuf<int64_t> cp;
+        cp.alloc(ctx->pool, (size_t)bncol + 1);
+        LAUNCH(ctx, k_block_colptr_out, grid_for(bncol + 1, 256), 256, 0, vd->bcolptr.p, bncol + 1, cp.p);
+        CUDA_CHECK(cudaMemcpyAsync(colptr, cp.p, (size_t)(bncol + 1) * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    if ((rowval || nzval) && n > 0) {
+        DevBuf<int64_t> rs;
+        DevBuf<double> vs;
+        int64_t *rd = nullptr;
+        double *vdp = nullptr;
+        if (rowval) { if (is_device_ptr(rowval)) rd = rowval; else { rs.alloc(ctx->pool, (size_t)n); rd = rs.p; } }
+        if (nzval) { if (is_device_ptr(nzval)) vdp = nzval; else { vs.alloc(ctx->pool, (size_t)n); vdp = vs.p; } }
+        LAUNCH(ctx, k_block_copy, grid_for(bncol * 32, 256), 256, 0, vd->bcolptr.p, vd->bfirst.p, bncol, ctx->rowval.p, ctx->nzval.p, vd->br0, rd, vdp);
+        if (rowval && rd != rowval) CUDA_CHECK(cudaMemcpyAsync(rowval, rd, (size_t)n * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+        if (nzval && vdp != nzval) CUDA_CHECK(cudaMemcpyAsync(nzval, vdp, (size_t)n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
     API_END(ctx)
 }
 

@@ -18,6 +18,14 @@
  *                                                                        ht_p2_p1_veclap_alt.jl:60-98
  *                             + assemble!(ass, lma) / transpose(lma)     src/Assemblers.jl:97-114
  *   efg_fetch_csc             finish!(ass) -> sparse(I,J,V,m,n)          src/Assemblers.jl:121-123
+ *   efg_vec_assemble          SysvecAssembler start!(av, nrow) + the `init!(fe, eldofs(el)); fe[j] += N[j]*Q*JxW;
+ *                             assemble!(av, fe)` half of the same integrate! loop
+ *                                                                        src/Assemblers.jl:196-223, src/LocalAssemblers.jl:95-152,
+ *                                                                        examples/heat/poisson/t3.jl:44-61, q4.jl:34-51
+ *   efg_fetch_vec             finish!(av)                                src/Assemblers.jl:230-232
+ *   efg_spmv                  `KT = K * T` right after assembly          examples/heat/poisson/t3.jl:78
+ *   efg_block_nnz/_fetch_block  `K[1:nu, 1:nu]`, `K[1:nu, nu+1:end]`     examples/heat/poisson/t3.jl:79,
+ *                                                                        examples/stokes/colliding_flow/ht_p2_p1_gen.jl (solve!)
  *
  * Conventions
  *   - Plain pointers and sizes only.  All index arrays are Int64 and 1-BASED, in the memory
@@ -72,6 +80,9 @@ typedef struct efg_ctx efg_ctx;
 #define EFG_FORM_STOKES_VECLAP_ALT  5 /* space 0: u (T6,2), 1: p (T3).  params = [mu]              */
 #define EFG_FORM_STOKES_VECLAP      6 /* space 0: ux, 1: uy (T6), 2: p (T3).  params = [mu]        */
 
+/* vector (right-hand side) forms */
+#define EFG_VFORM_HEAT_LOAD         1 /* space 0: scalar.  fe[j] += N[j]*Q*JxW, params = [Q]            */
+
 /* options for efg_set_option */
 #define EFG_OPT_PATH        1 /* 0 = auto (tiled fused kernel; meshes beyond its limits, e.g. a node shared by
                                  > 90 elements, fall back to the two-pass CUDA path), 1 = two-pass (element
@@ -92,6 +103,8 @@ typedef struct efg_ctx efg_ctx;
 #define EFG_STAT_TILE_ELEMS       7 /* sum over tiles of elements processed (incl. halo) */
 #define EFG_STAT_NUMERIC_BYTES    8 /* bytes the numeric kernel is designed to move per call */
 #define EFG_STAT_PATH             9 /* path used by the last symbolic phase (1 or 2) */
+#define EFG_STAT_VEC_MS          10 /* device time of the last efg_vec_assemble numeric part (2 kernels) */
+#define EFG_STAT_SPMV_MS         11 /* device time of the last efg_spmv kernel */
 
 int efg_create(int device, efg_ctx **out);
 int efg_destroy(efg_ctx *ctx);
@@ -135,6 +148,29 @@ int efg_fetch_csc(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval)
 /* Device-resident result for a consumer that stays on the GPU (colptr: Int64 1-based,
  * rowval: Int32 0-based, nzval: Float64); valid until the next start/symbolic/destroy. */
 int efg_device_csc(efg_ctx *ctx, const int64_t **colptr, const int32_t **rowval, const double **nzval);
+
+/* System VECTOR assembly (SysvecAssembler).  One call = start!(av, nrow) + the element loop of the vector form over
+ * mesh 0 / space 0 (set by efg_set_mesh / efg_set_space) + assemble!(av, fe) per element.  Contributions reach
+ * val[gi] in the reference's order (ascending element, local index ascending) and every operation is individually
+ * rounded, so the result is bit-identical to the CPU loop.  A dof number < 1 or > nrow gives EFG_ERR_INDEX
+ * (Julia: BoundsError).  With a column range set on an nrow x nrow system only the owned rows are assembled
+ * (owner-computes, same ranges as the matrix columns).  The dof -> contribution map is cached like the matrix
+ * pattern. */
+int efg_vec_assemble(efg_ctx *ctx, int vform, int quad_rule, const double *params, int nparams, int64_t nrow);
+/* finish!(av): nrow doubles (owned rows when sharded), host or device destination. */
+int efg_fetch_vec(efg_ctx *ctx, double *out);
+int efg_device_vec(efg_ctx *ctx, const double **val, int64_t *n);
+
+/* y = K*x with the assembled matrix, in SparseArrays' accumulation order (y[r] sums its terms by ascending column,
+ * product and sum rounded separately): bit-identical to Julia's `K * x`.  x: ncol doubles, y: nrow doubles, host or
+ * device.  The row-major view of the pattern is built at the first call and cached until the pattern changes. */
+int efg_spmv(efg_ctx *ctx, const double *x, double *y);
+/* K[row_first:row_last, col_first:col_last] (1-based inclusive, Julia range semantics; an empty range is
+ * first = last+1) as a SparseMatrixCSC: two-call pattern like efg_fetch_csc.  efg_block_nnz fixes the block and
+ * returns its stored-entry count; efg_fetch_block fills colptr (ncols_block+1), rowval (rebased to the block) and
+ * nzval.  Any pointer may be NULL. */
+int efg_block_nnz(efg_ctx *ctx, int64_t row_first, int64_t row_last, int64_t col_first, int64_t col_last, int64_t *nnz_out);
+int efg_fetch_block(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval);
 
 /* library / build information, e.g. "elfelgpu 0.1 sm_100a" */
 const char *efg_version(void);

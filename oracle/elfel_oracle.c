@@ -521,3 +521,57 @@ int64_t efo_sparse(int64_t nrow, int64_t ncol, int64_t ntrip,
     free(rowptr); free(ccol); free(cval); free(last);
     return nnz;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * System VECTOR assembly: SysvecAssembler + LocalVectorAssembler.
+ *   start!(av, nrow)         src/Assemblers.jl:196-200   val = zeros(nrow)
+ *   init!(fe, eldofs(el))    src/LocalAssemblers.jl:147-151   fe.V zeroed per element
+ *   fe[j] += N[j] * Q * JxW  examples/heat/poisson/t3.jl:57, q4.jl:47, test/test_heat.jl:53,167
+ *                            (Julia parses N[j]*Q*JxW as (N[j]*Q)*JxW; JxW = J * weight(qp))
+ *   assemble!(av, fe)        src/Assemblers.jl:217-223   val[gi] += V[i], i ascending, element by element
+ *   finish!(av)              src/Assemblers.jl:230-232   copy of val
+ * Returns 0, or -1 for an unavailable rule, -2 for a dof number outside 1..nrow (Julia: BoundsError).
+ * ------------------------------------------------------------------------------------------ */
+int64_t efo_assemble_vec_heat(int quad, int64_t e0, int64_t e1, const int64_t *conn, int kind, const double *xy,
+                              const int64_t *dofnums, double Q, int64_t nrow, double *val)
+{
+    qptab vq;
+    if (qptab_init(&vq, kind, quad) < 0) return -1;
+    const int nu = kind;
+    double J[2][2];
+    int64_t d[MAXBF]; double fe[MAXBF];
+    for (int64_t i = 0; i < nrow; i++) val[i] = 0.0;
+    for (int64_t e = e0; e < e1; e++) {
+        const int64_t *nodes = conn + e * nu;
+        eldofs(nodes, nu, dofnums, 1, d);
+        for (int j = 0; j < nu; j++) fe[j] = 0.0;
+        for (int q = 0; q < vq.npts; q++) {
+            double Jd = jacjac(xy, nodes, nu, vq.gp[q], J);
+            double JxW = Jd * vq.w[q];
+            for (int j = 0; j < nu; j++) fe[j] = fe[j] + (vq.N[q][j] * Q) * JxW;
+        }
+        for (int i = 0; i < nu; i++) {
+            if (d[i] < 1 || d[i] > nrow) return -2;
+            val[d[i] - 1] = val[d[i] - 1] + fe[i];
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * y = K * x for a SparseMatrixCSC (call site examples/heat/poisson/t3.jl:78
+ * `KT = K * T`).  SparseArrays' mul!(C, A, B, 1, 0): C zeroed, then for every column k in order,
+ * for every stored entry of the column: C[rowval] += nzval * x[k] -- a rounded product followed
+ * by a rounded sum, so y[r] accumulates its terms in ascending column order starting from 0.0.
+ * (restated from SparseArrays' published algorithm; the stdlib is not vendored: "parity unpinned"
+ * at ULP level, pinned end to end through the heat goldens.)
+ * ------------------------------------------------------------------------------------------ */
+void efo_spmv_csc(int64_t nrow, int64_t ncol, const int64_t *colptr, const int64_t *rowval, const double *nzval,
+                  const double *x, double *y)
+{
+    for (int64_t i = 0; i < nrow; i++) y[i] = 0.0;
+    for (int64_t k = 0; k < ncol; k++) {
+        const double xk = x[k];
+        for (int64_t p = colptr[k] - 1; p < colptr[k + 1] - 1; p++) y[rowval[p] - 1] = y[rowval[p] - 1] + nzval[p] * xk;
+    }
+}

@@ -46,6 +46,10 @@ def lib():
         L.efo_assemble_coo.restype = C.c_int64
         L.efo_sparse.argtypes = [C.c_int64, C.c_int64, C.c_int64, i64p, i64p, f64p, i64p, i64p, f64p]
         L.efo_sparse.restype = C.c_int64
+        L.efo_assemble_vec_heat.argtypes = [C.c_int, C.c_int64, C.c_int64, i64p, C.c_int, f64p, i64p, C.c_double, C.c_int64, f64p]
+        L.efo_assemble_vec_heat.restype = C.c_int64
+        L.efo_spmv_csc.argtypes = [C.c_int64, C.c_int64, i64p, i64p, f64p, f64p, f64p]
+        L.efo_spmv_csc.restype = None
         _lib = L
     return _lib
 
@@ -137,3 +141,26 @@ def assemble(form, quad, vmesh, pmesh, dofs, params, nrow, ncol, timing=None):
         timing["integrate_s"] = t1 - t0
         timing["finish_s"] = t2 - t1
     return out
+
+
+def assemble_vec_heat(quad, mesh, dofnums, Q, nrow, e0=0, e1=None):
+    """start!(av, nrow) / `fe[j] += N[j]*Q*JxW` element loop / finish!(av) -> the load vector (nrow,)."""
+    conn = _c(mesh.conn, np.int64); xy = _c(mesh.xy, np.float64); d = _c(dofnums, np.int64)
+    e1 = conn.shape[0] if e1 is None else e1
+    val = np.empty(nrow, dtype=np.float64)
+    rc = lib().efo_assemble_vec_heat(quad, e0, e1, _p(conn, C.c_int64), mesh.kind, _p(xy, C.c_double),
+                                     _p(d, C.c_int64), float(Q), nrow, _p(val, C.c_double))
+    if rc == -2:
+        raise IndexError("BoundsError: dof number outside 1..nrow")
+    if rc != 0:
+        raise ValueError("quadrature rule not available")
+    return val
+
+
+def spmv_csc(nrow, ncol, colptr, rowval, nzval, x):
+    """K * x with SparseArrays' column-sweep accumulation order."""
+    colptr = _c(colptr, np.int64); rowval = _c(rowval, np.int64); nzval = _c(nzval, np.float64); x = _c(x, np.float64)
+    y = np.empty(nrow, dtype=np.float64)
+    lib().efo_spmv_csc(nrow, ncol, _p(colptr, C.c_int64), _p(rowval, C.c_int64), _p(nzval, C.c_double),
+                       _p(x, C.c_double), _p(y, C.c_double))
+    return y

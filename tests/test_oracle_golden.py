@@ -161,6 +161,42 @@ def test_scatter_through_real_dof_maps(oracle):
     assert np.allclose(_csc(colptr, rowval, nzval, 12).toarray(), D, rtol=0, atol=1e-15)
 
 
+def test_sysvec_assembler_semantics(oracle):
+    # test/test_assemblers.jl:143-162 (mvass1): val[i] += v entry by entry, repeated dofs accumulate in call order.
+    # Driven through the vector path with single-node "elements": a 1-point T3 rule would not give arbitrary
+    # values, so the accumulation order is checked on the element loop itself: two T3 elements sharing nodes.
+    mesh = efg.T3block(1.0, 1.0, 1, 1)             # 2 triangles, 4 nodes
+    dof = np.array([[3], [1], [4], [2]], dtype=np.int64)
+    F = oracle.assemble_vec_heat(1, mesh, dof, 2.5, 4)
+    want = np.zeros(4)
+    for e in range(mesh.nel):                       # Python restatement of assemble!(av, fe)
+        x = mesh.xy[mesh.conn[e] - 1]
+        J = (x[1, 0] - x[0, 0]) * (x[2, 1] - x[0, 1]) - (x[2, 0] - x[0, 0]) * (x[1, 1] - x[0, 1])
+        for k in range(3):
+            gi = dof[mesh.conn[e, k] - 1, 0]
+            want[gi - 1] = want[gi - 1] + (0.0 + ((1 - 1 / 3 - 1 / 3 if k == 0 else 1 / 3) * 2.5) * (J * 0.5))
+    assert np.array_equal(F, want)
+    with pytest.raises(IndexError):                 # BoundsError: dof number beyond nrow
+        oracle.assemble_vec_heat(1, mesh, dof, 2.5, 3)
+
+
+def test_spmv_matches_scipy_and_julia_order(oracle):
+    # K*T of examples/heat/poisson/t3.jl:78 -- column sweep, y[r] accumulated by ascending column
+    rng = np.random.default_rng(7)
+    prob = efg.heat_problem(efg.T6, 9, perturb=True)
+    cp, rv, nz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    x = rng.standard_normal(prob.ndofs)
+    y = oracle.spmv_csc(prob.ndofs, prob.ndofs, cp, rv, nz, x)
+    K = _csc(cp, rv, nz, prob.ndofs)
+    assert np.allclose(y, K @ x, rtol=1e-13, atol=1e-13)
+    Kr = K.tocsr(); Kr.sort_indices()
+    r = 17
+    acc = 0.0
+    for c, a in zip(Kr.indices[Kr.indptr[r]:Kr.indptr[r + 1]], Kr.data[Kr.indptr[r]:Kr.indptr[r + 1]]):
+        acc = acc + a * x[c]
+    assert y[r] == acc
+
+
 def _solve(K, U, F, nu):
     # solve!: examples/heat/poisson/t3.jl:77-80
     KT = K @ U
@@ -182,14 +218,17 @@ def test_heat_t3_n4_golden_solution(oracle):
                                             [kappa], n, n)
     assert len(rowval) == 7 * N * N + 6 * N + 1          # nnz closed form
     K = _csc(colptr, rowval, nzval, n)
-    # fe[j] += N[j]*Q*JxW (t3.jl:57): 1-pt rule, N = 1/3, J = 2*area
-    F = np.zeros(n)
+    # F: SysvecAssembler + LocalVectorAssembler, fe[j] += N[j]*Q*JxW (test/test_heat.jl:40-57)
+    F = oracle.assemble_vec_heat(1, mesh, fesp.field.dofnums, Q, n)
+    # independent closed form: 1-pt rule, N = 1/3, J = 2*area
+    F2 = np.zeros(n)
     d = fesp.field.dofnums[:, 0]
     for e in range(mesh.nel):
         nodes = mesh.conn[e] - 1
         x = mesh.xy[nodes]
         J = (x[1, 0] - x[0, 0]) * (x[2, 1] - x[0, 1]) - (x[2, 0] - x[0, 0]) * (x[1, 1] - x[0, 1])
-        F[d[nodes] - 1] += (1 / 3) * Q * (J * 0.5)
+        F2[d[nodes] - 1] += (1 / 3) * Q * (J * 0.5)
+    assert np.allclose(F, F2, rtol=1e-14, atol=1e-16)
     T = _solve(K, efg.gathersysvec(fesp), F, efg.nunknowns(fesp))
     ref = [1.1875, 1.3749999999999998, 1.6874999999999998, 1.5624999999999998, 1.7499999999999998,
            2.0625, 2.1875, 2.375, 2.6875, 1.0, 1.0625, 1.25, 1.5625, 2.0, 1.125, 2.125, 1.5, 2.5,
@@ -211,11 +250,14 @@ def test_heat_q4_n100_unknowns_and_accuracy(oracle):
     colptr, rowval, nzval = oracle.assemble(oracle.FORM_HEAT, 2, mesh, None, [fesp.field.dofnums], [kappa], n, n)
     assert len(rowval) == (3 * N + 1) ** 2
     K = _csc(colptr, rowval, nzval, n)
-    # load vector: uniform squares, sum_q N_j * Q * JxW = Q * area / 4 per node
-    F = np.zeros(n)
+    # load vector through the restated SysvecAssembler path (test/test_heat.jl:154-171); on uniform squares
+    # sum_q N_j * Q * JxW = Q * area / 4 per node and element
+    F = oracle.assemble_vec_heat(2, mesh, fesp.field.dofnums, Q, n)
+    F2 = np.zeros(n)
     d = fesp.field.dofnums[:, 0]
     area = (1.0 / N) ** 2
-    np.add.at(F, d[mesh.conn - 1].ravel() - 1, Q * area / 4)
+    np.add.at(F2, d[mesh.conn - 1].ravel() - 1, Q * area / 4)
+    assert np.allclose(F, F2, rtol=1e-12, atol=1e-18)
     T = _solve(K, efg.gathersysvec(fesp), F, efg.nunknowns(fesp))
     efg.scattersysvec(fesp, T)
     err = np.abs(fesp.field.dofvals[:, 0] - tempf(mesh.xy[:, 0], mesh.xy[:, 1])).mean()
