@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--path", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-callers", action="store_true", help="skip the f1/f2 rows (load vector, K*x) timed after the hot path")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -337,6 +338,40 @@ def main():
                 "frac_of_nominal_8TBps": achieved / 8000.0,
                 "kernel": "k_tl_numeric" if path == 2 else "k_tp_elem_matrices+k_tp_gather"}
 
+    # ---- SURVEY 8f rows f1 / f2, timed beside the hot path (heat workloads, one GPU): the load vector of the same
+    # integrate! loop and K*T of the examples' solve!, device-resident, CUDA events inside the library ----------
+    callers = None
+    if world == 1 and prob.form.form_id == 1 and not args.no_callers and path == 2:
+        m0 = prob.meshes[0]
+        nd = int(prob.ndofs)
+        eng.vec_assemble(_lib.VFORM_HEAT_LOAD, prob.quad, [-6.0], nd)          # builds the dof -> contribution map
+        tv = []
+        for _ in range(5):
+            eng.vec_assemble(_lib.VFORM_HEAT_LOAD, prob.quad, [-6.0], nd)
+            tv.append(eng.stat(_lib.STAT_VEC_MS))
+        v_ms = float(np.median(tv))
+        v_alg = 4 * m0.kind * m0.nel_ + 16 * m0.nnodes_ + 4 * nd + 4 * m0.kind * m0.nel_ + 8 * nd
+        xd = torch.ones(nd, dtype=torch.float64, device="cuda")
+        yd = torch.empty(nd, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        eng.spmv(xd, yd)                                                       # builds the row-major view
+        ts = []
+        for _ in range(5):
+            eng.spmv(xd, yd)
+            ts.append(eng.stat(_lib.STAT_SPMV_MS))
+        s_ms = float(np.median(ts))
+        s_alg = 12 * nnz + 8 * nd + 8 * nd + 8 * (nd + 1)
+        callers = {
+            "load_vector": {"what": "efg_vec_assemble (SysvecAssembler: fe[j] += N[j]*Q*JxW), 2 kernels, dof map cached",
+                            "ms": v_ms, "elements_per_s": m0.nel_ / (v_ms / 1e3), "algorithmic_bytes": int(v_alg),
+                            "achieved_GBps": v_alg / (v_ms / 1e3) / 1e9, "frac": v_alg / (v_ms / 1e3) / 1e9 / peak},
+            "spmv": {"what": "efg_spmv (KT = K*T, SparseArrays summation order), row-major view cached",
+                     "ms": s_ms, "nnz_per_s": nnz / (s_ms / 1e3), "algorithmic_bytes": int(s_alg),
+                     "achieved_GBps": s_alg / (s_ms / 1e3) / 1e9, "frac": s_alg / (s_ms / 1e3) / 1e9 / peak,
+                     "y_checksum": float(yd.sum().item())},
+        }
+        del xd, yd
+
     out = {
         "metric": "elements assembled/s", "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -351,7 +386,7 @@ def main():
         "roofline": roofline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
         "phases": {"symbolic_ms": sym_ms, "numeric_ms": ms_step,
                    "value_with_symbolic": nel_global / ((ms_step + sym_ms) / 1e3)},
-        "device_bytes": eng.stat(_lib.STAT_DEVICE_BYTES), "nzval_checksum": checksum,
+        "device_bytes": eng.stat(_lib.STAT_DEVICE_BYTES), "nzval_checksum": checksum, "next_rows": callers,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         cn = min(args.cpu_n, n)

@@ -43,8 +43,11 @@ struct TileDescFull {
 static_assert(sizeof(TileDescFull) % 8 == 0, "TileDescFull is copied as 8-byte words");
 
 // metadata block of a tile, each part 16-byte aligned:
-//   [pk: u32 x nslot]      per owned nonzero: stage index of its 1st | 2nd << 16 contribution (0xFFFF = none);
-//                          0xFFFEFFFE marks a "heavy" nonzero (> TL_LIGHT contributions)
+//   [pk: u32 x nslot]      per owned nonzero: stage index of its 1st | 2nd << 16 contribution.  A missing 2nd
+//                          contribution, and both halves of a "heavy" nonzero (> TL_LIGHT contributions), name the
+//                          stage's NEUTRAL entry (index ND*nqs, holds -0.0: x + -0.0 == x bit for bit, for every x),
+//                          so the gather of the light nonzeros is branch-free; heavy nonzeros are overwritten
+//                          afterwards from their contribution lists
 //   [hidx: u16 x ncontrib] stage indices of the contributions of the heavy nonzeros, append order
 //   [runs: TileRun x nrun] [heavy: TileHeavy x nheavy]
 __host__ __device__ static inline int tl_align16(int b) { return (b + 15) & ~15; }
@@ -55,8 +58,8 @@ __host__ __device__ static inline int tl_geo_bytes(int gsz, int nelem) { return 
 __host__ __device__ static inline int tl_meta_goff_bytes(int nslot) { return tl_align16(4 * nslot); }          // pk
 __host__ __device__ static inline int tl_meta_gidx_bytes(int nc) { return tl_align16(2 * nc); }              // hidx
 struct TileHeavy { uint16_t s, o, c, pad; };   // tile slot, first entry in hidx, number of contributions
-#define TL_PK_NONE 0xFFFFu
-#define TL_PK_HEAVY 0xFFFEFFFEu
+// bytes of the stage: ND rows of nqs staged columns + the neutral entry
+__host__ __device__ static inline int tl_stage_bytes(int nd, int nqs) { return tl_align16((nd * nqs + 1) * 8); }
 
 struct TiledData {
     DevBuf<TileDescFull> tiles;
@@ -425,6 +428,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
         TileHeavy *__restrict__ heavy = reinterpret_cast<TileHeavy *>(mb + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib) +
                                                                      td.nrun * (int)sizeof(TileRun)) + (tcol_heavy[k] - td.heavy0);
         uint16_t cnt[TL_CAP], off[TL_CAP], first[TL_CAP], second[TL_CAP];
+        const uint16_t neutral = (uint16_t)(F::ND * (int)td.nqs);     // <= 65533 (checked by the host before this kernel)
         for (int t = 0; t < nr; t++) cnt[t] = 0;
         const uint32_t a0 = adjptr[cl], a1 = adjptr[cl + 1];
         // pass A: contributions per slot
@@ -443,7 +447,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
         uint32_t run = (uint32_t)(tcol_gidx[k] - td.gidx0);      // heavy contributions of the tile before this column
         int nh = 0;
         for (int t = 0; t < nr; t++) {
-            first[t] = second[t] = TL_PK_NONE;
+            first[t] = second[t] = neutral;
             off[t] = 0;
             if (cnt[t] > TL_LIGHT) {
                 if (run + cnt[t] > 65535u) *err = 3;
@@ -477,7 +481,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
             }
         }
         for (int t = 0; t < nr; t++)
-            pk[t] = cnt[t] > TL_LIGHT ? TL_PK_HEAVY : ((uint32_t)first[t] | ((uint32_t)second[t] << 16));
+            pk[t] = cnt[t] > TL_LIGHT ? ((uint32_t)neutral | ((uint32_t)neutral << 16)) : ((uint32_t)first[t] | ((uint32_t)second[t] << 16));
     }
 }
 
@@ -530,7 +534,7 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, const int64_t *__re
         d.pad2_[0] = d.pad2_[1] = 0;
         tiles[T] = d;
         meta_bytes[T] = d.meta_bytes;
-        atomicMax(&maxima[0], tl_align16(d.nqs * nd * 8) + max(tl_geo_bytes(gsz, d.nelem), d.meta_bytes));
+        atomicMax(&maxima[0], tl_stage_bytes(nd, d.nqs) + max(tl_geo_bytes(gsz, d.nelem), d.meta_bytes));
         atomicMax(&maxima[1], (int32_t)(((int64_t)q | 1) * nd > 0x7fffffff ? 0x7fffffff : ((int64_t)q | 1) * nd));
         atomicMax(&maxima[2], d.ncontrib); atomicMax(&maxima[3], d.nelem);
     }
@@ -645,7 +649,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     constexpr int DW = (int)(sizeof(TileDescFull) / 8);
     constexpr int GK = F::GK;
     constexpr int NW = BLOCK / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too
     if (tid < DW) reinterpret_cast<int64_t *>(&td)[tid] = reinterpret_cast<const int64_t *>(&tiles[blockIdx.x])[tid];
     // the tile that will occupy a CTA slot about one wave later (pf_dist = CTAs resident on the device): its
     // connectivity is pulled into L2 at the end of this CTA, so that tile's first dependent load is an L2 hit
@@ -663,7 +667,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     constexpr int GSZ = tl_gsz<F>();
     // SPLIT forms: the per-element geometry of phase 1 and the gather metadata of phase 2 share the same shared-memory
     // area, so the TMA copy is issued after phase 1; otherwise it is issued now and lands while phase 1 computes
-    unsigned char *smeta = smem_raw + tl_align16(F::ND * td.nqs * 8);
+    unsigned char *smeta = smem_raw + tl_stage_bytes(F::ND, td.nqs);
     if (!F::SPLIT && tid == 0) tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
     if (F::SPLIT) {   // the TMA copy is issued after phase 1 (shared area): pull the block into L2 meanwhile
         const char *mp = reinterpret_cast<const char *>(meta + td.meta0);
@@ -671,6 +675,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     }
     const int nq = td.nqs;      // stage row stride (odd)
     const int ncols = td.nq;    // staged columns
+    if (tid == 32) stage[F::ND * nq] = -0.0;    // the neutral entry (read by phase 2, after the barrier below)
 
     if constexpr (!F::SPLIT) {
         // phase 1: one thread per tile element: owned columns of the element matrix -> stage
@@ -689,7 +694,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     } else {
         // phase 1a: one thread per tile element: Jacobian / JxW / gradients at every quadrature point -> shared memory
         const int ne = td.nelem;
-        double *Gs = reinterpret_cast<double *>(smem_raw + tl_align16(F::ND * nq * 8));   // SoA: Gs[k * ne + le]
+        double *Gs = reinterpret_cast<double *>(smem_raw + tl_stage_bytes(F::ND, nq));   // SoA: Gs[k * ne + le]
         uint16_t *smask = reinterpret_cast<uint16_t *>(Gs + GSZ * ne);
         for (int le = tid; le < ne; le += BLOCK)
             tl_geometry_to_smem<F, S>(td.elem0 + le, le, ne, tconn, tmask, xy, Gs, smask);
@@ -727,32 +732,55 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
         while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= w0) lo = mid; else hi = mid - 1; }
         r = lo;
     }
-    int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
-    int64_t rnz = srun[r].nz0;
-    // light nonzeros (1 or 2 contributions: all but the matrix diagonals of node patches): one packed word per
-    // nonzero names both stage entries; four nonzeros in flight per lane
+    // Light nonzeros (1 or 2 contributions: all but the matrix diagonals of node patches): one packed word per
+    // nonzero names both stage entries (a missing one names the neutral entry), four nonzeros in flight per lane, no
+    // branches.  Destination: the warp tracks, uniformly, the run A that holds the first nonzero of its batch of 128
+    // and the run B after it; a batch inside A+B (nearly all) picks one of the two bases per lane.  Only batches that
+    // span three or more runs walk the run table lane by lane.
+    const int nrun = td.nrun;
+    int endA = srun[r].s0 + srun[r].len;
+    double *dstA = nzval + (srun[r].nz0 - srun[r].s0);          // dstA + s is the nzval entry of tile slot s in run A
+    int endB = endA;
+    double *dstB = dstA;
+    if (r + 1 < nrun) { endB = srun[r + 1].s0 + srun[r + 1].len; dstB = nzval + (srun[r + 1].nz0 - srun[r + 1].s0); }
     constexpr int U = 4;
     for (int sb = w0; sb < w1; sb += 32 * U) {
+        const int bend = min(sb + 32 * U, w1);
         uint32_t pk[U];
+        if (sb + 32 * U <= w1) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int s = sb + u * 32 + lane;
-            pk[u] = (s < w1) ? spk[s] : 0xFFFFFFFFu;
+            for (int u = 0; u < U; u++) pk[u] = spk[sb + u * 32 + lane];
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int s = sb + u * 32 + lane;
+                pk[u] = (s < w1) ? spk[s] : 0u;
+            }
         }
         double acc[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const uint32_t i0 = pk[u] & 0xFFFFu, i1 = pk[u] >> 16;
-            acc[u] = 0.0;
-            if (i0 < 0xFFFEu) acc[u] = stage[i0];
-            if (i1 < 0xFFFEu) acc[u] = __dadd_rn(acc[u], stage[i1]);
+        for (int u = 0; u < U; u++) acc[u] = __dadd_rn(stage[pk[u] & 0xFFFFu], stage[pk[u] >> 16]);
+        while (sb >= endA) {     // warp-uniform: the run that holds slot sb becomes A
+            r++;
+            endA = endB; dstA = dstB;
+            if (r + 1 < nrun) { endB = srun[r + 1].s0 + srun[r + 1].len; dstB = nzval + (srun[r + 1].nz0 - srun[r + 1].s0); }
         }
+        if (bend <= endB) {
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int s = sb + u * 32 + lane;
-            if (s < w1) {
-                while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
-                if (pk[u] != TL_PK_HEAVY) nzval[rnz + (s - rs0)] = acc[u];
+            for (int u = 0; u < U; u++) {
+                const int s = sb + u * 32 + lane;
+                double *d = (s < endA) ? dstA : dstB;
+                if (s < bend) d[s] = acc[u];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int s = sb + u * 32 + lane;
+                if (s < bend) {
+                    int rr = r;
+                    while (s >= srun[rr].s0 + srun[rr].len) rr++;
+                    nzval[srun[rr].nz0 + (s - srun[rr].s0)] = acc[u];
+                }
             }
         }
     }
@@ -763,7 +791,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
         const char *p1 = reinterpret_cast<const char *>(tmask + pf_elem0);
         for (int o = tid * 128; o < pf_nelem * 2; o += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + o));
     }
-    // heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum
+    // heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum; they
+    // overwrite the placeholder the light pass stored (same CTA, ordered by the barrier)
+    if (td.nheavy > 0) __syncthreads();
     for (int h = tid; h < td.nheavy; h += BLOCK) {
         const TileHeavy e = heavy[h];
         double acc = stage[hidx[e.o]];
