@@ -51,7 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return SO_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, os.path.join(CSRC, "elfel_gpu.cu")]
+    extra = os.environ.get("EFG_NVCC_EXTRA", "").split()      # e.g. -DTL_NEUTRAL=1 while A/B-ing kernel variants
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH, os.path.join(CSRC, "elfel_gpu.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

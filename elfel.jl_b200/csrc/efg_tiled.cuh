@@ -39,15 +39,15 @@ struct TileDescFull {
     uint16_t qbase[TL_MAXND + 1]; // qbase[r] = first staged column of "r-th owned column of an element"
     uint16_t nqs;           // stage row stride: nq rounded up to an odd number (rows i of one staged column fall in distinct banks)
     uint16_t pad2_[2];
+    int64_t geo0;           // byte offset of the tile's geometry block (TL_GEO)
+    int32_t geo_bytes;      // its size (multiple of 16); 0 = the form reads tconn/xy from global memory
+    int32_t nnode;          // unique nodes of the tile's elements
 };
 static_assert(sizeof(TileDescFull) % 8 == 0, "TileDescFull is copied as 8-byte words");
 
 // metadata block of a tile, each part 16-byte aligned:
-//   [pk: u32 x nslot]      per owned nonzero: stage index of its 1st | 2nd << 16 contribution.  A missing 2nd
-//                          contribution, and both halves of a "heavy" nonzero (> TL_LIGHT contributions), name the
-//                          stage's NEUTRAL entry (index ND*nqs, holds -0.0: x + -0.0 == x bit for bit, for every x),
-//                          so the gather of the light nonzeros is branch-free; heavy nonzeros are overwritten
-//                          afterwards from their contribution lists
+//   [pk: u32 x nslot]      per owned nonzero: stage index of its 1st | 2nd << 16 contribution (0xFFFF = none);
+//                          0xFFFEFFFE marks a "heavy" nonzero (> TL_LIGHT contributions)
 //   [hidx: u16 x ncontrib] stage indices of the contributions of the heavy nonzeros, append order
 //   [runs: TileRun x nrun] [heavy: TileHeavy x nheavy]
 __host__ __device__ static inline int tl_align16(int b) { return (b + 15) & ~15; }
@@ -57,17 +57,59 @@ template <class F> __host__ __device__ constexpr int tl_gsz() { return F::SPLIT 
 __host__ __device__ static inline int tl_geo_bytes(int gsz, int nelem) { return gsz ? tl_align16(nelem * (gsz * 8 + 2)) : 0; }
 __host__ __device__ static inline int tl_meta_goff_bytes(int nslot) { return tl_align16(4 * nslot); }          // pk
 __host__ __device__ static inline int tl_meta_gidx_bytes(int nc) { return tl_align16(2 * nc); }              // hidx
-struct TileHeavy { uint16_t s, o, c, pad; };   // tile slot, first entry in hidx, number of contributions
-// bytes of the stage: ND rows of nqs staged columns + the neutral entry
-__host__ __device__ static inline int tl_stage_bytes(int nd, int nqs) { return tl_align16((nd * nqs + 1) * 8); }
+struct TileHeavy { uint16_t s, o, c, pad; };
+// geometry block of a tile, each part 16-byte aligned: [txy: double2 x nnode] [conn16: u16 x GK x nelem] [mask16: u16 x nelem]
+__host__ __device__ static inline int tl_geo_xy_bytes(int nnode) { return 16 * nnode; }
+__host__ __device__ static inline int tl_geo_conn_bytes(int gk, int nelem) { return tl_align16(2 * gk * nelem); }
+__host__ __device__ static inline int tl_geo_block_bytes(int gk, int nelem, int nnode)
+{
+    return tl_geo_xy_bytes(nnode) + tl_geo_conn_bytes(gk, nelem) + tl_align16(2 * nelem);
+}
+#define TL_GEO_CAP 4096   // nelem*GK entries a tile's local numbering is built from (256 threads x 16)   // tile slot, first entry in hidx, number of contributions
+// Gather variants that were A/B-measured SLOWER on B200 and removed (profiles/README.md): a branch-free light gather
+// through a neutral -0.0 stage entry (34 % fewer instructions in the loop, one more LDS per single-contribution
+// nonzero: +10 %), warp-uniform two-run destination tracking (+2 %), 8 nonzeros in flight per lane (+13 %).  The
+// kernel is bound by the LSU data pipe and by latency, not by instruction issue.
+#ifndef TL_U
+#define TL_U 4          // light nonzeros in flight per lane
+#endif
+#ifndef TL_MINB
+#define TL_MINB 2       // CTAs per SM the one-thread-per-element kernels are compiled for
+#endif
+#ifndef TL_GEO
+#define TL_GEO 1        // one-thread-per-element forms: the tile's unique node coordinates + 16-bit local connectivity +
+                        // column masks form a "geometry block" fetched by ONE TMA bulk copy at tile start (no dependent
+                        // global loads in phase 1); 0: per-element global loads of tconn -> xy
+#endif
+// Persistent CTAs (one per CTA slot) that fetch the NEXT tile's geometry block while the current tile is in its gather
+// phase, and its gather metadata while the next tile computes.  Measured (profiles/README.md): no gain for the
+// one-thread-per-element forms with large tiles (T6 heat 3.96 vs 3.86 ms, Q4 2.11 vs 2.06 ms; T3 0.78 vs 0.80 ms).
+#ifndef TL_PERSIST_NS
+#define TL_PERSIST_NS 0
+#endif
+#ifndef TL_PERSIST_SPLIT
+#define TL_PERSIST_SPLIT 0
+#endif
+template <class F> constexpr bool tl_persist() { return TL_GEO && (F::SPLIT ? TL_PERSIST_SPLIT : TL_PERSIST_NS); }
+#ifndef TL_VEC_CONN
+#define TL_VEC_CONN 1   // tile connectivity read with 8/16-byte loads (T6: 3 x int2, Q4: 1 x int4) instead of 4-byte loads
+#endif
+#define TL_PK_NONE 0xFFFFu
+#define TL_PK_HEAVY 0xFFFEFFFEu
+// bytes of the stage: ND rows of nqs staged columns
+__host__ __device__ static inline int tl_stage_bytes(int nd, int nqs) { return tl_align16(nd * nqs * 8); }
 
 struct TiledData {
     DevBuf<TileDescFull> tiles;
     DevBuf<int32_t> tconn;
     DevBuf<uint16_t> tmask;
     DevBuf<unsigned char> meta;  // per-tile metadata blocks (bulk-copied to shared memory by the numeric kernel)
+    DevBuf<unsigned char> geo;   // per-tile geometry blocks (TL_GEO)
+    int64_t geo_total = 0;
     int64_t ntelem = 0, ncontrib = 0, nruns = 0, meta_bytes = 0;
     int smem_bytes = 0, stage_bytes = 0, meta_max = 0;
+    int off_meta = 0, off_geo = 0, off_gs = 0;   // persistent kernel: fixed shared-memory offsets (maxima over tiles)
+    bool persist = false;
     int block = 256;
 };
 
@@ -404,6 +446,78 @@ __global__ void k_tl_tconn(const uint32_t *__restrict__ order, int64_t n, const 
     }
 }
 
+// TL_GEO: tile-local node numbering.  One CTA per tile: block-wide radix sort of the tile's (node id, position) pairs,
+// head flags -> local ids.  tlocal[elem0*GK + pos] = local id of that connectivity entry, tnodes[elem0*GK + k] = k-th
+// unique node, tnn[T] = number of unique nodes.
+template <int GK>
+__global__ void __launch_bounds__(256) k_tl_geo_local(const int64_t *__restrict__ telem_ptr, const int32_t *__restrict__ tconn,
+                                                      uint16_t *__restrict__ tlocal, int32_t *__restrict__ tnodes, int32_t *__restrict__ tnn,
+                                                      int *__restrict__ err)
+{
+    constexpr int IPT = TL_GEO_CAP / 256;
+    using Sort = cub::BlockRadixSort<uint32_t, 256, IPT, uint16_t>;
+    using Scan = cub::BlockScan<int, 256>;
+    __shared__ union { typename Sort::TempStorage sort; typename Scan::TempStorage scan; } tmp;
+    __shared__ uint32_t last_key[256];
+    const int T = blockIdx.x, tid = threadIdx.x;
+    const int64_t e0 = telem_ptr[T];
+    const int n = (int)(telem_ptr[T + 1] - e0) * GK;
+    if (n > TL_GEO_CAP) { if (tid == 0) { *err = 5; tnn[T] = 0; } return; }
+    uint32_t key[IPT];
+    uint16_t pos[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        const int i = tid * IPT + k;
+        key[k] = i < n ? (uint32_t)tconn[e0 * GK + i] : 0xFFFFFFFFu;
+        pos[k] = (uint16_t)i;
+    }
+    Sort(tmp.sort).Sort(key, pos);
+    __syncthreads();
+    last_key[tid] = key[IPT - 1];
+    __syncthreads();
+    uint32_t prev = tid > 0 ? last_key[tid - 1] : 0xFFFFFFFFu;   // 0xFFFFFFFF is never a node id: the first key is a head
+    int heads = 0;
+    bool head[IPT];
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        head[k] = key[k] != 0xFFFFFFFFu && (key[k] != prev || (tid == 0 && k == 0));
+        heads += head[k] ? 1 : 0;
+        prev = key[k];
+    }
+    int before = 0, total = 0;
+    Scan(tmp.scan).ExclusiveSum(heads, before, total);
+    int id = before - 1;
+#pragma unroll
+    for (int k = 0; k < IPT; k++) {
+        if (key[k] == 0xFFFFFFFFu) continue;
+        if (head[k]) { id++; tnodes[e0 * GK + id] = (int32_t)key[k]; }
+        tlocal[e0 * GK + pos[k]] = (uint16_t)id;
+    }
+    if (tid == 0) tnn[T] = total;
+}
+// fills the geometry block of every tile: coordinates of its unique nodes, 16-bit local connectivity, column masks
+template <int GK>
+__global__ void k_tl_geo_fill(int ntiles, const TileDescFull *__restrict__ tiles, const uint16_t *__restrict__ tlocal,
+                              const int32_t *__restrict__ tnodes, const uint16_t *__restrict__ tmask, const double2 *__restrict__ xy,
+                              unsigned char *__restrict__ geo)
+{
+    for (int T = blockIdx.x; T < ntiles; T += gridDim.x) {
+        const TileDescFull &td = tiles[T];
+        if (td.geo_bytes == 0) continue;
+        unsigned char *gb = geo + td.geo0;
+        double2 *txy = reinterpret_cast<double2 *>(gb);
+        uint16_t *c16 = reinterpret_cast<uint16_t *>(gb + tl_geo_xy_bytes(td.nnode));
+        uint16_t *m16 = reinterpret_cast<uint16_t *>(gb + tl_geo_xy_bytes(td.nnode) + tl_geo_conn_bytes(GK, td.nelem));
+        for (int k = threadIdx.x; k < td.nnode; k += blockDim.x) txy[k] = xy[tnodes[td.elem0 * GK + k]];
+        for (int k = threadIdx.x; k < td.nelem * GK; k += blockDim.x) c16[k] = tlocal[td.elem0 * GK + k];
+        for (int k = threadIdx.x; k < td.nelem; k += blockDim.x) m16[k] = tmask[td.elem0 + k];
+    }
+}
+__global__ void k_tl_tiles_geo0(int ntiles, const int64_t *__restrict__ geo_off, TileDescFull *__restrict__ tiles)
+{
+    GRID_STRIDE(T, ntiles) tiles[T].geo0 = geo_off[T];
+}
+
 // per owned tile column: start offset of every slot's contributions (goff) + the stage index of
 // every contribution in append order (gidx), written into the owning tile's metadata block
 template <class F>
@@ -428,7 +542,6 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
         TileHeavy *__restrict__ heavy = reinterpret_cast<TileHeavy *>(mb + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib) +
                                                                      td.nrun * (int)sizeof(TileRun)) + (tcol_heavy[k] - td.heavy0);
         uint16_t cnt[TL_CAP], off[TL_CAP], first[TL_CAP], second[TL_CAP];
-        const uint16_t neutral = (uint16_t)(F::ND * (int)td.nqs);     // <= 65533 (checked by the host before this kernel)
         for (int t = 0; t < nr; t++) cnt[t] = 0;
         const uint32_t a0 = adjptr[cl], a1 = adjptr[cl + 1];
         // pass A: contributions per slot
@@ -447,7 +560,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
         uint32_t run = (uint32_t)(tcol_gidx[k] - td.gidx0);      // heavy contributions of the tile before this column
         int nh = 0;
         for (int t = 0; t < nr; t++) {
-            first[t] = second[t] = neutral;
+            first[t] = second[t] = TL_PK_NONE;
             off[t] = 0;
             if (cnt[t] > TL_LIGHT) {
                 if (run + cnt[t] > 65535u) *err = 3;
@@ -481,7 +594,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
             }
         }
         for (int t = 0; t < nr; t++)
-            pk[t] = cnt[t] > TL_LIGHT ? ((uint32_t)neutral | ((uint32_t)neutral << 16)) : ((uint32_t)first[t] | ((uint32_t)second[t] << 16));
+            pk[t] = cnt[t] > TL_LIGHT ? TL_PK_HEAVY : ((uint32_t)first[t] | ((uint32_t)second[t] << 16));
     }
 }
 
@@ -500,7 +613,8 @@ __global__ void k_tl_tiles_meta0(int ntiles, const int64_t *__restrict__ meta_of
     GRID_STRIDE(T, ntiles) tiles[T].meta0 = meta_off[T];
 }
 
-__global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ tcol_slot,
+__global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, int gk, const int32_t *__restrict__ tnn /* null: no geometry blocks */,
+                                int64_t *__restrict__ geo_bytes, const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ tcol_slot,
                                 const int64_t *__restrict__ tcol_gidx, const int64_t *__restrict__ tcol_heavy, const int64_t *__restrict__ telem_ptr,
                                 const int64_t *__restrict__ run_of_k /* exclusive scan of run-head flags */,
                                 int64_t nowned, int64_t nruns, const uint32_t *__restrict__ pc_hist, TileDescFull *__restrict__ tiles,
@@ -532,11 +646,17 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, const int64_t *__re
         d.meta_bytes = d.nslot > 0 ? tl_meta_goff_bytes(d.nslot) + tl_meta_gidx_bytes(d.ncontrib) + d.nrun * (int)sizeof(TileRun) + tl_align16((int)sizeof(TileHeavy) * d.nheavy) : 0;
         d.meta0 = 0;
         d.pad2_[0] = d.pad2_[1] = 0;
+        d.geo0 = 0;
+        d.nnode = tnn ? tnn[T] : 0;
+        d.geo_bytes = (tnn && d.nslot > 0) ? tl_geo_block_bytes(gk, d.nelem, d.nnode) : 0;
         tiles[T] = d;
         meta_bytes[T] = d.meta_bytes;
-        atomicMax(&maxima[0], tl_stage_bytes(nd, d.nqs) + max(tl_geo_bytes(gsz, d.nelem), d.meta_bytes));
+        geo_bytes[T] = d.geo_bytes;
+        atomicMax(&maxima[0], tl_stage_bytes(nd, d.nqs) + max(tl_geo_bytes(gsz, d.nelem), d.meta_bytes) + d.geo_bytes);
         atomicMax(&maxima[1], (int32_t)(((int64_t)q | 1) * nd > 0x7fffffff ? 0x7fffffff : ((int64_t)q | 1) * nd));
         atomicMax(&maxima[2], d.ncontrib); atomicMax(&maxima[3], d.nelem);
+        atomicMax(&maxima[4], tl_stage_bytes(nd, d.nqs)); atomicMax(&maxima[5], d.meta_bytes); atomicMax(&maxima[6], d.geo_bytes);
+        atomicMax(&maxima[7], tl_geo_bytes(gsz, d.nelem));
     }
 }
 
@@ -584,9 +704,49 @@ __device__ __noinline__ void tl_element_to_stage(int64_t g, uint32_t le, const i
 {
     constexpr int GK = F::GK;
     double X[GK], Y[GK];
+    int32_t nd[GK];
+#if TL_VEC_CONN
+    if constexpr (GK == 6) {          // 24 bytes per element: three aligned 8-byte loads
+        const int2 *c2 = reinterpret_cast<const int2 *>(tconn + g * 6);
+        const int2 a = __ldg(c2), b = __ldg(c2 + 1), c = __ldg(c2 + 2);
+        nd[0] = a.x; nd[1] = a.y; nd[2] = b.x; nd[3] = b.y; nd[4] = c.x; nd[5] = c.y;
+    } else if constexpr (GK == 4) {   // 16 bytes per element: one aligned 16-byte load
+        const int4 a = __ldg(reinterpret_cast<const int4 *>(tconn + g * 4));
+        nd[0] = a.x; nd[1] = a.y; nd[2] = a.z; nd[3] = a.w;
+    } else
+#endif
+    {
 #pragma unroll
-    for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[tconn[g * GK + a]]); X[a] = p.x; Y[a] = p.y; }
+        for (int a = 0; a < GK; a++) nd[a] = tconn[g * GK + a];
+    }
+#pragma unroll
+    for (int a = 0; a < GK; a++) { const double2 p = __ldg(&xy[nd[a]]); X[a] = p.x; Y[a] = p.y; }
     StageEmit<F> emit{stage, qbase, (uint32_t)tmask[g], le, nq};
+    F::template element<S>(X, Y, emit.m, emit);
+}
+
+// Same worker fed from the tile's geometry block in shared memory (TL_GEO)
+template <class F, bool S>
+__device__ __noinline__ void tl_element_to_stage_local(uint32_t le, const uint16_t *__restrict__ c16, const uint16_t *__restrict__ m16,
+                                                       const double2 *__restrict__ sxy, double *__restrict__ stage, const uint16_t *__restrict__ qbase, int nq)
+{
+    constexpr int GK = F::GK;
+    uint32_t nd[GK];
+    if constexpr (GK == 6) {          // 12 bytes per element: three aligned 4-byte loads
+        const uint32_t *c = reinterpret_cast<const uint32_t *>(c16 + le * 6);
+        const uint32_t a = c[0], b = c[1], d = c[2];
+        nd[0] = a & 0xFFFFu; nd[1] = a >> 16; nd[2] = b & 0xFFFFu; nd[3] = b >> 16; nd[4] = d & 0xFFFFu; nd[5] = d >> 16;
+    } else if constexpr (GK == 4) {   // 8 bytes per element: one aligned 8-byte load
+        const uint2 a = *reinterpret_cast<const uint2 *>(c16 + le * 4);
+        nd[0] = a.x & 0xFFFFu; nd[1] = a.x >> 16; nd[2] = a.y & 0xFFFFu; nd[3] = a.y >> 16;
+    } else {
+#pragma unroll
+        for (int a = 0; a < GK; a++) nd[a] = c16[le * GK + a];
+    }
+    double X[GK], Y[GK];
+#pragma unroll
+    for (int a = 0; a < GK; a++) { const double2 p = sxy[nd[a]]; X[a] = p.x; Y[a] = p.y; }
+    StageEmit<F> emit{stage, qbase, (uint32_t)m16[le], le, nq};
     F::template element<S>(X, Y, emit.m, emit);
 }
 
@@ -611,6 +771,27 @@ __device__ __forceinline__ void tl_geometry_to_smem(int64_t g, int le, int ne, c
         Gs[(2 * NQ * BK + q) * ne + le] = G.JxW[q];
     }
     smask[le] = tmask[g];
+}
+// same, fed from the tile's geometry block in shared memory (persistent kernel)
+template <class F, bool S>
+__device__ __forceinline__ void tl_geometry_to_smem_local(int le, int ne, const uint16_t *__restrict__ c16, const double2 *__restrict__ sxy,
+                                                          double *__restrict__ Gs)
+{
+    constexpr int GK = F::GK, NQ = F::NQ, BK = F::BK;
+    double X[GK], Y[GK];
+#pragma unroll
+    for (int a = 0; a < GK; a++) { const double2 p = sxy[c16[le * GK + a]]; X[a] = p.x; Y[a] = p.y; }
+    Geo<BK, NQ> G;
+    geo_compute<S, GK, BK, NQ>(X, Y, G);
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+#pragma unroll
+        for (int n = 0; n < BK; n++) {
+            Gs[(q * BK + n) * ne + le] = G.gx[q][n];
+            Gs[(NQ * BK + q * BK + n) * ne + le] = G.gy[q][n];
+        }
+        Gs[(2 * NQ * BK + q) * ne + le] = G.JxW[q];
+    }
 }
 template <class F, bool S>
 __device__ __forceinline__ void tl_column_to_stage(int qc, int le, int J, int ne, int nq, const double *__restrict__ Gs, double *__restrict__ stage)
@@ -637,28 +818,93 @@ __device__ __forceinline__ void tl_column_to_stage(int qc, int le, int J, int ne
         if (F::mask(i, J)) stage[i * nq + qc] = out[i];
 }
 
+// ---- phase 2 of the numeric kernels ---------------------------------------------------------------------
+// Light nonzeros (1 or 2 contributions: all but the matrix diagonals of node patches): one packed word per nonzero
+// names both stage entries; TL_U nonzeros in flight per lane; every lane tracks its run in registers.
+template <int BLOCK>
+__device__ __forceinline__ void tl_gather_light(const TileDescFull &td, const double *__restrict__ stage, const unsigned char *__restrict__ smeta,
+                                                double *__restrict__ nzval, int lane, int warp)
+{
+    constexpr int NW = BLOCK / 32;
+    const uint32_t *spk = reinterpret_cast<const uint32_t *>(smeta);
+    const TileRun *srun = reinterpret_cast<const TileRun *>(smeta + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
+    const int nslot = td.nslot;
+    const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // contiguous slots per warp
+    const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
+    int r = 0;
+    {
+        int lo = 0, hi = td.nrun - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= w0) lo = mid; else hi = mid - 1; }
+        r = lo;
+    }
+    int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
+    int64_t rnz = srun[r].nz0;
+    constexpr int U = TL_U;
+    for (int sb = w0; sb < w1; sb += 32 * U) {
+        uint32_t pk[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int s = sb + u * 32 + lane;
+            pk[u] = (s < w1) ? spk[s] : 0xFFFFFFFFu;
+        }
+        double acc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint32_t i0 = pk[u] & 0xFFFFu, i1 = pk[u] >> 16;
+            acc[u] = 0.0;
+            if (i0 < 0xFFFEu) acc[u] = stage[i0];
+            if (i1 < 0xFFFEu) acc[u] = __dadd_rn(acc[u], stage[i1]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int s = sb + u * 32 + lane;
+            if (s < w1) {
+                while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
+                if (pk[u] != TL_PK_HEAVY) nzval[rnz + (s - rs0)] = acc[u];
+            }
+        }
+    }
+}
+// Heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum.
+template <int BLOCK>
+__device__ __forceinline__ void tl_gather_heavy(const TileDescFull &td, const double *__restrict__ stage, const unsigned char *__restrict__ smeta,
+                                                double *__restrict__ nzval, int tid)
+{
+    const uint16_t *hidx = reinterpret_cast<const uint16_t *>(smeta + tl_meta_goff_bytes(td.nslot));
+    const TileRun *srun = reinterpret_cast<const TileRun *>(reinterpret_cast<const unsigned char *>(hidx) + tl_meta_gidx_bytes(td.ncontrib));
+    const TileHeavy *heavy = reinterpret_cast<const TileHeavy *>(reinterpret_cast<const unsigned char *>(srun) + td.nrun * (int)sizeof(TileRun));
+    for (int h = tid; h < td.nheavy; h += BLOCK) {
+        const TileHeavy e = heavy[h];
+        double acc = stage[hidx[e.o]];
+        for (int k = 1; k < (int)e.c; k++) acc = __dadd_rn(acc, stage[hidx[e.o + k]]);
+        const int s = e.s;
+        int lo = 0, hi = td.nrun - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
+        nzval[srun[lo].nz0 + (s - srun[lo].s0)] = acc;
+    }
+}
+
 template <class F, bool S, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *__restrict__ tiles, int ntiles,
                                                             const int32_t *__restrict__ tconn, const uint16_t *__restrict__ tmask,
                                                             const double2 *__restrict__ xy, const unsigned char *__restrict__ meta,
-                                                            double *__restrict__ nzval, int pf_dist, int unused_)
+                                                            double *__restrict__ nzval, int pf_dist, const unsigned char *__restrict__ geo)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDescFull td;
-    __shared__ __align__(8) unsigned long long bar;
+    __shared__ __align__(8) unsigned long long bar, bar2;
+    constexpr bool GEO = TL_GEO && !F::SPLIT;
     constexpr int DW = (int)(sizeof(TileDescFull) / 8);
     constexpr int GK = F::GK;
     constexpr int NW = BLOCK / 32;
-    const int tid = threadIdx.x, lane = tid & 31, warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler too
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < DW) reinterpret_cast<int64_t *>(&td)[tid] = reinterpret_cast<const int64_t *>(&tiles[blockIdx.x])[tid];
     // the tile that will occupy a CTA slot about one wave later (pf_dist = CTAs resident on the device): its
     // connectivity is pulled into L2 at the end of this CTA, so that tile's first dependent load is an L2 hit
-    const int tpf = blockIdx.x + pf_dist;
-    int64_t pf_elem0 = 0; int pf_nelem = 0;
-    if (tpf < ntiles) { pf_elem0 = tiles[tpf].elem0; pf_nelem = tiles[tpf].nelem; }
-    const uint32_t barA = tl_smem_addr(&bar);
+    const uint32_t barA = tl_smem_addr(&bar), barB = tl_smem_addr(&bar2);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barA));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(barB));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -668,6 +914,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     // SPLIT forms: the per-element geometry of phase 1 and the gather metadata of phase 2 share the same shared-memory
     // area, so the TMA copy is issued after phase 1; otherwise it is issued now and lands while phase 1 computes
     unsigned char *smeta = smem_raw + tl_stage_bytes(F::ND, td.nqs);
+    unsigned char *sgeo = smeta + td.meta_bytes;     // geometry block (GEO): txy | conn16 | mask16
+    if (GEO && tid == 0) tl_bulk_load(tl_smem_addr(sgeo), geo + td.geo0, (uint32_t)td.geo_bytes, barB);   // needed first
     if (!F::SPLIT && tid == 0) tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
     if (F::SPLIT) {   // the TMA copy is issued after phase 1 (shared area): pull the block into L2 meanwhile
         const char *mp = reinterpret_cast<const char *>(meta + td.meta0);
@@ -675,9 +923,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     }
     const int nq = td.nqs;      // stage row stride (odd)
     const int ncols = td.nq;    // staged columns
-    if (tid == 32) stage[F::ND * nq] = -0.0;    // the neutral entry (read by phase 2, after the barrier below)
 
-    if constexpr (!F::SPLIT) {
+    if constexpr (GEO) {
+        // phase 1 from the tile's geometry block: no global loads at all -- local connectivity and coordinates come
+        // from shared memory as soon as the bulk copy has landed
+        tl_mbar_wait(barB, 0);
+        const double2 *sxy = reinterpret_cast<const double2 *>(sgeo);
+        const uint16_t *sc16 = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode));
+        const uint16_t *sm16 = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode) + tl_geo_conn_bytes(GK, td.nelem));
+        for (int le = tid; le < td.nelem; le += BLOCK) tl_element_to_stage_local<F, S>((uint32_t)le, sc16, sm16, sxy, stage, td.qbase, nq);
+    } else if constexpr (!F::SPLIT) {
         // phase 1: one thread per tile element: owned columns of the element matrix -> stage
         for (int le = tid; le < td.nelem; le += BLOCK) {
             if constexpr (F::GK >= 4) {    // out of line: measured 4.47 -> 3.96 ms on config 2 (no spills in the hot code)
@@ -718,91 +973,114 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     tl_mbar_wait(barA, 0);
 
     // phase 2: every owned nonzero = left-to-right sum of its contributions (append order), stored once
-    {
-    const uint32_t *spk = reinterpret_cast<const uint32_t *>(smeta);
-    const uint16_t *hidx = reinterpret_cast<const uint16_t *>(smeta + tl_meta_goff_bytes(td.nslot));
-    const TileRun *srun = reinterpret_cast<const TileRun *>(reinterpret_cast<const unsigned char *>(hidx) + tl_meta_gidx_bytes(td.ncontrib));
-    const TileHeavy *heavy = reinterpret_cast<const TileHeavy *>(reinterpret_cast<const unsigned char *>(srun) + td.nrun * (int)sizeof(TileRun));
-    const int nslot = td.nslot;
-    const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // contiguous slots per warp
-    const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
-    int r = 0;
-    {
-        int lo = 0, hi = td.nrun - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= w0) lo = mid; else hi = mid - 1; }
-        r = lo;
+    tl_gather_light<BLOCK>(td, stage, smeta, nzval, lane, warp);
+    // The tile that will occupy a CTA slot about one wave later (pf_dist = CTAs resident on the device): its geometry
+    // block (or connectivity) is pulled into L2 at the end of this CTA, so that tile's first load is an L2 hit.  The
+    // descriptor is read here, not at kernel start, so nothing stays live across the two phases (no spills).
+    const int tpf = blockIdx.x + pf_dist;
+    int64_t pf_elem0 = 0; int pf_nelem = 0;
+    if (tpf < ntiles) {
+        if constexpr (GEO) { pf_elem0 = tiles[tpf].geo0; pf_nelem = tiles[tpf].geo_bytes; }
+        else { pf_elem0 = tiles[tpf].elem0; pf_nelem = tiles[tpf].nelem; }
     }
-    // Light nonzeros (1 or 2 contributions: all but the matrix diagonals of node patches): one packed word per
-    // nonzero names both stage entries (a missing one names the neutral entry), four nonzeros in flight per lane, no
-    // branches.  Destination: the warp tracks, uniformly, the run A that holds the first nonzero of its batch of 128
-    // and the run B after it; a batch inside A+B (nearly all) picks one of the two bases per lane.  Only batches that
-    // span three or more runs walk the run table lane by lane.
-    const int nrun = td.nrun;
-    int endA = srun[r].s0 + srun[r].len;
-    double *dstA = nzval + (srun[r].nz0 - srun[r].s0);          // dstA + s is the nzval entry of tile slot s in run A
-    int endB = endA;
-    double *dstB = dstA;
-    if (r + 1 < nrun) { endB = srun[r + 1].s0 + srun[r + 1].len; dstB = nzval + (srun[r + 1].nz0 - srun[r + 1].s0); }
-    constexpr int U = 4;
-    for (int sb = w0; sb < w1; sb += 32 * U) {
-        const int bend = min(sb + 32 * U, w1);
-        uint32_t pk[U];
-        if (sb + 32 * U <= w1) {
-#pragma unroll
-            for (int u = 0; u < U; u++) pk[u] = spk[sb + u * 32 + lane];
-        } else {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int s = sb + u * 32 + lane;
-                pk[u] = (s < w1) ? spk[s] : 0u;
-            }
-        }
-        double acc[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) acc[u] = __dadd_rn(stage[pk[u] & 0xFFFFu], stage[pk[u] >> 16]);
-        while (sb >= endA) {     // warp-uniform: the run that holds slot sb becomes A
-            r++;
-            endA = endB; dstA = dstB;
-            if (r + 1 < nrun) { endB = srun[r + 1].s0 + srun[r + 1].len; dstB = nzval + (srun[r + 1].nz0 - srun[r + 1].s0); }
-        }
-        if (bend <= endB) {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int s = sb + u * 32 + lane;
-                double *d = (s < endA) ? dstA : dstB;
-                if (s < bend) d[s] = acc[u];
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int s = sb + u * 32 + lane;
-                if (s < bend) {
-                    int rr = r;
-                    while (s >= srun[rr].s0 + srun[rr].len) rr++;
-                    nzval[srun[rr].nz0 + (s - srun[rr].s0)] = acc[u];
-                }
-            }
-        }
-    }
-    {   // pull the connectivity of the tile one wave ahead into L2
+    tl_gather_heavy<BLOCK>(td, stage, smeta, nzval, tid);
+    if constexpr (GEO) {   // pull the geometry block of the tile one wave ahead into L2
+        const char *p0 = reinterpret_cast<const char *>(geo + pf_elem0);
+        for (int o = tid * 128; o < pf_nelem; o += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
+    } else {   // pull the connectivity of the tile one wave ahead into L2
         const char *p0 = reinterpret_cast<const char *>(tconn + pf_elem0 * GK);
         const int nbytes = pf_nelem * GK * 4;
         for (int o = tid * 128; o < nbytes; o += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
         const char *p1 = reinterpret_cast<const char *>(tmask + pf_elem0);
         for (int o = tid * 128; o < pf_nelem * 2; o += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p1 + o));
     }
-    // heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum; they
-    // overwrite the placeholder the light pass stored (same CTA, ordered by the barrier)
-    if (td.nheavy > 0) __syncthreads();
-    for (int h = tid; h < td.nheavy; h += BLOCK) {
-        const TileHeavy e = heavy[h];
-        double acc = stage[hidx[e.o]];
-        for (int k = 1; k < (int)e.c; k++) acc = __dadd_rn(acc, stage[hidx[e.o + k]]);
-        const int s = e.s;
-        int lo = 0, hi = td.nrun - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
-        nzval[srun[lo].nz0 + (s - srun[lo].s0)] = acc;
+}
+
+// Persistent variant for the TL_GEO forms: gridDim.x CTAs (one per CTA slot of the device) walk the tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...  Shared memory holds three fixed areas -- stage | gather metadata | geometry
+// block -- and two mbarriers.  While tile k is in its gather phase (stage + metadata in use) the geometry block of tile
+// k+1 is already in flight into the geometry area; while tile k+1 computes (geometry + stage in use) its metadata lands
+// in the metadata area: no phase waits for a global-memory round trip except in the first iteration.
+template <class F, bool S, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric_p(const TileDescFull *__restrict__ tiles, int ntiles, const unsigned char *__restrict__ meta,
+                                                              const unsigned char *__restrict__ geo, double *__restrict__ nzval, int off_meta, int off_geo,
+                                                              int off_gs)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ TileDescFull tdb[2];
+    __shared__ __align__(8) unsigned long long barG, barM;
+    constexpr int DW = (int)(sizeof(TileDescFull) / 8);
+    constexpr int GK = F::GK;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *stage = reinterpret_cast<double *>(smem_raw);
+    unsigned char *smeta = smem_raw + off_meta, *sgeo = smem_raw + off_geo;
+    const uint32_t bG = tl_smem_addr(&barG), bM = tl_smem_addr(&barM);
+    int t = blockIdx.x;
+    if (t >= ntiles) return;
+    if (tid < DW) reinterpret_cast<int64_t *>(&tdb[0])[tid] = reinterpret_cast<const int64_t *>(&tiles[t])[tid];
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bG));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bM));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    __syncthreads();
+    if (tid == 0 && tdb[0].nslot != 0) {
+        tl_bulk_load(tl_smem_addr(sgeo), geo + tdb[0].geo0, (uint32_t)tdb[0].geo_bytes, bG);
+        tl_bulk_load(tl_smem_addr(smeta), meta + tdb[0].meta0, (uint32_t)tdb[0].meta_bytes, bM);
+    }
+    uint32_t pg = 0, pm = 0;     // phase parities of the two barriers
+    int buf = 0;
+    for (; t < ntiles; t += gridDim.x, buf ^= 1) {
+        const TileDescFull &td = tdb[buf];
+        const TileDescFull &tdn = tdb[buf ^ 1];
+        const int tn = t + gridDim.x;
+        // descriptor of the next tile: written now, read after the barrier between the two phases
+        if (tn < ntiles && tid < DW) reinterpret_cast<int64_t *>(&tdb[buf ^ 1])[tid] = reinterpret_cast<const int64_t *>(&tiles[tn])[tid];
+        const bool work = td.nslot != 0;      // CTA-uniform
+        if (work) {
+            // phase 1: one thread per tile element, everything from the geometry block in shared memory
+            tl_mbar_wait(bG, pg);
+            pg ^= 1;
+            const int nq = td.nqs;
+            const double2 *sxy = reinterpret_cast<const double2 *>(sgeo);
+            const uint16_t *sc16 = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode));
+            const uint16_t *sm16 = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode) + tl_geo_conn_bytes(GK, td.nelem));
+            if constexpr (!F::SPLIT) {
+                for (int le = tid; le < td.nelem; le += BLOCK) tl_element_to_stage_local<F, S>((uint32_t)le, sc16, sm16, sxy, stage, td.qbase, nq);
+            } else {
+                // phase 1a: one thread per tile element: Jacobian / JxW / gradients at every quadrature point -> Gs (SoA)
+                const int ne = td.nelem, ncols = td.nq;
+                double *Gs = reinterpret_cast<double *>(smem_raw + off_gs);
+                for (int le = tid; le < ne; le += BLOCK) tl_geometry_to_smem_local<F, S>(le, ne, sc16, sxy, Gs);
+                __syncthreads();
+                // phase 1b: one thread per staged column (tile element, owned local column) -> stage
+                for (int qc = tid; qc < ncols; qc += BLOCK) {
+                    int r = 0;
+                    while (r + 1 < F::ND && (int)td.qbase[r + 1] <= qc) r++;
+                    const int le = qc - (int)td.qbase[r];
+                    uint32_t mm = sm16[le];
+                    for (int k = 0; k < r; k++) mm &= mm - 1;
+                    const int J = __ffs(mm) - 1;
+                    tl_column_to_stage<F, S>(qc, le, J, ne, nq, Gs, stage);
+                }
+            }
+        }
+        __syncthreads();      // stage complete; geometry area free; next descriptor visible
+        if (tid == 0 && tn < ntiles && tdn.nslot != 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the area are done (barrier above)
+            tl_bulk_load(tl_smem_addr(sgeo), geo + tdn.geo0, (uint32_t)tdn.geo_bytes, bG);
+        }
+        if (work) {
+            tl_mbar_wait(bM, pm);
+            pm ^= 1;
+            tl_gather_light<BLOCK>(td, stage, smeta, nzval, lane, warp);
+            tl_gather_heavy<BLOCK>(td, stage, smeta, nzval, tid);
+        }
+        __syncthreads();      // stage + metadata free; tdb[buf] may be overwritten in the next iteration
+        if (tid == 0 && tn < ntiles && tdn.nslot != 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tl_bulk_load(tl_smem_addr(smeta), meta + tdn.meta0, (uint32_t)tdn.meta_bytes, bM);
+        }
     }
 }
 
@@ -821,7 +1099,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
 template <class F> __host__ __device__ constexpr int tl_block() { return F::SPLIT ? TL_BLOCK_SPLIT : (F::ND > 8 ? 256 : TL_BLOCK_NS); }
 
 static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32};
-#define TL_SMEM_TWO_CTAS (114 * 1024 + 512)
 template <class F> static int tl_default_tile_elems()
 {
     // shared memory per owned element-equivalent ~ stage ND*ND*8 + gather metadata NT*2 + ~2.7*ND*ND
@@ -854,6 +1131,20 @@ template <class F> static int tl_default_tile_elems()
 
 template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te);
 
+template <class F> constexpr int tl_minb() { return (F::SPLIT || F::ND > 8) ? 2 : TL_MINB; }
+
+// CTAs of the numeric kernel that fit an SM with the shared memory the last symbolic phase asked for
+template <class F> static int tl_ctas_per_sm(efg_ctx *ctx)
+{
+    TiledData *td = tiled_data(ctx);
+    const void *kern = td->persist ? (const void *)k_tl_numeric_p<F, false, tl_block<F>(), tl_minb<F>()>
+                                   : (const void *)k_tl_numeric<F, false, tl_block<F>(), tl_minb<F>()>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int per_sm = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tl_block<F>(), (size_t)td->smem_bytes));
+    return per_sm;
+}
+
 template <class F> void tiled_symbolic(efg_ctx *ctx)
 {
     if (ctx->opt_tile_elems > 0) { tiled_symbolic_te<F>(ctx, ctx->opt_tile_elems); return; }
@@ -861,16 +1152,22 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     for (;;) {
         try {
             tiled_symbolic_te<F>(ctx, te);
-            if (tiled_data(ctx)->smem_bytes <= TL_SMEM_TWO_CTAS || te <= 32) return;
+            if (te <= 32 || tl_ctas_per_sm<F>(ctx) >= 2) return;      // two co-resident CTAs overlap each other's phases
         } catch (const EfgError &e) {
             if (e.code != EFG_ERR_LIMIT || te <= 32) throw;
         }
         int next = 32;
-        for (int c : TL_TILE_SIZES) {
-            if (c >= te) continue;
-            if (F::SPLIT) { const double rounds = (double)c * F::ND / tl_block<F>(); if (rounds / ceil(rounds) < 0.85 && c > 32) continue; }
-            next = c;
-            break;
+        if (F::SPLIT) {
+            for (int c : TL_TILE_SIZES) {
+                if (c >= te) continue;
+                const double rounds = (double)c * F::ND / tl_block<F>();
+                if (rounds / ceil(rounds) < 0.85 && c > 32) continue;
+                next = c;
+                break;
+            }
+        } else {
+            next = ((int)(te * 0.97)) & ~7;     // the footprint (stage + gather metadata + geometry block) scales with te
+            if (next < 32) next = 32;
         }
         te = next;
         tiled_release(ctx);
@@ -1056,22 +1353,42 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     td->tconn.alloc(pool, (size_t)(ntelem * F::GK + 1));
     td->tmask.alloc(pool, (size_t)ntelem + 1);
     LAUNCH(ctx, k_tl_tconn<F::GK>, grid_for(ntelem, 256), 256, 0, order2.p, ntelem, telem_key.p, emask.p, gm.conn.p, td->tconn.p, td->tmask.p);
+    // TL_GEO (one-thread-per-element forms): tile-local node numbering for the geometry blocks
+    constexpr bool GEO = TL_GEO && (!F::SPLIT || tl_persist<F>());
+    DevBuf<uint16_t> tlocal;
+    DevBuf<int32_t> tnodes, tnn;
+    if (GEO) {
+        tlocal.alloc(pool, (size_t)(ntelem * F::GK + 1)); tnodes.alloc(pool, (size_t)(ntelem * F::GK + 1)); tnn.alloc(pool, (size_t)ntiles + 1);
+        LAUNCH(ctx, k_tl_geo_local<F::GK>, (unsigned)ntiles, 256, 0, telem_ptr.p, td->tconn.p, tlocal.p, tnodes.p, tnn.p, err.p);
+        if (tl_read(ctx, err.p))
+            efg_throw(EFG_ERR_LIMIT, "tiled path: a tile has more than %d connectivity entries; lower EFG_OPT_TILE_ELEMS", TL_GEO_CAP);
+    }
 
     trace.mark("T6 tile elements");
     // tile descriptors + metadata block layout
     DevBuf<int32_t> maxima;
-    DevBuf<int64_t> mbytes, moff;
-    maxima.alloc(pool, 4);
+    DevBuf<int64_t> mbytes, moff, gbytes, goffs;
+    maxima.alloc(pool, 8);
     mbytes.alloc(pool, (size_t)ntiles + 1); moff.alloc(pool, (size_t)ntiles + 1);
-    CUDA_CHECK(cudaMemsetAsync(maxima.p, 0, 4 * sizeof(int32_t), st));
+    gbytes.alloc(pool, (size_t)ntiles + 1); goffs.alloc(pool, (size_t)ntiles + 1);
+    CUDA_CHECK(cudaMemsetAsync(maxima.p, 0, 8 * sizeof(int32_t), st));
     CUDA_CHECK(cudaMemsetAsync(mbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
+    CUDA_CHECK(cudaMemsetAsync(gbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     td->tiles.alloc(pool, (size_t)ntiles);
-    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tl_gsz<F>(), tcol_ptr.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
+    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tl_gsz<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
            nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
     tl_excl_scan(ctx, mbytes.p, moff.p, (int64_t)ntiles + 1);
     const int64_t meta_total = tl_read(ctx, moff.p + ntiles);
     LAUNCH(ctx, k_tl_tiles_meta0, grid_for(ntiles, 256), 256, 0, ntiles, moff.p, td->tiles.p);
-    int32_t hmax[4];
+    if (GEO) {
+        tl_excl_scan(ctx, gbytes.p, goffs.p, (int64_t)ntiles + 1);
+        td->geo_total = tl_read(ctx, goffs.p + ntiles);
+        LAUNCH(ctx, k_tl_tiles_geo0, grid_for(ntiles, 256), 256, 0, ntiles, goffs.p, td->tiles.p);
+        td->geo.alloc(pool, (size_t)(td->geo_total > 0 ? td->geo_total : 16));
+        CUDA_CHECK(cudaMemsetAsync(td->geo.p, 0, (size_t)(td->geo_total > 0 ? td->geo_total : 16), st));
+        LAUNCH(ctx, k_tl_geo_fill<F::GK>, grid_for(ntiles, 1, (int64_t)148 * 16), 128, 0, ntiles, td->tiles.p, tlocal.p, tnodes.p, td->tmask.p, gm.xy.p, td->geo.p);
+    }
+    int32_t hmax[8];
     CUDA_CHECK(cudaMemcpyAsync(hmax, maxima.p, sizeof hmax, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     ctx->tl.max_nq = hmax[1] / ND; ctx->tl.max_nslot = 0; ctx->tl.max_nelem = hmax[3]; ctx->tl.max_nrun = 0;
@@ -1081,7 +1398,12 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
         efg_throw(EFG_ERR_LIMIT, "tiled path: a tile gathers %d heavy contributions (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[2]);
     td->stage_bytes = 0;
     td->meta_max = 0;
-    td->smem_bytes = hmax[0];                                  // max over tiles of (stage + gather metadata)
+    td->smem_bytes = hmax[0];                                  // max over tiles of (stage + gather metadata + geometry block)
+    td->persist = tl_persist<F>();
+    if (td->persist) {      // fixed areas: the next tile's blocks are fetched while the current tile still uses the others
+        td->off_meta = hmax[4]; td->off_geo = hmax[4] + hmax[5]; td->off_gs = hmax[4] + hmax[5] + hmax[6];
+        td->smem_bytes = hmax[4] + hmax[5] + hmax[6] + hmax[7];     // (hmax[7] = 0 for the one-thread-per-element forms)
+    }
     if (td->smem_bytes > 225 * 1024)
         efg_throw(EFG_ERR_LIMIT, "tiled path: a tile needs %d bytes of shared memory; lower EFG_OPT_TILE_ELEMS", td->smem_bytes);
     td->meta_bytes = meta_total;
@@ -1101,28 +1423,40 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     ctx->tl.ntiles = ntiles;
     ctx->tl.tile_elems = te;
     ctx->tl.sum_tile_elems = ntelem;
-    ctx->tl.numeric_bytes = ntelem * (F::GK * 4 + 2) + gm.nnodes * 16 + meta_total + nnz * 8 + (int64_t)ntiles * sizeof(TileDescFull);
+    ctx->tl.numeric_bytes = (GEO ? td->geo_total : ntelem * (F::GK * 4 + 2) + gm.nnodes * 16) + meta_total + nnz * 8 + (int64_t)ntiles * sizeof(TileDescFull);
+    if (GEO) { td->tconn.release(); td->tmask.release(); }     // the numeric kernel reads the geometry blocks instead
 }
 
 template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(efg_ctx *ctx)
 {
     TiledData *td = tiled_data(ctx);
     const MeshDev &gm = ctx->mesh[F::GMESH];
-    auto kern = k_tl_numeric<F, S, BLOCK, MINB>;
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
     int per_sm = 0, nsm = 0;
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
     CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-    if (per_sm < 1) efg_throw(EFG_ERR_LIMIT, "tiled path: the numeric kernel does not fit on an SM (%d bytes of shared memory)", td->smem_bytes);
-    int grid = ctx->tl.ntiles;                    // one CTA per tile
-    if (grid > 0)
-        LAUNCH(ctx, kern, (unsigned)grid, BLOCK, (size_t)td->smem_bytes, td->tiles.p, ctx->tl.ntiles, td->tconn.p, td->tmask.p, gm.xy.p,
-               td->meta.p, ctx->nzval.p, per_sm * nsm, 0);
+    if (td->persist) {
+        auto kern = k_tl_numeric_p<F, S, BLOCK, MINB>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
+        if (per_sm < 1) efg_throw(EFG_ERR_LIMIT, "tiled path: the numeric kernel does not fit on an SM (%d bytes of shared memory)", td->smem_bytes);
+        const int grid = ctx->tl.ntiles < per_sm * nsm ? ctx->tl.ntiles : per_sm * nsm;      // one CTA per CTA slot
+        if (grid > 0)
+            LAUNCH(ctx, kern, (unsigned)grid, BLOCK, (size_t)td->smem_bytes, td->tiles.p, ctx->tl.ntiles, td->meta.p, td->geo.p, ctx->nzval.p,
+                   td->off_meta, td->off_geo, td->off_gs);
+    } else {
+        auto kern = k_tl_numeric<F, S, BLOCK, MINB>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
+        if (per_sm < 1) efg_throw(EFG_ERR_LIMIT, "tiled path: the numeric kernel does not fit on an SM (%d bytes of shared memory)", td->smem_bytes);
+        const int grid = ctx->tl.ntiles;                    // one CTA per tile
+        if (grid > 0)
+            LAUNCH(ctx, kern, (unsigned)grid, BLOCK, (size_t)td->smem_bytes, td->tiles.p, ctx->tl.ntiles, td->tconn.p, td->tmask.p, gm.xy.p,
+                   td->meta.p, ctx->nzval.p, per_sm * nsm, td->geo.p);
+    }
     ctx->numeric_launches += 1;
 }
 template <class F, bool S> static void tl_launch_numeric(efg_ctx *ctx)
 {
-    tl_launch_numeric_b<F, S, tl_block<F>(), 2>(ctx);
+    tl_launch_numeric_b<F, S, tl_block<F>(), tl_minb<F>()>(ctx);
 }
 
 template <class F> void tiled_numeric(efg_ctx *ctx)

@@ -6,7 +6,7 @@
 module ElfelGPU
 
 using SparseArrays: SparseMatrixCSC
-using Elfel.Assemblers: AbstractSysmatAssembler
+using Elfel.Assemblers: AbstractSysmatAssembler, AbstractSysvecAssembler
 import Elfel.Assemblers: start!, assemble!, finish!
 using Elfel.FEIterators: FEIterator
 using Elfel.QPIterators: QPIterator
@@ -16,6 +16,7 @@ const LIB = get(ENV, "ELFELGPU_LIB", "libelfelgpu.so")
 
 # weak forms = the integrate! closures of the examples
 struct HeatForm;            kappa::Float64; end                 # examples/heat/poisson/t3.jl:53-58
+struct HeatLoadForm;        Q::Float64; end                     # examples/heat/poisson/t3.jl:57 (vector form)
 struct ElasticityForm;      D::Matrix{Float64}; end             # examples/elasticity/stretch/t6.jl:42-58
 struct StokesGenForm;       D::Matrix{Float64}; end             # examples/stokes/colliding_flow/ht_p2_p1_gen.jl
 struct StokesReddyForm;     mu::Float64; end                    # .../ht_p2_p1.jl
@@ -103,6 +104,59 @@ function finish!(a::SysmatAssemblerGPU)
     _check(a, ccall((:efg_fetch_csc, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
                     a.ctx, colptr, rowval, nzval))
     return SparseMatrixCSC(a.nrow, a.ncol, colptr, rowval, nzval)
+end
+
+# ---- system vector (SysvecAssembler, src/Assemblers.jl:170-232) ---------------------------------------------
+"""
+    SysvecAssemblerGPU(0.0; like = am)
+
+Selected in place of `SysvecAssembler`.  `like = am` shares the device context of a `SysmatAssemblerGPU`, so the
+mesh and dof maps sent for the matrix are reused by the vector half of the same `integrate!` call.
+"""
+mutable struct SysvecAssemblerGPU <: AbstractSysvecAssembler
+    owner::SysmatAssemblerGPU
+    ndofs::Int64
+    SysvecAssemblerGPU(zero::Float64 = 0.0; like::SysmatAssemblerGPU = SysmatAssemblerGPU(0.0)) = new(like, 0)
+end
+
+"start!(av, nrow) -- src/Assemblers.jl:196-200"
+start!(v::SysvecAssemblerGPU, nrow::Int64) = (v.ndofs = nrow; v)
+
+"assemble!(av, HeatLoadForm(Q), elit, qpit): the `init!(fe, eldofs(el)); fe[j] += N[j]*Q*JxW; assemble!(av, fe)` half of the loop"
+function assemble!(v::SysvecAssemblerGPU, form::HeatLoadForm, elit::FEIterator, qpit::QPIterator)
+    a = v.owner       # mesh 0 / space 0 were sent by assemble!(am, HeatForm(...), elit, qpit) on the shared context
+    p = [form.Q]
+    _check(a, ccall((:efg_vec_assemble, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Cint, Int64),
+                    a.ctx, 1, _rule(qpit, _kind(elit)), p, 1, v.ndofs))
+    return v
+end
+
+"finish!(av) -- src/Assemblers.jl:230-232"
+function finish!(v::SysvecAssemblerGPU)
+    F = Vector{Float64}(undef, v.ndofs)
+    _check(v.owner, ccall((:efg_fetch_vec, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), v.owner.ctx, F))
+    return F
+end
+
+# ---- what solve! does with K right after finish! (examples/heat/poisson/t3.jl:77-80), without fetching K ------
+"`KT = mul(am, T)` == `K * T`, same summation order as SparseArrays"
+function mul(a::SysmatAssemblerGPU, x::Vector{Float64})
+    y = Vector{Float64}(undef, a.nrow)
+    _check(a, ccall((:efg_spmv, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), a.ctx, x, y))
+    return y
+end
+
+"`block(am, 1:nu, 1:nu)` == `K[1:nu, 1:nu]`, sliced on the device"
+function block(a::SysmatAssemblerGPU, rows::UnitRange{Int}, cols::UnitRange{Int})
+    n = Ref{Int64}(0)
+    _check(a, ccall((:efg_block_nnz, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ref{Int64}),
+                    a.ctx, first(rows), last(rows), first(cols), last(cols), n))
+    colptr = Vector{Int64}(undef, length(cols) + 1)
+    rowval = Vector{Int64}(undef, n[])
+    nzval = Vector{Float64}(undef, n[])
+    _check(a, ccall((:efg_fetch_block, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+                    a.ctx, colptr, rowval, nzval))
+    return SparseMatrixCSC(length(rows), length(cols), colptr, rowval, nzval)
 end
 
 end # module

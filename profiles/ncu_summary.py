@@ -40,6 +40,18 @@ for a, b in zip(seg[:-1], seg[1:]):
     s_ = sum(int(r[isamp]) for r in data[a:b]); e_ = sum(int(r[iex]) for r in data[a:b])
     print(f"  between barriers [{a},{b}): samples {100*s_/max(tot,1):5.1f}%  executed {100*e_/max(totex,1):5.1f}%")
 stalls = [x for x in h if x.startswith("stall_") and "Not Issued" not in x]
+# finer regions: split at barriers, calls, unconditional exits / returns and the mbarrier wait (phase boundaries)
+import re
+marks = [i for i, r in enumerate(data) if re.search(r"^\s*(BAR\.SYNC|CALL|EXIT|RET|SYNCS\.PHASECHK)", r[isrc].strip())]
+seg2 = sorted(set([0] + [i + 1 for i in marks] + [len(data)]))
+print("regions (split at BAR.SYNC / CALL / EXIT / RET / mbarrier wait):")
+for a, b in zip(seg2[:-1], seg2[1:]):
+    s_ = sum(int(r[isamp]) for r in data[a:b]); e_ = sum(int(r[iex]) for r in data[a:b])
+    if s_ * 200 < tot and e_ * 200 < totex:
+        continue
+    st = sorted(((x, sum(int(r[h.index(x)]) for r in data[a:b])) for x in stalls), key=lambda x: -x[1])[:4]
+    st = [(n, round(100 * v / max(tot, 1), 1)) for n, v in st]
+    print(f"  [{a:5d},{b:5d}) ends at '{data[b-1][isrc].strip()[:28]}': samples {100*s_/max(tot,1):5.1f}%  executed {100*e_/max(totex,1):5.1f}%  {st}")
 print("top stall sites:")
 for r in sorted(data, key=lambda r: -int(r[isamp]))[:14]:
     st = sorted(((x, int(r[h.index(x)])) for x in stalls), key=lambda x: -x[1])[:2]
