@@ -89,6 +89,8 @@ struct efg_ctx {
     TwoPass tp;
     Tiled tl;
     void *tl_opaque = nullptr;
+    int form_req = 0, quad_req = 0;      // form / rule of the symbolic phase in progress
+    int te_hint = 0, te_hint_form = 0, te_hint_kind = 0, te_hint_quad = 0;   // tile size the last symbolic phase settled on
     void *vec_opaque = nullptr;  // efg_vector.cuh: system-vector assembly, K*x, sub-blocks
     DevBuf<char> scratch;        // persistent scratch for the largest symbolic temporaries (kept across calls: the
                                  // multi-GB sort buffers made cudaMallocAsync stall for 0.1-2.5 s when re-allocated every call)

@@ -91,6 +91,10 @@ __host__ __device__ static inline int tl_geo_block_bytes(int gk, int nelem, int 
 #define TL_PERSIST_SPLIT 0
 #endif
 template <class F> constexpr bool tl_persist() { return TL_GEO && (F::SPLIT ? TL_PERSIST_SPLIT : TL_PERSIST_NS); }
+#ifndef TL_GEO_SPLIT
+#define TL_GEO_SPLIT 1  // vector forms: phase 1a reads the tile's geometry block too (the block sits behind the shared
+                        // geometry/metadata area)
+#endif
 #ifndef TL_VEC_CONN
 #define TL_VEC_CONN 1   // tile connectivity read with 8/16-byte loads (T6: 3 x int2, Q4: 1 x int4) instead of 4-byte loads
 #endif
@@ -893,7 +897,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDescFull td;
     __shared__ __align__(8) unsigned long long bar, bar2;
-    constexpr bool GEO = TL_GEO && !F::SPLIT;
+    constexpr bool GEO = TL_GEO && (!F::SPLIT || TL_GEO_SPLIT);
     constexpr int DW = (int)(sizeof(TileDescFull) / 8);
     constexpr int GK = F::GK;
     constexpr int NW = BLOCK / 32;
@@ -914,7 +918,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     // SPLIT forms: the per-element geometry of phase 1 and the gather metadata of phase 2 share the same shared-memory
     // area, so the TMA copy is issued after phase 1; otherwise it is issued now and lands while phase 1 computes
     unsigned char *smeta = smem_raw + tl_stage_bytes(F::ND, td.nqs);
-    unsigned char *sgeo = smeta + td.meta_bytes;     // geometry block (GEO): txy | conn16 | mask16
+    // geometry block (GEO): txy | conn16 | mask16, behind the metadata area (vector forms: behind the area the metadata shares with Gs)
+    unsigned char *sgeo = smeta + (F::SPLIT ? max(td.meta_bytes, tl_geo_bytes(GSZ, td.nelem)) : td.meta_bytes);
     if (GEO && tid == 0) tl_bulk_load(tl_smem_addr(sgeo), geo + td.geo0, (uint32_t)td.geo_bytes, barB);   // needed first
     if (!F::SPLIT && tid == 0) tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
     if (F::SPLIT) {   // the TMA copy is issued after phase 1 (shared area): pull the block into L2 meanwhile
@@ -924,7 +929,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     const int nq = td.nqs;      // stage row stride (odd)
     const int ncols = td.nq;    // staged columns
 
-    if constexpr (GEO) {
+    if constexpr (!F::SPLIT && GEO) {
         // phase 1 from the tile's geometry block: no global loads at all -- local connectivity and coordinates come
         // from shared memory as soon as the bulk copy has landed
         tl_mbar_wait(barB, 0);
@@ -950,9 +955,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
         // phase 1a: one thread per tile element: Jacobian / JxW / gradients at every quadrature point -> shared memory
         const int ne = td.nelem;
         double *Gs = reinterpret_cast<double *>(smem_raw + tl_stage_bytes(F::ND, nq));   // SoA: Gs[k * ne + le]
-        uint16_t *smask = reinterpret_cast<uint16_t *>(Gs + GSZ * ne);
-        for (int le = tid; le < ne; le += BLOCK)
-            tl_geometry_to_smem<F, S>(td.elem0 + le, le, ne, tconn, tmask, xy, Gs, smask);
+        const uint16_t *smask;
+        if constexpr (GEO) {
+            tl_mbar_wait(barB, 0);
+            const double2 *sxy = reinterpret_cast<const double2 *>(sgeo);
+            const uint16_t *sc16 = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode));
+            smask = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode) + tl_geo_conn_bytes(GK, ne));
+            for (int le = tid; le < ne; le += BLOCK) tl_geometry_to_smem_local<F, S>(le, ne, sc16, sxy, Gs);
+        } else {
+            uint16_t *sm = reinterpret_cast<uint16_t *>(Gs + GSZ * ne);
+            for (int le = tid; le < ne; le += BLOCK)
+                tl_geometry_to_smem<F, S>(td.elem0 + le, le, ne, tconn, tmask, xy, Gs, sm);
+            smask = sm;
+        }
         __syncthreads();
         // phase 1b: one thread per staged column (tile element, owned local column) -> stage
         for (int qc = tid; qc < ncols; qc += BLOCK) {
@@ -1148,11 +1163,18 @@ template <class F> static int tl_ctas_per_sm(efg_ctx *ctx)
 template <class F> void tiled_symbolic(efg_ctx *ctx)
 {
     if (ctx->opt_tile_elems > 0) { tiled_symbolic_te<F>(ctx, ctx->opt_tile_elems); return; }
-    int te = tl_default_tile_elems<F>();
+    // start from the size the previous symbolic phase of this form settled on (re-assembly after efg_set_mesh, time
+    // stepping with a changing mesh): the search below then succeeds at the first attempt
+    const int vkind = ctx->mesh[0].kind;
+    const bool hinted = ctx->te_hint > 0 && ctx->te_hint_form == ctx->form_req && ctx->te_hint_kind == vkind && ctx->te_hint_quad == ctx->quad_req;
+    int te = hinted ? ctx->te_hint : tl_default_tile_elems<F>();
     for (;;) {
         try {
             tiled_symbolic_te<F>(ctx, te);
-            if (te <= 32 || tl_ctas_per_sm<F>(ctx) >= 2) return;      // two co-resident CTAs overlap each other's phases
+            if (te <= 32 || tl_ctas_per_sm<F>(ctx) >= 2) {      // two co-resident CTAs overlap each other's phases
+                ctx->te_hint = te; ctx->te_hint_form = ctx->form_req; ctx->te_hint_kind = vkind; ctx->te_hint_quad = ctx->quad_req;
+                return;
+            }
         } catch (const EfgError &e) {
             if (e.code != EFG_ERR_LIMIT || te <= 32) throw;
         }
@@ -1354,12 +1376,18 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     td->tmask.alloc(pool, (size_t)ntelem + 1);
     LAUNCH(ctx, k_tl_tconn<F::GK>, grid_for(ntelem, 256), 256, 0, order2.p, ntelem, telem_key.p, emask.p, gm.conn.p, td->tconn.p, td->tmask.p);
     // TL_GEO (one-thread-per-element forms): tile-local node numbering for the geometry blocks
-    constexpr bool GEO = TL_GEO && (!F::SPLIT || tl_persist<F>());
-    DevBuf<uint16_t> tlocal;
-    DevBuf<int32_t> tnodes, tnn;
+    constexpr bool GEO = TL_GEO && (!F::SPLIT || TL_GEO_SPLIT || tl_persist<F>());
+    // (tlocal / tnodes live in the persistent scratch: the sort buffers it held are dead by now)
+    uint16_t *tlocal = nullptr;
+    int32_t *tnodes = nullptr;
+    DevBuf<int32_t> tnn;
     if (GEO) {
-        tlocal.alloc(pool, (size_t)(ntelem * F::GK + 1)); tnodes.alloc(pool, (size_t)(ntelem * F::GK + 1)); tnn.alloc(pool, (size_t)ntiles + 1);
-        LAUNCH(ctx, k_tl_geo_local<F::GK>, (unsigned)ntiles, 256, 0, telem_ptr.p, td->tconn.p, tlocal.p, tnodes.p, tnn.p, err.p);
+        const size_t nent = (size_t)(ntelem * F::GK + 8);
+        char *sc = tl_scratch(ctx, nent * 4 + ((nent * 2 + 15) & ~(size_t)15));
+        tnodes = reinterpret_cast<int32_t *>(sc);
+        tlocal = reinterpret_cast<uint16_t *>(sc + nent * 4);
+        tnn.alloc(pool, (size_t)ntiles + 1);
+        LAUNCH(ctx, k_tl_geo_local<F::GK>, (unsigned)ntiles, 256, 0, telem_ptr.p, td->tconn.p, tlocal, tnodes, tnn.p, err.p);
         if (tl_read(ctx, err.p))
             efg_throw(EFG_ERR_LIMIT, "tiled path: a tile has more than %d connectivity entries; lower EFG_OPT_TILE_ELEMS", TL_GEO_CAP);
     }
@@ -1386,7 +1414,7 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
         LAUNCH(ctx, k_tl_tiles_geo0, grid_for(ntiles, 256), 256, 0, ntiles, goffs.p, td->tiles.p);
         td->geo.alloc(pool, (size_t)(td->geo_total > 0 ? td->geo_total : 16));
         CUDA_CHECK(cudaMemsetAsync(td->geo.p, 0, (size_t)(td->geo_total > 0 ? td->geo_total : 16), st));
-        LAUNCH(ctx, k_tl_geo_fill<F::GK>, grid_for(ntiles, 1, (int64_t)148 * 16), 128, 0, ntiles, td->tiles.p, tlocal.p, tnodes.p, td->tmask.p, gm.xy.p, td->geo.p);
+        LAUNCH(ctx, k_tl_geo_fill<F::GK>, grid_for(ntiles, 1, (int64_t)148 * 16), 128, 0, ntiles, td->tiles.p, tlocal, tnodes, td->tmask.p, gm.xy.p, td->geo.p);
     }
     int32_t hmax[8];
     CUDA_CHECK(cudaMemcpyAsync(hmax, maxima.p, sizeof hmax, cudaMemcpyDeviceToHost, st));

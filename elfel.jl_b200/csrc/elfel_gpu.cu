@@ -411,6 +411,7 @@ int efg_symbolic(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
         if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, vkind);
         CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
         int path = ctx->opt_path == 1 ? 1 : 2;
+        ctx->form_req = form; ctx->quad_req = quad;
         const bool ok = dispatch_form(form, vkind, npts, [&](auto F) {
             using Form = decltype(F);
             if (path == 2) {
