@@ -136,3 +136,44 @@ def test_heat_examples_end_to_end_through_the_mirrored_api():
             assert nu == 9801
             efg.scattersysvec(fesp, T)
             assert np.abs(fesp.field.dofvals[:, 0] - tempf(mesh.xy[:, 0], mesh.xy[:, 1])).mean() <= 1.0e-9
+
+
+def test_load_vector_and_spmv_larger_mesh(oracle):
+    """Beyond one radix-sort tile and several CTAs of the matrix kernel: 180 k T6 elements, default tile size."""
+    prob = efg.heat_problem(efg.T6, 300, perturb=True)
+    n = prob.ndofs
+    eng = efg.Engine(0)
+    efg.load_problem(eng, prob)
+    eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+    cp, rv, nz = eng.fetch_csc()
+    eng.vec_assemble(_lib.VFORM_HEAT_LOAD, prob.quad, [-6.0], n)
+    F = eng.fetch_vec()
+    assert np.array_equal(F, oracle.assemble_vec_heat(prob.quad, prob.meshes[0], prob.spaces[0].field.dofnums, -6.0, n))
+    x = np.random.default_rng(11).standard_normal(n)
+    assert np.array_equal(eng.spmv(x), oracle.spmv_csc(n, n, cp, rv, nz, x))
+    # the vector data survives a new numeric phase (same pattern), the row-major view too
+    eng.numeric([2.0])
+    _, _, nz2 = eng.fetch_csc()
+    assert np.array_equal(eng.spmv(x), oracle.spmv_csc(n, n, cp, rv, nz2, x))
+    assert np.array_equal(eng.fetch_vec(), F)
+    eng.close()
+
+
+def test_reassembly_reuses_tile_size_and_stays_bit_identical(oracle):
+    """efg_set_mesh invalidates the symbolic data; the tile size found by the first (occupancy-driven) search is
+    reused, and the result of the second assembly is the same bits."""
+    prob = efg.heat_problem(efg.T6, 160)
+    eng = efg.Engine(0)
+    efg.load_problem(eng, prob)
+    eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+    a = eng.fetch_csc()
+    tiles1 = eng.stat(_lib.STAT_NTILES)
+    efg.load_problem(eng, prob)                 # set_mesh / set_space / start again
+    eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+    b = eng.fetch_csc()
+    assert eng.stat(_lib.STAT_NTILES) == tiles1
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    ocp, orv, onz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    assert np.array_equal(a[0], ocp) and np.array_equal(a[1], orv)
+    assert np.all(np.abs(a[2] - onz) <= 1e-14 + 1e-12 * np.abs(onz))
+    eng.close()
