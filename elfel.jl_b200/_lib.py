@@ -32,7 +32,8 @@ VFORM_HEAT_LOAD = 1
 EXPORTS = ["efg_create", "efg_destroy", "efg_last_error", "efg_set_option", "efg_get_stat", "efg_get_stream",
            "efg_synchronize", "efg_set_mesh", "efg_set_space", "efg_start", "efg_set_column_range",
            "efg_set_column_ranges", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version",
-           "efg_vec_assemble", "efg_fetch_vec", "efg_device_vec", "efg_spmv", "efg_block_nnz", "efg_fetch_block"]
+           "efg_vec_assemble", "efg_fetch_vec", "efg_device_vec", "efg_spmv", "efg_block_nnz", "efg_fetch_block",
+           "efg_qp_locations", "efg_l2_error"]
 
 
 def _sources():
@@ -100,6 +101,8 @@ def load():
     L.efg_spmv.argtypes = [vp, vp, vp]
     L.efg_block_nnz.argtypes = [vp, i64, i64, i64, i64, i64p]
     L.efg_fetch_block.argtypes = [vp, vp, vp, vp]
+    L.efg_qp_locations.argtypes = [vp, ci, ci, vp, i64p]
+    L.efg_l2_error.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), ci, vp, i64, vp, f64p]
     for name in EXPORTS:
         if name not in ("efg_version", "efg_last_error") and hasattr(L, name):
             getattr(L, name).restype = ci

@@ -283,6 +283,28 @@ class Engine:
         return colptr, rowval, nzval
 
 
+    # ---- SURVEY 8f row f3 ---------------------------------------------------------------------------
+    def qp_locations(self, mesh_slot, quad, nel):
+        """location(el, qp) of every element / quadrature point of a mesh -> (nel, npts, 2)."""
+        npts = C.c_int64()
+        self._ck(self.L.efg_qp_locations(self.h, mesh_slot, quad, None, C.byref(npts)))
+        out = np.empty((int(nel), npts.value, 2), dtype=np.float64)
+        self._ck(self.L.efg_qp_locations(self.h, mesh_slot, quad, _ptr(out), C.byref(npts)))
+        return out
+
+    def l2_error(self, comps, quad, U, truth) -> float:
+        """comps: [(space_slot, component0based), ...] (1 or 2); U: system vector; truth: (nel, npts, ncomp)."""
+        slots = (C.c_int * len(comps))(*[int(c[0]) for c in comps])
+        cc = (C.c_int * len(comps))(*[int(c[1]) for c in comps])
+        if isinstance(U, np.ndarray):
+            U = np.ascontiguousarray(U, dtype=np.float64)
+        if isinstance(truth, np.ndarray):
+            truth = np.ascontiguousarray(truth, dtype=np.float64)
+        out = C.c_double()
+        self._ck(self.L.efg_l2_error(self.h, len(comps), slots, cc, quad, _ptr(U), int(U.shape[0]), _ptr(truth), C.byref(out)))
+        return out.value
+
+
 class SysmatAssemblerGPU:
     """Selected in place of SysmatAssemblerSparse; same start / assemble / finish life cycle."""
 
@@ -386,3 +408,27 @@ def block(ass: SysmatAssemblerGPU, r0, r1, c0, c1) -> SparseMatrixCSC:
         raise _lib.EfgError(_lib.ERR_STATE, "block before assemble")
     colptr, rowval, nzval = ass.engine.block(r0, r1, c0, c1)
     return SparseMatrixCSC(int(r1) - int(r0) + 1, int(c1) - int(c0) + 1, colptr, rowval, nzval)
+
+
+def evaluate_error(ass: SysmatAssemblerGPU, elits, qpit, U, truefs):
+    """The evaluate_pressure_error / evaluate_velocity_error loops of the Stokes examples
+    (examples/stokes/colliding_flow/ht_p2_p1.jl:120-178) on the device.  ``elits``: one FEIterator per field component
+    (the same iterator twice for the two components of a vector space); ``truefs``: one vectorised callable f(x, y) per
+    component, evaluated on the host at location(el, qp); ``U``: the system vector.  The spaces must be the ones the
+    assembler's context holds (the last ``assemble`` call)."""
+    eng = ass.engine
+    if isinstance(elits, FEIterator):
+        elits, truefs = (elits,), (truefs,)
+    loaded = getattr(eng, "_keep", [])
+    comps, seen = [], {}
+    for it in elits:
+        slot = [i for i, k in enumerate(loaded) if k.fesp is it.fesp]
+        if not slot:
+            raise _lib.EfgError(_lib.ERR_STATE, "evaluate_error: this space was not part of the last assemble call")
+        comps.append((slot[0], seen.get(slot[0], 0)))
+        seen[slot[0]] = seen.get(slot[0], 0) + 1
+    mesh = elits[0].fesp.mesh
+    mslot = 0 if loaded[0].fesp.mesh is mesh else 1
+    loc = eng.qp_locations(mslot, qpit.rule, mesh.conn.shape[0])
+    truth = np.stack([np.asarray(f(loc[..., 0], loc[..., 1]), dtype=np.float64) for f in truefs], axis=-1)
+    return eng.l2_error(comps, qpit.rule, U, truth)

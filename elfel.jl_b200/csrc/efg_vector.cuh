@@ -2,6 +2,8 @@
 //   f1  system VECTOR assembly: SysvecAssembler start!/assemble!/finish! fed by a LocalVectorAssembler
 //       (src/Assemblers.jl:196-232, src/LocalAssemblers.jl:95-152) for the load term of the heat examples,
 //       `fe[j] += N[j]*Q*JxW` (examples/heat/poisson/t3.jl:57, q4.jl:47);
+//   f3  the post-processing integrators of the Stokes examples: location(el, qp) (src/FEIterators.jl:227-235) and
+//       evaluate_pressure_error / evaluate_velocity_error (examples/stokes/colliding_flow/ht_p2_p1.jl:120-178);
 //   f2  what the examples do with K right after finish!: `KT = K*T` (examples/heat/poisson/t3.jl:78) and the
 //       partition K[1:nu,1:nu], K[1:nu,nu+1:end] (t3.jl:79, examples/stokes/colliding_flow/ht_p2_p1_gen.jl solve!),
 //       so a 10 GB matrix is not copied to the host just to be sliced.
@@ -229,4 +231,99 @@ __global__ void k_block_copy(const int64_t *__restrict__ bcolptr, const int64_t 
             if (oval) oval[o + k] = nzval[a + k];
         }
     }
+}
+
+// ---- f3: location(el, qp) and the L2 error integrators ---------------------------------------------------
+// out[(e*NQ + q)*2 + {0,1}] = sum_i x_i * N_i(q): first term assigned, node order, individually rounded operations
+template <int NEN, int NQ>
+__global__ void __launch_bounds__(256) k_qp_locations(const int32_t *__restrict__ conn, const double2 *__restrict__ xy, int64_t nel, double *__restrict__ out)
+{
+    const QTab &tg = c_tab[kind_slot(NEN)];
+    GRID_STRIDE(e, nel) {
+        double X[NEN], Y[NEN];
+        load_xy<NEN>(conn, xy, e, X, Y);
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            double lx = __dmul_rn(X[0], tg.N[q][0]), ly = __dmul_rn(Y[0], tg.N[q][0]);
+#pragma unroll
+            for (int i = 1; i < NEN; i++) { lx = __dadd_rn(lx, __dmul_rn(X[i], tg.N[q][i])); ly = __dadd_rn(ly, __dmul_rn(Y[i], tg.N[q][i])); }
+            reinterpret_cast<double2 *>(out)[e * NQ + q] = make_double2(lx, ly);
+        }
+    }
+}
+
+struct ErrComp { const int32_t *dof; int ncs, comp; };
+
+// one thread per element: sum over its quadrature points of JxW * sum_c (field_c - truth_c)^2, in the reference's
+// operation order; the element sums are then added by a fixed-shape tree (cub::DeviceReduce), so the result is
+// reproducible run to run and agrees with the CPU loop's single running sum to rounding (tests: 1e-12 relative)
+template <int NEN, int NQ, int NC>
+__global__ void __launch_bounds__(256) k_l2_error_elem(const int32_t *__restrict__ conn, const double2 *__restrict__ xy, int64_t nel, ErrComp c0, ErrComp c1,
+                                                       const double *__restrict__ U, int64_t nU, const double *__restrict__ truth,
+                                                       double *__restrict__ eout, int *__restrict__ err)
+{
+    const QTab &tg = c_tab[kind_slot(NEN)];
+    GRID_STRIDE(e, nel) {
+        double X[NEN], Y[NEN], v0[NEN], v1[NEN];
+#pragma unroll
+        for (int a = 0; a < NEN; a++) {
+            const int32_t n = conn[e * NEN + a];
+            const double2 p = __ldg(&xy[n]);
+            X[a] = p.x; Y[a] = p.y;
+            const int32_t d0 = c0.dof[(int64_t)n * c0.ncs + c0.comp];
+            const int32_t d1 = NC > 1 ? c1.dof[(int64_t)n * c1.ncs + c1.comp] : 0;
+            if (d0 < 0 || d0 >= nU || d1 < 0 || d1 >= nU) { *err = 1; v0[a] = v1[a] = 0.0; continue; }
+            v0[a] = U[d0];
+            v1[a] = NC > 1 ? U[d1] : 0.0;
+        }
+        double acc = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            double J00 = __dmul_rn(X[0], tg.gp[q][0][0]), J01 = __dmul_rn(X[0], tg.gp[q][0][1]);
+            double J10 = __dmul_rn(Y[0], tg.gp[q][0][0]), J11 = __dmul_rn(Y[0], tg.gp[q][0][1]);
+#pragma unroll
+            for (int n = 1; n < NEN; n++) {
+                J00 = __dadd_rn(J00, __dmul_rn(X[n], tg.gp[q][n][0])); J01 = __dadd_rn(J01, __dmul_rn(X[n], tg.gp[q][n][1]));
+                J10 = __dadd_rn(J10, __dmul_rn(Y[n], tg.gp[q][n][0])); J11 = __dadd_rn(J11, __dmul_rn(Y[n], tg.gp[q][n][1]));
+            }
+            const double JxW = __dmul_rn(__dsub_rn(__dmul_rn(J00, J11), __dmul_rn(J10, J01)), tg.w[q]);
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < NEN; j++) {
+                a0 = __dadd_rn(a0, __dmul_rn(v0[j], tg.N[q][j]));
+                if (NC > 1) a1 = __dadd_rn(a1, __dmul_rn(v1[j], tg.N[q][j]));
+            }
+            const double *t = truth + (e * NQ + q) * NC;
+            const double d0 = __dsub_rn(a0, t[0]);
+            double sq = __dmul_rn(d0, d0);
+            if (NC > 1) { const double d1 = __dsub_rn(a1, t[1]); sq = __dadd_rn(sq, __dmul_rn(d1, d1)); }
+            acc = __dadd_rn(acc, __dmul_rn(JxW, sq));
+        }
+        eout[e] = acc;
+    }
+}
+
+template <int NEN, int NQ> static void vec_locations(efg_ctx *ctx, const MeshDev &m, double *out)
+{
+    LAUNCH(ctx, (k_qp_locations<NEN, NQ>), grid_for(m.nel, 256), 256, 0, m.conn.p, m.xy.p, m.nel, out);
+}
+template <int NEN, int NQ> static void vec_l2_elem(efg_ctx *ctx, const MeshDev &m, int nc, ErrComp c0, ErrComp c1, const double *U, int64_t nU,
+                                                   const double *truth, double *eout, int *err)
+{
+    if (nc == 1) LAUNCH(ctx, (k_l2_error_elem<NEN, NQ, 1>), grid_for(m.nel, 256), 256, 0, m.conn.p, m.xy.p, m.nel, c0, c1, U, nU, truth, eout, err);
+    else LAUNCH(ctx, (k_l2_error_elem<NEN, NQ, 2>), grid_for(m.nel, 256), 256, 0, m.conn.p, m.xy.p, m.nel, c0, c1, U, nU, truth, eout, err);
+}
+// (element kind, number of quadrature points) -> instantiation
+template <class Fn> static bool vec_dispatch_kq(int kind, int npts, Fn &&fn)
+{
+    switch (kind * 100 + npts) {
+    case 301: fn(std::integral_constant<int, 3>{}, std::integral_constant<int, 1>{}); return true;
+    case 303: fn(std::integral_constant<int, 3>{}, std::integral_constant<int, 3>{}); return true;
+    case 601: fn(std::integral_constant<int, 6>{}, std::integral_constant<int, 1>{}); return true;
+    case 603: fn(std::integral_constant<int, 6>{}, std::integral_constant<int, 3>{}); return true;
+    case 401: fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{}); return true;
+    case 404: fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{}); return true;
+    case 409: fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 9>{}); return true;
+    }
+    return false;
 }

@@ -657,4 +657,71 @@ int efg_fetch_block(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzva
     API_END(ctx)
 }
 
+// ---- location(el, qp) and the evaluate_*_error integrators -------------------------------
+int efg_qp_locations(efg_ctx *ctx, int mesh_slot, int quad, double *out, int64_t *npts_out)
+{
+    API_BEGIN(ctx)
+    if (mesh_slot < 0 || mesh_slot > 1 || ctx->mesh[mesh_slot].kind == 0) efg_throw(EFG_ERR_STATE, "mesh %d not set", mesh_slot);
+    const MeshDev &m = ctx->mesh[mesh_slot];
+    const int npts = upload_tables(ctx, m.kind, quad);
+    if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, m.kind);
+    if (npts_out) *npts_out = npts;
+    if (out && m.nel > 0) {
+        const size_t n = (size_t)m.nel * npts * 2;
+        DevBuf<double> stage;
+        double *d = out;
+        if (!is_device_ptr(out)) { stage.alloc(ctx->pool, n); d = stage.p; }
+        if (!vec_dispatch_kq(m.kind, npts, [&](auto K, auto Q) { vec_locations<decltype(K)::value, decltype(Q)::value>(ctx, m, d); }))
+            efg_throw(EFG_ERR_INVALID, "no location kernel for element kind %d with %d points", m.kind, npts);
+        if (d != out) CUDA_CHECK(cudaMemcpyAsync(out, d, n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    API_END(ctx)
+}
+
+int efg_l2_error(efg_ctx *ctx, int ncomp, const int *space_slots, const int *comps, int quad, const double *U, int64_t nU,
+                 const double *truth, double *out)
+{
+    API_BEGIN(ctx)
+    if (ncomp < 1 || ncomp > 2 || !space_slots || !comps || !U || !truth || !out || nU < 0) efg_throw(EFG_ERR_INVALID, "bad efg_l2_error arguments");
+    ErrComp ec[2];
+    int mslot = -1;
+    for (int c = 0; c < ncomp; c++) {
+        if (space_slots[c] < 0 || space_slots[c] > 2 || ctx->space[space_slots[c]].mesh < 0) efg_throw(EFG_ERR_STATE, "space %d not set", space_slots[c]);
+        const SpaceDev &sp = ctx->space[space_slots[c]];
+        if (comps[c] < 0 || comps[c] >= sp.ncomp) efg_throw(EFG_ERR_INVALID, "space %d has no component %d", space_slots[c], comps[c]);
+        if (mslot >= 0 && sp.mesh != mslot) efg_throw(EFG_ERR_INVALID, "the components of one error integral must live on the same mesh");
+        mslot = sp.mesh;
+        ec[c] = ErrComp{sp.dof.p, sp.ncomp, comps[c]};
+    }
+    if (ncomp == 1) ec[1] = ec[0];
+    const MeshDev &m = ctx->mesh[mslot];
+    if (m.kind == 0) efg_throw(EFG_ERR_STATE, "mesh %d not set", mslot);
+    const int npts = upload_tables(ctx, m.kind, quad);
+    if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, m.kind);
+    const size_t nt = (size_t)m.nel * npts * ncomp;
+    DevBuf<double> us, ts, eout, sum;
+    DevBuf<int> err;
+    const double *Ud = U, *Td = truth;
+    if (!is_device_ptr(U)) { us.alloc(ctx->pool, (size_t)nU + 1); CUDA_CHECK(cudaMemcpyAsync(us.p, U, (size_t)nU * sizeof(double), cudaMemcpyDefault, ctx->stream)); Ud = us.p; }
+    if (!is_device_ptr(truth)) { ts.alloc(ctx->pool, nt + 1); CUDA_CHECK(cudaMemcpyAsync(ts.p, truth, nt * sizeof(double), cudaMemcpyDefault, ctx->stream)); Td = ts.p; }
+    eout.alloc(ctx->pool, (size_t)m.nel + 1); sum.alloc(ctx->pool, 1); err.alloc(ctx->pool, 1);
+    CUDA_CHECK(cudaMemsetAsync(err.p, 0, sizeof(int), ctx->stream));
+    if (!vec_dispatch_kq(m.kind, npts, [&](auto K, auto Q) {
+            vec_l2_elem<decltype(K)::value, decltype(Q)::value>(ctx, m, ncomp, ec[0], ec[1], Ud, nU, Td, eout.p, err.p); }))
+        efg_throw(EFG_ERR_INVALID, "no error integrator for element kind %d with %d points", m.kind, npts);
+    {
+        size_t tb = 0;
+        cub::DeviceReduce::Sum(nullptr, tb, eout.p, sum.p, m.nel, ctx->stream);
+        DevBuf<char> tmp;
+        tmp.alloc(ctx->pool, tb);
+        CUDA_CHECK(cub::DeviceReduce::Sum(tmp.p, tb, eout.p, sum.p, m.nel, ctx->stream));
+        ctx->launches += 2;
+    }
+    if (tl_read(ctx, err.p)) efg_throw(EFG_ERR_INDEX, "BoundsError: a dof number is < 1 or exceeds the length of U");
+    const double E = tl_read(ctx, sum.p);
+    *out = sqrt(E);
+    API_END(ctx)
+}
+
 } // extern "C"

@@ -23,6 +23,9 @@
  *                                                                        src/Assemblers.jl:196-223, src/LocalAssemblers.jl:95-152,
  *                                                                        examples/heat/poisson/t3.jl:44-61, q4.jl:34-51
  *   efg_fetch_vec             finish!(av)                                src/Assemblers.jl:230-232
+ *   efg_qp_locations          location(el, qp) for every element / quadrature point   src/FEIterators.jl:227-235
+ *   efg_l2_error              evaluate_pressure_error / evaluate_velocity_error      examples/stokes/colliding_flow/ht_p2_p1.jl:120-178,
+ *                                                                        ht_p2_p1_gen.jl:124-153, test/test_stokes.jl:438-496
  *   efg_spmv                  `KT = K * T` right after assembly          examples/heat/poisson/t3.jl:78
  *   efg_block_nnz/_fetch_block  `K[1:nu, 1:nu]`, `K[1:nu, nu+1:end]`     examples/heat/poisson/t3.jl:79,
  *                                                                        examples/stokes/colliding_flow/ht_p2_p1_gen.jl (solve!)
@@ -171,6 +174,20 @@ int efg_spmv(efg_ctx *ctx, const double *x, double *y);
  * nzval.  Any pointer may be NULL. */
 int efg_block_nnz(efg_ctx *ctx, int64_t row_first, int64_t row_last, int64_t col_first, int64_t col_last, int64_t *nnz_out);
 int efg_fetch_block(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval);
+
+/* Post-processing integrators of the Stokes examples.  The true-solution closures (truep, trueux, trueuy) stay on the
+ * caller's side: efg_qp_locations returns location(el, qp) for every element and quadrature point of a mesh
+ * (out: 2 x npts x nel doubles, point q of element e at out[(e*npts + q)*2]; out may be NULL to query npts), the caller
+ * evaluates its functions there, and efg_l2_error integrates
+ *     sqrt( sum_el sum_qp JxW * sum_c ( sum_j U[eldofs_c[j]] * N_j(qp)  -  truth[(e*npts + q)*ncomp + c] )^2 )
+ * for ncomp = 1 or 2 field components given as (space_slot, component) pairs on one mesh -- evaluate_pressure_error:
+ * {(p, 0)}; evaluate_velocity_error: {(ux, 0), (uy, 0)} or {(u, 0), (u, 1)}.  U is the system vector (what solve!
+ * returns; eldofvals(el) = U[eldofs(el)] after scattersysvec!), nU its length.  Per-element sums follow the reference's
+ * operation order; they are added by a fixed-shape tree, so the value is reproducible and equals the CPU loop's running
+ * sum to rounding (1e-12 relative in the tests). */
+int efg_qp_locations(efg_ctx *ctx, int mesh_slot, int quad_rule, double *out, int64_t *npts_out);
+int efg_l2_error(efg_ctx *ctx, int ncomp, const int *space_slots, const int *comps, int quad_rule, const double *U, int64_t nU,
+                 const double *truth, double *out);
 
 /* library / build information, e.g. "elfelgpu 0.1 sm_100a" */
 const char *efg_version(void);

@@ -159,4 +159,30 @@ function block(a::SysmatAssemblerGPU, rows::UnitRange{Int}, cols::UnitRange{Int}
     return SparseMatrixCSC(length(rows), length(cols), colptr, rowval, nzval)
 end
 
+# ---- post-processing integrators (examples/stokes/colliding_flow/ht_p2_p1.jl:120-178) -------------------------
+"""
+    evaluate_error(am, elits, qpit, U, truefs)
+
+`sqrt(sum_el sum_qp JxW * sum_c (u_c(qp) - truef_c(location(el, qp)...))^2)`: evaluate_pressure_error /
+evaluate_velocity_error with the element loop on the device.  `elits`: one FEIterator per field component (the
+same iterator twice for the two components of a vector space), all of them among the iterators of the last
+`assemble!(am, ...)` call (`slots` gives their space slots there); `truefs`: one function per component.
+"""
+function evaluate_error(a::SysmatAssemblerGPU, slots::NTuple{N,Tuple{Int,Int}}, mesh_slot::Int, nel::Int, quad::Int,
+                        U::Vector{Float64}, truefs::NTuple{N,Function}) where {N}
+    np = Ref{Int64}(0)
+    _check(a, ccall((:efg_qp_locations, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ref{Int64}), a.ctx, mesh_slot, quad, C_NULL, np))
+    loc = Array{Float64}(undef, 2, np[], nel)
+    _check(a, ccall((:efg_qp_locations, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ref{Int64}), a.ctx, mesh_slot, quad, loc, np))
+    truth = Array{Float64}(undef, N, np[], nel)
+    for c in 1:N
+        truth[c, :, :] .= truefs[c].(view(loc, 1, :, :), view(loc, 2, :, :))
+    end
+    ss = Cint[s[1] for s in slots]; cc = Cint[s[2] for s in slots]
+    out = Ref{Float64}(0.0)
+    _check(a, ccall((:efg_l2_error, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cint}, Ptr{Cint}, Cint, Ptr{Float64}, Int64, Ptr{Float64}, Ref{Float64}),
+                    a.ctx, N, ss, cc, quad, U, length(U), truth, out))
+    return out[]
+end
+
 end # module

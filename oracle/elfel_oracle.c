@@ -575,3 +575,63 @@ void efo_spmv_csc(int64_t nrow, int64_t ncol, const int64_t *colptr, const int64
         for (int64_t p = colptr[k] - 1; p < colptr[k + 1] - 1; p++) y[rowval[p] - 1] = y[rowval[p] - 1] + nzval[p] * xk;
     }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Post-processing integrators: location() and the evaluate_*_error loops.
+ *   location(el, qp)   src/FEIterators.jl:227-235   loc = x_1*N_1, then loc += x_i*N_i in node order
+ *   evaluate_pressure_error / evaluate_velocity_error
+ *                      examples/stokes/colliding_flow/ht_p2_p1.jl:120-178, ht_p2_p1_gen.jl:124-153,
+ *                      test/test_stokes.jl:438-496:
+ *       for el, for qp:  JxW = J*weight;  a_c = 0.0; for j: a_c += dofvals_c[j]*N[j];
+ *                        E += JxW * ((a_1 - t_1)^2 [+ (a_2 - t_2)^2]);     return sqrt(E)
+ * The true-solution closures are evaluated by the caller at the locations: `truth` is ncomp x npts x nel
+ * (component c of point q of element e at truth[(e*npts + q)*ncomp + c]).  eldofvals(el) are read
+ * from the system vector U through the dof numbers (what scattersysvec! put into the fields).
+ * ------------------------------------------------------------------------------------------ */
+int64_t efo_qp_locations(int quad, int64_t nel, const int64_t *conn, int kind, const double *xy, double *out)
+{
+    qptab vq;
+    if (qptab_init(&vq, kind, quad) < 0) return -1;
+    for (int64_t e = 0; e < nel; e++) {
+        const int64_t *nodes = conn + e * kind;
+        for (int q = 0; q < vq.npts; q++) {
+            const double *x = xy + 2 * (nodes[0] - 1);
+            double lx = x[0] * vq.N[q][0], ly = x[1] * vq.N[q][0];
+            for (int i = 1; i < kind; i++) {
+                x = xy + 2 * (nodes[i] - 1);
+                lx = lx + x[0] * vq.N[q][i]; ly = ly + x[1] * vq.N[q][i];
+            }
+            out[(e * vq.npts + q) * 2] = lx; out[(e * vq.npts + q) * 2 + 1] = ly;
+        }
+    }
+    return vq.npts;
+}
+
+/* dof[c] : dofnums array (ncomp_c x nnodes) of the space of component c, comp[c] its component (0-based),
+ * ncs[c] the number of components of that space.  Returns sqrt(E), or -1.0 for an unavailable rule. */
+double efo_l2_error(int quad, int64_t nel, const int64_t *conn, int kind, const double *xy, int ncomp,
+                    const int64_t *dof0, int ncs0, int comp0, const int64_t *dof1, int ncs1, int comp1,
+                    const double *U, const double *truth)
+{
+    qptab vq;
+    if (qptab_init(&vq, kind, quad) < 0) return -1.0;
+    double J[2][2];
+    double E = 0.0;
+    for (int64_t e = 0; e < nel; e++) {
+        const int64_t *nodes = conn + e * kind;
+        for (int q = 0; q < vq.npts; q++) {
+            double Jd = jacjac(xy, nodes, kind, vq.gp[q], J);
+            double JxW = Jd * vq.w[q];
+            double a0 = 0.0, a1 = 0.0;
+            for (int j = 0; j < kind; j++) {
+                a0 = a0 + U[dof0[(nodes[j] - 1) * ncs0 + comp0] - 1] * vq.N[q][j];
+                if (ncomp > 1) a1 = a1 + U[dof1[(nodes[j] - 1) * ncs1 + comp1] - 1] * vq.N[q][j];
+            }
+            const double *t = truth + (e * vq.npts + q) * ncomp;
+            double d0 = a0 - t[0];
+            if (ncomp > 1) { double d1 = a1 - t[1]; E = E + JxW * (d0 * d0 + d1 * d1); }
+            else E = E + JxW * (d0 * d0);
+        }
+    }
+    return sqrt(E);
+}

@@ -50,6 +50,11 @@ def lib():
         L.efo_assemble_vec_heat.restype = C.c_int64
         L.efo_spmv_csc.argtypes = [C.c_int64, C.c_int64, i64p, i64p, f64p, f64p, f64p]
         L.efo_spmv_csc.restype = None
+        L.efo_qp_locations.argtypes = [C.c_int, C.c_int64, i64p, C.c_int, f64p, f64p]
+        L.efo_qp_locations.restype = C.c_int64
+        L.efo_l2_error.argtypes = [C.c_int, C.c_int64, i64p, C.c_int, f64p, C.c_int, i64p, C.c_int, C.c_int,
+                                   i64p, C.c_int, C.c_int, f64p, f64p]
+        L.efo_l2_error.restype = C.c_double
         _lib = L
     return _lib
 
@@ -164,3 +169,34 @@ def spmv_csc(nrow, ncol, colptr, rowval, nzval, x):
     lib().efo_spmv_csc(nrow, ncol, _p(colptr, C.c_int64), _p(rowval, C.c_int64), _p(nzval, C.c_double),
                        _p(x, C.c_double), _p(y, C.c_double))
     return y
+
+
+def qp_locations(quad, mesh):
+    """location(el, qp) for every element / quadrature point -> (nel, npts, 2)."""
+    conn = _c(mesh.conn, np.int64); xy = _c(mesh.xy, np.float64)
+    out = np.empty((conn.shape[0], MAXQP_, 2))
+    n = lib().efo_qp_locations(quad, conn.shape[0], _p(conn, C.c_int64), mesh.kind, _p(xy, C.c_double), _p(out, C.c_double))
+    if n < 0:
+        raise ValueError("quadrature rule not available")
+    return out.reshape(-1)[:conn.shape[0] * n * 2].reshape(conn.shape[0], n, 2).copy()
+
+
+MAXQP_ = 25
+
+
+def l2_error(quad, mesh, comps, U, truth):
+    """evaluate_*_error: comps = [(dofnums, comp0based), ...] (1 or 2 entries, all on `mesh`), U the system vector,
+    truth (nel, npts, ncomp) the true solution at the quadrature-point locations -> sqrt(E)."""
+    conn = _c(mesh.conn, np.int64); xy = _c(mesh.xy, np.float64)
+    d = [_c(c[0], np.int64) for c in comps]
+    ncs = [x.shape[1] for x in d]
+    cc = [int(c[1]) for c in comps]
+    if len(d) == 1:
+        d.append(d[0]); ncs.append(ncs[0]); cc.append(cc[0])
+    U = _c(U, np.float64); truth = _c(truth, np.float64)
+    r = lib().efo_l2_error(quad, conn.shape[0], _p(conn, C.c_int64), mesh.kind, _p(xy, C.c_double), len(comps),
+                           _p(d[0], C.c_int64), ncs[0], cc[0], _p(d[1], C.c_int64), ncs[1], cc[1],
+                           _p(U, C.c_double), _p(truth, C.c_double))
+    if r < 0:
+        raise ValueError("quadrature rule not available")
+    return r

@@ -7,7 +7,7 @@ import pytest
 
 import elfel_jl_b200 as efg
 from elfel_jl_b200 import _lib
-from test_oracle_golden import _run_stokes, _csc, _solve
+from test_oracle_golden import _run_stokes, _csc, _solve, _oracle_errors, _truep, _trueux, _trueuy
 
 pytestmark = pytest.mark.gpu
 
@@ -22,22 +22,41 @@ def _gpu_assemble(form_id, spaces, params, tndof):
     efg.start(ass, tndof, tndof)
     efg.assemble(ass, form, elits, qpits)
     K = efg.finish(ass)
+    _LAST.update(ass=ass, elits=elits, qpits=qpits)
     return K.colptr, K.rowval, K.nzval
+
+
+_LAST = {}
+
+
+def _gpu_errors(oracle, vmesh, pmesh, spaces, Uv, three_spaces):
+    """evaluate_pressure_error / evaluate_velocity_error on the device (efg_qp_locations + efg_l2_error), checked
+    against the oracle's restatement: locations bit-identical, error norms to 1e-12 relative."""
+    ass, elits, qpits = _LAST["ass"], _LAST["elits"], _LAST["qpits"]
+    ep = efg.evaluate_error(ass, elits[-1], qpits[-1], Uv, _truep)
+    uel = (elits[0], elits[1]) if three_spaces else (elits[0], elits[0])
+    ev = efg.evaluate_error(ass, uel, qpits[0], Uv, (_trueux, _trueuy))
+    oep, oev = _oracle_errors(oracle, vmesh, pmesh, spaces, Uv, three_spaces)
+    assert abs(ep - oep) <= 1e-12 * abs(oep) and abs(ev - oev) <= 1e-12 * abs(oev)
+    eng = ass.engine
+    assert np.array_equal(eng.qp_locations(0, 3, vmesh.conn.shape[0]), oracle.qp_locations(3, vmesh))
+    assert np.array_equal(eng.qp_locations(1, 3, pmesh.conn.shape[0]), oracle.qp_locations(3, pmesh))
+    return ep, ev
 
 
 def test_stokes_reddy_goldens_gpu(oracle):
     ref = [(3.5171450671095306, 0.2968271617227661), (0.5999467323539439, 0.03781189670123018),
            (0.12350320261417459, 0.004741849976722882)]
     for N, r in zip((4, 8, 16), ref):
-        ep, ev, *_ = _run_stokes(oracle, oracle.FORM_STOKES_REDDY, N, True, assemble=_gpu_assemble)
+        ep, ev, *_ = _run_stokes(oracle, oracle.FORM_STOKES_REDDY, N, True, assemble=_gpu_assemble, errors=_gpu_errors)
         assert np.allclose([ep, ev], r, rtol=1e-9, atol=0)
 
 
 def test_stokes_veclap_alt_and_gen_goldens_gpu(oracle):
-    ep, ev, _, _, nnz = _run_stokes(oracle, oracle.FORM_STOKES_VECLAP_ALT, 4, False, assemble=_gpu_assemble)
+    ep, ev, _, _, nnz = _run_stokes(oracle, oracle.FORM_STOKES_VECLAP_ALT, 4, False, assemble=_gpu_assemble, errors=_gpu_errors)
     assert np.allclose([ep, ev], [2.596076907594511, 0.3001331486426876], rtol=1e-9, atol=0)
     assert nnz == 260 * 16 + 104 * 4 + 8
-    ep, ev, *_ = _run_stokes(oracle, oracle.FORM_STOKES_GEN, 4, False, assemble=_gpu_assemble)
+    ep, ev, *_ = _run_stokes(oracle, oracle.FORM_STOKES_GEN, 4, False, assemble=_gpu_assemble, errors=_gpu_errors)
     assert np.allclose([ep, ev], (3.5171450671095306, 0.2968271617227661), rtol=1e-9, atol=0)
 
 
@@ -65,3 +84,31 @@ def test_heat_t3_n4_golden_solution_gpu():
            2.0625, 2.1875, 2.375, 2.6875, 1.0, 1.0625, 1.25, 1.5625, 2.0, 1.125, 2.125, 1.5, 2.5,
            2.125, 3.125, 3.0, 3.0625, 3.25, 3.5625, 4.0]
     assert np.allclose(T, ref, rtol=0, atol=1e-13)
+
+
+def test_error_integrator_other_elements_and_errors(oracle):
+    """Q4 / T3 / T6 scalar fields with their own rules, a jittered mesh, a device-resident U; argument errors."""
+    import torch
+    rng = np.random.default_rng(5)
+    f = lambda x, y: np.sin(3 * x) * np.cos(2 * y)
+    for kind, N, quad in ((efg.Q4, 23, None), (efg.T3, 31, 3), (efg.T6, 17, None), (efg.T3, 12, None)):
+        prob = efg.heat_problem(kind, N, perturb=True, quad=quad)
+        eng = efg.Engine(0)
+        efg.load_problem(eng, prob)
+        U = rng.standard_normal(prob.ndofs)
+        loc = eng.qp_locations(0, prob.quad, prob.nel)
+        oloc = oracle.qp_locations(prob.quad, prob.meshes[0])
+        assert np.array_equal(loc, oloc)
+        truth = f(loc[..., 0], loc[..., 1])[..., None]
+        want = oracle.l2_error(prob.quad, prob.meshes[0], [(prob.spaces[0].field.dofnums, 0)], U, truth)
+        got = eng.l2_error([(0, 0)], prob.quad, U, truth)
+        assert abs(got - want) <= 1e-12 * want
+        got_d = eng.l2_error([(0, 0)], prob.quad, torch.from_numpy(U).cuda(), torch.from_numpy(np.ascontiguousarray(truth)).cuda())
+        assert got_d == got                                  # same bits: fixed-shape reduction
+        with pytest.raises(_lib.ArgumentError):              # U shorter than the dof numbers
+            eng.l2_error([(0, 0)], prob.quad, U[: prob.ndofs // 2], truth)
+        with pytest.raises(_lib.EfgError):
+            eng.l2_error([(0, 1)], prob.quad, U, truth)      # component 1 of a scalar space
+        with pytest.raises(_lib.EfgError):
+            eng.l2_error([(2, 0)], prob.quad, U, truth)      # space slot never set
+        eng.close()

@@ -321,7 +321,7 @@ def _errors(oracle, vmesh, pmesh, ux, uy, p):
     return np.sqrt(Ep), np.sqrt(Ev)
 
 
-def _run_stokes(oracle, form, N, three_spaces, assemble=None):
+def _run_stokes(oracle, form, N, three_spaces, assemble=None, errors=None):
     vmesh, pmesh = _stokes_meshes(N)
     if three_spaces:
         U = [efg.FESpace(vmesh, efg.FEH1_T6(), 1), efg.FESpace(vmesh, efg.FEH1_T6(), 1)]
@@ -347,8 +347,23 @@ def _run_stokes(oracle, form, N, three_spaces, assemble=None):
         ux, uy = U[0].field.dofvals[:, 0], U[1].field.dofvals[:, 0]
     else:
         ux, uy = U[0].field.dofvals[:, 0], U[0].field.dofvals[:, 1]
-    ep, ev = _errors(oracle, vmesh, pmesh, ux, uy, Ph.field.dofvals[:, 0])
+    ep_np, ev_np = _errors(oracle, vmesh, pmesh, ux, uy, Ph.field.dofvals[:, 0])
+    # the restated evaluate_pressure_error / evaluate_velocity_error (oracle C, or the GPU through `errors`): eldofvals
+    # come from the system vector through the dof numbers, the true solution is evaluated at location(el, qp)
+    ep, ev = (errors or _oracle_errors)(oracle, vmesh, pmesh, spaces, Uv, three_spaces)
+    assert np.allclose([ep, ev], [ep_np, ev_np], rtol=1e-11, atol=0)     # independent vectorised numpy evaluation
     return ep, ev, tndof, tnunk, len(rowval)
+
+
+def _oracle_errors(oracle, vmesh, pmesh, spaces, Uv, three_spaces):
+    lp = oracle.qp_locations(3, pmesh)
+    ep = oracle.l2_error(3, pmesh, [(spaces[-1].field.dofnums, 0)], Uv, _truep(lp[..., 0], lp[..., 1])[..., None])
+    lv = oracle.qp_locations(3, vmesh)
+    truth = np.stack([_trueux(lv[..., 0], lv[..., 1]), _trueuy(lv[..., 0], lv[..., 1])], axis=-1)
+    comps = ([(spaces[0].field.dofnums, 0), (spaces[1].field.dofnums, 0)] if three_spaces
+             else [(spaces[0].field.dofnums, 0), (spaces[0].field.dofnums, 1)])
+    ev = oracle.l2_error(3, vmesh, comps, Uv, truth)
+    return ep, ev
 
 
 def test_stokes_reddy_goldens(oracle):
