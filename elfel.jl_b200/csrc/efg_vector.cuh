@@ -179,6 +179,21 @@ __global__ void k_spmv_rows(const int64_t *__restrict__ rowptr, const uint32_t *
     }
 }
 
+// Heat forms: K is BITWISE symmetric (the element matrix is built from its upper triangle and both (r,c) and (c,r) sum
+// the same element contributions in the same order), so row r of K is column r of the CSC arrays read in place:
+// ascending rows of the column = ascending columns of the row = SparseArrays' accumulation order, with contiguous
+// reads and no row-major view at all.
+__global__ void k_spmv_cols_sym(const int64_t *__restrict__ colptr, const int32_t *__restrict__ rowval, const double *__restrict__ nzval,
+                                const double *__restrict__ x, int64_t n, double *__restrict__ y)
+{
+    GRID_STRIDE(c, n) {
+        double acc = 0.0;
+        const int64_t p1 = colptr[c + 1] - 1;
+        for (int64_t p = colptr[c] - 1; p < p1; p++) acc = __dadd_rn(acc, __dmul_rn(nzval[p], __ldg(&x[rowval[p]])));
+        y[c] = acc;
+    }
+}
+
 static void vec_build_csr(efg_ctx *ctx, VecData *vd)
 {
     const int64_t nnz = ctx->nnz, nrow = ctx->nrow, ncl = ctx->ncl;

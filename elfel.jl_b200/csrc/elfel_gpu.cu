@@ -585,7 +585,8 @@ int efg_spmv(efg_ctx *ctx, const double *x, double *y)
     if (ctx->have_range) efg_throw(EFG_ERR_STATE, "efg_spmv needs the whole matrix on this ctx (no column range)");
     if (!x || !y) efg_throw(EFG_ERR_INVALID, "null vector");
     VecData *vd = vec_get(ctx);
-    if (!vd->have_csr) vec_build_csr(ctx, vd);
+    const bool sym = ctx->form == EFG_FORM_HEAT && ctx->nrow == ctx->ncol;     // bitwise-symmetric K: columns are rows
+    if (!sym && !vd->have_csr) vec_build_csr(ctx, vd);
     DevBuf<double> xs, ys;
     const double *xd = x;
     double *yd = y;
@@ -596,7 +597,8 @@ int efg_spmv(efg_ctx *ctx, const double *x, double *y)
     }
     if (!is_device_ptr(y)) { ys.alloc(ctx->pool, (size_t)ctx->nrow + 1); yd = ys.p; }
     CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-    LAUNCH(ctx, k_spmv_rows, grid_for(ctx->nrow, 256, (int64_t)148 * 32), 256, 0, vd->rowptr.p, vd->tperm.p, vd->tcol.p, ctx->nzval.p, xd, ctx->nrow, yd);
+    if (sym) LAUNCH(ctx, k_spmv_cols_sym, grid_for(ctx->nrow, 256, (int64_t)148 * 32), 256, 0, ctx->colptr.p, ctx->rowval.p, ctx->nzval.p, xd, ctx->nrow, yd);
+    else LAUNCH(ctx, k_spmv_rows, grid_for(ctx->nrow, 256, (int64_t)148 * 32), 256, 0, vd->rowptr.p, vd->tperm.p, vd->tcol.p, ctx->nzval.p, xd, ctx->nrow, yd);
     CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (yd != y) CUDA_CHECK(cudaMemcpyAsync(y, yd, (size_t)ctx->nrow * sizeof(double), cudaMemcpyDefault, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

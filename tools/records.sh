@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-1 records with the final kernel: per-workload bench lines (N=1) + ncu full of the heat T6 and elasticity kernels
+# round records: per-workload bench lines (N=1), launch list and ncu --set full captures -> gpurun_out/ (copy what is to be kept into profiles/)
 mkdir -p gpurun_out
 python bench.py > gpurun_out/r1_bench_heat_t6_n1.json 2> gpurun_out/s12_err.log; echo "bench rc=$?"
 for wl in elasticity_t6 stokes_gen heat_q4; do python bench.py --workload $wl --no-e2e --no-cpu > gpurun_out/r1_bench_${wl}_n1.json 2>> gpurun_out/s12_err.log; done
