@@ -224,3 +224,16 @@ def merge_blocks(ncol, blocks):
             nzval[ga: ga + (b - a)] = nz[a:b]
             lc += k
     return gcolptr, rowval, nzval
+
+
+def merge_vectors(n, blocks):
+    """Scatter per-rank system-vector blocks [(firsts, lasts, values of the owned rows, ascending), ...] into the global
+    vector of length n (owner-computes: every row is owned by exactly one rank, so no reduction is needed)."""
+    out = np.empty(n, dtype=np.float64)
+    for firsts, lasts, vals in blocks:
+        o = 0
+        for f, l in zip(firsts, lasts):
+            k = l - f + 1
+            out[f - 1: l] = vals[o: o + k]
+            o += k
+    return out

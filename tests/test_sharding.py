@@ -73,6 +73,24 @@ def test_shards_merge_to_global_matrix(oracle, workload, n, world):
     assert nz.tobytes() == gnz.tobytes()       # halo elements replicated => identical sums, bit for bit
 
 
+@pytest.mark.parametrize("workload,n,world", [("heat_t6", 5, 3), ("heat_q4", 6, 2), ("heat_t3", 4, 4)])
+def test_sharded_load_vectors_merge_to_global_vector(oracle, workload, n, world):
+    """System-vector assembly shards by the same owned ranges as the matrix columns: every rank sums the contributions of
+    its sub-mesh (halo elements replicated) into its owned rows; the blocks scatter into the global vector bit for bit."""
+    kind, conn, xy, dofnums, band, form, quad = sh.build_global(workload, n, world, "cpu")
+    gmesh = efg.Mesh(kind, conn.numpy(), xy.numpy())
+    nd = dofnums.numel()
+    want = oracle.assemble_vec_heat(quad, gmesh, dofnums.numpy(), -6.0, nd)
+    blocks = []
+    for r in range(world):
+        s, (firsts, lasts), _ = sh.shard_problem(efg, workload, n, r, world, dev="cpu")
+        mesh = efg.Mesh(s.meshes[0].kind, s.meshes[0].conn.numpy(), s.meshes[0].xy.numpy())
+        full = oracle.assemble_vec_heat(s.quad, mesh, s.spaces[0].field.dofnums.numpy(), -6.0, s.ndofs)
+        rows = np.concatenate([np.arange(f, l + 1) for f, l in zip(firsts, lasts)])
+        blocks.append((firsts, lasts, full[rows - 1]))
+    assert sh.merge_vectors(nd, blocks).tobytes() == want.tobytes()
+
+
 def test_world2_gloo(tmp_path):
     """Two processes over gloo: each assembles its shard (oracle stand-in), nnz and a checksum are reduced."""
     script = tmp_path / "w2.py"
