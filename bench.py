@@ -379,7 +379,8 @@ def main():
         "config": {"workload": f"{WORKLOADS[args.workload][1]}, N={n}" + (f", columns split over {world} ranks" if world > 1 else ""),
                    "elements": int(nel_global), "ndofs": int(prob.ndofs), "nnz": int(nnz_global), "l2": "inputs larger than L2",
                    "path": {1: "two-pass", 2: "tiled-fused"}[path], "strict_fp": args.strict,
-                   "tile_elems": int(eng.stat(_lib.STAT_TILE_ELEMS) and args.tile_elems), "sfc_order": args.sfc,
+                   "tile_elems": int(args.tile_elems) or -(-int(prob.meshes[0].nel_) // max(int(eng.stat(_lib.STAT_NTILES)), 1)),
+                   "tile_elems_source": "option" if args.tile_elems else "automatic (largest size with two CTAs per SM)", "sfc_order": args.sfc,
                    "tiles": int(eng.stat(_lib.STAT_NTILES)),
                    "halo_factor": eng.stat(_lib.STAT_TILE_ELEMS) / max(prob.meshes[0].nel_, 1),
                    "rank_elements_incl_shard_halo": int(prob.meshes[0].nel_)},

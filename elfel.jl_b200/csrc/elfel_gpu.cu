@@ -585,7 +585,8 @@ int efg_spmv(efg_ctx *ctx, const double *x, double *y)
     if (ctx->have_range) efg_throw(EFG_ERR_STATE, "efg_spmv needs the whole matrix on this ctx (no column range)");
     if (!x || !y) efg_throw(EFG_ERR_INVALID, "null vector");
     VecData *vd = vec_get(ctx);
-    const bool sym = ctx->form == EFG_FORM_HEAT && ctx->nrow == ctx->ncol;     // bitwise-symmetric K: columns are rows
+    // bitwise-symmetric K (heat forms assembled by the tiled kernel, whose element matrix is mirrored from its upper triangle): columns are rows
+    const bool sym = ctx->form == EFG_FORM_HEAT && ctx->path == 2 && ctx->nrow == ctx->ncol;
     if (!sym && !vd->have_csr) vec_build_csr(ctx, vd);
     DevBuf<double> xs, ys;
     const double *xd = x;
