@@ -365,7 +365,7 @@ def main():
             "load_vector": {"what": "efg_vec_assemble (SysvecAssembler: fe[j] += N[j]*Q*JxW), 2 kernels, dof map cached",
                             "ms": v_ms, "elements_per_s": m0.nel_ / (v_ms / 1e3), "algorithmic_bytes": int(v_alg),
                             "achieved_GBps": v_alg / (v_ms / 1e3) / 1e9, "frac": v_alg / (v_ms / 1e3) / 1e9 / peak},
-            "spmv": {"what": "efg_spmv (KT = K*T, SparseArrays summation order), row-major view cached",
+            "spmv": {"what": "efg_spmv (KT = K*T, SparseArrays summation order); heat matrices are bitwise symmetric: CSC columns read in place as rows",
                      "ms": s_ms, "nnz_per_s": nnz / (s_ms / 1e3), "algorithmic_bytes": int(s_alg),
                      "achieved_GBps": s_alg / (s_ms / 1e3) / 1e9, "frac": s_alg / (s_ms / 1e3) / 1e9 / peak,
                      "y_checksum": float(yd.sum().item())},
