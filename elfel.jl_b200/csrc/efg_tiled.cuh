@@ -1152,8 +1152,9 @@ template <class F> constexpr int tl_minb() { return (F::SPLIT || F::ND > 8) ? 2 
 template <class F> static int tl_ctas_per_sm(efg_ctx *ctx)
 {
     TiledData *td = tiled_data(ctx);
-    const void *kern = td->persist ? (const void *)k_tl_numeric_p<F, false, tl_block<F>(), tl_minb<F>()>
-                                   : (const void *)k_tl_numeric<F, false, tl_block<F>(), tl_minb<F>()>;
+    const void *kern;
+    if constexpr (tl_persist<F>()) kern = (const void *)k_tl_numeric_p<F, false, tl_block<F>(), tl_minb<F>()>;
+    else kern = (const void *)k_tl_numeric<F, false, tl_block<F>(), tl_minb<F>()>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
     int per_sm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tl_block<F>(), (size_t)td->smem_bytes));
@@ -1461,7 +1462,7 @@ template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(
     const MeshDev &gm = ctx->mesh[F::GMESH];
     int per_sm = 0, nsm = 0;
     CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-    if (td->persist) {
+    if constexpr (tl_persist<F>()) {     // (compile-time: the persistent kernels are only instantiated when selected)
         auto kern = k_tl_numeric_p<F, S, BLOCK, MINB>;
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
