@@ -204,6 +204,145 @@ def shard_problem(efg, workload, n, rank, world, dev=None):
     return sh, ranges, nel_global
 
 
+@dataclass
+class Band:
+    """One rank's share of a structured block mesh generated WITHOUT the global arrays: local connectivity, the
+    coordinates of its nodes, their GLOBAL dof numbers and the owned column ranges (1-based, inclusive)."""
+    kind: int
+    conn: object
+    xy: object
+    dofnums: object
+    firsts: np.ndarray
+    lasts: np.ndarray
+    ndofs: int
+    nel_global: int
+    nnz_global: int
+    rows: tuple      # owned node rows [j0, j1)
+
+
+def band_rows(N, rank, world):
+    """Node rows [j0, j1) owned by `rank`: cell rows are dealt out in `world` near-equal contiguous blocks, a node row
+    goes with the cell row above it, the last rank also takes the top node row."""
+    base, rem = divmod(N, world)
+    j0 = rank * base + min(rank, rem)
+    j1 = j0 + base + (1 if rank < rem else 0)
+    return j0, (N + 1 if rank == world - 1 else j1)
+
+
+def heat_block_numbering(N, j, i):
+    """Closed form of setebc!(all boundary nodes) + numberfreedofs! + numberdatadofs! (src/FEFields.jl:137-177) on the
+    (N+1) x (N+1) vertex grid of T3block/Q4block (nodes x-fastest): free dofs 1..(N-1)^2 in node order, then the data
+    dofs in node order.  j, i: integer tensors (node row, node column)."""
+    nfree = (N - 1) * (N - 1)
+    free = (j - 1) * (N - 1) + i
+    d_bottom = nfree + 1 + i
+    d_side = nfree + 1 + (N + 1) + 2 * (j - 1) + (i == N).to(j.dtype)
+    d_top = nfree + 1 + (N + 1) + 2 * (N - 1) + i
+    interior = (i > 0) & (i < N) & (j > 0) & (j < N)
+    return torch.where(interior, free, torch.where(j == 0, d_bottom, torch.where(j == N, d_top, d_side)))
+
+
+def heat_block_owned_ranges(N, j0, j1):
+    """Column ranges (1-based inclusive) of the dofs of node rows [j0, j1) under heat_block_numbering."""
+    nfree = (N - 1) * (N - 1)
+    lo, hi = max(j0, 1), min(j1 - 1, N - 1)          # interior node rows owned
+    r = []
+    if lo <= hi:
+        r.append(((lo - 1) * (N - 1) + 1, hi * (N - 1)))
+    if j0 == 0:
+        r.append((nfree + 1, nfree + N + 1))
+    if lo <= hi:
+        r.append((nfree + N + 2 + 2 * (lo - 1), nfree + N + 1 + 2 * hi))
+    if j1 == N + 1:
+        r.append((nfree + N + 2 + 2 * (N - 1), nfree + 2 * N + 2 + 2 * (N - 1)))
+    r = [x for x in r if x[1] >= x[0]]
+    merged = []
+    for f, l in sorted(r):
+        if merged and f == merged[-1][1] + 1:
+            merged[-1] = (merged[-1][0], l)
+        else:
+            merged.append((f, l))
+    return (np.array([m[0] for m in merged], dtype=np.int64), np.array([m[1] for m in merged], dtype=np.int64))
+
+
+def block_band(kind, N, rank, world, dev="cpu"):
+    """Rank's share of the unit-square N x N heat problem on T3block / Q4block (BASELINE configs 1 and 5), strong
+    scaling: the cells of the node rows it owns plus one halo cell row per cut.  Element order, node order and
+    coordinates are those of the global generators restricted to the band, so per-nonzero sums see their contributions in
+    the same order as the unsharded assembly (bit-identical blocks)."""
+    if kind not in (Q4, T3):
+        raise ValueError("block_band: T3 / Q4 block meshes only")
+    j0, j1 = band_rows(N, rank, world)
+    ja, jb = max(j0 - 1, 0), min(j1, N)               # cell rows [ja, jb); node rows [ja, jb]
+    nr = jb - ja
+    i = torch.arange(N, dtype=torch.int64, device=dev).repeat_interleave(nr)
+    j = torch.arange(nr, dtype=torch.int64, device=dev).repeat(N)
+    f = j * (N + 1) + i                                # local 0-based id of the cell's lower-left node
+    if kind == Q4:
+        conn = torch.stack([f, f + 1, f + N + 2, f + N + 1], dim=1) + 1
+    else:
+        conn = torch.empty((2 * N * nr, 3), dtype=torch.int64, device=dev)
+        conn[0::2] = torch.stack([f, f + 1, f + N + 2], dim=1) + 1
+        conn[1::2] = torch.stack([f, f + N + 2, f + N + 1], dim=1) + 1
+    del i, j, f
+    xs = torch.arange(N + 1, dtype=torch.float64, device=dev) * 1.0 / N
+    ys = torch.arange(ja, jb + 1, dtype=torch.float64, device=dev) * 1.0 / N
+    xy = torch.stack([xs.repeat(nr + 1), ys.repeat_interleave(N + 1)], dim=1)
+    ni = torch.arange(N + 1, dtype=torch.int64, device=dev).repeat(nr + 1)
+    nj = torch.arange(ja, jb + 1, dtype=torch.int64, device=dev).repeat_interleave(N + 1)
+    dofnums = heat_block_numbering(N, nj, ni).view(-1, 1).contiguous()
+    firsts, lasts = heat_block_owned_ranges(N, j0, j1)
+    nelg = N * N * (1 if kind == Q4 else 2)
+    nnzg = (3 * N + 1) ** 2 if kind == Q4 else 7 * N * N + 6 * N + 1
+    return Band(kind, conn.contiguous(), xy.contiguous(), dofnums, firsts, lasts, (N + 1) * (N + 1), nelg, nnzg, (j0, j1))
+
+
+def q4_band(N, rank, world, dev="cpu"):
+    return block_band(Q4, N, rank, world, dev)
+
+
+def pattern_checksum(colptr, rowval, firsts, lasts):
+    """Order-independent checksum of a CSC column block: sum over stored entries of mix(row, col) mod 2^63 (torch int64
+    wrap-around arithmetic).  colptr (ncl+1) / rowval 1-based; firsts/lasts: the global column ranges of the block."""
+    dev = rowval.device
+    cols = torch.cat([torch.arange(int(f), int(l) + 1, dtype=torch.int64, device=dev) for f, l in zip(firsts, lasts)])
+    cnt = (colptr[1:] - colptr[:-1])
+    col_of = torch.repeat_interleave(cols, cnt)
+    return int(_mix(rowval, col_of).sum().item())
+
+
+def _mix(r, c):
+    return (r * 0x9E3779B1 + c * 0x85EBCA77) ^ ((r + 0x27D4EB2F) * (c + 0x165667B1))
+
+
+def q4_expected_checksums(N, j0, j1, dev="cpu", chunk_rows=256):
+    """What the heat Q4 assembly on the N x N block must produce for the columns of node rows [j0, j1), derived from the
+    grid alone (9-point node adjacency, uniform square cells: element matrix 1/6 [4 -1 -2 -1; ...]): (nnz, pattern
+    checksum, sum of nzval^2).  Independent of the library: used by bench.py to validate the sharded result."""
+    nnz, chk = 0, 0
+    sq = 0.0
+    for a in range(j0, j1, chunk_rows):
+        b = min(a + chunk_rows, j1)
+        cj = torch.arange(a, b, dtype=torch.int64, device=dev).repeat_interleave(N + 1)
+        ci = torch.arange(N + 1, dtype=torch.int64, device=dev).repeat(b - a)
+        cd = heat_block_numbering(N, cj, ci)
+        for dj in (-1, 0, 1):
+            for di in (-1, 0, 1):
+                rj, ri = cj + dj, ci + di
+                ok = (rj >= 0) & (rj <= N) & (ri >= 0) & (ri <= N)
+                rd = heat_block_numbering(N, rj[ok], ri[ok])
+                nnz += int(ok.sum().item())
+                chk = (chk + int(_mix(rd, cd[ok]).sum().item())) % (1 << 64)
+                # number of cells shared by the two nodes -> value: diagonal 4/6 per cell, edge neighbour -1/6 per cell, corner neighbour -2/6
+                cjo, cio, rjo, rio = cj[ok], ci[ok], rj[ok], ri[ok]
+                nx = (torch.minimum(cio, rio) < N).to(torch.float64) * (di != 0) + (di == 0) * ((cio > 0).to(torch.float64) + (cio < N).to(torch.float64))
+                ny = (torch.minimum(cjo, rjo) < N).to(torch.float64) * (dj != 0) + (dj == 0) * ((cjo > 0).to(torch.float64) + (cjo < N).to(torch.float64))
+                ncell = nx * ny
+                per = 4.0 / 6 if (di == 0 and dj == 0) else (-2.0 / 6 if (di != 0 and dj != 0) else -1.0 / 6)
+                sq += float(((ncell * per) ** 2).sum().item())
+    return nnz, chk, sq
+
+
 def merge_blocks(ncol, blocks):
     """Interleave per-rank CSC blocks [(firsts, lasts, colptr, rowval, nzval), ...] into the global CSC."""
     counts = np.zeros(ncol, dtype=np.int64)

@@ -203,27 +203,50 @@ static void bfungrad(int nbf, const double gp[][2], double J[2][2], double g[][2
 /* ------------------------------------------------------------------------------------------
  * COO buffer = SysmatAssemblerSparse (src/Assemblers.jl:19-24), caller-allocated.
  * ------------------------------------------------------------------------------------------ */
-typedef struct { int64_t *row, *col; double *val; int64_t n; } coo;
+/* The sink of assemble!: mode 0 is the reference's literal COO buffer (three growing vectors, 24 B per triplet).
+ * Modes 1-3 are the DIRECT-ACCUMULATE oracle: the same element traversal and the same left-to-right
+ * sums, but into a pre-built CSC pattern of a column block [c0, c1] instead of a COO list, so that matrices of the
+ * BASELINE sizes can be checked without 24 B/triplet + sparse() scratch:
+ *   1 = count the appended triplets of every column of the block, 2 = record their row indices (-> pattern),
+ *   3 = nzval[slot(row, col)] = nzval[...] + v in append order.  nzval starts as -0.0, and -0.0 + v == v exactly
+ *       (also for v = +-0.0), so the first contribution is "assigned" and later ones are folded left to right --
+ *       what sparse() does with duplicates (efo_sparse below).  Tested == mode 0 + efo_sparse bit for bit. */
+typedef struct {
+    int mode;
+    int64_t *row, *col; double *val; int64_t n;          /* mode 0 */
+    int64_t nrow, ncol, c0, c1;                           /* modes 1-3: column block, 1-based inclusive */
+    int64_t *cnt, *cand;                                  /* modes 1-2: per-column counts / fill cursors, candidate rows */
+    const int64_t *colptr, *rowval; double *nzval;        /* mode 3: pattern of the block (colptr 1-based, rebased) */
+    int bad;                                              /* an index was < 1 or > nrow/ncol (sparse(): ArgumentError) */
+} coo;
+
+static inline void coo_put(coo *a, int64_t r, int64_t c, double v)
+{
+    if (a->mode == 0) { a->row[a->n] = r; a->col[a->n] = c; a->val[a->n] = v; a->n++; return; }
+    a->n++;
+    if (r < 1 || r > a->nrow || c < 1 || c > a->ncol) { a->bad = 1; return; }
+    if (c < a->c0 || c > a->c1) return;
+    const int64_t lc = c - a->c0;
+    if (a->mode == 1) { a->cnt[lc]++; return; }
+    if (a->mode == 2) { a->cand[a->cnt[lc]++] = r; return; }
+    int64_t lo = a->colptr[lc] - 1, hi = a->colptr[lc + 1] - 1;
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (a->rowval[mid] < r) lo = mid + 1; else hi = mid; }
+    a->nzval[lo] = a->nzval[lo] + v;
+}
 
 /* assemble!(self, lma): src/Assemblers.jl:97-102 with init! ordering src/LocalAssemblers.jl:68-83:
  * column-major, k = j*nr + i, row = rdofs[i], col = cdofs[j]. M is column-major nr x nc. */
 static void coo_append(coo *a, int nr, int nc, const int64_t *rdofs, const int64_t *cdofs, const double *M)
 {
     for (int j = 0; j < nc; j++)
-        for (int i = 0; i < nr; i++) {
-            a->row[a->n] = rdofs[i]; a->col[a->n] = cdofs[j]; a->val[a->n] = M[j * nr + i];
-            a->n++;
-        }
+        for (int i = 0; i < nr; i++) coo_put(a, rdofs[i], cdofs[j], M[j * nr + i]);
 }
 /* assemble!(self, transpose(lma)): src/Assemblers.jl:109-114.  Iterating transpose(parent) in
  * column-major order of the transposed view: outer = parent row i, inner = parent column j. */
 static void coo_append_T(coo *a, int nr, int nc, const int64_t *rdofs, const int64_t *cdofs, const double *M)
 {
     for (int i = 0; i < nr; i++)
-        for (int j = 0; j < nc; j++) {
-            a->row[a->n] = cdofs[j]; a->col[a->n] = rdofs[i]; a->val[a->n] = M[j * nr + i];
-            a->n++;
-        }
+        for (int j = 0; j < nc; j++) coo_put(a, cdofs[j], rdofs[i], M[j * nr + i]);
 }
 
 /* _storedofs!: src/FEIterators.jl:161-171 -- node-major, component-minor. */
@@ -281,14 +304,14 @@ int64_t efo_triplets_per_element(int form, int vkind, int pkind)
  * Elements [e0, e1) are processed (0-based range) so the baseline can time a bounded sample.
  * Returns number of triplets appended, or <0 on error.
  * ------------------------------------------------------------------------------------------ */
-int64_t efo_assemble_coo(int form, int quad, int64_t e0, int64_t e1,
-                         const int64_t *vconn, int vkind, const double *vxy,
-                         const int64_t *pconn, int pkind, const double *pxy,
-                         const int64_t *dof0, const int64_t *dof1, const int64_t *dof2,
-                         const double *params,
-                         int64_t *row, int64_t *col, double *val)
+static int64_t element_loop(coo *ap, int form, int quad, int64_t e0, int64_t e1, const int64_t *elist,
+                            const int64_t *vconn, int vkind, const double *vxy,
+                            const int64_t *pconn, int pkind, const double *pxy,
+                            const int64_t *dof0, const int64_t *dof1, const int64_t *dof2,
+                            const double *params)
 {
-    coo a = { row, col, val, 0 };
+#define a (*ap)
+    const int values = (a.mode == 0 || a.mode == 3);   /* pattern passes skip the quadrature loop (ke stays 0) */
     qptab vq, pq;
     if (qptab_init(&vq, vkind, quad) < 0) return -1;
     if (pconn && qptab_init(&pq, pkind, quad) < 0) return -1;
@@ -299,11 +322,12 @@ int64_t efo_assemble_coo(int form, int quad, int64_t e0, int64_t e1,
     if (form == EFO_FORM_HEAT) { /* examples/heat/poisson/t3.jl:41-64 */
         const double kappa = params[0];
         int64_t d[MAXBF]; double ke[MAXBF * MAXBF];
-        for (int64_t e = e0; e < e1; e++) {
+        for (int64_t ee = e0; ee < e1; ee++) {
+            const int64_t e = elist ? elist[ee] : ee;
             const int64_t *nodes = vconn + e * nu;
             eldofs(nodes, nu, dof0, 1, d);
             memset(ke, 0, sizeof ke);
-            for (int q = 0; q < vq.npts; q++) {
+            for (int q = 0; values && q < vq.npts; q++) {
                 double Jd = jacjac(vxy, nodes, nu, vq.gp[q], J);
                 bfungrad(nu, vq.gp[q], J, g);
                 double JxW = Jd * vq.w[q];
@@ -319,11 +343,12 @@ int64_t efo_assemble_coo(int form, int quad, int64_t e0, int64_t e1,
     if (form == EFO_FORM_ELASTICITY) { /* examples/elasticity/stretch/t6.jl:40-63 */
         const int nd = 2 * nu;
         int64_t d[2 * MAXBF]; double ke[4 * MAXBF * MAXBF];
-        for (int64_t e = e0; e < e1; e++) {
+        for (int64_t ee = e0; ee < e1; ee++) {
+            const int64_t e = elist ? elist[ee] : ee;
             const int64_t *nodes = vconn + e * nu;
             eldofs(nodes, nu, dof0, 2, d);
             memset(ke, 0, sizeof ke);
-            for (int q = 0; q < vq.npts; q++) {
+            for (int q = 0; values && q < vq.npts; q++) {
                 double Jd = jacjac(vxy, nodes, nu, vq.gp[q], J);
                 bfungrad(nu, vq.gp[q], J, g);
                 double JxW = Jd * vq.w[q];
@@ -349,12 +374,13 @@ int64_t efo_assemble_coo(int form, int quad, int64_t e0, int64_t e1,
         const int nd = 2 * nu, np = pkind;
         int64_t du[2 * MAXBF], dp[MAXBF];
         double kuu[4 * MAXBF * MAXBF], kup[2 * MAXBF * MAXBF];
-        for (int64_t e = e0; e < e1; e++) {
+        for (int64_t ee = e0; ee < e1; ee++) {
+            const int64_t e = elist ? elist[ee] : ee;
             const int64_t *unodes = vconn + e * nu, *pnodes = pconn + e * np;
             eldofs(unodes, nu, dof0, 2, du);
             eldofs(pnodes, np, dof1, 1, dp);
             memset(kuu, 0, sizeof kuu); memset(kup, 0, sizeof kup);
-            for (int q = 0; q < vq.npts; q++) {
+            for (int q = 0; values && q < vq.npts; q++) {
                 double Jd = jacjac(vxy, unodes, nu, vq.gp[q], J); /* velocity element Jacobian (:61) */
                 double JxW = Jd * vq.w[q];
                 bfungrad(nu, vq.gp[q], J, g);
@@ -396,14 +422,15 @@ int64_t efo_assemble_coo(int form, int quad, int64_t e0, int64_t e1,
         int64_t dx[MAXBF], dy[MAXBF], dp[MAXBF];
         double kxx[MAXBF * MAXBF], kyy[MAXBF * MAXBF], kxy[MAXBF * MAXBF], kxp[MAXBF * MAXBF], kyp[MAXBF * MAXBF];
         double gp_[MAXBF][2];
-        for (int64_t e = e0; e < e1; e++) {
+        for (int64_t ee = e0; ee < e1; ee++) {
+            const int64_t e = elist ? elist[ee] : ee;
             const int64_t *unodes = vconn + e * nu, *pnodes = pconn + e * np;
             eldofs(unodes, nu, dof0, 1, dx);
             eldofs(unodes, nu, dof1, 1, dy);
             eldofs(pnodes, np, dof2, 1, dp);
             memset(kxx, 0, sizeof kxx); memset(kyy, 0, sizeof kyy); memset(kxy, 0, sizeof kxy);
             memset(kxp, 0, sizeof kxp); memset(kyp, 0, sizeof kyp);
-            for (int q = 0; q < vq.npts; q++) {
+            for (int q = 0; values && q < vq.npts; q++) {
                 double Jd = jacjac(pxy, pnodes, np, pq.gp[q], J); /* PRESSURE element Jacobian (:72) */
                 double JxW = Jd * pq.w[q];
                 bfungrad(np, pq.gp[q], J, gp_); /* gradNp: computed, unused (:74) */
@@ -451,6 +478,99 @@ int64_t efo_assemble_coo(int form, int quad, int64_t e0, int64_t e1,
         return a.n;
     }
     return -2;
+#undef a
+}
+
+int64_t efo_assemble_coo(int form, int quad, int64_t e0, int64_t e1,
+                         const int64_t *vconn, int vkind, const double *vxy,
+                         const int64_t *pconn, int pkind, const double *pxy,
+                         const int64_t *dof0, const int64_t *dof1, const int64_t *dof2,
+                         const double *params,
+                         int64_t *row, int64_t *col, double *val)
+{
+    coo a;
+    memset(&a, 0, sizeof a);
+    a.row = row; a.col = col; a.val = val;
+    return element_loop(&a, form, quad, e0, e1, NULL, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, params);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * DIRECT-ACCUMULATE oracle for a column block [c0, c1] (1-based inclusive) of the nrow x ncol matrix.
+ * Elements visited: elist[0..nsel) (ascending element numbers, e.g. the elements touching the block) or all of
+ * [0, nel) when elist is NULL -- elements without a column in the block contribute nothing either way.
+ *   efo_direct_pattern: colptr (c1-c0+2 entries, 1-based, rebased to the block) and rowval (capacity = the count the
+ *     first call returns when rowval is NULL): the rows of every column ascending, duplicates removed, explicit zeros
+ *     kept -- the pattern sparse() produces (efo_sparse).  Returns nnz of the block, -1 ArgumentError, -3 no memory.
+ *   efo_direct_values: nzval of that pattern, every nonzero = left-to-right sum of its contributions in append order
+ *     (ascending element, the reference's assemble! order inside an element).
+ * ------------------------------------------------------------------------------------------ */
+static int cmp_i64(const void *x, const void *y)
+{
+    const int64_t p = *(const int64_t *)x, q = *(const int64_t *)y;
+    return (p > q) - (p < q);
+}
+
+int64_t efo_direct_pattern(int form, int quad, int64_t nel, const int64_t *elist, int64_t nsel,
+                           const int64_t *vconn, int vkind, const double *vxy,
+                           const int64_t *pconn, int pkind, const double *pxy,
+                           const int64_t *dof0, const int64_t *dof1, const int64_t *dof2,
+                           int64_t nrow, int64_t ncol, int64_t c0, int64_t c1,
+                           int64_t *colptr, int64_t *rowval)
+{
+    const int64_t nc = c1 - c0 + 1;
+    const double dummy[9] = {0};
+    coo a;
+    memset(&a, 0, sizeof a);
+    a.nrow = nrow; a.ncol = ncol; a.c0 = c0; a.c1 = c1;
+    int64_t *cnt = (int64_t *)calloc((size_t)nc + 1, sizeof(int64_t));
+    if (!cnt) return -3;
+    a.mode = 1; a.cnt = cnt;
+    const int64_t n_it = elist ? nsel : nel;
+    if (element_loop(&a, form, quad, 0, n_it, elist, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, dummy) < 0 || a.bad) {
+        free(cnt);
+        return -1;
+    }
+    /* counts -> start offsets (cursor array for the fill pass) */
+    int64_t tot = 0;
+    for (int64_t j = 0; j < nc; j++) { const int64_t c = cnt[j]; cnt[j] = tot; tot += c; }
+    cnt[nc] = tot;
+    int64_t *start = (int64_t *)malloc(((size_t)nc + 1) * sizeof(int64_t));
+    int64_t *cand = (int64_t *)malloc((size_t)(tot > 0 ? tot : 1) * sizeof(int64_t));
+    if (!start || !cand) { free(cnt); free(start); free(cand); return -3; }
+    memcpy(start, cnt, ((size_t)nc + 1) * sizeof(int64_t));
+    a.mode = 2; a.cand = cand; a.n = 0;
+    element_loop(&a, form, quad, 0, n_it, elist, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, dummy);
+    int64_t nnz = 0;
+    colptr[0] = 1;
+    for (int64_t j = 0; j < nc; j++) {
+        int64_t *r = cand + start[j];
+        const int64_t m = start[j + 1] - start[j];
+        qsort(r, (size_t)m, sizeof(int64_t), cmp_i64);
+        for (int64_t k = 0; k < m; k++)
+            if (k == 0 || r[k] != r[k - 1]) { if (rowval) rowval[nnz] = r[k]; nnz++; }
+        colptr[j + 1] = nnz + 1;
+    }
+    free(cnt); free(start); free(cand);
+    return nnz;
+}
+
+int64_t efo_direct_values(int form, int quad, int64_t nel, const int64_t *elist, int64_t nsel,
+                          const int64_t *vconn, int vkind, const double *vxy,
+                          const int64_t *pconn, int pkind, const double *pxy,
+                          const int64_t *dof0, const int64_t *dof1, const int64_t *dof2,
+                          const double *params, int64_t nrow, int64_t ncol, int64_t c0, int64_t c1,
+                          const int64_t *colptr, const int64_t *rowval, double *nzval)
+{
+    coo a;
+    memset(&a, 0, sizeof a);
+    a.mode = 3; a.nrow = nrow; a.ncol = ncol; a.c0 = c0; a.c1 = c1;
+    a.colptr = colptr; a.rowval = rowval; a.nzval = nzval;
+    const int64_t nnz = colptr[c1 - c0 + 1] - 1;
+    for (int64_t k = 0; k < nnz; k++) nzval[k] = -0.0;
+    const int64_t n_it = elist ? nsel : nel;
+    const int64_t r = element_loop(&a, form, quad, 0, n_it, elist, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, params);
+    if (r < 0) return r;
+    return a.bad ? -1 : nnz;
 }
 
 /* ------------------------------------------------------------------------------------------

@@ -44,6 +44,11 @@ def lib():
                                        i64p, C.c_int, f64p, i64p, C.c_int, f64p,
                                        i64p, i64p, i64p, f64p, i64p, i64p, f64p]
         L.efo_assemble_coo.restype = C.c_int64
+        common = [C.c_int, C.c_int, C.c_int64, i64p, C.c_int64, i64p, C.c_int, f64p, i64p, C.c_int, f64p, i64p, i64p, i64p]
+        L.efo_direct_pattern.argtypes = common + [C.c_int64, C.c_int64, C.c_int64, C.c_int64, i64p, i64p]
+        L.efo_direct_pattern.restype = C.c_int64
+        L.efo_direct_values.argtypes = common + [f64p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, i64p, i64p, f64p]
+        L.efo_direct_values.restype = C.c_int64
         L.efo_sparse.argtypes = [C.c_int64, C.c_int64, C.c_int64, i64p, i64p, f64p, i64p, i64p, f64p]
         L.efo_sparse.restype = C.c_int64
         L.efo_assemble_vec_heat.argtypes = [C.c_int, C.c_int64, C.c_int64, i64p, C.c_int, f64p, i64p, C.c_double, C.c_int64, f64p]
@@ -146,6 +151,83 @@ def assemble(form, quad, vmesh, pmesh, dofs, params, nrow, ncol, timing=None):
         timing["integrate_s"] = t1 - t0
         timing["finish_s"] = t2 - t1
     return out
+
+
+def elements_touching(dofs_per_mesh, c0, c1):
+    """Ascending 0-based numbers of the elements with at least one dof in the column block [c0, c1] (1-based inclusive).
+    dofs_per_mesh: [(conn (nel, nen), dofnums (nnodes, ncomp)), ...] for every space of the form."""
+    hit = None
+    for conn, dofnums in dofs_per_mesh:
+        d = np.asarray(dofnums)
+        inb = ((d >= c0) & (d <= c1)).any(axis=1)
+        h = inb[np.asarray(conn) - 1].any(axis=1)
+        hit = h if hit is None else (hit | h)
+    return np.nonzero(hit)[0].astype(np.int64)
+
+
+def assemble_direct(form, quad, vmesh, pmesh, dofs, params, nrow, ncol, c0=1, c1=None, elist=None, timing=None):
+    """Direct-accumulate oracle: CSC of the column block [c0, c1] (1-based inclusive; default: the whole
+    matrix) -- the same element traversal and left-to-right sums as assemble(), into a pre-built pattern, without the
+    24 B/triplet COO list.  colptr is rebased to the block.  Bit-identical to assemble() (tested)."""
+    L = lib()
+    c1 = ncol if c1 is None else c1
+    pk = pmesh.kind if pmesh is not None else 0
+    vconn = _c(vmesh.conn, np.int64); vxy = _c(vmesh.xy, np.float64)
+    pconn = _c(pmesh.conn, np.int64) if pmesh is not None else None
+    pxy = _c(pmesh.xy, np.float64) if pmesh is not None else None
+    d = [_c(x, np.int64) for x in dofs] + [None] * (3 - len(dofs))
+    prm = _c(np.atleast_1d(params), np.float64)
+    el = _c(elist, np.int64) if elist is not None else None
+    nsel = 0 if el is None else len(el)
+    nel = vconn.shape[0]
+    head = (form, quad, nel, _p(el, C.c_int64), nsel, _p(vconn, C.c_int64), vmesh.kind, _p(vxy, C.c_double),
+            _p(pconn, C.c_int64), pk, _p(pxy, C.c_double), _p(d[0], C.c_int64), _p(d[1], C.c_int64), _p(d[2], C.c_int64))
+    t0 = time.perf_counter()
+    colptr = np.empty(c1 - c0 + 2, dtype=np.int64)
+    nnz = L.efo_direct_pattern(*head, nrow, ncol, c0, c1, _p(colptr, C.c_int64), None)
+    if nnz == -1:
+        raise ValueError("ArgumentError: row/column index out of range (dof number 0 or > nrow?)")
+    if nnz < 0:
+        raise MemoryError("oracle direct mode: allocation failed")
+    rowval = np.empty(max(nnz, 1), dtype=np.int64)
+    L.efo_direct_pattern(*head, nrow, ncol, c0, c1, _p(colptr, C.c_int64), _p(rowval, C.c_int64))
+    t1 = time.perf_counter()
+    nzval = np.empty(max(nnz, 1), dtype=np.float64)
+    rc = L.efo_direct_values(*head, _p(prm, C.c_double), nrow, ncol, c0, c1, _p(colptr, C.c_int64), _p(rowval, C.c_int64),
+                             _p(nzval, C.c_double))
+    if rc != nnz:
+        raise RuntimeError(f"oracle direct accumulation failed (rc={rc})")
+    if timing is not None:
+        timing["pattern_s"] = t1 - t0
+        timing["values_s"] = time.perf_counter() - t1
+    return colptr, rowval[:nnz], nzval[:nnz]
+
+
+def assemble_direct_parallel(prob_args, nrow, ncol, space_pairs, nblocks=None, threads=None, c0=1, c1=None):
+    """assemble_direct over `nblocks` column blocks of [c0, c1] on a thread pool (ctypes releases the GIL), each block
+    visiting only the elements that touch it; the blocks are concatenated.  Same result as assemble_direct, used to check
+    matrices of the BASELINE sizes in bounded time and memory.  prob_args = (form, quad, vmesh, pmesh, dofs, params);
+    space_pairs = [(conn, dofnums) per space] (see elements_touching)."""
+    from concurrent.futures import ThreadPoolExecutor
+    c1 = ncol if c1 is None else c1
+    threads = threads or min(os.cpu_count() or 1, 16)
+    nblocks = nblocks or max(threads * 2, 1)
+    nblocks = max(1, min(nblocks, c1 - c0 + 1))
+    cuts = np.linspace(c0 - 1, c1, nblocks + 1).astype(np.int64)
+    lib()
+
+    def one(k):
+        a, b = int(cuts[k]) + 1, int(cuts[k + 1])
+        el = elements_touching(space_pairs, a, b)
+        return assemble_direct(*prob_args, nrow, ncol, c0=a, c1=b, elist=el)
+    with ThreadPoolExecutor(threads) as ex:
+        parts = list(ex.map(one, range(nblocks)))
+    colptr = [np.array([1], dtype=np.int64)]
+    off = 0
+    for cp, _, _ in parts:
+        colptr.append(cp[1:] + off)
+        off += int(cp[-1]) - 1
+    return np.concatenate(colptr), np.concatenate([p[1] for p in parts]), np.concatenate([p[2] for p in parts])
 
 
 def assemble_vec_heat(quad, mesh, dofnums, Q, nrow, e0=0, e1=None):

@@ -399,3 +399,34 @@ def test_stokes_dof_counts_n100():
     efg.setebc(Ph, 0, 1, 1, 0.0)
     efg.numberdofs([Uh, Ph])
     assert (efg.ndofs(Uh) + efg.ndofs(Ph), efg.nunknowns(Uh) + efg.nunknowns(Ph)) == (91003, 89402)
+
+
+# ---- the direct-accumulate mode is the literal COO + sparse() mode, bit for bit -------------------------
+@pytest.mark.parametrize("make", [
+    lambda: efg.heat_problem(efg.T3, 9, True), lambda: efg.heat_problem(efg.T6, 7, True), lambda: efg.heat_problem(efg.Q4, 8, True),
+    lambda: efg.heat_problem(efg.Q4, 5, True, quad=3), lambda: efg.elasticity_problem(6, efg.T6, True),
+    lambda: efg.stokes_problem(5, "gen", True), lambda: efg.stokes_problem(5, "reddy", True),
+    lambda: efg.stokes_problem(4, "veclap_alt", True), lambda: efg.stokes_problem(4, "veclap", True)])
+def test_direct_accumulate_mode_equals_coo_mode(oracle, make):
+    p = make()
+    a = oracle.assemble(*efg.oracle_args(p), p.ndofs, p.ndofs)
+    b = oracle.assemble_direct(*efg.oracle_args(p), p.ndofs, p.ndofs)
+    assert all(x.tobytes() == y.tobytes() for x, y in zip(a, b))
+    pairs = [(p.meshes[ms].conn, s.field.dofnums) for s, ms in zip(p.spaces, p.space_mesh)]
+    c = oracle.assemble_direct_parallel(efg.oracle_args(p), p.ndofs, p.ndofs, pairs, nblocks=5, threads=3)
+    assert all(x.tobytes() == y.tobytes() for x, y in zip(a, c))
+    # a column block on its own, visiting only the elements that touch it
+    c0, c1 = p.ndofs // 3, 2 * p.ndofs // 3
+    el = oracle.elements_touching(pairs, c0, c1)
+    assert len(el) <= p.nel
+    cb = oracle.assemble_direct(*efg.oracle_args(p), p.ndofs, p.ndofs, c0=c0, c1=c1, elist=el)
+    lo, hi = a[0][c0 - 1] - 1, a[0][c1] - 1
+    assert np.array_equal(cb[0], a[0][c0 - 1:c1 + 1] - a[0][c0 - 1] + 1) and np.array_equal(cb[1], a[1][lo:hi])
+    assert cb[2].tobytes() == a[2][lo:hi].tobytes()
+
+
+def test_direct_accumulate_mode_rejects_unnumbered_dofs(oracle):
+    p = efg.heat_problem(efg.T3, 5)
+    efg.numberfreedofs(p.spaces[0])
+    with pytest.raises(ValueError):
+        oracle.assemble_direct(*efg.oracle_args(p), p.ndofs, p.ndofs)

@@ -118,3 +118,48 @@ sys.stdout.write("done%d\\n" % r); sys.stdout.flush()
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "done0" in r.stdout and "done1" in r.stdout
+
+
+# ---- band-only generation (BASELINE config 5 strong scaling: no global arrays on any rank) ---------------------------
+def _owned_block(cp, rv, nz, firsts, lasts):
+    cols = np.concatenate([np.arange(f, l + 1) for f, l in zip(firsts, lasts)])
+    cnt = np.diff(cp)[cols - 1]
+    lcp = np.concatenate([[1], 1 + np.cumsum(cnt)]).astype(np.int64)
+    idx = np.concatenate([np.arange(cp[c - 1] - 1, cp[c] - 1) for c in cols]) if len(cols) else np.zeros(0, np.int64)
+    return lcp, rv[idx], nz[idx]
+
+
+@pytest.mark.parametrize("kind,N,world", [(efg.Q4, 7, 1), (efg.Q4, 8, 3), (efg.Q4, 5, 5), (efg.T3, 6, 4)])
+def test_block_bands_reproduce_the_global_problem(oracle, kind, N, world):
+    prob = efg.heat_problem(kind, N)
+    quad = prob.quad
+    gcp, grv, gnz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    blocks, owned, nnz_sum, chk_sum, sq_sum = [], np.zeros(prob.ndofs, dtype=np.int64), 0, 0, 0.0
+    for r in range(world):
+        b = sh.block_band(kind, N, r, world)
+        assert b.ndofs == prob.ndofs and b.nel_global == prob.nel and b.nnz_global == len(grv)
+        # the closed-form numbering is the host mirror's numbering, the band's nodes are a contiguous slice of the grid
+        j0, j1 = b.rows
+        ja = max(j0 - 1, 0)
+        sl = slice(ja * (N + 1), ja * (N + 1) + b.xy.shape[0])
+        assert np.array_equal(b.dofnums.numpy(), prob.spaces[0].field.dofnums[sl])
+        assert np.array_equal(b.xy.numpy(), prob.meshes[0].xy[sl])
+        for f, l in zip(b.firsts, b.lasts):
+            owned[f - 1: l] += 1
+        mesh = efg.Mesh(kind, b.conn.numpy(), b.xy.numpy())
+        cp, rv, nz = oracle.assemble(1, quad, mesh, None, [b.dofnums.numpy()], [1.0], b.ndofs, b.ndofs)
+        lcp, lrv, lnz = _owned_block(cp, rv, nz, b.firsts, b.lasts)
+        blocks.append((b.firsts, b.lasts, lcp, lrv, lnz))
+        if kind == efg.Q4:      # grid-derived expectations (what bench.py validates the sharded GPU result against)
+            ennz, echk, esq = sh.q4_expected_checksums(N, j0, j1, chunk_rows=3)
+            assert ennz == len(lrv)
+            got = sh.pattern_checksum(torch.from_numpy(lcp), torch.from_numpy(lrv), b.firsts, b.lasts)
+            assert (got - echk) % (1 << 64) == 0
+            assert abs(esq - float((lnz ** 2).sum())) <= 1e-12 * esq
+            nnz_sum += ennz
+    assert np.all(owned == 1)
+    cp, rv, nz = sh.merge_blocks(prob.ndofs, blocks)
+    assert np.array_equal(cp, gcp) and np.array_equal(rv, grv)
+    assert nz.tobytes() == gnz.tobytes()
+    if kind == efg.Q4:
+        assert nnz_sum == (3 * N + 1) ** 2
