@@ -154,6 +154,15 @@ def _ptr(a):
     return a.data_ptr()
 
 
+class _DeviceArray:
+    """A 1-D device array owned by an Engine, described through the CUDA array interface (version 3)."""
+
+    def __init__(self, ptr, n, typestr, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr or 0), False), "version": 3,
+                                         "strides": None, "stream": 1}
+
+
 class Engine:
     """One ``efg_ctx`` (one device, one stream).  Thin, 1:1 with the C ABI."""
 
@@ -248,6 +257,15 @@ class Engine:
         self._ck(self.L.efg_fetch_csc(self.h, _ptr(colptr), _ptr(rowval), _ptr(nzval)))
         return colptr, rowval, nzval
 
+
+    def device_csc(self):
+        """Zero-copy views of the device-resident result (efg_device_csc): (colptr int64 1-based, rowval int32 0-BASED,
+        nzval float64) as objects exposing ``__cuda_array_interface__`` (torch.as_tensor / cupy.asarray wrap them without
+        a copy).  Valid until the next symbolic phase / efg_set_mesh / close."""
+        cp, rv, nz = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.efg_device_csc(self.h, C.byref(cp), C.byref(rv), C.byref(nz)))
+        return (_DeviceArray(cp.value, self.ncols_local + 1, "<i8", self), _DeviceArray(rv.value, self.nnz, "<i4", self),
+                _DeviceArray(nz.value, self.nnz, "<f8", self))
 
     # ---- SURVEY 8f rows f1 / f2 -------------------------------------------------------------------
     def vec_assemble(self, vform_id, quad, params, nrow):

@@ -56,6 +56,8 @@ struct efg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evn0 = nullptr, evn1 = nullptr;
+    cudaEvent_t ev_tab = nullptr;          // after this ctx's last upload of / launch reading the __constant__ tables (TabGuard)
+    bool tab_event_recorded = false;
     std::string err;
     DevPool pool;
 

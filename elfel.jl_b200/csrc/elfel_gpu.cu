@@ -75,10 +75,9 @@ static void basis_tables(int kind, double r, double s, double *N, double (*g)[2]
     }
 }
 
-// Upload tables for the rule of element kind `vkind`; triangles share their rule between T3 and T6.
-static int upload_tables(efg_ctx *ctx, int vkind, int rule)
+// Host copy of the tables of (element kind `vkind`, rule): triangles share their rule between T3 and T6.  Returns npts or -1.
+static int build_tables(int vkind, int rule, QTab (&h)[3])
 {
-    QTab h[3];
     memset(h, 0, sizeof h);
     double pc[EFG_MAXQ][2], w[EFG_MAXQ];
     const int npts = quadrature_points(vkind, rule, pc, w);
@@ -92,10 +91,99 @@ static int upload_tables(efg_ctx *ctx, int vkind, int rule)
             basis_tables(kinds[k], pc[q][0], pc[q][1], h[k].N[q], h[k].gp[q]);
         }
     }
-    CUDA_CHECK(cudaMemcpyToSymbolAsync(c_tab, h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream)); // h is a stack buffer
     return npts;
 }
+static int quad_npts(int vkind, int rule)
+{
+    double pc[EFG_MAXQ][2], w[EFG_MAXQ];
+    const int npts = quadrature_points(vkind, rule, pc, w);
+    return (npts < 0 || npts > EFG_MAXQ) ? -1 : npts;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ownership of the __constant__ tables.  c_tab / c_prm exist once per DEVICE (every device has its own copy of the
+// module's constant bank), shared by all ctx of this process on that device, while every entry point that launches
+// a table-reading kernel returns without synchronising.  TabGuard serialises what has to be serialised and nothing
+// else:
+//   - a per-device mutex is held from "make the tables mine" until this ctx's table-reading launches are enqueued
+//     and an event after them is recorded on the ctx's stream;
+//   - the device's current content (host mirror) is compared first: identical tables/parameters are not uploaded
+//     again (the usual case: repeated efg_numeric calls, or several ctx using the same rule);
+//   - before an upload, the ctx's stream waits for the table events of every OTHER live ctx on the device, so no
+//     kernel still reading the old tables is overtaken; its own earlier kernels are ordered by the stream itself.
+// Ctx on different devices never contend (different mutex, different constant bank): one host thread per GPU works.
+// ------------------------------------------------------------------------------------------------
+#include <mutex>
+#include <algorithm>
+#define EFG_MAX_DEVICES 64
+struct DevTables {
+    std::mutex mu;
+    bool valid = false;
+    QTab tab[3];
+    double prm[16];
+    std::vector<efg_ctx *> users;       // live ctx on this device
+    efg_ctx *uploader = nullptr;        // whose stream carried the last upload
+};
+static DevTables g_devtab[EFG_MAX_DEVICES];
+
+static void tables_register(efg_ctx *ctx)
+{
+    DevTables &d = g_devtab[ctx->device];
+    std::lock_guard<std::mutex> lk(d.mu);
+    d.users.push_back(ctx);
+}
+static void tables_unregister(efg_ctx *ctx)
+{
+    DevTables &d = g_devtab[ctx->device];
+    std::lock_guard<std::mutex> lk(d.mu);
+    d.users.erase(std::remove(d.users.begin(), d.users.end(), ctx), d.users.end());
+    if (d.uploader == ctx) d.uploader = nullptr;      // (its stream has been synchronised by efg_destroy)
+}
+
+struct TabGuard {
+    efg_ctx *ctx;
+    DevTables &d;
+    std::unique_lock<std::mutex> lk;
+    int npts = -1;
+    // prm == nullptr: the kernels about to be launched do not read c_prm
+    TabGuard(efg_ctx *c, int vkind, int rule, const double *prm, int nprm) : ctx(c), d(g_devtab[c->device]), lk(d.mu)
+    {
+        QTab h[3];
+        npts = build_tables(vkind, rule, h);
+        if (npts < 0) return;
+        double hp[16] = {0};
+        for (int i = 0; i < nprm && i < 16; i++) hp[i] = prm[i];
+        const bool same_tab = d.valid && memcmp(h, d.tab, sizeof h) == 0;
+        const bool same_prm = !prm || (d.valid && memcmp(hp, d.prm, sizeof hp) == 0);
+        if (same_tab && same_prm) { order_after_upload(); return; }
+        for (efg_ctx *o : d.users)
+            if (o != ctx && o->tab_event_recorded) CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, o->ev_tab, 0));
+        d.valid = false;
+        // sources are small pageable host buffers: the runtime stages them before the call returns
+        if (!same_tab) CUDA_CHECK(cudaMemcpyToSymbolAsync(c_tab, h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
+        if (!same_prm) CUDA_CHECK(cudaMemcpyToSymbolAsync(c_prm, hp, sizeof hp, 0, cudaMemcpyHostToDevice, ctx->stream));
+        // a ctx that finds "its" content later must still be ordered after this upload: it waits for our event
+        memcpy(d.tab, h, sizeof h);
+        if (prm) memcpy(d.prm, hp, sizeof hp);
+        d.valid = true;
+        d.uploader = ctx;
+        CUDA_CHECK(cudaEventRecord(ctx->ev_tab, ctx->stream));
+        ctx->tab_event_recorded = true;
+    }
+    // a ctx that did not upload reads tables another ctx's stream wrote: order its kernels after that upload
+    void order_after_upload()
+    {
+        if (d.uploader && d.uploader != ctx && d.uploader->tab_event_recorded)
+            CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, d.uploader->ev_tab, 0));
+    }
+    ~TabGuard()
+    {
+        if (npts >= 0) {        // everything this ctx enqueued while holding the tables
+            if (cudaEventRecord(ctx->ev_tab, ctx->stream) == cudaSuccess) ctx->tab_event_recorded = true;
+            else cudaGetLastError();
+        }
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // ingestion: Int64 1-based host/device arrays -> Int32 0-based device arrays (validated)
@@ -182,13 +270,14 @@ int efg_create(int device, efg_ctx **out)
     *out = nullptr;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return EFG_ERR_CUDA; }
-    if (device < 0 || device >= ndev) return EFG_ERR_INVALID;
+    if (device < 0 || device >= ndev || device >= EFG_MAX_DEVICES) return EFG_ERR_INVALID;
     efg_ctx *ctx = new (std::nothrow) efg_ctx();
     if (!ctx) return EFG_ERR_OOM;
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
-        cudaEventCreate(&ctx->evn0) != cudaSuccess || cudaEventCreate(&ctx->evn1) != cudaSuccess) {
+        cudaEventCreate(&ctx->evn0) != cudaSuccess || cudaEventCreate(&ctx->evn1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
         return EFG_ERR_CUDA;
@@ -202,6 +291,7 @@ int efg_create(int device, efg_ctx **out)
         }
         cudaGetLastError();
     }
+    tables_register(ctx);
     *out = ctx;
     return EFG_OK;
 }
@@ -211,6 +301,7 @@ int efg_destroy(efg_ctx *ctx)
     if (!ctx) return EFG_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    tables_unregister(ctx);
     invalidate(ctx);
     for (auto &m : ctx->mesh) { m.conn.release(); m.xy.release(); }
     for (auto &s : ctx->space) s.dof.release();
@@ -221,7 +312,7 @@ int efg_destroy(efg_ctx *ctx)
         if (cudaDeviceGetDefaultMemPool(&mp, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
         cudaGetLastError();
     }
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evn0); cudaEventDestroy(ctx->evn1);
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evn0); cudaEventDestroy(ctx->evn1); cudaEventDestroy(ctx->ev_tab);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return EFG_OK;
@@ -382,6 +473,9 @@ static void check_form_inputs(efg_ctx *ctx, int form)
         const SpaceDev &sp = ctx->space[s];
         if (sp.mesh != mesh || sp.ncomp != ncomp)
             efg_throw(EFG_ERR_INVALID, "form %d needs space %d on mesh %d with %d component(s)", form, s, mesh, ncomp);
+        if (sp.nnodes != ctx->mesh[mesh].nnodes)     // efg_set_mesh replaced the mesh after efg_set_space
+            efg_throw(EFG_ERR_STATE, "space %d numbers %lld nodes, mesh %d now has %lld: call efg_set_space again", s, (long long)sp.nnodes,
+                      mesh, (long long)ctx->mesh[mesh].nnodes);
     };
     auto need_pmesh = [&]() {
         const MeshDev &m1 = ctx->mesh[1];
@@ -407,7 +501,7 @@ int efg_symbolic(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
     if (!(ctx->have_symbolic && ctx->form == form && ctx->quad == quad)) {
         invalidate(ctx);
         const int vkind = ctx->mesh[0].kind;
-        const int npts = upload_tables(ctx, vkind, quad);
+        const int npts = quad_npts(vkind, quad);       // (the symbolic phase does not read the tables)
         if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, vkind);
         CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
         int path = ctx->opt_path == 1 ? 1 : 2;
@@ -445,11 +539,7 @@ int efg_numeric(efg_ctx *ctx, const double *params, int nparams)
     if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_numeric before efg_symbolic");
     const int need = (ctx->form == EFG_FORM_ELASTICITY || ctx->form == EFG_FORM_STOKES_GEN) ? 9 : 1;
     if (!params || nparams != need) efg_throw(EFG_ERR_INVALID, "form %d takes %d parameter(s)", ctx->form, need);
-    double h[16] = {0};
-    for (int i = 0; i < need; i++) h[i] = params[i];
-    CUDA_CHECK(cudaMemcpyToSymbolAsync(c_prm, h, sizeof h, 0, cudaMemcpyHostToDevice, ctx->stream));
-    // the tables may have been overwritten by another ctx of this process: re-upload (cheap)
-    upload_tables(ctx, ctx->vkind, ctx->quad);
+    TabGuard tabs(ctx, ctx->vkind, ctx->quad, params, need);     // tables + parameters current on this device until the launches are enqueued
     ctx->numeric_launches = 0;
     CUDA_CHECK(cudaEventRecord(ctx->evn0, ctx->stream));
     dispatch_form(ctx->form, ctx->vkind, ctx->nq, [&](auto F) {
@@ -525,9 +615,10 @@ int efg_vec_assemble(efg_ctx *ctx, int vform, int quad, const double *params, in
     const MeshDev &m0 = ctx->mesh[0];
     if (m0.kind == 0) efg_throw(EFG_ERR_STATE, "mesh 0 not set");
     if (ctx->space[0].mesh != 0 || ctx->space[0].ncomp != 1) efg_throw(EFG_ERR_INVALID, "the heat load vector needs space 0 on mesh 0 with 1 component");
+    if (ctx->space[0].nnodes != m0.nnodes) efg_throw(EFG_ERR_STATE, "space 0 numbers %lld nodes, mesh 0 now has %lld: call efg_set_space again", (long long)ctx->space[0].nnodes, (long long)m0.nnodes);
     if (!params || nparams != 1) efg_throw(EFG_ERR_INVALID, "vector form %d takes 1 parameter (Q)", vform);
     if (nrow < 0 || nrow >= ((int64_t)1 << 31)) efg_throw(EFG_ERR_INVALID, "bad vector length");
-    const int npts = upload_tables(ctx, m0.kind, quad);
+    const int npts = quad_npts(m0.kind, quad);
     if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, m0.kind);
     VecData *vd = vec_get(ctx);
     if (!(vd->have_sym && vd->nrow == nrow)) {
@@ -539,6 +630,7 @@ int efg_vec_assemble(efg_ctx *ctx, int vform, int quad, const double *params, in
         }
     }
     const double Q = params[0];
+    TabGuard tabs(ctx, m0.kind, quad, nullptr, 0);
     CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
     const int key = m0.kind * 100 + npts;
     switch (key) {
@@ -666,7 +758,7 @@ int efg_qp_locations(efg_ctx *ctx, int mesh_slot, int quad, double *out, int64_t
     API_BEGIN(ctx)
     if (mesh_slot < 0 || mesh_slot > 1 || ctx->mesh[mesh_slot].kind == 0) efg_throw(EFG_ERR_STATE, "mesh %d not set", mesh_slot);
     const MeshDev &m = ctx->mesh[mesh_slot];
-    const int npts = upload_tables(ctx, m.kind, quad);
+    const int npts = quad_npts(m.kind, quad);
     if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, m.kind);
     if (npts_out) *npts_out = npts;
     if (out && m.nel > 0) {
@@ -674,6 +766,7 @@ int efg_qp_locations(efg_ctx *ctx, int mesh_slot, int quad, double *out, int64_t
         DevBuf<double> stage;
         double *d = out;
         if (!is_device_ptr(out)) { stage.alloc(ctx->pool, n); d = stage.p; }
+        TabGuard tabs(ctx, m.kind, quad, nullptr, 0);
         if (!vec_dispatch_kq(m.kind, npts, [&](auto K, auto Q) { vec_locations<decltype(K)::value, decltype(Q)::value>(ctx, m, d); }))
             efg_throw(EFG_ERR_INVALID, "no location kernel for element kind %d with %d points", m.kind, npts);
         if (d != out) CUDA_CHECK(cudaMemcpyAsync(out, d, n * sizeof(double), cudaMemcpyDefault, ctx->stream));
@@ -694,14 +787,16 @@ int efg_l2_error(efg_ctx *ctx, int ncomp, const int *space_slots, const int *com
         const SpaceDev &sp = ctx->space[space_slots[c]];
         if (comps[c] < 0 || comps[c] >= sp.ncomp) efg_throw(EFG_ERR_INVALID, "space %d has no component %d", space_slots[c], comps[c]);
         if (mslot >= 0 && sp.mesh != mslot) efg_throw(EFG_ERR_INVALID, "the components of one error integral must live on the same mesh");
+        if (sp.nnodes != ctx->mesh[sp.mesh].nnodes) efg_throw(EFG_ERR_STATE, "space %d numbers %lld nodes, its mesh now has %lld: call efg_set_space again", space_slots[c], (long long)sp.nnodes, (long long)ctx->mesh[sp.mesh].nnodes);
         mslot = sp.mesh;
         ec[c] = ErrComp{sp.dof.p, sp.ncomp, comps[c]};
     }
     if (ncomp == 1) ec[1] = ec[0];
     const MeshDev &m = ctx->mesh[mslot];
     if (m.kind == 0) efg_throw(EFG_ERR_STATE, "mesh %d not set", mslot);
-    const int npts = upload_tables(ctx, m.kind, quad);
+    const int npts = quad_npts(m.kind, quad);
     if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, m.kind);
+    TabGuard tabs(ctx, m.kind, quad, nullptr, 0);
     const size_t nt = (size_t)m.nel * npts * ncomp;
     DevBuf<double> us, ts, eout, sum;
     DevBuf<int> err;
