@@ -31,7 +31,7 @@ VFORM_HEAT_LOAD = 1
 
 EXPORTS = ["efg_create", "efg_destroy", "efg_last_error", "efg_set_option", "efg_get_stat", "efg_get_stream",
            "efg_synchronize", "efg_set_mesh", "efg_set_space", "efg_start", "efg_set_column_range",
-           "efg_set_column_ranges", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version",
+           "efg_set_column_ranges", "efg_pattern", "efg_fetch_pattern_async", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version",
            "efg_vec_assemble", "efg_fetch_vec", "efg_device_vec", "efg_spmv", "efg_block_nnz", "efg_fetch_block",
            "efg_qp_locations", "efg_l2_error"]
 
@@ -91,6 +91,8 @@ def load():
     if hasattr(L, "efg_set_column_ranges"):
         L.efg_set_column_ranges.argtypes = [vp, i64, i64p, i64p]
     L.efg_symbolic.argtypes = [vp, ci, ci, i64p]
+    L.efg_pattern.argtypes = [vp, ci, ci, i64p]
+    L.efg_fetch_pattern_async.argtypes = [vp, vp, vp]
     L.efg_numeric.argtypes = [vp, f64p, ci]
     L.efg_assemble.argtypes = [vp, ci, ci, f64p, ci, i64p]
     L.efg_fetch_csc.argtypes = [vp, vp, vp, vp]

@@ -237,6 +237,18 @@ class Engine:
         self.nnz = nnz.value
         return nnz.value
 
+    def pattern(self, form_id, quad) -> int:
+        """First half of the symbolic phase: the CSC pattern only (-> nnz); the tiles are built by the next numeric call."""
+        nnz = C.c_int64()
+        self._ck(self.L.efg_pattern(self.h, form_id, quad, C.byref(nnz)))
+        self.nnz = nnz.value
+        return nnz.value
+
+    def fetch_pattern_async(self, colptr, rowval):
+        """Start copying colptr / rowval to the caller's arrays; completed by the next fetch_csc call."""
+        self._keep_out = (colptr, rowval)
+        self._ck(self.L.efg_fetch_pattern_async(self.h, _ptr(colptr), _ptr(rowval)))
+
     def numeric(self, params):
         p = np.ascontiguousarray(params, dtype=np.float64)
         self._ck(self.L.efg_numeric(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), len(p)))

@@ -91,6 +91,14 @@ struct efg_ctx {
     TwoPass tp;
     Tiled tl;
     void *tl_opaque = nullptr;
+    void *tl_sym_opaque = nullptr;       // efg_tiled.cuh: pattern-phase data waiting for the tile phase
+    bool have_pattern = false;           // colptr / rowval / nnz are valid (the tiles may still be pending)
+    cudaEvent_t ev_pattern = nullptr;    // recorded on `stream` when colptr / rowval are complete
+    cudaStream_t copy_stream = nullptr;  // device -> host copies that overlap the rest of the symbolic / numeric phase
+    cudaEvent_t ev_copy = nullptr;
+    bool copy_pending = false;
+    DevBuf<int64_t> cstage[2];           // rowval Int32 -> Int64 staging of the copy stream
+    int tl_smem_budget = 0;              // dynamic shared memory per CTA that still lets two CTAs share an SM
     int form_req = 0, quad_req = 0;      // form / rule of the symbolic phase in progress
     int te_hint = 0, te_hint_form = 0, te_hint_kind = 0, te_hint_quad = 0;   // tile size the last symbolic phase settled on
     void *vec_opaque = nullptr;  // efg_vector.cuh: system-vector assembly, K*x, sub-blocks

@@ -103,6 +103,18 @@ template <class F> constexpr bool tl_persist() { return TL_GEO && (F::SPLIT ? TL
 // bytes of the stage: ND rows of nqs staged columns
 __host__ __device__ static inline int tl_stage_bytes(int nd, int nqs) { return tl_align16(nd * nqs * 8); }
 
+// what the pattern phase (A) leaves for the tile phase (B); released once the tiles exist
+struct TiledSym {
+    DevBuf<int32_t> edof;            // combined element dof vectors, ND x nel
+    DevBuf<uint32_t> adj, adjptr;    // column -> (element, local column) pairs, ascending element
+    DevBuf<uint32_t> eorder;         // elements along the space-filling curve (empty: natural order)
+    DevBuf<uint8_t> colcnt, hcnt;    // rows per column, heavy nonzeros per column
+    DevBuf<uint16_t> ccnt;           // contributions to the heavy nonzeros of a column
+    DevBuf<int64_t> colptr0;         // 0-based column offsets
+    int64_t npairs = 0;
+    bool have_order = false;
+};
+
 struct TiledData {
     DevBuf<TileDescFull> tiles;
     DevBuf<int32_t> tconn;
@@ -114,6 +126,7 @@ struct TiledData {
     int smem_bytes = 0, stage_bytes = 0, meta_max = 0;
     int off_meta = 0, off_geo = 0, off_gs = 0;   // persistent kernel: fixed shared-memory offsets (maxima over tiles)
     bool persist = false;
+    bool complete = false;       // false: the tile phase stopped early (shared-memory footprint too large for this tile size)
     int block = 256;
 };
 
@@ -122,13 +135,21 @@ static inline TiledData *&tiled_data(efg_ctx *ctx)
     static_assert(sizeof(void *) == 8, "");
     return *reinterpret_cast<TiledData **>(&ctx->tl_opaque);
 }
+static inline TiledSym *&tiled_sym(efg_ctx *ctx) { return *reinterpret_cast<TiledSym **>(&ctx->tl_sym_opaque); }
 
-inline void tiled_release(efg_ctx *ctx)
+inline void tiled_release_tiles(efg_ctx *ctx)
 {
     TiledData *&d = tiled_data(ctx);
     delete d;
     d = nullptr;
     ctx->tl.ntiles = 0;
+}
+inline void tiled_release(efg_ctx *ctx)
+{
+    tiled_release_tiles(ctx);
+    TiledSym *&y = tiled_sym(ctx);
+    delete y;
+    y = nullptr;
 }
 
 // ---- CUB helpers ---------------------------------------------------------------------------------
@@ -261,24 +282,29 @@ __global__ void k_tl_etile_identity(int64_t nel, int te, int32_t *__restrict__ e
 }
 __global__ void k_tl_fill_i32(int32_t *p, int64_t n, int32_t v) { GRID_STRIDE(i, n) p[i] = v; }
 
-// owner tile of every column in range + adjacency pair generation
+// adjacency pair generation: (local column, pair id) for every (element, local dof) whose column this ctx owns
 template <int ND>
-__global__ void k_tl_owner_pairs(const int32_t *__restrict__ edof, const int32_t *__restrict__ etile, int64_t nel,
-                                 ColMap cm, uint32_t ncl, int32_t *__restrict__ owner, uint32_t *__restrict__ adjcnt,
-                                 uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+__global__ void k_tl_pairs(const int32_t *__restrict__ edof, int64_t nel, ColMap cm, uint32_t ncl, uint32_t *__restrict__ adjcnt,
+                           uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
 {
     GRID_STRIDE(t, nel * ND) {
-        const int64_t e = t / ND;
         const int64_t lc = cm.local(edof[t]);
         if (lc >= 0) {
-            const uint32_t cl = (uint32_t)lc;
-            atomicMin(&owner[cl], etile[e]);
-            atomicAdd(&adjcnt[cl], 1u);
-            keys[t] = cl;
+            atomicAdd(&adjcnt[(uint32_t)lc], 1u);
+            keys[t] = (uint32_t)lc;
         } else {
             keys[t] = ncl;
         }
         vals[t] = (uint32_t)t;
+    }
+}
+// owner tile of every owned column = the lowest tile among the elements that contain its dof
+template <int ND>
+__global__ void k_tl_owner(const int32_t *__restrict__ edof, const int32_t *__restrict__ etile, int64_t nel, ColMap cm, int32_t *__restrict__ owner)
+{
+    GRID_STRIDE(t, nel * ND) {
+        const int64_t lc = cm.local(edof[t]);
+        if (lc >= 0) atomicMin(&owner[lc], etile[t / ND]);
     }
 }
 
@@ -1144,94 +1170,116 @@ template <class F> static int tl_default_tile_elems()
     return te;
 }
 
-template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te);
-
 template <class F> constexpr int tl_minb() { return (F::SPLIT || F::ND > 8) ? 2 : TL_MINB; }
 
-// CTAs of the numeric kernel that fit an SM with the shared memory the last symbolic phase asked for
+template <class F> static const void *tl_numeric_kernel()
+{
+    if constexpr (tl_persist<F>()) return (const void *)k_tl_numeric_p<F, false, tl_block<F>(), tl_minb<F>()>;
+    else return (const void *)k_tl_numeric<F, false, tl_block<F>(), tl_minb<F>()>;
+}
+// CTAs of the numeric kernel that fit an SM with the shared memory the last tile phase asked for
 template <class F> static int tl_ctas_per_sm(efg_ctx *ctx)
 {
     TiledData *td = tiled_data(ctx);
-    const void *kern;
-    if constexpr (tl_persist<F>()) kern = (const void *)k_tl_numeric_p<F, false, tl_block<F>(), tl_minb<F>()>;
-    else kern = (const void *)k_tl_numeric<F, false, tl_block<F>(), tl_minb<F>()>;
+    const void *kern = tl_numeric_kernel<F>();
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
     int per_sm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tl_block<F>(), (size_t)td->smem_bytes));
     return per_sm;
 }
-
-template <class F> void tiled_symbolic(efg_ctx *ctx)
+// dynamic shared memory a CTA may use if two CTAs are to share an SM
+template <class F> static int tl_smem_budget()
 {
-    if (ctx->opt_tile_elems > 0) { tiled_symbolic_te<F>(ctx, ctx->opt_tile_elems); return; }
-    // start from the size the previous symbolic phase of this form settled on (re-assembly after efg_set_mesh, time
-    // stepping with a changing mesh): the search below then succeeds at the first attempt
-    const int vkind = ctx->mesh[0].kind;
-    const bool hinted = ctx->te_hint > 0 && ctx->te_hint_form == ctx->form_req && ctx->te_hint_kind == vkind && ctx->te_hint_quad == ctx->quad_req;
-    int te = hinted ? ctx->te_hint : tl_default_tile_elems<F>();
-    for (;;) {
-        try {
-            tiled_symbolic_te<F>(ctx, te);
-            if (te <= 32 || tl_ctas_per_sm<F>(ctx) >= 2) {      // two co-resident CTAs overlap each other's phases
-                ctx->te_hint = te; ctx->te_hint_form = ctx->form_req; ctx->te_hint_kind = vkind; ctx->te_hint_quad = ctx->quad_req;
-                return;
-            }
-        } catch (const EfgError &e) {
-            if (e.code != EFG_ERR_LIMIT || te <= 32) throw;
-        }
-        int next = 32;
-        if (F::SPLIT) {
-            for (int c : TL_TILE_SIZES) {
-                if (c >= te) continue;
-                const double rounds = (double)c * F::ND / tl_block<F>();
-                if (rounds / ceil(rounds) < 0.85 && c > 32) continue;
-                next = c;
-                break;
-            }
-        } else {
-            next = ((int)(te * 0.97)) & ~7;     // the footprint (stage + gather metadata + geometry block) scales with te
-            if (next < 32) next = 32;
-        }
-        te = next;
-        tiled_release(ctx);
-        ctx->rowval.release(); ctx->colptr.release(); ctx->nzval.release();
-    }
+    size_t avail = 0;
+    if (cudaOccupancyAvailableDynamicSMemPerBlock(&avail, tl_numeric_kernel<F>(), 2, tl_block<F>()) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return (int)avail;
 }
 
-template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
+// ---- phase A: the CSC pattern (independent of the tile size) --------------------------------------------------------
+// T0 combined element dof vectors -> T2/T3 adjacency (column -> (element, local column), ascending element: one stable radix
+// sort) -> T4 per column: sorted unique rows = colptr / rowval.  When this returns (ev_pattern recorded) the pattern can
+// already travel to the host while phase B and the numeric kernel run.
+template <class F> static void tiled_pattern(efg_ctx *ctx)
 {
     static_assert(F::ND <= TL_MAXND, "");
     constexpr int ND = F::ND;
     const MeshDev &m0 = ctx->mesh[0];
-    const MeshDev &gm = ctx->mesh[F::GMESH];
     const int64_t nel = m0.nel;
     const int64_t ncl = ctx->ncl;
     if (nel * ND >= ((int64_t)1 << 32)) efg_throw(EFG_ERR_LIMIT, "tiled path: nel*ND exceeds 2^32; shard the mesh (efg_set_column_range)");
     cudaStream_t st = ctx->stream;
     DevPool &pool = ctx->pool;
-    TiledData *td = new TiledData();
-    tiled_data(ctx) = td;
+    tiled_release(ctx);
+    TiledSym *sy = new TiledSym();
+    tiled_sym(ctx) = sy;
     TlTrace trace(ctx);
+    // one slab for everything the two phases allocate before nnz is known (pairs: edof + adj + 24 B of sort scratch, per
+    // column: counts, offsets, owners, tile column lists), a second one below once nnz is known
+    pool.reserve((size_t)(nel * ND) * 36 + (size_t)nel * 24 + (size_t)ncl * 72 + ((size_t)64 << 20));
 
     DevBuf<int> err;
     err.alloc(pool, 1);
     CUDA_CHECK(cudaMemsetAsync(err.p, 0, sizeof(int), st));
-
     trace.mark("start");
     // T0: combined element dof table
-    DevBuf<int32_t> edof;
-    edof.alloc(pool, (size_t)(nel * ND));
+    sy->edof.alloc(pool, (size_t)(nel * ND));
     DofSrc src{m0.conn.p, ctx->mesh[1].conn.p, ctx->space[0].dof.p, ctx->space[1].dof.p, ctx->space[2].dof.p};
-    LAUNCH(ctx, k_tl_edofs<F>, grid_for(nel, 256), 256, 0, src, nel, ctx->nrow, ctx->ncol, edof.p, err.p);
+    LAUNCH(ctx, k_tl_edofs<F>, grid_for(nel, 256), 256, 0, src, nel, ctx->nrow, ctx->ncol, sy->edof.p, err.p);
     if (tl_read(ctx, err.p))
         efg_throw(EFG_ERR_INDEX, "ArgumentError: a dof number is < 1 or exceeds nrow/ncol (was every space numbered, incl. data dofs?)");
-
     trace.mark("T0 edofs");
-    // T1: element order -> tile of each element
-    const int ntiles = (int)((nel + te - 1) / te);
-    DevBuf<int32_t> etile;
-    etile.alloc(pool, (size_t)nel);
-    if (ctx->opt_sfc && nel > te) {
+
+    // T2/T3: adjacency (column -> (element, local column)), ascending element
+    DevBuf<uint32_t> adjcnt;
+    adjcnt.alloc(pool, (size_t)ncl + 2); sy->adjptr.alloc(pool, (size_t)ncl + 2);
+    CUDA_CHECK(cudaMemsetAsync(adjcnt.p, 0, (size_t)(ncl + 2) * sizeof(uint32_t), st));
+    sy->adj.alloc(pool, (size_t)(nel * ND));
+    {
+        const size_t np = (size_t)(nel * ND);
+        uint32_t *k1 = reinterpret_cast<uint32_t *>(tl_scratch(ctx, 3 * (np + 2) * sizeof(uint64_t))), *k2 = k1 + np, *v1 = k2 + np;   // (sized for phase B's 64-bit sort)
+        LAUNCH(ctx, k_tl_pairs<ND>, grid_for(nel * ND, 256), 256, 0, sy->edof.p, nel, COLMAP(ctx), (uint32_t)ncl, adjcnt.p, k1, v1);
+        tl_sort_pairs(ctx, k1, k2, v1, sy->adj.p, nel * ND, bits_for(ncl));
+    }
+    tl_excl_scan(ctx, adjcnt.p, sy->adjptr.p, ncl + 1);
+    sy->npairs = (int64_t)tl_read(ctx, sy->adjptr.p + ncl);
+    trace.mark("T2/T3 adjacency");
+
+    // T4: CSC pattern
+    sy->colcnt.alloc(pool, (size_t)ncl + 1); sy->hcnt.alloc(pool, (size_t)ncl + 1); sy->ccnt.alloc(pool, (size_t)ncl + 1); sy->colptr0.alloc(pool, (size_t)ncl + 1);
+    CUDA_CHECK(cudaMemsetAsync(sy->colcnt.p, 0, (size_t)ncl + 1, st));
+    CUDA_CHECK(cudaMemsetAsync(sy->hcnt.p, 0, (size_t)ncl + 1, st));
+    CUDA_CHECK(cudaMemsetAsync(sy->ccnt.p, 0, ((size_t)ncl + 1) * 2, st));
+    LAUNCH(ctx, k_tl_col_count<F>, grid_for(ncl, 128), 128, 0, sy->adjptr.p, sy->adj.p, sy->edof.p, ncl, sy->colcnt.p, sy->ccnt.p, sy->hcnt.p, err.p);
+    if (tl_read(ctx, err.p))
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a matrix column has more than %d distinct rows (node valence too high); use EFG_OPT_PATH=1", TL_CAP);
+    {
+        cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const uint8_t *> it(sy->colcnt.p, cub::CastOp<int64_t>());
+        tl_excl_scan(ctx, it, sy->colptr0.p, ncl + 1);
+    }
+    const int64_t nnz = tl_read(ctx, sy->colptr0.p + ncl);
+    ctx->nnz = nnz;
+    // everything proportional to nnz and to the tile elements: rowval 4 + nzval 8 + gather words 4 (+ heavy lists) per
+    // nonzero, geometry blocks and tile-element lists per pair
+    pool.reserve((size_t)nnz * 17 + (size_t)(nel * ND) * 12 + (size_t)nel * 40 + ((size_t)64 << 20));
+    ctx->rowval.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
+    ctx->colptr.alloc(pool, (size_t)ncl + 1);
+    LAUNCH(ctx, k_tl_col_fill<F>, grid_for(ncl + 1, 128), 128, 0, sy->adjptr.p, sy->adj.p, sy->edof.p, ncl, sy->colptr0.p, ctx->rowval.p, ctx->colptr.p);
+    CUDA_CHECK(cudaEventRecord(ctx->ev_pattern, st));
+    ctx->have_pattern = true;
+    trace.mark("T4 pattern");
+}
+
+// ---- phase B0: element order along a space-filling curve (independent of the tile size) -------------------------------
+template <class F> static void tiled_order(efg_ctx *ctx)
+{
+    TiledSym *sy = tiled_sym(ctx);
+    const MeshDev &gm = ctx->mesh[F::GMESH];
+    const int64_t nel = ctx->mesh[0].nel;
+    cudaStream_t st = ctx->stream;
+    DevPool &pool = ctx->pool;
+    TlTrace trace(ctx);
+    sy->have_order = false;
+    if (ctx->opt_sfc && nel > 32) {
         DevBuf<BBox> bb;
         bb.alloc(pool, 1);
         cub::TransformInputIterator<BBox, XYToBBox, const double2 *> it(gm.xy.p, XYToBBox());
@@ -1242,56 +1290,55 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
         tmp.alloc(pool, tb);
         CUDA_CHECK(cub::DeviceReduce::Reduce(tmp.p, tb, it, bb.p, gm.nnodes, BBoxOp(), init, st));
         ctx->launches += 2;
-        DevBuf<uint32_t> k1, k2, v1, v2;
-        k1.alloc(pool, (size_t)nel); k2.alloc(pool, (size_t)nel); v1.alloc(pool, (size_t)nel); v2.alloc(pool, (size_t)nel);
+        DevBuf<uint32_t> k1, k2, v1;
+        k1.alloc(pool, (size_t)nel); k2.alloc(pool, (size_t)nel); v1.alloc(pool, (size_t)nel);
+        sy->eorder.alloc(pool, (size_t)nel);
         LAUNCH(ctx, k_tl_morton, grid_for(nel, 256), 256, 0, gm.conn.p, gm.kind, gm.xy.p, nel, bb.p, k1.p, v1.p);
-        tl_sort_pairs(ctx, k1.p, k2.p, v1.p, v2.p, nel, 32);
-        LAUNCH(ctx, k_tl_etile_from_order, grid_for(nel, 256), 256, 0, v2.p, nel, te, etile.p);
-    } else {
-        LAUNCH(ctx, k_tl_etile_identity, grid_for(nel, 256), 256, 0, nel, te, etile.p);
+        tl_sort_pairs(ctx, k1.p, k2.p, v1.p, sy->eorder.p, nel, 32);
+        sy->have_order = true;
     }
-
     trace.mark("T1 morton order");
-    // T2/T3: column owners + adjacency (column -> (element, local column)), ascending element
+}
+
+// ---- phase B: tiles of `te` elements -- owners, tile column lists, tile elements (own + halo), geometry blocks, gather words --
+template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
+{
+    constexpr int ND = F::ND;
+    const MeshDev &m0 = ctx->mesh[0];
+    const MeshDev &gm = ctx->mesh[F::GMESH];
+    const int64_t nel = m0.nel;
+    const int64_t ncl = ctx->ncl;
+    const int64_t nnz = ctx->nnz;
+    cudaStream_t st = ctx->stream;
+    DevPool &pool = ctx->pool;
+    TiledSym *sy = tiled_sym(ctx);
+    const int64_t npairs = sy->npairs;
+    tiled_release_tiles(ctx);
+    TiledData *td = new TiledData();
+    tiled_data(ctx) = td;
+    TlTrace trace(ctx);
+
+    DevBuf<int> err;
+    err.alloc(pool, 1);
+    CUDA_CHECK(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+
+    // T1: tile of each element
+    const int ntiles = (int)((nel + te - 1) / te);
+    DevBuf<int32_t> etile;
+    etile.alloc(pool, (size_t)nel);
+    if (sy->have_order && nel > te) LAUNCH(ctx, k_tl_etile_from_order, grid_for(nel, 256), 256, 0, sy->eorder.p, nel, te, etile.p);
+    else LAUNCH(ctx, k_tl_etile_identity, grid_for(nel, 256), 256, 0, nel, te, etile.p);
+    // T2: column owners
     DevBuf<int32_t> owner;
-    DevBuf<uint32_t> adjcnt, adjptr, adj;
     owner.alloc(pool, (size_t)ncl + 1);
-    adjcnt.alloc(pool, (size_t)ncl + 2); adjptr.alloc(pool, (size_t)ncl + 2);
     LAUNCH(ctx, k_tl_fill_i32, grid_for(ncl + 1, 256), 256, 0, owner.p, ncl + 1, INT_MAX);
-    CUDA_CHECK(cudaMemsetAsync(adjcnt.p, 0, (size_t)(ncl + 2) * sizeof(uint32_t), st));
-    adj.alloc(pool, (size_t)(nel * ND));
-    {
-        const size_t np = (size_t)(nel * ND);
-        uint32_t *k1 = reinterpret_cast<uint32_t *>(tl_scratch(ctx, 3 * np * sizeof(uint32_t))), *k2 = k1 + np, *v1 = k2 + np;
-        LAUNCH(ctx, k_tl_owner_pairs<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, etile.p, nel, COLMAP(ctx), (uint32_t)ncl, owner.p, adjcnt.p, k1, v1);
-        tl_sort_pairs(ctx, k1, k2, v1, adj.p, nel * ND, bits_for(ncl));
-    }
-    tl_excl_scan(ctx, adjcnt.p, adjptr.p, ncl + 1);
-    const int64_t npairs = (int64_t)tl_read(ctx, adjptr.p + ncl);
+    LAUNCH(ctx, k_tl_owner<ND>, grid_for(nel * ND, 256), 256, 0, sy->edof.p, etile.p, nel, COLMAP(ctx), owner.p);
+    etile.release();
+    trace.mark("T1/T2 tiles+owners");
 
-    trace.mark("T2/T3 owners+adjacency");
-    // T4: CSC pattern
-    DevBuf<uint8_t> colcnt, hcnt;
-    DevBuf<uint16_t> ccnt;
-    DevBuf<int64_t> colptr0;
-    colcnt.alloc(pool, (size_t)ncl + 1); hcnt.alloc(pool, (size_t)ncl + 1); ccnt.alloc(pool, (size_t)ncl + 1); colptr0.alloc(pool, (size_t)ncl + 1);
-    CUDA_CHECK(cudaMemsetAsync(colcnt.p, 0, (size_t)ncl + 1, st));
-    CUDA_CHECK(cudaMemsetAsync(hcnt.p, 0, (size_t)ncl + 1, st));
-    CUDA_CHECK(cudaMemsetAsync(ccnt.p, 0, ((size_t)ncl + 1) * 2, st));
-    LAUNCH(ctx, k_tl_col_count<F>, grid_for(ncl, 128), 128, 0, adjptr.p, adj.p, edof.p, ncl, colcnt.p, ccnt.p, hcnt.p, err.p);
-    if (tl_read(ctx, err.p))
-        efg_throw(EFG_ERR_LIMIT, "tiled path: a matrix column has more than %d distinct rows (node valence too high); use EFG_OPT_PATH=1", TL_CAP);
-    {
-        cub::TransformInputIterator<int64_t, cub::CastOp<int64_t>, const uint8_t *> it(colcnt.p, cub::CastOp<int64_t>());
-        tl_excl_scan(ctx, it, colptr0.p, ncl + 1);
-    }
-    const int64_t nnz = tl_read(ctx, colptr0.p + ncl);
-    ctx->nnz = nnz;
-    ctx->rowval.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
-    ctx->colptr.alloc(pool, (size_t)ncl + 1);
-    LAUNCH(ctx, k_tl_col_fill<F>, grid_for(ncl + 1, 128), 128, 0, adjptr.p, adj.p, edof.p, ncl, colptr0.p, ctx->rowval.p, ctx->colptr.p);
-
-    trace.mark("T4 pattern");
+    const int32_t *edof_p = sy->edof.p;
+    const uint32_t *adj_p = sy->adj.p, *adjptr_p = sy->adjptr.p;
+    const int64_t *colptr0_p = sy->colptr0.p;
     // T5: tile column lists, tile-order slot / gather offsets, runs
     DevBuf<uint32_t> tkeys, tcols;
     tkeys.alloc(pool, (size_t)ncl + 1); tcols.alloc(pool, (size_t)ncl + 1);
@@ -1307,11 +1354,11 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     const int64_t nowned = tl_read(ctx, tcol_ptr.p + ntiles);
     {
         cub::CountingInputIterator<int64_t> cnt_it(0);
-        cub::TransformInputIterator<int64_t, GatherU8, cub::CountingInputIterator<int64_t>> it8(cnt_it, GatherU8{colcnt.p, tcols.p, nowned});
+        cub::TransformInputIterator<int64_t, GatherU8, cub::CountingInputIterator<int64_t>> it8(cnt_it, GatherU8{sy->colcnt.p, tcols.p, nowned});
         tl_excl_scan(ctx, it8, tcol_slot.p, nowned + 1);
-        cub::TransformInputIterator<int64_t, GatherU16, cub::CountingInputIterator<int64_t>> it16(cnt_it, GatherU16{ccnt.p, tcols.p, nowned});
+        cub::TransformInputIterator<int64_t, GatherU16, cub::CountingInputIterator<int64_t>> it16(cnt_it, GatherU16{sy->ccnt.p, tcols.p, nowned});
         tl_excl_scan(ctx, it16, tcol_gidx.p, nowned + 1);
-        cub::TransformInputIterator<int64_t, GatherU8, cub::CountingInputIterator<int64_t>> ith(cnt_it, GatherU8{hcnt.p, tcols.p, nowned});
+        cub::TransformInputIterator<int64_t, GatherU8, cub::CountingInputIterator<int64_t>> ith(cnt_it, GatherU8{sy->hcnt.p, tcols.p, nowned});
         tl_excl_scan(ctx, ith, tcol_heavy.p, nowned + 1);
     }
     const int64_t ncontrib = tl_read(ctx, tcol_gidx.p + nowned);
@@ -1331,7 +1378,7 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     DevBuf<TileRun> runs;
     runs.alloc(pool, (size_t)(nruns > 0 ? nruns : 1));
     run_firstk.alloc(pool, (size_t)(nruns > 0 ? nruns : 1));
-    LAUNCH(ctx, k_tl_run_fill, grid_for(nowned, 256), 256, 0, rflag.p, runidx.p, tkeys.p, tcols.p, nowned, tcol_slot.p, tcol_ptr.p, colptr0.p, runs.p, run_firstk.p);
+    LAUNCH(ctx, k_tl_run_fill, grid_for(nowned, 256), 256, 0, rflag.p, runidx.p, tkeys.p, tcols.p, nowned, tcol_slot.p, tcol_ptr.p, colptr0_p, runs.p, run_firstk.p);
     LAUNCH(ctx, k_tl_run_len, grid_for(nruns, 256), 256, 0, run_firstk.p, nruns, nowned, tcol_slot.p, runs.p);
 
     trace.mark("T5 tile columns/runs");
@@ -1342,7 +1389,7 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     uint64_t *ek2 = ek1 + npk;
     int64_t *eidx = reinterpret_cast<int64_t *>(ek2 + npk);
     int32_t *eflag = reinterpret_cast<int32_t *>(ek1);       // ek1 is dead once sorted into ek2
-    LAUNCH(ctx, k_tl_telem_keys<ND>, grid_for(nel * ND, 256), 256, 0, edof.p, nel, COLMAP(ctx), owner.p, ntiles, ek1);
+    LAUNCH(ctx, k_tl_telem_keys<ND>, grid_for(nel * ND, 256), 256, 0, edof_p, nel, COLMAP(ctx), owner.p, ntiles, ek1);
     tl_sort_keys(ctx, ek1, ek2, nel * ND, 36 + bits_for(ntiles));   // out-of-range pairs carry tile id ntiles: they sort last
     trace.mark("  T6a keys+sort64");
     CUDA_CHECK(cudaMemsetAsync(eflag, 0, ((size_t)npairs + 1) * sizeof(int32_t), st));
@@ -1364,15 +1411,12 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     pc_hist.alloc(pool, (size_t)ntiles * 17);
     CUDA_CHECK(cudaMemsetAsync(pc_hist.p, 0, (size_t)ntiles * 17 * sizeof(uint32_t), st));
     LAUNCH(ctx, k_tl_telem_fill, grid_for(npairs, 256), 256, 0, ek2, npairs, eflag, eidx, telem_key.p, emask.p, key2.p, val2.p, pc_hist.p);
-    trace.mark("  T6c alloc+telem_fill");
-    trace.mark("  T6d release");
     tl_sort_pairs(ctx, key2.p, key2s.p, val2.p, order2.p, ntelem, 5 + bits_for(ntiles));
     trace.mark("  T6e sort popcount");
     LAUNCH(ctx, k_tl_invert, grid_for(ntelem, 256), 256, 0, order2.p, ntelem, newpos.p);
     DevBuf<int64_t> telem_ptr;
     telem_ptr.alloc(pool, (size_t)ntiles + 1);
     LAUNCH(ctx, k_tl_lower_bounds<uint64_t>, grid_for(ntiles + 1, 256), 256, 0, telem_key.p, ntelem, ntiles, 32, telem_ptr.p);
-    trace.mark("  T6f invert+bounds");
     td->tconn.alloc(pool, (size_t)(ntelem * F::GK + 1));
     td->tmask.alloc(pool, (size_t)ntelem + 1);
     LAUNCH(ctx, k_tl_tconn<F::GK>, grid_for(ntelem, 256), 256, 0, order2.p, ntelem, telem_key.p, emask.p, gm.conn.p, td->tconn.p, td->tmask.p);
@@ -1406,6 +1450,29 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
     td->tiles.alloc(pool, (size_t)ntiles);
     LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tl_gsz<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
            nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
+    int32_t hmax[8];
+    CUDA_CHECK(cudaMemcpyAsync(hmax, maxima.p, sizeof hmax, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    ctx->tl.max_nq = hmax[1] / ND; ctx->tl.max_nslot = 0; ctx->tl.max_nelem = hmax[3]; ctx->tl.max_nrun = 0;
+    ctx->tl.tile_elems = te;
+    td->stage_bytes = 0;
+    td->meta_max = 0;
+    td->smem_bytes = hmax[0];                                  // max over tiles of (stage + gather metadata + geometry block)
+    td->persist = tl_persist<F>();
+    if (td->persist) {      // fixed areas: the next tile's blocks are fetched while the current tile still uses the others
+        td->off_meta = hmax[4]; td->off_geo = hmax[4] + hmax[5]; td->off_gs = hmax[4] + hmax[5] + hmax[6];
+        td->smem_bytes = hmax[4] + hmax[5] + hmax[6] + hmax[7];     // (hmax[7] = 0 for the one-thread-per-element forms)
+    }
+    if (hmax[1] > 65533)
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile stages %d element-matrix entries (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[1]);
+    if (hmax[2] > 65535)
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile gathers %d heavy contributions (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[2]);
+    if (td->smem_bytes > 225 * 1024)
+        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile needs %d bytes of shared memory; lower EFG_OPT_TILE_ELEMS", td->smem_bytes);
+    // Known now: the shared memory the numeric kernel would need with this tile size.  If it does not let two CTAs share an
+    // SM the caller retries with a smaller size -- so stop here, before the (expensive) geometry blocks and gather words.
+    if (ctx->opt_tile_elems == 0 && te > 32 && td->smem_bytes > ctx->tl_smem_budget) { td->complete = false; trace.mark("tile descriptors (too large)"); return; }
+
     tl_excl_scan(ctx, mbytes.p, moff.p, (int64_t)ntiles + 1);
     const int64_t meta_total = tl_read(ctx, moff.p + ntiles);
     LAUNCH(ctx, k_tl_tiles_meta0, grid_for(ntiles, 256), 256, 0, ntiles, moff.p, td->tiles.p);
@@ -1417,43 +1484,82 @@ template <class F> static void tiled_symbolic_te(efg_ctx *ctx, int te)
         CUDA_CHECK(cudaMemsetAsync(td->geo.p, 0, (size_t)(td->geo_total > 0 ? td->geo_total : 16), st));
         LAUNCH(ctx, k_tl_geo_fill<F::GK>, grid_for(ntiles, 1, (int64_t)148 * 16), 128, 0, ntiles, td->tiles.p, tlocal, tnodes, td->tmask.p, gm.xy.p, td->geo.p);
     }
-    int32_t hmax[8];
-    CUDA_CHECK(cudaMemcpyAsync(hmax, maxima.p, sizeof hmax, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
-    ctx->tl.max_nq = hmax[1] / ND; ctx->tl.max_nslot = 0; ctx->tl.max_nelem = hmax[3]; ctx->tl.max_nrun = 0;
-    if (hmax[1] > 65533)
-        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile stages %d element-matrix entries (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[1]);
-    if (hmax[2] > 65535)
-        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile gathers %d heavy contributions (> 65535); lower EFG_OPT_TILE_ELEMS", hmax[2]);
-    td->stage_bytes = 0;
-    td->meta_max = 0;
-    td->smem_bytes = hmax[0];                                  // max over tiles of (stage + gather metadata + geometry block)
-    td->persist = tl_persist<F>();
-    if (td->persist) {      // fixed areas: the next tile's blocks are fetched while the current tile still uses the others
-        td->off_meta = hmax[4]; td->off_geo = hmax[4] + hmax[5]; td->off_gs = hmax[4] + hmax[5] + hmax[6];
-        td->smem_bytes = hmax[4] + hmax[5] + hmax[6] + hmax[7];     // (hmax[7] = 0 for the one-thread-per-element forms)
-    }
-    if (td->smem_bytes > 225 * 1024)
-        efg_throw(EFG_ERR_LIMIT, "tiled path: a tile needs %d bytes of shared memory; lower EFG_OPT_TILE_ELEMS", td->smem_bytes);
     td->meta_bytes = meta_total;
 
     trace.mark("tile descriptors");
     // T8: gather lists into the metadata blocks
     td->meta.alloc(pool, (size_t)(meta_total > 0 ? meta_total : 16));
     CUDA_CHECK(cudaMemsetAsync(td->meta.p, 0, (size_t)(meta_total > 0 ? meta_total : 16), st));
-    LAUNCH(ctx, k_tl_gather_build<F>, grid_for(nowned, 128), 128, 0, tkeys.p, tcols.p, nowned, adjptr.p, adj.p, edof.p, colptr0.p, ctx->rowval.p,
+    LAUNCH(ctx, k_tl_gather_build<F>, grid_for(nowned, 128), 128, 0, tkeys.p, tcols.p, nowned, adjptr_p, adj_p, edof_p, colptr0_p, ctx->rowval.p,
            telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, td->meta.p, err.p);
     LAUNCH(ctx, k_tl_meta_finish, grid_for(ntiles, 128), 128, 0, ntiles, td->tiles.p, runs.p, td->meta.p);
     const int e2 = tl_read(ctx, err.p);
     if (e2) efg_throw(EFG_ERR_LIMIT, "tiled path: a tile's gather list exceeds 16-bit offsets (%d); lower EFG_OPT_TILE_ELEMS", e2);
 
     trace.mark("T8 gather build");
-    ctx->nzval.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
+    if (ctx->nzval.n < (size_t)(nnz > 0 ? nnz : 1)) ctx->nzval.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
     ctx->tl.ntiles = ntiles;
-    ctx->tl.tile_elems = te;
     ctx->tl.sum_tile_elems = ntelem;
     ctx->tl.numeric_bytes = (GEO ? td->geo_total : ntelem * (F::GK * 4 + 2) + gm.nnodes * 16) + meta_total + nnz * 8 + (int64_t)ntiles * sizeof(TileDescFull);
     if (GEO) { td->tconn.release(); td->tmask.release(); }     // the numeric kernel reads the geometry blocks instead
+    td->complete = true;
+}
+
+// next smaller tile size to try after `te` needed `smem` bytes against a budget of `budget`
+template <class F> static int tl_next_tile_elems(int te, int smem, int budget)
+{
+    const double scale = (budget > 0 && smem > budget) ? (double)budget / smem : 0.97;
+    int next = 32;
+    if (F::SPLIT) {
+        for (int c : TL_TILE_SIZES) {
+            if (c >= te) continue;
+            const double rounds = (double)c * F::ND / tl_block<F>();
+            if (rounds / ceil(rounds) < 0.85 && c > 32) continue;
+            next = c;
+            if (c <= te * scale * 1.03) break;      // (else: this candidate would overflow as well)
+        }
+    } else {
+        next = ((int)(te * (scale < 0.97 ? scale * 0.99 : 0.97))) & ~7;     // the footprint scales with te
+        if (next < 32) next = 32;
+    }
+    return next;
+}
+
+// phase B with the tile-size search: the largest tile whose shared-memory footprint lets two CTAs share an SM
+template <class F> static void tiled_tiles_search(efg_ctx *ctx)
+{
+    if (!tiled_sym(ctx)) efg_throw(EFG_ERR_STATE, "tile phase without a pattern phase");
+    tiled_order<F>(ctx);
+    ctx->tl_smem_budget = tl_smem_budget<F>();
+    if (ctx->opt_tile_elems > 0) { tiled_tiles<F>(ctx, ctx->opt_tile_elems); return; }
+    // start from the size the previous symbolic phase of this form settled on (re-assembly after efg_set_mesh, time
+    // stepping with a changing mesh): the search below then succeeds at the first attempt
+    const int vkind = ctx->mesh[0].kind;
+    const bool hinted = ctx->te_hint > 0 && ctx->te_hint_form == ctx->form_req && ctx->te_hint_kind == vkind && ctx->te_hint_quad == ctx->quad_req;
+    int te = hinted ? ctx->te_hint : tl_default_tile_elems<F>();
+    for (;;) {
+        int smem = 0;
+        try {
+            tiled_tiles<F>(ctx, te);
+            TiledData *td = tiled_data(ctx);
+            smem = td->smem_bytes;
+            if (td->complete && (te <= 32 || tl_ctas_per_sm<F>(ctx) >= 2)) {      // two co-resident CTAs overlap each other's phases
+                ctx->te_hint = te; ctx->te_hint_form = ctx->form_req; ctx->te_hint_kind = vkind; ctx->te_hint_quad = ctx->quad_req;
+                return;
+            }
+        } catch (const EfgError &e) {
+            if (e.code != EFG_ERR_LIMIT || te <= 32) throw;
+        }
+        te = tl_next_tile_elems<F>(te, smem, ctx->tl_smem_budget);
+    }
+}
+
+template <class F> void tiled_symbolic(efg_ctx *ctx)
+{
+    if (!(ctx->have_pattern && tiled_sym(ctx))) tiled_pattern<F>(ctx);
+    tiled_tiles_search<F>(ctx);
+    delete tiled_sym(ctx);          // the pattern-phase tables are not needed once the tiles exist
+    tiled_sym(ctx) = nullptr;
 }
 
 template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(efg_ctx *ctx)

@@ -219,9 +219,24 @@ static void ingest_index(efg_ctx *ctx, const int64_t *src, int64_t n, int64_t lo
     if (herr) efg_throw(EFG_ERR_INDEX, "%s: index out of range [%lld, %lld]", what, (long long)lo, (long long)hi);
 }
 
+static void wait_copies(efg_ctx *ctx)
+{
+    if (ctx->copy_pending && ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        ctx->copy_pending = false;
+    }
+}
+static bool is_device_ptr(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
 static void invalidate(efg_ctx *ctx)
 {
+    wait_copies(ctx);              // an asynchronous pattern fetch may still read colptr / rowval
     ctx->have_symbolic = false;
+    ctx->have_pattern = false;
     ctx->have_values = false;
     ctx->nnz = 0;
     ctx->colptr.release(); ctx->rowval.release(); ctx->nzval.release();
@@ -277,20 +292,13 @@ int efg_create(int device, efg_ctx **out)
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
         cudaEventCreate(&ctx->evn0) != cudaSuccess || cudaEventCreate(&ctx->evn1) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_tab, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_pattern, cudaEventDisableTiming) != cudaSuccess) {
         cudaGetLastError();
         delete ctx;
         return EFG_ERR_CUDA;
     }
     ctx->pool.stream = ctx->stream;
-    {   // keep freed blocks in the device's default memory pool instead of returning them to the OS at every sync
-        cudaMemPool_t mp;
-        if (cudaDeviceGetDefaultMemPool(&mp, device) == cudaSuccess) {
-            uint64_t thr = UINT64_MAX;
-            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-        cudaGetLastError();
-    }
     tables_register(ctx);
     *out = ctx;
     return EFG_OK;
@@ -305,14 +313,13 @@ int efg_destroy(efg_ctx *ctx)
     invalidate(ctx);
     for (auto &m : ctx->mesh) { m.conn.release(); m.xy.release(); }
     for (auto &s : ctx->space) s.dof.release();
-    ctx->rfirst.release(); ctx->rlast1.release(); ctx->roff.release(); ctx->scratch.release();
+    ctx->rfirst.release(); ctx->rlast1.release(); ctx->roff.release(); ctx->scratch.release(); ctx->cstage[0].release(); ctx->cstage[1].release();
     cudaStreamSynchronize(ctx->stream);
-    {
-        cudaMemPool_t mp;
-        if (cudaDeviceGetDefaultMemPool(&mp, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(mp, 0);
-        cudaGetLastError();
-    }
-    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evn0); cudaEventDestroy(ctx->evn1); cudaEventDestroy(ctx->ev_tab);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    ctx->pool.destroy();           // the ctx's private arena goes back to the driver; nothing process-global is touched
+    cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evn0); cudaEventDestroy(ctx->evn1); cudaEventDestroy(ctx->ev_tab); cudaEventDestroy(ctx->ev_pattern);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return EFG_OK;
@@ -493,42 +500,64 @@ static void check_form_inputs(efg_ctx *ctx, int form)
     }
 }
 
+// The symbolic phase in two steps.  want_tiles = false stops after the CSC pattern (colptr / rowval / nnz) on the tiled
+// path, so the caller can size its arrays and start moving the pattern to the host while the tiles are built.
+static void run_symbolic(efg_ctx *ctx, int form, int quad, bool want_tiles)
+{
+    if (!ctx->started) efg_throw(EFG_ERR_STATE, "efg_symbolic before efg_start");
+    check_form_inputs(ctx, form);
+    const bool same = ctx->form == form && ctx->quad == quad;
+    if (ctx->have_symbolic && same) return;
+    if (ctx->have_pattern && same && !want_tiles) return;
+    const int vkind = ctx->mesh[0].kind;
+    const int npts = quad_npts(vkind, quad);       // (the symbolic phase does not read the tables)
+    if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, vkind);
+    const bool resume = ctx->have_pattern && same;      // the pattern exists, the tiles are pending
+    if (!resume) { invalidate(ctx); ctx->symbolic_ms = 0; }
+    CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
+    int path = resume ? ctx->path : (ctx->opt_path == 1 ? 1 : 2);
+    ctx->form_req = form; ctx->quad_req = quad;
+    bool complete = false;
+    bool ok = false;
+    try {
+    ok = dispatch_form(form, vkind, npts, [&](auto F) {
+        using Form = decltype(F);
+        if (path == 2) {
+            try {
+                if (!resume) tiled_pattern<Form>(ctx);
+                if (want_tiles) { tiled_symbolic<Form>(ctx); complete = true; }
+            } catch (const EfgError &e) {
+                // auto mode: a mesh beyond the tiled path's limits (node valence, ...) takes the general two-pass path
+                if (e.code != EFG_ERR_LIMIT || ctx->opt_path == 2) throw;
+                invalidate(ctx);
+                path = 1;
+            }
+        }
+        if (path == 1) { twopass_symbolic<Form>(ctx); ctx->have_pattern = true; complete = true; CUDA_CHECK(cudaEventRecord(ctx->ev_pattern, ctx->stream)); }
+    });
+    } catch (...) { invalidate(ctx); throw; }       // no half-built state survives an error
+    if (!ok) efg_throw(EFG_ERR_INVALID, "form %d is not available for element kind %d with rule %d", form, vkind, quad);
+    CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->symbolic_ms += ms;
+    ctx->form = form; ctx->quad = quad; ctx->nq = npts; ctx->vkind = vkind; ctx->path = path;
+    ctx->have_symbolic = complete;
+}
+
+int efg_pattern(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
+{
+    API_BEGIN(ctx)
+    run_symbolic(ctx, form, quad, false);
+    if (nnz_out) *nnz_out = ctx->nnz;
+    API_END(ctx)
+}
+
 int efg_symbolic(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
 {
     API_BEGIN(ctx)
-    if (!ctx->started) efg_throw(EFG_ERR_STATE, "efg_symbolic before efg_start");
-    check_form_inputs(ctx, form);
-    if (!(ctx->have_symbolic && ctx->form == form && ctx->quad == quad)) {
-        invalidate(ctx);
-        const int vkind = ctx->mesh[0].kind;
-        const int npts = quad_npts(vkind, quad);       // (the symbolic phase does not read the tables)
-        if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, vkind);
-        CUDA_CHECK(cudaEventRecord(ctx->ev0, ctx->stream));
-        int path = ctx->opt_path == 1 ? 1 : 2;
-        ctx->form_req = form; ctx->quad_req = quad;
-        const bool ok = dispatch_form(form, vkind, npts, [&](auto F) {
-            using Form = decltype(F);
-            if (path == 2) {
-                try {
-                    tiled_symbolic<Form>(ctx);
-                } catch (const EfgError &e) {
-                    // auto mode: a mesh beyond the tiled path's limits (node valence, ...) takes the general two-pass path
-                    if (e.code != EFG_ERR_LIMIT || ctx->opt_path == 2) throw;
-                    invalidate(ctx);
-                    path = 1;
-                }
-            }
-            if (path == 1) twopass_symbolic<Form>(ctx);
-        });
-        if (!ok) efg_throw(EFG_ERR_INVALID, "form %d is not available for element kind %d with rule %d", form, vkind, quad);
-        CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
-        CUDA_CHECK(cudaEventSynchronize(ctx->ev1));
-        float ms = 0;
-        CUDA_CHECK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-        ctx->symbolic_ms = ms;
-        ctx->form = form; ctx->quad = quad; ctx->nq = npts; ctx->vkind = vkind; ctx->path = path;
-        ctx->have_symbolic = true;
-    }
+    run_symbolic(ctx, form, quad, true);
     if (nnz_out) *nnz_out = ctx->nnz;
     API_END(ctx)
 }
@@ -536,6 +565,7 @@ int efg_symbolic(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
 int efg_numeric(efg_ctx *ctx, const double *params, int nparams)
 {
     API_BEGIN(ctx)
+    if (!ctx->have_symbolic && ctx->have_pattern) run_symbolic(ctx, ctx->form, ctx->quad, true);     // efg_pattern came first: build the tiles now
     if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_numeric before efg_symbolic");
     const int need = (ctx->form == EFG_FORM_ELASTICITY || ctx->form == EFG_FORM_STOKES_GEN) ? 9 : 1;
     if (!params || nparams != need) efg_throw(EFG_ERR_INVALID, "form %d takes %d parameter(s)", ctx->form, need);
@@ -558,35 +588,70 @@ int efg_assemble(efg_ctx *ctx, int form, int quad, const double *params, int npa
     return efg_numeric(ctx, params, nparams);
 }
 
+// ---- result -> caller's arrays.  The pattern travels on the ctx's COPY stream (behind ev_pattern), the values on the main
+// stream behind the numeric kernel: a pattern fetch issued right after efg_pattern overlaps the tile phase and the numeric
+// kernel, and the PCIe link stays busy from the moment the pattern exists.
+static void ensure_copy_stream(efg_ctx *ctx)
+{
+    if (!ctx->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->ev_copy) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
+}
+static void enqueue_pattern_copy(efg_ctx *ctx, int64_t *colptr, int64_t *rowval)
+{
+    ensure_copy_stream(ctx);
+    cudaStream_t cs = ctx->copy_stream;
+    CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_pattern, 0));
+    const int64_t ncl = ctx->ncl;
+    if (colptr) CUDA_CHECK(cudaMemcpyAsync(colptr, ctx->colptr.p, (size_t)(ncl + 1) * sizeof(int64_t), cudaMemcpyDefault, cs));
+    if (rowval && ctx->nnz > 0) {
+        if (is_device_ptr(rowval)) {        // device destination: widen in place, no staging
+            k_rowval_out<<<grid_for(ctx->nnz, 256), 256, 0, cs>>>(ctx->rowval.p, ctx->nnz, rowval);
+            ctx->launches++;
+            CUDA_CHECK(cudaGetLastError());
+        } else {
+            // Int32 0-based -> Int64 1-based in two staging buffers; a chunk's conversion (~0.1 ms) is short against its
+            // copy (~4.7 ms at PCIe Gen5), the event keeps a buffer from being overwritten before its copy has finished
+            const int64_t CH = (int64_t)32 << 20;
+            const int64_t cap = ctx->nnz < CH ? ctx->nnz : CH;
+            for (int b = 0; b < 2; b++)
+                if (ctx->cstage[b].n < (size_t)cap) ctx->cstage[b].alloc(ctx->pool, (size_t)cap);
+            int b = 0;
+            for (int64_t o = 0; o < ctx->nnz; o += CH, b ^= 1) {
+                const int64_t m = ctx->nnz - o < CH ? ctx->nnz - o : CH;
+                k_rowval_out<<<grid_for(m, 256), 256, 0, cs>>>(ctx->rowval.p + o, m, ctx->cstage[b].p);
+                ctx->launches++;
+                CUDA_CHECK(cudaGetLastError());
+                CUDA_CHECK(cudaMemcpyAsync(rowval + o, ctx->cstage[b].p, (size_t)m * sizeof(int64_t), cudaMemcpyDefault, cs));
+            }
+        }
+    }
+    ctx->copy_pending = true;
+}
+
+int efg_fetch_pattern_async(efg_ctx *ctx, int64_t *colptr, int64_t *rowval)
+{
+    API_BEGIN(ctx)
+    if (!ctx->have_pattern) efg_throw(EFG_ERR_STATE, "efg_fetch_pattern_async before efg_pattern / efg_symbolic");
+    enqueue_pattern_copy(ctx, colptr, rowval);
+    API_END(ctx)
+}
+
 int efg_fetch_csc(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval)
 {
     API_BEGIN(ctx)
-    if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_fetch_csc before efg_symbolic");
+    if (!ctx->have_pattern) efg_throw(EFG_ERR_STATE, "efg_fetch_csc before efg_symbolic");
     if (nzval && !ctx->have_values) efg_throw(EFG_ERR_STATE, "efg_fetch_csc(nzval) before efg_numeric");
-    const int64_t ncl = ctx->ncl;
-    if (colptr) CUDA_CHECK(cudaMemcpyAsync(colptr, ctx->colptr.p, (size_t)(ncl + 1) * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+    if (colptr || rowval) enqueue_pattern_copy(ctx, colptr, rowval);
     if (nzval && ctx->nnz > 0) CUDA_CHECK(cudaMemcpyAsync(nzval, ctx->nzval.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDefault, ctx->stream));
-    if (rowval && ctx->nnz > 0) {
-        const int64_t CH = (int64_t)32 << 20;
-        DevBuf<int64_t> stage[2];
-        const int64_t cap = ctx->nnz < CH ? ctx->nnz : CH;
-        stage[0].alloc(ctx->pool, (size_t)cap); stage[1].alloc(ctx->pool, (size_t)cap);
-        int b = 0;
-        for (int64_t o = 0; o < ctx->nnz; o += CH, b ^= 1) {
-            const int64_t m = ctx->nnz - o < CH ? ctx->nnz - o : CH;
-            LAUNCH(ctx, k_rowval_out, grid_for(m, 256), 256, 0, ctx->rowval.p + o, m, stage[b].p);
-            CUDA_CHECK(cudaMemcpyAsync(rowval + o, stage[b].p, (size_t)m * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
-        }
-        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    }
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    wait_copies(ctx);             // also completes an earlier efg_fetch_pattern_async
     API_END(ctx)
 }
 
 int efg_device_csc(efg_ctx *ctx, const int64_t **colptr, const int32_t **rowval, const double **nzval)
 {
     API_BEGIN(ctx)
-    if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_device_csc before efg_symbolic");
+    if (!ctx->have_pattern) efg_throw(EFG_ERR_STATE, "efg_device_csc before efg_symbolic");
     if (colptr) *colptr = ctx->colptr.p;
     if (rowval) *rowval = ctx->rowval.p;
     if (nzval) *nzval = ctx->nzval.p;
@@ -594,12 +659,6 @@ int efg_device_csc(efg_ctx *ctx, const int64_t **colptr, const int32_t **rowval,
 }
 
 // ---- SURVEY 8f rows f1 / f2 (efg_vector.cuh) ----------------------------------------------------------
-static bool is_device_ptr(const void *p)
-{
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
-}
 static float elapsed_sync(efg_ctx *ctx)
 {
     float ms = 0;

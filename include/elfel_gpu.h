@@ -46,8 +46,11 @@
  *   - One ctx = one device + one CUDA stream; not re-entrant.  Different ctx may be used from
  *     different host threads.  Multi-GPU = one ctx (one process) per GPU, each assembling a
  *     contiguous block of matrix columns (efg_set_column_range); no communication is needed.
- *   - The quadrature tables and form parameters live in __constant__ memory of the library: within one process
- *     run the numeric phase of one ctx at a time (multi-GPU = one process per GPU, as in bench.py).
+ *   - The quadrature tables and form parameters live in __constant__ memory (one copy per device).  The library
+ *     hands them over between the ctx of a device in stream order (per-device lock + events), so several ctx --
+ *     on one device or one per device, from one host thread or several -- may be used freely and asynchronously.
+ *   - Device memory comes from a private arena per ctx (plain cudaMalloc slabs, sub-allocated on the host); no
+ *     process-global allocator state is touched, efg_destroy returns everything to the driver.
  *   - There is no CPU fallback: without a CUDA device efg_create fails with EFG_ERR_CUDA.
  */
 #ifndef ELFEL_GPU_H
@@ -139,6 +142,11 @@ int efg_set_column_ranges(efg_ctx *ctx, int64_t nranges, const int64_t *col_firs
 /* Symbolic phase: CSC pattern + scatter maps on the device.  quad_rule: triangles npts (1|3),
  * squares Gauss order (1..3).  Cached until mesh/space/start/range/options change. */
 int efg_symbolic(efg_ctx *ctx, int form_id, int quad_rule, int64_t *nnz_out);
+/* First half of efg_symbolic only: the CSC pattern (colptr / rowval / nnz); the scatter maps are built by the next
+ * efg_symbolic / efg_numeric / efg_assemble call.  For callers that overlap: efg_pattern -> allocate the three output
+ * arrays (nnz known) -> efg_fetch_pattern_async -> efg_numeric -> efg_fetch_csc(NULL, NULL, nzval).
+ * Replaces what finish! gets from sparse() (src/Assemblers.jl:121-123) in two steps: structure first, values later. */
+int efg_pattern(efg_ctx *ctx, int form_id, int quad_rule, int64_t *nnz_out);
 /* Numeric phase: element quadrature loop fused with the deterministic scatter -> nzval (device). */
 int efg_numeric(efg_ctx *ctx, const double *params, int nparams);
 /* symbolic (if not cached) + numeric. */
@@ -148,6 +156,10 @@ int efg_assemble(efg_ctx *ctx, int form_id, int quad_rule, const double *params,
 /* finish!: copy out the SparseMatrixCSC fields (Int64 1-based colptr/rowval, Float64 nzval).
  * Any pointer may be NULL to skip that array.  Destination may be host or device memory. */
 int efg_fetch_csc(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval);
+/* Starts copying colptr / rowval (either may be NULL) on the ctx's copy stream and returns at once; the copy overlaps
+ * whatever the ctx does next (tile phase, numeric kernel).  The arrays are complete -- and must stay valid until --
+ * the next efg_fetch_csc call on this ctx (any arguments; it waits for the copy) or efg_destroy. */
+int efg_fetch_pattern_async(efg_ctx *ctx, int64_t *colptr, int64_t *rowval);
 /* Device-resident result for a consumer that stays on the GPU (colptr: Int64 1-based,
  * rowval: Int32 0-based, nzval: Float64); valid until the next start/symbolic/destroy. */
 int efg_device_csc(efg_ctx *ctx, const int64_t **colptr, const int32_t **rowval, const double **nzval);

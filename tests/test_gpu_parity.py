@@ -260,3 +260,72 @@ def test_auto_path_falls_back_for_high_valence_mesh(oracle):
             cp, rv, nz = eng.fetch_csc()
             assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz)
         eng.close()
+
+
+def test_two_contexts_with_different_rules_interleave(oracle):
+    """The quadrature tables / parameters sit in per-device __constant__ memory shared by every ctx of the process, and
+    efg_numeric returns without synchronising: two engines on one device with different rules and parameters, their
+    numeric calls interleaved with no host sync in between, must both produce their own matrix."""
+    pa = efg.heat_problem(efg.T6, 120, True)                 # triangle rule, 3 points, kappa = 1
+    pb = efg.heat_problem(efg.Q4, 150, True, kappa=2.5)      # Gauss order 2
+    pc = efg.heat_problem(efg.T6, 120, True, kappa=0.5, quad=1)
+    want = [oracle.assemble(*efg.oracle_args(p), p.ndofs, p.ndofs) for p in (pa, pb, pc)]
+    engs = []
+    for p in (pa, pb, pc):
+        e = efg.Engine(0)
+        efg.load_problem(e, p)
+        e.symbolic(p.form.form_id, p.quad)
+        engs.append(e)
+    for _ in range(6):                                       # a -> b -> c -> a ... no synchronisation in between
+        for e, p in zip(engs, (pa, pb, pc)):
+            e.numeric(p.form.params())
+    for e, p, (ocp, orv, onz) in zip(engs, (pa, pb, pc), want):
+        cp, rv, nz = e.fetch_csc()
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+        assert np.all(np.abs(nz - onz) <= ATOL + RTOL * np.abs(onz)), f"{p.name}: max |d| = {np.abs(nz - onz).max()}"
+        e.close()
+
+
+def test_pattern_first_then_overlapped_fetch(oracle):
+    """efg_pattern -> (caller sizes its arrays) -> efg_fetch_pattern_async -> efg_numeric -> efg_fetch_csc(nzval): the sequence
+    of the Julia shim's finish!; same matrix as the one-call sequence, also when repeated and with a column range."""
+    prob = efg.elasticity_problem(45, efg.T6, True)
+    ocp, orv, onz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    eng = efg.Engine(0)
+    for rep in range(2):
+        efg.load_problem(eng, prob)
+        nnz = eng.pattern(prob.form.form_id, prob.quad)
+        assert nnz == len(orv)
+        cp = np.empty(prob.ndofs + 1, dtype=np.int64); rv = np.empty(nnz, dtype=np.int64); nz = np.empty(nnz)
+        eng.fetch_pattern_async(cp, rv)
+        eng.numeric(prob.form.params())
+        eng.fetch_csc(None, None, nz)
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+        assert np.all(np.abs(nz - onz) <= ATOL + RTOL * np.abs(onz))
+    # pattern only, fetched synchronously, values never computed
+    efg.load_problem(eng, prob, column_range=(101, 4000))
+    nnz = eng.pattern(prob.form.form_id, prob.quad)
+    cp, rv, _ = eng.fetch_csc(np.empty(3901, dtype=np.int64), np.empty(nnz, dtype=np.int64), None)
+    assert np.array_equal(cp, ocp[100:4001] - ocp[100] + 1) and np.array_equal(rv, orv[ocp[100] - 1: ocp[4000] - 1])
+    with pytest.raises(efg.EfgError):
+        eng.fetch_csc(None, None, np.empty(nnz))             # no values yet
+    eng.close()
+
+
+def test_remesh_without_renumbering_is_rejected():
+    """efg_set_mesh with a different node count leaves the spaces stale: the next symbolic phase must say so
+    (EFG_ERR_STATE) instead of reading past the dof map."""
+    small, big = efg.heat_problem(efg.T3, 6), efg.heat_problem(efg.T3, 9)
+    eng = efg.Engine(0)
+    efg.load_problem(eng, small)
+    eng.assemble(small.form.form_id, small.quad, small.form.params())
+    eng.set_mesh(0, efg.T3, big.meshes[0].conn, big.meshes[0].xy)
+    eng.start(big.ndofs, big.ndofs)
+    with pytest.raises(efg.EfgError) as ei:
+        eng.assemble(big.form.form_id, big.quad, big.form.params())
+    assert ei.value.code == _lib.ERR_STATE
+    with pytest.raises(efg.EfgError):
+        eng.vec_assemble(_lib.VFORM_HEAT_LOAD, big.quad, [1.0], big.ndofs)
+    eng.set_space(0, 0, big.spaces[0].field.dofnums)
+    eng.assemble(big.form.form_id, big.quad, big.form.params())
+    eng.close()
