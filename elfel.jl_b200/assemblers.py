@@ -411,7 +411,12 @@ def assemble(ass: SysmatAssemblerGPU, form, elits, qpits):
         ass._assembled = True
         return ass
     eng.start(ass.nrow, ass.ncol)
-    eng.assemble(form.form_id, qpits[0].rule, form.params())
+    # structure first (-> nnz: the SparseMatrixCSC arrays can be allocated), and it starts travelling to the host on the
+    # copy stream while the scatter maps and the values are computed; finish() waits for it and fetches the values
+    nnz = eng.pattern(form.form_id, qpits[0].rule)
+    ass._out = (np.empty(ass.ncol + 1, dtype=np.int64), np.empty(nnz, dtype=np.int64), np.empty(nnz, dtype=np.float64))
+    eng.fetch_pattern_async(ass._out[0], ass._out[1])
+    eng.numeric(form.params())
     ass._assembled = True
     return ass
 
@@ -421,7 +426,8 @@ def finish(ass):
         raise _lib.EfgError(_lib.ERR_STATE, "finish before assemble")
     if isinstance(ass, SysvecAssemblerGPU):   # finish!(av): src/Assemblers.jl:230-232
         return ass.engine.fetch_vec()
-    colptr, rowval, nzval = ass.engine.fetch_csc()
+    colptr, rowval, nzval = ass._out
+    ass.engine.fetch_csc(None, None, nzval)
     return SparseMatrixCSC(ass.nrow, ass.ncol, colptr, rowval, nzval)
 
 

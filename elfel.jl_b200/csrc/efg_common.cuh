@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <new>
+#include <cstdlib>
 #include <algorithm>
 #include <iterator>
 
@@ -47,6 +48,7 @@ struct EfgError {
 struct DevPool {
     int64_t bytes = 0;                    // handed out
     int64_t reserved = 0;                 // held in slabs
+    int64_t peak = 0;                     // high-water mark of `bytes`
     cudaStream_t stream = nullptr;
     size_t next_slab = (size_t)256 << 20; // growth hint for the next slab (raised by reserve())
     struct Slab { char *base; size_t size; };
@@ -74,6 +76,7 @@ struct DevPool {
     bool grow(size_t need)
     {
         size_t want = need > next_slab ? need : next_slab;
+        if (want < (size_t)reserved / 8) want = round_up((size_t)reserved / 8);     // geometric growth: few slabs, bounded waste
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess && want > need) { cudaGetLastError(); want = need; e = cudaMalloc(&p, want); }
@@ -85,6 +88,8 @@ struct DevPool {
         }
         slabs.push_back(Slab{(char *)p, want});
         reserved += (int64_t)want;
+        next_slab = (size_t)256 << 20;          // a reserve() hint covers one slab
+        if (getenv("EFG_TRACE")) fprintf(stderr, "[efg trace] arena: new slab of %.2f GB (asked %.2f GB), %zu slabs, %.2f GB reserved\n", want / 1e9, need / 1e9, slabs.size(), reserved / 1e9);
         add_free((char *)p, want);
         return true;
     }
@@ -108,6 +113,7 @@ struct DevPool {
                 if (sz > n) free_blocks[p + n] = sz - n;
                 live[p] = n;
                 bytes += (int64_t)n;
+                if (bytes > peak) peak = bytes;
                 return p;
             }
             if (attempt == 0 && !grow(n)) break;
@@ -161,15 +167,13 @@ template <class T> struct DevBuf {
     {
         release();
         pool = &pl;
-        const int64_t before = pl.bytes;
         p = (T *)pl.alloc(count * sizeof(T));
-        held = pl.bytes - before;
         n = count;
     }
     void release()
     {
         if (p) {
-            if (pool) { pool->free(p); pool->bytes -= held; } else cudaFree(p);
+            if (pool) pool->free(p); else cudaFree(p);
         }
         p = nullptr; n = 0; held = 0;
     }

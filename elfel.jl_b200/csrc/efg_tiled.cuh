@@ -1187,12 +1187,19 @@ template <class F> static int tl_ctas_per_sm(efg_ctx *ctx)
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tl_block<F>(), (size_t)td->smem_bytes));
     return per_sm;
 }
-// dynamic shared memory a CTA may use if two CTAs are to share an SM
-template <class F> static int tl_smem_budget()
+// dynamic shared memory a CTA may use if two CTAs are to share an SM: half of the SM's shared memory minus the per-CTA
+// reservation and the kernel's static shared memory (the occupancy query stays the final arbiter)
+template <class F> static int tl_smem_budget(efg_ctx *ctx)
 {
-    size_t avail = 0;
-    if (cudaOccupancyAvailableDynamicSMemPerBlock(&avail, tl_numeric_kernel<F>(), 2, tl_block<F>()) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return (int)avail;
+    int per_sm = 0, reserved = 0, optin = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device));
+    CUDA_CHECK(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device));
+    CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    cudaFuncAttributes fa;
+    CUDA_CHECK(cudaFuncGetAttributes(&fa, tl_numeric_kernel<F>()));
+    int b = per_sm / 2 - reserved - (int)fa.sharedSizeBytes;
+    if (b > optin - (int)fa.sharedSizeBytes) b = optin - (int)fa.sharedSizeBytes;
+    return b > 0 ? b : 0;
 }
 
 // ---- phase A: the CSC pattern (independent of the tile size) --------------------------------------------------------
@@ -1215,7 +1222,7 @@ template <class F> static void tiled_pattern(efg_ctx *ctx)
     TlTrace trace(ctx);
     // one slab for everything the two phases allocate before nnz is known (pairs: edof + adj + 24 B of sort scratch, per
     // column: counts, offsets, owners, tile column lists), a second one below once nnz is known
-    pool.reserve((size_t)(nel * ND) * 36 + (size_t)nel * 24 + (size_t)ncl * 72 + ((size_t)64 << 20));
+    pool.reserve((size_t)(nel * ND) * 32 + (size_t)ncl * 24 + ((size_t)64 << 20));
 
     DevBuf<int> err;
     err.alloc(pool, 1);
@@ -1260,7 +1267,7 @@ template <class F> static void tiled_pattern(efg_ctx *ctx)
     ctx->nnz = nnz;
     // everything proportional to nnz and to the tile elements: rowval 4 + nzval 8 + gather words 4 (+ heavy lists) per
     // nonzero, geometry blocks and tile-element lists per pair
-    pool.reserve((size_t)nnz * 17 + (size_t)(nel * ND) * 12 + (size_t)nel * 40 + ((size_t)64 << 20));
+    pool.reserve((size_t)nnz * 9 + (size_t)(nel * ND) * 8 + ((size_t)64 << 20));
     ctx->rowval.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
     ctx->colptr.alloc(pool, (size_t)ncl + 1);
     LAUNCH(ctx, k_tl_col_fill<F>, grid_for(ncl + 1, 128), 128, 0, sy->adjptr.p, sy->adj.p, sy->edof.p, ncl, sy->colptr0.p, ctx->rowval.p, ctx->colptr.p);
@@ -1471,6 +1478,7 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
         efg_throw(EFG_ERR_LIMIT, "tiled path: a tile needs %d bytes of shared memory; lower EFG_OPT_TILE_ELEMS", td->smem_bytes);
     // Known now: the shared memory the numeric kernel would need with this tile size.  If it does not let two CTAs share an
     // SM the caller retries with a smaller size -- so stop here, before the (expensive) geometry blocks and gather words.
+    if (trace.on) fprintf(stderr, "[efg trace] te = %d: %d bytes of shared memory per CTA, budget %d\n", te, td->smem_bytes, ctx->tl_smem_budget);
     if (ctx->opt_tile_elems == 0 && te > 32 && td->smem_bytes > ctx->tl_smem_budget) { td->complete = false; trace.mark("tile descriptors (too large)"); return; }
 
     tl_excl_scan(ctx, mbytes.p, moff.p, (int64_t)ntiles + 1);
@@ -1497,7 +1505,6 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
     if (e2) efg_throw(EFG_ERR_LIMIT, "tiled path: a tile's gather list exceeds 16-bit offsets (%d); lower EFG_OPT_TILE_ELEMS", e2);
 
     trace.mark("T8 gather build");
-    if (ctx->nzval.n < (size_t)(nnz > 0 ? nnz : 1)) ctx->nzval.alloc(pool, (size_t)(nnz > 0 ? nnz : 1));
     ctx->tl.ntiles = ntiles;
     ctx->tl.sum_tile_elems = ntelem;
     ctx->tl.numeric_bytes = (GEO ? td->geo_total : ntelem * (F::GK * 4 + 2) + gm.nnodes * 16) + meta_total + nnz * 8 + (int64_t)ntiles * sizeof(TileDescFull);
@@ -1530,7 +1537,7 @@ template <class F> static void tiled_tiles_search(efg_ctx *ctx)
 {
     if (!tiled_sym(ctx)) efg_throw(EFG_ERR_STATE, "tile phase without a pattern phase");
     tiled_order<F>(ctx);
-    ctx->tl_smem_budget = tl_smem_budget<F>();
+    ctx->tl_smem_budget = tl_smem_budget<F>(ctx);
     if (ctx->opt_tile_elems > 0) { tiled_tiles<F>(ctx, ctx->opt_tile_elems); return; }
     // start from the size the previous symbolic phase of this form settled on (re-assembly after efg_set_mesh, time
     // stepping with a changing mesh): the search below then succeeds at the first attempt
@@ -1560,6 +1567,12 @@ template <class F> void tiled_symbolic(efg_ctx *ctx)
     tiled_tiles_search<F>(ctx);
     delete tiled_sym(ctx);          // the pattern-phase tables are not needed once the tiles exist
     tiled_sym(ctx) = nullptr;
+    ctx->scratch.release();         // (allocation is free with the arena: nothing is kept "warm" any more)
+    // the values go where the sort scratch and the pattern-phase tables were
+    const int64_t nnz = ctx->nnz;
+    if (ctx->nzval.n < (size_t)(nnz > 0 ? nnz : 1)) ctx->nzval.alloc(ctx->pool, (size_t)(nnz > 0 ? nnz : 1));
+    if (getenv("EFG_TRACE")) fprintf(stderr, "[efg trace] arena after the symbolic phase: %.2f GB in use (peak %.2f), %.2f GB reserved in %zu slabs\n",
+                                     ctx->pool.bytes / 1e9, ctx->pool.peak / 1e9, ctx->pool.reserved / 1e9, ctx->pool.slabs.size());
 }
 
 template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(efg_ctx *ctx)

@@ -141,6 +141,7 @@ template <int NEN> static void vec_symbolic(efg_ctx *ctx, VecData *vd, int64_t n
     vd->val.alloc(ctx->pool, (size_t)(nrl > 0 ? nrl : 1));
     vd->nrl = nrl; vd->nrow = nrow;
     vd->have_sym = true;
+    ctx->scratch.release();
 }
 
 template <int NEN, int NQ> static void vec_numeric_heat(efg_ctx *ctx, VecData *vd, double Q)
@@ -215,6 +216,7 @@ static void vec_build_csr(efg_ctx *ctx, VecData *vd)
         tl_excl_scan(ctx, it, vd->rowptr.p, nrow + 1);
     }
     vd->have_csr = true;
+    ctx->scratch.release();
 }
 
 // entries of column c (local) with r0 <= row < r1: rows are ascending inside a column

@@ -365,7 +365,7 @@ int efg_get_stat(efg_ctx *ctx, int which, double *out)
         break;
     case EFG_STAT_KERNEL_LAUNCHES: *out = (double)ctx->launches; break;
     case EFG_STAT_NUMERIC_LAUNCHES: *out = (double)ctx->numeric_launches; break;
-    case EFG_STAT_DEVICE_BYTES: *out = (double)ctx->pool.bytes; break;
+    case EFG_STAT_DEVICE_BYTES: *out = (double)ctx->pool.reserved; break;
     case EFG_STAT_NTILES: *out = (double)ctx->tl.ntiles; break;
     case EFG_STAT_TILE_ELEMS: *out = (double)ctx->tl.sum_tile_elems; break;
     case EFG_STAT_NUMERIC_BYTES: *out = (double)ctx->tl.numeric_bytes; break;

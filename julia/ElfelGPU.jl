@@ -33,11 +33,15 @@ mutable struct SysmatAssemblerGPU <: AbstractSysmatAssembler
     nrow::Int64
     ncol::Int64
     nnz::Int64
+    colptr::Vector{Int64}      # the SparseMatrixCSC fields: allocated in assemble! as soon as nnz is known, so that the
+    rowval::Vector{Int64}      # structure is already on its way to the host while the values are computed
+    nzval::Vector{Float64}
+    loaded::Vector{Any}        # the FEIterators of the last assemble! call, in space-slot order
     function SysmatAssemblerGPU(zero::Float64 = 0.0; device::Integer = 0)
         r = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:efg_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r)
         rc == 0 || error("efg_create failed ($rc): no usable CUDA device (there is no CPU fallback)")
-        a = new(r[], 0, 0, 0)
+        a = new(r[], 0, 0, 0, Int64[], Int64[], Float64[], Any[])
         finalizer(x -> ccall((:efg_destroy, LIB), Cint, (Ptr{Cvoid},), x.ctx), a)
         return a
     end
@@ -89,21 +93,26 @@ function assemble!(a::SysmatAssemblerGPU, form, elits, qpits)
         _check(a, ccall((:efg_start, LIB), Cint, (Ptr{Cvoid}, Int64, Int64), a.ctx, a.nrow, a.ncol))
         p = params(form)
         nnz = Ref{Int64}(0)
-        _check(a, ccall((:efg_assemble, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Cint, Ref{Int64}),
-                        a.ctx, formid(form), _rule(qpits[1], _kind(elits[1])), p, length(p), nnz))
+        rule = _rule(qpits[1], _kind(elits[1]))
+        # structure first: the pattern (-> nnz) ...
+        _check(a, ccall((:efg_pattern, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Int64}), a.ctx, formid(form), rule, nnz))
         a.nnz = nnz[]
+        a.colptr = Vector{Int64}(undef, a.ncol + 1)
+        a.rowval = Vector{Int64}(undef, a.nnz)
+        a.nzval = Vector{Float64}(undef, a.nnz)
+        # ... starts travelling to the host (copy stream) while the scatter maps and the values are computed
+        _check(a, ccall((:efg_fetch_pattern_async, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), a.ctx, a.colptr, a.rowval))
+        _check(a, ccall((:efg_numeric, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), a.ctx, p, length(p)))
+        a.loaded = Any[it for it in elits]
     end
     return a
 end
 
-"finish!(ass) -- src/Assemblers.jl:121-123: the arrays are allocated here and filled by the library (no copy)."
+"finish!(ass) -- src/Assemblers.jl:121-123: waits for the structure, copies the values; the arrays are wrapped without a copy."
 function finish!(a::SysmatAssemblerGPU)
-    colptr = Vector{Int64}(undef, a.ncol + 1)
-    rowval = Vector{Int64}(undef, a.nnz)
-    nzval = Vector{Float64}(undef, a.nnz)
     _check(a, ccall((:efg_fetch_csc, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
-                    a.ctx, colptr, rowval, nzval))
-    return SparseMatrixCSC(a.nrow, a.ncol, colptr, rowval, nzval)
+                    a.ctx, C_NULL, C_NULL, a.nzval))
+    return SparseMatrixCSC(a.nrow, a.ncol, a.colptr, a.rowval, a.nzval)
 end
 
 # ---- system vector (SysvecAssembler, src/Assemblers.jl:170-232) ---------------------------------------------
@@ -166,10 +175,24 @@ end
 `sqrt(sum_el sum_qp JxW * sum_c (u_c(qp) - truef_c(location(el, qp)...))^2)`: evaluate_pressure_error /
 evaluate_velocity_error with the element loop on the device.  `elits`: one FEIterator per field component (the
 same iterator twice for the two components of a vector space), all of them among the iterators of the last
-`assemble!(am, ...)` call (`slots` gives their space slots there); `truefs`: one function per component.
+`assemble!(am, ...)` call; `truefs`: one function per component.  Same signature as the Python mirror
+(elfel.jl_b200/assemblers.py:evaluate_error) and as INTEGRATION.md shows.
 """
-function evaluate_error(a::SysmatAssemblerGPU, slots::NTuple{N,Tuple{Int,Int}}, mesh_slot::Int, nel::Int, quad::Int,
-                        U::Vector{Float64}, truefs::NTuple{N,Function}) where {N}
+function evaluate_error(a::SysmatAssemblerGPU, elits, qpit::QPIterator, U::Vector{Float64}, truefs)
+    elits isa FEIterator && (elits = (elits,); truefs = (truefs,))
+    N = length(elits)
+    slots = Tuple{Int,Int}[]
+    seen = Dict{Int,Int}()
+    for it in elits                                   # (space slot, component) of every field component
+        s = findfirst(k -> k._fld0 === it._fld0, a.loaded)
+        s === nothing && error("evaluate_error: this space was not part of the last assemble! call")
+        c = get(seen, s, 0)
+        push!(slots, (s - 1, c))
+        seen[s] = c + 1
+    end
+    mesh_slot = a.loaded[1]._bir === elits[1]._bir ? 0 : 1
+    nel = length(elits[1])
+    quad = _rule(qpit, _kind(elits[1]))
     np = Ref{Int64}(0)
     _check(a, ccall((:efg_qp_locations, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ref{Int64}), a.ctx, mesh_slot, quad, C_NULL, np))
     loc = Array{Float64}(undef, 2, np[], nel)

@@ -49,3 +49,35 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("oracle_args", "").replace("the oracle", "").replace("CPU oracle", "").replace("oracle.assemble", ""), f
+
+
+def _build_c_smoke(tmp_path):
+    import subprocess
+    efg.build()
+    exe = str(tmp_path / "c_abi_smoke")
+    libdir = os.path.dirname(_lib.SO_PATH)
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c_abi_smoke.c"), "-o", exe, "-L", libdir, "-lelfelgpu", "-lm",
+                        f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr          # the header is valid, warning-free C99 and the library links from plain C
+    return exe
+
+
+def test_header_is_valid_c99_and_links_from_c(tmp_path):
+    import subprocess
+    import torch
+    exe = _build_c_smoke(tmp_path)
+    if torch.cuda.is_available():
+        pytest.skip("covered by the gpu test")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "NO DEVICE" in r.stdout, r.stdout + r.stderr      # fails loudly, no CPU fallback
+
+
+@pytest.mark.gpu
+def test_c_program_assembles_config1_through_the_abi(tmp_path):
+    """BASELINE config 1 assembled by a plain C99 program (tests/c_abi_smoke.c): no ctypes, no Python objects."""
+    import subprocess
+    exe = _build_c_smoke(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.startswith("OK "), r.stdout + r.stderr
+    assert "nnz=70601" in r.stdout
