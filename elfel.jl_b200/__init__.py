@@ -19,7 +19,7 @@ from .fespaces import (FE, FEH1_T3, FEH1_T6, FEH1_Q4, FEField, FESpace, edofbfnu
 from . import _lib
 from ._lib import build, EfgError, ArgumentError
 from .assemblers import (FEIterator, QPIterator, HeatForm, HeatLoadForm, SysvecAssemblerGPU, mul, block, evaluate_error, ElasticityForm, StokesGenForm, StokesReddyForm,
-                         StokesVeclapAltForm, StokesVeclapForm, SparseMatrixCSC, Engine, SysmatAssemblerGPU,
+                         StokesVeclapAltForm, StokesVeclapForm, SparseMatrixCSC, Engine, MultiEngine, SysmatAssemblerGPU,
                          start, assemble, finish)
 from .problems import (Problem, heat_problem, elasticity_problem, stokes_problem, plane_stress_D, load_problem,
                        oracle_args)

@@ -33,7 +33,9 @@ EXPORTS = ["efg_create", "efg_destroy", "efg_last_error", "efg_set_option", "efg
            "efg_synchronize", "efg_set_mesh", "efg_set_space", "efg_start", "efg_set_column_range",
            "efg_set_column_ranges", "efg_pattern", "efg_fetch_pattern_async", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version",
            "efg_vec_assemble", "efg_fetch_vec", "efg_device_vec", "efg_spmv", "efg_block_nnz", "efg_fetch_block",
-           "efg_qp_locations", "efg_l2_error"]
+           "efg_qp_locations", "efg_l2_error",
+           "efgm_create", "efgm_destroy", "efgm_last_error", "efgm_device_count", "efgm_set_option", "efgm_set_mesh", "efgm_set_space",
+           "efgm_start", "efgm_assemble", "efgm_numeric", "efgm_fetch_csc", "efgm_get_stat", "efgm_device_ctx"]
 
 
 def _sources():
@@ -105,8 +107,22 @@ def load():
     L.efg_fetch_block.argtypes = [vp, vp, vp, vp]
     L.efg_qp_locations.argtypes = [vp, ci, ci, vp, i64p]
     L.efg_l2_error.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), ci, vp, i64, vp, f64p]
+    L.efgm_create.argtypes = [ci, C.POINTER(ci), C.POINTER(vp)]
+    L.efgm_destroy.argtypes = [vp]
+    L.efgm_last_error.argtypes = [vp]
+    L.efgm_last_error.restype = C.c_char_p
+    L.efgm_device_count.argtypes = [vp]
+    L.efgm_set_option.argtypes = [vp, ci, i64]
+    L.efgm_set_mesh.argtypes = [vp, ci, ci, i64, i64, vp, vp]
+    L.efgm_set_space.argtypes = [vp, ci, ci, ci, i64, vp]
+    L.efgm_start.argtypes = [vp, i64, i64]
+    L.efgm_assemble.argtypes = [vp, ci, ci, f64p, ci, i64p]
+    L.efgm_numeric.argtypes = [vp, f64p, ci]
+    L.efgm_fetch_csc.argtypes = [vp, vp, vp, vp]
+    L.efgm_get_stat.argtypes = [vp, ci, ci, f64p]
+    L.efgm_device_ctx.argtypes = [vp, ci, C.POINTER(vp), i64p, C.POINTER(i64p), C.POINTER(i64p)]
     for name in EXPORTS:
-        if name not in ("efg_version", "efg_last_error") and hasattr(L, name):
+        if name not in ("efg_version", "efg_last_error", "efgm_last_error") and hasattr(L, name):
             getattr(L, name).restype = ci
     _lib = L
     return L

@@ -335,6 +335,83 @@ class Engine:
         return out.value
 
 
+class MultiEngine:
+    """One ``efg_multi``: several GPUs behind one handle, global arrays in, global CSC out (include/elfel_gpu.h, efgm_*).
+    The global arrays passed to set_mesh / set_space must stay alive until assemble() has returned."""
+
+    def __init__(self, devices):
+        self.L = _lib.load()
+        devs = list(devices)
+        arr = (C.c_int * len(devs))(*devs)
+        h = C.c_void_p()
+        rc = self.L.efgm_create(len(devs), arr, C.byref(h))
+        if rc != _lib.OK:
+            raise _lib.EfgError(rc, "efgm_create failed: no usable CUDA device (there is no CPU fallback)")
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.efgm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != _lib.OK:
+            msg = self.L.efgm_last_error(self.h).decode()
+            raise (_lib.ArgumentError if rc == _lib.ERR_INDEX else _lib.EfgError)(rc, msg)
+
+    def set_option(self, opt, value):
+        self._ck(self.L.efgm_set_option(self.h, opt, int(value)))
+
+    def set_mesh(self, slot, kind, conn, xy):
+        self._keep += [conn, xy]
+        self._ck(self.L.efgm_set_mesh(self.h, slot, kind, int(conn.shape[0]), int(xy.shape[0]), _ptr(conn), _ptr(xy)))
+
+    def set_space(self, slot, mesh_slot, dofnums):
+        self._keep.append(dofnums)
+        self._ck(self.L.efgm_set_space(self.h, slot, mesh_slot, int(dofnums.shape[1]), int(dofnums.shape[0]), _ptr(dofnums)))
+
+    def start(self, nrow, ncol):
+        self.nrow, self.ncol = int(nrow), int(ncol)
+        self._ck(self.L.efgm_start(self.h, int(nrow), int(ncol)))
+
+    def assemble(self, form_id, quad, params) -> int:
+        nnz = C.c_int64()
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._ck(self.L.efgm_assemble(self.h, form_id, quad, p.ctypes.data_as(C.POINTER(C.c_double)), len(p), C.byref(nnz)))
+        self.nnz = nnz.value
+        self._keep = []
+        return nnz.value
+
+    def numeric(self, params):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._ck(self.L.efgm_numeric(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), len(p)))
+
+    def fetch_csc(self):
+        colptr = np.empty(self.ncol + 1, dtype=np.int64)
+        rowval = np.empty(self.nnz, dtype=np.int64)
+        nzval = np.empty(self.nnz, dtype=np.float64)
+        self._ck(self.L.efgm_fetch_csc(self.h, _ptr(colptr), _ptr(rowval), _ptr(nzval)))
+        return colptr, rowval, nzval
+
+    def stat(self, which, device=-1) -> float:
+        v = C.c_double()
+        self._ck(self.L.efgm_get_stat(self.h, which, device, C.byref(v)))
+        return v.value
+
+    def device_ranges(self, device):
+        """Column ranges (firsts, lasts; 1-based inclusive) of the block device index `device` holds."""
+        n, f, l = C.c_int64(), C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
+        self._ck(self.L.efgm_device_ctx(self.h, device, None, C.byref(n), C.byref(f), C.byref(l)))
+        return (np.array([f[i] for i in range(n.value)], dtype=np.int64), np.array([l[i] for i in range(n.value)], dtype=np.int64))
+
+
 class SysmatAssemblerGPU:
     """Selected in place of SysmatAssemblerSparse; same start / assemble / finish life cycle."""
 

@@ -4,6 +4,7 @@
 #include "efg_twopass.cuh"
 #include "efg_tiled.cuh"
 #include "efg_vector.cuh"
+#include "efg_multi.cuh"
 
 #include <cstring>
 #include <cmath>
@@ -879,6 +880,231 @@ int efg_l2_error(efg_ctx *ctx, int ncomp, const int *space_slots, const int *com
     const double E = tl_read(ctx, sum.p);
     *out = sqrt(E);
     API_END(ctx)
+}
+
+
+// ---- several GPUs behind one handle (efg_multi.cuh) ---------------------------------------------------------------------
+#define MAPI_BEGIN(m)                                                           \
+    if (!(m)) return EFG_ERR_INVALID;                                           \
+    try {
+#define MAPI_END(m)                                                             \
+        return EFG_OK;                                                          \
+    } catch (const EfgError &e) {                                               \
+        (m)->err = e.msg;                                                       \
+        return e.code;                                                          \
+    } catch (const std::bad_alloc &) {                                          \
+        (m)->err = "host allocation failed";                                    \
+        return EFG_ERR_OOM;                                                     \
+    } catch (...) {                                                             \
+        (m)->err = "unknown error";                                             \
+        return EFG_ERR_CUDA;                                                    \
+    }
+
+int efgm_create(int ngpu, const int *devices, efg_multi **out)
+{
+    if (!out) return EFG_ERR_INVALID;
+    *out = nullptr;
+    if (ngpu < 1 || ngpu > 255) return EFG_ERR_INVALID;
+    efg_multi *m = new (std::nothrow) efg_multi();
+    if (!m) return EFG_ERR_OOM;
+    m->dev.resize((size_t)ngpu);
+    for (int i = 0; i < ngpu; i++) {
+        m->dev[i].band = i;
+        const int rc = efg_create(devices ? devices[i] : i, &m->dev[i].ctx);
+        if (rc != EFG_OK) {
+            for (int j = 0; j < i; j++) efg_destroy(m->dev[j].ctx);
+            delete m;
+            return rc;
+        }
+    }
+    *out = m;
+    return EFG_OK;
+}
+
+int efgm_destroy(efg_multi *m)
+{
+    if (!m) return EFG_ERR_INVALID;
+    for (auto &d : m->dev) efg_destroy(d.ctx);
+    delete m;
+    return EFG_OK;
+}
+
+const char *efgm_last_error(const efg_multi *m) { return m ? m->err.c_str() : "null handle"; }
+int efgm_device_count(const efg_multi *m) { return m ? (int)m->dev.size() : 0; }
+
+int efgm_set_option(efg_multi *m, int option, int64_t value)
+{
+    MAPI_BEGIN(m)
+    if (option < 1 || option > 7) efg_throw(EFG_ERR_INVALID, "unknown option %d", option);
+    for (auto &d : m->dev) multi_ck(d.ctx, efg_set_option(d.ctx, option, value));
+    MAPI_END(m)
+}
+
+int efgm_set_mesh(efg_multi *m, int slot, int kind, int64_t nel, int64_t nnodes, const int64_t *conn, const double *xy)
+{
+    MAPI_BEGIN(m)
+    if (slot < 0 || slot > 1) efg_throw(EFG_ERR_INVALID, "mesh_slot must be 0 or 1");
+    if (kind != EFG_T3 && kind != EFG_Q4 && kind != EFG_T6) efg_throw(EFG_ERR_INVALID, "unsupported element kind %d", kind);
+    if (nel < 0 || nnodes < 0 || (nel > 0 && (!conn || !xy))) efg_throw(EFG_ERR_INVALID, "bad mesh arguments");
+    if (nnodes >= ((int64_t)1 << 31) || nel >= ((int64_t)1 << 31)) efg_throw(EFG_ERR_LIMIT, "mesh too large for 32-bit device indices");
+    m->mesh[slot] = GlobalMesh{kind, nel, nnodes, conn, xy};
+    if (slot == 0) m->mesh[1] = GlobalMesh{};           // like the single-GPU ctx: a new mesh 0 starts a new problem
+    m->sharded = false; m->assembled = false;
+    MAPI_END(m)
+}
+
+int efgm_set_space(efg_multi *m, int slot, int mesh_slot, int ncomp, int64_t nnodes, const int64_t *dofnums)
+{
+    MAPI_BEGIN(m)
+    if (slot < 0 || slot > 2 || mesh_slot < 0 || mesh_slot > 1) efg_throw(EFG_ERR_INVALID, "bad space/mesh slot");
+    if (ncomp < 1 || ncomp > 2) efg_throw(EFG_ERR_INVALID, "ncomp must be 1 or 2");
+    if (nnodes != m->mesh[mesh_slot].nnodes) efg_throw(EFG_ERR_INVALID, "space has %lld terms, its mesh has %lld nodes", (long long)nnodes, (long long)m->mesh[mesh_slot].nnodes);
+    if (nnodes > 0 && !dofnums) efg_throw(EFG_ERR_INVALID, "null dofnums");
+    m->space[slot] = GlobalSpace{mesh_slot, ncomp, nnodes, dofnums};
+    for (int s = slot + 1; s < 3; s++) if (slot == 0) m->space[s] = GlobalSpace{};
+    m->sharded = false; m->assembled = false;
+    MAPI_END(m)
+}
+
+int efgm_start(efg_multi *m, int64_t nrow, int64_t ncol)
+{
+    MAPI_BEGIN(m)
+    if (nrow < 0 || ncol < 0) efg_throw(EFG_ERR_INVALID, "negative matrix size");
+    if (nrow >= ((int64_t)1 << 31) || ncol >= ((int64_t)1 << 31)) efg_throw(EFG_ERR_LIMIT, "matrix dimension exceeds 32-bit device indices");
+    if (m->nrow != nrow || m->ncol != ncol) m->assembled = false;
+    m->nrow = nrow; m->ncol = ncol; m->started = true;
+    MAPI_END(m)
+}
+
+int efgm_assemble(efg_multi *m, int form, int quad, const double *params, int nparams, int64_t *nnz_out)
+{
+    MAPI_BEGIN(m)
+    if (!m->started) efg_throw(EFG_ERR_STATE, "efgm_assemble before efgm_start");
+    if (m->mesh[0].kind == 0) efg_throw(EFG_ERR_STATE, "mesh 0 not set");
+    if (m->mesh[1].kind && m->mesh[1].nel != m->mesh[0].nel) efg_throw(EFG_ERR_INVALID, "the two meshes must have the same elements");
+    int rc;
+    if (!m->sharded) {
+        int axis = 1;
+        std::vector<double> cuts;
+        multi_cuts(m, axis, cuts);
+        rc = multi_parallel(m, [&](int i) { multi_shard_device(m, m->dev[(size_t)i], axis, cuts); });
+        if (rc != EFG_OK) throw EfgError{rc, m->err};
+        m->sharded = true;
+    }
+    rc = multi_parallel(m, [&](int i) {
+        MultiDev &d = m->dev[(size_t)i];
+        d.nnz = 0;
+        if (d.firsts.empty()) return;          // an empty band (more devices than distinct coordinates)
+        multi_ck(d.ctx, efg_start(d.ctx, m->nrow, m->ncol));
+        multi_ck(d.ctx, efg_set_column_ranges(d.ctx, (int64_t)d.firsts.size(), d.firsts.data(), d.lasts.data()));
+        multi_ck(d.ctx, efg_assemble(d.ctx, form, quad, params, nparams, &d.nnz));
+    });
+    if (rc != EFG_OK) throw EfgError{rc, m->err};
+    m->nnz = 0;
+    for (auto &d : m->dev) m->nnz += d.nnz;
+    m->form = form; m->quad = quad; m->assembled = true;
+    if (nnz_out) *nnz_out = m->nnz;
+    MAPI_END(m)
+}
+
+int efgm_numeric(efg_multi *m, const double *params, int nparams)
+{
+    MAPI_BEGIN(m)
+    if (!m->assembled) efg_throw(EFG_ERR_STATE, "efgm_numeric before efgm_assemble");
+    const int rc = multi_parallel(m, [&](int i) {
+        MultiDev &d = m->dev[(size_t)i];
+        if (!d.firsts.empty()) multi_ck(d.ctx, efg_numeric(d.ctx, params, nparams));
+    });
+    if (rc != EFG_OK) throw EfgError{rc, m->err};
+    MAPI_END(m)
+}
+
+int efgm_fetch_csc(efg_multi *m, int64_t *colptr, int64_t *rowval, double *nzval)
+{
+    MAPI_BEGIN(m)
+    if (!m->assembled) efg_throw(EFG_ERR_STATE, "efgm_fetch_csc before efgm_assemble");
+    if (!colptr) efg_throw(EFG_ERR_INVALID, "efgm_fetch_csc needs colptr (the blocks are placed through it)");
+    if (is_device_ptr(colptr) || (rowval && is_device_ptr(rowval)) || (nzval && is_device_ptr(nzval)))
+        efg_throw(EFG_ERR_INVALID, "efgm_fetch_csc fills HOST arrays (the device blocks stay available through the per-device ctx)");
+    const int64_t ncol = m->ncol;
+    std::vector<std::vector<int64_t>> lcp(m->dev.size());
+    // per-column counts of every device block into colptr[1..ncol]
+    colptr[0] = 1;
+    int rc = multi_parallel(m, [&](int i) {
+        MultiDev &d = m->dev[(size_t)i];
+        if (d.firsts.empty()) return;
+        std::vector<int64_t> &cp = lcp[(size_t)i];
+        cp.resize((size_t)d.ctx->ncl + 1);
+        multi_ck(d.ctx, efg_fetch_csc(d.ctx, cp.data(), nullptr, nullptr));
+        int64_t k = 0;
+        for (size_t r = 0; r < d.firsts.size(); r++)
+            for (int64_t c = d.firsts[r]; c <= d.lasts[r]; c++, k++) colptr[c] = cp[(size_t)k + 1] - cp[(size_t)k];
+    });
+    if (rc != EFG_OK) throw EfgError{rc, m->err};
+    for (int64_t c = 1; c <= ncol; c++) colptr[c] += colptr[c - 1];
+    if (colptr[ncol] - 1 != m->nnz) efg_throw(EFG_ERR_STATE, "the device blocks do not cover every column exactly once (nnz %lld vs %lld)", (long long)(colptr[ncol] - 1), (long long)m->nnz);
+    if (!rowval && !nzval) return EFG_OK;
+    // every column run of every device goes straight to its place in the caller's arrays
+    rc = multi_parallel(m, [&](int i) {
+        MultiDev &d = m->dev[(size_t)i];
+        if (d.firsts.empty()) return;
+        efg_ctx *ctx = d.ctx;
+        CUDA_CHECK(cudaSetDevice(ctx->device));
+        const std::vector<int64_t> &cp = lcp[(size_t)i];
+        const int64_t CH = (int64_t)32 << 20;
+        DevBuf<int64_t> stage[2];
+        if (rowval) { const int64_t cap = ctx->nnz < CH ? (ctx->nnz > 0 ? ctx->nnz : 1) : CH; stage[0].alloc(ctx->pool, (size_t)cap); stage[1].alloc(ctx->pool, (size_t)cap); }
+        int b = 0;
+        int64_t k = 0;
+        for (size_t r = 0; r < d.firsts.size(); r++) {
+            const int64_t ncols = d.lasts[r] - d.firsts[r] + 1;
+            const int64_t src = cp[(size_t)k] - 1, len = cp[(size_t)(k + ncols)] - cp[(size_t)k];
+            const int64_t dst = colptr[d.firsts[r] - 1] - 1;
+            k += ncols;
+            if (len == 0) continue;
+            if (nzval) CUDA_CHECK(cudaMemcpyAsync(nzval + dst, ctx->nzval.p + src, (size_t)len * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            if (rowval)
+                for (int64_t o = 0; o < len; o += CH, b ^= 1) {
+                    const int64_t n = len - o < CH ? len - o : CH;
+                    LAUNCH(ctx, k_rowval_out, grid_for(n, 256), 256, 0, ctx->rowval.p + src + o, n, stage[b].p);
+                    CUDA_CHECK(cudaMemcpyAsync(rowval + dst + o, stage[b].p, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+                }
+        }
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    });
+    if (rc != EFG_OK) throw EfgError{rc, m->err};
+    MAPI_END(m)
+}
+
+/* which: EFG_STAT_*; device < 0: milliseconds -> max over the devices, counts and bytes -> sum; device >= 0: that device's ctx */
+int efgm_get_stat(efg_multi *m, int which, int device, double *out)
+{
+    MAPI_BEGIN(m)
+    if (!out) efg_throw(EFG_ERR_INVALID, "null output");
+    if (device >= (int)m->dev.size()) efg_throw(EFG_ERR_INVALID, "no such device index");
+    double acc = 0.0;
+    for (int i = 0; i < (int)m->dev.size(); i++) {
+        if (device >= 0 && i != device) continue;
+        double v = 0.0;
+        multi_ck(m->dev[(size_t)i].ctx, efg_get_stat(m->dev[(size_t)i].ctx, which, &v));
+        const bool is_ms = which == EFG_STAT_SYMBOLIC_MS || which == EFG_STAT_NUMERIC_MS || which == EFG_STAT_VEC_MS || which == EFG_STAT_SPMV_MS;
+        acc = is_ms ? (v > acc ? v : acc) : acc + v;
+    }
+    *out = acc;
+    MAPI_END(m)
+}
+
+/* the ctx of device index i (its column block: efg_device_csc, efg_fetch_csc, ...) and the owned column ranges of that block */
+int efgm_device_ctx(efg_multi *m, int device, efg_ctx **ctx_out, int64_t *nranges_out, const int64_t **firsts_out, const int64_t **lasts_out)
+{
+    MAPI_BEGIN(m)
+    if (device < 0 || device >= (int)m->dev.size()) efg_throw(EFG_ERR_INVALID, "no such device index");
+    MultiDev &d = m->dev[(size_t)device];
+    if (ctx_out) *ctx_out = d.ctx;
+    if (nranges_out) *nranges_out = (int64_t)d.firsts.size();
+    if (firsts_out) *firsts_out = d.firsts.data();
+    if (lasts_out) *lasts_out = d.lasts.data();
+    MAPI_END(m)
 }
 
 } // extern "C"

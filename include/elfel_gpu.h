@@ -44,8 +44,9 @@
  *     EFG_ERR_INDEX, mirroring sparse()'s ArgumentError (e.g. a space that was never
  *     data-numbered holds dof number 0, src/FEFields.jl:148).
  *   - One ctx = one device + one CUDA stream; not re-entrant.  Different ctx may be used from
- *     different host threads.  Multi-GPU = one ctx (one process) per GPU, each assembling a
- *     contiguous block of matrix columns (efg_set_column_range); no communication is needed.
+ *     different host threads.  Multi-GPU: either one ctx per GPU driven by the caller (one process or thread per
+ *     GPU, each assembling its column ranges: efg_set_column_ranges), or one efg_multi handle (efgm_* below) that
+ *     takes the global arrays and shards internally; no communication is needed in either case.
  *   - The quadrature tables and form parameters live in __constant__ memory (one copy per device).  The library
  *     hands them over between the ctx of a device in stream order (per-device lock + events), so several ctx --
  *     on one device or one per device, from one host thread or several -- may be used freely and asynchronously.
@@ -203,6 +204,35 @@ int efg_l2_error(efg_ctx *ctx, int ncomp, const int *space_slots, const int *com
 
 /* library / build information, e.g. "elfelgpu 0.1 sm_100a" */
 const char *efg_version(void);
+
+/* ---- several GPUs behind one handle (SURVEY 8b "efg_create_multi": same calls, the library shards internally; 8e) -------
+ * The caller passes the GLOBAL arrays exactly as to the single-GPU functions above (what FEIterator holds:
+ * src/FEIterators.jl:54-81); they are borrowed until efgm_assemble has returned (GC.@preserve around the whole
+ * assemble!).  Inside, one host thread per device selects -- on the device -- the elements touching the nodes of its band
+ * (halo elements replicated), owns the columns of that band's dofs and runs the single-GPU phases on its sub-mesh; there
+ * is no communication between the devices.  efgm_fetch_csc interleaves the device blocks by column into the caller's
+ * SparseMatrixCSC arrays; the result is bit-identical to the single-GPU result.  `devices` may be NULL (= 0 .. ngpu-1)
+ * and may name a device more than once. */
+typedef struct efg_multi efg_multi;
+int efgm_create(int ngpu, const int *devices, efg_multi **out);
+int efgm_destroy(efg_multi *m);
+const char *efgm_last_error(const efg_multi *m);
+int efgm_device_count(const efg_multi *m);
+int efgm_set_option(efg_multi *m, int option, int64_t value);
+int efgm_set_mesh(efg_multi *m, int mesh_slot, int elemkind, int64_t nel, int64_t nnodes, const int64_t *conn, const double *xy);
+int efgm_set_space(efg_multi *m, int space_slot, int mesh_slot, int ncomp, int64_t nnodes, const int64_t *dofnums);
+int efgm_start(efg_multi *m, int64_t nrow, int64_t ncol);
+/* shards (first call after efgm_set_mesh / efgm_set_space), then symbolic + numeric on every device; nnz of the global matrix */
+int efgm_assemble(efg_multi *m, int form_id, int quad_rule, const double *params, int nparams, int64_t *nnz_out);
+/* numeric phase again on the cached shards and patterns (time stepping, Newton) */
+int efgm_numeric(efg_multi *m, const double *params, int nparams);
+/* global SparseMatrixCSC fields into HOST arrays (colptr: ncol+1, required; rowval / nzval may be NULL) */
+int efgm_fetch_csc(efg_multi *m, int64_t *colptr, int64_t *rowval, double *nzval);
+/* EFG_STAT_* over the devices: device < 0: milliseconds -> max, counts and bytes -> sum; device >= 0: that device only */
+int efgm_get_stat(efg_multi *m, int which, int device, double *out);
+/* the ctx of device index `device` (its column block stays on the device: efg_device_csc, efg_spmv is per block) and
+ * the column ranges (1-based, inclusive, ascending) that block holds; valid until the next efgm_set_* / efgm_destroy */
+int efgm_device_ctx(efg_multi *m, int device, efg_ctx **ctx_out, int64_t *nranges_out, const int64_t **firsts_out, const int64_t **lasts_out);
 
 #ifdef __cplusplus
 }

@@ -16,7 +16,7 @@ def test_library_builds_and_exports_header_symbols():
     so = efg.build()
     L = ctypes.CDLL(so)
     hdr = open(os.path.join(ROOT, "include", "elfel_gpu.h")).read()
-    declared = set(re.findall(r"\b(efg_[a-z_0-9]+)\s*\(", hdr))
+    declared = set(re.findall(r"\b(efgm?_[a-z_0-9]+)\s*\(", hdr))
     assert declared, "no declarations parsed"
     for name in declared:
         assert hasattr(L, name), f"{name} declared in the header but not exported"
