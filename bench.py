@@ -374,6 +374,86 @@ def run_config5(torch, dist, efg, _lib, args, rank, world, local, peak):
     return rec
 
 
+def run_verify(args):
+    """--verify: BASELINE configs 2, 3 and 4 at FULL size on the GPU, checked against the direct-accumulate oracle on a spread
+    of column blocks (bit-exact pattern; nzval within 1e-12 relative / 1e-14 absolute in the default FP mode and == in the
+    strict mode).  One JSON line with the largest errors seen."""
+    import torch
+    import elfel_jl_b200 as efg
+    from elfel_jl_b200 import _lib
+    from oracle import oracle as orc
+    from concurrent.futures import ThreadPoolExecutor
+    orc.build()
+    res = []
+    for wl, n in (("heat_t6", 4000), ("elasticity_t6", 2000), ("stokes_gen", 1000)):
+        if args.workload != "heat_t6" and wl != args.workload:
+            continue
+        n = args.n or n
+        t0 = time.perf_counter()
+        prob = make_problem(efg, wl, n)
+        nd = int(prob.ndofs)
+        pairs = [(prob.meshes[ms].conn, sp.field.dofnums) for sp, ms in zip(prob.spaces, prob.space_mesh)]
+        dconn = [(torch.from_numpy(np.ascontiguousarray(c)).cuda(), torch.from_numpy(np.ascontiguousarray(d)).cuda()) for c, d in pairs]
+        gen_s = time.perf_counter() - t0
+        # column blocks: the first and last free columns, the data-dof tail, and blocks spread over the rest
+        width = max(1000, min(args.verify_cols, nd))
+        starts = sorted(set([1, max(1, nd - width + 1)] + [max(1, int(x)) for x in np.linspace(1, max(1, nd - width + 1), args.verify_blocks)]))
+        blocks = [(a, min(a + width - 1, nd)) for a in starts]
+        eng = efg.Engine(0)
+        efg.load_problem(eng, prob)
+        rec = {"workload": f"{WORKLOADS[wl][1]}, N={n}", "elements": int(prob.nel), "ndofs": nd, "column_blocks": len(blocks), "columns_checked": 0,
+               "nonzeros_checked": 0, "pattern_bit_exact": True, "default_fp": {"max_abs": 0.0, "max_rel": 0.0, "within_1e-12_1e-14": True},
+               "strict_fp": {"max_abs": 0.0, "identical": True}}
+        gpu = {}
+        for strict in (0, 1):
+            eng.set_option(_lib.OPT_STRICT_FP, strict)
+            nnz = eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+            gpu[strict] = [eng.block(1, nd, a, b) for a, b in blocks]
+        rec["nnz"] = int(nnz)
+
+        def elems_of(a, b):
+            hit = None
+            for c, d in dconn:
+                inb = ((d >= a) & (d <= b)).any(dim=1)
+                h = inb[c - 1].any(dim=1)
+                hit = h if hit is None else (hit | h)
+            return torch.nonzero(hit).reshape(-1).cpu().numpy().astype(np.int64)
+        elists = [elems_of(a, b) for a, b in blocks]
+
+        def oracle_block(k):
+            a, b = blocks[k]
+            return orc.assemble_direct(*efg.oracle_args(prob), nd, nd, c0=a, c1=b, elist=elists[k])
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(min(os.cpu_count() or 1, 16)) as ex:
+            want = list(ex.map(oracle_block, range(len(blocks))))
+        rec["oracle_s"] = time.perf_counter() - t0
+        for k, (ocp, orv, onz) in enumerate(want):
+            for strict in (0, 1):
+                cp, rv, nz = gpu[strict][k]
+                ok = np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+                rec["pattern_bit_exact"] = rec["pattern_bit_exact"] and bool(ok)
+                if not ok:
+                    continue
+                d = np.abs(nz - onz)
+                if strict:
+                    rec["strict_fp"]["max_abs"] = max(rec["strict_fp"]["max_abs"], float(d.max(initial=0.0)))
+                    rec["strict_fp"]["identical"] = rec["strict_fp"]["identical"] and bool(np.array_equal(nz, onz))
+                else:
+                    rel = d / np.maximum(np.abs(onz), 1e-300)
+                    rec["default_fp"]["max_abs"] = max(rec["default_fp"]["max_abs"], float(d.max(initial=0.0)))
+                    rec["default_fp"]["max_rel"] = max(rec["default_fp"]["max_rel"], float(rel[np.abs(onz) > 1e-14].max(initial=0.0)))
+                    rec["default_fp"]["within_1e-12_1e-14"] = rec["default_fp"]["within_1e-12_1e-14"] and bool(np.all(d <= 1e-14 + 1e-12 * np.abs(onz)))
+            rec["columns_checked"] += blocks[k][1] - blocks[k][0] + 1
+            rec["nonzeros_checked"] += int(len(orv))
+        rec["mesh_generation_s"] = gen_s
+        eng.close()
+        del dconn, gpu, want
+        torch.cuda.empty_cache()
+        res.append(rec)
+    print(json.dumps({"verify": res, "oracle": "oracle/elfel_oracle.c direct-accumulate mode (== the COO + sparse() restatement, tests/test_oracle_golden.py)",
+                      "tolerance": "pattern bit-exact; nzval 1e-12 relative / 1e-14 absolute (default FP mode), == (EFG_OPT_STRICT_FP)"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -397,12 +477,17 @@ def main():
     ap.add_argument("--config5-n", type=int, default=16384)
     ap.add_argument("--no-others", action="store_true", help="skip other_configs (N = 1 only)")
     ap.add_argument("--only-config5", action="store_true", help="print only the config 5 record (development)")
+    ap.add_argument("--verify", action="store_true", help="full-size parity of configs 2/3/4 against the oracle on column blocks (one JSON line)")
+    ap.add_argument("--verify-blocks", type=int, default=10)
+    ap.add_argument("--verify-cols", type=int, default=40000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     args.cpu_n = args.cpu_n or args.ref_n
     if args.impl == "reference":
         return run_reference(args)
+    if args.verify:
+        return run_verify(args)
 
     import torch
     import elfel_jl_b200 as efg
