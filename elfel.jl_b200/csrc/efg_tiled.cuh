@@ -47,9 +47,9 @@ static_assert(sizeof(TileDescFull) % 8 == 0, "TileDescFull is copied as 8-byte w
 
 // metadata block of a tile, each part 16-byte aligned:
 //   [pk: u32 x nslot]      per owned nonzero: stage index of its 1st | 2nd << 16 contribution (0xFFFF = none);
-//                          0xFFFEFFFE marks a "heavy" nonzero (> TL_LIGHT contributions)
+//                          0xFFFEFFFE marks a "heavy" nonzero (> TL_LIGHT contributions), 0xFFFFFFFF a padding slot
 //   [hidx: u16 x ncontrib] stage indices of the contributions of the heavy nonzeros, append order
-//   [runs: TileRun x nrun] [heavy: TileHeavy x nheavy]
+//   [rowbase: i64 x nslot/32] index in nzval of the first slot of every row of 32 slots   [heavy: TileHeavy x nheavy]
 __host__ __device__ static inline int tl_align16(int b) { return (b + 15) & ~15; }
 // SPLIT forms keep per-element geometry (gradients + JxW at every quadrature point, SoA) and the column masks in
 // shared memory between the two steps of phase 1
@@ -58,6 +58,10 @@ __host__ __device__ static inline int tl_geo_bytes(int gsz, int nelem) { return 
 __host__ __device__ static inline int tl_meta_goff_bytes(int nslot) { return tl_align16(4 * nslot); }          // pk
 __host__ __device__ static inline int tl_meta_gidx_bytes(int nc) { return tl_align16(2 * nc); }              // hidx
 struct TileHeavy { uint16_t s, o, c, pad; };
+// row table: the owned nonzeros of a tile are laid out in ROWS of 32 slots that never straddle a run (every run of nonzeros
+// contiguous in nzval starts at a multiple of 32 slots; the tail of its last row is padding, pk = 0xFFFFFFFF), so the
+// destination of lane l of row r is simply rowbase[r] + l
+__host__ __device__ static inline int tl_meta_rows_bytes(int nslot) { return tl_align16(8 * (nslot >> 5)); }
 // geometry block of a tile, each part 16-byte aligned: [txy: double2 x nnode] [conn16: u16 x GK x nelem] [mask16: u16 x nelem]
 __host__ __device__ static inline int tl_geo_xy_bytes(int nnode) { return 16 * nnode; }
 __host__ __device__ static inline int tl_geo_conn_bytes(int gk, int nelem) { return tl_align16(2 * gk * nelem); }
@@ -423,6 +427,31 @@ __global__ void k_tl_run_len(const int64_t *__restrict__ run_firstk, int64_t nru
     }
 }
 
+// padded slot layout: every run starts at a multiple of 32 slots
+__global__ void k_tl_run_padlen(const TileRun *__restrict__ runs, int64_t nruns, int64_t *__restrict__ padlen)
+{
+    GRID_STRIDE(r, nruns + 1) padlen[r] = r < nruns ? (((int64_t)runs[r].len + 31) & ~(int64_t)31) : 0;
+}
+// pslot[k] = padded position of the first slot of owned tile column k (pslot[nowned] = total)
+__global__ void k_tl_pslot(const int32_t *__restrict__ flag, const int64_t *__restrict__ runidx, const int64_t *__restrict__ run_firstk,
+                           const int64_t *__restrict__ tcol_slot, const int64_t *__restrict__ run_pad0, int64_t nowned, int64_t nruns,
+                           int64_t *__restrict__ pslot)
+{
+    GRID_STRIDE(k, nowned + 1) {
+        if (k == nowned) { pslot[k] = run_pad0[nruns]; continue; }
+        const int64_t r = flag[k] ? runidx[k] : runidx[k] - 1;
+        pslot[k] = run_pad0[r] + (tcol_slot[k] - tcol_slot[run_firstk[r]]);
+    }
+}
+__global__ void k_tl_run_s0(const int64_t *__restrict__ run_firstk, int64_t nruns, const uint32_t *__restrict__ tkeys, const int64_t *__restrict__ tcol_ptr,
+                            const int64_t *__restrict__ pslot, TileRun *__restrict__ runs)
+{
+    GRID_STRIDE(r, nruns) {
+        const int64_t k = run_firstk[r];
+        runs[r].s0 = (int32_t)(pslot[k] - pslot[tcol_ptr[tkeys[k]]]);
+    }
+}
+
 // tile-element keys: (T << 36) | (e << 4) | lj for every (e, lj) whose column is owned
 template <int ND>
 __global__ void k_tl_telem_keys(const int32_t *__restrict__ edof, int64_t nel, ColMap cm, const int32_t *__restrict__ owner,
@@ -570,7 +599,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
         uint32_t *__restrict__ pk = reinterpret_cast<uint32_t *>(mb) + sloc;
         uint16_t *__restrict__ hidx = reinterpret_cast<uint16_t *>(mb + tl_meta_goff_bytes(td.nslot));
         TileHeavy *__restrict__ heavy = reinterpret_cast<TileHeavy *>(mb + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib) +
-                                                                     td.nrun * (int)sizeof(TileRun)) + (tcol_heavy[k] - td.heavy0);
+                                                                     tl_meta_rows_bytes(td.nslot)) + (tcol_heavy[k] - td.heavy0);
         uint16_t cnt[TL_CAP], off[TL_CAP], first[TL_CAP], second[TL_CAP];
         for (int t = 0; t < nr; t++) cnt[t] = 0;
         const uint32_t a0 = adjptr[cl], a1 = adjptr[cl + 1];
@@ -628,14 +657,20 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
     }
 }
 
-// the tile's runs into its metadata block
-__global__ void k_tl_meta_finish(int ntiles, const TileDescFull *__restrict__ tiles, const TileRun *__restrict__ runs, unsigned char *__restrict__ meta)
+// row table + padding slots of every run into its tile's metadata block
+__global__ void k_tl_meta_rows(int64_t nruns, const TileRun *__restrict__ runs, const int64_t *__restrict__ run_firstk, const uint32_t *__restrict__ tkeys,
+                               const TileDescFull *__restrict__ tiles, unsigned char *__restrict__ meta)
 {
-    GRID_STRIDE(T, ntiles) {
-        const TileDescFull &td = tiles[T];
+    GRID_STRIDE(r, nruns) {
+        const TileDescFull &td = tiles[tkeys[run_firstk[r]]];
         if (td.meta_bytes == 0) continue;
-        TileRun *dst = reinterpret_cast<TileRun *>(meta + td.meta0 + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
-        for (int rr = 0; rr < td.nrun; rr++) dst[rr] = runs[td.run0 + rr];
+        unsigned char *mb = meta + td.meta0;
+        uint32_t *pk = reinterpret_cast<uint32_t *>(mb);
+        int64_t *rowbase = reinterpret_cast<int64_t *>(mb + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
+        const TileRun run = runs[r];
+        const int padlen = (run.len + 31) & ~31;
+        for (int j = 0; j < (padlen >> 5); j++) rowbase[(run.s0 >> 5) + j] = run.nz0 + 32 * (int64_t)j;
+        for (int t = run.len; t < padlen; t++) pk[run.s0 + t] = 0xFFFFFFFFu;
     }
 }
 __global__ void k_tl_tiles_meta0(int ntiles, const int64_t *__restrict__ meta_off, TileDescFull *__restrict__ tiles)
@@ -673,7 +708,7 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, int gk, const int32
         for (int r = 0; r <= TL_MAXND; r++) { d.qbase[r] = (uint16_t)(q > 65535u ? 65535u : q); if (r < TL_MAXND) q += above[r]; }
         d.nq = (int32_t)q;
         d.nqs = (uint16_t)((q | 1u) > 65535u ? 65535u : (q | 1u));
-        d.meta_bytes = d.nslot > 0 ? tl_meta_goff_bytes(d.nslot) + tl_meta_gidx_bytes(d.ncontrib) + d.nrun * (int)sizeof(TileRun) + tl_align16((int)sizeof(TileHeavy) * d.nheavy) : 0;
+        d.meta_bytes = d.nslot > 0 ? tl_meta_goff_bytes(d.nslot) + tl_meta_gidx_bytes(d.ncontrib) + tl_meta_rows_bytes(d.nslot) + tl_align16((int)sizeof(TileHeavy) * d.nheavy) : 0;
         d.meta0 = 0;
         d.pad2_[0] = d.pad2_[1] = 0;
         d.geo0 = 0;
@@ -684,6 +719,7 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, int gk, const int32
         geo_bytes[T] = d.geo_bytes;
         atomicMax(&maxima[0], tl_stage_bytes(nd, d.nqs) + max(tl_geo_bytes(gsz, d.nelem), d.meta_bytes) + d.geo_bytes);
         atomicMax(&maxima[1], (int32_t)(((int64_t)q | 1) * nd > 0x7fffffff ? 0x7fffffff : ((int64_t)q | 1) * nd));
+        if (d.nslot > 65535) atomicMax(&maxima[1], 0x7fffffff);      // TileHeavy addresses slots with 16 bits
         atomicMax(&maxima[2], d.ncontrib); atomicMax(&maxima[3], d.nelem);
         atomicMax(&maxima[4], tl_stage_bytes(nd, d.nqs)); atomicMax(&maxima[5], d.meta_bytes); atomicMax(&maxima[6], d.geo_bytes);
         atomicMax(&maxima[7], tl_geo_bytes(gsz, d.nelem));
@@ -850,32 +886,26 @@ __device__ __forceinline__ void tl_column_to_stage(int qc, int le, int J, int ne
 
 // ---- phase 2 of the numeric kernels ---------------------------------------------------------------------
 // Light nonzeros (1 or 2 contributions: all but the matrix diagonals of node patches): one packed word per nonzero
-// names both stage entries; TL_U nonzeros in flight per lane; every lane tracks its run in registers.
+// names both stage entries.  The slots are walked in rows of 32 (one per lane) that never straddle a run, TL_U rows in
+// flight per warp: destination = rowbase[row] + lane, no per-nonzero run tracking.
 template <int BLOCK>
 __device__ __forceinline__ void tl_gather_light(const TileDescFull &td, const double *__restrict__ stage, const unsigned char *__restrict__ smeta,
                                                 double *__restrict__ nzval, int lane, int warp)
 {
     constexpr int NW = BLOCK / 32;
-    const uint32_t *spk = reinterpret_cast<const uint32_t *>(smeta);
-    const TileRun *srun = reinterpret_cast<const TileRun *>(smeta + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
-    const int nslot = td.nslot;
-    const int per_warp = ((nslot + NW - 1) / NW + 31) & ~31;      // contiguous slots per warp
-    const int w0 = min(warp * per_warp, nslot), w1 = min(w0 + per_warp, nslot);
-    int r = 0;
-    {
-        int lo = 0, hi = td.nrun - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= w0) lo = mid; else hi = mid - 1; }
-        r = lo;
-    }
-    int rs0 = srun[r].s0, rend = rs0 + srun[r].len;
-    int64_t rnz = srun[r].nz0;
     constexpr int U = TL_U;
-    for (int sb = w0; sb < w1; sb += 32 * U) {
+    const uint32_t *spk = reinterpret_cast<const uint32_t *>(smeta);
+    const int64_t *srow = reinterpret_cast<const int64_t *>(smeta + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
+    const int nrows = td.nslot >> 5;
+    for (int r0 = warp; r0 < nrows; r0 += NW * U) {
         uint32_t pk[U];
+        int64_t base[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const int s = sb + u * 32 + lane;
-            pk[u] = (s < w1) ? spk[s] : 0xFFFFFFFFu;
+            const int r = r0 + u * NW;
+            const bool in = r < nrows;
+            pk[u] = in ? spk[r * 32 + lane] : 0xFFFFFFFFu;
+            base[u] = in ? srow[r] : 0;
         }
         double acc[U];
 #pragma unroll
@@ -886,13 +916,8 @@ __device__ __forceinline__ void tl_gather_light(const TileDescFull &td, const do
             if (i1 < 0xFFFEu) acc[u] = __dadd_rn(acc[u], stage[i1]);
         }
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int s = sb + u * 32 + lane;
-            if (s < w1) {
-                while (s >= rend) { r++; rs0 = srun[r].s0; rend = rs0 + srun[r].len; rnz = srun[r].nz0; }
-                if (pk[u] != TL_PK_HEAVY) nzval[rnz + (s - rs0)] = acc[u];
-            }
-        }
+        for (int u = 0; u < U; u++)
+            if ((pk[u] & 0xFFFFu) < 0xFFFEu) nzval[base[u] + lane] = acc[u];      // (heavy and padding slots carry 0xFFFE / 0xFFFF there)
     }
 }
 // Heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum.
@@ -901,16 +926,13 @@ __device__ __forceinline__ void tl_gather_heavy(const TileDescFull &td, const do
                                                 double *__restrict__ nzval, int tid)
 {
     const uint16_t *hidx = reinterpret_cast<const uint16_t *>(smeta + tl_meta_goff_bytes(td.nslot));
-    const TileRun *srun = reinterpret_cast<const TileRun *>(reinterpret_cast<const unsigned char *>(hidx) + tl_meta_gidx_bytes(td.ncontrib));
-    const TileHeavy *heavy = reinterpret_cast<const TileHeavy *>(reinterpret_cast<const unsigned char *>(srun) + td.nrun * (int)sizeof(TileRun));
+    const int64_t *srow = reinterpret_cast<const int64_t *>(reinterpret_cast<const unsigned char *>(hidx) + tl_meta_gidx_bytes(td.ncontrib));
+    const TileHeavy *heavy = reinterpret_cast<const TileHeavy *>(reinterpret_cast<const unsigned char *>(srow) + tl_meta_rows_bytes(td.nslot));
     for (int h = tid; h < td.nheavy; h += BLOCK) {
         const TileHeavy e = heavy[h];
         double acc = stage[hidx[e.o]];
         for (int k = 1; k < (int)e.c; k++) acc = __dadd_rn(acc, stage[hidx[e.o + k]]);
-        const int s = e.s;
-        int lo = 0, hi = td.nrun - 1;
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (srun[mid].s0 <= s) lo = mid; else hi = mid - 1; }
-        nzval[srun[lo].nz0 + (s - srun[lo].s0)] = acc;
+        nzval[srow[e.s >> 5] + (e.s & 31)] = acc;
     }
 }
 
@@ -1387,6 +1409,14 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
     run_firstk.alloc(pool, (size_t)(nruns > 0 ? nruns : 1));
     LAUNCH(ctx, k_tl_run_fill, grid_for(nowned, 256), 256, 0, rflag.p, runidx.p, tkeys.p, tcols.p, nowned, tcol_slot.p, tcol_ptr.p, colptr0_p, runs.p, run_firstk.p);
     LAUNCH(ctx, k_tl_run_len, grid_for(nruns, 256), 256, 0, run_firstk.p, nruns, nowned, tcol_slot.p, runs.p);
+    // padded slot positions (rows of 32 slots never straddle a run): pslot replaces tcol_slot wherever a POSITION in the
+    // tile's metadata is meant
+    DevBuf<int64_t> padlen, run_pad0, pslot;
+    padlen.alloc(pool, (size_t)nruns + 2); run_pad0.alloc(pool, (size_t)nruns + 2); pslot.alloc(pool, (size_t)nowned + 2);
+    LAUNCH(ctx, k_tl_run_padlen, grid_for(nruns + 1, 256), 256, 0, runs.p, nruns, padlen.p);
+    tl_excl_scan(ctx, padlen.p, run_pad0.p, nruns + 1);
+    LAUNCH(ctx, k_tl_pslot, grid_for(nowned + 1, 256), 256, 0, rflag.p, runidx.p, run_firstk.p, tcol_slot.p, run_pad0.p, nowned, nruns, pslot.p);
+    LAUNCH(ctx, k_tl_run_s0, grid_for(nruns, 256), 256, 0, run_firstk.p, nruns, tkeys.p, tcol_ptr.p, pslot.p, runs.p);
 
     trace.mark("T5 tile columns/runs");
     // T6: tile element lists (own + halo), masks, popcount-descending order inside a tile
@@ -1455,7 +1485,7 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
     CUDA_CHECK(cudaMemsetAsync(mbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     CUDA_CHECK(cudaMemsetAsync(gbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     td->tiles.alloc(pool, (size_t)ntiles);
-    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tl_gsz<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
+    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tl_gsz<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, pslot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
            nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
     int32_t hmax[8];
     CUDA_CHECK(cudaMemcpyAsync(hmax, maxima.p, sizeof hmax, cudaMemcpyDeviceToHost, st));
@@ -1499,8 +1529,8 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
     td->meta.alloc(pool, (size_t)(meta_total > 0 ? meta_total : 16));
     CUDA_CHECK(cudaMemsetAsync(td->meta.p, 0, (size_t)(meta_total > 0 ? meta_total : 16), st));
     LAUNCH(ctx, k_tl_gather_build<F>, grid_for(nowned, 128), 128, 0, tkeys.p, tcols.p, nowned, adjptr_p, adj_p, edof_p, colptr0_p, ctx->rowval.p,
-           telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, tcol_slot.p, tcol_gidx.p, tcol_heavy.p, td->meta.p, err.p);
-    LAUNCH(ctx, k_tl_meta_finish, grid_for(ntiles, 128), 128, 0, ntiles, td->tiles.p, runs.p, td->meta.p);
+           telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, pslot.p, tcol_gidx.p, tcol_heavy.p, td->meta.p, err.p);
+    LAUNCH(ctx, k_tl_meta_rows, grid_for(nruns, 128), 128, 0, nruns, runs.p, run_firstk.p, tkeys.p, td->tiles.p, td->meta.p);
     const int e2 = tl_read(ctx, err.p);
     if (e2) efg_throw(EFG_ERR_LIMIT, "tiled path: a tile's gather list exceeds 16-bit offsets (%d); lower EFG_OPT_TILE_ELEMS", e2);
 
