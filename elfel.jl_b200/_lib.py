@@ -34,6 +34,8 @@ EXPORTS = ["efg_create", "efg_destroy", "efg_last_error", "efg_set_option", "efg
            "efg_set_column_ranges", "efg_pattern", "efg_fetch_pattern_async", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version",
            "efg_vec_assemble", "efg_fetch_vec", "efg_device_vec", "efg_spmv", "efg_block_nnz", "efg_fetch_block",
            "efg_qp_locations", "efg_l2_error",
+           "efg_gen_mesh", "efg_gen_mesh_corners", "efg_gen_space", "efg_setebc_box", "efg_setebc_nodes", "efg_number_dofs",
+           "efg_fetch_mesh", "efg_fetch_dofnums",
            "efgm_create", "efgm_destroy", "efgm_last_error", "efgm_device_count", "efgm_set_option", "efgm_set_mesh", "efgm_set_space",
            "efgm_start", "efgm_assemble", "efgm_numeric", "efgm_fetch_csc", "efgm_get_stat", "efgm_device_ctx"]
 
@@ -107,6 +109,15 @@ def load():
     L.efg_fetch_block.argtypes = [vp, vp, vp, vp]
     L.efg_qp_locations.argtypes = [vp, ci, ci, vp, i64p]
     L.efg_l2_error.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci), ci, vp, i64, vp, f64p]
+    f64 = C.c_double
+    L.efg_gen_mesh.argtypes = [vp, ci, ci, i64, i64, f64, f64, f64, f64]
+    L.efg_gen_mesh_corners.argtypes = [vp, ci, ci]
+    L.efg_gen_space.argtypes = [vp, ci, ci, ci]
+    L.efg_setebc_box.argtypes = [vp, ci, ci, f64, f64, f64, f64]
+    L.efg_setebc_nodes.argtypes = [vp, ci, ci, i64, vp]
+    L.efg_number_dofs.argtypes = [vp, ci, C.POINTER(ci), i64p, i64p]
+    L.efg_fetch_mesh.argtypes = [vp, ci, i64p, i64p, vp, vp]
+    L.efg_fetch_dofnums.argtypes = [vp, ci, vp]
     L.efgm_create.argtypes = [ci, C.POINTER(ci), C.POINTER(vp)]
     L.efgm_destroy.argtypes = [vp]
     L.efgm_last_error.argtypes = [vp]

@@ -279,6 +279,42 @@ class Engine:
         return (_DeviceArray(cp.value, self.ncols_local + 1, "<i8", self), _DeviceArray(rv.value, self.nnz, "<i4", self),
                 _DeviceArray(nz.value, self.nnz, "<f8", self))
 
+    # ---- inputs made on the device -------------------------------------------------
+    def gen_mesh(self, slot, kind, nL, nW, Length=1.0, Width=1.0, xshift=0.0, yshift=0.0):
+        self._ck(self.L.efg_gen_mesh(self.h, slot, kind, int(nL), int(nW), float(Length), float(Width), float(xshift), float(yshift)))
+
+    def gen_mesh_corners(self, slot_dst, slot_src):
+        self._ck(self.L.efg_gen_mesh_corners(self.h, slot_dst, slot_src))
+
+    def gen_space(self, slot, mesh_slot, ncomp):
+        self._ck(self.L.efg_gen_space(self.h, slot, mesh_slot, ncomp))
+
+    def setebc_box(self, space_slot, comp, x0, x1, y0, y1):
+        self._ck(self.L.efg_setebc_box(self.h, space_slot, comp, float(x0), float(x1), float(y0), float(y1)))
+
+    def setebc_nodes(self, space_slot, comp, node_ids):
+        ids = np.ascontiguousarray(node_ids, dtype=np.int64)
+        self._ck(self.L.efg_setebc_nodes(self.h, space_slot, comp, len(ids), ids.ctypes.data))
+
+    def number_dofs(self, space_slots):
+        arr = (C.c_int * len(space_slots))(*[int(s) for s in space_slots])
+        nfree, ndofs = C.c_int64(), C.c_int64()
+        self._ck(self.L.efg_number_dofs(self.h, len(space_slots), arr, C.byref(nfree), C.byref(ndofs)))
+        return nfree.value, ndofs.value
+
+    def fetch_mesh(self, slot, kind):
+        nel, nn = C.c_int64(), C.c_int64()
+        self._ck(self.L.efg_fetch_mesh(self.h, slot, C.byref(nel), C.byref(nn), None, None))
+        conn = np.empty((nel.value, kind), dtype=np.int64)
+        xy = np.empty((nn.value, 2), dtype=np.float64)
+        self._ck(self.L.efg_fetch_mesh(self.h, slot, None, None, _ptr(conn), _ptr(xy)))
+        return conn, xy
+
+    def fetch_dofnums(self, space_slot, nnodes, ncomp):
+        out = np.empty((int(nnodes), int(ncomp)), dtype=np.int64)
+        self._ck(self.L.efg_fetch_dofnums(self.h, space_slot, _ptr(out)))
+        return out
+
     # ---- SURVEY 8f rows f1 / f2 -------------------------------------------------------------------
     def vec_assemble(self, vform_id, quad, params, nrow):
         p = np.ascontiguousarray(params, dtype=np.float64)

@@ -29,6 +29,7 @@ struct SpaceDev {
     int mesh = -1, ncomp = 0;
     int64_t nnodes = 0;
     DevBuf<int32_t> dof;    // ncomp x nnodes, 0-based (-1 = dof number 0 = unnumbered)
+    DevBuf<uint8_t> isdatum; // ncomp x nnodes: prescribed dofs (only for spaces made by efg_gen_space)
 };
 
 // --- two-pass path (element matrices to HBM, then segmented gather) ---------------------------

@@ -10,6 +10,15 @@
 #include <utility>
 
 #define EFG_MAXQ 9
+// Default (non-strict) FP mode only -- the strict mode always performs the reference's operations one by one:
+#ifndef TL_DIV_CORR
+#define TL_DIV_CORR 0     // 1: quotients by the Jacobian determinant get a Markstein residual correction (correctly rounded in almost all cases);
+                          // 0 (measured: T6 heat 3.16 -> 3.00 ms, Q4 1.73 -> 1.62 ms, full-size parity unchanged): q = n * (1/d) with a ~1-ulp reciprocal
+#endif
+#ifndef TL_FAST_ACC
+#define TL_FAST_ACC 1     // 1: element-matrix entries are accumulated with pre-scaled factors and FMAs (2 DFMA per entry and quadrature
+                          // point instead of 4 operations); differences to the reference's rounding sequence are O(1e-16) relative
+#endif
 
 struct QTab {
     double w[EFG_MAXQ];
@@ -61,7 +70,11 @@ template <bool S> struct SharedDivisor {
     }
     __device__ __forceinline__ double operator()(double n) const {
         if constexpr (S) return __ddiv_rn(n, d);
+#if TL_DIV_CORR
         else { const double q = n * inv; const double r = fma(-q, d, n); return fma(r, inv, q); }
+#else
+        else return n * inv;      // <= 1.5 ulp: the reciprocal is good to ~1 ulp (two Newton steps), far inside the 1e-12 parity bar
+#endif
     }
 };
 
@@ -164,11 +177,36 @@ template <bool S> __device__ __forceinline__ double dotB(const double (&db)[3], 
                      : fadd<S>(fmul<S>(db[1], gy), fmul<S>(db[2], gx));
 }
 
+
+// One entry of a B'DB element matrix, all quadrature points: row dof of component ci with gradients (ax, ay), column given
+// by db[q] = D*B_j (fast mode: already scaled by JxW).  Strict mode = the operation sequence of column_rt.
+template <bool S, int NQ>
+__device__ __forceinline__ double bdb_entry(const double (&db)[NQ][3], int ci, const double (&ax)[NQ], const double (&ay)[NQ], const double (&jw)[NQ])
+{
+    double acc = 0.0;
+    if constexpr (!S && TL_FAST_ACC) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const double a = ci == 0 ? db[q][0] : db[q][1];
+            const double g1 = ci == 0 ? ax[q] : ay[q], g2 = ci == 0 ? ay[q] : ax[q];
+            acc = q == 0 ? fma(a, g1, db[q][2] * g2) : fma(a, g1, fma(db[q][2], g2, acc));
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const double t = fmul<S>(dotB<S>(db[q], ci, ax[q], ay[q]), jw[q]);
+            acc = q == 0 ? t : fadd<S>(acc, t);
+        }
+    }
+    return acc;
+}
+
 // ------------------------------------------------------------------------------------------------
 // K1 heat: ke[i,j] += dot(gradN[i], gradN[j]) * (kappa * JxW)   examples/heat/poisson/t3.jl:53-58
 template <int VK, int NQ_> struct HeatForm {
     static constexpr int ND = VK, NT = VK * VK, GK = VK, BK = VK, NQ = NQ_, GMESH = 0, NSPACES = 1;
     static constexpr bool SPLIT = false;
+    static constexpr bool SYM = true;       // the element matrix is bitwise symmetric: a sink may take the upper triangle only (emit.tri)
     __host__ __device__ static constexpr bool mask(int, int) { return true; }
     __host__ __device__ static constexpr int kidx(int i, int j) { return j * ND + i; }
     __device__ static void edofs(const DofSrc &s, int64_t e, int32_t (&d)[ND]) {
@@ -198,20 +236,33 @@ template <int VK, int NQ_> struct HeatForm {
             double gx[BK], gy[BK], JxW;
             geo_qp<S, GK, BK>(X, Y, q, gx, gy, JxW);
             const double kJ = fmul<S>(kappa, JxW);
+            if constexpr (!S && TL_FAST_ACC) {
+                double sx[BK], sy[BK];
 #pragma unroll
-            for (int j = 0; j < ND; j++)
+                for (int i = 0; i < ND; i++) { sx[i] = gx[i] * kJ; sy[i] = gy[i] * kJ; }
 #pragma unroll
-                for (int i = 0; i <= j; i++) {
-                    const double t = fmul<S>(fadd<S>(fmul<S>(gx[i], gx[j]), fmul<S>(gy[i], gy[j])), kJ);
-                    K[i][j] = q == 0 ? t : fadd<S>(K[i][j], t);
-                }
+                for (int j = 0; j < ND; j++)
+#pragma unroll
+                    for (int i = 0; i <= j; i++)
+                        K[i][j] = q == 0 ? fma(sx[i], gx[j], sy[i] * gy[j]) : fma(sx[i], gx[j], fma(sy[i], gy[j], K[i][j]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < ND; j++)
+#pragma unroll
+                    for (int i = 0; i <= j; i++) {
+                        const double t = fmul<S>(fadd<S>(fmul<S>(gx[i], gx[j]), fmul<S>(gy[i], gy[j])), kJ);
+                        K[i][j] = q == 0 ? t : fadd<S>(K[i][j], t);
+                    }
+            }
         }
-        emit_cols<Emit>(std::make_integer_sequence<int, ND>{}, K, m, emit);
+        if constexpr (Emit::TRI) emit.tri(K, m);
+        else emit_cols<Emit>(std::make_integer_sequence<int, ND>{}, K, m, emit);
     }
 };
 
 // K2 elasticity: ke[i,j] += dot(D*B_j, B_i) * JxW               examples/elasticity/stretch/t6.jl:52-58
 template <int VK, int NQ_> struct ElasticityForm {
+    static constexpr bool SYM = false;
     static constexpr int ND = 2 * VK, NT = ND * ND, GK = VK, BK = VK, NQ = NQ_, GMESH = 0, NSPACES = 1;
     template <bool S, class Emit>
     __device__ __forceinline__ static void element(const double (&X)[GK], const double (&Y)[GK], uint32_t m, Emit &emit) {
@@ -237,6 +288,24 @@ template <int VK, int NQ_> struct ElasticityForm {
         double db[NQ][3];
 #pragma unroll
         for (int q = 0; q < NQ; q++) DB<S>(c_prm, cj, gjx[q], gjy[q], db[q]);
+        if constexpr (!S && TL_FAST_ACC) {      // D*B_j scaled by JxW once, then two FMAs per entry and quadrature point
+#pragma unroll
+            for (int q = 0; q < NQ; q++)
+#pragma unroll
+                for (int r = 0; r < 3; r++) db[q][r] *= G.JxW[q];
+#pragma unroll
+            for (int i = 0; i < ND; i++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < NQ; q++) {
+                    const double a = (i % 2 == 0) ? db[q][0] : db[q][1];        // B_i = (g1, 0, g2) or (0, g2, g1)
+                    const double g1 = (i % 2 == 0) ? G.gx[q][i / 2] : G.gy[q][i / 2], g2 = (i % 2 == 0) ? G.gy[q][i / 2] : G.gx[q][i / 2];
+                    acc = q == 0 ? fma(a, g1, db[q][2] * g2) : fma(a, g1, fma(db[q][2], g2, acc));
+                }
+                out[i] = acc;
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < ND; i++) {
             double acc = 0.0;
@@ -254,6 +323,56 @@ template <int VK, int NQ_> struct ElasticityForm {
         for (int q = 0; q < NQ; q++) { gjx[q] = G.gx[q][J / 2]; gjy[q] = G.gy[q][J / 2]; }
         column_rt<S>(G, J, gjx, gjy, out);
     }
+    // BOTH columns of node nb (local dofs 2nb, 2nb+1) in one sweep over the row nodes: the row gradients are read once for
+    // two columns.  g(k) reads value k of the element's geometry record (gx[q][n] at q*BK+n, gy at NQ*BK + q*BK+n, JxW at
+    // 2*NQ*BK + q), put(i, v0, v1) receives row i of the two columns.  Same arithmetic as column_rt, entry by entry.
+    __device__ __forceinline__ static bool pairable(int J0) { return (J0 & 1) == 0; }
+    // one column, same streaming sweep (put(i, v))
+    template <bool S, class Load, class Put>
+    __device__ __forceinline__ static void column_single_rt(Load &&g, int J, Put &&put) {
+        const int nb = J >> 1, cj = J & 1;
+        double db[NQ][3], jw[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            jw[q] = g(2 * NQ * BK + q);
+            DB<S>(c_prm, cj, g(q * BK + nb), g(NQ * BK + q * BK + nb), db[q]);
+            if constexpr (!S && TL_FAST_ACC) {
+#pragma unroll
+                for (int r = 0; r < 3; r++) db[q][r] *= jw[q];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < VK; a++) {
+            double ax[NQ], ay[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) { ax[q] = g(q * BK + a); ay[q] = g(NQ * BK + q * BK + a); }
+            put(2 * a, bdb_entry<S, NQ>(db, 0, ax, ay, jw));
+            put(2 * a + 1, bdb_entry<S, NQ>(db, 1, ax, ay, jw));
+        }
+    }
+    template <bool S, class Load, class Put>
+    __device__ __forceinline__ static void column_pair_rt(Load &&g, int nb, Put &&put) {
+        double db0[NQ][3], db1[NQ][3], jw[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            jw[q] = g(2 * NQ * BK + q);
+            const double gjx = g(q * BK + nb), gjy = g(NQ * BK + q * BK + nb);
+            DB<S>(c_prm, 0, gjx, gjy, db0[q]);
+            DB<S>(c_prm, 1, gjx, gjy, db1[q]);
+            if constexpr (!S && TL_FAST_ACC) {
+#pragma unroll
+                for (int r = 0; r < 3; r++) { db0[q][r] *= jw[q]; db1[q][r] *= jw[q]; }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < VK; a++) {
+            double ax[NQ], ay[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; q++) { ax[q] = g(q * BK + a); ay[q] = g(NQ * BK + q * BK + a); }
+            put(2 * a, bdb_entry<S, NQ>(db0, 0, ax, ay, jw), bdb_entry<S, NQ>(db1, 0, ax, ay, jw));
+            put(2 * a + 1, bdb_entry<S, NQ>(db0, 1, ax, ay, jw), bdb_entry<S, NQ>(db1, 1, ax, ay, jw));
+        }
+    }
 };
 
 // Taylor-Hood T6/T3 Stokes forms.  Combined local dofs of the "2-space" forms (gen, veclap_alt):
@@ -265,6 +384,7 @@ template <int VK, int NQ_> struct ElasticityForm {
 // K5 veclap_alt: kuu[i,j] += (mu*JxW)*dot(g_i,g_j) only where c[i]==c[j] (others stay explicit zeros)
 //        examples/stokes/colliding_flow/ht_p2_p1_veclap_alt.jl:71-87
 template <bool VECLAP_ALT> struct Stokes2Form {
+    static constexpr bool SYM = false;
     static constexpr int VK = 6, PK = 3, NQ = 3;
     static constexpr int ND = 15, NT = 144 + 36 + 36, GK = 6, BK = 6, GMESH = 0, NSPACES = 2;
     template <bool S, class Emit>
@@ -297,15 +417,33 @@ template <bool VECLAP_ALT> struct Stokes2Form {
                 double db[3][3];
 #pragma unroll
                 for (int q = 0; q < 3; q++) DB<S>(c_prm, cj, gjx[q], gjy[q], db[q]);
+                if constexpr (!S && TL_FAST_ACC) {      // (see ElasticityForm::column_rt)
 #pragma unroll
-                for (int i = 0; i < 12; i++) {
-                    double acc = 0.0;
+                    for (int q = 0; q < 3; q++)
 #pragma unroll
-                    for (int q = 0; q < 3; q++) {
-                        const double t = fmul<S>(dotB<S>(db[q], i % 2, G.gx[q][i / 2], G.gy[q][i / 2]), G.JxW[q]);
-                        acc = q == 0 ? t : fadd<S>(acc, t);
+                        for (int r = 0; r < 3; r++) db[q][r] *= G.JxW[q];
+#pragma unroll
+                    for (int i = 0; i < 12; i++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 3; q++) {
+                            const double a = (i % 2 == 0) ? db[q][0] : db[q][1];
+                            const double g1 = (i % 2 == 0) ? G.gx[q][i / 2] : G.gy[q][i / 2], g2 = (i % 2 == 0) ? G.gy[q][i / 2] : G.gx[q][i / 2];
+                            acc = q == 0 ? fma(a, g1, db[q][2] * g2) : fma(a, g1, fma(db[q][2], g2, acc));
+                        }
+                        out[i] = acc;
                     }
-                    out[i] = acc;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 12; i++) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int q = 0; q < 3; q++) {
+                            const double t = fmul<S>(dotB<S>(db[q], i % 2, G.gx[q][i / 2], G.gy[q][i / 2]), G.JxW[q]);
+                            acc = q == 0 ? t : fadd<S>(acc, t);
+                        }
+                        out[i] = acc;
+                    }
                 }
             } else {
                 const double mu = c_prm[0];
@@ -357,11 +495,141 @@ template <bool VECLAP_ALT> struct Stokes2Form {
         for (int q = 0; q < 3; q++) { gjx[q] = G.gx[q][J < 12 ? J / 2 : 0]; gjy[q] = G.gy[q][J < 12 ? J / 2 : 0]; }
         column_rt<S>(G, J, gjx, gjy, out);
     }
+    // both velocity columns of node nb in one sweep (see ElasticityForm::column_pair_rt); pressure columns stay single
+    __device__ __forceinline__ static bool pairable(int J0) { return (J0 & 1) == 0 && J0 < 12; }
+    // one column, streaming sweep over the row nodes (put(i, v)); rows 12..14 of a pressure column are never appended
+    template <bool S, class Load, class Put>
+    __device__ __forceinline__ static void column_single_rt(Load &&g, int J, Put &&put) {
+        constexpr int NQ_ = 3, BK_ = 6;
+        const QTab &tp = c_tab[kind_slot(3)];
+        double jw[NQ_];
+#pragma unroll
+        for (int q = 0; q < NQ_; q++) jw[q] = g(2 * NQ_ * BK_ + q);
+        if (J >= 12) {                          // column of pressure dof m: kup[i, m] = sum_q (-JxW*Np[m]) * gradNu[i][c[i]]
+            const int m = J - 12;
+            double w[NQ_];
+#pragma unroll
+            for (int q = 0; q < NQ_; q++) w[q] = fmul<S>(-jw[q], tp.N[q][m]);
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < NQ_; q++) {
+                    const double t0 = fmul<S>(w[q], g(q * BK_ + a)), t1 = fmul<S>(w[q], g(NQ_ * BK_ + q * BK_ + a));
+                    a0 = q == 0 ? t0 : fadd<S>(a0, t0);
+                    a1 = q == 0 ? t1 : fadd<S>(a1, t1);
+                }
+                put(2 * a, a0);
+                put(2 * a + 1, a1);
+            }
+            return;
+        }
+        const int nb = J >> 1, cj = J & 1;
+        double gjx[NQ_], gjy[NQ_];
+#pragma unroll
+        for (int q = 0; q < NQ_; q++) { gjx[q] = g(q * BK_ + nb); gjy[q] = g(NQ_ * BK_ + q * BK_ + nb); }
+        if constexpr (!VECLAP_ALT) {
+            double db[NQ_][3];
+#pragma unroll
+            for (int q = 0; q < NQ_; q++) {
+                DB<S>(c_prm, cj, gjx[q], gjy[q], db[q]);
+                if constexpr (!S && TL_FAST_ACC) {
+#pragma unroll
+                    for (int r = 0; r < 3; r++) db[q][r] *= jw[q];
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                double ax[NQ_], ay[NQ_];
+#pragma unroll
+                for (int q = 0; q < NQ_; q++) { ax[q] = g(q * BK_ + a); ay[q] = g(NQ_ * BK_ + q * BK_ + a); }
+                put(2 * a, bdb_entry<S, NQ_>(db, 0, ax, ay, jw));
+                put(2 * a + 1, bdb_entry<S, NQ_>(db, 1, ax, ay, jw));
+            }
+        } else {
+            const double mu = c_prm[0];
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < NQ_; q++) {
+                    const double t = fmul<S>(fmul<S>(mu, jw[q]), fadd<S>(fmul<S>(g(q * BK_ + a), gjx[q]), fmul<S>(g(NQ_ * BK_ + q * BK_ + a), gjy[q])));
+                    acc = q == 0 ? t : fadd<S>(acc, t);
+                }
+                put(2 * a, cj == 0 ? acc : 0.0);
+                put(2 * a + 1, cj == 1 ? acc : 0.0);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ_; q++) {
+                const double t = fmul<S>(fmul<S>(-jw[q], tp.N[q][m]), cj == 0 ? gjx[q] : gjy[q]);
+                acc = q == 0 ? t : fadd<S>(acc, t);
+            }
+            put(12 + m, acc);
+        }
+    }
+    template <bool S, class Load, class Put>
+    __device__ __forceinline__ static void column_pair_rt(Load &&g, int nb, Put &&put) {
+        constexpr int NQ_ = 3, BK_ = 6;
+        const QTab &tp = c_tab[kind_slot(3)];
+        double jw[NQ_], gjx[NQ_], gjy[NQ_];
+#pragma unroll
+        for (int q = 0; q < NQ_; q++) { jw[q] = g(2 * NQ_ * BK_ + q); gjx[q] = g(q * BK_ + nb); gjy[q] = g(NQ_ * BK_ + q * BK_ + nb); }
+        if constexpr (!VECLAP_ALT) {
+            double db0[NQ_][3], db1[NQ_][3];
+#pragma unroll
+            for (int q = 0; q < NQ_; q++) {
+                DB<S>(c_prm, 0, gjx[q], gjy[q], db0[q]);
+                DB<S>(c_prm, 1, gjx[q], gjy[q], db1[q]);
+                if constexpr (!S && TL_FAST_ACC) {
+#pragma unroll
+                    for (int r = 0; r < 3; r++) { db0[q][r] *= jw[q]; db1[q][r] *= jw[q]; }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                double ax[NQ_], ay[NQ_];
+#pragma unroll
+                for (int q = 0; q < NQ_; q++) { ax[q] = g(q * BK_ + a); ay[q] = g(NQ_ * BK_ + q * BK_ + a); }
+                put(2 * a, bdb_entry<S, NQ_>(db0, 0, ax, ay, jw), bdb_entry<S, NQ_>(db1, 0, ax, ay, jw));
+                put(2 * a + 1, bdb_entry<S, NQ_>(db0, 1, ax, ay, jw), bdb_entry<S, NQ_>(db1, 1, ax, ay, jw));
+            }
+        } else {
+            const double mu = c_prm[0];
+#pragma unroll
+            for (int a = 0; a < 6; a++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < NQ_; q++) {
+                    const double t = fmul<S>(fmul<S>(mu, jw[q]), fadd<S>(fmul<S>(g(q * BK_ + a), gjx[q]), fmul<S>(g(NQ_ * BK_ + q * BK_ + a), gjy[q])));
+                    acc = q == 0 ? t : fadd<S>(acc, t);
+                }
+                put(2 * a, acc, 0.0);          // entries with c[i] != c[j] stay explicit zeros
+                put(2 * a + 1, 0.0, acc);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++) {          // rows 12..14 = transpose(kup): kup[J, m]
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ_; q++) {
+                const double w = fmul<S>(-jw[q], tp.N[q][m]);
+                const double t0 = fmul<S>(w, gjx[q]), t1 = fmul<S>(w, gjy[q]);
+                a0 = q == 0 ? t0 : fadd<S>(a0, t0);
+                a1 = q == 0 ? t1 : fadd<S>(a1, t1);
+            }
+            put(12 + m, a0, a1);
+        }
+    }
 };
 
 // K4 Reddy: examples/stokes/colliding_flow/ht_p2_p1.jl:77-101 (Jacobian of the PRESSURE element);
 // veclap: examples/stokes/colliding_flow/ht_p2_p1_veclap.jl:75-94 (no ux-uy coupling blocks).
 template <bool VECLAP> struct Stokes3Form {
+    static constexpr bool SYM = false;
     static constexpr int VK = 6, PK = 3, NQ = 3;
     static constexpr int ND = 15, NT = VECLAP ? 144 : 216, GK = 3, BK = 6, GMESH = 1, NSPACES = 3;
     static constexpr bool SPLIT = false;

@@ -99,6 +99,16 @@ template <class F> constexpr bool tl_persist() { return TL_GEO && (F::SPLIT ? TL
 #define TL_GEO_SPLIT 1  // vector forms: phase 1a reads the tile's geometry block too (the block sits behind the shared
                         // geometry/metadata area)
 #endif
+#ifndef TL_PAIRS
+#define TL_PAIRS 1      // vector forms, phase 1b: one thread per node (both dofs' columns) instead of one per column
+#endif
+#ifndef TL_SYM_STAGE
+#define TL_SYM_STAGE 1  // forms with a bitwise-symmetric element matrix (heat) stage its upper triangle only: ND(ND+1)/2 rows of
+                        // one entry per tile element instead of ND rows of one entry per (element, owned column)
+#endif
+template <class F> __host__ __device__ constexpr bool tl_sym() { return TL_SYM_STAGE && F::SYM && !F::SPLIT; }
+template <class F> __host__ __device__ constexpr int tl_srows() { return tl_sym<F>() ? F::ND * (F::ND + 1) / 2 : F::ND; }
+__host__ __device__ constexpr int tl_tri(int a, int b) { return b * (b + 1) / 2 + a; }      // a <= b
 #ifndef TL_VEC_CONN
 #define TL_VEC_CONN 1   // tile connectivity read with 8/16-byte loads (T6: 3 x int2, Q4: 1 x int4) instead of 4-byte loads
 #endif
@@ -645,7 +655,8 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                 const int32_t r = edof[(int64_t)e * F::ND + i];
                 int l2 = 0, h2 = nr;
                 while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (rowval[r0 + mid] < r) l2 = mid + 1; else h2 = mid; }
-                const uint32_t sidx = (uint32_t)i * (uint32_t)td.nqs + q;
+                const uint32_t sidx = tl_sym<F>() ? (uint32_t)tl_tri(i < lj ? i : lj, i < lj ? lj : i) * (uint32_t)td.nqs + le
+                                                  : (uint32_t)i * (uint32_t)td.nqs + q;
                 if (sidx >= 0xFFFEu) *err = 4;
                 if (cnt[l2] > TL_LIGHT) { hidx[off[l2]] = (uint16_t)sidx; off[l2]++; }
                 else if (off[l2]++ == 0) first[l2] = (uint16_t)sidx;
@@ -678,7 +689,7 @@ __global__ void k_tl_tiles_meta0(int ntiles, const int64_t *__restrict__ meta_of
     GRID_STRIDE(T, ntiles) tiles[T].meta0 = meta_off[T];
 }
 
-__global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, int gk, const int32_t *__restrict__ tnn /* null: no geometry blocks */,
+__global__ void k_tl_tiles_fill(int ntiles, int nd /* stage rows */, bool sym, int gsz, int gk, const int32_t *__restrict__ tnn /* null: no geometry blocks */,
                                 int64_t *__restrict__ geo_bytes, const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ tcol_slot,
                                 const int64_t *__restrict__ tcol_gidx, const int64_t *__restrict__ tcol_heavy, const int64_t *__restrict__ telem_ptr,
                                 const int64_t *__restrict__ run_of_k /* exclusive scan of run-head flags */,
@@ -707,6 +718,7 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, int gk, const int32
         uint32_t q = 0;
         for (int r = 0; r <= TL_MAXND; r++) { d.qbase[r] = (uint16_t)(q > 65535u ? 65535u : q); if (r < TL_MAXND) q += above[r]; }
         d.nq = (int32_t)q;
+        if (sym) q = (uint32_t)d.nelem;          // symmetric stage: one column per tile element
         d.nqs = (uint16_t)((q | 1u) > 65535u ? 65535u : (q | 1u));
         d.meta_bytes = d.nslot > 0 ? tl_meta_goff_bytes(d.nslot) + tl_meta_gidx_bytes(d.ncontrib) + tl_meta_rows_bytes(d.nslot) + tl_align16((int)sizeof(TileHeavy) * d.nheavy) : 0;
         d.meta0 = 0;
@@ -730,6 +742,15 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd, int gsz, int gk, const int32
 __device__ __forceinline__ uint32_t tl_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 template <class F> struct StageEmit {
+    static constexpr bool TRI = tl_sym<F>();
+    // upper triangle of a bitwise-symmetric element matrix: entry (a, b), a <= b, is staged if column a or column b is owned
+    __device__ __forceinline__ void tri(const double (&K)[F::ND][F::ND], uint32_t mm) {
+#pragma unroll
+        for (int b = 0; b < F::ND; b++)
+#pragma unroll
+            for (int a = 0; a <= b; a++)
+                if (mm & ((1u << a) | (1u << b))) stage[tl_tri(a, b) * nq + le] = K[a][b];
+    }
     double *__restrict__ stage;
     const uint16_t *__restrict__ qbase;
     uint32_t m, le;
@@ -838,7 +859,7 @@ __device__ __forceinline__ void tl_geometry_to_smem(int64_t g, int le, int ne, c
     }
     smask[le] = tmask[g];
 }
-// same, fed from the tile's geometry block in shared memory (persistent kernel)
+// same, fed from the tile's geometry block in shared memory; one quadrature point at a time (small register footprint)
 template <class F, bool S>
 __device__ __forceinline__ void tl_geometry_to_smem_local(int le, int ne, const uint16_t *__restrict__ c16, const double2 *__restrict__ sxy,
                                                           double *__restrict__ Gs)
@@ -847,41 +868,65 @@ __device__ __forceinline__ void tl_geometry_to_smem_local(int le, int ne, const 
     double X[GK], Y[GK];
 #pragma unroll
     for (int a = 0; a < GK; a++) { const double2 p = sxy[c16[le * GK + a]]; X[a] = p.x; Y[a] = p.y; }
-    Geo<BK, NQ> G;
-    geo_compute<S, GK, BK, NQ>(X, Y, G);
 #pragma unroll
     for (int q = 0; q < NQ; q++) {
+        double gx[BK], gy[BK], JxW;
+        geo_qp<S, GK, BK>(X, Y, q, gx, gy, JxW);
 #pragma unroll
         for (int n = 0; n < BK; n++) {
-            Gs[(q * BK + n) * ne + le] = G.gx[q][n];
-            Gs[(NQ * BK + q * BK + n) * ne + le] = G.gy[q][n];
+            Gs[(q * BK + n) * ne + le] = gx[n];
+            Gs[(NQ * BK + q * BK + n) * ne + le] = gy[n];
         }
-        Gs[(2 * NQ * BK + q) * ne + le] = G.JxW[q];
+        Gs[(2 * NQ * BK + q) * ne + le] = JxW;
     }
 }
 template <class F, bool S>
 __device__ __forceinline__ void tl_column_to_stage(int qc, int le, int J, int ne, int nq, const double *__restrict__ Gs, double *__restrict__ stage)
 {
-    constexpr int NQ = F::NQ, BK = F::BK;
-    Geo<BK, NQ> G;
-    double gjx[NQ], gjy[NQ];
-    const int nj = F::colnode(J);
+    const double *ge = Gs + le;       // geometry record of the element: value k at ge[k * ne]
+    F::template column_single_rt<S>([&](int k) { return ge[k * ne]; }, J, [&](int i, double v) { stage[i * nq + qc] = v; });
+}
+
+// both columns of one node (local dofs J0, J0+1) of tile element le -> staged columns qc0, qc1
+template <class F, bool S>
+__device__ __forceinline__ void tl_column_pair_to_stage(int qc0, int qc1, int le, int J0, int ne, int nq, const double *__restrict__ Gs, double *__restrict__ stage)
+{
+    const double *ge = Gs + le;
+    F::template column_pair_rt<S>([&](int k) { return ge[k * ne]; }, F::colnode(J0),
+                                  [&](int i, double v0, double v1) { stage[i * nq + qc0] = v0; stage[i * nq + qc1] = v1; });
+}
+// Phase 1b of the SPLIT forms: one thread per PAIR of staged columns of a tile element (the two dofs of a node; the row
+// gradients are read once for both).  Elements are ordered by their number of owned columns (descending), qbase[r] = first
+// staged column of "r-th owned column of an element", so pair rank p of element le covers staged columns qbase[2p] + le and
+// qbase[2p+1] + le.  Columns that do not pair up (a pressure dof, a node with one owned dof) take the single-column worker.
+template <class F, bool S, int BLOCK>
+__device__ __forceinline__ void tl_phase1b_pairs(const TileDescFull &td, const uint16_t *__restrict__ smask, int ne, int nq, const double *__restrict__ Gs,
+                                                 double *__restrict__ stage, int tid)
+{
+    constexpr int NP = (F::ND + 1) / 2;
+    int total = 0;
 #pragma unroll
-    for (int q = 0; q < NQ; q++) {
+    for (int p = 0; p < NP; p++) total += (int)td.qbase[2 * p + 1] - (int)td.qbase[2 * p];
+    for (int t = tid; t < total; t += BLOCK) {
+        int p = 0, le = t;
 #pragma unroll
-        for (int n = 0; n < BK; n++) {
-            G.gx[q][n] = Gs[(q * BK + n) * ne + le];
-            G.gy[q][n] = Gs[(NQ * BK + q * BK + n) * ne + le];
+        for (int pp = 0; pp < NP - 1; pp++) {
+            const int c = (int)td.qbase[2 * p + 1] - (int)td.qbase[2 * p];
+            if (le >= c) { le -= c; p++; }
         }
-        G.JxW[q] = Gs[(2 * NQ * BK + q) * ne + le];
-        gjx[q] = Gs[(q * BK + nj) * ne + le];
-        gjy[q] = Gs[(NQ * BK + q * BK + nj) * ne + le];
+        uint32_t mm = smask[le];
+        for (int k = 0; k < 2 * p; k++) mm &= mm - 1;
+        const int J0 = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const int J1 = mm ? __ffs(mm) - 1 : -1;
+        const int qc0 = (int)td.qbase[2 * p] + le, qc1 = (int)td.qbase[2 * p + 1] + le;
+        if (J1 == J0 + 1 && F::pairable(J0)) {
+            tl_column_pair_to_stage<F, S>(qc0, qc1, le, J0, ne, nq, Gs, stage);
+        } else {
+            tl_column_to_stage<F, S>(qc0, le, J0, ne, nq, Gs, stage);
+            if (J1 >= 0) tl_column_to_stage<F, S>(qc1, le, J1, ne, nq, Gs, stage);
+        }
     }
-    double out[F::ND];
-    F::template column_rt<S>(G, J, gjx, gjy, out);
-#pragma unroll
-    for (int i = 0; i < F::ND; i++)
-        if (F::mask(i, J)) stage[i * nq + qc] = out[i];
 }
 
 // ---- phase 2 of the numeric kernels ---------------------------------------------------------------------
@@ -965,7 +1010,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     constexpr int GSZ = tl_gsz<F>();
     // SPLIT forms: the per-element geometry of phase 1 and the gather metadata of phase 2 share the same shared-memory
     // area, so the TMA copy is issued after phase 1; otherwise it is issued now and lands while phase 1 computes
-    unsigned char *smeta = smem_raw + tl_stage_bytes(F::ND, td.nqs);
+    unsigned char *smeta = smem_raw + tl_stage_bytes(tl_srows<F>(), td.nqs);
     // geometry block (GEO): txy | conn16 | mask16, behind the metadata area (vector forms: behind the area the metadata shares with Gs)
     unsigned char *sgeo = smeta + (F::SPLIT ? max(td.meta_bytes, tl_geo_bytes(GSZ, td.nelem)) : td.meta_bytes);
     if (GEO && tid == 0) tl_bulk_load(tl_smem_addr(sgeo), geo + td.geo0, (uint32_t)td.geo_bytes, barB);   // needed first
@@ -1002,7 +1047,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     } else {
         // phase 1a: one thread per tile element: Jacobian / JxW / gradients at every quadrature point -> shared memory
         const int ne = td.nelem;
-        double *Gs = reinterpret_cast<double *>(smem_raw + tl_stage_bytes(F::ND, nq));   // SoA: Gs[k * ne + le]
+        double *Gs = reinterpret_cast<double *>(smem_raw + tl_stage_bytes(tl_srows<F>(), nq));   // SoA: Gs[k * ne + le]
         const uint16_t *smask;
         if constexpr (GEO) {
             tl_mbar_wait(barB, 0);
@@ -1017,6 +1062,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
             smask = sm;
         }
         __syncthreads();
+#if TL_PAIRS
+        tl_phase1b_pairs<F, S, BLOCK>(td, smask, ne, nq, Gs, stage, tid);
+#else
         // phase 1b: one thread per staged column (tile element, owned local column) -> stage
         for (int qc = tid; qc < ncols; qc += BLOCK) {
             int r = 0;
@@ -1027,6 +1075,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
             const int J = __ffs(mm) - 1;
             tl_column_to_stage<F, S>(qc, le, J, ne, nq, Gs, stage);
         }
+#endif
     }
     __syncthreads();
     if (F::SPLIT && tid == 0) {
@@ -1116,6 +1165,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric_p(const TileDescFull
                 double *Gs = reinterpret_cast<double *>(smem_raw + off_gs);
                 for (int le = tid; le < ne; le += BLOCK) tl_geometry_to_smem_local<F, S>(le, ne, sc16, sxy, Gs);
                 __syncthreads();
+#if TL_PAIRS
+                (void)ncols;
+                tl_phase1b_pairs<F, S, BLOCK>(td, sm16, ne, nq, Gs, stage, tid);
+#else
                 // phase 1b: one thread per staged column (tile element, owned local column) -> stage
                 for (int qc = tid; qc < ncols; qc += BLOCK) {
                     int r = 0;
@@ -1126,6 +1179,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric_p(const TileDescFull
                     const int J = __ffs(mm) - 1;
                     tl_column_to_stage<F, S>(qc, le, J, ne, nq, Gs, stage);
                 }
+#endif
             }
         }
         __syncthreads();      // stage complete; geometry area free; next descriptor visible
@@ -1157,23 +1211,29 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric_p(const TileDescFull
 #define TL_BLOCK_NS 320
 #endif
 #ifndef TL_BLOCK_SPLIT
-#define TL_BLOCK_SPLIT 256
+#define TL_BLOCK_SPLIT (TL_PAIRS ? 352 : 256)
 #endif
-template <class F> __host__ __device__ constexpr int tl_block() { return F::SPLIT ? TL_BLOCK_SPLIT : (F::ND > 8 ? 256 : TL_BLOCK_NS); }
+#ifndef TL_BLOCK_SPLIT15
+#define TL_BLOCK_SPLIT15 256    // Stokes gen / veclap_alt (15 columns, tiles of 32 elements: 8 pair items per element -> 256 work items)
+#endif
+template <class F> __host__ __device__ constexpr int tl_block() { return F::SPLIT ? (F::ND >= 15 ? TL_BLOCK_SPLIT15 : TL_BLOCK_SPLIT) : (F::ND > 8 ? 256 : TL_BLOCK_NS); }
 
 static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32};
+template <class F> __host__ __device__ constexpr int tl_items_1b() { return TL_PAIRS ? (F::ND + 1) / 2 : F::ND; }
 template <class F> static int tl_default_tile_elems()
 {
     // shared memory per owned element-equivalent ~ stage ND*ND*8 + gather metadata NT*2 + ~2.7*ND*ND
-    const double per_elem = F::ND * F::ND * 10.7 + F::NT * 2.0;   // (SPLIT forms: the geometry area aliases the metadata area)
+    // (SPLIT forms: the geometry area aliases the metadata area; symmetric stage: upper triangle of every tile element incl. halo)
+    const double per_elem = tl_sym<F>() ? tl_srows<F>() * 8.0 * 1.3 + F::ND * F::ND * 2.7 + F::NT * 2.0 : F::ND * F::ND * 10.7 + F::NT * 2.0;
     int te = 32;
     for (int c : TL_TILE_SIZES)
         if (c * per_elem <= 118.0 * 1024) { te = c; break; }
     if (F::SPLIT) {
-        // phase 1b runs in rounds of tl_block() staged columns (te*ND on average): avoid a nearly empty last round
+        // phase 1b runs in rounds of tl_block() work items (te*ND staged columns, or te*ceil(ND/2) column pairs): avoid a
+        // nearly empty last round
         for (int c : TL_TILE_SIZES) {
             if (c > te) continue;
-            const double rounds = (double)c * F::ND / tl_block<F>();
+            const double rounds = (double)c * tl_items_1b<F>() / tl_block<F>();
             if (rounds / ceil(rounds) >= 0.85) { te = c; break; }
         }
     }
@@ -1485,12 +1545,12 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
     CUDA_CHECK(cudaMemsetAsync(mbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     CUDA_CHECK(cudaMemsetAsync(gbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     td->tiles.alloc(pool, (size_t)ntiles);
-    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, ND, tl_gsz<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, pslot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
+    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, tl_srows<F>(), tl_sym<F>(), tl_gsz<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, pslot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
            nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
     int32_t hmax[8];
     CUDA_CHECK(cudaMemcpyAsync(hmax, maxima.p, sizeof hmax, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    ctx->tl.max_nq = hmax[1] / ND; ctx->tl.max_nslot = 0; ctx->tl.max_nelem = hmax[3]; ctx->tl.max_nrun = 0;
+    ctx->tl.max_nq = hmax[1] / tl_srows<F>(); ctx->tl.max_nslot = 0; ctx->tl.max_nelem = hmax[3]; ctx->tl.max_nrun = 0;
     ctx->tl.tile_elems = te;
     td->stage_bytes = 0;
     td->meta_max = 0;
@@ -1550,7 +1610,7 @@ template <class F> static int tl_next_tile_elems(int te, int smem, int budget)
     if (F::SPLIT) {
         for (int c : TL_TILE_SIZES) {
             if (c >= te) continue;
-            const double rounds = (double)c * F::ND / tl_block<F>();
+            const double rounds = (double)c * tl_items_1b<F>() / tl_block<F>();
             if (rounds / ceil(rounds) < 0.85 && c > 32) continue;
             next = c;
             if (c <= te * scale * 1.03) break;      // (else: this candidate would overflow as well)

@@ -189,6 +189,7 @@ template <class F> void twopass_symbolic(efg_ctx *ctx)
 
 // numeric kernel 1: all element matrices, Ke[k*nel + e] (coalesced across elements)
 template <class F> struct KeEmit {
+    static constexpr bool TRI = false;
     double *__restrict__ Ke;
     int64_t e, nel;
     template <int J> __device__ __forceinline__ void col(const double (&out)[F::ND]) {

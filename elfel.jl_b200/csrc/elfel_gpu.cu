@@ -5,6 +5,7 @@
 #include "efg_tiled.cuh"
 #include "efg_vector.cuh"
 #include "efg_multi.cuh"
+#include "efg_gen.cuh"
 
 #include <cstring>
 #include <cmath>
@@ -313,7 +314,7 @@ int efg_destroy(efg_ctx *ctx)
     tables_unregister(ctx);
     invalidate(ctx);
     for (auto &m : ctx->mesh) { m.conn.release(); m.xy.release(); }
-    for (auto &s : ctx->space) s.dof.release();
+    for (auto &s : ctx->space) { s.dof.release(); s.isdatum.release(); }
     ctx->rfirst.release(); ctx->rlast1.release(); ctx->roff.release(); ctx->scratch.release(); ctx->cstage[0].release(); ctx->cstage[1].release();
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -420,6 +421,7 @@ int efg_set_space(efg_ctx *ctx, int slot, int mesh_slot, int ncomp, int64_t nnod
     SpaceDev &s = ctx->space[slot];
     s.mesh = mesh_slot; s.ncomp = ncomp; s.nnodes = nnodes;
     s.dof.alloc(ctx->pool, (size_t)(nnodes * ncomp));
+    s.isdatum.release();
     // dof number 0 (= not numbered) is accepted here and rejected by the symbolic phase, like sparse() does
     ingest_index(ctx, dofnums, nnodes * ncomp, 0, ((int64_t)1 << 31) - 1, s.dof.p, "efg_set_space: dof number");
     API_END(ctx)
@@ -1105,6 +1107,179 @@ int efgm_device_ctx(efg_multi *m, int device, efg_ctx **ctx_out, int64_t *nrange
     if (firsts_out) *firsts_out = d.firsts.data();
     if (lasts_out) *lasts_out = d.lasts.data();
     MAPI_END(m)
+}
+
+
+// ---- meshes, EBCs and numbering made on the device (efg_gen.cuh) ---------------------------------------
+int efg_gen_mesh(efg_ctx *ctx, int slot, int kind, int64_t nL, int64_t nW, double Length, double Width, double xshift, double yshift)
+{
+    API_BEGIN(ctx)
+    if (slot < 0 || slot > 1) efg_throw(EFG_ERR_INVALID, "mesh_slot must be 0 or 1");
+    if (kind != EFG_T3 && kind != EFG_Q4 && kind != EFG_T6) efg_throw(EFG_ERR_INVALID, "unsupported element kind %d", kind);
+    if (nL < 1 || nW < 1 || !(Length > 0.0) || !(Width > 0.0)) efg_throw(EFG_ERR_INVALID, "bad block dimensions");
+    const int64_t nv = (nL + 1) * (nW + 1);
+    const int64_t nnodes = kind == EFG_T6 ? nv + (4 * nW + 1) + (nL - 1) * (3 * nW + 1) : nv;
+    const int64_t nel = kind == EFG_Q4 ? nL * nW : 2 * nL * nW;
+    if (nnodes >= ((int64_t)1 << 31) || nel * kind >= ((int64_t)1 << 32)) efg_throw(EFG_ERR_LIMIT, "mesh too large for 32-bit device indices");
+    invalidate(ctx);
+    MeshDev &m = ctx->mesh[slot];
+    m.kind = kind; m.nel = nel; m.nnodes = nnodes;
+    m.conn.alloc(ctx->pool, (size_t)(nel * kind));
+    m.xy.alloc(ctx->pool, (size_t)nnodes);
+    LAUNCH(ctx, k_gen_grid_xy, grid_for(nv, 256), 256, 0, nL, nW, Length, Width, m.xy.p);
+    if (kind == EFG_T3) LAUNCH(ctx, k_gen_t3, grid_for(nL * nW, 256), 256, 0, nL, nW, m.conn.p);
+    else if (kind == EFG_Q4) LAUNCH(ctx, k_gen_q4, grid_for(nL * nW, 256), 256, 0, nL, nW, m.conn.p);
+    else LAUNCH(ctx, k_gen_t6, grid_for(nL * nW, 256), 256, 0, nL, nW, Length, Width, m.conn.p, m.xy.p);
+    if (xshift != 0.0 || yshift != 0.0) LAUNCH(ctx, k_gen_shift, grid_for(nnodes, 256), 256, 0, m.xy.p, nnodes, xshift, yshift);
+    API_END(ctx)
+}
+
+/* T6toT3: the pressure mesh of a Taylor-Hood pair -- the corner nodes of every T6 element, own vertex collection */
+int efg_gen_mesh_corners(efg_ctx *ctx, int slot_dst, int slot_src)
+{
+    API_BEGIN(ctx)
+    if (slot_dst < 0 || slot_dst > 1 || slot_src < 0 || slot_src > 1 || slot_dst == slot_src) efg_throw(EFG_ERR_INVALID, "bad mesh slots");
+    const MeshDev &src = ctx->mesh[slot_src];
+    if (src.kind != EFG_T6) efg_throw(EFG_ERR_STATE, "efg_gen_mesh_corners needs a T6 mesh in the source slot");
+    DevBuf<int32_t> mx;
+    mx.alloc(ctx->pool, 1);
+    CUDA_CHECK(cudaMemsetAsync(mx.p, 0, sizeof(int32_t), ctx->stream));
+    MeshDev &m = ctx->mesh[slot_dst];
+    invalidate(ctx);
+    m.kind = EFG_T3; m.nel = src.nel;
+    m.conn.alloc(ctx->pool, (size_t)(src.nel * 3 + 1));
+    LAUNCH(ctx, k_gen_corners, grid_for(src.nel, 256), 256, 0, src.conn.p, src.nel, m.conn.p, mx.p);
+    const int64_t nv = (int64_t)tl_read(ctx, mx.p) + 1;
+    m.nnodes = nv;
+    m.xy.alloc(ctx->pool, (size_t)nv);
+    CUDA_CHECK(cudaMemcpyAsync(m.xy.p, src.xy.p, (size_t)nv * sizeof(double2), cudaMemcpyDeviceToDevice, ctx->stream));
+    API_END(ctx)
+}
+
+int efg_gen_space(efg_ctx *ctx, int slot, int mesh_slot, int ncomp)
+{
+    API_BEGIN(ctx)
+    if (slot < 0 || slot > 2 || mesh_slot < 0 || mesh_slot > 1) efg_throw(EFG_ERR_INVALID, "bad space/mesh slot");
+    if (ncomp < 1 || ncomp > 2) efg_throw(EFG_ERR_INVALID, "ncomp must be 1 or 2");
+    if (ctx->mesh[mesh_slot].kind == 0) efg_throw(EFG_ERR_STATE, "mesh %d not set", mesh_slot);
+    invalidate(ctx);
+    SpaceDev &s = ctx->space[slot];
+    s.mesh = mesh_slot; s.ncomp = ncomp; s.nnodes = ctx->mesh[mesh_slot].nnodes;
+    s.dof.alloc(ctx->pool, (size_t)(s.nnodes * ncomp));
+    s.isdatum.alloc(ctx->pool, (size_t)(s.nnodes * ncomp) + 1);      // (+1: the numbering scans read n + 1 flags)
+    LAUNCH(ctx, k_tl_fill_i32, grid_for(s.nnodes * ncomp, 256), 256, 0, s.dof.p, s.nnodes * ncomp, -1);     // unnumbered
+    CUDA_CHECK(cudaMemsetAsync(s.isdatum.p, 0, (size_t)(s.nnodes * ncomp) + 1, ctx->stream));
+    API_END(ctx)
+}
+
+static SpaceDev &gen_space_of(efg_ctx *ctx, int slot)
+{
+    if (slot < 0 || slot > 2 || ctx->space[slot].mesh < 0 || !ctx->space[slot].isdatum.p) efg_throw(EFG_ERR_STATE, "space %d was not made by efg_gen_space", slot);
+    return ctx->space[slot];
+}
+
+/* comp: 1-based component, 0 = every component */
+int efg_setebc_box(efg_ctx *ctx, int space_slot, int comp, double x0, double x1, double y0, double y1)
+{
+    API_BEGIN(ctx)
+    SpaceDev &s = gen_space_of(ctx, space_slot);
+    if (comp < 0 || comp > s.ncomp) efg_throw(EFG_ERR_INVALID, "space %d has no component %d", space_slot, comp);
+    invalidate(ctx);
+    LAUNCH(ctx, k_gen_ebc_box, grid_for(s.nnodes, 256), 256, 0, ctx->mesh[s.mesh].xy.p, s.nnodes, s.ncomp, comp - 1, x0, x1, y0, y1, s.isdatum.p);
+    API_END(ctx)
+}
+
+int efg_setebc_nodes(efg_ctx *ctx, int space_slot, int comp, int64_t n, const int64_t *node_ids)
+{
+    API_BEGIN(ctx)
+    SpaceDev &s = gen_space_of(ctx, space_slot);
+    if (comp < 0 || comp > s.ncomp) efg_throw(EFG_ERR_INVALID, "space %d has no component %d", space_slot, comp);
+    if (n < 0 || (n > 0 && !node_ids)) efg_throw(EFG_ERR_INVALID, "bad node list");
+    invalidate(ctx);
+    if (n == 0) return EFG_OK;
+    DevBuf<int64_t> ids;
+    DevBuf<int> err;
+    ids.alloc(ctx->pool, (size_t)n); err.alloc(ctx->pool, 1);
+    CUDA_CHECK(cudaMemcpyAsync(ids.p, node_ids, (size_t)n * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(err.p, 0, sizeof(int), ctx->stream));
+    LAUNCH(ctx, k_gen_ebc_nodes, grid_for(n, 256), 256, 0, ids.p, n, s.nnodes, s.ncomp, comp - 1, s.isdatum.p, err.p);
+    if (tl_read(ctx, err.p)) efg_throw(EFG_ERR_INDEX, "BoundsError: a node id is outside 1..%lld", (long long)s.nnodes);
+    API_END(ctx)
+}
+
+/* numberdofs!(spaces in the order given): free dofs of space 1, 2, ... first, then the data dofs in the same nesting */
+int efg_number_dofs(efg_ctx *ctx, int nspaces, const int *space_slots, int64_t *nfree_out, int64_t *ndofs_out)
+{
+    API_BEGIN(ctx)
+    if (nspaces < 1 || nspaces > 3 || !space_slots) efg_throw(EFG_ERR_INVALID, "bad space list");
+    invalidate(ctx);
+    std::vector<DevBuf<int64_t>> freepos((size_t)nspaces), datapos((size_t)nspaces);
+    std::vector<int64_t> nfree((size_t)nspaces), ndata((size_t)nspaces);
+    for (int k = 0; k < nspaces; k++) {
+        SpaceDev &s = gen_space_of(ctx, space_slots[k]);
+        const int64_t n = s.nnodes * s.ncomp;
+        freepos[(size_t)k].alloc(ctx->pool, (size_t)n + 1); datapos[(size_t)k].alloc(ctx->pool, (size_t)n + 1);
+        cub::TransformInputIterator<int64_t, NotU8, const uint8_t *> itf(s.isdatum.p, NotU8());
+        cub::TransformInputIterator<int64_t, IsU8, const uint8_t *> itd(s.isdatum.p, IsU8());
+        tl_excl_scan(ctx, itf, freepos[(size_t)k].p, n + 1);
+        tl_excl_scan(ctx, itd, datapos[(size_t)k].p, n + 1);
+        nfree[(size_t)k] = tl_read(ctx, freepos[(size_t)k].p + n);
+        ndata[(size_t)k] = n - nfree[(size_t)k];
+    }
+    int64_t free0 = 0, data0 = 0;
+    for (int k = 0; k < nspaces; k++) data0 += nfree[(size_t)k];
+    const int64_t nf_total = data0;
+    for (int k = 0; k < nspaces; k++) {
+        SpaceDev &s = ctx->space[space_slots[k]];
+        const int64_t n = s.nnodes * s.ncomp;
+        if (data0 + ndata[(size_t)k] >= ((int64_t)1 << 31)) efg_throw(EFG_ERR_LIMIT, "more than 2^31 dofs");
+        LAUNCH(ctx, k_gen_numbers, grid_for(n, 256), 256, 0, s.isdatum.p, freepos[(size_t)k].p, datapos[(size_t)k].p, n, free0, data0, s.dof.p);
+        free0 += nfree[(size_t)k];
+        data0 += ndata[(size_t)k];
+    }
+    if (nfree_out) *nfree_out = nf_total;
+    if (ndofs_out) *ndofs_out = data0;
+    API_END(ctx)
+}
+
+/* copies of the device-resident inputs in the reference's layout (Int64 1-based conn nen x nel, xy 2 x nnodes); sizes via NULL pointers */
+int efg_fetch_mesh(efg_ctx *ctx, int slot, int64_t *nel_out, int64_t *nnodes_out, int64_t *conn, double *xy)
+{
+    API_BEGIN(ctx)
+    if (slot < 0 || slot > 1 || ctx->mesh[slot].kind == 0) efg_throw(EFG_ERR_STATE, "mesh %d not set", slot);
+    const MeshDev &m = ctx->mesh[slot];
+    if (nel_out) *nel_out = m.nel;
+    if (nnodes_out) *nnodes_out = m.nnodes;
+    if (conn) {
+        const int64_t n = m.nel * m.kind;
+        DevBuf<int64_t> tmp;
+        int64_t *d = conn;
+        if (!is_device_ptr(conn)) { tmp.alloc(ctx->pool, (size_t)n + 1); d = tmp.p; }
+        LAUNCH(ctx, k_gen_index_out, grid_for(n, 256), 256, 0, m.conn.p, n, d);
+        if (d != conn) CUDA_CHECK(cudaMemcpyAsync(conn, d, (size_t)n * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (xy) {
+        CUDA_CHECK(cudaMemcpyAsync(xy, m.xy.p, (size_t)m.nnodes * sizeof(double2), cudaMemcpyDefault, ctx->stream));
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    API_END(ctx)
+}
+
+int efg_fetch_dofnums(efg_ctx *ctx, int space_slot, int64_t *dofnums)
+{
+    API_BEGIN(ctx)
+    if (space_slot < 0 || space_slot > 2 || ctx->space[space_slot].mesh < 0) efg_throw(EFG_ERR_STATE, "space %d not set", space_slot);
+    if (!dofnums) efg_throw(EFG_ERR_INVALID, "null output");
+    const SpaceDev &s = ctx->space[space_slot];
+    const int64_t n = s.nnodes * s.ncomp;
+    DevBuf<int64_t> tmp;
+    int64_t *d = dofnums;
+    if (!is_device_ptr(dofnums)) { tmp.alloc(ctx->pool, (size_t)n + 1); d = tmp.p; }
+    LAUNCH(ctx, k_gen_index_out, grid_for(n, 256), 256, 0, s.dof.p, n, d);
+    if (d != dofnums) CUDA_CHECK(cudaMemcpyAsync(dofnums, d, (size_t)n * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    API_END(ctx)
 }
 
 } // extern "C"

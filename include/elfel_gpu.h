@@ -205,6 +205,27 @@ int efg_l2_error(efg_ctx *ctx, int ncomp, const int *space_slots, const int *com
 /* library / build information, e.g. "elfelgpu 0.1 sm_100a" */
 const char *efg_version(void);
 
+/* ---- the inputs made on the device (no host arrays, nothing crosses PCIe) ------------------------------
+ * efg_gen_mesh: MeshSteward's T3block (orientation :a) / Q4block / T6block(Length, Width, nL, nW) as the examples call them
+ *   (examples/heat/poisson/t3.jl:34, q4.jl:24, examples/elasticity/stretch/t6.jl:34): nodes x-fastest, elements i outer /
+ *   j inner (test/qmesh-conn.dat), T6: corner nodes first, mid-side nodes in first-encounter order; then every coordinate
+ *   is shifted by (xshift, yshift) (the Stokes examples' transform(ir, x -> x - A)).
+ * efg_gen_mesh_corners: T6toT3 (examples/stokes/colliding_flow/ht_p2_p1_gen.jl:42): the pressure mesh.
+ * efg_gen_space / efg_setebc_box / efg_setebc_nodes / efg_number_dofs: FESpace(mesh, fe, ncomp), setebc! on the nodes of
+ *   vselect(geom; box = [x0 x1 y0 y1]) (pass the box already inflated) or on a node list (component 1..ncomp, 0 = all),
+ *   numberdofs!(spaces): free dofs first, spaces in the order given, node-major / component-minor
+ *   (src/FESpaces.jl:141-173,250-259, src/FEFields.jl:124-177).
+ * efg_fetch_mesh / efg_fetch_dofnums: the device-resident inputs copied out in the reference's layout (Int64, 1-based),
+ *   for any mesh / space of the ctx (generated or uploaded); NULL array pointers skip the copy (sizes only). */
+int efg_gen_mesh(efg_ctx *ctx, int mesh_slot, int elemkind, int64_t nL, int64_t nW, double Length, double Width, double xshift, double yshift);
+int efg_gen_mesh_corners(efg_ctx *ctx, int mesh_slot_dst, int mesh_slot_src);
+int efg_gen_space(efg_ctx *ctx, int space_slot, int mesh_slot, int ncomp);
+int efg_setebc_box(efg_ctx *ctx, int space_slot, int comp, double x0, double x1, double y0, double y1);
+int efg_setebc_nodes(efg_ctx *ctx, int space_slot, int comp, int64_t n, const int64_t *node_ids);
+int efg_number_dofs(efg_ctx *ctx, int nspaces, const int *space_slots, int64_t *nfree_out, int64_t *ndofs_out);
+int efg_fetch_mesh(efg_ctx *ctx, int mesh_slot, int64_t *nel_out, int64_t *nnodes_out, int64_t *conn, double *xy);
+int efg_fetch_dofnums(efg_ctx *ctx, int space_slot, int64_t *dofnums);
+
 /* ---- several GPUs behind one handle (SURVEY 8b "efg_create_multi": same calls, the library shards internally; 8e) -------
  * The caller passes the GLOBAL arrays exactly as to the single-GPU functions above (what FEIterator holds:
  * src/FEIterators.jl:54-81); they are borrowed until efgm_assemble has returned (GC.@preserve around the whole
