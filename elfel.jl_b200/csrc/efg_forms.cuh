@@ -8,6 +8,7 @@
 #pragma once
 #include <cstdint>
 #include <utility>
+#include <type_traits>
 
 #define EFG_MAXQ 9
 // Default (non-strict) FP mode only -- the strict mode always performs the reference's operations one by one:
@@ -27,8 +28,10 @@ struct QTab {
 };
 
 // slot 0: T3, 1: Q4, 2: T6 -- tables of the ACTIVE quadrature rule for each element kind
-// (the T3 table at the T6 rule's points is the pressure basis of the Taylor-Hood pair).
-__constant__ QTab c_tab[3];
+// (the T3 table at the T6 rule's points is the pressure basis of the Taylor-Hood pair);
+// slot 3: FEH1_T3_BUBBLE (4 functions), slot 4: FEL2_T3 / FEL2_Q4 (one constant function) -- SURVEY 8f row f5.
+#define EFG_NTAB 5
+__constant__ QTab c_tab[EFG_NTAB];
 __constant__ double c_prm[16];
 
 __host__ __device__ constexpr int kind_slot(int kind) { return kind == 3 ? 0 : (kind == 4 ? 1 : 2); }
@@ -82,12 +85,13 @@ template <bool S> struct SharedDivisor {
 // GK = kind of the geometry carrier (whose nodes X,Y are given), BK = kind whose basis gradients
 // are wanted (BK != GK only for the Reddy/veclap Stokes forms: T3 Jacobian applied to T6 gradients,
 // examples/stokes/colliding_flow/ht_p2_p1.jl:72-76).
-template <bool S, int GK, int BK>
+// BS = c_tab slot of the BK basis functions (default: the H1 element with BK nodes).
+template <bool S, int GK, int BK, int BS = kind_slot(BK)>
 __device__ __forceinline__ void geo_qp(const double (&X)[GK], const double (&Y)[GK], int q,
                                        double (&gx)[BK], double (&gy)[BK], double &JxW)
 {
     const QTab &tg = c_tab[kind_slot(GK)];
-    const QTab &tb = c_tab[kind_slot(BK)];
+    const QTab &tb = c_tab[BS];
     // _jac: src/FElements.jl:148-156 -- J = sum_n x_n (outer) dN_n/dxi, node order, first term assigned.
     // ALWAYS evaluated without FMA contraction: the sum cancels from O(1) to O(h), so any other
     // rounding sequence differs from the reference by O(eps/h) relative -- more than the 1e-12 /
@@ -116,12 +120,15 @@ template <int BK, int NQ> struct Geo {
     double JxW[NQ];
 };
 
-template <bool S, int GK, int BK, int NQ>
+template <bool S, int GK, int BK, int NQ, int BS = kind_slot(BK)>
 __device__ __forceinline__ void geo_compute(const double (&X)[GK], const double (&Y)[GK], Geo<BK, NQ> &G)
 {
 #pragma unroll
-    for (int q = 0; q < NQ; q++) geo_qp<S, GK, BK>(X, Y, q, G.gx[q], G.gy[q], G.JxW[q]);
+    for (int q = 0; q < NQ; q++) geo_qp<S, GK, BK, BS>(X, Y, q, G.gx[q], G.gy[q], G.JxW[q]);
 }
+// table slot of a form's basis functions: F::BSLOT if the form names one, else the H1 element with F::BK nodes
+template <class F, class = void> struct form_bslot { static constexpr int value = kind_slot(F::BK); };
+template <class F> struct form_bslot<F, std::void_t<decltype(F::BSLOT)>> { static constexpr int value = F::BSLOT; };
 
 // Generic element driver: all quadrature points' gradients in registers, then the owned columns one
 // by one.  emit.template col<J>(out) receives column J of the element matrix.
@@ -143,7 +150,7 @@ template <class F, bool S, class Emit>
 __device__ __forceinline__ void element_generic(const double (&X)[F::GK], const double (&Y)[F::GK], uint32_t m, Emit &emit)
 {
     Geo<F::BK, F::NQ> G;
-    geo_compute<S, F::GK, F::BK, F::NQ>(X, Y, G);
+    geo_compute<S, F::GK, F::BK, F::NQ, form_bslot<F>::value>(X, Y, G);
     element_columns<F, S, Emit>(std::make_integer_sequence<int, F::ND>{}, G, m, emit);
 }
 
@@ -151,6 +158,7 @@ __device__ __forceinline__ void element_generic(const double (&X)[F::GK], const 
 struct DofSrc {
     const int32_t *conn0, *conn1;          // 0-based node ids of mesh 0 / mesh 1
     const int32_t *dof0, *dof1, *dof2;     // 0-based dof numbers (ncomp x nnodes), -1 = dof number 0
+    const int32_t *cdof0, *cdof1, *cdof2;  // 0-based dof numbers of the spaces' cell fields (ncomp x nel), null = no cell field
 };
 
 // A form provides:
@@ -628,59 +636,83 @@ template <bool VECLAP_ALT> struct Stokes2Form {
 
 // K4 Reddy: examples/stokes/colliding_flow/ht_p2_p1.jl:77-101 (Jacobian of the PRESSURE element);
 // veclap: examples/stokes/colliding_flow/ht_p2_p1_veclap.jl:75-94 (no ux-uy coupling blocks).
-template <bool VECLAP> struct Stokes3Form {
+// The same loop on the other velocity / pressure pairs of the examples, PAIR =
+//   EFG_PAIR_T6_T3 (6)   FEH1_T6 / FEH1_T3 on the T6toT3 mesh (slot 1), Jacobian of the pressure element
+//   EFG_PAIR_T3B_T3 (7)  FEH1_T3_BUBBLE / FEH1_T3, one T3 mesh: examples/stokes/colliding_flow/p1b_p1.jl:53-109,
+//                        test/test_stokes.jl:190-247; the 4th velocity dof sits on the cell (src/FElements.jl:339)
+//   EFG_PAIR_Q4_L2 (14)  FEH1_Q4 / FEL2_Q4, one Q4 mesh: examples/stokes/colliding_flow/q1_q0.jl:52-108 -- Jacobian of
+//                        the velocity element (:70), the single pressure dof sits on the cell (src/FElements.jl:410)
+//   EFG_PAIR_T3_L2 (13)  FEH1_T3 / FEL2_T3 (src/FElements.jl:422-448), same structure on triangles
+// Local dofs: [ux: NV][uy: NV][p: NP]; eldofs() of a space = its vertex dofs, then its cell dof (src/FEIterators.jl:185-194).
+#define EFG_PAIR_T6_T3 6
+#define EFG_PAIR_T3B_T3 7
+#define EFG_PAIR_T3_L2 13
+#define EFG_PAIR_Q4_L2 14
+template <int PAIR> struct ReddyPair;
+template <> struct ReddyPair<EFG_PAIR_T6_T3>  { static constexpr int NV = 6, NP = 3, VN = 6, PN = 3, VC = 0, PC = 0, GK = 3, GMESH = 1, PMESH = 1, VS = 2, PS = 0; };
+template <> struct ReddyPair<EFG_PAIR_T3B_T3> { static constexpr int NV = 4, NP = 3, VN = 3, PN = 3, VC = 1, PC = 0, GK = 3, GMESH = 0, PMESH = 0, VS = 3, PS = 0; };
+template <> struct ReddyPair<EFG_PAIR_T3_L2>  { static constexpr int NV = 3, NP = 1, VN = 3, PN = 0, VC = 0, PC = 1, GK = 3, GMESH = 0, PMESH = 0, VS = 0, PS = 4; };
+template <> struct ReddyPair<EFG_PAIR_Q4_L2>  { static constexpr int NV = 4, NP = 1, VN = 4, PN = 0, VC = 0, PC = 1, GK = 4, GMESH = 0, PMESH = 0, VS = 1, PS = 4; };
+
+template <bool VECLAP, int PAIR = EFG_PAIR_T6_T3, int NQ_ = 3> struct Stokes3Form {
+    using P = ReddyPair<PAIR>;
     static constexpr bool SYM = false;
-    static constexpr int VK = 6, PK = 3, NQ = 3;
-    static constexpr int ND = 15, NT = VECLAP ? 144 : 216, GK = 3, BK = 6, GMESH = 1, NSPACES = 3;
+    static constexpr int NV = P::NV, NP = P::NP, NQ = NQ_;
+    // BK = number of velocity basis functions (sizes the gradient arrays), BSLOT = their table in c_tab
+    static constexpr int ND = 2 * NV + NP, NT = (VECLAP ? 2 : 4) * NV * NV + 4 * NV * NP, GK = P::GK, BK = NV, BSLOT = P::VS, GMESH = P::GMESH, NSPACES = 3;
     static constexpr bool SPLIT = false;
     template <bool S, class Emit>
     __device__ __forceinline__ static void element(const double (&X)[GK], const double (&Y)[GK], uint32_t m, Emit &emit) {
-        element_generic<Stokes3Form<VECLAP>, S, Emit>(X, Y, m, emit);
+        element_generic<Stokes3Form<VECLAP, PAIR, NQ_>, S, Emit>(X, Y, m, emit);
     }
     __host__ __device__ static constexpr bool mask(int i, int j) {
-        if (i >= 12 && j >= 12) return false;
-        if (VECLAP && ((i < 6 && j >= 6 && j < 12) || (j < 6 && i >= 6 && i < 12))) return false;
+        if (i >= 2 * NV && j >= 2 * NV) return false;
+        if (VECLAP && ((i < NV && j >= NV && j < 2 * NV) || (j < NV && i >= NV && i < 2 * NV))) return false;
         return true;
     }
     __host__ __device__ static constexpr int kidx(int i, int j) {
+        constexpr int VV = NV * NV, VP = NV * NP, U2 = 2 * NV;
         if (!VECLAP) {
-            if (i < 6 && j < 6) return j * 6 + i;                              // kuxux
-            if (i < 6 && j < 12) return 36 + (j - 6) * 6 + i;                  // kuxuy
-            if (i < 12 && j < 6) return 72 + j * 6 + (i - 6);                  // transpose(kuxuy)
-            if (i < 12 && j < 12) return 108 + (j - 6) * 6 + (i - 6);          // kuyuy
-            if (i < 6) return 144 + (j - 12) * 6 + i;                          // kuxp
-            if (j < 6) return 162 + j * 3 + (i - 12);                          // transpose(kuxp)
-            if (i < 12) return 180 + (j - 12) * 6 + (i - 6);                   // kuyp
-            return 198 + (j - 6) * 3 + (i - 12);                               // transpose(kuyp)
+            if (i < NV && j < NV) return j * NV + i;                                   // kuxux
+            if (i < NV && j < U2) return VV + (j - NV) * NV + i;                       // kuxuy
+            if (i < U2 && j < NV) return 2 * VV + j * NV + (i - NV);                   // transpose(kuxuy)
+            if (i < U2 && j < U2) return 3 * VV + (j - NV) * NV + (i - NV);            // kuyuy
+            if (i < NV) return 4 * VV + (j - U2) * NV + i;                             // kuxp
+            if (j < NV) return 4 * VV + VP + j * NP + (i - U2);                        // transpose(kuxp)
+            if (i < U2) return 4 * VV + 2 * VP + (j - U2) * NV + (i - NV);             // kuyp
+            return 4 * VV + 3 * VP + (j - NV) * NP + (i - U2);                         // transpose(kuyp)
         } else {
-            if (i < 6 && j < 6) return j * 6 + i;                              // kuxux
-            if (i >= 6 && i < 12 && j >= 6 && j < 12) return 36 + (j - 6) * 6 + (i - 6); // kuyuy
-            if (i < 6) return 72 + (j - 12) * 6 + i;                           // kuxp
-            if (j < 6) return 90 + j * 3 + (i - 12);                           // transpose(kuxp)
-            if (i < 12) return 108 + (j - 12) * 6 + (i - 6);                   // kuyp
-            return 126 + (j - 6) * 3 + (i - 12);                               // transpose(kuyp)
+            if (i < NV && j < NV) return j * NV + i;                                   // kuxux
+            if (i >= NV && i < U2 && j >= NV && j < U2) return VV + (j - NV) * NV + (i - NV); // kuyuy
+            if (i < NV) return 2 * VV + (j - U2) * NV + i;                             // kuxp
+            if (j < NV) return 2 * VV + VP + j * NP + (i - U2);                        // transpose(kuxp)
+            if (i < U2) return 2 * VV + 2 * VP + (j - U2) * NV + (i - NV);             // kuyp
+            return 2 * VV + 3 * VP + (j - NV) * NP + (i - U2);                         // transpose(kuyp)
         }
     }
     __device__ static void edofs(const DofSrc &s, int64_t e, int32_t (&d)[ND]) {
 #pragma unroll
-        for (int a = 0; a < 6; a++) {
-            const int64_t n = s.conn0[e * 6 + a];
-            d[a] = s.dof0[n]; d[6 + a] = s.dof1[n];
+        for (int a = 0; a < P::VN; a++) {
+            const int64_t n = s.conn0[e * P::VN + a];
+            d[a] = s.dof0[n]; d[NV + a] = s.dof1[n];
         }
+        if constexpr (P::VC) { d[P::VN] = s.cdof0[e]; d[NV + P::VN] = s.cdof1[e]; }
+        const int32_t *pconn = P::PMESH ? s.conn1 : s.conn0;
 #pragma unroll
-        for (int m = 0; m < 3; m++) d[12 + m] = s.dof2[s.conn1[e * 3 + m]];
+        for (int m = 0; m < P::PN; m++) d[2 * NV + m] = s.dof2[pconn[e * P::PN + m]];
+        if constexpr (P::PC) d[2 * NV + P::PN] = s.cdof2[e];
     }
-    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<6, 3> &G, double (&out)[ND]) {
-        const QTab &tp = c_tab[kind_slot(3)];
+    template <bool S, int J> __device__ __forceinline__ static void column(const Geo<NV, NQ> &G, double (&out)[ND]) {
+        const QTab &tp = c_tab[P::PS];
         const double mu = c_prm[0];
 #pragma unroll
-        for (int i = 0; i < 15; i++) out[i] = 0.0;
-        if constexpr (J < 6) {          // column of ux dof J
+        for (int i = 0; i < ND; i++) out[i] = 0.0;
+        if constexpr (J < NV) {          // column of ux dof J
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
+            for (int i = 0; i < NV; i++) {
                 double a = 0.0, b = 0.0;
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
+                for (int q = 0; q < NQ; q++) {
                     const double mJ = fmul<S>(mu, G.JxW[q]);
                     double t;
                     if constexpr (!VECLAP)   // (mu*JxW) * (2*gx_i*gx_j + gy_i*gy_j)
@@ -693,25 +725,25 @@ template <bool VECLAP> struct Stokes3Form {
                         b = q == 0 ? u : fadd<S>(b, u);
                     }
                 }
-                out[i] = a; out[6 + i] = b;
+                out[i] = a; out[NV + i] = b;
             }
 #pragma unroll
-            for (int m = 0; m < 3; m++) {  // transpose(kuxp): kuxp[J, m] = (-JxW) * (gx_J * Np_m)
+            for (int m = 0; m < NP; m++) {  // transpose(kuxp): kuxp[J, m] = (-JxW) * (gx_J * Np_m)
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
+                for (int q = 0; q < NQ; q++) {
                     const double t = fmul<S>(-G.JxW[q], fmul<S>(G.gx[q][J], tp.N[q][m]));
                     acc = q == 0 ? t : fadd<S>(acc, t);
                 }
-                out[12 + m] = acc;
+                out[2 * NV + m] = acc;
             }
-        } else if constexpr (J < 12) {  // column of uy dof b
-            constexpr int b_ = J - 6;
+        } else if constexpr (J < 2 * NV) {  // column of uy dof b
+            constexpr int b_ = J - NV;
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
+            for (int i = 0; i < NV; i++) {
                 double a = 0.0, c = 0.0;
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
+                for (int q = 0; q < NQ; q++) {
                     const double mJ = fmul<S>(mu, G.JxW[q]);
                     if constexpr (!VECLAP) { // kuxuy[i, b] = (mu*JxW) * (gx_i * gy_b)
                         const double u = fmul<S>(mJ, fmul<S>(G.gx[q][i], G.gy[q][b_]));
@@ -724,31 +756,31 @@ template <bool VECLAP> struct Stokes3Form {
                         t = fmul<S>(mJ, fadd<S>(fmul<S>(G.gx[q][i], G.gx[q][b_]), fmul<S>(G.gy[q][i], G.gy[q][b_])));
                     c = q == 0 ? t : fadd<S>(c, t);
                 }
-                out[i] = a; out[6 + i] = c;
+                out[i] = a; out[NV + i] = c;
             }
 #pragma unroll
-            for (int m = 0; m < 3; m++) {  // transpose(kuyp): kuyp[b, m] = (-JxW) * (gy_b * Np_m)
+            for (int m = 0; m < NP; m++) {  // transpose(kuyp): kuyp[b, m] = (-JxW) * (gy_b * Np_m)
                 double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
+                for (int q = 0; q < NQ; q++) {
                     const double t = fmul<S>(-G.JxW[q], fmul<S>(G.gy[q][b_], tp.N[q][m]));
                     acc = q == 0 ? t : fadd<S>(acc, t);
                 }
-                out[12 + m] = acc;
+                out[2 * NV + m] = acc;
             }
         } else {                        // column of p dof m: kuxp[i, m], kuyp[i, m]
-            constexpr int m = J - 12;
+            constexpr int m = J - 2 * NV;
 #pragma unroll
-            for (int i = 0; i < 6; i++) {
+            for (int i = 0; i < NV; i++) {
                 double a = 0.0, c = 0.0;
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
+                for (int q = 0; q < NQ; q++) {
                     const double t = fmul<S>(-G.JxW[q], fmul<S>(G.gx[q][i], tp.N[q][m]));
                     const double u = fmul<S>(-G.JxW[q], fmul<S>(G.gy[q][i], tp.N[q][m]));
                     a = q == 0 ? t : fadd<S>(a, t);
                     c = q == 0 ? u : fadd<S>(c, u);
                 }
-                out[i] = a; out[6 + i] = c;
+                out[i] = a; out[NV + i] = c;
             }
         }
     }

@@ -35,6 +35,19 @@
 #define EFO_T3 3
 #define EFO_Q4 4
 #define EFO_T6 6
+/* finite elements with a dof on the cell itself (FEData ndofperfeat = [1,0,1,0] / [0,0,1,0]) */
+#define EFO_T3B 7   /* FEH1_T3_BUBBLE: src/FElements.jl:324-355 -- 3 vertex functions + the cubic bubble of the cell      */
+#define EFO_L2 1    /* FEL2_T3 / FEL2_Q4: src/FElements.jl:394-445 -- one constant function, dof on the cell; the geometry */
+                    /* carrier is the H1 element of the mesh (_geometrycarrier, :403,:432)                                */
+
+/* Spaces whose element is not the plain H1 element of their mesh (row f5).  NULL = the classic case.
+ *   vfe : element of the velocity space(s) (spaces 0, 1 of the Reddy forms): 0 = H1 element of mesh 0, or EFO_T3B
+ *   pfe : element of the pressure space (space 2):                           0 = H1 element of mesh 1, or EFO_L2
+ *   cdof0..2 : FEField.dofnums of the dim-2 (cell) field of spaces 0..2, ncomp x nel, NULL = the space has none */
+typedef struct {
+    int vfe, pfe;
+    const int64_t *cdof0, *cdof1, *cdof2;
+} efo_ext;
 
 enum {
     EFO_FORM_HEAT = 1,            /* examples/heat/poisson/t3.jl:53-58, q4.jl:43-48 */
@@ -70,7 +83,7 @@ static int gauss1(int order, double *pc, double *w) /* src/RefShapes.jl:91-106 *
 
 int efo_quadrature(int elemkind, int rule, double *pc, double *w)
 {
-    if (elemkind == EFO_T3 || elemkind == EFO_T6) {
+    if (elemkind == EFO_T3 || elemkind == EFO_T6 || elemkind == EFO_T3B) {
         if (rule == 1) { /* src/RefShapes.jl:114-116 */
             pc[0] = 1.0 / 3.; pc[1] = 1.0 / 3.;
             w[0] = 1.0 / 2.0;
@@ -104,7 +117,11 @@ int efo_quadrature(int elemkind, int rule, double *pc, double *w)
  * T3: src/FElements.jl:239-246; T6: :264-288; Q4: :306-320.  g is nbf x 2 row-major.
  * Julia evaluates `-3+4*r+4*s` as (-3 + 4r) + 4s, `4-8*r-4*s` as (4 - 8r) - 4s.
  * ------------------------------------------------------------------------------------------ */
-int efo_nbf(int elemkind) { return elemkind; }
+int efo_nbf(int elemkind) { return elemkind == EFO_T3B ? 4 : elemkind; }
+/* dofs of an element: on its nodes (dim 0 field) / on the cell (dim 2 field); _storedofs! visits dim 0 first
+ * (src/FEIterators.jl:185-194), _number_edofs numbers the basis functions in the same order (src/FESpaces.jl:87-105) */
+static int fe_nodedofs(int fe) { return fe == EFO_T3B ? 3 : (fe == EFO_L2 ? 0 : fe); }
+static int fe_celldofs(int fe) { return (fe == EFO_T3B || fe == EFO_L2) ? 1 : 0; }
 
 void efo_bfun(int elemkind, double r, double s, double *N)
 {
@@ -123,6 +140,11 @@ void efo_bfun(int elemkind, double r, double s, double *N)
         N[1] = 0.25 * (1. + r) * (1. - s);
         N[2] = 0.25 * (1. + r) * (1. + s);
         N[3] = 0.25 * (1. - r) * (1. + s);
+    } else if (elemkind == EFO_T3B) {   /* src/FElements.jl:341-347: ((1 - xi - eta) * xi) * eta */
+        N[0] = (1 - r - s); N[1] = r; N[2] = s;
+        N[3] = (1 - r - s) * r * s;
+    } else if (elemkind == EFO_L2) {    /* src/FElements.jl:412-414, 441-443 */
+        N[0] = 1.0;
     }
 }
 
@@ -144,6 +166,13 @@ void efo_bfungradpar(int elemkind, double r, double s, double *g)
         g[2] = (1. - s) * 0.25;  g[3] = -(1. + r) * 0.25;
         g[4] = (1. + s) * 0.25;  g[5] = (1. + r) * 0.25;
         g[6] = -(1. + s) * 0.25; g[7] = (1. - r) * 0.25;
+    } else if (elemkind == EFO_T3B) {   /* src/FElements.jl:349-356 */
+        g[0] = -1.; g[1] = -1.;
+        g[2] = +1.; g[3] = 0.;
+        g[4] = 0.;  g[5] = +1.;
+        g[6] = (-r * s + (1 - r - s) * s); g[7] = (-r * s + (1 - r - s) * r);
+    } else if (elemkind == EFO_L2) {    /* src/FElements.jl:416-419, 445-448 */
+        g[0] = 0.0; g[1] = 0.0;
     }
 }
 
@@ -159,11 +188,12 @@ typedef struct {
     double gp[MAXQP][MAXBF][2];    /* scalar parametric gradients  */
 } qptab;
 
-static int qptab_init(qptab *t, int elemkind, int rule)
+/* shape: the element kind whose reference shape supplies the rule (an L2 element lives on its mesh's T3 / Q4 cell) */
+static int qptab_init_shape(qptab *t, int elemkind, int shape, int rule)
 {
     double pc[2 * MAXQP];
     t->kind = elemkind; t->nbf = efo_nbf(elemkind);
-    t->npts = efo_quadrature(elemkind, rule, pc, t->w);
+    t->npts = efo_quadrature(shape, rule, pc, t->w);
     if (t->npts < 0) return -1;
     for (int q = 0; q < t->npts; q++) {
         efo_bfun(elemkind, pc[2 * q], pc[2 * q + 1], t->N[q]);
@@ -171,6 +201,7 @@ static int qptab_init(qptab *t, int elemkind, int rule)
     }
     return 0;
 }
+static int qptab_init(qptab *t, int elemkind, int rule) { return qptab_init_shape(t, elemkind, elemkind, rule); }
 
 /* _jac: src/FElements.jl:148-156.  J = sum_n x_n (outer) gradNpar_n, summed in node order,
  * first term assigned.  J[i][k] = sum_n x_n[i] * g_n[k].
@@ -258,6 +289,14 @@ static void eldofs(const int64_t *nodes, int nen, const int64_t *dofnums, int nc
             d[p++] = dofnums[(nodes[k] - 1) * ncomp + i];
 }
 
+/* the same for an element with a cell field: the dofs of the dim-0 entities first, then those of the cell e (0-based) */
+static void eldofs_fe(int fe, const int64_t *nodes, const int64_t *dofnums, const int64_t *celldofnums, int64_t e, int64_t *d)
+{
+    const int nn = fe_nodedofs(fe);
+    eldofs(nodes, nn, dofnums, 1, d);
+    if (fe_celldofs(fe)) d[nn] = celldofnums[e];
+}
+
 /* B(g,k): examples/elasticity/stretch/t6.jl:42 */
 static void Bmat(const double g[2], int k, double b[3])
 {
@@ -277,7 +316,7 @@ static double dot2(const double a[2], const double b[2]) { return a[0] * b[0] + 
 /* Number of COO triplets each element appends for a form. */
 int64_t efo_triplets_per_element(int form, int vkind, int pkind)
 {
-    int64_t nu = vkind, np = pkind;
+    int64_t nu = efo_nbf(vkind), np = efo_nbf(pkind);   /* (element kinds incl. EFO_T3B / EFO_L2) */
     switch (form) {
     case EFO_FORM_HEAT: return nu * nu;
     case EFO_FORM_ELASTICITY: return 4 * nu * nu;
@@ -308,14 +347,17 @@ static int64_t element_loop(coo *ap, int form, int quad, int64_t e0, int64_t e1,
                             const int64_t *vconn, int vkind, const double *vxy,
                             const int64_t *pconn, int pkind, const double *pxy,
                             const int64_t *dof0, const int64_t *dof1, const int64_t *dof2,
-                            const double *params)
+                            const double *params, const efo_ext *x)
 {
 #define a (*ap)
     const int values = (a.mode == 0 || a.mode == 3);   /* pattern passes skip the quadrature loop (ke stays 0) */
+    /* elements of the velocity / pressure spaces: the H1 element of the mesh unless row f5's ext block says otherwise */
+    const int vfe = (x && x->vfe) ? x->vfe : vkind, pfe = (x && x->pfe) ? x->pfe : pkind;
+    if ((vfe != vkind || pfe != pkind) && form != EFO_FORM_STOKES_REDDY && form != EFO_FORM_STOKES_VECLAP) return -2;
     qptab vq, pq;
-    if (qptab_init(&vq, vkind, quad) < 0) return -1;
-    if (pconn && qptab_init(&pq, pkind, quad) < 0) return -1;
-    const int nu = vkind;
+    if (qptab_init_shape(&vq, vfe, vkind, quad) < 0) return -1;
+    if (pconn && qptab_init_shape(&pq, pfe, pkind, quad) < 0) return -1;
+    const int nu = vq.nbf;
     double J[2][2];
     double g[MAXBF][2];
 
@@ -416,22 +458,28 @@ static int64_t element_loop(coo *ap, int form, int quad, int64_t e0, int64_t e1,
 
     if (form == EFO_FORM_STOKES_REDDY || form == EFO_FORM_STOKES_VECLAP) {
         /* Reddy: examples/stokes/colliding_flow/ht_p2_p1.jl:55-113, test/test_stokes.jl:374-422
-         * veclap: examples/stokes/colliding_flow/ht_p2_p1_veclap.jl:55-106 */
-        const int np = pkind;
+         * veclap: examples/stokes/colliding_flow/ht_p2_p1_veclap.jl:55-106
+         * row f5, the same loop on other element pairs (one mesh: pconn == vconn):
+         *   FEH1_T3_BUBBLE / FEH1_T3   examples/stokes/colliding_flow/p1b_p1.jl:53-109, test/test_stokes.jl:190-247
+         *   FEH1_Q4 / FEL2_Q4           examples/stokes/colliding_flow/q1_q0.jl:52-108 (Jacobian of the VELOCITY element :70) */
+        const int np = pq.nbf;
+        if (!pconn) return -2;
+        if (pfe == EFO_L2 && vfe != vkind) return -2;     /* (no example pairs a bubble velocity with an L2 pressure) */
         const double mu = params[0];
         int64_t dx[MAXBF], dy[MAXBF], dp[MAXBF];
         double kxx[MAXBF * MAXBF], kyy[MAXBF * MAXBF], kxy[MAXBF * MAXBF], kxp[MAXBF * MAXBF], kyp[MAXBF * MAXBF];
         double gp_[MAXBF][2];
         for (int64_t ee = e0; ee < e1; ee++) {
             const int64_t e = elist ? elist[ee] : ee;
-            const int64_t *unodes = vconn + e * nu, *pnodes = pconn + e * np;
-            eldofs(unodes, nu, dof0, 1, dx);
-            eldofs(unodes, nu, dof1, 1, dy);
-            eldofs(pnodes, np, dof2, 1, dp);
+            const int64_t *unodes = vconn + e * vkind, *pnodes = pconn + e * pkind;
+            eldofs_fe(vfe, unodes, dof0, x ? x->cdof0 : NULL, e, dx);
+            eldofs_fe(vfe, unodes, dof1, x ? x->cdof1 : NULL, e, dy);
+            eldofs_fe(pfe, pnodes, dof2, x ? x->cdof2 : NULL, e, dp);
             memset(kxx, 0, sizeof kxx); memset(kyy, 0, sizeof kyy); memset(kxy, 0, sizeof kxy);
             memset(kxp, 0, sizeof kxp); memset(kyp, 0, sizeof kyp);
             for (int q = 0; values && q < vq.npts; q++) {
-                double Jd = jacjac(pxy, pnodes, np, pq.gp[q], J); /* PRESSURE element Jacobian (:72) */
+                double Jd = pfe == EFO_L2 ? jacjac(vxy, unodes, vkind, vq.gp[q], J)    /* q1_q0.jl:70: jacjac(uxel, uxqp) */
+                                          : jacjac(pxy, pnodes, pkind, pq.gp[q], J);   /* PRESSURE element Jacobian (:72) */
                 double JxW = Jd * pq.w[q];
                 bfungrad(np, pq.gp[q], J, gp_); /* gradNp: computed, unused (:74) */
                 bfungrad(nu, vq.gp[q], J, g);   /* gradNux == gradNuy numerically */
@@ -486,12 +534,12 @@ int64_t efo_assemble_coo(int form, int quad, int64_t e0, int64_t e1,
                          const int64_t *pconn, int pkind, const double *pxy,
                          const int64_t *dof0, const int64_t *dof1, const int64_t *dof2,
                          const double *params,
-                         int64_t *row, int64_t *col, double *val)
+                         int64_t *row, int64_t *col, double *val, const efo_ext *ext)
 {
     coo a;
     memset(&a, 0, sizeof a);
     a.row = row; a.col = col; a.val = val;
-    return element_loop(&a, form, quad, e0, e1, NULL, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, params);
+    return element_loop(&a, form, quad, e0, e1, NULL, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, params, ext);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -515,7 +563,7 @@ int64_t efo_direct_pattern(int form, int quad, int64_t nel, const int64_t *elist
                            const int64_t *pconn, int pkind, const double *pxy,
                            const int64_t *dof0, const int64_t *dof1, const int64_t *dof2,
                            int64_t nrow, int64_t ncol, int64_t c0, int64_t c1,
-                           int64_t *colptr, int64_t *rowval)
+                           int64_t *colptr, int64_t *rowval, const efo_ext *ext)
 {
     const int64_t nc = c1 - c0 + 1;
     const double dummy[9] = {0};
@@ -526,7 +574,7 @@ int64_t efo_direct_pattern(int form, int quad, int64_t nel, const int64_t *elist
     if (!cnt) return -3;
     a.mode = 1; a.cnt = cnt;
     const int64_t n_it = elist ? nsel : nel;
-    if (element_loop(&a, form, quad, 0, n_it, elist, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, dummy) < 0 || a.bad) {
+    if (element_loop(&a, form, quad, 0, n_it, elist, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, dummy, ext) < 0 || a.bad) {
         free(cnt);
         return -1;
     }
@@ -539,7 +587,7 @@ int64_t efo_direct_pattern(int form, int quad, int64_t nel, const int64_t *elist
     if (!start || !cand) { free(cnt); free(start); free(cand); return -3; }
     memcpy(start, cnt, ((size_t)nc + 1) * sizeof(int64_t));
     a.mode = 2; a.cand = cand; a.n = 0;
-    element_loop(&a, form, quad, 0, n_it, elist, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, dummy);
+    element_loop(&a, form, quad, 0, n_it, elist, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, dummy, ext);
     int64_t nnz = 0;
     colptr[0] = 1;
     for (int64_t j = 0; j < nc; j++) {
@@ -559,7 +607,7 @@ int64_t efo_direct_values(int form, int quad, int64_t nel, const int64_t *elist,
                           const int64_t *pconn, int pkind, const double *pxy,
                           const int64_t *dof0, const int64_t *dof1, const int64_t *dof2,
                           const double *params, int64_t nrow, int64_t ncol, int64_t c0, int64_t c1,
-                          const int64_t *colptr, const int64_t *rowval, double *nzval)
+                          const int64_t *colptr, const int64_t *rowval, double *nzval, const efo_ext *ext)
 {
     coo a;
     memset(&a, 0, sizeof a);
@@ -568,7 +616,7 @@ int64_t efo_direct_values(int form, int quad, int64_t nel, const int64_t *elist,
     const int64_t nnz = colptr[c1 - c0 + 1] - 1;
     for (int64_t k = 0; k < nnz; k++) nzval[k] = -0.0;
     const int64_t n_it = elist ? nsel : nel;
-    const int64_t r = element_loop(&a, form, quad, 0, n_it, elist, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, params);
+    const int64_t r = element_loop(&a, form, quad, 0, n_it, elist, vconn, vkind, vxy, pconn, pkind, pxy, dof0, dof1, dof2, params, ext);
     if (r < 0) return r;
     return a.bad ? -1 : nnz;
 }
@@ -751,6 +799,40 @@ double efo_l2_error(int quad, int64_t nel, const int64_t *conn, int kind, const 
             double d0 = a0 - t[0];
             if (ncomp > 1) { double d1 = a1 - t[1]; E = E + JxW * (d0 * d0 + d1 * d1); }
             else E = E + JxW * (d0 * d0);
+        }
+    }
+    return sqrt(E);
+}
+
+/* The same integrator for scalar spaces whose element has a cell dof (row f5): examples/stokes/colliding_flow/
+ * p1b_p1.jl:117-172 -- evaluate_velocity_error sums all FOUR basis functions of FEH1_T3_BUBBLE (eldofvals: vertex values
+ * then the bubble's, src/FEIterators.jl:201-208); jacjac / location of such an element use the first `kind` (vertex)
+ * gradients / functions (src/FElements.jl:148-156 loops over the nodes).  fe = EFO_T3B, or a plain H1 kind. */
+double efo_l2_error_fe(int quad, int64_t nel, const int64_t *conn, int kind, const double *xy, int fe, int ncomp,
+                       const int64_t *dof0, const int64_t *cdof0, const int64_t *dof1, const int64_t *cdof1,
+                       const double *U, const double *truth)
+{
+    qptab vq;
+    if (qptab_init_shape(&vq, fe, kind, quad) < 0) return -1.0;
+    double J[2][2];
+    double E = 0.0;
+    int64_t d0[MAXBF], d1[MAXBF];
+    for (int64_t e = 0; e < nel; e++) {
+        const int64_t *nodes = conn + e * kind;
+        eldofs_fe(fe, nodes, dof0, cdof0, e, d0);
+        if (ncomp > 1) eldofs_fe(fe, nodes, dof1, cdof1, e, d1);
+        for (int q = 0; q < vq.npts; q++) {
+            double Jd = jacjac(xy, nodes, kind, vq.gp[q], J);
+            double JxW = Jd * vq.w[q];
+            double a0 = 0.0, a1 = 0.0;
+            for (int j = 0; j < vq.nbf; j++) {
+                a0 = a0 + U[d0[j] - 1] * vq.N[q][j];
+                if (ncomp > 1) a1 = a1 + U[d1[j] - 1] * vq.N[q][j];
+            }
+            const double *t = truth + (e * vq.npts + q) * ncomp;
+            double e0 = a0 - t[0];
+            if (ncomp > 1) { double e1 = a1 - t[1]; E = E + JxW * (e0 * e0 + e1 * e1); }
+            else E = E + JxW * (e0 * e0);
         }
     }
     return sqrt(E);
