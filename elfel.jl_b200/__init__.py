@@ -13,7 +13,7 @@ loudly if it is missing.
 """
 from .meshes import (Mesh, T3, Q4, T6, T3block, Q4block, T6block, T6block_fast, T3toT6, T6toT3,
                      transform, boundary_nodes, vselect, jitter)
-from .fespaces import (FE, FEH1_T3, FEH1_T6, FEH1_Q4, FEField, FESpace, edofbfnum, edofcompnt,
+from .fespaces import (FE, FEH1_T3, FEH1_T6, FEH1_Q4, FEH1_T3_BUBBLE, FEL2_T3, FEL2_Q4, bfun, edofmdim, FEField, FESpace, edofbfnum, edofcompnt,
                        ndofsperel, setebc, numberfreedofs, numberdatadofs, numberdofs, nunknowns,
                        ndofs, highestfreedofnum, highestdatadofnum, gathersysvec, scattersysvec)
 from . import _lib
@@ -21,5 +21,5 @@ from ._lib import build, EfgError, ArgumentError
 from .assemblers import (FEIterator, QPIterator, HeatForm, HeatLoadForm, SysvecAssemblerGPU, mul, block, evaluate_error, ElasticityForm, StokesGenForm, StokesReddyForm,
                          StokesVeclapAltForm, StokesVeclapForm, SparseMatrixCSC, Engine, MultiEngine, SysmatAssemblerGPU,
                          start, assemble, finish)
-from .problems import (Problem, heat_problem, elasticity_problem, stokes_problem, plane_stress_D, load_problem,
+from .problems import (Problem, heat_problem, elasticity_problem, stokes_problem, stokes_f5_problem, plane_stress_D, load_problem,
                        oracle_args)

@@ -28,13 +28,14 @@ PATH_AUTO, PATH_TWOPASS, PATH_TILED = 0, 1, 2
 (STAT_SYMBOLIC_MS, STAT_NUMERIC_MS, STAT_KERNEL_LAUNCHES, STAT_NUMERIC_LAUNCHES, STAT_DEVICE_BYTES,
  STAT_NTILES, STAT_TILE_ELEMS, STAT_NUMERIC_BYTES, STAT_PATH, STAT_VEC_MS, STAT_SPMV_MS) = range(1, 12)
 VFORM_HEAT_LOAD = 1
+FE_H1, FE_L2, FE_T3_BUBBLE = 0, 1, 7     # efg_set_space_fe
 
 EXPORTS = ["efg_create", "efg_destroy", "efg_last_error", "efg_set_option", "efg_get_stat", "efg_get_stream",
            "efg_synchronize", "efg_set_mesh", "efg_set_space", "efg_start", "efg_set_column_range",
            "efg_set_column_ranges", "efg_pattern", "efg_fetch_pattern_async", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version",
            "efg_vec_assemble", "efg_fetch_vec", "efg_device_vec", "efg_spmv", "efg_block_nnz", "efg_fetch_block",
            "efg_qp_locations", "efg_l2_error",
-           "efg_gen_mesh", "efg_gen_mesh_corners", "efg_gen_space", "efg_setebc_box", "efg_setebc_nodes", "efg_number_dofs",
+           "efg_set_space_fe", "efg_gen_mesh", "efg_gen_mesh_corners", "efg_gen_space", "efg_setebc_box", "efg_setebc_nodes", "efg_number_dofs",
            "efg_fetch_mesh", "efg_fetch_dofnums",
            "efgm_create", "efgm_destroy", "efgm_last_error", "efgm_device_count", "efgm_set_option", "efgm_set_mesh", "efgm_set_space",
            "efgm_start", "efgm_assemble", "efgm_numeric", "efgm_fetch_csc", "efgm_get_stat", "efgm_device_ctx"]
@@ -90,6 +91,7 @@ def load():
     L.efg_synchronize.argtypes = [vp]
     L.efg_set_mesh.argtypes = [vp, ci, ci, i64, i64, vp, vp]
     L.efg_set_space.argtypes = [vp, ci, ci, ci, i64, vp]
+    L.efg_set_space_fe.argtypes = [vp, ci, ci, ci, ci, i64, vp, i64, vp]
     L.efg_start.argtypes = [vp, i64, i64]
     L.efg_set_column_range.argtypes = [vp, i64, i64]
     if hasattr(L, "efg_set_column_ranges"):

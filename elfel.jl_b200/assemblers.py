@@ -44,7 +44,8 @@ class FEIterator:
         self.fesp = fesp
         self._bir = fesp.mesh.conn        # element -> nodes, (nel, nen) int64 1-based
         self._geom = fesp.mesh.xy         # (nnodes, 2)
-        self._fld0 = fesp.field
+        self._fld0 = fesp.field           # vertex dofs (None for an L2 space)
+        self._fld2 = fesp.cellfield       # cell dofs (FEH1_T3_BUBBLE, FEL2_*), else None
 
     def __len__(self):
         return self._bir.shape[0]
@@ -211,10 +212,16 @@ class Engine:
         nel, nnodes = int(conn.shape[0]), int(xy.shape[0])
         self._ck(self.L.efg_set_mesh(self.h, slot, kind, nel, nnodes, _ptr(conn), _ptr(xy)))
 
-    def set_space(self, slot, mesh_slot, dofnums):
-        """dofnums: (nnodes, ncomp) int64 1-based."""
-        nnodes, ncomp = int(dofnums.shape[0]), int(dofnums.shape[1])
-        self._ck(self.L.efg_set_space(self.h, slot, mesh_slot, ncomp, nnodes, _ptr(dofnums)))
+    def set_space(self, slot, mesh_slot, dofnums, fe=_lib.FE_H1, cell_dofnums=None):
+        """dofnums: (nnodes, ncomp) int64 1-based (None for an L2 space); fe / cell_dofnums (nel, ncomp): spaces whose
+        element carries a dof on the cell (efg_set_space_fe)."""
+        if fe == _lib.FE_H1:
+            nnodes, ncomp = int(dofnums.shape[0]), int(dofnums.shape[1])
+            self._ck(self.L.efg_set_space(self.h, slot, mesh_slot, ncomp, nnodes, _ptr(dofnums)))
+            return
+        nel, ncomp = int(cell_dofnums.shape[0]), int(cell_dofnums.shape[1])
+        nnodes = 0 if dofnums is None else int(dofnums.shape[0])
+        self._ck(self.L.efg_set_space_fe(self.h, slot, mesh_slot, int(fe), ncomp, nnodes, _ptr(dofnums), nel, _ptr(cell_dofnums)))
 
     def start(self, nrow, ncol):
         self._ck(self.L.efg_start(self.h, int(nrow), int(ncol)))
@@ -480,7 +487,8 @@ class SysvecAssemblerGPU:
 def _load_spaces(eng, elits, reuse=False):
     """Upload meshes + dof maps.  ``reuse``: skip the upload when this engine was last loaded from exactly these
     objects (the vector half of one integrate! call that follows the matrix half on a shared context)."""
-    token = tuple((id(it.fesp.mesh), id(it._fld0.dofnums)) for it in elits)
+    token = tuple((id(it.fesp.mesh), id(it._fld0.dofnums) if it._fld0 is not None else 0,
+                   id(it._fld2.dofnums) if it._fld2 is not None else 0) for it in elits)
     if reuse and getattr(eng, "_loaded", None) == token:
         return
     meshes = []
@@ -493,7 +501,9 @@ def _load_spaces(eng, elits, reuse=False):
         eng.set_mesh(slot, m.kind, np.ascontiguousarray(m.conn, dtype=np.int64), np.ascontiguousarray(m.xy, dtype=np.float64))
     for slot, it in enumerate(elits):
         mslot = [i for i, m in enumerate(meshes) if m is it.fesp.mesh][0]
-        eng.set_space(slot, mslot, np.ascontiguousarray(it._fld0.dofnums, dtype=np.int64))
+        nd = None if it._fld0 is None else np.ascontiguousarray(it._fld0.dofnums, dtype=np.int64)
+        cd = None if it._fld2 is None else np.ascontiguousarray(it._fld2.dofnums, dtype=np.int64)
+        eng.set_space(slot, mslot, nd, it.fesp.fe.fe_id, cd)
     eng._loaded = token
     eng._keep = [it for it in elits]      # the ids in the token stay valid while these are alive
 

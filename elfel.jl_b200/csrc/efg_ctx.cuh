@@ -30,6 +30,10 @@ struct SpaceDev {
     int64_t nnodes = 0;
     DevBuf<int32_t> dof;    // ncomp x nnodes, 0-based (-1 = dof number 0 = unnumbered)
     DevBuf<uint8_t> isdatum; // ncomp x nnodes: prescribed dofs (only for spaces made by efg_gen_space)
+    // elements with a dof on the cell (efg_set_space_fe)
+    int fe = 0;             // EFG_FE_H1 (the H1 element of the mesh), EFG_FE_T3_BUBBLE, EFG_FE_L2
+    int64_t ncells = 0;
+    DevBuf<int32_t> cdof;   // ncomp x ncells, 0-based: the dim-2 field's dof numbers (null: no cell field)
 };
 
 // --- two-pass path (element matrices to HBM, then segmented gather) ---------------------------
@@ -145,11 +149,18 @@ template <class Fn> inline bool dispatch_form(int form, int vkind, int nq, Fn &&
     case EFG_FORM_STOKES_VECLAP_ALT:
         if (vkind == 6 && nq == 3) { fn(Stokes2Form<true>{}); return true; }
         return false;
+    // the three-space forms: vkind is the velocity / pressure PAIR (form_kind(): the mesh kind for the H1 pairs)
     case EFG_FORM_STOKES_REDDY:
-        if (vkind == 6 && nq == 3) { fn(Stokes3Form<false>{}); return true; }
+        if (vkind == EFG_PAIR_T6_T3 && nq == 3) { fn(Stokes3Form<false>{}); return true; }
+        if (vkind == EFG_PAIR_T3B_T3 && nq == 3) { fn(Stokes3Form<false, EFG_PAIR_T3B_T3, 3>{}); return true; }
+        if (vkind == EFG_PAIR_Q4_L2 && nq == 4) { fn(Stokes3Form<false, EFG_PAIR_Q4_L2, 4>{}); return true; }
+        if (vkind == EFG_PAIR_T3_L2 && nq == 3) { fn(Stokes3Form<false, EFG_PAIR_T3_L2, 3>{}); return true; }
         return false;
     case EFG_FORM_STOKES_VECLAP:
-        if (vkind == 6 && nq == 3) { fn(Stokes3Form<true>{}); return true; }
+        if (vkind == EFG_PAIR_T6_T3 && nq == 3) { fn(Stokes3Form<true>{}); return true; }
+        if (vkind == EFG_PAIR_T3B_T3 && nq == 3) { fn(Stokes3Form<true, EFG_PAIR_T3B_T3, 3>{}); return true; }
+        if (vkind == EFG_PAIR_Q4_L2 && nq == 4) { fn(Stokes3Form<true, EFG_PAIR_Q4_L2, 4>{}); return true; }
+        if (vkind == EFG_PAIR_T3_L2 && nq == 3) { fn(Stokes3Form<true, EFG_PAIR_T3_L2, 3>{}); return true; }
         return false;
     }
     return false;

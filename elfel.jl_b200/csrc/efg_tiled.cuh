@@ -1312,7 +1312,7 @@ template <class F> static void tiled_pattern(efg_ctx *ctx)
     trace.mark("start");
     // T0: combined element dof table
     sy->edof.alloc(pool, (size_t)(nel * ND));
-    DofSrc src{m0.conn.p, ctx->mesh[1].conn.p, ctx->space[0].dof.p, ctx->space[1].dof.p, ctx->space[2].dof.p};
+    DofSrc src{m0.conn.p, ctx->mesh[1].conn.p, ctx->space[0].dof.p, ctx->space[1].dof.p, ctx->space[2].dof.p, ctx->space[0].cdof.p, ctx->space[1].cdof.p, ctx->space[2].cdof.p};
     LAUNCH(ctx, k_tl_edofs<F>, grid_for(nel, 256), 256, 0, src, nel, ctx->nrow, ctx->ncol, sy->edof.p, err.p);
     if (tl_read(ctx, err.p))
         efg_throw(EFG_ERR_INDEX, "ArgumentError: a dof number is < 1 or exceeds nrow/ncol (was every space numbered, incl. data dofs?)");
@@ -1631,7 +1631,7 @@ template <class F> static void tiled_tiles_search(efg_ctx *ctx)
     if (ctx->opt_tile_elems > 0) { tiled_tiles<F>(ctx, ctx->opt_tile_elems); return; }
     // start from the size the previous symbolic phase of this form settled on (re-assembly after efg_set_mesh, time
     // stepping with a changing mesh): the search below then succeeds at the first attempt
-    const int vkind = ctx->mesh[0].kind;
+    const int vkind = ctx->mesh[0].kind * 100 + ctx->space[0].fe * 10 + ctx->space[2].fe;      // (mesh kind and the spaces' elements)
     const bool hinted = ctx->te_hint > 0 && ctx->te_hint_form == ctx->form_req && ctx->te_hint_kind == vkind && ctx->te_hint_quad == ctx->quad_req;
     int te = hinted ? ctx->te_hint : tl_default_tile_elems<F>();
     for (;;) {

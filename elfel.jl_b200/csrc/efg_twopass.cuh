@@ -113,7 +113,7 @@ template <class F> void twopass_symbolic(efg_ctx *ctx)
     if (ntrip >= (int64_t)1 << 32)
         efg_throw(EFG_ERR_LIMIT, "two-pass path: %lld triplets exceed the 2^32 limit; shard the mesh (efg_set_column_range)", (long long)ntrip);
     const int64_t ncl = ctx->ncl;
-    DofSrc src{m0.conn.p, ctx->mesh[1].conn.p, ctx->space[0].dof.p, ctx->space[1].dof.p, ctx->space[2].dof.p};
+    DofSrc src{m0.conn.p, ctx->mesh[1].conn.p, ctx->space[0].dof.p, ctx->space[1].dof.p, ctx->space[2].dof.p, ctx->space[0].cdof.p, ctx->space[1].cdof.p, ctx->space[2].cdof.p};
 
     DevBuf<uint64_t> keys, keys2;
     DevBuf<uint32_t> vals;

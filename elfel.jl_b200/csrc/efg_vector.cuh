@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) k_qp_locations(const int32_t *__restrict_
     }
 }
 
-struct ErrComp { const int32_t *dof; int ncs, comp; };
+struct ErrComp { const int32_t *dof; int ncs, comp; const int32_t *cdof = nullptr; };    // cdof: cell dofs of an FEH1_T3_BUBBLE space (row f5)
 
 // one thread per element: sum over its quadrature points of JxW * sum_c (field_c - truth_c)^2, in the reference's
 // operation order; the element sums are then added by a fixed-shape tree (cub::DeviceReduce), so the result is
@@ -293,6 +293,14 @@ __global__ void __launch_bounds__(256) k_l2_error_elem(const int32_t *__restrict
             v0[a] = U[d0];
             v1[a] = NC > 1 ? U[d1] : 0.0;
         }
+        // FEH1_T3_BUBBLE: eldofvals = vertex values, then the bubble's (examples/stokes/colliding_flow/p1b_p1.jl:150-160)
+        const bool bub = NEN == 3 && c0.cdof != nullptr;
+        double b0 = 0.0, b1 = 0.0;
+        if (bub) {
+            const int32_t d0 = c0.cdof[e], d1 = NC > 1 ? c1.cdof[e] : 0;
+            if (d0 < 0 || d0 >= nU || d1 < 0 || d1 >= nU) *err = 1;
+            else { b0 = U[d0]; b1 = NC > 1 ? U[d1] : 0.0; }
+        }
         double acc = 0.0;
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
@@ -309,6 +317,11 @@ __global__ void __launch_bounds__(256) k_l2_error_elem(const int32_t *__restrict
             for (int j = 0; j < NEN; j++) {
                 a0 = __dadd_rn(a0, __dmul_rn(v0[j], tg.N[q][j]));
                 if (NC > 1) a1 = __dadd_rn(a1, __dmul_rn(v1[j], tg.N[q][j]));
+            }
+            if (bub) {
+                const double Nb = c_tab[3].N[q][3];
+                a0 = __dadd_rn(a0, __dmul_rn(b0, Nb));
+                if (NC > 1) a1 = __dadd_rn(a1, __dmul_rn(b1, Nb));
             }
             const double *t = truth + (e * NQ + q) * NC;
             const double d0 = __dsub_rn(a0, t[0]);

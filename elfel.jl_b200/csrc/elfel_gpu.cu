@@ -52,9 +52,21 @@ static int quadrature_points(int kind, int rule, double (*pc)[2], double *w)
     return -1;
 }
 
+// reference shape (element kind of the mesh) behind a form's kind code (the velocity / pressure pairs of row f5 live on one T3 / Q4 mesh)
+static int kind_shape(int vkind)
+{
+    return vkind == EFG_PAIR_T3B_T3 || vkind == EFG_PAIR_T3_L2 ? EFG_T3 : (vkind == EFG_PAIR_Q4_L2 ? EFG_Q4 : vkind);
+}
+
 static void basis_tables(int kind, double r, double s, double *N, double (*g)[2])
 {
-    if (kind == EFG_T3) { // src/FElements.jl:239-246
+    if (kind == EFG_FE_T3_BUBBLE) { // src/FElements.jl:341-356: ((1 - xi - eta) * xi) * eta and its parametric gradient
+        N[0] = (1 - r - s); N[1] = r; N[2] = s; N[3] = (1 - r - s) * r * s;
+        g[0][0] = -1.; g[0][1] = -1.; g[1][0] = +1.; g[1][1] = 0.; g[2][0] = 0.; g[2][1] = +1.;
+        g[3][0] = (-r * s + (1 - r - s) * s); g[3][1] = (-r * s + (1 - r - s) * r);
+    } else if (kind == EFG_FE_L2) { // src/FElements.jl:412-419, 441-448
+        N[0] = 1.0; g[0][0] = 0.0; g[0][1] = 0.0;
+    } else if (kind == EFG_T3) { // src/FElements.jl:239-246
         N[0] = (1 - r - s); N[1] = r; N[2] = s;
         g[0][0] = -1.; g[0][1] = -1.; g[1][0] = +1.; g[1][1] = 0.; g[2][0] = 0.; g[2][1] = +1.;
     } else if (kind == EFG_T6) { // src/FElements.jl:264-288
@@ -78,16 +90,17 @@ static void basis_tables(int kind, double r, double s, double *N, double (*g)[2]
 }
 
 // Host copy of the tables of (element kind `vkind`, rule): triangles share their rule between T3 and T6.  Returns npts or -1.
-static int build_tables(int vkind, int rule, QTab (&h)[3])
+static int build_tables(int vkind, int rule, QTab (&h)[EFG_NTAB])
 {
     memset(h, 0, sizeof h);
     double pc[EFG_MAXQ][2], w[EFG_MAXQ];
+    vkind = kind_shape(vkind);
     const int npts = quadrature_points(vkind, rule, pc, w);
     if (npts < 0 || npts > EFG_MAXQ) return -1;
-    const int kinds[3] = {EFG_T3, EFG_Q4, EFG_T6};
-    for (int k = 0; k < 3; k++) {
+    const int kinds[EFG_NTAB] = {EFG_T3, EFG_Q4, EFG_T6, EFG_FE_T3_BUBBLE, EFG_FE_L2};     // c_tab slots
+    for (int k = 0; k < EFG_NTAB; k++) {
         const bool tri = kinds[k] != EFG_Q4, vtri = vkind != EFG_Q4;
-        if (tri != vtri) continue;
+        if (tri != vtri && kinds[k] != EFG_FE_L2) continue;
         for (int q = 0; q < npts; q++) {
             h[k].w[q] = w[q];
             basis_tables(kinds[k], pc[q][0], pc[q][1], h[k].N[q], h[k].gp[q]);
@@ -98,7 +111,7 @@ static int build_tables(int vkind, int rule, QTab (&h)[3])
 static int quad_npts(int vkind, int rule)
 {
     double pc[EFG_MAXQ][2], w[EFG_MAXQ];
-    const int npts = quadrature_points(vkind, rule, pc, w);
+    const int npts = quadrature_points(kind_shape(vkind), rule, pc, w);
     return (npts < 0 || npts > EFG_MAXQ) ? -1 : npts;
 }
 
@@ -121,7 +134,7 @@ static int quad_npts(int vkind, int rule)
 struct DevTables {
     std::mutex mu;
     bool valid = false;
-    QTab tab[3];
+    QTab tab[EFG_NTAB];
     double prm[16];
     std::vector<efg_ctx *> users;       // live ctx on this device
     efg_ctx *uploader = nullptr;        // whose stream carried the last upload
@@ -150,7 +163,7 @@ struct TabGuard {
     // prm == nullptr: the kernels about to be launched do not read c_prm
     TabGuard(efg_ctx *c, int vkind, int rule, const double *prm, int nprm) : ctx(c), d(g_devtab[c->device]), lk(d.mu)
     {
-        QTab h[3];
+        QTab h[EFG_NTAB];
         npts = build_tables(vkind, rule, h);
         if (npts < 0) return;
         double hp[16] = {0};
@@ -314,7 +327,7 @@ int efg_destroy(efg_ctx *ctx)
     tables_unregister(ctx);
     invalidate(ctx);
     for (auto &m : ctx->mesh) { m.conn.release(); m.xy.release(); }
-    for (auto &s : ctx->space) { s.dof.release(); s.isdatum.release(); }
+    for (auto &s : ctx->space) { s.dof.release(); s.isdatum.release(); s.cdof.release(); }
     ctx->rfirst.release(); ctx->rlast1.release(); ctx->roff.release(); ctx->scratch.release(); ctx->cstage[0].release(); ctx->cstage[1].release();
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
@@ -422,8 +435,39 @@ int efg_set_space(efg_ctx *ctx, int slot, int mesh_slot, int ncomp, int64_t nnod
     s.mesh = mesh_slot; s.ncomp = ncomp; s.nnodes = nnodes;
     s.dof.alloc(ctx->pool, (size_t)(nnodes * ncomp));
     s.isdatum.release();
+    s.fe = EFG_FE_H1; s.ncells = 0; s.cdof.release();
     // dof number 0 (= not numbered) is accepted here and rejected by the symbolic phase, like sparse() does
     ingest_index(ctx, dofnums, nnodes * ncomp, 0, ((int64_t)1 << 31) - 1, s.dof.p, "efg_set_space: dof number");
+    API_END(ctx)
+}
+
+/* FESpace(mesh, FEH1_T3_BUBBLE() | FEL2_T3() | FEL2_Q4(), ncomp): fields on the vertices and / or on the cells */
+int efg_set_space_fe(efg_ctx *ctx, int slot, int mesh_slot, int fe, int ncomp, int64_t nnodes, const int64_t *dofnums,
+                     int64_t nel, const int64_t *cell_dofnums)
+{
+    if (fe == EFG_FE_H1) return efg_set_space(ctx, slot, mesh_slot, ncomp, nnodes, dofnums);
+    API_BEGIN(ctx)
+    if (slot < 0 || slot > 2 || mesh_slot < 0 || mesh_slot > 1) efg_throw(EFG_ERR_INVALID, "bad space/mesh slot");
+    if (fe != EFG_FE_T3_BUBBLE && fe != EFG_FE_L2) efg_throw(EFG_ERR_INVALID, "unknown finite element %d", fe);
+    if (ncomp != 1) efg_throw(EFG_ERR_INVALID, "spaces with cell dofs have one component here (the examples use one scalar space per velocity component)");
+    const MeshDev &m = ctx->mesh[mesh_slot];
+    if (fe == EFG_FE_T3_BUBBLE && m.kind != EFG_T3) efg_throw(EFG_ERR_INVALID, "FEH1_T3_BUBBLE needs a T3 mesh");
+    if (fe == EFG_FE_L2 && m.kind != EFG_T3 && m.kind != EFG_Q4) efg_throw(EFG_ERR_INVALID, "FEL2 needs a T3 or Q4 mesh");
+    const bool nodal = fe == EFG_FE_T3_BUBBLE;
+    if (nodal && nnodes != m.nnodes) efg_throw(EFG_ERR_INVALID, "space has %lld vertex terms, its mesh has %lld nodes", (long long)nnodes, (long long)m.nnodes);
+    if (nel != m.nel) efg_throw(EFG_ERR_INVALID, "space has %lld cell terms, its mesh has %lld elements", (long long)nel, (long long)m.nel);
+    if ((nodal && nnodes > 0 && !dofnums) || (nel > 0 && !cell_dofnums)) efg_throw(EFG_ERR_INVALID, "null dofnums");
+    invalidate(ctx);
+    SpaceDev &s = ctx->space[slot];
+    s.mesh = mesh_slot; s.ncomp = ncomp; s.nnodes = m.nnodes; s.fe = fe; s.ncells = nel;
+    s.isdatum.release();
+    s.dof.release();
+    if (nodal) {
+        s.dof.alloc(ctx->pool, (size_t)(nnodes * ncomp));
+        ingest_index(ctx, dofnums, nnodes * ncomp, 0, ((int64_t)1 << 31) - 1, s.dof.p, "efg_set_space_fe: dof number");
+    }
+    s.cdof.alloc(ctx->pool, (size_t)(nel * ncomp));
+    ingest_index(ctx, cell_dofnums, nel * ncomp, 0, ((int64_t)1 << 31) - 1, s.cdof.p, "efg_set_space_fe: cell dof number");
     API_END(ctx)
 }
 
@@ -475,17 +519,33 @@ int efg_set_column_ranges(efg_ctx *ctx, int64_t nranges, const int64_t *firsts, 
     API_END(ctx)
 }
 
+// Kind code of a form's instantiation: the mesh kind, or -- three-space forms -- the velocity / pressure pair
+// (EFG_PAIR_*: T6/T3 on two meshes, or a row-f5 pair on one mesh, recognised by the spaces' elements).
+static int form_kind(const efg_ctx *ctx, int form)
+{
+    const int k = ctx->mesh[0].kind;
+    if (form != EFG_FORM_STOKES_REDDY && form != EFG_FORM_STOKES_VECLAP) return k;
+    const int vfe = ctx->space[0].fe, pfe = ctx->space[2].fe;
+    if (vfe == EFG_FE_T3_BUBBLE && pfe == EFG_FE_H1) return EFG_PAIR_T3B_T3;
+    if (vfe == EFG_FE_H1 && pfe == EFG_FE_L2) return k == EFG_Q4 ? EFG_PAIR_Q4_L2 : EFG_PAIR_T3_L2;
+    return k;
+}
+
 static void check_form_inputs(efg_ctx *ctx, int form)
 {
     const MeshDev &m0 = ctx->mesh[0];
     if (m0.kind == 0) efg_throw(EFG_ERR_STATE, "mesh 0 not set");
-    auto need_space = [&](int s, int mesh, int ncomp) {
+    auto need_space = [&](int s, int mesh, int ncomp, int fe = EFG_FE_H1) {
         const SpaceDev &sp = ctx->space[s];
         if (sp.mesh != mesh || sp.ncomp != ncomp)
             efg_throw(EFG_ERR_INVALID, "form %d needs space %d on mesh %d with %d component(s)", form, s, mesh, ncomp);
+        if (sp.fe != fe) efg_throw(EFG_ERR_INVALID, "form %d: space %d has finite element %d, expected %d", form, s, sp.fe, fe);
         if (sp.nnodes != ctx->mesh[mesh].nnodes)     // efg_set_mesh replaced the mesh after efg_set_space
             efg_throw(EFG_ERR_STATE, "space %d numbers %lld nodes, mesh %d now has %lld: call efg_set_space again", s, (long long)sp.nnodes,
                       mesh, (long long)ctx->mesh[mesh].nnodes);
+        if (fe != EFG_FE_H1 && sp.ncells != ctx->mesh[mesh].nel)
+            efg_throw(EFG_ERR_STATE, "space %d numbers %lld cells, mesh %d now has %lld: call efg_set_space_fe again", s, (long long)sp.ncells,
+                      mesh, (long long)ctx->mesh[mesh].nel);
     };
     auto need_pmesh = [&]() {
         const MeshDev &m1 = ctx->mesh[1];
@@ -498,7 +558,14 @@ static void check_form_inputs(efg_ctx *ctx, int form)
     case EFG_FORM_STOKES_GEN:
     case EFG_FORM_STOKES_VECLAP_ALT: need_pmesh(); need_space(0, 0, 2); need_space(1, 1, 1); break;
     case EFG_FORM_STOKES_REDDY:
-    case EFG_FORM_STOKES_VECLAP: need_pmesh(); need_space(0, 0, 1); need_space(1, 0, 1); need_space(2, 1, 1); break;
+    case EFG_FORM_STOKES_VECLAP:
+        switch (form_kind(ctx, form)) {
+        case EFG_PAIR_T3B_T3: need_space(0, 0, 1, EFG_FE_T3_BUBBLE); need_space(1, 0, 1, EFG_FE_T3_BUBBLE); need_space(2, 0, 1); break;
+        case EFG_PAIR_Q4_L2:
+        case EFG_PAIR_T3_L2: need_space(0, 0, 1); need_space(1, 0, 1); need_space(2, 0, 1, EFG_FE_L2); break;
+        default: need_pmesh(); need_space(0, 0, 1); need_space(1, 0, 1); need_space(2, 1, 1);
+        }
+        break;
     default: efg_throw(EFG_ERR_INVALID, "unknown form %d", form);
     }
 }
@@ -512,7 +579,7 @@ static void run_symbolic(efg_ctx *ctx, int form, int quad, bool want_tiles)
     const bool same = ctx->form == form && ctx->quad == quad;
     if (ctx->have_symbolic && same) return;
     if (ctx->have_pattern && same && !want_tiles) return;
-    const int vkind = ctx->mesh[0].kind;
+    const int vkind = form_kind(ctx, form);
     const int npts = quad_npts(vkind, quad);       // (the symbolic phase does not read the tables)
     if (npts < 0) efg_throw(EFG_ERR_INVALID, "quadrature rule %d not available for element kind %d", quad, vkind);
     const bool resume = ctx->have_pattern && same;      // the pattern exists, the tiles are pending
@@ -677,6 +744,7 @@ int efg_vec_assemble(efg_ctx *ctx, int vform, int quad, const double *params, in
     const MeshDev &m0 = ctx->mesh[0];
     if (m0.kind == 0) efg_throw(EFG_ERR_STATE, "mesh 0 not set");
     if (ctx->space[0].mesh != 0 || ctx->space[0].ncomp != 1) efg_throw(EFG_ERR_INVALID, "the heat load vector needs space 0 on mesh 0 with 1 component");
+    if (ctx->space[0].fe != EFG_FE_H1) efg_throw(EFG_ERR_INVALID, "the heat load vector needs an H1 space (vertex dofs only)");
     if (ctx->space[0].nnodes != m0.nnodes) efg_throw(EFG_ERR_STATE, "space 0 numbers %lld nodes, mesh 0 now has %lld: call efg_set_space again", (long long)ctx->space[0].nnodes, (long long)m0.nnodes);
     if (!params || nparams != 1) efg_throw(EFG_ERR_INVALID, "vector form %d takes 1 parameter (Q)", vform);
     if (nrow < 0 || nrow >= ((int64_t)1 << 31)) efg_throw(EFG_ERR_INVALID, "bad vector length");
@@ -849,9 +917,11 @@ int efg_l2_error(efg_ctx *ctx, int ncomp, const int *space_slots, const int *com
         const SpaceDev &sp = ctx->space[space_slots[c]];
         if (comps[c] < 0 || comps[c] >= sp.ncomp) efg_throw(EFG_ERR_INVALID, "space %d has no component %d", space_slots[c], comps[c]);
         if (mslot >= 0 && sp.mesh != mslot) efg_throw(EFG_ERR_INVALID, "the components of one error integral must live on the same mesh");
+        if (sp.fe == EFG_FE_L2) efg_throw(EFG_ERR_INVALID, "efg_l2_error: space %d has no vertex dofs (FEL2)", space_slots[c]);
         if (sp.nnodes != ctx->mesh[sp.mesh].nnodes) efg_throw(EFG_ERR_STATE, "space %d numbers %lld nodes, its mesh now has %lld: call efg_set_space again", space_slots[c], (long long)sp.nnodes, (long long)ctx->mesh[sp.mesh].nnodes);
         mslot = sp.mesh;
-        ec[c] = ErrComp{sp.dof.p, sp.ncomp, comps[c]};
+        ec[c] = ErrComp{sp.dof.p, sp.ncomp, comps[c], sp.fe == EFG_FE_T3_BUBBLE ? sp.cdof.p : nullptr};
+        if (c > 0 && (ec[c].cdof != nullptr) != (ec[0].cdof != nullptr)) efg_throw(EFG_ERR_INVALID, "the components of one error integral must use the same finite element");
     }
     if (ncomp == 1) ec[1] = ec[0];
     const MeshDev &m = ctx->mesh[mslot];
@@ -1165,6 +1235,7 @@ int efg_gen_space(efg_ctx *ctx, int slot, int mesh_slot, int ncomp)
     invalidate(ctx);
     SpaceDev &s = ctx->space[slot];
     s.mesh = mesh_slot; s.ncomp = ncomp; s.nnodes = ctx->mesh[mesh_slot].nnodes;
+    s.fe = EFG_FE_H1; s.ncells = 0; s.cdof.release();
     s.dof.alloc(ctx->pool, (size_t)(s.nnodes * ncomp));
     s.isdatum.alloc(ctx->pool, (size_t)(s.nnodes * ncomp) + 1);      // (+1: the numbering scans read n + 1 flags)
     LAUNCH(ctx, k_tl_fill_i32, grid_for(s.nnodes * ncomp, 256), 256, 0, s.dof.p, s.nnodes * ncomp, -1);     // unnumbered
@@ -1272,6 +1343,7 @@ int efg_fetch_dofnums(efg_ctx *ctx, int space_slot, int64_t *dofnums)
     if (space_slot < 0 || space_slot > 2 || ctx->space[space_slot].mesh < 0) efg_throw(EFG_ERR_STATE, "space %d not set", space_slot);
     if (!dofnums) efg_throw(EFG_ERR_INVALID, "null output");
     const SpaceDev &s = ctx->space[space_slot];
+    if (!s.dof.p) efg_throw(EFG_ERR_INVALID, "space %d has no vertex dofs (FEL2)", space_slot);
     const int64_t n = s.nnodes * s.ncomp;
     DevBuf<int64_t> tmp;
     int64_t *d = dofnums;

@@ -5,6 +5,9 @@ heat:       examples/heat/poisson/t3.jl:93-104, q4.jl (all boundary nodes prescr
 elasticity: examples/elasticity/stretch/t6.jl:78-99 (edges x=0 and x=A, both components)
 stokes:     examples/stokes/colliding_flow/ht_p2_p1_gen.jl:152-177 (whole velocity boundary + one
             pressure node nearest the centre; numberdofs!([Uh, Ph]))
+p1b_p1:     examples/stokes/colliding_flow/p1b_p1.jl:175-200 (FEH1_T3_BUBBLE velocities, FEH1_T3 pressure, one T3 mesh)
+q1_q0:      examples/stokes/colliding_flow/q1_q0.jl:131-153 (FEH1_Q4 velocities, FEL2_Q4 pressure: the CELL nearest the
+            centre is pinned, setebc!(pfesp, 2, ...))
 """
 from __future__ import annotations
 
@@ -15,8 +18,8 @@ import numpy as np
 from . import _lib
 from .assemblers import (ElasticityForm, HeatForm, StokesGenForm, StokesReddyForm, StokesVeclapAltForm,
                          StokesVeclapForm)
-from .fespaces import (FEH1_Q4, FEH1_T3, FEH1_T6, FESpace, ndofs, numberdatadofs, numberdofs, numberfreedofs,
-                       setebc)
+from .fespaces import (FEH1_Q4, FEH1_T3, FEH1_T6, FEH1_T3_BUBBLE, FEL2_Q4, FEL2_T3, FESpace, ndofs, numberdatadofs, numberdofs,
+                       numberfreedofs, setebc)
 from .meshes import Q4, T3, T6, Mesh, Q4block, T3block, T6block, T6block_fast, T6toT3, jitter, transform
 
 
@@ -35,7 +38,12 @@ class Problem:
         return self.meshes[0].nel
 
     def dofs(self):
-        return [s.field.dofnums for s in self.spaces]
+        """vertex-field dof numbers per space (None for an L2 space)"""
+        return [None if s.field is None else s.field.dofnums for s in self.spaces]
+
+    def cell_dofs(self):
+        """cell-field dof numbers per space (None where the element has no cell dof)"""
+        return [None if s.cellfield is None else s.cellfield.dofnums for s in self.spaces]
 
 
 def _structured_boundary(nL, nW, kind, mesh):
@@ -131,13 +139,41 @@ def stokes_problem(N: int, formulation: str = "gen", perturb: bool = False, A: f
     return Problem(f"stokes_{formulation}_N{N}", form, 3, [vmesh, pmesh], spaces, smesh, sum(ndofs(s) for s in spaces))
 
 
+def stokes_f5_problem(N: int, pair: str = "p1b_p1", formulation: str = "reddy", perturb: bool = False, A: float = 1.0) -> Problem:
+    """The colliding-flow set-up on the element pairs of SURVEY 8f row f5, all three spaces on ONE mesh:
+    pair = "p1b_p1" (FEH1_T3_BUBBLE / FEH1_T3, npts 3), "q1_q0" (FEH1_Q4 / FEL2_Q4, Gauss order 2) or
+    "p1_p0" (FEH1_T3 / FEL2_T3, npts 3)."""
+    if pair == "q1_q0":
+        mesh, vfe, pfe, q = Q4block(2 * A, 2 * A, N, N), FEH1_Q4(), FEL2_Q4(), 2
+    else:
+        mesh = T3block(2 * A, 2 * A, N, N)
+        vfe, pfe, q = (FEH1_T3_BUBBLE(), FEH1_T3(), 3) if pair == "p1b_p1" else (FEH1_T3(), FEL2_T3(), 3)
+    transform(mesh, lambda x: x - A)
+    bnd = _structured_boundary(N, N, mesh.kind, mesh)
+    regular_xy = mesh.xy
+    if perturb:
+        mesh = jitter(mesh)
+    ux, uy, Ph = FESpace(mesh, vfe, 1), FESpace(mesh, vfe, 1), FESpace(mesh, pfe, 1)
+    _setebc_nodes(ux, bnd); _setebc_nodes(uy, bnd)
+    if Ph.field is not None:      # the pressure node nearest the centre
+        _setebc_nodes(Ph, np.array([int(np.argmin((regular_xy ** 2).sum(axis=1))) + 1]))
+    else:                         # q1_q0.jl:147-148: setebc!(pfesp, 2, atcenter[1], 1, 0.0) -- the id of the NODE nearest the centre, used as a cell id
+        Ph.cellfield.isdatum[int(np.argmin((regular_xy ** 2).sum(axis=1))), 0] = True
+    spaces = [ux, uy, Ph]
+    numberdofs(spaces)
+    form = StokesReddyForm(1.0) if formulation == "reddy" else StokesVeclapForm(1.0)
+    return Problem(f"stokes_{pair}_{formulation}_N{N}", form, q, [mesh], spaces, [0, 0, 0], sum(ndofs(s) for s in spaces))
+
+
 def load_problem(engine, prob: Problem, column_range=None):
     """Push a Problem through the C ABI: efg_set_mesh / efg_set_space / efg_start (/ efg_set_column_range)."""
     for slot, m in enumerate(prob.meshes):
         engine.set_mesh(slot, m.kind, np.ascontiguousarray(m.conn, dtype=np.int64),
                         np.ascontiguousarray(m.xy, dtype=np.float64))
     for slot, (s, ms) in enumerate(zip(prob.spaces, prob.space_mesh)):
-        engine.set_space(slot, ms, np.ascontiguousarray(s.field.dofnums, dtype=np.int64))
+        nd = None if s.field is None else np.ascontiguousarray(s.field.dofnums, dtype=np.int64)
+        cd = None if s.cellfield is None else np.ascontiguousarray(s.cellfield.dofnums, dtype=np.int64)
+        engine.set_space(slot, ms, nd, s.fe.fe_id, cd)
     engine.start(prob.ndofs, prob.ndofs)
     if column_range is not None:
         engine.set_column_range(*column_range)
@@ -146,4 +182,7 @@ def load_problem(engine, prob: Problem, column_range=None):
 def oracle_args(prob: Problem):
     """(form_id, quad, vmesh, pmesh, dofs, params) for oracle.assemble -- used by tests/bench only."""
     pm = prob.meshes[1] if len(prob.meshes) > 1 else None
+    if any(s.cellfield is not None for s in prob.spaces):      # row f5: one mesh, elements named per space
+        dofs = {"dofs": prob.dofs(), "cell_dofs": prob.cell_dofs(), "vfe": prob.spaces[0].fe.fe_id, "pfe": prob.spaces[2].fe.fe_id}
+        return prob.form.form_id, prob.quad, prob.meshes[0], prob.meshes[0], dofs, prob.form.params()
     return prob.form.form_id, prob.quad, prob.meshes[0], pm, prob.dofs(), prob.form.params()

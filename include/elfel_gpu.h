@@ -79,11 +79,23 @@ typedef struct efg_ctx efg_ctx;
 #define EFG_Q4 4
 #define EFG_T6 6
 
+/* SURVEY 8f row f5 -- finite elements with a dof on the cell itself, for efg_set_space_fe:
+ *   EFG_FE_H1         the H1 element of the space's mesh (FEH1_T3 / FEH1_Q4 / FEH1_T6): vertex dofs only
+ *   EFG_FE_T3_BUBBLE  FEH1_T3_BUBBLE (src/FElements.jl:324-355): vertex dofs + one dof on the cell (the cubic bubble)
+ *   EFG_FE_L2         FEL2_T3 / FEL2_Q4 (src/FElements.jl:394-448): one dof on the cell, no vertex dofs; the geometry
+ *                     carrier is the H1 element of the mesh (_geometrycarrier) */
+#define EFG_FE_H1         0
+#define EFG_FE_L2         1
+#define EFG_FE_T3_BUBBLE  7
+
 /* weak forms (the integrate! closures of the reference's examples/tests) */
 #define EFG_FORM_HEAT               1 /* space 0: scalar.        params = [kappa]                  */
 #define EFG_FORM_ELASTICITY         2 /* space 0: 2 components.  params = D 3x3 column-major (9)   */
 #define EFG_FORM_STOKES_GEN         3 /* space 0: u (T6,2), 1: p (T3).  params = D (9)             */
 #define EFG_FORM_STOKES_REDDY       4 /* space 0: ux, 1: uy (T6), 2: p (T3).  params = [mu]        */
+                                     /* ... and, on ONE mesh (slot 0), the pairs of examples/stokes/colliding_flow/p1b_p1.jl
+                                        (ux, uy: EFG_FE_T3_BUBBLE, p: FEH1_T3, npts 3), q1_q0.jl (ux, uy: FEH1_Q4,
+                                        p: EFG_FE_L2, Gauss order 2) and FEH1_T3 / EFG_FE_L2 (npts 3); same for _VECLAP */
 #define EFG_FORM_STOKES_VECLAP_ALT  5 /* space 0: u (T6,2), 1: p (T3).  params = [mu]              */
 #define EFG_FORM_STOKES_VECLAP      6 /* space 0: ux, 1: uy (T6), 2: p (T3).  params = [mu]        */
 
@@ -128,6 +140,13 @@ int efg_set_mesh(efg_ctx *ctx, int mesh_slot, int elemkind, int64_t nel, int64_t
 /* space_slot 0..2, living on mesh_slot; dofnums is ncomp x nnodes. */
 int efg_set_space(efg_ctx *ctx, int space_slot, int mesh_slot, int ncomp, int64_t nnodes,
                   const int64_t *dofnums);
+
+/* The same for a space whose element carries a dof on the cell (row f5): `fe` = EFG_FE_*; dofnums (ncomp x nnodes) are the
+ * dof numbers of the dim-0 field, cell_dofnums (ncomp x nel) those of the dim-2 field -- FESpace._irsfields[0] / [2]
+ * (src/FESpaces.jl:75-85), element dof order: vertex dofs first, then the cell's (src/FEIterators.jl:185-194).
+ * EFG_FE_L2: nnodes = 0 / dofnums = NULL; EFG_FE_H1: nel = 0 / cell_dofnums = NULL (= efg_set_space). */
+int efg_set_space_fe(efg_ctx *ctx, int space_slot, int mesh_slot, int fe, int ncomp, int64_t nnodes, const int64_t *dofnums,
+                     int64_t nel, const int64_t *cell_dofnums);
 
 /* start!(ass, nrow, ncol): resets the assembler; mesh/space data are kept. */
 int efg_start(efg_ctx *ctx, int64_t nrow, int64_t ncol);

@@ -17,6 +17,14 @@ _SO = os.path.join(_HERE, "libelfel_oracle.so")
 
 FORM_HEAT, FORM_ELASTICITY, FORM_STOKES_GEN, FORM_STOKES_REDDY, FORM_STOKES_VECLAP_ALT, FORM_STOKES_VECLAP = 1, 2, 3, 4, 5, 6
 
+FE_H1, FE_L2, FE_T3_BUBBLE = 0, 1, 7      # elements with a dof on the cell
+
+
+class _Ext(C.Structure):      # efo_ext
+    _fields_ = [("vfe", C.c_int), ("pfe", C.c_int), ("cdof0", C.POINTER(C.c_int64)), ("cdof1", C.POINTER(C.c_int64)),
+                ("cdof2", C.POINTER(C.c_int64))]
+
+
 _lib = None
 
 
@@ -42,12 +50,12 @@ def lib():
         L.efo_triplets_per_element.restype = C.c_int64
         L.efo_assemble_coo.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64,
                                        i64p, C.c_int, f64p, i64p, C.c_int, f64p,
-                                       i64p, i64p, i64p, f64p, i64p, i64p, f64p]
+                                       i64p, i64p, i64p, f64p, i64p, i64p, f64p, C.POINTER(_Ext)]
         L.efo_assemble_coo.restype = C.c_int64
         common = [C.c_int, C.c_int, C.c_int64, i64p, C.c_int64, i64p, C.c_int, f64p, i64p, C.c_int, f64p, i64p, i64p, i64p]
-        L.efo_direct_pattern.argtypes = common + [C.c_int64, C.c_int64, C.c_int64, C.c_int64, i64p, i64p]
+        L.efo_direct_pattern.argtypes = common + [C.c_int64, C.c_int64, C.c_int64, C.c_int64, i64p, i64p, C.POINTER(_Ext)]
         L.efo_direct_pattern.restype = C.c_int64
-        L.efo_direct_values.argtypes = common + [f64p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, i64p, i64p, f64p]
+        L.efo_direct_values.argtypes = common + [f64p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, i64p, i64p, f64p, C.POINTER(_Ext)]
         L.efo_direct_values.restype = C.c_int64
         L.efo_sparse.argtypes = [C.c_int64, C.c_int64, C.c_int64, i64p, i64p, f64p, i64p, i64p, f64p]
         L.efo_sparse.restype = C.c_int64
@@ -60,6 +68,8 @@ def lib():
         L.efo_l2_error.argtypes = [C.c_int, C.c_int64, i64p, C.c_int, f64p, C.c_int, i64p, C.c_int, C.c_int,
                                    i64p, C.c_int, C.c_int, f64p, f64p]
         L.efo_l2_error.restype = C.c_double
+        L.efo_l2_error_fe.argtypes = [C.c_int, C.c_int64, i64p, C.c_int, f64p, C.c_int, C.c_int, i64p, i64p, i64p, i64p, f64p, f64p]
+        L.efo_l2_error_fe.restype = C.c_double
         _lib = L
     return _lib
 
@@ -74,6 +84,18 @@ def _c(a, dt):
     return None if a is None else np.ascontiguousarray(a, dtype=dt)
 
 
+def _spaces(dofs):
+    """dofs: a list of up to three (nnodes, ncomp) dofnums arrays, or -- spaces with cell dofs, row f5 -- a dict
+    {"dofs": [...], "cell_dofs": [...], "vfe": FE_*, "pfe": FE_*}.  -> (d[3], ext pointer or None, keep-alive, (vfe, pfe))"""
+    if isinstance(dofs, dict):
+        d = [_c(x, np.int64) for x in dofs["dofs"]] + [None] * (3 - len(dofs["dofs"]))
+        cd = [_c(x, np.int64) for x in dofs["cell_dofs"]] + [None] * (3 - len(dofs["cell_dofs"]))
+        ext = _Ext(int(dofs["vfe"]), int(dofs["pfe"]), _p(cd[0], C.c_int64), _p(cd[1], C.c_int64), _p(cd[2], C.c_int64))
+        return d, C.byref(ext), (cd, ext), (int(dofs["vfe"]), int(dofs["pfe"]))
+    d = [_c(x, np.int64) for x in dofs] + [None] * (3 - len(dofs))
+    return d, None, None, (0, 0)
+
+
 def quadrature(kind, rule):
     pc = np.zeros((25, 2))
     w = np.zeros(25)
@@ -84,13 +106,13 @@ def quadrature(kind, rule):
 
 
 def bfun(kind, r, s):
-    N = np.zeros(kind)
+    N = np.zeros(lib().efo_nbf(kind))
     lib().efo_bfun(kind, r, s, _p(N, C.c_double))
     return N
 
 
 def bfungradpar(kind, r, s):
-    g = np.zeros((kind, 2))
+    g = np.zeros((lib().efo_nbf(kind), 2))
     lib().efo_bfungradpar(kind, r, s, _p(g, C.c_double))
     return g
 
@@ -103,7 +125,8 @@ def assemble_coo(form, quad, vmesh, pmesh, dofs, params, e0=0, e1=None):
     L = lib()
     e1 = vmesh.conn.shape[0] if e1 is None else e1
     pk = pmesh.kind if pmesh is not None else 0
-    tpe = L.efo_triplets_per_element(form, vmesh.kind, pk)
+    d, ext, _keep, (vfe, pfe) = _spaces(dofs)
+    tpe = L.efo_triplets_per_element(form, vfe or vmesh.kind, pfe or pk)
     nt = tpe * (e1 - e0)
     row = np.empty(nt, dtype=np.int64)
     col = np.empty(nt, dtype=np.int64)
@@ -112,12 +135,11 @@ def assemble_coo(form, quad, vmesh, pmesh, dofs, params, e0=0, e1=None):
     vxy = _c(vmesh.xy, np.float64)
     pconn = _c(pmesh.conn, np.int64) if pmesh is not None else None
     pxy = _c(pmesh.xy, np.float64) if pmesh is not None else None
-    d = [_c(x, np.int64) for x in dofs] + [None] * (3 - len(dofs))
     prm = _c(np.atleast_1d(params), np.float64)
     n = L.efo_assemble_coo(form, quad, e0, e1, _p(vconn, C.c_int64), vmesh.kind, _p(vxy, C.c_double),
                            _p(pconn, C.c_int64), pk, _p(pxy, C.c_double),
                            _p(d[0], C.c_int64), _p(d[1], C.c_int64), _p(d[2], C.c_int64),
-                           _p(prm, C.c_double), _p(row, C.c_int64), _p(col, C.c_int64), _p(val, C.c_double))
+                           _p(prm, C.c_double), _p(row, C.c_int64), _p(col, C.c_int64), _p(val, C.c_double), ext)
     if n != nt:
         raise RuntimeError(f"oracle element loop failed (rc={n})")
     return row, col, val
@@ -155,12 +177,13 @@ def assemble(form, quad, vmesh, pmesh, dofs, params, nrow, ncol, timing=None):
 
 def elements_touching(dofs_per_mesh, c0, c1):
     """Ascending 0-based numbers of the elements with at least one dof in the column block [c0, c1] (1-based inclusive).
-    dofs_per_mesh: [(conn (nel, nen), dofnums (nnodes, ncomp)), ...] for every space of the form."""
+    dofs_per_mesh: [(conn (nel, nen), dofnums (nnodes, ncomp)), ...] for every space of the form; conn = None for a
+    cell field (dofnums (nel, ncomp): term e belongs to element e)."""
     hit = None
     for conn, dofnums in dofs_per_mesh:
         d = np.asarray(dofnums)
         inb = ((d >= c0) & (d <= c1)).any(axis=1)
-        h = inb[np.asarray(conn) - 1].any(axis=1)
+        h = inb if conn is None else inb[np.asarray(conn) - 1].any(axis=1)
         hit = h if hit is None else (hit | h)
     return np.nonzero(hit)[0].astype(np.int64)
 
@@ -175,7 +198,7 @@ def assemble_direct(form, quad, vmesh, pmesh, dofs, params, nrow, ncol, c0=1, c1
     vconn = _c(vmesh.conn, np.int64); vxy = _c(vmesh.xy, np.float64)
     pconn = _c(pmesh.conn, np.int64) if pmesh is not None else None
     pxy = _c(pmesh.xy, np.float64) if pmesh is not None else None
-    d = [_c(x, np.int64) for x in dofs] + [None] * (3 - len(dofs))
+    d, ext, _keep, _ = _spaces(dofs)
     prm = _c(np.atleast_1d(params), np.float64)
     el = _c(elist, np.int64) if elist is not None else None
     nsel = 0 if el is None else len(el)
@@ -184,17 +207,17 @@ def assemble_direct(form, quad, vmesh, pmesh, dofs, params, nrow, ncol, c0=1, c1
             _p(pconn, C.c_int64), pk, _p(pxy, C.c_double), _p(d[0], C.c_int64), _p(d[1], C.c_int64), _p(d[2], C.c_int64))
     t0 = time.perf_counter()
     colptr = np.empty(c1 - c0 + 2, dtype=np.int64)
-    nnz = L.efo_direct_pattern(*head, nrow, ncol, c0, c1, _p(colptr, C.c_int64), None)
+    nnz = L.efo_direct_pattern(*head, nrow, ncol, c0, c1, _p(colptr, C.c_int64), None, ext)
     if nnz == -1:
         raise ValueError("ArgumentError: row/column index out of range (dof number 0 or > nrow?)")
     if nnz < 0:
         raise MemoryError("oracle direct mode: allocation failed")
     rowval = np.empty(max(nnz, 1), dtype=np.int64)
-    L.efo_direct_pattern(*head, nrow, ncol, c0, c1, _p(colptr, C.c_int64), _p(rowval, C.c_int64))
+    L.efo_direct_pattern(*head, nrow, ncol, c0, c1, _p(colptr, C.c_int64), _p(rowval, C.c_int64), ext)
     t1 = time.perf_counter()
     nzval = np.empty(max(nnz, 1), dtype=np.float64)
     rc = L.efo_direct_values(*head, _p(prm, C.c_double), nrow, ncol, c0, c1, _p(colptr, C.c_int64), _p(rowval, C.c_int64),
-                             _p(nzval, C.c_double))
+                             _p(nzval, C.c_double), ext)
     if rc != nnz:
         raise RuntimeError(f"oracle direct accumulation failed (rc={rc})")
     if timing is not None:
@@ -279,6 +302,22 @@ def l2_error(quad, mesh, comps, U, truth):
     r = lib().efo_l2_error(quad, conn.shape[0], _p(conn, C.c_int64), mesh.kind, _p(xy, C.c_double), len(comps),
                            _p(d[0], C.c_int64), ncs[0], cc[0], _p(d[1], C.c_int64), ncs[1], cc[1],
                            _p(U, C.c_double), _p(truth, C.c_double))
+    if r < 0:
+        raise ValueError("quadrature rule not available")
+    return r
+
+
+def l2_error_fe(quad, mesh, fe, comps, U, truth):
+    """evaluate_*_error for scalar spaces whose element has a cell dof (FEH1_T3_BUBBLE, row f5): comps =
+    [(dofnums (nnodes,1), cell_dofnums (nel,1)), ...] (1 or 2 entries)."""
+    conn = _c(mesh.conn, np.int64); xy = _c(mesh.xy, np.float64)
+    d = [(_c(c[0], np.int64), _c(c[1], np.int64)) for c in comps]
+    if len(d) == 1:
+        d.append(d[0])
+    U = _c(U, np.float64); truth = _c(truth, np.float64)
+    r = lib().efo_l2_error_fe(quad, conn.shape[0], _p(conn, C.c_int64), mesh.kind, _p(xy, C.c_double), int(fe), len(comps),
+                              _p(d[0][0], C.c_int64), _p(d[0][1], C.c_int64), _p(d[1][0], C.c_int64), _p(d[1][1], C.c_int64),
+                              _p(U, C.c_double), _p(truth, C.c_double))
     if r < 0:
         raise ValueError("quadrature rule not available")
     return r

@@ -1,0 +1,130 @@
+"""SURVEY 8f row f5 -- FEH1_T3_BUBBLE / FEL2_T3 / FEL2_Q4 (src/FElements.jl:324-355, 394-448): the oracle's and the host
+mirror's restatement against the known answers the reference's own tests hold (test/test_felements.jl:86-151,
+test/test_fespaces.jl:117-170), and the p1b_p1 / q1_q0 colliding-flow examples solved end to end with the oracle matrix
+(examples/stokes/colliding_flow/p1b_p1.jl, q1_q0.jl).  The reference asserts no (ep, ev) values for these two examples
+(test/test_stokes.jl:156-312 only runs the bubble case), so entry values are pinned through the Reddy loop they share
+with the T6/T3 goldens plus the element tables below; the convergence rates are the additional end-to-end check."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spl
+
+import elfel_jl_b200 as efg
+
+trueux = lambda x, y: 20 * x * y ** 3
+trueuy = lambda x, y: 5 * x ** 4 - 5 * y ** 4
+truep = lambda x, y: 60 * x ** 2 * y - 20 * y ** 3
+
+
+def test_bubble_and_l2_tables_match_the_reference_known_answers(oracle):
+    # test/test_fespaces.jl:130,146: bfun(FEH1_T3_BUBBLE, [1/3, 1/3])
+    want = [0.3333333333333334, 0.3333333333333333, 0.3333333333333333, 0.03703703703703704]
+    assert np.allclose(oracle.bfun(oracle.FE_T3_BUBBLE, 1 / 3, 1 / 3), want, rtol=0, atol=1e-16)
+    assert np.allclose(efg.bfun(efg.FEH1_T3_BUBBLE(), [1 / 3, 1 / 3]), want, rtol=0, atol=1e-16)
+    g = oracle.bfungradpar(oracle.FE_T3_BUBBLE, 0.2, 0.3)
+    assert np.array_equal(g[:3], [[-1., -1.], [1., 0.], [0., 1.]])          # the T3 rows, test/test_felements.jl:22-24
+    assert np.allclose(g[3], [-0.2 * 0.3 + 0.5 * 0.3, -0.2 * 0.3 + 0.5 * 0.2], rtol=0, atol=1e-17)     # src/FElements.jl:354
+    # test/test_felements.jl:105-107,149-151: FEL2_Q4 / FEL2_T3: bfun == [1.0], gradient [0 0]
+    assert np.array_equal(oracle.bfun(oracle.FE_L2, 0.25, 0.25), [1.0])
+    assert np.array_equal(oracle.bfungradpar(oracle.FE_L2, 0.25, 0.25), [[0.0, 0.0]])
+    assert np.array_equal(efg.bfun(efg.FEL2_Q4(), [0.25, 0.25]), [1.0])
+
+
+def test_host_mirror_of_spaces_with_cell_dofs():
+    mesh = efg.T3block(1.0, 1.0, 2, 3)
+    # test/test_fespaces.jl:119-128,150-170 (ndofperfeat, ndofsperel, edofmdim / edofbfnum / edofcompnt by the loop of :150-164)
+    for ncopies in (1, 2):
+        fesp = efg.FESpace(mesh, efg.FEH1_T3_BUBBLE(), ncopies)
+        assert fesp.fe.ndofperfeat == (1, 0, 1) and fesp.fe.nbf == 4
+        assert efg.ndofsperel(fesp) == 4 * ncopies
+        emdim, bfnum, compnt, bfn = [], [], [], 1
+        for m, nfeat, nd in ((0, 3, 1), (1, 3, 0), (2, 1, 1)):
+            for _ in range(nfeat):
+                for _ in range(nd):
+                    for j in range(1, ncopies + 1):
+                        emdim.append(m); bfnum.append(bfn); compnt.append(j)
+                    bfn += 1
+        assert list(efg.edofmdim(fesp)) == emdim and list(efg.edofbfnum(fesp)) == bfnum and list(efg.edofcompnt(fesp)) == compnt
+        assert fesp.field.dofnums[0, 0] == 0          # :168 dofnum(fesp, 0, 1, 1) == 0 before numbering
+    l2 = efg.FESpace(mesh, efg.FEL2_T3(), 1)
+    assert l2.field is None and l2.cellfield.nterms == mesh.nel and efg.ndofsperel(l2) == 1       # test_felements.jl:138-141
+    # numbering: free dofs of the vertex field, then of the cell field, then the data dofs (src/FESpaces.jl:141-173)
+    ux = efg.FESpace(mesh, efg.FEH1_T3_BUBBLE(), 1)
+    efg.setebc(ux, 0, 1, 1, 5.0); efg.setebc(ux, 0, 4, 1, 6.0)
+    efg.numberdofs([ux, l2])
+    nn, ne = mesh.nnodes, mesh.nel
+    assert efg.nunknowns(ux) == nn - 2 + ne and efg.ndofs(ux) == nn + ne
+    assert sorted(np.concatenate([ux.field.dofnums.ravel(), ux.cellfield.dofnums.ravel(), l2.cellfield.dofnums.ravel()])) == list(range(1, nn + 2 * ne + 1))
+    assert ux.cellfield.dofnums[0, 0] == nn - 2 + 1 and l2.cellfield.dofnums[0, 0] == nn - 2 + ne + 1
+    assert set(ux.field.dofnums[[0, 3], 0]) == {nn + 2 * ne - 1, nn + 2 * ne}
+    U = efg.gathersysvec([ux, l2])
+    assert U[ux.field.dofnums[0, 0] - 1] == 5.0 and U[ux.field.dofnums[3, 0] - 1] == 6.0
+
+
+def _solve(oracle, pair, N):
+    prob = efg.stokes_f5_problem(N, pair)
+    cp, rv, nz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    K = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(prob.ndofs, prob.ndofs))
+    xy = prob.meshes[0].xy
+    for s_, f in zip(prob.spaces[:2], (trueux, trueuy)):
+        d = s_.field.isdatum[:, 0]
+        s_.field.dofvals[d, 0] = f(xy[d, 0], xy[d, 1])
+    U = efg.gathersysvec(prob.spaces)
+    nu = sum(efg.nunknowns(s_) for s_ in prob.spaces)
+    KT = K @ U
+    U[:nu] = spl.spsolve(K[:nu, :nu].tocsc(), -KT[:nu])
+    return prob, K, U
+
+
+def test_triplet_counts_and_symmetry_of_the_f5_pairs(oracle):
+    for pair, nt, nd in (("p1b_p1", 112, 11), ("q1_q0", 80, 9), ("p1_p0", 48, 7)):
+        prob = efg.stokes_f5_problem(5, pair, perturb=True)
+        row, col, val = oracle.assemble_coo(*efg.oracle_args(prob))
+        assert len(row) == nt * prob.nel
+        assert row.min() >= 1 and row.max() <= prob.ndofs
+        cp, rv, nz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+        K = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(prob.ndofs, prob.ndofs))
+        assert abs(K - K.T).max() <= 1e-15 * abs(K).max()
+        a = oracle.assemble_direct(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+        assert np.array_equal(a[0], cp) and np.array_equal(a[1], rv) and a[2].tobytes() == nz.tobytes()
+        # the column of a cell dof holds the rows of its own element only: a bubble velocity couples to all 11 element dofs,
+        # an L2 pressure to the 2 x NV velocity dofs (no pressure-pressure block)
+        s_ = prob.spaces[0] if pair == "p1b_p1" else prob.spaces[2]
+        c = int(s_.cellfield.dofnums[3, 0])
+        assert cp[c] - cp[c - 1] == (11 if pair == "p1b_p1" else nd - 1)
+    # veclap variant drops the two ux-uy blocks
+    prob = efg.stokes_f5_problem(4, "p1b_p1", "veclap")
+    assert len(oracle.assemble_coo(*efg.oracle_args(prob))[0]) == (112 - 32) * prob.nel
+
+
+def test_p1b_p1_colliding_flow_converges_at_the_mini_element_rates(oracle):
+    """examples/stokes/colliding_flow/p1b_p1.jl end to end with the oracle matrix: velocity error O(h^2), pressure better
+    than O(h^1.5) between N = 8, 16, 32 (the example prints (ep, ev) for N = 4 ... 64; the reference asserts no values)."""
+    errs = []
+    for N in (8, 16, 32):
+        prob, K, U = _solve(oracle, "p1b_p1", N)
+        ux, uy, ph = prob.spaces
+        m = prob.meshes[0]
+        loc = oracle.qp_locations(prob.quad, m)
+        ev = oracle.l2_error_fe(prob.quad, m, oracle.FE_T3_BUBBLE,
+                                [(ux.field.dofnums, ux.cellfield.dofnums), (uy.field.dofnums, uy.cellfield.dofnums)], U,
+                                np.stack([trueux(loc[..., 0], loc[..., 1]), trueuy(loc[..., 0], loc[..., 1])], -1))
+        ep = oracle.l2_error(prob.quad, m, [(ph.field.dofnums, 0)], U, truep(loc[..., 0], loc[..., 1])[..., None])
+        errs.append((ep, ev))
+    for (ep0, ev0), (ep1, ev1) in zip(errs[:-1], errs[1:]):
+        assert 3.6 < ev0 / ev1 < 4.4, (ev0, ev1)
+        assert ep0 / ep1 > 2.8, (ep0, ep1)
+
+
+def test_q1_q0_velocity_converges(oracle):
+    """examples/stokes/colliding_flow/q1_q0.jl with the oracle matrix: the (unstable-pressure) Q1-Q0 pair still gives
+    second-order velocities."""
+    ev = []
+    for N in (8, 16, 32):
+        prob, K, U = _solve(oracle, "q1_q0", N)
+        ux, uy, _ = prob.spaces
+        m = prob.meshes[0]
+        loc = oracle.qp_locations(prob.quad, m)
+        ev.append(oracle.l2_error(prob.quad, m, [(ux.field.dofnums, 0), (uy.field.dofnums, 0)], U,
+                                  np.stack([trueux(loc[..., 0], loc[..., 1]), trueuy(loc[..., 0], loc[..., 1])], -1)))
+    assert 3.5 < ev[0] / ev[1] < 4.5 and 3.5 < ev[1] / ev[2] < 4.5, ev
