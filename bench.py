@@ -586,7 +586,7 @@ def main():
         o_colptr = torch.empty(ncl + 1, dtype=torch.int64).pin_memory()
         o_rowval = torch.empty(nnz, dtype=torch.int64).pin_memory()
         o_nzval = torch.empty(nnz, dtype=torch.float64).pin_memory()
-        d2h = 8 * (ncl + 1) + 16 * nnz
+        d2h = 8 * (ncl + 1) + 4 * nnz + 8 * nnz      # colptr Int64, rowval as the device's Int32 (widened in place by host threads), nzval
         t0 = time.perf_counter()
         eng.fetch_pattern_async(o_colptr, o_rowval)
         eng.numeric(params)

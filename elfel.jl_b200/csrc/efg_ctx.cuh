@@ -102,6 +102,8 @@ struct efg_ctx {
     cudaStream_t copy_stream = nullptr;  // device -> host copies that overlap the rest of the symbolic / numeric phase
     cudaEvent_t ev_copy = nullptr;
     bool copy_pending = false;
+    bool widen_failed = false;
+    void *widen = nullptr;               // HostWiden job of a pattern fetch into a host array (efg_hostcopy.cuh)
     DevBuf<int64_t> cstage[2];           // rowval Int32 -> Int64 staging of the copy stream
     int tl_smem_budget = 0;              // dynamic shared memory per CTA that still lets two CTAs share an SM
     int form_req = 0, quad_req = 0;      // form / rule of the symbolic phase in progress

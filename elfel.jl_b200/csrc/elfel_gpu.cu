@@ -6,6 +6,7 @@
 #include "efg_vector.cuh"
 #include "efg_multi.cuh"
 #include "efg_gen.cuh"
+#include "efg_hostcopy.cuh"
 
 #include <cstring>
 #include <cmath>
@@ -236,6 +237,13 @@ static void ingest_index(efg_ctx *ctx, const int64_t *src, int64_t n, int64_t lo
 
 static void wait_copies(efg_ctx *ctx)
 {
+    if (ctx->widen) {               // host threads widening the row indices in the caller's array (efg_hostcopy.cuh)
+        HostWiden *w = static_cast<HostWiden *>(ctx->widen);
+        w->join();
+        if (w->failed != 0) ctx->widen_failed = true;       // reported by the fetch call that waits for the copy
+        delete w;
+        ctx->widen = nullptr;
+    }
     if (ctx->copy_pending && ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         ctx->copy_pending = false;
@@ -679,20 +687,27 @@ static void enqueue_pattern_copy(efg_ctx *ctx, int64_t *colptr, int64_t *rowval)
             ctx->launches++;
             CUDA_CHECK(cudaGetLastError());
         } else {
-            // Int32 0-based -> Int64 1-based in two staging buffers; a chunk's conversion (~0.1 ms) is short against its
-            // copy (~4.7 ms at PCIe Gen5), the event keeps a buffer from being overwritten before its copy has finished
-            const int64_t CH = (int64_t)32 << 20;
-            const int64_t cap = ctx->nnz < CH ? ctx->nnz : CH;
-            for (int b = 0; b < 2; b++)
-                if (ctx->cstage[b].n < (size_t)cap) ctx->cstage[b].alloc(ctx->pool, (size_t)cap);
-            int b = 0;
-            for (int64_t o = 0; o < ctx->nnz; o += CH, b ^= 1) {
-                const int64_t m = ctx->nnz - o < CH ? ctx->nnz - o : CH;
-                k_rowval_out<<<grid_for(m, 256), 256, 0, cs>>>(ctx->rowval.p + o, m, ctx->cstage[b].p);
-                ctx->launches++;
-                CUDA_CHECK(cudaGetLastError());
-                CUDA_CHECK(cudaMemcpyAsync(rowval + o, ctx->cstage[b].p, (size_t)m * sizeof(int64_t), cudaMemcpyDefault, cs));
+            // host destination: the Int32 array crosses the link unwidened into the upper half of the caller's array and
+            // host threads widen it in place while later chunks / the values are still travelling (efg_hostcopy.cuh)
+            wait_copies(ctx);                  // (an earlier fetch into the same array has to be complete)
+            HostWiden *w = new HostWiden();
+            ctx->widen = w;
+            w->dst = rowval; w->nnz = ctx->nnz; w->device = ctx->device;
+            int ndev = 1;
+            if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 1; }
+            w->nthreads = host_widen_threads(ndev);
+            w->cuts = widen_cuts(ctx->nnz, (int64_t)32 << 20);
+            const int nch = (int)w->cuts.size() - 1;
+            char *up = reinterpret_cast<char *>(rowval) + 4 * ctx->nnz;
+            for (int c = 0; c < nch; c++) {
+                const int64_t a = w->cuts[(size_t)c], m = w->cuts[(size_t)c + 1] - a;
+                CUDA_CHECK(cudaMemcpyAsync(up + 4 * a, ctx->rowval.p + a, (size_t)m * sizeof(int32_t), cudaMemcpyDefault, cs));
+                cudaEvent_t e;
+                CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+                w->events.push_back(e);
+                CUDA_CHECK(cudaEventRecord(e, cs));
             }
+            for (int t = 0; t < w->nthreads; t++) w->threads.emplace_back(widen_worker, w, t);
         }
     }
     ctx->copy_pending = true;
@@ -715,6 +730,7 @@ int efg_fetch_csc(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval)
     if (nzval && ctx->nnz > 0) CUDA_CHECK(cudaMemcpyAsync(nzval, ctx->nzval.p, (size_t)ctx->nnz * sizeof(double), cudaMemcpyDefault, ctx->stream));
     CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     wait_copies(ctx);             // also completes an earlier efg_fetch_pattern_async
+    if (ctx->widen_failed) { ctx->widen_failed = false; efg_throw(EFG_ERR_CUDA, "device -> host copy of the row indices failed"); }
     API_END(ctx)
 }
 

@@ -178,7 +178,10 @@ int efg_assemble(efg_ctx *ctx, int form_id, int quad_rule, const double *params,
 int efg_fetch_csc(efg_ctx *ctx, int64_t *colptr, int64_t *rowval, double *nzval);
 /* Starts copying colptr / rowval (either may be NULL) on the ctx's copy stream and returns at once; the copy overlaps
  * whatever the ctx does next (tile phase, numeric kernel).  The arrays are complete -- and must stay valid until --
- * the next efg_fetch_csc call on this ctx (any arguments; it waits for the copy) or efg_destroy. */
+ * the next efg_fetch_csc call on this ctx (any arguments; it waits for the copy) or efg_destroy.
+ * A HOST rowval array receives the device's Int32 indices unwidened (half the PCIe traffic) in its upper half and a few
+ * library threads widen them in place to Int64 1-based while the rest is still travelling (EFG_HOST_THREADS overrides
+ * their number: default min(8, cores / visible GPUs), at least 2); page-locked arrays copy at link speed. */
 int efg_fetch_pattern_async(efg_ctx *ctx, int64_t *colptr, int64_t *rowval);
 /* Device-resident result for a consumer that stays on the GPU (colptr: Int64 1-based,
  * rowval: Int32 0-based, nzval: Float64); valid until the next start/symbolic/destroy. */

@@ -67,3 +67,14 @@ def test_vector_forms_and_iterators_carry_what_the_abi_needs():
         efg.QPIterator(fesp, kind="Simpson")
     it = efg.FEIterator(fesp)
     assert len(it) == 4 and it._bir.shape == (4, 4) and it._geom.shape == (9, 2)
+
+
+def test_in_place_widening_of_the_row_indices(tmp_path):
+    """efg_hostcopy.cuh: the Int32 row indices arrive in the upper half of the caller's Int64 array and several host threads
+    widen them in place -- every entry must come out as in32 + 1 for all sizes / chunkings (CUDA calls stubbed)."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "host_widen_test"
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(root, "elfel.jl_b200", "csrc"),
+                           "-o", str(exe), os.path.join(root, "tests", "host_widen_test.cpp")])
+    subprocess.check_call([str(exe)])
