@@ -103,6 +103,8 @@ struct efg_ctx {
     cudaEvent_t ev_copy = nullptr;
     bool copy_pending = false;
     bool widen_failed = false;
+    std::vector<cudaEvent_t> widen_events;   // one per chunk of a pattern fetch, created once
+    void *mailbox = nullptr, *mailbox_dev = nullptr;    // page-locked mapped words for small read-backs (tl_read)
     void *widen = nullptr;               // HostWiden job of a pattern fetch into a host array (efg_hostcopy.cuh)
     DevBuf<int64_t> cstage[2];           // rowval Int32 -> Int64 staging of the copy stream
     int tl_smem_budget = 0;              // dynamic shared memory per CTA that still lets two CTAs share an SM

@@ -78,7 +78,7 @@ __host__ __device__ static inline int tl_geo_block_bytes(int gk, int nelem, int 
 #define TL_U 4          // light nonzeros in flight per lane
 #endif
 #ifndef TL_MINB
-#define TL_MINB 2       // CTAs per SM the one-thread-per-element kernels are compiled for
+#define TL_MINB 2       // CTAs per SM of the one-thread-per-element kernels with 5-8 local dofs (T6 heat); see TL_BLOCK_NS
 #endif
 #ifndef TL_GEO
 #define TL_GEO 1        // one-thread-per-element forms: the tile's unique node coordinates + 16-bit local connectivity +
@@ -206,15 +206,36 @@ static inline int bits_for(int64_t maxval)
     while (((int64_t)1 << b) <= maxval) b++;
     return b;
 }
+// Small device -> host read-backs (counts, maxima, error flags) go through a page-locked, device-mapped "mailbox": a
+// one-thread kernel stores the words there and the host reads them after the stream has drained.  No copy engine is
+// involved, so a read-back of the symbolic phase never queues behind the chunks of a pattern fetch that is using the
+// device -> host engine at that moment (measured: the tile phase of config 2 took 83 ms instead of 51 ms next to it).
+__global__ void k_mailbox(const unsigned char *__restrict__ src, int nbytes, unsigned char *__restrict__ dst)
+{
+    for (int i = threadIdx.x; i < nbytes; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+static void tl_read_bytes(efg_ctx *ctx, const void *dptr, void *out, int nbytes)
+{
+    if (!ctx->mailbox) {
+        CUDA_CHECK(cudaHostAlloc(&ctx->mailbox, 256, cudaHostAllocMapped));
+        CUDA_CHECK(cudaHostGetDevicePointer(&ctx->mailbox_dev, ctx->mailbox, 0));
+    }
+    if (nbytes > 256) efg_throw(EFG_ERR_INVALID, "internal: mailbox read of %d bytes", nbytes);
+    k_mailbox<<<1, 32, 0, ctx->stream>>>(static_cast<const unsigned char *>(dptr), nbytes, static_cast<unsigned char *>(ctx->mailbox_dev));
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->mailbox, (size_t)nbytes);
+}
 template <class T> static T tl_read(efg_ctx *ctx, const T *dptr)
 {
     T h;
-    CUDA_CHECK(cudaMemcpyAsync(&h, dptr, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    tl_read_bytes(ctx, dptr, &h, (int)sizeof(T));
     return h;
 }
 
 // EFG_TRACE=1: wall-clock per symbolic step on stderr (synchronises; for diagnosing host-side stalls)
+#include <cstring>
 #include <chrono>
 #include <cstdlib>
 struct TlTrace {
@@ -1205,10 +1226,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric_p(const TileDescFull
 // Tile sizes tried in turn (largest first): powers of two and 3*2^k keep space-filling-curve tiles compact
 // (a 256-element T6 tile is a 16 x 8 block of cells).  The first size whose shared-memory footprint lets two
 // CTAs share an SM is used.
-// Threads per CTA (two CTAs per SM): 320 for the one-thread-per-element forms (96 registers/thread, 20 warps/SM:
-// measured faster than 256 x 128 registers for T3/T6/Q4 heat), 256 for the SPLIT forms (measured).
+// Threads per CTA x CTAs per SM of the one-thread-per-element forms, measured (profiles/r2_ab_ctas_per_sm.txt), always 20
+// warps per SM at <= 96 registers (five warps per scheduler partition -- six would cap the kernel at 80 registers):
+//   T3 / Q4 heat (<= 4 local dofs): 5 x 128.  2 x 320 -> 4 x 160 -> 5 x 128: Q4 1.548 -> 1.417 -> 1.378 ms, T3 0.627 -> 0.604
+//     -> 0.599 ms: more CTAs in different phases overlap the compute-bound phase 1 of one with the LSU-bound gather of
+//     another, and their tiles stay large enough (200-370 elements);
+//   T6 heat (6 local dofs): 2 x 320.  4 x 160 gives the same kernel time (2.787 vs 2.809 ms) with tiles of 104 instead of
+//     232 elements, which makes the tile phase of the symbolic part 12 ms slower (more tiles): not worth it end to end.
+// SPLIT forms: 2 CTAs of 352 threads (elasticity) / 256 (Stokes), measured.
 #ifndef TL_BLOCK_NS
 #define TL_BLOCK_NS 320
+#endif
+#ifndef TL_BLOCK_NS4
+#define TL_BLOCK_NS4 128
+#endif
+#ifndef TL_MINB4
+#define TL_MINB4 5
 #endif
 #ifndef TL_BLOCK_SPLIT
 #define TL_BLOCK_SPLIT (TL_PAIRS ? 352 : 256)
@@ -1216,7 +1249,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric_p(const TileDescFull
 #ifndef TL_BLOCK_SPLIT15
 #define TL_BLOCK_SPLIT15 256    // Stokes gen / veclap_alt (15 columns, tiles of 32 elements: 8 pair items per element -> 256 work items)
 #endif
-template <class F> __host__ __device__ constexpr int tl_block() { return F::SPLIT ? (F::ND >= 15 ? TL_BLOCK_SPLIT15 : TL_BLOCK_SPLIT) : (F::ND > 8 ? 256 : TL_BLOCK_NS); }
+template <class F> __host__ __device__ constexpr int tl_block() { return F::SPLIT ? (F::ND >= 15 ? TL_BLOCK_SPLIT15 : TL_BLOCK_SPLIT) : (F::ND > 8 ? 256 : (F::ND <= 4 ? TL_BLOCK_NS4 : TL_BLOCK_NS)); }
+
+template <class F> constexpr int tl_minb() { return (F::SPLIT || F::ND > 8) ? 2 : (F::ND <= 4 ? TL_MINB4 : TL_MINB); }
 
 static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32};
 template <class F> __host__ __device__ constexpr int tl_items_1b() { return TL_PAIRS ? (F::ND + 1) / 2 : F::ND; }
@@ -1227,7 +1262,7 @@ template <class F> static int tl_default_tile_elems()
     const double per_elem = tl_sym<F>() ? tl_srows<F>() * 8.0 * 1.3 + F::ND * F::ND * 2.7 + F::NT * 2.0 : F::ND * F::ND * 10.7 + F::NT * 2.0;
     int te = 32;
     for (int c : TL_TILE_SIZES)
-        if (c * per_elem <= 118.0 * 1024) { te = c; break; }
+        if (c * per_elem <= 118.0 * 1024 * 2 / tl_minb<F>()) { te = c; break; }
     if (F::SPLIT) {
         // phase 1b runs in rounds of tl_block() work items (te*ND staged columns, or te*ceil(ND/2) column pairs): avoid a
         // nearly empty last round
@@ -1252,7 +1287,6 @@ template <class F> static int tl_default_tile_elems()
     return te;
 }
 
-template <class F> constexpr int tl_minb() { return (F::SPLIT || F::ND > 8) ? 2 : TL_MINB; }
 
 template <class F> static const void *tl_numeric_kernel()
 {
@@ -1279,7 +1313,7 @@ template <class F> static int tl_smem_budget(efg_ctx *ctx)
     CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     cudaFuncAttributes fa;
     CUDA_CHECK(cudaFuncGetAttributes(&fa, tl_numeric_kernel<F>()));
-    int b = per_sm / 2 - reserved - (int)fa.sharedSizeBytes;
+    int b = per_sm / tl_minb<F>() - reserved - (int)fa.sharedSizeBytes;
     if (b > optin - (int)fa.sharedSizeBytes) b = optin - (int)fa.sharedSizeBytes;
     return b > 0 ? b : 0;
 }
@@ -1548,8 +1582,7 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
     LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, tl_srows<F>(), tl_sym<F>(), tl_gsz<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, pslot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
            nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
     int32_t hmax[8];
-    CUDA_CHECK(cudaMemcpyAsync(hmax, maxima.p, sizeof hmax, cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    tl_read_bytes(ctx, maxima.p, hmax, (int)sizeof hmax);
     ctx->tl.max_nq = hmax[1] / tl_srows<F>(); ctx->tl.max_nslot = 0; ctx->tl.max_nelem = hmax[3]; ctx->tl.max_nrun = 0;
     ctx->tl.tile_elems = te;
     td->stage_bytes = 0;
@@ -1640,7 +1673,7 @@ template <class F> static void tiled_tiles_search(efg_ctx *ctx)
             tiled_tiles<F>(ctx, te);
             TiledData *td = tiled_data(ctx);
             smem = td->smem_bytes;
-            if (td->complete && (te <= 32 || tl_ctas_per_sm<F>(ctx) >= 2)) {      // two co-resident CTAs overlap each other's phases
+            if (td->complete && (te <= 32 || tl_ctas_per_sm<F>(ctx) >= tl_minb<F>())) {      // co-resident CTAs overlap each other's phases
                 ctx->te_hint = te; ctx->te_hint_form = ctx->form_req; ctx->te_hint_kind = vkind; ctx->te_hint_quad = ctx->quad_req;
                 return;
             }

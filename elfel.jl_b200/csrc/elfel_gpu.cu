@@ -339,6 +339,8 @@ int efg_destroy(efg_ctx *ctx)
     ctx->rfirst.release(); ctx->rlast1.release(); ctx->roff.release(); ctx->scratch.release(); ctx->cstage[0].release(); ctx->cstage[1].release();
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+    for (cudaEvent_t e : ctx->widen_events) cudaEventDestroy(e);
     ctx->pool.destroy();           // the ctx's private arena goes back to the driver; nothing process-global is touched
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evn0); cudaEventDestroy(ctx->evn1); cudaEventDestroy(ctx->ev_tab); cudaEventDestroy(ctx->ev_pattern);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -696,16 +698,19 @@ static void enqueue_pattern_copy(efg_ctx *ctx, int64_t *colptr, int64_t *rowval)
             int ndev = 1;
             if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 1; }
             w->nthreads = host_widen_threads(ndev);
-            w->cuts = widen_cuts(ctx->nnz, (int64_t)32 << 20);
+            w->cuts = widen_cuts(ctx->nnz, (int64_t)16 << 20);      // 64 MB per copy (~1.1 ms on the link)
             const int nch = (int)w->cuts.size() - 1;
             char *up = reinterpret_cast<char *>(rowval) + 4 * ctx->nnz;
             for (int c = 0; c < nch; c++) {
                 const int64_t a = w->cuts[(size_t)c], m = w->cuts[(size_t)c + 1] - a;
                 CUDA_CHECK(cudaMemcpyAsync(up + 4 * a, ctx->rowval.p + a, (size_t)m * sizeof(int32_t), cudaMemcpyDefault, cs));
-                cudaEvent_t e;
-                CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
-                w->events.push_back(e);
-                CUDA_CHECK(cudaEventRecord(e, cs));
+                if ((size_t)c >= ctx->widen_events.size()) {
+                    cudaEvent_t e;
+                    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+                    ctx->widen_events.push_back(e);
+                }
+                w->events.push_back(ctx->widen_events[(size_t)c]);
+                CUDA_CHECK(cudaEventRecord(w->events.back(), cs));
             }
             for (int t = 0; t < w->nthreads; t++) w->threads.emplace_back(widen_worker, w, t);
         }

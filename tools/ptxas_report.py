@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """Build the library with -Xptxas -v and list registers / spills / stack of the numeric kernels.
-usage: python tools/ptxas_report.py [substring filter]   (EFG_LIB / EFG_NVCC_EXTRA respected)"""
+usage: python tools/ptxas_report.py [substring filter]   (EFG_LIB / EFG_NVCC_EXTRA respected; REBUILDS the library)
+       python tools/ptxas_report.py --log build.log [substring filter]   (parses the stderr of an earlier -Xptxas -v build)"""
 import os, re, subprocess, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from elfel_jl_b200 import _lib
-nvcc = "/usr/local/cuda/bin/nvcc"
-extra = os.environ.get("EFG_NVCC_EXTRA", "").split()
-cmd = [nvcc] + _lib.NVCC_FLAGS + extra + ["-Xptxas", "-v", "-o", _lib.SO_PATH, os.path.join(_lib.CSRC, "elfel_gpu.cu")]
-r = subprocess.run(cmd, capture_output=True, text=True)
-if r.returncode:
-    print(r.stderr[-3000:]); sys.exit(1)
+if len(sys.argv) > 2 and sys.argv[1] == "--log":
+    lines = open(sys.argv[2]).read().splitlines()
+    del sys.argv[1:3]
+else:
+    nvcc = "/usr/local/cuda/bin/nvcc"
+    extra = os.environ.get("EFG_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + _lib.NVCC_FLAGS + extra + ["-Xptxas", "-v", "-o", _lib.SO_PATH, os.path.join(_lib.CSRC, "elfel_gpu.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        print(r.stderr[-3000:]); sys.exit(1)
+    lines = r.stderr.splitlines()
 filt = sys.argv[1] if len(sys.argv) > 1 else "k_tl_numeric"
-lines = r.stderr.splitlines()
 dem = {}
 for i, l in enumerate(lines):
     m = re.search(r"Compiling entry function '(\S+)'", l)
