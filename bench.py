@@ -226,6 +226,9 @@ def bench_device_problem(torch, efg, _lib, local, workload, n, steps, warmup, pe
         m.nel_, m.nnodes_ = int(c.shape[0]), int(x.shape[0])
     prob.ndofs_local_ = int(sum(d.numel() for d in dofs))
     eng = efg.Engine(local)
+    te = int(os.environ.get("EFG_BENCH_TE_" + workload.upper(), 0))      # kernel tuning (tools/ab2.py): forced tile size
+    if te:
+        eng.set_option(_lib.OPT_TILE_ELEMS, te)
     stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local))
     for slot, (kind, c, x) in enumerate(meshes):
         eng.set_mesh(slot, kind, c, x)

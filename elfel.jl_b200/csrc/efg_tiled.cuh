@@ -1251,7 +1251,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric_p(const TileDescFull
 #endif
 template <class F> __host__ __device__ constexpr int tl_block() { return F::SPLIT ? (F::ND >= 15 ? TL_BLOCK_SPLIT15 : TL_BLOCK_SPLIT) : (F::ND > 8 ? 256 : (F::ND <= 4 ? TL_BLOCK_NS4 : TL_BLOCK_NS)); }
 
-template <class F> constexpr int tl_minb() { return (F::SPLIT || F::ND > 8) ? 2 : (F::ND <= 4 ? TL_MINB4 : TL_MINB); }
+#ifndef TL_MINB_SPLIT
+#define TL_MINB_SPLIT 2
+#endif
+template <class F> constexpr int tl_minb() { return F::SPLIT ? TL_MINB_SPLIT : (F::ND > 8 ? 2 : (F::ND <= 4 ? TL_MINB4 : TL_MINB)); }
 
 static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32};
 template <class F> __host__ __device__ constexpr int tl_items_1b() { return TL_PAIRS ? (F::ND + 1) / 2 : F::ND; }

@@ -85,10 +85,21 @@ function assemble!(a::SysmatAssemblerGPU, form, elits, qpits)
                                 (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Int64}, Ptr{Float64}),
                                 a.ctx, mslot - 1, _kind(it), length(it), length(it._geom), conn, xy))
             end
-            dof = reinterpret(Int64, it._fld0.dofnums)                 # ncomp x nnodes
-            ncomp = length(eltype(it._fld0.dofnums))
-            _check(a, ccall((:efg_set_space, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Int64, Ptr{Int64}),
-                            a.ctx, slot - 1, mslot - 1, ncomp, length(it._fld0.dofnums), dof))
+            if it._fld2 === nothing                                     # vertex dofs only: FEH1_T3 / FEH1_Q4 / FEH1_T6
+                dof = reinterpret(Int64, it._fld0.dofnums)             # ncomp x nnodes
+                ncomp = length(eltype(it._fld0.dofnums))
+                _check(a, ccall((:efg_set_space, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Int64, Ptr{Int64}),
+                                a.ctx, slot - 1, mslot - 1, ncomp, length(it._fld0.dofnums), dof))
+            else                                                       # a dof on the cell: FEH1_T3_BUBBLE (7), FEL2_T3 / FEL2_Q4 (1)
+                fe = it._fld0 === nothing ? 1 : 7                      # EFG_FE_L2 / EFG_FE_T3_BUBBLE (src/FEIterators.jl:66-79)
+                cdof = reinterpret(Int64, it._fld2.dofnums)            # ncomp x nel
+                ncomp = length(eltype(it._fld2.dofnums))
+                ndof = it._fld0 === nothing ? C_NULL : pointer(reinterpret(Int64, it._fld0.dofnums))
+                nn = it._fld0 === nothing ? 0 : length(it._fld0.dofnums)
+                _check(a, ccall((:efg_set_space_fe, LIB), Cint,
+                                (Ptr{Cvoid}, Cint, Cint, Cint, Cint, Int64, Ptr{Int64}, Int64, Ptr{Int64}),
+                                a.ctx, slot - 1, mslot - 1, fe, ncomp, nn, ndof, length(it._fld2.dofnums), cdof))
+            end
         end
         _check(a, ccall((:efg_start, LIB), Cint, (Ptr{Cvoid}, Int64, Int64), a.ctx, a.nrow, a.ncol))
         p = params(form)

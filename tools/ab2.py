@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """A/B of kernel builds: one process per library (EFG_LIB), all workloads timed in it with device-generated meshes.
-usage: python tools/ab2.py lib_a.so lib_b.so ...   |   internal: python tools/ab2.py --one"""
+usage: python tools/ab2.py lib_a.so lib_b.so:stokes_gen=64,elasticity_t6=112 ...   (name=te forces a tile size)
+internal: python tools/ab2.py --one"""
 import json, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -17,7 +18,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "--one":
         out.append(f"{wl} {r['ms_per_step']:.3f} ms ({r['roofline']['frac']:.3f}) te={r['tile_elems']}")
     print(" | ".join(out), flush=True)
 else:
-    for lib in sys.argv[1:]:
+    for spec in sys.argv[1:]:
+        lib, _, tes = spec.partition(":")
         env = dict(os.environ, EFG_LIB=os.path.abspath(lib))
+        for kv in filter(None, tes.split(",")):
+            env["EFG_BENCH_TE_" + kv.split("=")[0].upper()] = kv.split("=")[1]
         r = subprocess.run([sys.executable, __file__, "--one"], capture_output=True, text=True, env=env)
-        print(f"{os.path.basename(lib):24s}", (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1], flush=True)
+        print(f"{os.path.basename(spec):40s}", (r.stdout.strip().splitlines() or [r.stderr[-300:]])[-1], flush=True)
