@@ -11,9 +11,9 @@ reference interface for this path (meshes, FESpace numbering, iterators, assembl
 There is NO CPU fallback: every assembly call goes through the CUDA library and fails
 loudly if it is missing.
 """
-from .meshes import (Mesh, T3, Q4, T6, T3block, Q4block, T6block, T6block_fast, T3toT6, T6toT3,
+from .meshes import (Mesh, T3, Q4, T6, T4, T4block, T3block, Q4block, T6block, T6block_fast, T3toT6, T6toT3,
                      transform, boundary_nodes, vselect, jitter)
-from .fespaces import (FE, FEH1_T3, FEH1_T6, FEH1_Q4, FEH1_T3_BUBBLE, FEL2_T3, FEL2_Q4, bfun, edofmdim, FEField, FESpace, edofbfnum, edofcompnt,
+from .fespaces import (FE, FEH1_T3, FEH1_T6, FEH1_Q4, FEH1_T3_BUBBLE, FEH1_T4, FEL2_T3, FEL2_Q4, bfun, edofmdim, FEField, FESpace, edofbfnum, edofcompnt,
                        ndofsperel, setebc, numberfreedofs, numberdatadofs, numberdofs, nunknowns,
                        ndofs, highestfreedofnum, highestdatadofnum, gathersysvec, scattersysvec)
 from . import _lib

@@ -35,7 +35,7 @@ EXPORTS = ["efg_create", "efg_destroy", "efg_last_error", "efg_set_option", "efg
            "efg_set_column_ranges", "efg_pattern", "efg_fetch_pattern_async", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version",
            "efg_vec_assemble", "efg_fetch_vec", "efg_device_vec", "efg_spmv", "efg_block_nnz", "efg_fetch_block",
            "efg_qp_locations", "efg_l2_error",
-           "efg_set_space_fe", "efg_gen_mesh", "efg_gen_mesh_corners", "efg_gen_space", "efg_setebc_box", "efg_setebc_nodes", "efg_number_dofs",
+           "efg_set_space_fe", "efg_set_mesh3", "efg_gen_mesh", "efg_gen_mesh_corners", "efg_gen_space", "efg_setebc_box", "efg_setebc_nodes", "efg_number_dofs",
            "efg_fetch_mesh", "efg_fetch_dofnums",
            "efgm_create", "efgm_destroy", "efgm_last_error", "efgm_device_count", "efgm_set_option", "efgm_set_mesh", "efgm_set_space",
            "efgm_start", "efgm_assemble", "efgm_numeric", "efgm_fetch_csc", "efgm_get_stat", "efgm_device_ctx"]
@@ -91,6 +91,7 @@ def load():
     L.efg_synchronize.argtypes = [vp]
     L.efg_set_mesh.argtypes = [vp, ci, ci, i64, i64, vp, vp]
     L.efg_set_space.argtypes = [vp, ci, ci, ci, i64, vp]
+    L.efg_set_mesh3.argtypes = [vp, ci, ci, i64, i64, vp, vp]
     L.efg_set_space_fe.argtypes = [vp, ci, ci, ci, ci, i64, vp, i64, vp]
     L.efg_start.argtypes = [vp, i64, i64]
     L.efg_set_column_range.argtypes = [vp, i64, i64]

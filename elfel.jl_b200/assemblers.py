@@ -210,6 +210,9 @@ class Engine:
     def set_mesh(self, slot, kind, conn, xy):
         """conn: (nel, nen) int64 1-based, xy: (nnodes, 2) float64 -- numpy (host) or torch (host/device)."""
         nel, nnodes = int(conn.shape[0]), int(xy.shape[0])
+        if int(xy.shape[1]) == 3:       # FEH1_T4: xyz (nnodes, 3)
+            self._ck(self.L.efg_set_mesh3(self.h, slot, kind, nel, nnodes, _ptr(conn), _ptr(xy)))
+            return
         self._ck(self.L.efg_set_mesh(self.h, slot, kind, nel, nnodes, _ptr(conn), _ptr(xy)))
 
     def set_space(self, slot, mesh_slot, dofnums, fe=_lib.FE_H1, cell_dofnums=None):

@@ -23,6 +23,8 @@ struct MeshDev {
     int64_t nel = 0, nnodes = 0;
     DevBuf<int32_t> conn;   // nen x nel, 0-based
     DevBuf<double2> xy;     // nnodes
+    DevBuf<double> z;       // nnodes, 3-D meshes only (EFG_T4)
+    int nen() const { return kind == EFG_T4 ? 4 : kind; }
 };
 
 struct SpaceDev {
@@ -140,6 +142,9 @@ template <class Fn> inline bool dispatch_form(int form, int vkind, int nq, Fn &&
         if (vkind == 4 && nq == 1) { fn(HeatForm<4, 1>{}); return true; }
         if (vkind == 4 && nq == 4) { fn(HeatForm<4, 4>{}); return true; }
         if (vkind == 4 && nq == 9) { fn(HeatForm<4, 9>{}); return true; }
+        if (vkind == EFG_T4 && nq == 1) { fn(HeatFormT4<1>{}); return true; }
+        if (vkind == EFG_T4 && nq == 4) { fn(HeatFormT4<4>{}); return true; }
+        if (vkind == EFG_T4 && nq == 5) { fn(HeatFormT4<5>{}); return true; }
         return false;
     case EFG_FORM_ELASTICITY:
         if (vkind == 3 && nq == 1) { fn(ElasticityForm<3, 1>{}); return true; }

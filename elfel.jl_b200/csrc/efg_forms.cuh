@@ -30,7 +30,10 @@ struct QTab {
 // slot 0: T3, 1: Q4, 2: T6 -- tables of the ACTIVE quadrature rule for each element kind
 // (the T3 table at the T6 rule's points is the pressure basis of the Taylor-Hood pair);
 // slot 3: FEH1_T3_BUBBLE (4 functions), slot 4: FEL2_T3 / FEL2_Q4 (one constant function) -- SURVEY 8f row f5.
-#define EFG_NTAB 5
+// slot 5: FEH1_T4 (3-D): weights and N of the tetrahedron rule; its parametric gradients are the constants of
+// src/FElements.jl:380-386 and live in the kernel.
+#define EFG_NTAB 6
+#define EFG_TAB_T4 5
 __constant__ QTab c_tab[EFG_NTAB];
 __constant__ double c_prm[16];
 
@@ -783,5 +786,93 @@ template <bool VECLAP, int PAIR = EFG_PAIR_T6_T3, int NQ_ = 3> struct Stokes3For
                 out[i] = a; out[NV + i] = c;
             }
         }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// K1 heat on FEH1_T4: examples/heat/poisson/t4.jl:31-57 -- the loop of t3.jl in 3-D.
+//   _jac: J = sum_n x_n (outer) g_n, 3x3, node order, first term assigned (src/FElements.jl:148-156), never contracted
+//   Jacobian(Val{3}): src/FElements.jl:138-146 (literal grouping)
+//   bfungrad: g / Jac = (Jac' \ g)' -- StaticArrays' closed-form 3x3 solve: det by dot(col1, cross(col2, col3)), then the
+//   cofactor rows times g, three divisions by the determinant per basis function
+// One thread per element; assembled by the two-pass path (DIM3: the tiled kernel's geometry blocks are 2-D).
+// ------------------------------------------------------------------------------------------------
+template <class F, class = void> struct form_dim3 { static constexpr bool value = false; };
+template <class F> struct form_dim3<F, std::void_t<decltype(F::DIM3)>> { static constexpr bool value = F::DIM3; };
+
+template <int NQ_> struct HeatFormT4 {
+    static constexpr bool DIM3 = true, SYM = true, SPLIT = false;
+    static constexpr int ND = 4, NT = 16, GK = 4, BK = 4, NQ = NQ_, GMESH = 0, NSPACES = 1;
+    __host__ __device__ static constexpr bool mask(int, int) { return true; }
+    __host__ __device__ static constexpr int kidx(int i, int j) { return j * ND + i; }
+    __device__ static void edofs(const DofSrc &s, int64_t e, int32_t (&d)[ND]) {
+#pragma unroll
+        for (int a = 0; a < 4; a++) d[a] = s.dof0[s.conn0[e * 4 + a]];
+    }
+    template <bool S>
+    __device__ __forceinline__ static void geometry(const double (&X)[4], const double (&Y)[4], const double (&Z)[4],
+                                                    double (&g)[4][3], double &det) {
+        const double GP[4][3] = {{-1.0, -1.0, -1.0}, {+1.0, 0.0, 0.0}, {0.0, +1.0, 0.0}, {0.0, 0.0, +1.0}};
+        double J[3][3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) { J[0][k] = __dmul_rn(X[0], GP[0][k]); J[1][k] = __dmul_rn(Y[0], GP[0][k]); J[2][k] = __dmul_rn(Z[0], GP[0][k]); }
+#pragma unroll
+        for (int n = 1; n < 4; n++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                J[0][k] = __dadd_rn(J[0][k], __dmul_rn(X[n], GP[n][k]));
+                J[1][k] = __dadd_rn(J[1][k], __dmul_rn(Y[n], GP[n][k]));
+                J[2][k] = __dadd_rn(J[2][k], __dmul_rn(Z[n], GP[n][k]));
+            }
+        // the determinant and the cofactors cancel like the 2-D Jacobian: individually rounded in every mode
+        auto m2 = [](double a, double b, double c, double d) { return __dsub_rn(__dmul_rn(a, b), __dmul_rn(c, d)); };
+        det = __dadd_rn(__dsub_rn(__dmul_rn(J[0][0], m2(J[1][1], J[2][2], J[2][1], J[1][2])),
+                                  __dmul_rn(J[0][1], m2(J[1][0], J[2][2], J[1][2], J[2][0]))),
+                        __dmul_rn(J[0][2], m2(J[1][0], J[2][1], J[1][1], J[2][0])));
+        double a[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) a[r][c] = J[c][r];
+        const double c0 = m2(a[1][1], a[2][2], a[2][1], a[1][2]), c1 = m2(a[2][1], a[0][2], a[0][1], a[2][2]), c2 = m2(a[0][1], a[1][2], a[1][1], a[0][2]);
+        const double d = __dadd_rn(__dadd_rn(__dmul_rn(a[0][0], c0), __dmul_rn(a[1][0], c1)), __dmul_rn(a[2][0], c2));
+        const double M[3][3] = {{m2(a[1][1], a[2][2], a[1][2], a[2][1]), m2(a[0][2], a[2][1], a[0][1], a[2][2]), m2(a[0][1], a[1][2], a[0][2], a[1][1])},
+                                {m2(a[1][2], a[2][0], a[1][0], a[2][2]), m2(a[0][0], a[2][2], a[0][2], a[2][0]), m2(a[0][2], a[1][0], a[0][0], a[1][2])},
+                                {m2(a[1][0], a[2][1], a[1][1], a[2][0]), m2(a[0][1], a[2][0], a[0][0], a[2][1]), m2(a[0][0], a[1][1], a[0][1], a[1][0])}};
+        const SharedDivisor<S> div(d);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+                g[j][r] = div(__dadd_rn(__dadd_rn(__dmul_rn(M[r][0], GP[j][0]), __dmul_rn(M[r][1], GP[j][1])), __dmul_rn(M[r][2], GP[j][2])));
+    }
+    template <class Emit, int J> __device__ __forceinline__ static void emit_col(const double (&K)[ND][ND], uint32_t m, Emit &emit) {
+        if (m & (1u << J)) {
+            double out[ND];
+#pragma unroll
+            for (int i = 0; i < ND; i++) out[i] = (i <= J) ? K[i][J] : K[J][i];
+            emit.template col<J>(out);
+        }
+    }
+    template <bool S, class Emit>
+    __device__ __forceinline__ static void element3(const double (&X)[4], const double (&Y)[4], const double (&Z)[4], uint32_t m, Emit &emit) {
+        const QTab &t = c_tab[EFG_TAB_T4];
+        const double kappa = c_prm[0];
+        double g[4][3], det;
+        geometry<S>(X, Y, Z, g, det);          // affine element: the same Jacobian at every quadrature point
+        double K[ND][ND];
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const double kJ = fmul<S>(kappa, fmul<S>(det, t.w[q]));
+#pragma unroll
+            for (int j = 0; j < ND; j++)
+#pragma unroll
+                for (int i = 0; i <= j; i++) {
+                    const double dt = fadd<S>(fadd<S>(fmul<S>(g[i][0], g[j][0]), fmul<S>(g[i][1], g[j][1])), fmul<S>(g[i][2], g[j][2]));
+                    const double v = fmul<S>(dt, kJ);
+                    K[i][j] = q == 0 ? v : fadd<S>(K[i][j], v);
+                }
+        }
+        emit_col<Emit, 0>(K, m, emit); emit_col<Emit, 1>(K, m, emit); emit_col<Emit, 2>(K, m, emit); emit_col<Emit, 3>(K, m, emit);
     }
 };

@@ -200,7 +200,7 @@ template <class F> struct KeEmit {
 };
 
 template <class F, bool S>
-__global__ void __launch_bounds__(128) k_tp_elem_matrices(const int32_t *__restrict__ gconn, const double2 *__restrict__ gxy,
+__global__ void __launch_bounds__(128) k_tp_elem_matrices(const int32_t *__restrict__ gconn, const double2 *__restrict__ gxy, const double *__restrict__ gz,
                                                           int64_t nel, double *__restrict__ Ke)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -208,7 +208,14 @@ __global__ void __launch_bounds__(128) k_tp_elem_matrices(const int32_t *__restr
         double X[F::GK], Y[F::GK];
         load_xy<F::GK>(gconn, gxy, e, X, Y);
         KeEmit<F> emit{Ke, e, nel};
-        F::template element<S>(X, Y, 0xffffffffu, emit);
+        if constexpr (form_dim3<F>::value) {        // FEH1_T4: third coordinate plane
+            double Z[F::GK];
+#pragma unroll
+            for (int a = 0; a < F::GK; a++) Z[a] = __ldg(&gz[gconn[e * F::GK + a]]);
+            F::template element3<S>(X, Y, Z, 0xffffffffu, emit);
+        } else {
+            F::template element<S>(X, Y, 0xffffffffu, emit);
+        }
     }
 }
 
@@ -235,9 +242,9 @@ template <class F> void twopass_numeric(efg_ctx *ctx)
     const MeshDev &gm = ctx->mesh[F::GMESH];
     const int64_t nel = ctx->mesh[0].nel;
     if (ctx->opt_strict)
-        LAUNCH(ctx, (k_tp_elem_matrices<F, true>), grid_for(nel, 128, 148 * 32), 128, 0, gm.conn.p, gm.xy.p, nel, ctx->tp.Ke.p);
+        LAUNCH(ctx, (k_tp_elem_matrices<F, true>), grid_for(nel, 128, 148 * 32), 128, 0, gm.conn.p, gm.xy.p, gm.z.p, nel, ctx->tp.Ke.p);
     else
-        LAUNCH(ctx, (k_tp_elem_matrices<F, false>), grid_for(nel, 128, 148 * 32), 128, 0, gm.conn.p, gm.xy.p, nel, ctx->tp.Ke.p);
+        LAUNCH(ctx, (k_tp_elem_matrices<F, false>), grid_for(nel, 128, 148 * 32), 128, 0, gm.conn.p, gm.xy.p, gm.z.p, nel, ctx->tp.Ke.p);
     LAUNCH(ctx, k_tp_gather<F::NT>, grid_for(ctx->nnz, 256, 148 * 32), 256, 0, ctx->tp.perm.p, ctx->tp.seg_start.p,
            ctx->tp.Ke.p, nel, ctx->nnz, ctx->nzval.p);
     ctx->numeric_launches += 2;

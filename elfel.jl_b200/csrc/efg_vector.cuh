@@ -95,6 +95,31 @@ __global__ void __launch_bounds__(256) k_vec_heat_load(const int32_t *__restrict
     }
 }
 
+// the same on FEH1_T4 (examples/heat/poisson/t4.jl:41-55): 3x3 Jacobian, Jacobian(Val{3}) of src/FElements.jl:138-146
+template <int NQ>
+__global__ void __launch_bounds__(256) k_vec_heat_load_t4(const int32_t *__restrict__ conn, const double2 *__restrict__ xy, const double *__restrict__ z,
+                                                          int64_t nel, double Q, double *__restrict__ fe)
+{
+    const QTab &tg = c_tab[EFG_TAB_T4];
+    GRID_STRIDE(e, nel) {
+        double X[4], Y[4], Z[4];
+        load_xy<4>(conn, xy, e, X, Y);
+#pragma unroll
+        for (int a = 0; a < 4; a++) Z[a] = __ldg(&z[conn[e * 4 + a]]);
+        double g[4][3], det;
+        HeatFormT4<NQ>::template geometry<true>(X, Y, Z, g, det);
+        double f[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            const double JxW = __dmul_rn(det, tg.w[q]);
+#pragma unroll
+            for (int j = 0; j < 4; j++) f[j] = __dadd_rn(f[j], __dmul_rn(__dmul_rn(tg.N[q][j], Q), JxW));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) fe[(int64_t)j * nel + e] = f[j];
+    }
+}
+
 // one thread per owned row: val = ((0.0 + c1) + c2) + ... in the reference's order
 template <int NEN>
 __global__ void k_vec_gather(const uint32_t *__restrict__ adjptr, const uint32_t *__restrict__ adj, const double *__restrict__ fe,
@@ -149,6 +174,13 @@ template <int NEN, int NQ> static void vec_numeric_heat(efg_ctx *ctx, VecData *v
     const MeshDev &m = ctx->mesh[0];
     LAUNCH(ctx, (k_vec_heat_load<NEN, NQ>), grid_for(m.nel, 256, (int64_t)148 * 32), 256, 0, m.conn.p, m.xy.p, m.nel, Q, vd->fe.p);
     LAUNCH(ctx, k_vec_gather<NEN>, grid_for(vd->nrl, 256, (int64_t)148 * 32), 256, 0, vd->adjptr.p, vd->adj.p, vd->fe.p, m.nel, vd->nrl, vd->val.p);
+}
+
+template <int NQ> static void vec_numeric_heat_t4(efg_ctx *ctx, VecData *vd, double Q)
+{
+    const MeshDev &m = ctx->mesh[0];
+    LAUNCH(ctx, (k_vec_heat_load_t4<NQ>), grid_for(m.nel, 256, (int64_t)148 * 32), 256, 0, m.conn.p, m.xy.p, m.z.p, m.nel, Q, vd->fe.p);
+    LAUNCH(ctx, k_vec_gather<4>, grid_for(vd->nrl, 256, (int64_t)148 * 32), 256, 0, vd->adjptr.p, vd->adj.p, vd->fe.p, m.nel, vd->nrl, vd->val.p);
 }
 
 // ---- f2: K*x in SparseArrays' accumulation order, and sub-blocks of K -------------------------------------

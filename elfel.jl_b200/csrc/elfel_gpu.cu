@@ -91,15 +91,45 @@ static void basis_tables(int kind, double r, double s, double *N, double (*g)[2]
 }
 
 // Host copy of the tables of (element kind `vkind`, rule): triangles share their rule between T3 and T6.  Returns npts or -1.
+// tetrahedron rules: src/RefShapes.jl:232-259 (weights as literally written); returns npts, pc is npts x 3
+static int quadrature_points_t4(int npts, double (*pc)[3], double *w)
+{
+    if (npts == 1) { pc[0][0] = pc[0][1] = pc[0][2] = 0.25; w[0] = 1.0 / 6.0; return 1; }
+    if (npts == 4) {
+        const double a = 0.13819660, b = 0.58541020;
+        const double P[4][3] = {{a, a, a}, {b, a, a}, {a, b, a}, {a, a, b}};
+        for (int q = 0; q < 4; q++) { for (int k = 0; k < 3; k++) pc[q][k] = P[q][k]; w[q] = 0.041666666666666666667; }
+        return 4;
+    }
+    if (npts == 5) {
+        const double a = 1.0 / 6.0, b = 0.25, c = 0.5, d = -0.8, e = 0.45;
+        const double P[5][3] = {{b, b, b}, {c, a, a}, {a, c, a}, {a, a, c}, {a, a, a}};
+        const double W[5] = {d, e, e, e, e};
+        for (int q = 0; q < 5; q++) { for (int k = 0; k < 3; k++) pc[q][k] = P[q][k]; w[q] = W[q] / 6; }
+        return 5;
+    }
+    return -1;
+}
+
 static int build_tables(int vkind, int rule, QTab (&h)[EFG_NTAB])
 {
     memset(h, 0, sizeof h);
+    if (vkind == EFG_T4) {     // src/FElements.jl:372-378: N = (1 - r - s - t, r, s, t)
+        double pc3[EFG_MAXQ][3], w3[EFG_MAXQ];
+        const int n3 = quadrature_points_t4(rule, pc3, w3);
+        for (int q = 0; q < n3; q++) {
+            h[EFG_TAB_T4].w[q] = w3[q];
+            h[EFG_TAB_T4].N[q][0] = (1 - pc3[q][0] - pc3[q][1] - pc3[q][2]); h[EFG_TAB_T4].N[q][1] = pc3[q][0];
+            h[EFG_TAB_T4].N[q][2] = pc3[q][1]; h[EFG_TAB_T4].N[q][3] = pc3[q][2];
+        }
+        return n3;
+    }
     double pc[EFG_MAXQ][2], w[EFG_MAXQ];
     vkind = kind_shape(vkind);
     const int npts = quadrature_points(vkind, rule, pc, w);
     if (npts < 0 || npts > EFG_MAXQ) return -1;
-    const int kinds[EFG_NTAB] = {EFG_T3, EFG_Q4, EFG_T6, EFG_FE_T3_BUBBLE, EFG_FE_L2};     // c_tab slots
-    for (int k = 0; k < EFG_NTAB; k++) {
+    const int kinds[5] = {EFG_T3, EFG_Q4, EFG_T6, EFG_FE_T3_BUBBLE, EFG_FE_L2};     // c_tab slots 0..4 (slot 5: FEH1_T4, above)
+    for (int k = 0; k < 5; k++) {
         const bool tri = kinds[k] != EFG_Q4, vtri = vkind != EFG_Q4;
         if (tri != vtri && kinds[k] != EFG_FE_L2) continue;
         for (int q = 0; q < npts; q++) {
@@ -112,6 +142,7 @@ static int build_tables(int vkind, int rule, QTab (&h)[EFG_NTAB])
 static int quad_npts(int vkind, int rule)
 {
     double pc[EFG_MAXQ][2], w[EFG_MAXQ];
+    if (vkind == EFG_T4) return (rule == 1 || rule == 4 || rule == 5) ? rule : -1;
     const int npts = quadrature_points(kind_shape(vkind), rule, pc, w);
     return (npts < 0 || npts > EFG_MAXQ) ? -1 : npts;
 }
@@ -334,7 +365,7 @@ int efg_destroy(efg_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     tables_unregister(ctx);
     invalidate(ctx);
-    for (auto &m : ctx->mesh) { m.conn.release(); m.xy.release(); }
+    for (auto &m : ctx->mesh) { m.conn.release(); m.xy.release(); m.z.release(); }
     for (auto &s : ctx->space) { s.dof.release(); s.isdatum.release(); s.cdof.release(); }
     ctx->rfirst.release(); ctx->rlast1.release(); ctx->roff.release(); ctx->scratch.release(); ctx->cstage[0].release(); ctx->cstage[1].release();
     cudaStreamSynchronize(ctx->stream);
@@ -428,8 +459,47 @@ int efg_set_mesh(efg_ctx *ctx, int slot, int kind, int64_t nel, int64_t nnodes, 
     m.kind = kind; m.nel = nel; m.nnodes = nnodes;
     m.conn.alloc(ctx->pool, (size_t)(nel * kind));
     m.xy.alloc(ctx->pool, (size_t)nnodes);
+    m.z.release();
     if (nnodes > 0) CUDA_CHECK(cudaMemcpyAsync(m.xy.p, xy, (size_t)nnodes * sizeof(double2), cudaMemcpyDefault, ctx->stream));
     ingest_index(ctx, conn, nel * kind, 1, nnodes, m.conn.p, "efg_set_mesh: node id");
+    API_END(ctx)
+}
+
+__global__ void k_split_xyz(const double *__restrict__ xyz, int64_t n, double2 *__restrict__ xy, double *__restrict__ z)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        xy[i] = make_double2(xyz[3 * i], xyz[3 * i + 1]);
+        z[i] = xyz[3 * i + 2];
+    }
+}
+
+/* a 3-D mesh (FEH1_T4): xyz is 3 x nnodes */
+int efg_set_mesh3(efg_ctx *ctx, int slot, int kind, int64_t nel, int64_t nnodes, const int64_t *conn, const double *xyz)
+{
+    API_BEGIN(ctx)
+    if (slot != 0) efg_throw(EFG_ERR_INVALID, "a 3-D mesh goes into mesh slot 0");
+    if (kind != EFG_T4) efg_throw(EFG_ERR_INVALID, "unsupported 3-D element kind %d", kind);
+    if (nel < 0 || nnodes < 0 || (nel > 0 && (!conn || !xyz))) efg_throw(EFG_ERR_INVALID, "bad mesh arguments");
+    if (nnodes >= ((int64_t)1 << 31) || nel >= ((int64_t)1 << 29)) efg_throw(EFG_ERR_LIMIT, "mesh too large for 32-bit device indices");
+    invalidate(ctx);
+    MeshDev &m = ctx->mesh[slot];
+    m.kind = kind; m.nel = nel; m.nnodes = nnodes;
+    m.conn.alloc(ctx->pool, (size_t)(nel * 4));
+    m.xy.alloc(ctx->pool, (size_t)nnodes);
+    m.z.alloc(ctx->pool, (size_t)nnodes);
+    if (nnodes > 0) {
+        DevBuf<double> stage;
+        const double *src = xyz;
+        if (!is_device_ptr(xyz)) {
+            stage.alloc(ctx->pool, (size_t)nnodes * 3);
+            CUDA_CHECK(cudaMemcpyAsync(stage.p, xyz, (size_t)nnodes * 3 * sizeof(double), cudaMemcpyDefault, ctx->stream));
+            src = stage.p;
+        }
+        LAUNCH(ctx, k_split_xyz, grid_for(nnodes, 256), 256, 0, src, nnodes, m.xy.p, m.z.p);
+        CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    }
+    ingest_index(ctx, conn, nel * 4, 1, nnodes, m.conn.p, "efg_set_mesh3: node id");
     API_END(ctx)
 }
 
@@ -602,7 +672,10 @@ static void run_symbolic(efg_ctx *ctx, int form, int quad, bool want_tiles)
     try {
     ok = dispatch_form(form, vkind, npts, [&](auto F) {
         using Form = decltype(F);
-        if (path == 2) {
+        if constexpr (form_dim3<Form>::value) {     // 3-D forms (FEH1_T4): the general two-pass path only
+            if (ctx->opt_path == 2) efg_throw(EFG_ERR_LIMIT, "the tiled path has no 3-D elements; use EFG_OPT_PATH 0 or 1");
+            path = 1;
+        } else if (path == 2) {
             try {
                 if (!resume) tiled_pattern<Form>(ctx);
                 if (want_tiles) { tiled_symbolic<Form>(ctx); complete = true; }
@@ -654,7 +727,8 @@ int efg_numeric(efg_ctx *ctx, const double *params, int nparams)
     CUDA_CHECK(cudaEventRecord(ctx->evn0, ctx->stream));
     dispatch_form(ctx->form, ctx->vkind, ctx->nq, [&](auto F) {
         using Form = decltype(F);
-        if (ctx->path == 1) twopass_numeric<Form>(ctx); else tiled_numeric<Form>(ctx);
+        if constexpr (form_dim3<Form>::value) twopass_numeric<Form>(ctx);
+        else { if (ctx->path == 1) twopass_numeric<Form>(ctx); else tiled_numeric<Form>(ctx); }
     });
     CUDA_CHECK(cudaEventRecord(ctx->evn1, ctx->stream));
     ctx->have_values = true;
@@ -776,7 +850,7 @@ int efg_vec_assemble(efg_ctx *ctx, int vform, int quad, const double *params, in
         vd->have_sym = false; vd->have_val = false;
         switch (m0.kind) {
         case EFG_T3: vec_symbolic<3>(ctx, vd, nrow); break;
-        case EFG_Q4: vec_symbolic<4>(ctx, vd, nrow); break;
+        case EFG_Q4: case EFG_T4: vec_symbolic<4>(ctx, vd, nrow); break;
         default: vec_symbolic<6>(ctx, vd, nrow); break;
         }
     }
@@ -792,6 +866,9 @@ int efg_vec_assemble(efg_ctx *ctx, int vform, int quad, const double *params, in
     case 401: vec_numeric_heat<4, 1>(ctx, vd, Q); break;
     case 404: vec_numeric_heat<4, 4>(ctx, vd, Q); break;
     case 409: vec_numeric_heat<4, 9>(ctx, vd, Q); break;
+    case EFG_T4 * 100 + 1: vec_numeric_heat_t4<1>(ctx, vd, Q); break;
+    case EFG_T4 * 100 + 4: vec_numeric_heat_t4<4>(ctx, vd, Q); break;
+    case EFG_T4 * 100 + 5: vec_numeric_heat_t4<5>(ctx, vd, Q); break;
     default: efg_throw(EFG_ERR_INVALID, "the heat load vector is not available for element kind %d with rule %d", m0.kind, quad);
     }
     CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1343,6 +1420,7 @@ int efg_fetch_mesh(efg_ctx *ctx, int slot, int64_t *nel_out, int64_t *nnodes_out
     if (nel_out) *nel_out = m.nel;
     if (nnodes_out) *nnodes_out = m.nnodes;
     if (conn) {
+        if (m.kind == EFG_T4) efg_throw(EFG_ERR_INVALID, "efg_fetch_mesh: 2-D meshes only");
         const int64_t n = m.nel * m.kind;
         DevBuf<int64_t> tmp;
         int64_t *d = conn;

@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from .meshes import Mesh, T3, Q4, T6
+from .meshes import Mesh, T3, Q4, T6, T4
 
 
 class FE:
@@ -22,7 +22,8 @@ class FE:
 
     def __init__(self, kind: int, name: str, ndofperfeat=(1, 0, 0), fe_id: int = 0):
         self.kind, self.name, self.ndofperfeat, self.fe_id = kind, name, tuple(ndofperfeat), fe_id
-        self.nbf = kind * self.ndofperfeat[0] + self.ndofperfeat[2]
+        self.nen = 4 if kind == T4 else kind            # nodes per element
+        self.nbf = self.nen * self.ndofperfeat[0] + self.ndofperfeat[2]
 
     def __repr__(self):
         return self.name
@@ -40,6 +41,11 @@ def FEH1_Q4():
     return FE(Q4, "FEH1_Q4")
 
 
+def FEH1_T4():
+    """src/FElements.jl:359-386 (3-D; examples/heat/poisson/t4.jl)"""
+    return FE(T4, "FEH1_T4")
+
+
 def FEH1_T3_BUBBLE():
     return FE(T3, "FEH1_T3_BUBBLE", (1, 0, 1), 7)
 
@@ -54,6 +60,8 @@ def FEL2_Q4():
 
 def bfun(fe: FE, pc):
     """Scalar basis functions at parametric point pc (src/FElements.jl:239-246, 264-288, 306-320, 341-347, 412-414)."""
+    if fe.kind == T4:
+        return np.array([1 - pc[0] - pc[1] - pc[2], pc[0], pc[1], pc[2]], dtype=np.float64)
     r, s = float(pc[0]), float(pc[1])
     if fe.ndofperfeat[0] == 0:
         return np.array([1.0])
@@ -127,7 +135,7 @@ class FESpace:
         nbf = fe.nbf
         self._edofbfnum = np.repeat(np.arange(1, nbf + 1), nfecopies)
         self._edofcompnt = np.tile(np.arange(1, nfecopies + 1), nbf)
-        nv = fe.kind * fe.ndofperfeat[0] * nfecopies
+        nv = fe.nen * fe.ndofperfeat[0] * nfecopies
         self._edofmdim = np.concatenate([np.zeros(nv, dtype=np.int64), np.full(nbf * nfecopies - nv, 2, dtype=np.int64)])
 
     def fields(self):

@@ -25,6 +25,7 @@ from dataclasses import dataclass
 import numpy as np
 
 T3, Q4, T6 = 3, 4, 6
+T4 = 40      # linear tetrahedron: 4 nodes, 3-D (the C ABI's EFG_T4; every other kind code equals its node count)
 
 
 @dataclass
@@ -33,9 +34,9 @@ class Mesh:
 
     Mirrors what FEIterator caches: ``_bir`` and ``_geom`` (src/FEIterators.jl:55-56)."""
 
-    kind: int            # T3 / Q4 / T6 (= nodes per element)
+    kind: int            # T3 / Q4 / T6 (= nodes per element) or T4
     conn: np.ndarray     # (nel, nen) int64, 1-based
-    xy: np.ndarray       # (nnodes, 2) float64
+    xy: np.ndarray       # (nnodes, 2) float64; (nnodes, 3) for T4
 
     @property
     def nel(self) -> int:
@@ -74,6 +75,32 @@ def T3block(Length, Width, nL, nW, orientation="a") -> Mesh:
     conn[0::2] = t1
     conn[1::2] = t2
     return Mesh(T3, conn + 1, _grid_xy(Length, Width, nL, nW))
+
+
+def T4block(Length, Width, Height, nL, nW, nH) -> Mesh:
+    """Tetrahedral block (examples/heat/poisson/t4.jl:23: T4block(A, A, A, N, N, N)).  Nodes x-fastest, then y, then z, like
+    the 2-D blocks.  MeshSteward's own split of a hexahedral cell into tetrahedra is not vendored ("parity unpinned"; the
+    engine takes the mesh as data): every cell is cut into the six tetrahedra of the Kuhn triangulation around its main
+    diagonal, all positively oriented, cells in i-outer / j / k-inner order."""
+    xs = np.arange(nL + 1, dtype=np.float64) * float(Length) / nL
+    ys = np.arange(nW + 1, dtype=np.float64) * float(Width) / nW
+    zs = np.arange(nH + 1, dtype=np.float64) * float(Height) / nH
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    xyz = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    i, j, k = np.meshgrid(np.arange(nL, dtype=np.int64), np.arange(nW, dtype=np.int64), np.arange(nH, dtype=np.int64), indexing="ij")
+    f = (k.ravel() * (nW + 1) + j.ravel()) * (nL + 1) + i.ravel()
+    sx, sy, sz = 1, nL + 1, (nL + 1) * (nW + 1)
+    tets = []
+    import itertools
+    for perm in itertools.permutations((0, 1, 2)):        # walk from the cell's first node to the opposite one, one axis at a time
+        steps = [(sx, sy, sz)[a] for a in perm]
+        v = [f, f + steps[0], f + steps[0] + steps[1], f + steps[0] + steps[1] + steps[2]]
+        odd = perm in ((0, 2, 1), (2, 1, 0), (1, 0, 2))   # odd permutations are negatively oriented: swap two nodes
+        if odd:
+            v[1], v[2] = v[2], v[1]
+        tets.append(np.stack(v, axis=1))
+    conn = np.stack(tets, axis=1).reshape(-1, 4)
+    return Mesh(T4, conn + 1, xyz)
 
 
 def Q4block(Length, Width, nL, nW) -> Mesh:

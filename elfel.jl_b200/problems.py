@@ -18,9 +18,9 @@ import numpy as np
 from . import _lib
 from .assemblers import (ElasticityForm, HeatForm, StokesGenForm, StokesReddyForm, StokesVeclapAltForm,
                          StokesVeclapForm)
-from .fespaces import (FEH1_Q4, FEH1_T3, FEH1_T6, FEH1_T3_BUBBLE, FEL2_Q4, FEL2_T3, FESpace, ndofs, numberdatadofs, numberdofs,
+from .fespaces import (FEH1_Q4, FEH1_T3, FEH1_T4, FEH1_T6, FEH1_T3_BUBBLE, FEL2_Q4, FEL2_T3, FESpace, ndofs, numberdatadofs, numberdofs,
                        numberfreedofs, setebc)
-from .meshes import Q4, T3, T6, Mesh, Q4block, T3block, T6block, T6block_fast, T6toT3, jitter, transform
+from .meshes import Q4, T3, T4, T6, Mesh, Q4block, T3block, T4block, T6block, T6block_fast, T6toT3, jitter, transform
 
 
 @dataclass
@@ -76,11 +76,22 @@ def heat_problem(kind: int, N: int, perturb: bool = False, kappa: float = 1.0, q
         mesh, fe, q = T6block_fast(1.0, 1.0, N, N), FEH1_T6(), 3
     elif kind == Q4:
         mesh, fe, q = Q4block(1.0, 1.0, N, N), FEH1_Q4(), 2
+    elif kind == T4:      # examples/heat/poisson/t4.jl: unit cube, every boundary node prescribed, default rule (1 point)
+        mesh, fe, q = T4block(1.0, 1.0, 1.0, N, N, N), FEH1_T4(), 1
     else:
         raise ValueError(kind)
-    bnd = _structured_boundary(N, N, kind, mesh)
-    if perturb:
-        mesh = jitter(mesh)
+    if kind == T4:
+        on = ((mesh.xy == 0.0) | (mesh.xy == 1.0)).any(axis=1)
+        bnd = np.nonzero(on)[0] + 1
+        if perturb:       # interior nodes moved by up to 0.2 h
+            rng = np.random.default_rng(20260101)
+            xyz = mesh.xy.copy()
+            xyz[~on] += rng.uniform(-0.2 / N, 0.2 / N, size=(int((~on).sum()), 3))
+            mesh = Mesh(T4, mesh.conn, xyz)
+    else:
+        bnd = _structured_boundary(N, N, kind, mesh)
+        if perturb:
+            mesh = jitter(mesh)
     fesp = FESpace(mesh, fe)
     _setebc_nodes(fesp, bnd)
     numberfreedofs(fesp)

@@ -78,6 +78,9 @@ typedef struct efg_ctx efg_ctx;
 #define EFG_T3 3
 #define EFG_Q4 4
 #define EFG_T6 6
+/* FEH1_T4, the linear tetrahedron (src/FElements.jl:359-386; examples/heat/poisson/t4.jl): 4 nodes, 3-D coordinates.
+ * The only kind code that is not its node count; meshes of this kind are set with efg_set_mesh3. */
+#define EFG_T4 40
 
 /* SURVEY 8f row f5 -- finite elements with a dof on the cell itself, for efg_set_space_fe:
  *   EFG_FE_H1         the H1 element of the space's mesh (FEH1_T3 / FEH1_Q4 / FEH1_T6): vertex dofs only
@@ -137,6 +140,11 @@ int efg_synchronize(efg_ctx *ctx);
 /* mesh_slot 0: the mesh of space 0 (Stokes: velocity mesh); mesh_slot 1: Stokes pressure mesh. */
 int efg_set_mesh(efg_ctx *ctx, int mesh_slot, int elemkind, int64_t nel, int64_t nnodes,
                  const int64_t *conn, const double *xy);
+/* The same for a 3-D mesh (row f5: EFG_T4): conn is 4 x nel, xyz is 3 x nnodes (the "geom" attribute of SVector{3}).
+ * Available for EFG_FORM_HEAT (triangle-style rule = npts 1, 4 or 5 of src/RefShapes.jl:232-259) and EFG_VFORM_HEAT_LOAD;
+ * assembled by the general two-pass path (element matrices to HBM + ordered gather), not by the tiled kernel. */
+int efg_set_mesh3(efg_ctx *ctx, int mesh_slot, int elemkind, int64_t nel, int64_t nnodes,
+                  const int64_t *conn, const double *xyz);
 /* space_slot 0..2, living on mesh_slot; dofnums is ncomp x nnodes. */
 int efg_set_space(efg_ctx *ctx, int space_slot, int mesh_slot, int ncomp, int64_t nnodes,
                   const int64_t *dofnums);

@@ -117,7 +117,7 @@ int efo_quadrature(int elemkind, int rule, double *pc, double *w)
  * T3: src/FElements.jl:239-246; T6: :264-288; Q4: :306-320.  g is nbf x 2 row-major.
  * Julia evaluates `-3+4*r+4*s` as (-3 + 4r) + 4s, `4-8*r-4*s` as (4 - 8r) - 4s.
  * ------------------------------------------------------------------------------------------ */
-int efo_nbf(int elemkind) { return elemkind == EFO_T3B ? 4 : elemkind; }
+int efo_nbf(int elemkind) { return (elemkind == EFO_T3B || elemkind == 40 /* EFO_T4 */) ? 4 : elemkind; }
 /* dofs of an element: on its nodes (dim 0 field) / on the cell (dim 2 field); _storedofs! visits dim 0 first
  * (src/FEIterators.jl:185-194), _number_edofs numbers the basis functions in the same order (src/FESpaces.jl:87-105) */
 static int fe_nodedofs(int fe) { return fe == EFO_T3B ? 3 : (fe == EFO_L2 ? 0 : fe); }
@@ -228,6 +228,72 @@ static void bfungrad(int nbf, const double gp[][2], double J[2][2], double g[][2
     for (int j = 0; j < nbf; j++) {
         g[j][0] = (J[1][1] * gp[j][0] - J[1][0] * gp[j][1]) / d;
         g[j][1] = (J[0][0] * gp[j][1] - J[0][1] * gp[j][0]) / d;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------
+ * FEH1_T4 -- the 3-D member of row f5: examples/heat/poisson/t4.jl (the same integrate! loop as t3.jl on tetrahedra).
+ *   basis / parametric gradients   src/FElements.jl:359-386 (N = (1-r-s-t, r, s, t), constant gradient rows)
+ *   rules                          src/RefShapes.jl:232-259 (_tetrahedron npts 1, 4, 5), weights as literally written
+ *   _jac                           src/FElements.jl:148-156: J = sum_n x_n (outer) g_n, 3x3, node order, first term assigned
+ *   Jacobian(Val{3})               src/FElements.jl:138-146 (the unrolled determinant, literal grouping)
+ *   bfungrad                       src/QPIterators.jl:132-140: g / Jac = (Jac' \ g)' with StaticArrays 1.0.1's closed-form
+ *                                  3x3 solve (src/solve.jl): d = det(a) = dot(col1, cross(col2, col3)), then the cofactor
+ *                                  rows times b, each divided by d (three true divisions).  Not vendored: restated from the
+ *                                  published source, "parity unpinned" below 1e-12 like the 2x2 solve above.
+ * xyz is 3 x nnodes (VecAttrib of SVector{3}).
+ * ------------------------------------------------------------------------------------------ */
+#define EFO_T4 40
+static const double T4_GP[4][3] = {{-1.0, -1.0, -1.0}, {+1.0, 0.0, 0.0}, {0.0, +1.0, 0.0}, {0.0, 0.0, +1.0}};
+
+int efo_quadrature_t4(int npts, double *pc /* npts x 3 */, double *w)
+{
+    if (npts == 1) {
+        pc[0] = 0.25; pc[1] = 0.25; pc[2] = 0.25;
+        w[0] = 1.0 / 6.0;
+        return 1;
+    } else if (npts == 4) {
+        const double a = 0.13819660, b = 0.58541020;
+        const double P[4][3] = {{a, a, a}, {b, a, a}, {a, b, a}, {a, a, b}};
+        for (int q = 0; q < 4; q++) { pc[3 * q] = P[q][0]; pc[3 * q + 1] = P[q][1]; pc[3 * q + 2] = P[q][2]; w[q] = 0.041666666666666666667; }
+        return 4;
+    } else if (npts == 5) { /* Zienkiewicz #3 */
+        const double a = 1.0 / 6.0, b = 0.25, c = 0.5, d = -0.8, e = 0.45;
+        const double P[5][3] = {{b, b, b}, {c, a, a}, {a, c, a}, {a, a, c}, {a, a, a}};
+        const double W[5] = {d, e, e, e, e};
+        for (int q = 0; q < 5; q++) { pc[3 * q] = P[q][0]; pc[3 * q + 1] = P[q][1]; pc[3 * q + 2] = P[q][2]; w[q] = W[q] / 6; }
+        return 5;
+    }
+    return -1;
+}
+void efo_bfun_t4(double r, double s, double t, double *N) { N[0] = (1 - r - s - t); N[1] = r; N[2] = s; N[3] = t; }
+
+static double jacjac3(const double *xyz, const int64_t *nodes, double J[3][3])
+{
+    const double *x = xyz + 3 * (nodes[0] - 1);
+    for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) J[i][k] = x[i] * T4_GP[0][k];
+    for (int n = 1; n < 4; n++) {
+        x = xyz + 3 * (nodes[n] - 1);
+        for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) J[i][k] = J[i][k] + x[i] * T4_GP[n][k];
+    }
+    return (+J[0][0] * (J[1][1] * J[2][2] - J[2][1] * J[1][2])
+            - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0])
+            + J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]));
+}
+static void bfungrad3(double J[3][3], double g[4][3])
+{
+    double a[3][3];                                   /* a = Jac' */
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) a[r][c] = J[c][r];
+    /* det(a): x0, x1, x2 = columns of a; dot(x0, cross(x1, x2)) */
+    const double c0 = a[1][1] * a[2][2] - a[2][1] * a[1][2];
+    const double c1 = a[2][1] * a[0][2] - a[0][1] * a[2][2];
+    const double c2 = a[0][1] * a[1][2] - a[1][1] * a[0][2];
+    const double d = (a[0][0] * c0 + a[1][0] * c1) + a[2][0] * c2;
+    for (int j = 0; j < 4; j++) {
+        const double *b = T4_GP[j];
+        g[j][0] = (((a[1][1] * a[2][2] - a[1][2] * a[2][1]) * b[0] + (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * b[1]) + (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * b[2]) / d;
+        g[j][1] = (((a[1][2] * a[2][0] - a[1][0] * a[2][2]) * b[0] + (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * b[1]) + (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * b[2]) / d;
+        g[j][2] = (((a[1][0] * a[2][1] - a[1][1] * a[2][0]) * b[0] + (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * b[1]) + (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * b[2]) / d;
     }
 }
 
@@ -355,11 +421,36 @@ static int64_t element_loop(coo *ap, int form, int quad, int64_t e0, int64_t e1,
     const int vfe = (x && x->vfe) ? x->vfe : vkind, pfe = (x && x->pfe) ? x->pfe : pkind;
     if ((vfe != vkind || pfe != pkind) && form != EFO_FORM_STOKES_REDDY && form != EFO_FORM_STOKES_VECLAP) return -2;
     qptab vq, pq;
-    if (qptab_init_shape(&vq, vfe, vkind, quad) < 0) return -1;
+    if (vkind == EFO_T4) { if (form != EFO_FORM_HEAT) return -2; vq.nbf = 4; vq.npts = 0; }
+    else if (qptab_init_shape(&vq, vfe, vkind, quad) < 0) return -1;
     if (pconn && qptab_init_shape(&pq, pfe, pkind, quad) < 0) return -1;
     const int nu = vq.nbf;
     double J[2][2];
     double g[MAXBF][2];
+
+    if (form == EFO_FORM_HEAT && vkind == EFO_T4) { /* examples/heat/poisson/t4.jl:31-57; quad = npts of the tetrahedron rule */
+        const double kappa = params[0];
+        double pc3[3 * 5], w3[5], J3[3][3], g3[4][3];
+        const int np3 = efo_quadrature_t4(quad, pc3, w3);
+        if (np3 < 0) return -1;
+        int64_t d[4]; double ke[16];
+        for (int64_t ee = e0; ee < e1; ee++) {
+            const int64_t e = elist ? elist[ee] : ee;
+            const int64_t *nodes = vconn + e * 4;
+            eldofs(nodes, 4, dof0, 1, d);
+            memset(ke, 0, sizeof ke);
+            for (int q = 0; values && q < np3; q++) {
+                double Jd = jacjac3(vxy, nodes, J3);
+                bfungrad3(J3, g3);
+                double JxW = Jd * w3[q];
+                for (int j = 0; j < 4; j++)
+                    for (int i = 0; i < 4; i++)
+                        ke[j * 4 + i] = ke[j * 4 + i] + ((g3[i][0] * g3[j][0] + g3[i][1] * g3[j][1]) + g3[i][2] * g3[j][2]) * (kappa * JxW);
+            }
+            coo_append(&a, 4, 4, d, d, ke);
+        }
+        return a.n;
+    }
 
     if (form == EFO_FORM_HEAT) { /* examples/heat/poisson/t3.jl:41-64 */
         const double kappa = params[0];
@@ -703,6 +794,28 @@ int64_t efo_sparse(int64_t nrow, int64_t ncol, int64_t ntrip,
 int64_t efo_assemble_vec_heat(int quad, int64_t e0, int64_t e1, const int64_t *conn, int kind, const double *xy,
                               const int64_t *dofnums, double Q, int64_t nrow, double *val)
 {
+    if (kind == EFO_T4) { /* examples/heat/poisson/t4.jl:41-55; xy is 3 x nnodes */
+        double pc3[3 * 5], w3[5], J3[3][3], N4[5][4];
+        const int np3 = efo_quadrature_t4(quad, pc3, w3);
+        if (np3 < 0) return -1;
+        for (int q = 0; q < np3; q++) efo_bfun_t4(pc3[3 * q], pc3[3 * q + 1], pc3[3 * q + 2], N4[q]);
+        int64_t d4[4]; double f4[4];
+        for (int64_t i = 0; i < nrow; i++) val[i] = 0.0;
+        for (int64_t e = e0; e < e1; e++) {
+            const int64_t *nodes = conn + e * 4;
+            eldofs(nodes, 4, dofnums, 1, d4);
+            for (int j = 0; j < 4; j++) f4[j] = 0.0;
+            for (int q = 0; q < np3; q++) {
+                double JxW = jacjac3(xy, nodes, J3) * w3[q];
+                for (int j = 0; j < 4; j++) f4[j] = f4[j] + (N4[q][j] * Q) * JxW;
+            }
+            for (int i = 0; i < 4; i++) {
+                if (d4[i] < 1 || d4[i] > nrow) return -2;
+                val[d4[i] - 1] = val[d4[i] - 1] + f4[i];
+            }
+        }
+        return 0;
+    }
     qptab vq;
     if (qptab_init(&vq, kind, quad) < 0) return -1;
     const int nu = kind;

@@ -128,3 +128,63 @@ def test_q1_q0_velocity_converges(oracle):
         ev.append(oracle.l2_error(prob.quad, m, [(ux.field.dofnums, 0), (uy.field.dofnums, 0)], U,
                                   np.stack([trueux(loc[..., 0], loc[..., 1]), trueuy(loc[..., 0], loc[..., 1])], -1)))
     assert 3.5 < ev[0] / ev[1] < 4.5 and 3.5 < ev[1] / ev[2] < 4.5, ev
+
+
+# ---- FEH1_T4 (3-D): examples/heat/poisson/t4.jl ------------------------------------------------------------------------
+def _solve_t4(oracle, N, quad, perturb=False):
+    tempf = lambda x, y, z: 1.0 + x ** 2 + 2.0 * y ** 2          # t4.jl:19, Q = -6, kappa = 1
+    prob = efg.heat_problem(efg.T4, N, perturb, quad=quad)
+    cp, rv, nz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    K = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(prob.ndofs, prob.ndofs))
+    F = oracle.assemble_vec_heat(prob.quad, prob.meshes[0], prob.spaces[0].field.dofnums, -6.0, prob.ndofs)
+    fs, xyz = prob.spaces[0], prob.meshes[0].xy
+    d = fs.field.isdatum[:, 0]
+    fs.field.dofvals[d, 0] = tempf(xyz[d, 0], xyz[d, 1], xyz[d, 2])
+    T = efg.gathersysvec(fs)
+    nu = efg.nunknowns(fs)
+    KT = K @ T
+    T[:nu] = spl.spsolve(K[:nu, :nu].tocsc(), F[:nu] - KT[:nu])
+    return prob, K, float(np.abs(T[fs.field.dofnums[:, 0] - 1] - tempf(xyz[:, 0], xyz[:, 1], xyz[:, 2])).mean())
+
+
+def test_t4_tables_match_the_reference_known_answers(oracle):
+    # test/test_felements.jl:62-79: FEH1_T4 has vertex dofs only, bfun at the centroid = 1/4 each, constant gradient rows
+    fe = efg.FEH1_T4()
+    assert fe.ndofperfeat == (1, 0, 0) and fe.nbf == 4
+    assert np.allclose(efg.bfun(fe, [0.25, 0.25, 0.25]), [0.25] * 4, rtol=0, atol=1e-16)
+    import ctypes as C
+    L = oracle.lib()
+    pc, w = (C.c_double * 15)(), (C.c_double * 5)()
+    for npts in (1, 4, 5):          # src/RefShapes.jl:232-259: every rule integrates a constant over the unit tetrahedron
+        assert L.efo_quadrature_t4(npts, pc, w) == npts
+        assert abs(sum(w[:npts]) - 1.0 / 6.0) < 1e-15
+    N = (C.c_double * 4)()
+    L.efo_bfun_t4.argtypes = [C.c_double] * 3 + [C.POINTER(C.c_double)]
+    L.efo_bfun_t4(0.25, 0.25, 0.25, N)
+    assert list(N) == [0.25] * 4
+
+
+def test_t4_heat_example_meets_the_reference_correctness_bar(oracle):
+    """examples/heat/poisson/t4.jl:78-87: mean nodal |T - tempf| <= 1e-9 (checkcorrectness) -- with the oracle's K and F on
+    the Kuhn-split block, for the default 1-point rule and the 4- and 5-point rules."""
+    for N, quad in ((4, 1), (7, 1), (5, 4), (5, 5)):
+        prob, K, err = _solve_t4(oracle, N, quad)
+        assert prob.nel == 6 * N ** 3 and prob.ndofs == (N + 1) ** 3
+        assert abs(K - K.T).max() == 0.0                      # bitwise symmetric like the 2-D heat matrices
+        assert err <= 1e-9, (N, quad, err)
+
+
+def test_t4_patch_test_on_a_distorted_mesh(oracle):
+    """A linear temperature field is reproduced to rounding on a jittered tetrahedral mesh (Q = 0): exercises the full 3x3
+    Jacobian / cofactor solve of the restatement, which the axis-aligned block does not."""
+    lin = lambda x, y, z: 1 + 2 * x - 3 * y + 0.5 * z
+    prob = efg.heat_problem(efg.T4, 5, True, quad=4)
+    cp, rv, nz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    K = sp.csc_matrix((nz, rv - 1, cp - 1), shape=(prob.ndofs, prob.ndofs))
+    fs, xyz = prob.spaces[0], prob.meshes[0].xy
+    d = fs.field.isdatum[:, 0]
+    fs.field.dofvals[d, 0] = lin(xyz[d, 0], xyz[d, 1], xyz[d, 2])
+    T = efg.gathersysvec(fs)
+    nu = efg.nunknowns(fs)
+    T[:nu] = spl.spsolve(K[:nu, :nu].tocsc(), -(K @ T)[:nu])
+    assert np.abs(T[fs.field.dofnums[:, 0] - 1] - lin(xyz[:, 0], xyz[:, 1], xyz[:, 2])).max() < 1e-13

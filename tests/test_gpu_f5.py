@@ -116,3 +116,56 @@ def test_p1b_p1_example_end_to_end_on_the_device(oracle):
     ep0 = oracle.l2_error(3, m, [(ph.field.dofnums, 0)], U, truep(loc[..., 0], loc[..., 1])[..., None])
     assert abs(ev - ev0) <= 1e-12 * ev0 and abs(ep - ep0) <= 1e-12 * ep0
     assert ev < 0.25 and ep < 6.0          # N = 16: (5.33, 0.220) with the oracle matrix (tests/test_f5_elements.py)
+
+
+# ---- FEH1_T4 (3-D): examples/heat/poisson/t4.jl, assembled by the two-pass CUDA path -----------------------------------
+@pytest.mark.parametrize("quad", [1, 4, 5])
+@pytest.mark.parametrize("perturb", [False, True], ids=["regular", "jittered"])
+def test_t4_heat_vs_oracle(oracle, quad, perturb):
+    prob = efg.heat_problem(efg.T4, 9, perturb, quad=quad)
+    ocp, orv, onz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    oF = oracle.assemble_vec_heat(prob.quad, prob.meshes[0], prob.spaces[0].field.dofnums, -6.0, prob.ndofs)
+    for strict in (1, 0):
+        eng = efg.Engine(0)
+        eng.set_option(_lib.OPT_STRICT_FP, strict)
+        efg.load_problem(eng, prob)
+        eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+        cp, rv, nz = eng.fetch_csc()
+        assert int(eng.stat(_lib.STAT_PATH)) == _lib.PATH_TWOPASS
+        eng.vec_assemble(_lib.VFORM_HEAT_LOAD, prob.quad, [-6.0], prob.ndofs)
+        F = eng.fetch_vec()
+        eng.close()
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+        assert F.tobytes() == oF.tobytes()                     # the load vector is bit-identical in both modes
+        if strict:
+            assert np.array_equal(nz, onz), f"max |d| = {np.abs(nz - onz).max()}"
+        else:
+            assert np.all(np.abs(nz - onz) <= ATOL + RTOL * np.abs(onz)), f"max |d| = {np.abs(nz - onz).max()}"
+
+
+def test_t4_example_end_to_end_through_the_mirrored_api():
+    """examples/heat/poisson/t4.jl: K and F on the GPU from one shared context, solve on the host, checkcorrectness bar 1e-9."""
+    tempf = lambda x, y, z: 1.0 + x ** 2 + 2.0 * y ** 2
+    N = 12
+    prob = efg.heat_problem(efg.T4, N)
+    fesp, xyz = prob.spaces[0], prob.meshes[0].xy
+    d = fesp.field.isdatum[:, 0]
+    fesp.field.dofvals[d, 0] = tempf(xyz[d, 0], xyz[d, 1], xyz[d, 2])
+    elit, qpit = efg.FEIterator(fesp), efg.QPIterator(fesp, kind="default")
+    am = efg.SysmatAssemblerGPU(0.0)
+    av = efg.SysvecAssemblerGPU(0.0, like=am)
+    efg.start(am, prob.ndofs, prob.ndofs); efg.start(av, prob.ndofs)
+    efg.assemble(am, efg.HeatForm(1.0), elit, qpit)
+    efg.assemble(av, efg.HeatLoadForm(-6.0), elit, qpit)
+    K, F = efg.finish(am).to_scipy(), efg.finish(av)
+    T = efg.gathersysvec(fesp)
+    nu = efg.nunknowns(fesp)
+    KT = efg.mul(am, T)
+    T[:nu] = spl.spsolve(K[:nu, :nu].tocsc(), F[:nu] - KT[:nu])
+    err = np.abs(T[fesp.field.dofnums[:, 0] - 1] - tempf(xyz[:, 0], xyz[:, 1], xyz[:, 2])).mean()
+    assert err <= 1e-9, err
+    with pytest.raises(_lib.EfgError):          # the tiled kernel has no 3-D elements
+        e = efg.Engine(0)
+        e.set_option(_lib.OPT_PATH, _lib.PATH_TILED)
+        efg.load_problem(e, prob)
+        e.assemble(prob.form.form_id, prob.quad, prob.form.params())
