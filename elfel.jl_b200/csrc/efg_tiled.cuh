@@ -99,6 +99,14 @@ template <class F> constexpr bool tl_persist() { return TL_GEO && (F::SPLIT ? TL
 #define TL_GEO_SPLIT 1  // vector forms: phase 1a reads the tile's geometry block too (the block sits behind the shared
                         // geometry/metadata area)
 #endif
+#ifndef TL_GS_ALIAS
+#define TL_GS_ALIAS 1   // vector forms: 1 = the per-element geometry Gs of phase 1 shares its shared-memory area with the gather
+                        // metadata (whose TMA copy can then only be issued after phase 1); 0 = separate areas, the copy is
+                        // issued at tile start like for the scalar forms, at the price of smaller tiles
+#endif
+#ifndef TL_GS_ALIAS15
+#define TL_GS_ALIAS15 1 // the same switch for the 15-dof Stokes forms (their tiles are at the 32-element floor already)
+#endif
 #ifndef TL_PAIRS
 #define TL_PAIRS 1      // vector forms, phase 1b: one thread per node (both dofs' columns) instead of one per column
 #endif
@@ -106,6 +114,7 @@ template <class F> constexpr bool tl_persist() { return TL_GEO && (F::SPLIT ? TL
 #define TL_SYM_STAGE 1  // forms with a bitwise-symmetric element matrix (heat) stage its upper triangle only: ND(ND+1)/2 rows of
                         // one entry per tile element instead of ND rows of one entry per (element, owned column)
 #endif
+template <class F> __host__ __device__ constexpr bool tl_gs_alias() { return F::ND >= 15 ? TL_GS_ALIAS15 : TL_GS_ALIAS; }
 template <class F> __host__ __device__ constexpr bool tl_sym() { return TL_SYM_STAGE && F::SYM && !F::SPLIT; }
 template <class F> __host__ __device__ constexpr int tl_srows() { return tl_sym<F>() ? F::ND * (F::ND + 1) / 2 : F::ND; }
 __host__ __device__ constexpr int tl_tri(int a, int b) { return b * (b + 1) / 2 + a; }      // a <= b
@@ -710,7 +719,7 @@ __global__ void k_tl_tiles_meta0(int ntiles, const int64_t *__restrict__ meta_of
     GRID_STRIDE(T, ntiles) tiles[T].meta0 = meta_off[T];
 }
 
-__global__ void k_tl_tiles_fill(int ntiles, int nd /* stage rows */, bool sym, int gsz, int gk, const int32_t *__restrict__ tnn /* null: no geometry blocks */,
+__global__ void k_tl_tiles_fill(int ntiles, int nd /* stage rows */, bool sym, int gsz, bool gs_alias, int gk, const int32_t *__restrict__ tnn /* null: no geometry blocks */,
                                 int64_t *__restrict__ geo_bytes, const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ tcol_slot,
                                 const int64_t *__restrict__ tcol_gidx, const int64_t *__restrict__ tcol_heavy, const int64_t *__restrict__ telem_ptr,
                                 const int64_t *__restrict__ run_of_k /* exclusive scan of run-head flags */,
@@ -750,7 +759,7 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd /* stage rows */, bool sym, i
         tiles[T] = d;
         meta_bytes[T] = d.meta_bytes;
         geo_bytes[T] = d.geo_bytes;
-        atomicMax(&maxima[0], tl_stage_bytes(nd, d.nqs) + max(tl_geo_bytes(gsz, d.nelem), d.meta_bytes) + d.geo_bytes);
+        atomicMax(&maxima[0], tl_stage_bytes(nd, d.nqs) + (gs_alias ? max(tl_geo_bytes(gsz, d.nelem), d.meta_bytes) : tl_geo_bytes(gsz, d.nelem) + d.meta_bytes) + d.geo_bytes);
         atomicMax(&maxima[1], (int32_t)(((int64_t)q | 1) * nd > 0x7fffffff ? 0x7fffffff : ((int64_t)q | 1) * nd));
         if (d.nslot > 65535) atomicMax(&maxima[1], 0x7fffffff);      // TileHeavy addresses slots with 16 bits
         atomicMax(&maxima[2], d.ncontrib); atomicMax(&maxima[3], d.nelem);
@@ -1033,10 +1042,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     // area, so the TMA copy is issued after phase 1; otherwise it is issued now and lands while phase 1 computes
     unsigned char *smeta = smem_raw + tl_stage_bytes(tl_srows<F>(), td.nqs);
     // geometry block (GEO): txy | conn16 | mask16, behind the metadata area (vector forms: behind the area the metadata shares with Gs)
-    unsigned char *sgeo = smeta + (F::SPLIT ? max(td.meta_bytes, tl_geo_bytes(GSZ, td.nelem)) : td.meta_bytes);
+    constexpr bool LATE_META = F::SPLIT && tl_gs_alias<F>();      // metadata copied in after phase 1 (its area doubles as Gs)
+    unsigned char *sgeo = smeta + (F::SPLIT ? (tl_gs_alias<F>() ? max(td.meta_bytes, tl_geo_bytes(GSZ, td.nelem)) : td.meta_bytes + tl_geo_bytes(GSZ, td.nelem)) : td.meta_bytes);
     if (GEO && tid == 0) tl_bulk_load(tl_smem_addr(sgeo), geo + td.geo0, (uint32_t)td.geo_bytes, barB);   // needed first
-    if (!F::SPLIT && tid == 0) tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
-    if (F::SPLIT) {   // the TMA copy is issued after phase 1 (shared area): pull the block into L2 meanwhile
+    if (!LATE_META && tid == 0) tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
+    if (LATE_META) {   // the TMA copy is issued after phase 1 (shared area): pull the block into L2 meanwhile
         const char *mp = reinterpret_cast<const char *>(meta + td.meta0);
         for (int o = tid * 128; o < td.meta_bytes; o += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(mp + o));
     }
@@ -1068,7 +1078,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     } else {
         // phase 1a: one thread per tile element: Jacobian / JxW / gradients at every quadrature point -> shared memory
         const int ne = td.nelem;
-        double *Gs = reinterpret_cast<double *>(smem_raw + tl_stage_bytes(tl_srows<F>(), nq));   // SoA: Gs[k * ne + le]
+        double *Gs = reinterpret_cast<double *>(smeta + (tl_gs_alias<F>() ? 0 : td.meta_bytes));   // SoA: Gs[k * ne + le]
         const uint16_t *smask;
         if constexpr (GEO) {
             tl_mbar_wait(barB, 0);
@@ -1099,7 +1109,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
 #endif
     }
     __syncthreads();
-    if (F::SPLIT && tid == 0) {
+    if (LATE_META && tid == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of the area are done (barrier above)
         tl_bulk_load(tl_smem_addr(smeta), meta + td.meta0, (uint32_t)td.meta_bytes, barA);
     }
@@ -1226,7 +1236,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric_p(const TileDescFull
 // Tile sizes tried in turn (largest first): powers of two and 3*2^k keep space-filling-curve tiles compact
 // (a 256-element T6 tile is a 16 x 8 block of cells).  The first size whose shared-memory footprint lets two
 // CTAs share an SM is used.
-// Threads per CTA x CTAs per SM of the one-thread-per-element forms, measured (profiles/r2_ab_ctas_per_sm.txt), always 20
+// Threads per CTA x CTAs per SM of the one-thread-per-element forms, measured (profiles/r2_ab_cta_shapes_and_layouts.txt), always 20
 // warps per SM at <= 96 registers (five warps per scheduler partition -- six would cap the kernel at 80 registers):
 //   T3 / Q4 heat (<= 4 local dofs): 5 x 128.  2 x 320 -> 4 x 160 -> 5 x 128: Q4 1.548 -> 1.417 -> 1.378 ms, T3 0.627 -> 0.604
 //     -> 0.599 ms: more CTAs in different phases overlap the compute-bound phase 1 of one with the LSU-bound gather of
@@ -1582,7 +1592,7 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
     CUDA_CHECK(cudaMemsetAsync(mbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     CUDA_CHECK(cudaMemsetAsync(gbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     td->tiles.alloc(pool, (size_t)ntiles);
-    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, tl_srows<F>(), tl_sym<F>(), tl_gsz<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, pslot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
+    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, tl_srows<F>(), tl_sym<F>(), tl_gsz<F>(), tl_gs_alias<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, pslot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
            nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
     int32_t hmax[8];
     tl_read_bytes(ctx, maxima.p, hmax, (int)sizeof hmax);
