@@ -699,6 +699,8 @@ def main():
     # ---- SURVEY 8f rows f1 / f2, timed beside the hot path (heat workloads, one GPU): the load vector of the same
     # integrate! loop and K*T of the examples' solve!, device-resident, CUDA events inside the library ----------
     callers = None
+    st_ntiles, st_tile_elems = int(eng.stat(_lib.STAT_NTILES)), eng.stat(_lib.STAT_TILE_ELEMS)
+    st_dev_bytes = eng.stat(_lib.STAT_DEVICE_BYTES)
     if world == 1 and prob.form.form_id == 1 and not args.no_callers and path == 2:
         m0 = prob.meshes[0]
         nd = int(prob.ndofs)
@@ -729,6 +731,25 @@ def main():
                      "y_checksum": float(yd.sum().item())},
         }
         del xd, yd
+        # K and F from ONE pass (efg_numeric_with_load): a second tiling with room for the element load vector in the stage
+        try:
+            eng.set_option(_lib.OPT_FUSE_LOAD, 1)
+            eng.symbolic(fid, quad)
+            for _ in range(3):
+                eng.numeric_with_load(params, -6.0)
+            tf = []
+            for _ in range(5):
+                eng.numeric_with_load(params, -6.0)
+                eng.synchronize()
+                tf.append(eng.stat(_lib.STAT_NUMERIC_MS))
+            f_ms = float(np.median(tf))
+            callers["fused_matrix_and_load_vector"] = {
+                "what": "efg_numeric_with_load: K and F of one integrate! pass in ONE kernel (fe staged next to ke, gathered through the "
+                        "diagonal nonzeros' contribution lists); compare with numeric + load_vector",
+                "ms": f_ms, "separate_ms": ms_step + v_ms, "extra_ms_over_matrix_only": f_ms - ms_step,
+                "tile_elems": -(-int(m0.nel_) // max(int(eng.stat(_lib.STAT_NTILES)), 1))}
+        except Exception as e:          # noqa: BLE001 -- a record, not the headline
+            callers["fused_matrix_and_load_vector"] = {"error": f"{type(e).__name__}: {e}"}
 
     out = {
         "metric": "elements assembled/s", "value": value, "unit": "elements/s", "n_gpus": world, "steps": args.steps,
@@ -739,15 +760,15 @@ def main():
                    "l2": "working set below 2 x L2: a 252 MB buffer is written between timed launches (each launch has its own event pair)"
                          if small else "inputs larger than L2",
                    "path": {1: "two-pass", 2: "tiled-fused"}[path], "strict_fp": args.strict,
-                   "tile_elems": int(args.tile_elems) or -(-int(prob.meshes[0].nel_) // max(int(eng.stat(_lib.STAT_NTILES)), 1)),
+                   "tile_elems": int(args.tile_elems) or -(-int(prob.meshes[0].nel_) // max(st_ntiles, 1)),
                    "tile_elems_source": "option" if args.tile_elems else "automatic (largest size with two CTAs per SM)", "sfc_order": args.sfc,
-                   "tiles": int(eng.stat(_lib.STAT_NTILES)),
-                   "halo_factor": eng.stat(_lib.STAT_TILE_ELEMS) / max(prob.meshes[0].nel_, 1),
+                   "tiles": st_ntiles,
+                   "halo_factor": st_tile_elems / max(prob.meshes[0].nel_, 1),
                    "rank_elements_incl_shard_halo": int(prob.meshes[0].nel_)},
         "roofline": roofline, "e2e": e2e, "gpu_launches": gpu_launches, "clocks": clocks,
         "phases": {"symbolic_ms": sym_ms, "symbolic_ms_is": "first call of the process", "numeric_ms": ms_step,
                    "value_with_symbolic": nel_global / ((ms_step + sym_ms) / 1e3)},
-        "device_bytes": eng.stat(_lib.STAT_DEVICE_BYTES), "nzval_checksum": checksum, "next_rows": callers,
+        "device_bytes": st_dev_bytes, "nzval_checksum": checksum, "next_rows": callers,
     }
     eng.close()
     del h_mesh, h_dofs, prob

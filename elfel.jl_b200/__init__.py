@@ -20,6 +20,6 @@ from . import _lib
 from ._lib import build, EfgError, ArgumentError
 from .assemblers import (FEIterator, QPIterator, HeatForm, HeatLoadForm, SysvecAssemblerGPU, mul, block, evaluate_error, ElasticityForm, StokesGenForm, StokesReddyForm,
                          StokesVeclapAltForm, StokesVeclapForm, SparseMatrixCSC, Engine, MultiEngine, SysmatAssemblerGPU,
-                         start, assemble, finish)
+                         start, assemble, assemble_both, finish)
 from .problems import (Problem, heat_problem, elasticity_problem, stokes_problem, stokes_f5_problem, plane_stress_D, load_problem,
                        oracle_args)

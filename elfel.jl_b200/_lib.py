@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
 # error codes / constants (mirror of the header)
 OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_INDEX, ERR_STATE, ERR_LIMIT = 0, -1, -2, -3, -4, -5, -6
 FORM_HEAT, FORM_ELASTICITY, FORM_STOKES_GEN, FORM_STOKES_REDDY, FORM_STOKES_VECLAP_ALT, FORM_STOKES_VECLAP = 1, 2, 3, 4, 5, 6
-OPT_PATH, OPT_STRICT_FP, OPT_TILE_ELEMS, OPT_SFC_ORDER = 1, 2, 3, 4
+OPT_PATH, OPT_STRICT_FP, OPT_TILE_ELEMS, OPT_SFC_ORDER, OPT_FUSE_LOAD = 1, 2, 3, 4, 5
 PATH_AUTO, PATH_TWOPASS, PATH_TILED = 0, 1, 2
 (STAT_SYMBOLIC_MS, STAT_NUMERIC_MS, STAT_KERNEL_LAUNCHES, STAT_NUMERIC_LAUNCHES, STAT_DEVICE_BYTES,
  STAT_NTILES, STAT_TILE_ELEMS, STAT_NUMERIC_BYTES, STAT_PATH, STAT_VEC_MS, STAT_SPMV_MS) = range(1, 12)
@@ -32,7 +32,7 @@ FE_H1, FE_L2, FE_T3_BUBBLE = 0, 1, 7     # efg_set_space_fe
 
 EXPORTS = ["efg_create", "efg_destroy", "efg_last_error", "efg_set_option", "efg_get_stat", "efg_get_stream",
            "efg_synchronize", "efg_set_mesh", "efg_set_space", "efg_start", "efg_set_column_range",
-           "efg_set_column_ranges", "efg_pattern", "efg_fetch_pattern_async", "efg_symbolic", "efg_numeric", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version",
+           "efg_set_column_ranges", "efg_pattern", "efg_fetch_pattern_async", "efg_symbolic", "efg_numeric", "efg_numeric_with_load", "efg_assemble", "efg_fetch_csc", "efg_device_csc", "efg_version",
            "efg_vec_assemble", "efg_fetch_vec", "efg_device_vec", "efg_spmv", "efg_block_nnz", "efg_fetch_block",
            "efg_qp_locations", "efg_l2_error",
            "efg_set_space_fe", "efg_set_mesh3", "efg_gen_mesh", "efg_gen_mesh_corners", "efg_gen_space", "efg_setebc_box", "efg_setebc_nodes", "efg_number_dofs",
@@ -91,6 +91,7 @@ def load():
     L.efg_synchronize.argtypes = [vp]
     L.efg_set_mesh.argtypes = [vp, ci, ci, i64, i64, vp, vp]
     L.efg_set_space.argtypes = [vp, ci, ci, ci, i64, vp]
+    L.efg_numeric_with_load.argtypes = [vp, f64p, ci, C.c_double]
     L.efg_set_mesh3.argtypes = [vp, ci, ci, i64, i64, vp, vp]
     L.efg_set_space_fe.argtypes = [vp, ci, ci, ci, ci, i64, vp, i64, vp]
     L.efg_start.argtypes = [vp, i64, i64]

@@ -263,6 +263,12 @@ class Engine:
         p = np.ascontiguousarray(params, dtype=np.float64)
         self._ck(self.L.efg_numeric(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), len(p)))
 
+    def numeric_with_load(self, params, Q):
+        """K and the heat load vector in one pass (efg_numeric_with_load; set OPT_FUSE_LOAD before the symbolic phase)."""
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        self._ck(self.L.efg_numeric_with_load(self.h, p.ctypes.data_as(C.POINTER(C.c_double)), len(p), float(Q)))
+        self.nvec = self.nrow
+
     def assemble(self, form_id, quad, params) -> int:
         nnz = C.c_int64()
         p = np.ascontiguousarray(params, dtype=np.float64)
@@ -545,6 +551,28 @@ def assemble(ass: SysmatAssemblerGPU, form, elits, qpits):
     eng.numeric(form.params())
     ass._assembled = True
     return ass
+
+
+def assemble_both(am: SysmatAssemblerGPU, av: "SysvecAssemblerGPU", form, vform, elit, qpit):
+    """ONE integrate! pass for the matrix and the vector, like the reference's heat loops, which fill ``ke`` and ``fe`` in the
+    same quadrature loop and call ``assemble!(am, ke); assemble!(av, fe)`` per element (examples/heat/poisson/t3.jl:41-64):
+    ``assemble_both(am, av, HeatForm(kappa), HeatLoadForm(Q), elit, qpit)`` then ``finish(am)``, ``finish(av)``.
+    ``av`` must share ``am``'s context (``SysvecAssemblerGPU(0.0, like=am)``).  The fused kernel stages the element load
+    vector next to the element matrix (efg_numeric_with_load); F is bit-identical to the separate ``assemble(av, ...)``."""
+    if av.engine is not am.engine:
+        raise ValueError("assemble_both: the vector assembler must share the matrix assembler's context (like=am)")
+    if not (am._started and av._started):
+        raise _lib.EfgError(_lib.ERR_STATE, "assemble before start")
+    eng = am.engine
+    eng.set_option(_lib.OPT_FUSE_LOAD, 1)
+    _load_spaces(eng, (elit,))
+    eng.start(am.nrow, am.ncol)
+    nnz = eng.pattern(form.form_id, qpit.rule)
+    am._out = (np.empty(am.ncol + 1, dtype=np.int64), np.empty(nnz, dtype=np.int64), np.empty(nnz, dtype=np.float64))
+    eng.fetch_pattern_async(am._out[0], am._out[1])
+    eng.numeric_with_load(form.params(), vform.params()[0])
+    am._assembled = av._assembled = True
+    return am, av
 
 
 def finish(ass):

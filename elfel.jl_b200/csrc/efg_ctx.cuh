@@ -57,6 +57,7 @@ struct Tiled {
     int64_t sum_tile_elems = 0;  // tile elements incl. halo, summed over tiles
     int max_nq = 0, max_nslot = 0, max_nelem = 0, max_nrun = 0;
     int64_t numeric_bytes = 0;
+    bool fused_rows = false;     // the tiling reserves stage rows for the fused load vector (EFG_OPT_FUSE_LOAD)
 };
 
 struct efg_ctx {
@@ -85,6 +86,7 @@ struct efg_ctx {
     int opt_strict = 0;
     int opt_tile_elems = 0;
     int opt_sfc = 1;
+    int opt_fuse_load = 0;
 
     // symbolic state
     bool have_symbolic = false;

@@ -133,6 +133,10 @@ __device__ __forceinline__ void geo_compute(const double (&X)[GK], const double 
 template <class F, class = void> struct form_bslot { static constexpr int value = kind_slot(F::BK); };
 template <class F> struct form_bslot<F, std::void_t<decltype(F::BSLOT)>> { static constexpr int value = F::BSLOT; };
 
+// does the sink of an element worker also take the element load vector (StageEmit<F, true>)?
+template <class E, class = void> struct emit_with_f { static constexpr bool value = false; };
+template <class E> struct emit_with_f<E, std::void_t<decltype(E::WITH_F)>> { static constexpr bool value = E::WITH_F; };
+
 // Generic element driver: all quadrature points' gradients in registers, then the owned columns one
 // by one.  emit.template col<J>(out) receives column J of the element matrix.
 template <class F, bool S, class Emit, int J>
@@ -268,6 +272,30 @@ template <int VK, int NQ_> struct HeatForm {
         }
         if constexpr (Emit::TRI) emit.tri(K, m);
         else emit_cols<Emit>(std::make_integer_sequence<int, ND>{}, K, m, emit);
+        // fused load vector (examples/heat/poisson/t3.jl:57: fe[j] += N[j]*Q*JxW in the same quadrature loop; Q = c_prm[1]):
+        // a second, cheap pass over the quadrature points (Jacobian determinant only), every operation individually rounded
+        // in the reference's order in BOTH FP modes, so the vector is bit-identical to the CPU loop like efg_vec_assemble's
+        if constexpr (emit_with_f<Emit>::value) {
+            const QTab &tg = c_tab[kind_slot(GK)];
+            const double Q = c_prm[1];
+            double f[ND];
+#pragma unroll
+            for (int j = 0; j < ND; j++) f[j] = 0.0;
+#pragma unroll
+            for (int q = 0; q < NQ; q++) {
+                double J00 = __dmul_rn(X[0], tg.gp[q][0][0]), J01 = __dmul_rn(X[0], tg.gp[q][0][1]);
+                double J10 = __dmul_rn(Y[0], tg.gp[q][0][0]), J11 = __dmul_rn(Y[0], tg.gp[q][0][1]);
+#pragma unroll
+                for (int n = 1; n < GK; n++) {
+                    J00 = __dadd_rn(J00, __dmul_rn(X[n], tg.gp[q][n][0])); J01 = __dadd_rn(J01, __dmul_rn(X[n], tg.gp[q][n][1]));
+                    J10 = __dadd_rn(J10, __dmul_rn(Y[n], tg.gp[q][n][0])); J11 = __dadd_rn(J11, __dmul_rn(Y[n], tg.gp[q][n][1]));
+                }
+                const double JxW = __dmul_rn(__dsub_rn(__dmul_rn(J00, J11), __dmul_rn(J10, J01)), tg.w[q]);
+#pragma unroll
+                for (int j = 0; j < ND; j++) f[j] = __dadd_rn(f[j], __dmul_rn(__dmul_rn(tg.N[q][j], Q), JxW));
+            }
+            emit.fvec(f, m);
+        }
     }
 };
 

@@ -117,7 +117,12 @@ template <class F> constexpr bool tl_persist() { return TL_GEO && (F::SPLIT ? TL
 template <class F> __host__ __device__ constexpr bool tl_gs_alias() { return F::ND >= 15 ? TL_GS_ALIAS15 : TL_GS_ALIAS; }
 template <class F> __host__ __device__ constexpr bool tl_sym() { return TL_SYM_STAGE && F::SYM && !F::SPLIT; }
 template <class F> __host__ __device__ constexpr int tl_srows() { return tl_sym<F>() ? F::ND * (F::ND + 1) / 2 : F::ND; }
-__host__ __device__ constexpr int tl_tri(int a, int b) { return b * (b + 1) / 2 + a; }      // a <= b
+// stage row of entry (a, b), a <= b, of an nd x nd upper triangle: the DIAGONAL entries take rows 0 .. nd-1 (a contribution
+// to a diagonal nonzero of the matrix is recognised by its stage index alone: fused load vector), the others follow column by column
+__host__ __device__ constexpr int tl_tri(int a, int b, int nd) { return a == b ? a : nd + b * (b - 1) / 2 + a; }
+// fused load vector (examples/heat/poisson/t3.jl:57: fe[j] += N[j]*Q*JxW in the loop that builds ke):
+// forms that can stage fe next to their element matrix
+template <class F> __host__ __device__ constexpr bool tl_can_fuse() { return TL_SYM_STAGE && F::SYM && !F::SPLIT && F::GK == F::ND && !form_dim3<F>::value; }
 #ifndef TL_VEC_CONN
 #define TL_VEC_CONN 1   // tile connectivity read with 8/16-byte loads (T6: 3 x int2, Q4: 1 x int4) instead of 4-byte loads
 #endif
@@ -386,7 +391,7 @@ __device__ __forceinline__ int tl_column_rows(const uint32_t *__restrict__ adj, 
 template <class F>
 __global__ void k_tl_col_count(const uint32_t *__restrict__ adjptr, const uint32_t *__restrict__ adj, const int32_t *__restrict__ edof,
                                int64_t ncl, uint8_t *__restrict__ colcnt, uint16_t *__restrict__ ccnt, uint8_t *__restrict__ hcnt,
-                               int *__restrict__ err)
+                               int *__restrict__ err, int diag_heavy /* fused load vector: every diagonal nonzero takes the heavy list */)
 {
     GRID_STRIDE(cl, ncl) {
         int32_t rows[TL_CAP];
@@ -395,7 +400,7 @@ __global__ void k_tl_col_count(const uint32_t *__restrict__ adjptr, const uint32
         const int n = tl_column_rows<F, true>(adj, adjptr[cl], adjptr[cl + 1], edof, rows, cnt, nc);
         if (n < 0 || nc > 65535) { *err = 2; colcnt[cl] = 0; ccnt[cl] = 0; hcnt[cl] = 0; continue; }
         int h = 0, hc = 0;
-        for (int t = 0; t < n; t++) if (cnt[t] > TL_LIGHT) { h++; hc += cnt[t]; }
+        for (int t = 0; t < n; t++) if (cnt[t] > TL_LIGHT || (diag_heavy && rows[t] == (int32_t)cl)) { h++; hc += cnt[t] + ((diag_heavy && rows[t] == (int32_t)cl) ? 2 : 0); }      // (+2: the dof, see k_tl_gather_build)
         colcnt[cl] = (uint8_t)n;
         ccnt[cl] = (uint16_t)hc;      // contributions to heavy nonzeros only
         hcnt[cl] = (uint8_t)h;
@@ -626,7 +631,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                                   const uint64_t *__restrict__ telem_key, const int64_t *__restrict__ telem_ptr,
                                   const uint16_t *__restrict__ mask, const uint32_t *__restrict__ newpos,
                                   const TileDescFull *__restrict__ tiles, const int64_t *__restrict__ tcol_slot, const int64_t *__restrict__ tcol_gidx,
-                                  const int64_t *__restrict__ tcol_heavy, unsigned char *__restrict__ meta, int *__restrict__ err)
+                                  const int64_t *__restrict__ tcol_heavy, unsigned char *__restrict__ meta, int *__restrict__ err, int diag_heavy)
 {
     GRID_STRIDE(k, nowned) {
         const uint32_t T = tkeys[k], cl = tcols[k];
@@ -661,11 +666,12 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
         for (int t = 0; t < nr; t++) {
             first[t] = second[t] = TL_PK_NONE;
             off[t] = 0;
+            if (diag_heavy && rowval[r0 + t] == (int32_t)cl) cnt[t] |= 0x8000u;      // forced heavy (the count itself stays below 2^15)
             if (cnt[t] > TL_LIGHT) {
-                if (run + cnt[t] > 65535u) *err = 3;
-                heavy[nh++] = TileHeavy{(uint16_t)(sloc + t), (uint16_t)run, cnt[t], 0};
+                if (run + (cnt[t] & 0x7FFFu) + 2u > 65535u) *err = 3;
+                heavy[nh++] = TileHeavy{(uint16_t)(sloc + t), (uint16_t)run, (uint16_t)(cnt[t] & 0x7FFFu), 0};
                 off[t] = (uint16_t)run;
-                run += cnt[t];
+                run += (cnt[t] & 0x7FFFu) + ((cnt[t] & 0x8000u) ? 2u : 0u);      // a diagonal entry's list ends with its dof (two 16-bit halves)
             }
         }
         // pass B: stage indices, append order (ascending element, column-major inside an element)
@@ -685,7 +691,7 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                 const int32_t r = edof[(int64_t)e * F::ND + i];
                 int l2 = 0, h2 = nr;
                 while (l2 < h2) { const int mid = (l2 + h2) >> 1; if (rowval[r0 + mid] < r) l2 = mid + 1; else h2 = mid; }
-                const uint32_t sidx = tl_sym<F>() ? (uint32_t)tl_tri(i < lj ? i : lj, i < lj ? lj : i) * (uint32_t)td.nqs + le
+                const uint32_t sidx = tl_sym<F>() ? (uint32_t)tl_tri(i < lj ? i : lj, i < lj ? lj : i, F::ND) * (uint32_t)td.nqs + le
                                                   : (uint32_t)i * (uint32_t)td.nqs + q;
                 if (sidx >= 0xFFFEu) *err = 4;
                 if (cnt[l2] > TL_LIGHT) { hidx[off[l2]] = (uint16_t)sidx; off[l2]++; }
@@ -693,8 +699,13 @@ __global__ void k_tl_gather_build(const uint32_t *__restrict__ tkeys, const uint
                 else second[l2] = (uint16_t)sidx;
             }
         }
-        for (int t = 0; t < nr; t++)
+        for (int t = 0; t < nr; t++) {
             pk[t] = cnt[t] > TL_LIGHT ? TL_PK_HEAVY : ((uint32_t)first[t] | ((uint32_t)second[t] << 16));
+            if (cnt[t] & 0x8000u) {      // fused load vector: the dof (= row index) of the diagonal nonzero rides behind its contributions
+                const uint32_t d = (uint32_t)rowval[r0 + t];
+                hidx[off[t]] = (uint16_t)(d & 0xFFFFu); hidx[off[t] + 1] = (uint16_t)(d >> 16);
+            }
+        }
     }
 }
 
@@ -771,15 +782,21 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd /* stage rows */, bool sym, i
 // ---- numeric kernel ---------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t tl_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <class F> struct StageEmit {
+template <class F, bool WF = false> struct StageEmit {
     static constexpr bool TRI = tl_sym<F>();
+    static constexpr bool WITH_F = WF;      // the worker also stages the element load vector (rows srows .. srows+ND-1)
+    __device__ __forceinline__ void fvec(const double (&f)[F::ND], uint32_t mm) {
+#pragma unroll
+        for (int j = 0; j < F::ND; j++)
+            if (mm & (1u << j)) stage[(tl_srows<F>() + j) * nq + le] = f[j];
+    }
     // upper triangle of a bitwise-symmetric element matrix: entry (a, b), a <= b, is staged if column a or column b is owned
     __device__ __forceinline__ void tri(const double (&K)[F::ND][F::ND], uint32_t mm) {
 #pragma unroll
         for (int b = 0; b < F::ND; b++)
 #pragma unroll
             for (int a = 0; a <= b; a++)
-                if (mm & ((1u << a) | (1u << b))) stage[tl_tri(a, b) * nq + le] = K[a][b];
+                if (mm & ((1u << a) | (1u << b))) stage[tl_tri(a, b, F::ND) * nq + le] = K[a][b];
     }
     double *__restrict__ stage;
     const uint16_t *__restrict__ qbase;
@@ -843,7 +860,7 @@ __device__ __noinline__ void tl_element_to_stage(int64_t g, uint32_t le, const i
 }
 
 // Same worker fed from the tile's geometry block in shared memory (TL_GEO)
-template <class F, bool S>
+template <class F, bool S, bool WF = false>
 __device__ __noinline__ void tl_element_to_stage_local(uint32_t le, const uint16_t *__restrict__ c16, const uint16_t *__restrict__ m16,
                                                        const double2 *__restrict__ sxy, double *__restrict__ stage, const uint16_t *__restrict__ qbase, int nq)
 {
@@ -863,7 +880,7 @@ __device__ __noinline__ void tl_element_to_stage_local(uint32_t le, const uint16
     double X[GK], Y[GK];
 #pragma unroll
     for (int a = 0; a < GK; a++) { const double2 p = sxy[nd[a]]; X[a] = p.x; Y[a] = p.y; }
-    StageEmit<F> emit{stage, qbase, (uint32_t)m16[le], le, nq};
+    StageEmit<F, WF> emit{stage, qbase, (uint32_t)m16[le], le, nq};
     F::template element<S>(X, Y, emit.m, emit);
 }
 
@@ -996,27 +1013,47 @@ __device__ __forceinline__ void tl_gather_light(const TileDescFull &td, const do
     }
 }
 // Heavy nonzeros: listed per tile, one per lane (all lanes loop about equally long), left-to-right sum.
-template <int BLOCK>
+// WF (fused load vector): a tiling built with EFG_OPT_FUSE_LOAD lists EVERY diagonal nonzero here.  A heavy entry whose first
+// contribution is a diagonal stage entry (index < fdiag = ND * nqs) is a diagonal nonzero of the matrix; the load-vector entry of
+// its dof (= its row index) sums the fe entries of the same elements in the same order (ascending element = the order
+// assemble!(av, fe) adds them, src/Assemblers.jl:217-223), found foff = srows * nqs further on in the stage.  The light walk
+// above stays exactly the unfused one (a first version detected diagonal slots there and paid a dependent rowval load per row
+// of slots: 5.4 ms instead of 2.8 for T6 heat).
+template <int BLOCK, bool WF = false>
 __device__ __forceinline__ void tl_gather_heavy(const TileDescFull &td, const double *__restrict__ stage, const unsigned char *__restrict__ smeta,
-                                                double *__restrict__ nzval, int tid)
+                                                double *__restrict__ nzval, int tid, uint32_t fdiag = 0, uint32_t foff = 0,
+                                                const int32_t *__restrict__ rowval = nullptr, double *__restrict__ fout = nullptr)
 {
     const uint16_t *hidx = reinterpret_cast<const uint16_t *>(smeta + tl_meta_goff_bytes(td.nslot));
     const int64_t *srow = reinterpret_cast<const int64_t *>(reinterpret_cast<const unsigned char *>(hidx) + tl_meta_gidx_bytes(td.ncontrib));
     const TileHeavy *heavy = reinterpret_cast<const TileHeavy *>(reinterpret_cast<const unsigned char *>(srow) + tl_meta_rows_bytes(td.nslot));
     for (int h = tid; h < td.nheavy; h += BLOCK) {
         const TileHeavy e = heavy[h];
+        const int64_t pos = srow[e.s >> 5] + (e.s & 31);
+        int32_t dof = -1;
+        if constexpr (WF) { if ((uint32_t)hidx[e.o] < fdiag) dof = (int32_t)((uint32_t)hidx[e.o + e.c] | ((uint32_t)hidx[e.o + e.c + 1] << 16)); }
         double acc = stage[hidx[e.o]];
         for (int k = 1; k < (int)e.c; k++) acc = __dadd_rn(acc, stage[hidx[e.o + k]]);
-        nzval[srow[e.s >> 5] + (e.s & 31)] = acc;
+        nzval[pos] = acc;
+        if constexpr (WF) {
+            if (dof >= 0) {
+                double f = stage[hidx[e.o] + foff];
+                for (int k = 1; k < (int)e.c; k++) f = __dadd_rn(f, stage[hidx[e.o + k] + foff]);
+                fout[dof] = f;
+            }
+        }
     }
 }
 
-template <class F, bool S, int BLOCK, int MINB>
+template <class F, bool S, int BLOCK, int MINB, bool WF = false>
 __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *__restrict__ tiles, int ntiles,
                                                             const int32_t *__restrict__ tconn, const uint16_t *__restrict__ tmask,
                                                             const double2 *__restrict__ xy, const unsigned char *__restrict__ meta,
-                                                            double *__restrict__ nzval, int pf_dist, const unsigned char *__restrict__ geo)
+                                                            double *__restrict__ nzval, int pf_dist, const unsigned char *__restrict__ geo,
+                                                            const int32_t *__restrict__ rowval = nullptr, double *__restrict__ fout = nullptr)
 {
+    static_assert(!WF || (tl_can_fuse<F>() && TL_GEO), "fused load vector: symmetric-stage scalar forms on the geometry-block path");
+    constexpr int SROWS = tl_srows<F>() + (WF ? F::ND : 0);      // stage rows (WF: + one row per local dof for fe)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ TileDescFull td;
     __shared__ __align__(8) unsigned long long bar, bar2;
@@ -1040,7 +1077,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     constexpr int GSZ = tl_gsz<F>();
     // SPLIT forms: the per-element geometry of phase 1 and the gather metadata of phase 2 share the same shared-memory
     // area, so the TMA copy is issued after phase 1; otherwise it is issued now and lands while phase 1 computes
-    unsigned char *smeta = smem_raw + tl_stage_bytes(tl_srows<F>(), td.nqs);
+    unsigned char *smeta = smem_raw + tl_stage_bytes(SROWS, td.nqs);
     // geometry block (GEO): txy | conn16 | mask16, behind the metadata area (vector forms: behind the area the metadata shares with Gs)
     constexpr bool LATE_META = F::SPLIT && tl_gs_alias<F>();      // metadata copied in after phase 1 (its area doubles as Gs)
     unsigned char *sgeo = smeta + (F::SPLIT ? (tl_gs_alias<F>() ? max(td.meta_bytes, tl_geo_bytes(GSZ, td.nelem)) : td.meta_bytes + tl_geo_bytes(GSZ, td.nelem)) : td.meta_bytes);
@@ -1060,7 +1097,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
         const double2 *sxy = reinterpret_cast<const double2 *>(sgeo);
         const uint16_t *sc16 = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode));
         const uint16_t *sm16 = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode) + tl_geo_conn_bytes(GK, td.nelem));
-        for (int le = tid; le < td.nelem; le += BLOCK) tl_element_to_stage_local<F, S>((uint32_t)le, sc16, sm16, sxy, stage, td.qbase, nq);
+        for (int le = tid; le < td.nelem; le += BLOCK) tl_element_to_stage_local<F, S, WF>((uint32_t)le, sc16, sm16, sxy, stage, td.qbase, nq);
     } else if constexpr (!F::SPLIT) {
         // phase 1: one thread per tile element: owned columns of the element matrix -> stage
         for (int le = tid; le < td.nelem; le += BLOCK) {
@@ -1116,6 +1153,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
     tl_mbar_wait(barA, 0);
 
     // phase 2: every owned nonzero = left-to-right sum of its contributions (append order), stored once
+    const uint32_t fdiag = (uint32_t)F::ND * (uint32_t)nq, foff = (uint32_t)tl_srows<F>() * (uint32_t)nq;
     tl_gather_light<BLOCK>(td, stage, smeta, nzval, lane, warp);
     // The tile that will occupy a CTA slot about one wave later (pf_dist = CTAs resident on the device): its geometry
     // block (or connectivity) is pulled into L2 at the end of this CTA, so that tile's first load is an L2 hit.  The
@@ -1126,7 +1164,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
         if constexpr (GEO) { pf_elem0 = tiles[tpf].geo0; pf_nelem = tiles[tpf].geo_bytes; }
         else { pf_elem0 = tiles[tpf].elem0; pf_nelem = tiles[tpf].nelem; }
     }
-    tl_gather_heavy<BLOCK>(td, stage, smeta, nzval, tid);
+    tl_gather_heavy<BLOCK, WF>(td, stage, smeta, nzval, tid, fdiag, foff, rowval, fout);
     if constexpr (GEO) {   // pull the geometry block of the tile one wave ahead into L2
         const char *p0 = reinterpret_cast<const char *>(geo + pf_elem0);
         for (int o = tid * 128; o < pf_nelem; o += BLOCK * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + o));
@@ -1301,16 +1339,26 @@ template <class F> static int tl_default_tile_elems()
 }
 
 
-template <class F> static const void *tl_numeric_kernel()
+// stage rows of the tiling being built: the fused load vector (EFG_OPT_FUSE_LOAD at symbolic time) adds one row per local dof
+template <class F> static int tl_stage_rows(const efg_ctx *ctx)
+{
+    if constexpr (tl_can_fuse<F>()) return tl_srows<F>() + (ctx->opt_fuse_load ? F::ND : 0);
+    else return tl_srows<F>();
+}
+template <class F> static const void *tl_numeric_kernel(const efg_ctx *ctx)
 {
     if constexpr (tl_persist<F>()) return (const void *)k_tl_numeric_p<F, false, tl_block<F>(), tl_minb<F>()>;
-    else return (const void *)k_tl_numeric<F, false, tl_block<F>(), tl_minb<F>()>;
+    else {
+        if constexpr (tl_can_fuse<F>() && TL_GEO)
+            if (ctx->opt_fuse_load) return (const void *)k_tl_numeric<F, false, tl_block<F>(), tl_minb<F>(), true>;
+        return (const void *)k_tl_numeric<F, false, tl_block<F>(), tl_minb<F>()>;
+    }
 }
 // CTAs of the numeric kernel that fit an SM with the shared memory the last tile phase asked for
 template <class F> static int tl_ctas_per_sm(efg_ctx *ctx)
 {
     TiledData *td = tiled_data(ctx);
-    const void *kern = tl_numeric_kernel<F>();
+    const void *kern = tl_numeric_kernel<F>(ctx);
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
     int per_sm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tl_block<F>(), (size_t)td->smem_bytes));
@@ -1325,7 +1373,7 @@ template <class F> static int tl_smem_budget(efg_ctx *ctx)
     CUDA_CHECK(cudaDeviceGetAttribute(&reserved, cudaDevAttrReservedSharedMemoryPerBlock, ctx->device));
     CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     cudaFuncAttributes fa;
-    CUDA_CHECK(cudaFuncGetAttributes(&fa, tl_numeric_kernel<F>()));
+    CUDA_CHECK(cudaFuncGetAttributes(&fa, tl_numeric_kernel<F>(ctx)));
     int b = per_sm / tl_minb<F>() - reserved - (int)fa.sharedSizeBytes;
     if (b > optin - (int)fa.sharedSizeBytes) b = optin - (int)fa.sharedSizeBytes;
     return b > 0 ? b : 0;
@@ -1385,7 +1433,7 @@ template <class F> static void tiled_pattern(efg_ctx *ctx)
     CUDA_CHECK(cudaMemsetAsync(sy->colcnt.p, 0, (size_t)ncl + 1, st));
     CUDA_CHECK(cudaMemsetAsync(sy->hcnt.p, 0, (size_t)ncl + 1, st));
     CUDA_CHECK(cudaMemsetAsync(sy->ccnt.p, 0, ((size_t)ncl + 1) * 2, st));
-    LAUNCH(ctx, k_tl_col_count<F>, grid_for(ncl, 128), 128, 0, sy->adjptr.p, sy->adj.p, sy->edof.p, ncl, sy->colcnt.p, sy->ccnt.p, sy->hcnt.p, err.p);
+    LAUNCH(ctx, k_tl_col_count<F>, grid_for(ncl, 128), 128, 0, sy->adjptr.p, sy->adj.p, sy->edof.p, ncl, sy->colcnt.p, sy->ccnt.p, sy->hcnt.p, err.p, (int)(ctx->opt_fuse_load && !ctx->have_range && tl_can_fuse<F>()));
     if (tl_read(ctx, err.p))
         efg_throw(EFG_ERR_LIMIT, "tiled path: a matrix column has more than %d distinct rows (node valence too high); use EFG_OPT_PATH=1", TL_CAP);
     {
@@ -1592,11 +1640,12 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
     CUDA_CHECK(cudaMemsetAsync(mbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     CUDA_CHECK(cudaMemsetAsync(gbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     td->tiles.alloc(pool, (size_t)ntiles);
-    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, tl_srows<F>(), tl_sym<F>(), tl_gsz<F>(), tl_gs_alias<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, pslot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
+    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, tl_stage_rows<F>(ctx), tl_sym<F>(), tl_gsz<F>(), tl_gs_alias<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, pslot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
            nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
     int32_t hmax[8];
     tl_read_bytes(ctx, maxima.p, hmax, (int)sizeof hmax);
-    ctx->tl.max_nq = hmax[1] / tl_srows<F>(); ctx->tl.max_nslot = 0; ctx->tl.max_nelem = hmax[3]; ctx->tl.max_nrun = 0;
+    ctx->tl.max_nq = hmax[1] / tl_stage_rows<F>(ctx);
+    ctx->tl.fused_rows = tl_stage_rows<F>(ctx) != tl_srows<F>(); ctx->tl.max_nslot = 0; ctx->tl.max_nelem = hmax[3]; ctx->tl.max_nrun = 0;
     ctx->tl.tile_elems = te;
     td->stage_bytes = 0;
     td->meta_max = 0;
@@ -1635,7 +1684,7 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
     td->meta.alloc(pool, (size_t)(meta_total > 0 ? meta_total : 16));
     CUDA_CHECK(cudaMemsetAsync(td->meta.p, 0, (size_t)(meta_total > 0 ? meta_total : 16), st));
     LAUNCH(ctx, k_tl_gather_build<F>, grid_for(nowned, 128), 128, 0, tkeys.p, tcols.p, nowned, adjptr_p, adj_p, edof_p, colptr0_p, ctx->rowval.p,
-           telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, pslot.p, tcol_gidx.p, tcol_heavy.p, td->meta.p, err.p);
+           telem_key.p, telem_ptr.p, emask.p, newpos.p, td->tiles.p, pslot.p, tcol_gidx.p, tcol_heavy.p, td->meta.p, err.p, (int)(ctx->opt_fuse_load && !ctx->have_range && tl_can_fuse<F>()));
     LAUNCH(ctx, k_tl_meta_rows, grid_for(nruns, 128), 128, 0, nruns, runs.p, run_firstk.p, tkeys.p, td->tiles.p, td->meta.p);
     const int e2 = tl_read(ctx, err.p);
     if (e2) efg_throw(EFG_ERR_LIMIT, "tiled path: a tile's gather list exceeds 16-bit offsets (%d); lower EFG_OPT_TILE_ELEMS", e2);
@@ -1734,7 +1783,7 @@ template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(
         const int grid = ctx->tl.ntiles;                    // one CTA per tile
         if (grid > 0)
             LAUNCH(ctx, kern, (unsigned)grid, BLOCK, (size_t)td->smem_bytes, td->tiles.p, ctx->tl.ntiles, td->tconn.p, td->tmask.p, gm.xy.p,
-                   td->meta.p, ctx->nzval.p, per_sm * nsm, td->geo.p);
+                   td->meta.p, ctx->nzval.p, per_sm * nsm, td->geo.p, (const int32_t *)nullptr, (double *)nullptr);
     }
     ctx->numeric_launches += 1;
 }
@@ -1746,4 +1795,31 @@ template <class F, bool S> static void tl_launch_numeric(efg_ctx *ctx)
 template <class F> void tiled_numeric(efg_ctx *ctx)
 {
     if (ctx->opt_strict) tl_launch_numeric<F, true>(ctx); else tl_launch_numeric<F, false>(ctx);
+}
+
+// K and the load vector in one pass (efg_numeric_with_load): fout is the nrow-long vector, zeroed by the caller
+template <class F, bool S> static void tl_launch_numeric_fused(efg_ctx *ctx, double *fout)
+{
+    if constexpr (tl_can_fuse<F>() && TL_GEO && !tl_persist<F>()) {
+        TiledData *td = tiled_data(ctx);
+        const MeshDev &gm = ctx->mesh[F::GMESH];
+        constexpr int BLOCK = tl_block<F>(), MINB = tl_minb<F>();
+        int per_sm = 0, nsm = 0;
+        CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+        auto kern = k_tl_numeric<F, S, BLOCK, MINB, true>;
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
+        CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
+        if (per_sm < 1) efg_throw(EFG_ERR_LIMIT, "tiled path: the numeric kernel does not fit on an SM (%d bytes of shared memory)", td->smem_bytes);
+        if (ctx->tl.ntiles > 0)
+            LAUNCH(ctx, kern, (unsigned)ctx->tl.ntiles, BLOCK, (size_t)td->smem_bytes, td->tiles.p, ctx->tl.ntiles, td->tconn.p, td->tmask.p, gm.xy.p,
+                   td->meta.p, ctx->nzval.p, per_sm * nsm, td->geo.p, ctx->rowval.p, fout);
+        ctx->numeric_launches += 1;
+    } else {
+        (void)fout;
+        efg_throw(EFG_ERR_INVALID, "the fused load vector is available for the heat forms on the tiled path");
+    }
+}
+template <class F> void tiled_numeric_fused(efg_ctx *ctx, double *fout)
+{
+    if (ctx->opt_strict) tl_launch_numeric_fused<F, true>(ctx, fout); else tl_launch_numeric_fused<F, false>(ctx, fout);
 }

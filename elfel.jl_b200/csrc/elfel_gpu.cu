@@ -399,6 +399,9 @@ int efg_set_option(efg_ctx *ctx, int option, int64_t value)
     case EFG_OPT_SFC_ORDER:
         if (ctx->opt_sfc != (value ? 1 : 0)) { ctx->opt_sfc = value ? 1 : 0; invalidate(ctx); }
         break;
+    case EFG_OPT_FUSE_LOAD:
+        if (ctx->opt_fuse_load != (value ? 1 : 0)) { ctx->opt_fuse_load = value ? 1 : 0; invalidate(ctx); }
+        break;
     default: efg_throw(EFG_ERR_INVALID, "unknown option %d", option);
     }
     API_END(ctx)
@@ -732,6 +735,41 @@ int efg_numeric(efg_ctx *ctx, const double *params, int nparams)
     });
     CUDA_CHECK(cudaEventRecord(ctx->evn1, ctx->stream));
     ctx->have_values = true;
+    API_END(ctx)
+}
+
+/* K and F of one integrate! pass (heat forms, tiled path): the element load vector is staged next to the element matrix and
+ * gathered through the diagonal nonzeros' contribution lists */
+int efg_numeric_with_load(efg_ctx *ctx, const double *params, int nparams, double Q)
+{
+    API_BEGIN(ctx)
+    if (!ctx->have_symbolic && ctx->have_pattern) run_symbolic(ctx, ctx->form, ctx->quad, true);
+    if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_numeric_with_load before efg_symbolic");
+    if (ctx->form != EFG_FORM_HEAT || ctx->path != 2) efg_throw(EFG_ERR_INVALID, "the fused load vector needs EFG_FORM_HEAT on the tiled path");
+    if (!ctx->tl.fused_rows) efg_throw(EFG_ERR_STATE, "set EFG_OPT_FUSE_LOAD = 1 before the symbolic phase");
+    if (ctx->have_range || ctx->nrow != ctx->ncol) efg_throw(EFG_ERR_INVALID, "the fused load vector needs an unsharded square system");
+    if (!params || nparams != 1) efg_throw(EFG_ERR_INVALID, "form %d takes 1 parameter (kappa)", ctx->form);
+    VecData *vd = vec_get(ctx);
+    const int64_t nrow = ctx->nrow;
+    if (!(vd->nrl == nrow && vd->nrow == nrow && vd->val.n >= (size_t)(nrow > 0 ? nrow : 1))) {
+        vd->have_sym = false;
+        vd->val.alloc(ctx->pool, (size_t)(nrow > 0 ? nrow : 1));
+        vd->nrl = nrow; vd->nrow = nrow;
+    }
+    vd->have_val = false;
+    const double prm[2] = {params[0], Q};
+    TabGuard tabs(ctx, ctx->vkind, ctx->quad, prm, 2);
+    ctx->numeric_launches = 0;
+    CUDA_CHECK(cudaEventRecord(ctx->evn0, ctx->stream));
+    CUDA_CHECK(cudaMemsetAsync(vd->val.p, 0, (size_t)(nrow > 0 ? nrow : 1) * sizeof(double), ctx->stream));    // dofs no element touches
+    dispatch_form(ctx->form, ctx->vkind, ctx->nq, [&](auto F) {
+        using Form = decltype(F);
+        if constexpr (form_dim3<Form>::value) efg_throw(EFG_ERR_INVALID, "the fused load vector is not available for 3-D elements");
+        else tiled_numeric_fused<Form>(ctx, vd->val.p);
+    });
+    CUDA_CHECK(cudaEventRecord(ctx->evn1, ctx->stream));
+    ctx->have_values = true;
+    vd->have_val = true;
     API_END(ctx)
 }
 

@@ -114,6 +114,8 @@ typedef struct efg_ctx efg_ctx;
 #define EFG_OPT_TILE_ELEMS  3 /* elements per tile of the fused kernel (0 = automatic) */
 #define EFG_OPT_SFC_ORDER   4 /* 1 (default) = tiles follow a space-filling-curve order of the
                                  elements, 0 = tiles follow the given element order */
+#define EFG_OPT_FUSE_LOAD   5 /* 1 = the next symbolic phase of a heat form reserves room for the element load vector next
+                                 to the element matrix, so that efg_numeric_with_load can produce K and F in one pass */
 
 /* statistics for efg_get_stat (milliseconds are device times from CUDA events on the ctx stream) */
 #define EFG_STAT_SYMBOLIC_MS      1
@@ -177,6 +179,12 @@ int efg_symbolic(efg_ctx *ctx, int form_id, int quad_rule, int64_t *nnz_out);
 int efg_pattern(efg_ctx *ctx, int form_id, int quad_rule, int64_t *nnz_out);
 /* Numeric phase: element quadrature loop fused with the deterministic scatter -> nzval (device). */
 int efg_numeric(efg_ctx *ctx, const double *params, int nparams);
+/* K and the load vector F of ONE integrate! pass -- the reference's heat loops compute `ke[i,j] += ...` and
+ * `fe[j] += N[j]*Q*JxW` in the same quadrature loop and call assemble!(am, ke); assemble!(av, fe) per element
+ * (examples/heat/poisson/t3.jl:41-64, q4.jl:31-54).  Needs EFG_FORM_HEAT on the tiled path, an unsharded ctx and
+ * EFG_OPT_FUSE_LOAD = 1 at symbolic time; params = [kappa].  F (length nrow; zero for dofs no element touches) is then
+ * read with efg_fetch_vec / efg_device_vec like the result of efg_vec_assemble, and is bit-identical to it. */
+int efg_numeric_with_load(efg_ctx *ctx, const double *params, int nparams, double Q);
 /* symbolic (if not cached) + numeric. */
 int efg_assemble(efg_ctx *ctx, int form_id, int quad_rule, const double *params, int nparams,
                  int64_t *nnz_out);

@@ -187,3 +187,77 @@ def test_reassembly_reuses_tile_size_and_stays_bit_identical(oracle):
     assert np.array_equal(a[0], ocp) and np.array_equal(a[1], orv)
     assert np.all(np.abs(a[2] - onz) <= 1e-14 + 1e-12 * np.abs(onz))
     eng.close()
+
+
+# ---- K and F from ONE pass (efg_numeric_with_load): the element load vector rides in the matrix kernel's stage ----------
+@pytest.mark.parametrize("strict", [0, 1])
+@pytest.mark.parametrize("kind,N,quad", [(efg.T3, 61, 1), (efg.T3, 33, 3), (efg.T6, 47, 3), (efg.T6, 30, 1), (efg.Q4, 53, 2), (efg.Q4, 20, 3)])
+def test_fused_matrix_and_load_vector(oracle, kind, N, quad, strict):
+    prob = efg.heat_problem(kind, N, True, quad=quad)
+    Q = -6.0
+    oF = oracle.assemble_vec_heat(prob.quad, prob.meshes[0], prob.spaces[0].field.dofnums, Q, prob.ndofs)
+    # reference result of the library's own separate paths
+    e0 = efg.Engine(0)
+    e0.set_option(_lib.OPT_STRICT_FP, strict)
+    efg.load_problem(e0, prob)
+    e0.assemble(prob.form.form_id, prob.quad, prob.form.params())
+    cp0, rv0, nz0 = e0.fetch_csc()
+    e0.close()
+    eng = efg.Engine(0)
+    eng.set_option(_lib.OPT_STRICT_FP, strict)
+    eng.set_option(_lib.OPT_FUSE_LOAD, 1)
+    efg.load_problem(eng, prob)
+    eng.symbolic(prob.form.form_id, prob.quad)
+    eng.numeric_with_load(prob.form.params(), Q)
+    cp, rv, nz = eng.fetch_csc()
+    F = eng.fetch_vec()
+    assert np.array_equal(cp, cp0) and np.array_equal(rv, rv0)
+    assert nz.tobytes() == nz0.tobytes()                      # K is the unfused kernel's K bit for bit
+    assert F.tobytes() == oF.tobytes()                        # F is the CPU loop's vector bit for bit, in both FP modes
+    # the plain numeric kernel still runs on the fused tiling, and a fused call can follow it
+    eng.numeric(prob.form.params())
+    assert eng.fetch_csc()[2].tobytes() == nz0.tobytes()
+    eng.numeric_with_load(prob.form.params(), 2.5)
+    assert eng.fetch_vec().tobytes() == oracle.assemble_vec_heat(prob.quad, prob.meshes[0], prob.spaces[0].field.dofnums, 2.5, prob.ndofs).tobytes()
+    eng.close()
+
+
+def test_fused_pass_needs_the_option_and_a_heat_form():
+    prob = efg.heat_problem(efg.T3, 9)
+    eng = efg.Engine(0)
+    efg.load_problem(eng, prob)
+    eng.symbolic(prob.form.form_id, prob.quad)
+    with pytest.raises(_lib.EfgError):           # EFG_OPT_FUSE_LOAD was not set at symbolic time
+        eng.numeric_with_load(prob.form.params(), 1.0)
+    eng.close()
+    pe = efg.elasticity_problem(7)
+    e2 = efg.Engine(0)
+    e2.set_option(_lib.OPT_FUSE_LOAD, 1)
+    efg.load_problem(e2, pe)
+    e2.symbolic(pe.form.form_id, pe.quad)
+    with pytest.raises(_lib.EfgError):
+        e2.numeric_with_load([1.0], 1.0)
+    e2.close()
+
+
+def test_heat_example_with_one_fused_pass(oracle):
+    """examples/heat/poisson/t3.jl end to end: K and F from ONE pass through the mirrored API -> the golden vector of
+    test/test_heat.jl:110 is reproduced by the same solve as in test_heat_examples_end_to_end_through_the_mirrored_api."""
+    import scipy.sparse.linalg as spl
+    prob = efg.heat_problem(efg.T3, 4)
+    fesp = prob.spaces[0]
+    xy = prob.meshes[0].xy
+    tempf = lambda x, y: 1.0 + x ** 2 + 2.0 * y ** 2
+    d = fesp.field.isdatum[:, 0]
+    fesp.field.dofvals[d, 0] = tempf(xy[d, 0], xy[d, 1])
+    elit, qpit = efg.FEIterator(fesp), efg.QPIterator(fesp, kind="default")
+    am = efg.SysmatAssemblerGPU(0.0)
+    av = efg.SysvecAssemblerGPU(0.0, like=am)
+    efg.start(am, prob.ndofs, prob.ndofs); efg.start(av, prob.ndofs)
+    efg.assemble_both(am, av, efg.HeatForm(1.0), efg.HeatLoadForm(-6.0), elit, qpit)
+    K, F = efg.finish(am).to_scipy(), efg.finish(av)
+    T = efg.gathersysvec(fesp)
+    nu = efg.nunknowns(fesp)
+    KT = efg.mul(am, T)
+    T[:nu] = spl.spsolve(K[:nu, :nu].tocsc(), F[:nu] - KT[:nu])
+    assert np.abs(T[fesp.field.dofnums[:, 0] - 1] - tempf(xy[:, 0], xy[:, 1])).max() < 1e-13     # nodally exact (test/test_heat.jl:110)
