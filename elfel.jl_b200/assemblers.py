@@ -482,7 +482,9 @@ class SysmatAssemblerGPU:
 
 class SysvecAssemblerGPU:
     """Selected in place of SysvecAssembler (src/Assemblers.jl:170-232).  ``like=am`` shares the device context of a
-    SysmatAssemblerGPU, so the mesh and dof maps uploaded for the matrix are reused for the vector."""
+    SysmatAssemblerGPU, so the mesh and dof maps uploaded for the matrix are reused for the vector.  Call order on a
+    shared context: ``assemble(am, ...)`` first, then ``assemble(av, ...)`` (a later matrix assembly re-uploads the inputs and
+    drops the vector: fetch it with ``finish(av)`` before) -- or ``assemble_both`` for K and F in one pass."""
 
     def __init__(self, zero: float = 0.0, device: int = 0, like: "SysmatAssemblerGPU | None" = None):
         if not isinstance(zero, float):
@@ -496,9 +498,15 @@ class SysvecAssemblerGPU:
 def _load_spaces(eng, elits, reuse=False):
     """Upload meshes + dof maps.  ``reuse``: skip the upload when this engine was last loaded from exactly these
     objects (the vector half of one integrate! call that follows the matrix half on a shared context)."""
-    token = tuple((id(it.fesp.mesh), id(it._fld0.dofnums) if it._fld0 is not None else 0,
-                   id(it._fld2.dofnums) if it._fld2 is not None else 0) for it in elits)
-    if reuse and getattr(eng, "_loaded", None) == token:
+    # the arrays themselves (strong references, compared by identity): numberfreedofs / numberdatadofs / setebc replace
+    # field.dofnums by a new array, which is then seen as a change; an id() of a freed array could be recycled.  In-place
+    # edits of mesh.xy / dofnums are NOT detected: call assemble(am, ...) again (it always re-uploads) after such edits.
+    token = []
+    for it in elits:
+        token += [it.fesp.mesh.conn, it.fesp.mesh.xy, None if it._fld0 is None else it._fld0.dofnums,
+                  None if it._fld2 is None else it._fld2.dofnums]
+    old = getattr(eng, "_loaded", None)
+    if reuse and old is not None and len(old) == len(token) and all(a is b for a, b in zip(old, token)):
         return
     meshes = []
     for it in elits:
@@ -514,7 +522,7 @@ def _load_spaces(eng, elits, reuse=False):
         cd = None if it._fld2 is None else np.ascontiguousarray(it._fld2.dofnums, dtype=np.int64)
         eng.set_space(slot, mslot, nd, it.fesp.fe.fe_id, cd)
     eng._loaded = token
-    eng._keep = [it for it in elits]      # the ids in the token stay valid while these are alive
+    eng._keep = [it for it in elits]
 
 
 def start(ass, nrow, ncol=None):
