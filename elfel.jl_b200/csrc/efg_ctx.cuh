@@ -24,6 +24,7 @@ struct MeshDev {
     DevBuf<int32_t> conn;   // nen x nel, 0-based
     DevBuf<double2> xy;     // nnodes
     DevBuf<double> z;       // nnodes, 3-D meshes only (EFG_T4)
+    const double *pending_xy = nullptr;   // EFG_OPT_DEFER_XY: the caller's coordinates, not copied yet
     int nen() const { return kind == EFG_T4 ? 4 : kind; }
 };
 
@@ -87,6 +88,7 @@ struct efg_ctx {
     int opt_tile_elems = 0;
     int opt_sfc = 1;
     int opt_fuse_load = 0;
+    int opt_defer_xy = 0;
 
     // symbolic state
     bool have_symbolic = false;
@@ -107,7 +109,9 @@ struct efg_ctx {
     cudaEvent_t ev_copy = nullptr;
     bool copy_pending = false;
     bool widen_failed = false;
-    std::vector<cudaEvent_t> widen_events;   // one per chunk of a pattern fetch, created once
+    cudaStream_t in_stream = nullptr;        // deferred coordinate copies (overlap the pattern kernels)
+    cudaEvent_t ev_xy = nullptr;
+    bool xy_in_flight = false;
     void *mailbox = nullptr, *mailbox_dev = nullptr;    // page-locked mapped words for small read-backs (tl_read)
     void *widen = nullptr;               // HostWiden job of a pattern fetch into a host array (efg_hostcopy.cuh)
     DevBuf<int64_t> cstage[2];           // rowval Int32 -> Int64 staging of the copy stream

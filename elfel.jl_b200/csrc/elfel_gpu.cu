@@ -270,6 +270,8 @@ static void wait_copies(efg_ctx *ctx)
 {
     if (ctx->widen) {               // host threads widening the row indices in the caller's array (efg_hostcopy.cuh)
         HostWiden *w = static_cast<HostWiden *>(ctx->widen);
+        if (ctx->copy_stream && cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess) { w->failed = 1; cudaGetLastError(); }
+        w->all_arrived = 1;         // (every chunk is in host memory now, or the copy failed: nobody waits any longer)
         w->join();
         if (w->failed != 0) ctx->widen_failed = true;       // reported by the fetch call that waits for the copy
         delete w;
@@ -311,11 +313,46 @@ __global__ void k_rowval_out(const int32_t *__restrict__ in, int64_t n, int64_t 
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
-#define API_BEGIN(ctx)                                                          \
+// EFG_OPT_DEFER_XY: efg_set_mesh keeps the caller's coordinate pointer instead of copying; the copy is issued on a separate
+// input stream when the symbolic phase starts (it then overlaps the pattern kernels, which read connectivity and dof maps
+// only), or on the main stream by whichever other entry point comes first.
+static void flush_deferred_xy(efg_ctx *ctx, bool overlapped)
+{
+    for (int k = 0; k < 2; k++) {
+        MeshDev &m = ctx->mesh[k];
+        if (!m.pending_xy) continue;
+        const double *src = m.pending_xy;
+        m.pending_xy = nullptr;
+        if (m.nnodes <= 0) continue;
+        if (overlapped) {
+            if (!ctx->in_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->in_stream, cudaStreamNonBlocking));
+            if (!ctx->ev_xy) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_xy, cudaEventDisableTiming));
+            // ordered after whatever the main stream did to the (re-allocated) buffer so far
+            CUDA_CHECK(cudaEventRecord(ctx->ev_xy, ctx->stream));
+            CUDA_CHECK(cudaStreamWaitEvent(ctx->in_stream, ctx->ev_xy, 0));
+            CUDA_CHECK(cudaMemcpyAsync(m.xy.p, src, (size_t)m.nnodes * sizeof(double2), cudaMemcpyDefault, ctx->in_stream));
+            CUDA_CHECK(cudaEventRecord(ctx->ev_xy, ctx->in_stream));
+            ctx->xy_in_flight = true;
+        } else {
+            CUDA_CHECK(cudaMemcpyAsync(m.xy.p, src, (size_t)m.nnodes * sizeof(double2), cudaMemcpyDefault, ctx->stream));
+        }
+    }
+}
+// the main stream's next kernels read coordinates: wait for an overlapped copy
+static void wait_deferred_xy(efg_ctx *ctx)
+{
+    if (ctx->xy_in_flight) { CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_xy, 0)); ctx->xy_in_flight = false; }
+}
+
+#define API_BEGIN_RAW(ctx)                                                      \
     if (!(ctx)) return EFG_ERR_INVALID;                                         \
     try {                                                                       \
         cudaError_t sd__ = cudaSetDevice((ctx)->device);                        \
         if (sd__ != cudaSuccess) efg_throw(EFG_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(sd__));
+/* every entry point that may read coordinates first brings in the ones efg_set_mesh deferred (EFG_OPT_DEFER_XY) */
+#define API_BEGIN(ctx)                                                          \
+    API_BEGIN_RAW(ctx)                                                          \
+        flush_deferred_xy(ctx, false);
 #define API_END(ctx)                                                            \
         return EFG_OK;                                                          \
     } catch (const EfgError &e) {                                               \
@@ -371,7 +408,8 @@ int efg_destroy(efg_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
-    for (cudaEvent_t e : ctx->widen_events) cudaEventDestroy(e);
+    if (ctx->in_stream) { cudaStreamSynchronize(ctx->in_stream); cudaStreamDestroy(ctx->in_stream); }
+    if (ctx->ev_xy) cudaEventDestroy(ctx->ev_xy);
     ctx->pool.destroy();           // the ctx's private arena goes back to the driver; nothing process-global is touched
     cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1); cudaEventDestroy(ctx->evn0); cudaEventDestroy(ctx->evn1); cudaEventDestroy(ctx->ev_tab); cudaEventDestroy(ctx->ev_pattern);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -385,7 +423,7 @@ const char *efg_last_error(const efg_ctx *ctx) { return ctx ? ctx->err.c_str() :
 
 int efg_set_option(efg_ctx *ctx, int option, int64_t value)
 {
-    API_BEGIN(ctx)
+    API_BEGIN_RAW(ctx)
     switch (option) {
     case EFG_OPT_PATH:
         if (value < 0 || value > 2) efg_throw(EFG_ERR_INVALID, "EFG_OPT_PATH must be 0, 1 or 2");
@@ -399,6 +437,7 @@ int efg_set_option(efg_ctx *ctx, int option, int64_t value)
     case EFG_OPT_SFC_ORDER:
         if (ctx->opt_sfc != (value ? 1 : 0)) { ctx->opt_sfc = value ? 1 : 0; invalidate(ctx); }
         break;
+    case EFG_OPT_DEFER_XY: ctx->opt_defer_xy = value ? 1 : 0; break;
     case EFG_OPT_FUSE_LOAD:
         if (ctx->opt_fuse_load != (value ? 1 : 0)) { ctx->opt_fuse_load = value ? 1 : 0; invalidate(ctx); }
         break;
@@ -409,7 +448,7 @@ int efg_set_option(efg_ctx *ctx, int option, int64_t value)
 
 int efg_get_stat(efg_ctx *ctx, int which, double *out)
 {
-    API_BEGIN(ctx)
+    API_BEGIN_RAW(ctx)
     if (!out) efg_throw(EFG_ERR_INVALID, "null output");
     switch (which) {
     case EFG_STAT_SYMBOLIC_MS: *out = ctx->symbolic_ms; break;
@@ -452,7 +491,7 @@ int efg_synchronize(efg_ctx *ctx)
 
 int efg_set_mesh(efg_ctx *ctx, int slot, int kind, int64_t nel, int64_t nnodes, const int64_t *conn, const double *xy)
 {
-    API_BEGIN(ctx)
+    API_BEGIN_RAW(ctx)
     if (slot < 0 || slot > 1) efg_throw(EFG_ERR_INVALID, "mesh_slot must be 0 or 1");
     if (kind != EFG_T3 && kind != EFG_Q4 && kind != EFG_T6) efg_throw(EFG_ERR_INVALID, "unsupported element kind %d", kind);
     if (nel < 0 || nnodes < 0 || (nel > 0 && (!conn || !xy))) efg_throw(EFG_ERR_INVALID, "bad mesh arguments");
@@ -463,7 +502,9 @@ int efg_set_mesh(efg_ctx *ctx, int slot, int kind, int64_t nel, int64_t nnodes, 
     m.conn.alloc(ctx->pool, (size_t)(nel * kind));
     m.xy.alloc(ctx->pool, (size_t)nnodes);
     m.z.release();
-    if (nnodes > 0) CUDA_CHECK(cudaMemcpyAsync(m.xy.p, xy, (size_t)nnodes * sizeof(double2), cudaMemcpyDefault, ctx->stream));
+    m.pending_xy = nullptr;
+    if (ctx->opt_defer_xy && nnodes > 0 && !is_device_ptr(xy)) m.pending_xy = xy;          // copied when the symbolic phase starts
+    else if (nnodes > 0) CUDA_CHECK(cudaMemcpyAsync(m.xy.p, xy, (size_t)nnodes * sizeof(double2), cudaMemcpyDefault, ctx->stream));
     ingest_index(ctx, conn, nel * kind, 1, nnodes, m.conn.p, "efg_set_mesh: node id");
     API_END(ctx)
 }
@@ -508,7 +549,7 @@ int efg_set_mesh3(efg_ctx *ctx, int slot, int kind, int64_t nel, int64_t nnodes,
 
 int efg_set_space(efg_ctx *ctx, int slot, int mesh_slot, int ncomp, int64_t nnodes, const int64_t *dofnums)
 {
-    API_BEGIN(ctx)
+    API_BEGIN_RAW(ctx)
     if (slot < 0 || slot > 2 || mesh_slot < 0 || mesh_slot > 1) efg_throw(EFG_ERR_INVALID, "bad space/mesh slot");
     if (ncomp < 1 || ncomp > 2) efg_throw(EFG_ERR_INVALID, "ncomp must be 1 or 2");
     if (nnodes != ctx->mesh[mesh_slot].nnodes) efg_throw(EFG_ERR_INVALID, "space has %lld terms, its mesh has %lld nodes", (long long)nnodes, (long long)ctx->mesh[mesh_slot].nnodes);
@@ -556,7 +597,7 @@ int efg_set_space_fe(efg_ctx *ctx, int slot, int mesh_slot, int fe, int ncomp, i
 
 int efg_start(efg_ctx *ctx, int64_t nrow, int64_t ncol)
 {
-    API_BEGIN(ctx)
+    API_BEGIN_RAW(ctx)
     if (nrow < 0 || ncol < 0) efg_throw(EFG_ERR_INVALID, "negative matrix size");
     if (nrow >= ((int64_t)1 << 31) || ncol >= ((int64_t)1 << 31)) efg_throw(EFG_ERR_LIMIT, "matrix dimension exceeds 32-bit device indices");
     const bool same = ctx->started && ctx->nrow == nrow && ctx->ncol == ncol && !ctx->have_range;
@@ -570,7 +611,7 @@ int efg_start(efg_ctx *ctx, int64_t nrow, int64_t ncol)
 
 int efg_set_column_range(efg_ctx *ctx, int64_t first, int64_t last)
 {
-    API_BEGIN(ctx)
+    API_BEGIN_RAW(ctx)
     if (!ctx->started) efg_throw(EFG_ERR_STATE, "efg_set_column_range before efg_start");
     if (first < 1 || last > ctx->ncol || last < first - 1) efg_throw(EFG_ERR_INVALID, "bad column range");
     invalidate(ctx);
@@ -580,7 +621,7 @@ int efg_set_column_range(efg_ctx *ctx, int64_t first, int64_t last)
 
 int efg_set_column_ranges(efg_ctx *ctx, int64_t nranges, const int64_t *firsts, const int64_t *lasts)
 {
-    API_BEGIN(ctx)
+    API_BEGIN_RAW(ctx)
     if (!ctx->started) efg_throw(EFG_ERR_STATE, "efg_set_column_ranges before efg_start");
     if (nranges < 1 || nranges > (1 << 24) || !firsts || !lasts) efg_throw(EFG_ERR_INVALID, "bad column range list");
     std::vector<int32_t> f((size_t)nranges), l((size_t)nranges), o((size_t)nranges);
@@ -659,6 +700,7 @@ static void run_symbolic(efg_ctx *ctx, int form, int quad, bool want_tiles)
 {
     if (!ctx->started) efg_throw(EFG_ERR_STATE, "efg_symbolic before efg_start");
     check_form_inputs(ctx, form);
+    flush_deferred_xy(ctx, true);          // deferred coordinates travel while the pattern kernels run
     const bool same = ctx->form == form && ctx->quad == quad;
     if (ctx->have_symbolic && same) return;
     if (ctx->have_pattern && same && !want_tiles) return;
@@ -681,7 +723,7 @@ static void run_symbolic(efg_ctx *ctx, int form, int quad, bool want_tiles)
         } else if (path == 2) {
             try {
                 if (!resume) tiled_pattern<Form>(ctx);
-                if (want_tiles) { tiled_symbolic<Form>(ctx); complete = true; }
+                if (want_tiles) { wait_deferred_xy(ctx); tiled_symbolic<Form>(ctx); complete = true; }
             } catch (const EfgError &e) {
                 // auto mode: a mesh beyond the tiled path's limits (node valence, ...) takes the general two-pass path
                 if (e.code != EFG_ERR_LIMIT || ctx->opt_path == 2) throw;
@@ -689,7 +731,7 @@ static void run_symbolic(efg_ctx *ctx, int form, int quad, bool want_tiles)
                 path = 1;
             }
         }
-        if (path == 1) { twopass_symbolic<Form>(ctx); ctx->have_pattern = true; complete = true; CUDA_CHECK(cudaEventRecord(ctx->ev_pattern, ctx->stream)); }
+        if (path == 1) { twopass_symbolic<Form>(ctx); wait_deferred_xy(ctx); ctx->have_pattern = true; complete = true; CUDA_CHECK(cudaEventRecord(ctx->ev_pattern, ctx->stream)); }
     });
     } catch (...) { invalidate(ctx); throw; }       // no half-built state survives an error
     if (!ok) efg_throw(EFG_ERR_INVALID, "form %d is not available for element kind %d with rule %d", form, vkind, quad);
@@ -704,7 +746,7 @@ static void run_symbolic(efg_ctx *ctx, int form, int quad, bool want_tiles)
 
 int efg_pattern(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
 {
-    API_BEGIN(ctx)
+    API_BEGIN_RAW(ctx)
     run_symbolic(ctx, form, quad, false);
     if (nnz_out) *nnz_out = ctx->nnz;
     API_END(ctx)
@@ -712,7 +754,7 @@ int efg_pattern(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
 
 int efg_symbolic(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
 {
-    API_BEGIN(ctx)
+    API_BEGIN_RAW(ctx)
     run_symbolic(ctx, form, quad, true);
     if (nnz_out) *nnz_out = ctx->nnz;
     API_END(ctx)
@@ -721,6 +763,7 @@ int efg_symbolic(efg_ctx *ctx, int form, int quad, int64_t *nnz_out)
 int efg_numeric(efg_ctx *ctx, const double *params, int nparams)
 {
     API_BEGIN(ctx)
+    wait_deferred_xy(ctx);
     if (!ctx->have_symbolic && ctx->have_pattern) run_symbolic(ctx, ctx->form, ctx->quad, true);     // efg_pattern came first: build the tiles now
     if (!ctx->have_symbolic) efg_throw(EFG_ERR_STATE, "efg_numeric before efg_symbolic");
     const int need = (ctx->form == EFG_FORM_ELASTICITY || ctx->form == EFG_FORM_STOKES_GEN) ? 9 : 1;
@@ -816,13 +859,7 @@ static void enqueue_pattern_copy(efg_ctx *ctx, int64_t *colptr, int64_t *rowval)
             for (int c = 0; c < nch; c++) {
                 const int64_t a = w->cuts[(size_t)c], m = w->cuts[(size_t)c + 1] - a;
                 CUDA_CHECK(cudaMemcpyAsync(up + 4 * a, ctx->rowval.p + a, (size_t)m * sizeof(int32_t), cudaMemcpyDefault, cs));
-                if ((size_t)c >= ctx->widen_events.size()) {
-                    cudaEvent_t e;
-                    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
-                    ctx->widen_events.push_back(e);
-                }
-                w->events.push_back(ctx->widen_events[(size_t)c]);
-                CUDA_CHECK(cudaEventRecord(w->events.back(), cs));
+                CUDA_CHECK(cudaLaunchHostFunc(cs, widen_chunk_arrived, w));
             }
             for (int t = 0; t < w->nthreads; t++) w->threads.emplace_back(widen_worker, w, t);
         }
@@ -832,7 +869,7 @@ static void enqueue_pattern_copy(efg_ctx *ctx, int64_t *colptr, int64_t *rowval)
 
 int efg_fetch_pattern_async(efg_ctx *ctx, int64_t *colptr, int64_t *rowval)
 {
-    API_BEGIN(ctx)
+    API_BEGIN_RAW(ctx)
     if (!ctx->have_pattern) efg_throw(EFG_ERR_STATE, "efg_fetch_pattern_async before efg_pattern / efg_symbolic");
     enqueue_pattern_copy(ctx, colptr, rowval);
     API_END(ctx)

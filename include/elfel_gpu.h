@@ -114,6 +114,10 @@ typedef struct efg_ctx efg_ctx;
 #define EFG_OPT_TILE_ELEMS  3 /* elements per tile of the fused kernel (0 = automatic) */
 #define EFG_OPT_SFC_ORDER   4 /* 1 (default) = tiles follow a space-filling-curve order of the
                                  elements, 0 = tiles follow the given element order */
+#define EFG_OPT_DEFER_XY    6 /* 1 = efg_set_mesh does not copy a HOST coordinate array: the array is borrowed until the next
+                                 efg_pattern / efg_symbolic / efg_assemble call returns (or any later call on the ctx), where it
+                                 is copied on a separate stream while the pattern kernels run (they read connectivity and dof
+                                 maps only).  For callers that keep the mesh alive across the whole assemble! (the Julia shim) */
 #define EFG_OPT_FUSE_LOAD   5 /* 1 = the next symbolic phase of a heat form reserves room for the element load vector next
                                  to the element matrix, so that efg_numeric_with_load can produce K and F in one pass */
 

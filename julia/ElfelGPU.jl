@@ -42,6 +42,9 @@ mutable struct SysmatAssemblerGPU <: AbstractSysmatAssembler
         rc = ccall((:efg_create, LIB), Cint, (Cint, Ref{Ptr{Cvoid}}), device, r)
         rc == 0 || error("efg_create failed ($rc): no usable CUDA device (there is no CPU fallback)")
         a = new(r[], 0, 0, 0, Int64[], Int64[], Float64[], Any[])
+        # EFG_OPT_DEFER_XY (6): the coordinate array is borrowed until efg_pattern returns and copied while the pattern kernels
+        # run; assemble! below keeps the iterators (and with them the mesh) alive across the whole sequence
+        ccall((:efg_set_option, LIB), Cint, (Ptr{Cvoid}, Cint, Int64), a.ctx, 6, 1)
         finalizer(x -> ccall((:efg_destroy, LIB), Cint, (Ptr{Cvoid},), x.ctx), a)
         return a
     end

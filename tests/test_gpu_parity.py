@@ -329,3 +329,35 @@ def test_remesh_without_renumbering_is_rejected():
     eng.set_space(0, 0, big.spaces[0].field.dofnums)
     eng.assemble(big.form.form_id, big.quad, big.form.params())
     eng.close()
+
+
+def test_deferred_coordinate_copy_gives_the_same_matrix(oracle):
+    """EFG_OPT_DEFER_XY: efg_set_mesh borrows the host coordinates and the copy overlaps the pattern kernels; any entry point
+    that reads coordinates first (here efg_qp_locations) brings them in on the main stream instead."""
+    prob = efg.heat_problem(efg.T6, 37, True)
+    ocp, orv, onz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    m = prob.meshes[0]
+    conn, xy, dof = (np.ascontiguousarray(m.conn, dtype=np.int64), np.ascontiguousarray(m.xy, dtype=np.float64),
+                     np.ascontiguousarray(prob.spaces[0].field.dofnums, dtype=np.int64))      # kept alive below
+    for seq in ("pattern-numeric", "assemble", "locations-first"):
+        eng = efg.Engine(0)
+        eng.set_option(_lib.OPT_DEFER_XY, 1)
+        eng.set_option(_lib.OPT_STRICT_FP, 1)
+        eng.set_mesh(0, m.kind, conn, xy)
+        eng.set_space(0, 0, dof)
+        eng.start(prob.ndofs, prob.ndofs)
+        if seq == "locations-first":
+            loc = eng.qp_locations(0, prob.quad, m.nel)
+            assert loc.tobytes() == oracle.qp_locations(prob.quad, m).tobytes()
+        if seq == "pattern-numeric":
+            nnz = eng.pattern(prob.form.form_id, prob.quad)
+            cp, rv = np.empty(prob.ndofs + 1, dtype=np.int64), np.empty(nnz, dtype=np.int64)
+            eng.fetch_pattern_async(cp, rv)
+            eng.numeric(prob.form.params())
+            nz = np.empty(nnz, dtype=np.float64)
+            eng.fetch_csc(None, None, nz)
+        else:
+            eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+            cp, rv, nz = eng.fetch_csc()
+        eng.close()
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz), seq
