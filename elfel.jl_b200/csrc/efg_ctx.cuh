@@ -109,6 +109,7 @@ struct efg_ctx {
     cudaEvent_t ev_copy = nullptr;
     bool copy_pending = false;
     bool widen_failed = false;
+    std::vector<cudaEvent_t> widen_events;   // one per chunk of a pattern fetch, created once (their creation costs ~0.4 ms each)
     cudaStream_t in_stream = nullptr;        // deferred coordinate copies (overlap the pattern kernels)
     cudaEvent_t ev_xy = nullptr;
     bool xy_in_flight = false;

@@ -19,9 +19,8 @@
 
 struct HostWiden {
     std::vector<std::thread> threads;
-    std::atomic<int> chunks_arrived{0};       // bumped by a host function enqueued behind every chunk's copy (no events: creating
-                                              // ~50 blocking-sync events cost 35 ms in the first call of a process)
-    std::atomic<int> all_arrived{0};          // set by the joining thread once the copy stream has drained (or failed)
+    std::vector<cudaEvent_t> events;          // events[c]: chunk c has arrived (owned by the ctx, reused by every fetch:
+                                              // creating ~100 blocking-sync events per call cost 35 ms)
     std::vector<int64_t> cuts;                // chunk c = [cuts[c], cuts[c+1])
     std::atomic<int> arrived{0};              // barrier between chunks
     std::atomic<int> failed{0};
@@ -52,16 +51,15 @@ static inline void widen_range(const int32_t *in, int64_t *out, int64_t a, int64
     _mm_sfence();
 }
 
-static void CUDART_CB widen_chunk_arrived(void *p) { static_cast<HostWiden *>(p)->chunks_arrived.fetch_add(1, std::memory_order_release); }
-
 static void widen_worker(HostWiden *w, int tid)
 {
+    cudaSetDevice(w->device);
     const int32_t *in = reinterpret_cast<const int32_t *>(reinterpret_cast<const char *>(w->dst) + 4 * w->nnz);
     const int nch = (int)w->cuts.size() - 1;
     for (int c = 0; c < nch; c++) {
-        for (int spins = 0; w->chunks_arrived.load(std::memory_order_acquire) <= c && !w->all_arrived.load(std::memory_order_acquire); spins++) {
-            if (spins < 64) std::this_thread::yield(); else std::this_thread::sleep_for(std::chrono::microseconds(40));
-        }
+        // blocking-sync events: a polling loop with short sleeps measured 40 ms slower per fetch (timer slack), host-function
+        // callbacks 20 ms slower (they stall the copy stream); their creation (~0.4 ms each) is paid once per ctx
+        if (cudaEventSynchronize(w->events[(size_t)c]) != cudaSuccess) { w->failed = 1; cudaGetLastError(); }
         const int64_t a = w->cuts[(size_t)c], b = w->cuts[(size_t)c + 1], len = b - a;
         const int64_t lo = a + len * tid / w->nthreads, hi = a + len * (tid + 1) / w->nthreads;
         if (w->failed) { /* skip the work, keep the barrier protocol */ }

@@ -1029,12 +1029,12 @@ __device__ __forceinline__ void tl_gather_heavy(const TileDescFull &td, const do
     const TileHeavy *heavy = reinterpret_cast<const TileHeavy *>(reinterpret_cast<const unsigned char *>(srow) + tl_meta_rows_bytes(td.nslot));
     for (int h = tid; h < td.nheavy; h += BLOCK) {
         const TileHeavy e = heavy[h];
-        const int64_t pos = srow[e.s >> 5] + (e.s & 31);
-        int32_t dof = -1;
-        if constexpr (WF) { if ((uint32_t)hidx[e.o] < fdiag) dof = (int32_t)((uint32_t)hidx[e.o + e.c] | ((uint32_t)hidx[e.o + e.c + 1] << 16)); }
         double acc = stage[hidx[e.o]];
         for (int k = 1; k < (int)e.c; k++) acc = __dadd_rn(acc, stage[hidx[e.o + k]]);
+        const int64_t pos = srow[e.s >> 5] + (e.s & 31);
         nzval[pos] = acc;
+        int32_t dof = -1;
+        if constexpr (WF) { if ((uint32_t)hidx[e.o] < fdiag) dof = (int32_t)((uint32_t)hidx[e.o + e.c] | ((uint32_t)hidx[e.o + e.c + 1] << 16)); }
         if constexpr (WF) {
             if (dof >= 0) {
                 double f = stage[hidx[e.o] + foff];
@@ -1281,7 +1281,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric_p(const TileDescFull
 //     another, and their tiles stay large enough (200-370 elements);
 //   T6 heat (6 local dofs): 2 x 320.  4 x 160 gives the same kernel time (2.787 vs 2.809 ms) with tiles of 104 instead of
 //     232 elements, which makes the tile phase of the symbolic part 12 ms slower (more tiles): not worth it end to end.
-// SPLIT forms: 2 CTAs of 352 threads (elasticity) / 256 (Stokes), measured.
+// SPLIT forms: 2 CTAs of 384 threads (elasticity: 256 / 288 / 320 / 352 / 384 / 416 -> 3.72 / 3.70 / 3.59 / 3.39 / 3.29 / 4.51 ms;
+// 24 warps = six per scheduler partition at the 80 registers 352 threads already had) / 256 (Stokes), measured.
 #ifndef TL_BLOCK_NS
 #define TL_BLOCK_NS 320
 #endif
@@ -1292,7 +1293,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric_p(const TileDescFull
 #define TL_MINB4 5
 #endif
 #ifndef TL_BLOCK_SPLIT
-#define TL_BLOCK_SPLIT (TL_PAIRS ? 352 : 256)
+#define TL_BLOCK_SPLIT (TL_PAIRS ? 384 : 256)
 #endif
 #ifndef TL_BLOCK_SPLIT15
 #define TL_BLOCK_SPLIT15 256    // Stokes gen / veclap_alt (15 columns, tiles of 32 elements: 8 pair items per element -> 256 work items)
@@ -1339,6 +1340,21 @@ template <class F> static int tl_default_tile_elems()
 }
 
 
+// The dynamic-shared-memory ceiling of a kernel is a per-FUNCTION attribute shared by every ctx / host thread of the process:
+// it is always raised to the device's opt-in maximum (never to the size one tiling needs), so that two ctx with different
+// tile sizes cannot lower it under each other's launches (efgm_*: one host thread per device; a symbolic phase of one ctx
+// used to race with the numeric launch of another).
+static cudaError_t tl_raise_smem_limit(const efg_ctx *ctx, const void *kern)
+{
+    int optin = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    if (e != cudaSuccess) return e;
+    cudaFuncAttributes fa;
+    e = cudaFuncGetAttributes(&fa, kern);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+}
+
 // stage rows of the tiling being built: the fused load vector (EFG_OPT_FUSE_LOAD at symbolic time) adds one row per local dof
 template <class F> static int tl_stage_rows(const efg_ctx *ctx)
 {
@@ -1359,7 +1375,7 @@ template <class F> static int tl_ctas_per_sm(efg_ctx *ctx)
 {
     TiledData *td = tiled_data(ctx);
     const void *kern = tl_numeric_kernel<F>(ctx);
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+    if (tl_raise_smem_limit(ctx, kern) != cudaSuccess) { cudaGetLastError(); return 0; }
     int per_sm = 0;
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tl_block<F>(), (size_t)td->smem_bytes));
     return per_sm;
@@ -1768,7 +1784,7 @@ template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(
     CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
     if constexpr (tl_persist<F>()) {     // (compile-time: the persistent kernels are only instantiated when selected)
         auto kern = k_tl_numeric_p<F, S, BLOCK, MINB>;
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
+        CUDA_CHECK(tl_raise_smem_limit(ctx, (const void *)kern));
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
         if (per_sm < 1) efg_throw(EFG_ERR_LIMIT, "tiled path: the numeric kernel does not fit on an SM (%d bytes of shared memory)", td->smem_bytes);
         const int grid = ctx->tl.ntiles < per_sm * nsm ? ctx->tl.ntiles : per_sm * nsm;      // one CTA per CTA slot
@@ -1777,7 +1793,7 @@ template <class F, bool S, int BLOCK, int MINB> static void tl_launch_numeric_b(
                    td->off_meta, td->off_geo, td->off_gs);
     } else {
         auto kern = k_tl_numeric<F, S, BLOCK, MINB>;
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
+        CUDA_CHECK(tl_raise_smem_limit(ctx, (const void *)kern));
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
         if (per_sm < 1) efg_throw(EFG_ERR_LIMIT, "tiled path: the numeric kernel does not fit on an SM (%d bytes of shared memory)", td->smem_bytes);
         const int grid = ctx->tl.ntiles;                    // one CTA per tile
@@ -1807,7 +1823,7 @@ template <class F, bool S> static void tl_launch_numeric_fused(efg_ctx *ctx, dou
         int per_sm = 0, nsm = 0;
         CUDA_CHECK(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
         auto kern = k_tl_numeric<F, S, BLOCK, MINB, true>;
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, td->smem_bytes));
+        CUDA_CHECK(tl_raise_smem_limit(ctx, (const void *)kern));
         CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, (size_t)td->smem_bytes));
         if (per_sm < 1) efg_throw(EFG_ERR_LIMIT, "tiled path: the numeric kernel does not fit on an SM (%d bytes of shared memory)", td->smem_bytes);
         if (ctx->tl.ntiles > 0)

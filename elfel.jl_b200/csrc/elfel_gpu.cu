@@ -270,8 +270,6 @@ static void wait_copies(efg_ctx *ctx)
 {
     if (ctx->widen) {               // host threads widening the row indices in the caller's array (efg_hostcopy.cuh)
         HostWiden *w = static_cast<HostWiden *>(ctx->widen);
-        if (ctx->copy_stream && cudaStreamSynchronize(ctx->copy_stream) != cudaSuccess) { w->failed = 1; cudaGetLastError(); }
-        w->all_arrived = 1;         // (every chunk is in host memory now, or the copy failed: nobody waits any longer)
         w->join();
         if (w->failed != 0) ctx->widen_failed = true;       // reported by the fetch call that waits for the copy
         delete w;
@@ -408,6 +406,7 @@ int efg_destroy(efg_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+    for (cudaEvent_t e : ctx->widen_events) cudaEventDestroy(e);
     if (ctx->in_stream) { cudaStreamSynchronize(ctx->in_stream); cudaStreamDestroy(ctx->in_stream); }
     if (ctx->ev_xy) cudaEventDestroy(ctx->ev_xy);
     ctx->pool.destroy();           // the ctx's private arena goes back to the driver; nothing process-global is touched
@@ -859,7 +858,13 @@ static void enqueue_pattern_copy(efg_ctx *ctx, int64_t *colptr, int64_t *rowval)
             for (int c = 0; c < nch; c++) {
                 const int64_t a = w->cuts[(size_t)c], m = w->cuts[(size_t)c + 1] - a;
                 CUDA_CHECK(cudaMemcpyAsync(up + 4 * a, ctx->rowval.p + a, (size_t)m * sizeof(int32_t), cudaMemcpyDefault, cs));
-                CUDA_CHECK(cudaLaunchHostFunc(cs, widen_chunk_arrived, w));
+                if ((size_t)c >= ctx->widen_events.size()) {
+                    cudaEvent_t e;
+                    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | cudaEventBlockingSync));
+                    ctx->widen_events.push_back(e);
+                }
+                w->events.push_back(ctx->widen_events[(size_t)c]);
+                CUDA_CHECK(cudaEventRecord(w->events.back(), cs));
             }
             for (int t = 0; t < w->nthreads; t++) w->threads.emplace_back(widen_worker, w, t);
         }
