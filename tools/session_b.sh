@@ -2,14 +2,14 @@
 # GPU session: default bench line, launch list, ncu full captures summarised on the box (the .ncu-rep files stay there: 64 MiB limit)
 mkdir -p gpurun_out
 t0=$(date +%s)
-python bench.py > gpurun_out/e2_bench.json 2> gpurun_out/e2_bench.err
-echo "bench rc=$? $(( $(date +%s) - t0 )) s"; tail -3 gpurun_out/e2_bench.err
+python bench.py > gpurun_out/f1_bench.json 2> gpurun_out/f1_bench.err
+echo "bench rc=$? $(( $(date +%s) - t0 )) s"; tail -3 gpurun_out/f1_bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2_launches_bench_heat_t6_N4000.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --e2e-warmup 1 --no-others > gpurun_out/e2_launch.log 2>&1; echo "launch list rc=$?"
+    python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 --e2e-warmup 1 --no-others > gpurun_out/f1_launch.log 2>&1; echo "launch list rc=$?"
 for wl in heat_t6 elasticity_t6 stokes_gen; do
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:k_tl_numeric --launch-skip 4 --launch-count 1 \
-    -o /tmp/r2_k_tl_numeric_${wl} -f python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu --no-e2e --no-callers --no-others > gpurun_out/e2_ncu_$wl.log 2>&1; echo "ncu $wl rc=$?"
-python profiles/ncu_summary.py /tmp/r2_k_tl_numeric_${wl}.ncu-rep > gpurun_out/r2_ncu_k_tl_numeric_${wl}.txt 2>&1
-ls -la /tmp/r2_k_tl_numeric_${wl}.ncu-rep
+    -o /tmp/r2f_k_tl_numeric_${wl} -f python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu --no-e2e --no-callers --no-others > gpurun_out/f1_ncu_$wl.log 2>&1; echo "ncu $wl rc=$?"
+python profiles/ncu_summary.py /tmp/r2f_k_tl_numeric_${wl}.ncu-rep > gpurun_out/r2_ncu_k_tl_numeric_${wl}.txt 2>&1
+ls -la /tmp/r2f_k_tl_numeric_${wl}.ncu-rep
 done
 echo "total $(( $(date +%s) - t0 )) s"
