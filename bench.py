@@ -475,6 +475,7 @@ def main():
     ap.add_argument("--path", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-widen", type=int, default=-1, help="e2e: 1 = Int32 row indices widened by host threads, 0 = widened on the device, -1 = 1 for <= 2 ranks")
     ap.add_argument("--no-defer-xy", action="store_true", help="e2e: copy the coordinates inside efg_set_mesh instead of overlapping them with the pattern kernels")
     ap.add_argument("--no-callers", action="store_true", help="skip the f1/f2 rows (load vector, K*x) timed after the hot path")
     ap.add_argument("--no-config5", action="store_true", help="skip the config 5 strong-scaling record")
@@ -576,6 +577,10 @@ def main():
     # known, like the caller of the two-call pattern does) --------------------------------------------------------------
     e2e = None
     fid, quad = prob.form.form_id, prob.quad
+    # row indices: Int32 over PCIe + host-side widening while one or two ranks share the host, device-side widening beyond
+    # (8 ranks: the host's memory system is the bottleneck; measured 1296 ms with host widening at 8 GPUs)
+    host_widen = args.host_widen if args.host_widen >= 0 else int(world <= 2)
+    eng.set_option(_lib.OPT_HOST_WIDEN, host_widen)
     if not args.no_defer_xy:
         eng.set_option(_lib.OPT_DEFER_XY, 1)     # the pinned inputs stay alive across the sequence (like the Julia shim's GC.@preserve)
     torch.cuda.synchronize()
@@ -592,7 +597,7 @@ def main():
         o_colptr = torch.empty(ncl + 1, dtype=torch.int64).pin_memory()
         o_rowval = torch.empty(nnz, dtype=torch.int64).pin_memory()
         o_nzval = torch.empty(nnz, dtype=torch.float64).pin_memory()
-        d2h = 8 * (ncl + 1) + 4 * nnz + 8 * nnz      # colptr Int64, rowval as the device's Int32 (widened in place by host threads), nzval
+        d2h = 8 * (ncl + 1) + (4 if host_widen else 8) * nnz + 8 * nnz      # colptr Int64, rowval (Int32 when widened by host threads), nzval
         t0 = time.perf_counter()
         eng.fetch_pattern_async(o_colptr, o_rowval)
         eng.numeric(params)
@@ -645,6 +650,7 @@ def main():
         e2e = {"value": nel_global / e2e_s, "unit": "elements/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps, "warmup": args.e2e_warmup,
                "all_calls_ms": all_ts, "symbolic_ms_per_call": sym_hist,
+               "row_index_widening": "host threads, Int32 over PCIe (EFG_OPT_HOST_WIDEN = 1)" if host_widen else "device, Int64 over PCIe (EFG_OPT_HOST_WIDEN = 0: many ranks share the host)",
                "what": "efg_set_mesh/_space (EFG_OPT_DEFER_XY: coordinates copied while the pattern kernels run) + efg_start + efg_pattern + efg_fetch_pattern_async + efg_numeric + efg_fetch_csc(nzval), pinned host buffers "
                        "(the sequence of the Julia shim's assemble!/finish!: structure copied out while tiles and values are computed)",
                "plain_sequence_ms": 1e3 * float(np.min(ps)),

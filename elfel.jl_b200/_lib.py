@@ -23,7 +23,7 @@ NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a",
 # error codes / constants (mirror of the header)
 OK, ERR_INVALID, ERR_CUDA, ERR_OOM, ERR_INDEX, ERR_STATE, ERR_LIMIT = 0, -1, -2, -3, -4, -5, -6
 FORM_HEAT, FORM_ELASTICITY, FORM_STOKES_GEN, FORM_STOKES_REDDY, FORM_STOKES_VECLAP_ALT, FORM_STOKES_VECLAP = 1, 2, 3, 4, 5, 6
-OPT_PATH, OPT_STRICT_FP, OPT_TILE_ELEMS, OPT_SFC_ORDER, OPT_FUSE_LOAD, OPT_DEFER_XY = 1, 2, 3, 4, 5, 6
+OPT_PATH, OPT_STRICT_FP, OPT_TILE_ELEMS, OPT_SFC_ORDER, OPT_FUSE_LOAD, OPT_DEFER_XY, OPT_HOST_WIDEN = 1, 2, 3, 4, 5, 6, 7
 PATH_AUTO, PATH_TWOPASS, PATH_TILED = 0, 1, 2
 (STAT_SYMBOLIC_MS, STAT_NUMERIC_MS, STAT_KERNEL_LAUNCHES, STAT_NUMERIC_LAUNCHES, STAT_DEVICE_BYTES,
  STAT_NTILES, STAT_TILE_ELEMS, STAT_NUMERIC_BYTES, STAT_PATH, STAT_VEC_MS, STAT_SPMV_MS) = range(1, 12)

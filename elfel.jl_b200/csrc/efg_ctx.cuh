@@ -89,6 +89,7 @@ struct efg_ctx {
     int opt_sfc = 1;
     int opt_fuse_load = 0;
     int opt_defer_xy = 0;
+    int opt_host_widen = -1;
 
     // symbolic state
     bool have_symbolic = false;

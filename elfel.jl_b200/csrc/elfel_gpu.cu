@@ -437,6 +437,7 @@ int efg_set_option(efg_ctx *ctx, int option, int64_t value)
         if (ctx->opt_sfc != (value ? 1 : 0)) { ctx->opt_sfc = value ? 1 : 0; invalidate(ctx); }
         break;
     case EFG_OPT_DEFER_XY: ctx->opt_defer_xy = value ? 1 : 0; break;
+    case EFG_OPT_HOST_WIDEN: ctx->opt_host_widen = value < 0 ? -1 : (value ? 1 : 0); break;
     case EFG_OPT_FUSE_LOAD:
         if (ctx->opt_fuse_load != (value ? 1 : 0)) { ctx->opt_fuse_load = value ? 1 : 0; invalidate(ctx); }
         break;
@@ -830,6 +831,18 @@ static void ensure_copy_stream(efg_ctx *ctx)
     if (!ctx->copy_stream) CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
     if (!ctx->ev_copy) CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming));
 }
+// EFG_OPT_HOST_WIDEN: 1 = row indices cross PCIe as Int32 and host threads widen them (fastest for one or two GPUs per host:
+// config 2 e2e 313 -> 262 ms), 0 = widened on the device (8 ranks on one host: the host's memory system is the bottleneck and
+// the widening threads add 2x the row-index bytes to it), -1 = by the number of visible devices (<= 2: host).
+// The environment variable EFG_HOST_WIDEN overrides the option.
+static bool host_widen_wanted(const efg_ctx *ctx)
+{
+    if (const char *e = getenv("EFG_HOST_WIDEN")) return atoi(e) != 0;
+    if (ctx->opt_host_widen >= 0) return ctx->opt_host_widen != 0;
+    int ndev = 1;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 1; }
+    return ndev <= 2;
+}
 static void enqueue_pattern_copy(efg_ctx *ctx, int64_t *colptr, int64_t *rowval)
 {
     ensure_copy_stream(ctx);
@@ -842,6 +855,22 @@ static void enqueue_pattern_copy(efg_ctx *ctx, int64_t *colptr, int64_t *rowval)
             k_rowval_out<<<grid_for(ctx->nnz, 256), 256, 0, cs>>>(ctx->rowval.p, ctx->nnz, rowval);
             ctx->launches++;
             CUDA_CHECK(cudaGetLastError());
+        } else if (!host_widen_wanted(ctx)) {
+            // host destination, widened on the DEVICE: Int32 0-based -> Int64 1-based in two staging buffers (stream order keeps
+            // a buffer from being overwritten before its copy has finished).  Twice the PCIe bytes of the path below but no host
+            // memory traffic beyond the DMA writes: the better choice when many ranks share one host (EFG_OPT_HOST_WIDEN)
+            const int64_t CH = (int64_t)32 << 20;
+            const int64_t cap = ctx->nnz < CH ? ctx->nnz : CH;
+            for (int b = 0; b < 2; b++)
+                if (ctx->cstage[b].n < (size_t)cap) ctx->cstage[b].alloc(ctx->pool, (size_t)cap);
+            int b = 0;
+            for (int64_t o = 0; o < ctx->nnz; o += CH, b ^= 1) {
+                const int64_t m = ctx->nnz - o < CH ? ctx->nnz - o : CH;
+                k_rowval_out<<<grid_for(m, 256), 256, 0, cs>>>(ctx->rowval.p + o, m, ctx->cstage[b].p);
+                ctx->launches++;
+                CUDA_CHECK(cudaGetLastError());
+                CUDA_CHECK(cudaMemcpyAsync(rowval + o, ctx->cstage[b].p, (size_t)m * sizeof(int64_t), cudaMemcpyDefault, cs));
+            }
         } else {
             // host destination: the Int32 array crosses the link unwidened into the upper half of the caller's array and
             // host threads widen it in place while later chunks / the values are still travelling (efg_hostcopy.cuh)

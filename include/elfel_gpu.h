@@ -118,6 +118,9 @@ typedef struct efg_ctx efg_ctx;
                                  efg_pattern / efg_symbolic / efg_assemble call returns (or any later call on the ctx), where it
                                  is copied on a separate stream while the pattern kernels run (they read connectivity and dof
                                  maps only).  For callers that keep the mesh alive across the whole assemble! (the Julia shim) */
+#define EFG_OPT_HOST_WIDEN  7 /* row indices fetched into a HOST array: 1 = sent as the device's Int32 and widened in place by library
+                                 threads (half the PCIe bytes; best for 1-2 GPUs per host), 0 = widened on the device (best when many
+                                 ranks share one host's memory system), -1 (default) = 1 if at most two devices are visible */
 #define EFG_OPT_FUSE_LOAD   5 /* 1 = the next symbolic phase of a heat form reserves room for the element load vector next
                                  to the element matrix, so that efg_numeric_with_load can produce K and F in one pass */
 
