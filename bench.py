@@ -81,6 +81,68 @@ def algorithmic_bytes(prob, nnz):
     return b
 
 
+
+def bench_widened_rows(torch, efg, _lib, local, steps, warmup, peak):
+    """SURVEY 8f rows f4 / f5 measured like the other configs (numeric phase, CUDA events on the library's stream):
+    f4: mesh + EBC + numbering of config 2 made on the device through the C ABI (efg_gen_*) and assembled from there;
+    f5: the Reddy loop on the bubble / L2-pressure pairs (tiled path) and the tetrahedral heat form (two-pass path)."""
+    recs = []
+    # ---- f4: config 2 generated on the device ----------------------------------------------------------------------
+    try:
+        N = 4000
+        eng = efg.Engine(local)
+        stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local))
+        eng.synchronize()
+        t0 = time.perf_counter()
+        eng.gen_mesh(0, efg.T6, N, N, 1.0, 1.0)
+        eng.gen_space(0, 0, 1)
+        tol = 1.0 / N / 100
+        for box in ((0, 1, -tol, tol), (0, 1, 1 - tol, 1 + tol), (-tol, tol, 0, 1), (1 - tol, 1 + tol, 0, 1)):
+            eng.setebc_box(0, 1, box[0] - tol, box[1] + tol, box[2], box[3])
+        nfree, nd = eng.number_dofs([0])
+        eng.synchronize()
+        gen_ms = 1e3 * (time.perf_counter() - t0)
+        eng.start(nd, nd)
+        nnz = eng.symbolic(_lib.FORM_HEAT, 3)
+        ms = time_numeric(torch, eng, stream, [1.0], steps, warmup, False) / steps
+        nel = 2 * N * N
+        recs.append({"row": "f4", "workload": f"heat FEH1_T6 N={N}: T6block + EBC boxes + numberdofs! made on the device (efg_gen_*), nothing crosses PCIe",
+                     "generation_ms": gen_ms, "elements": nel, "ndofs": int(nd), "nunknowns": int(nfree), "nnz": int(nnz),
+                     "nnz_closed_form_ok": int(nnz) == 46 * N * N + 16 * N + 1, "ms_per_step": ms, "value": nel / (ms / 1e3), "unit": "elements/s"})
+        eng.close()
+    except Exception as e:      # noqa: BLE001 -- side records never take the headline line down
+        recs.append({"row": "f4", "error": f"{type(e).__name__}: {e}"})
+    # ---- f5 -----------------------------------------------------------------------------------------------------------
+    def one(name, prob, row="f5"):
+        eng = efg.Engine(local)
+        stream = torch.cuda.ExternalStream(eng.stream(), device=torch.device("cuda", local))
+        efg.load_problem(eng, prob)
+        nnz = eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+        m = prob.meshes[0]
+        nen = m.conn.shape[1]
+        ndof_entries = sum((0 if sp.field is None else sp.field.dofnums.size) + (0 if sp.cellfield is None else sp.cellfield.dofnums.size)
+                           for sp in prob.spaces)
+        nv = prob.spaces[0].fe.nbf                 # COO triplets the reference appends per element (src/Assemblers.jl:97-114)
+        ntrip = 4 * nv * nv + 4 * nv * prob.spaces[2].fe.nbf if prob.form.form_id == _lib.FORM_STOKES_REDDY else nv * nv
+        alg = 4 * nen * m.nel + 8 * m.xy.shape[1] * m.nnodes + 4 * ndof_entries + 4 * ntrip * m.nel + 8 * nnz
+        small = alg < 2 * L2_BYTES
+        ms = time_numeric(torch, eng, stream, prob.form.params(), steps, warmup, small) / steps
+        path = int(eng.stat(_lib.STAT_PATH))
+        rec = {"row": row, "workload": name, "elements": m.nel, "ndofs": int(prob.ndofs), "nnz": int(nnz), "path": {1: "two-pass", 2: "tiled-fused"}[path],
+               "ms_per_step": ms, "value": m.nel / (ms / 1e3), "unit": "elements/s", "algorithmic_bytes_per_element": alg / m.nel,
+               "roofline": {"achieved": alg / (ms / 1e3) / 1e9, "peak": peak, "frac": alg / (ms / 1e3) / 1e9 / peak, "unit": "GB/s"}}
+        eng.close()
+        return rec
+    for name, make in (("Stokes Reddy FEH1_T3_BUBBLE / FEH1_T3 (p1b_p1.jl), N=1200", lambda: efg.stokes_f5_problem(1200, "p1b_p1")),
+                       ("Stokes Reddy FEH1_Q4 / FEL2_Q4 (q1_q0.jl), N=2000", lambda: efg.stokes_f5_problem(2000, "q1_q0")),
+                       ("heat FEH1_T4 (t4.jl), 100^3 cells = 6 M tetrahedra", lambda: efg.heat_problem(efg.T4, 100))):
+        try:
+            recs.append(one(name, make()))
+        except Exception as e:      # noqa: BLE001
+            recs.append({"row": "f5", "workload": name, "error": f"{type(e).__name__}: {e}"})
+    return recs
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -481,6 +543,7 @@ def main():
     ap.add_argument("--no-config5", action="store_true", help="skip the config 5 strong-scaling record")
     ap.add_argument("--config5-n", type=int, default=16384)
     ap.add_argument("--no-others", action="store_true", help="skip other_configs (N = 1 only)")
+    ap.add_argument("--no-widened", action="store_true", help="skip widened_rows (SURVEY 8f rows f4 / f5 timed like the other configs)")
     ap.add_argument("--only-config5", action="store_true", help="print only the config 5 record (development)")
     ap.add_argument("--verify", action="store_true", help="full-size parity of configs 2/3/4 against the oracle on column blocks (one JSON line)")
     ap.add_argument("--verify-blocks", type=int, default=10)
@@ -792,6 +855,8 @@ def main():
             except Exception as e:      # keep the headline line even if a side record fails
                 others.append({"workload": wl, "error": f"{type(e).__name__}: {e}"})
         out["other_configs"] = others
+        if not args.no_widened:
+            out["widened_rows"] = bench_widened_rows(torch, efg, _lib, local, args.steps, args.warmup, peak)
     if not args.no_config5 and args.workload == "heat_t6" and not args.n:
         try:
             out["config5"] = run_config5(torch, dist, efg, _lib, args, rank, world, local, peak)

@@ -883,6 +883,8 @@ template <int NQ_> struct HeatFormT4 {
         }
     }
     template <bool S, class Emit>
+    __device__ __forceinline__ static void element(const double (&)[4], const double (&)[4], uint32_t, Emit &) {}      // (2-D entry point: unused)
+    template <bool S, class Emit>
     __device__ __forceinline__ static void element3(const double (&X)[4], const double (&Y)[4], const double (&Z)[4], uint32_t m, Emit &emit) {
         const QTab &t = c_tab[EFG_TAB_T4];
         const double kappa = c_prm[0];
@@ -901,6 +903,7 @@ template <int NQ_> struct HeatFormT4 {
                     K[i][j] = q == 0 ? v : fadd<S>(K[i][j], v);
                 }
         }
-        emit_col<Emit, 0>(K, m, emit); emit_col<Emit, 1>(K, m, emit); emit_col<Emit, 2>(K, m, emit); emit_col<Emit, 3>(K, m, emit);
+        if constexpr (Emit::TRI) emit.tri(K, m);
+        else { emit_col<Emit, 0>(K, m, emit); emit_col<Emit, 1>(K, m, emit); emit_col<Emit, 2>(K, m, emit); emit_col<Emit, 3>(K, m, emit); }
     }
 };

@@ -65,9 +65,11 @@ __host__ __device__ static inline int tl_meta_rows_bytes(int nslot) { return tl_
 // geometry block of a tile, each part 16-byte aligned: [txy: double2 x nnode] [conn16: u16 x GK x nelem] [mask16: u16 x nelem]
 __host__ __device__ static inline int tl_geo_xy_bytes(int nnode) { return 16 * nnode; }
 __host__ __device__ static inline int tl_geo_conn_bytes(int gk, int nelem) { return tl_align16(2 * gk * nelem); }
-__host__ __device__ static inline int tl_geo_block_bytes(int gk, int nelem, int nnode)
+// 3-D meshes (FEH1_T4) append [tz: double x nnode]
+__host__ __device__ static inline int tl_geo_z_off(int gk, int nelem, int nnode) { return tl_geo_xy_bytes(nnode) + tl_geo_conn_bytes(gk, nelem) + tl_align16(2 * nelem); }
+__host__ __device__ static inline int tl_geo_block_bytes(int gk, int nelem, int nnode, int dim3 = 0)
 {
-    return tl_geo_xy_bytes(nnode) + tl_geo_conn_bytes(gk, nelem) + tl_align16(2 * nelem);
+    return tl_geo_z_off(gk, nelem, nnode) + (dim3 ? tl_align16(8 * nnode) : 0);
 }
 #define TL_GEO_CAP 4096   // nelem*GK entries a tile's local numbering is built from (256 threads x 16)   // tile slot, first entry in hidx, number of contributions
 // Gather variants that were A/B-measured SLOWER on B200 and removed (profiles/README.md): a branch-free light gather
@@ -318,6 +320,33 @@ __global__ void k_tl_morton(const int32_t *__restrict__ gconn, int gk, const dou
         const uint32_t qx = (uint32_t)fmin(fmax((cx - b.x0) * sx, 0.0), 65535.0);
         const uint32_t qy = (uint32_t)fmin(fmax((cy - b.y0) * sy, 0.0), 65535.0);
         keys[e] = spread16(qx) | (spread16(qy) << 1);
+        vals[e] = (uint32_t)e;
+    }
+}
+// 3-D meshes: 10 bits per axis
+__device__ __forceinline__ uint32_t spread10(uint32_t v)
+{
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void k_tl_morton3(const int32_t *__restrict__ gconn, int gk, const double2 *__restrict__ xy, const double *__restrict__ z, int64_t nel,
+                             const BBox *__restrict__ bb, const double *__restrict__ zmm, uint32_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    const BBox b = *bb;
+    const double z0 = zmm[0], z1 = zmm[1];
+    const double sx = (b.x1 > b.x0) ? 1023.0 / (b.x1 - b.x0) : 0.0, sy = (b.y1 > b.y0) ? 1023.0 / (b.y1 - b.y0) : 0.0, sz = (z1 > z0) ? 1023.0 / (z1 - z0) : 0.0;
+    GRID_STRIDE(e, nel) {
+        double cx = 0, cy = 0, cz = 0;
+        for (int a = 0; a < gk; a++) { const int32_t n = gconn[e * gk + a]; const double2 p = xy[n]; cx += p.x; cy += p.y; cz += z[n]; }
+        cx /= gk; cy /= gk; cz /= gk;
+        const uint32_t qx = (uint32_t)fmin(fmax((cx - b.x0) * sx, 0.0), 1023.0);
+        const uint32_t qy = (uint32_t)fmin(fmax((cy - b.y0) * sy, 0.0), 1023.0);
+        const uint32_t qz = (uint32_t)fmin(fmax((cz - z0) * sz, 0.0), 1023.0);
+        keys[e] = spread10(qx) | (spread10(qy) << 1) | (spread10(qz) << 2);
         vals[e] = (uint32_t)e;
     }
 }
@@ -603,12 +632,16 @@ __global__ void __launch_bounds__(256) k_tl_geo_local(const int64_t *__restrict_
 template <int GK>
 __global__ void k_tl_geo_fill(int ntiles, const TileDescFull *__restrict__ tiles, const uint16_t *__restrict__ tlocal,
                               const int32_t *__restrict__ tnodes, const uint16_t *__restrict__ tmask, const double2 *__restrict__ xy,
-                              unsigned char *__restrict__ geo)
+                              unsigned char *__restrict__ geo, const double *__restrict__ z = nullptr)
 {
     for (int T = blockIdx.x; T < ntiles; T += gridDim.x) {
         const TileDescFull &td = tiles[T];
         if (td.geo_bytes == 0) continue;
         unsigned char *gb = geo + td.geo0;
+        if (z) {
+            double *tz = reinterpret_cast<double *>(gb + tl_geo_z_off(GK, td.nelem, td.nnode));
+            for (int k = threadIdx.x; k < td.nnode; k += blockDim.x) tz[k] = z[tnodes[td.elem0 * GK + k]];
+        }
         double2 *txy = reinterpret_cast<double2 *>(gb);
         uint16_t *c16 = reinterpret_cast<uint16_t *>(gb + tl_geo_xy_bytes(td.nnode));
         uint16_t *m16 = reinterpret_cast<uint16_t *>(gb + tl_geo_xy_bytes(td.nnode) + tl_geo_conn_bytes(GK, td.nelem));
@@ -730,7 +763,7 @@ __global__ void k_tl_tiles_meta0(int ntiles, const int64_t *__restrict__ meta_of
     GRID_STRIDE(T, ntiles) tiles[T].meta0 = meta_off[T];
 }
 
-__global__ void k_tl_tiles_fill(int ntiles, int nd /* stage rows */, bool sym, int gsz, bool gs_alias, int gk, const int32_t *__restrict__ tnn /* null: no geometry blocks */,
+__global__ void k_tl_tiles_fill(int ntiles, int nd /* stage rows */, bool sym, int gsz, bool gs_alias, int gk, int dim3, const int32_t *__restrict__ tnn /* null: no geometry blocks */,
                                 int64_t *__restrict__ geo_bytes, const int64_t *__restrict__ tcol_ptr, const int64_t *__restrict__ tcol_slot,
                                 const int64_t *__restrict__ tcol_gidx, const int64_t *__restrict__ tcol_heavy, const int64_t *__restrict__ telem_ptr,
                                 const int64_t *__restrict__ run_of_k /* exclusive scan of run-head flags */,
@@ -766,7 +799,7 @@ __global__ void k_tl_tiles_fill(int ntiles, int nd /* stage rows */, bool sym, i
         d.pad2_[0] = d.pad2_[1] = 0;
         d.geo0 = 0;
         d.nnode = tnn ? tnn[T] : 0;
-        d.geo_bytes = (tnn && d.nslot > 0) ? tl_geo_block_bytes(gk, d.nelem, d.nnode) : 0;
+        d.geo_bytes = (tnn && d.nslot > 0) ? tl_geo_block_bytes(gk, d.nelem, d.nnode, dim3) : 0;
         tiles[T] = d;
         meta_bytes[T] = d.meta_bytes;
         geo_bytes[T] = d.geo_bytes;
@@ -882,6 +915,23 @@ __device__ __noinline__ void tl_element_to_stage_local(uint32_t le, const uint16
     for (int a = 0; a < GK; a++) { const double2 p = sxy[nd[a]]; X[a] = p.x; Y[a] = p.y; }
     StageEmit<F, WF> emit{stage, qbase, (uint32_t)m16[le], le, nq};
     F::template element<S>(X, Y, emit.m, emit);
+}
+
+// the same for a 3-D form (FEH1_T4): third coordinate plane behind the mask array of the geometry block
+template <class F, bool S>
+__device__ __noinline__ void tl_element_to_stage_local3(uint32_t le, const uint16_t *__restrict__ c16, const uint16_t *__restrict__ m16,
+                                                        const double2 *__restrict__ sxy, const double *__restrict__ sz, double *__restrict__ stage,
+                                                        const uint16_t *__restrict__ qbase, int nq)
+{
+    constexpr int GK = F::GK;
+    static_assert(GK == 4, "");
+    const uint2 a = *reinterpret_cast<const uint2 *>(c16 + le * 4);
+    const uint32_t nd[4] = {a.x & 0xFFFFu, a.x >> 16, a.y & 0xFFFFu, a.y >> 16};
+    double X[GK], Y[GK], Z[GK];
+#pragma unroll
+    for (int k = 0; k < GK; k++) { const double2 p = sxy[nd[k]]; X[k] = p.x; Y[k] = p.y; Z[k] = sz[nd[k]]; }
+    StageEmit<F> emit{stage, qbase, (uint32_t)m16[le], le, nq};
+    F::template element3<S>(X, Y, Z, emit.m, emit);
 }
 
 // SPLIT forms, phase 1a / 1b workers (inlined: out of line measured 4% slower here)
@@ -1097,6 +1147,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
         const double2 *sxy = reinterpret_cast<const double2 *>(sgeo);
         const uint16_t *sc16 = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode));
         const uint16_t *sm16 = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode) + tl_geo_conn_bytes(GK, td.nelem));
+        if constexpr (form_dim3<F>::value) {
+            const double *sz = reinterpret_cast<const double *>(sgeo + tl_geo_z_off(GK, td.nelem, td.nnode));
+            for (int le = tid; le < td.nelem; le += BLOCK) tl_element_to_stage_local3<F, S>((uint32_t)le, sc16, sm16, sxy, sz, stage, td.qbase, nq);
+        } else
         for (int le = tid; le < td.nelem; le += BLOCK) tl_element_to_stage_local<F, S, WF>((uint32_t)le, sc16, sm16, sxy, stage, td.qbase, nq);
     } else if constexpr (!F::SPLIT) {
         // phase 1: one thread per tile element: owned columns of the element matrix -> stage
@@ -1493,6 +1547,18 @@ template <class F> static void tiled_order(efg_ctx *ctx)
         DevBuf<uint32_t> k1, k2, v1;
         k1.alloc(pool, (size_t)nel); k2.alloc(pool, (size_t)nel); v1.alloc(pool, (size_t)nel);
         sy->eorder.alloc(pool, (size_t)nel);
+        if constexpr (form_dim3<F>::value) {
+            DevBuf<double> zmm;
+            zmm.alloc(pool, 2);
+            size_t t2 = 0;
+            cub::DeviceReduce::Min(nullptr, t2, gm.z.p, zmm.p, gm.nnodes, st);
+            DevBuf<char> tmp2;
+            tmp2.alloc(pool, t2);
+            CUDA_CHECK(cub::DeviceReduce::Min(tmp2.p, t2, gm.z.p, zmm.p, gm.nnodes, st));
+            CUDA_CHECK(cub::DeviceReduce::Max(tmp2.p, t2, gm.z.p, zmm.p + 1, gm.nnodes, st));
+            ctx->launches += 2;
+            LAUNCH(ctx, k_tl_morton3, grid_for(nel, 256), 256, 0, gm.conn.p, (int)F::GK, gm.xy.p, gm.z.p, nel, bb.p, zmm.p, k1.p, v1.p);
+        } else
         LAUNCH(ctx, k_tl_morton, grid_for(nel, 256), 256, 0, gm.conn.p, gm.kind, gm.xy.p, nel, bb.p, k1.p, v1.p);
         tl_sort_pairs(ctx, k1.p, k2.p, v1.p, sy->eorder.p, nel, 32);
         sy->have_order = true;
@@ -1656,7 +1722,7 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
     CUDA_CHECK(cudaMemsetAsync(mbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     CUDA_CHECK(cudaMemsetAsync(gbytes.p, 0, ((size_t)ntiles + 1) * sizeof(int64_t), st));
     td->tiles.alloc(pool, (size_t)ntiles);
-    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, tl_stage_rows<F>(ctx), tl_sym<F>(), tl_gsz<F>(), tl_gs_alias<F>(), (int)F::GK, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, pslot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
+    LAUNCH(ctx, k_tl_tiles_fill, grid_for(ntiles, 128), 128, 0, ntiles, tl_stage_rows<F>(ctx), tl_sym<F>(), tl_gsz<F>(), tl_gs_alias<F>(), (int)F::GK, (int)form_dim3<F>::value, GEO ? tnn.p : (const int32_t *)nullptr, gbytes.p, tcol_ptr.p, pslot.p, tcol_gidx.p, tcol_heavy.p, telem_ptr.p, runidx.p,
            nowned, nruns, pc_hist.p, td->tiles.p, mbytes.p, maxima.p);
     int32_t hmax[8];
     tl_read_bytes(ctx, maxima.p, hmax, (int)sizeof hmax);
@@ -1691,7 +1757,7 @@ template <class F> static void tiled_tiles(efg_ctx *ctx, int te)
         LAUNCH(ctx, k_tl_tiles_geo0, grid_for(ntiles, 256), 256, 0, ntiles, goffs.p, td->tiles.p);
         td->geo.alloc(pool, (size_t)(td->geo_total > 0 ? td->geo_total : 16));
         CUDA_CHECK(cudaMemsetAsync(td->geo.p, 0, (size_t)(td->geo_total > 0 ? td->geo_total : 16), st));
-        LAUNCH(ctx, k_tl_geo_fill<F::GK>, grid_for(ntiles, 1, (int64_t)148 * 16), 128, 0, ntiles, td->tiles.p, tlocal, tnodes, td->tmask.p, gm.xy.p, td->geo.p);
+        LAUNCH(ctx, k_tl_geo_fill<F::GK>, grid_for(ntiles, 1, (int64_t)148 * 16), 128, 0, ntiles, td->tiles.p, tlocal, tnodes, td->tmask.p, gm.xy.p, td->geo.p, form_dim3<F>::value ? gm.z.p : (const double *)nullptr);
     }
     td->meta_bytes = meta_total;
 

@@ -717,10 +717,7 @@ static void run_symbolic(efg_ctx *ctx, int form, int quad, bool want_tiles)
     try {
     ok = dispatch_form(form, vkind, npts, [&](auto F) {
         using Form = decltype(F);
-        if constexpr (form_dim3<Form>::value) {     // 3-D forms (FEH1_T4): the general two-pass path only
-            if (ctx->opt_path == 2) efg_throw(EFG_ERR_LIMIT, "the tiled path has no 3-D elements; use EFG_OPT_PATH 0 or 1");
-            path = 1;
-        } else if (path == 2) {
+        if (path == 2) {
             try {
                 if (!resume) tiled_pattern<Form>(ctx);
                 if (want_tiles) { wait_deferred_xy(ctx); tiled_symbolic<Form>(ctx); complete = true; }
@@ -773,8 +770,7 @@ int efg_numeric(efg_ctx *ctx, const double *params, int nparams)
     CUDA_CHECK(cudaEventRecord(ctx->evn0, ctx->stream));
     dispatch_form(ctx->form, ctx->vkind, ctx->nq, [&](auto F) {
         using Form = decltype(F);
-        if constexpr (form_dim3<Form>::value) twopass_numeric<Form>(ctx);
-        else { if (ctx->path == 1) twopass_numeric<Form>(ctx); else tiled_numeric<Form>(ctx); }
+        if (ctx->path == 1) twopass_numeric<Form>(ctx); else tiled_numeric<Form>(ctx);
     });
     CUDA_CHECK(cudaEventRecord(ctx->evn1, ctx->stream));
     ctx->have_values = true;

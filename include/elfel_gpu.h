@@ -150,8 +150,8 @@ int efg_synchronize(efg_ctx *ctx);
 int efg_set_mesh(efg_ctx *ctx, int mesh_slot, int elemkind, int64_t nel, int64_t nnodes,
                  const int64_t *conn, const double *xy);
 /* The same for a 3-D mesh (row f5: EFG_T4): conn is 4 x nel, xyz is 3 x nnodes (the "geom" attribute of SVector{3}).
- * Available for EFG_FORM_HEAT (triangle-style rule = npts 1, 4 or 5 of src/RefShapes.jl:232-259) and EFG_VFORM_HEAT_LOAD;
- * assembled by the general two-pass path (element matrices to HBM + ordered gather), not by the tiled kernel. */
+ * Available for EFG_FORM_HEAT (triangle-style rule = npts 1, 4 or 5 of src/RefShapes.jl:232-259) and EFG_VFORM_HEAT_LOAD,
+ * on both paths (tiled kernel: 3-D Morton tiles, geometry blocks with a third coordinate plane). */
 int efg_set_mesh3(efg_ctx *ctx, int mesh_slot, int elemkind, int64_t nel, int64_t nnodes,
                   const int64_t *conn, const double *xyz);
 /* space_slot 0..2, living on mesh_slot; dofnums is ncomp x nnodes. */

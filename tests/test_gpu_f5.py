@@ -118,20 +118,22 @@ def test_p1b_p1_example_end_to_end_on_the_device(oracle):
     assert ev < 0.25 and ep < 6.0          # N = 16: (5.33, 0.220) with the oracle matrix (tests/test_f5_elements.py)
 
 
-# ---- FEH1_T4 (3-D): examples/heat/poisson/t4.jl, assembled by the two-pass CUDA path -----------------------------------
+# ---- FEH1_T4 (3-D): examples/heat/poisson/t4.jl, tiled and two-pass paths -----------------------------------
+@pytest.mark.parametrize("path", [_lib.PATH_TWOPASS, _lib.PATH_TILED], ids=["twopass", "tiled"])
 @pytest.mark.parametrize("quad", [1, 4, 5])
 @pytest.mark.parametrize("perturb", [False, True], ids=["regular", "jittered"])
-def test_t4_heat_vs_oracle(oracle, quad, perturb):
+def test_t4_heat_vs_oracle(oracle, quad, perturb, path):
     prob = efg.heat_problem(efg.T4, 9, perturb, quad=quad)
     ocp, orv, onz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
     oF = oracle.assemble_vec_heat(prob.quad, prob.meshes[0], prob.spaces[0].field.dofnums, -6.0, prob.ndofs)
     for strict in (1, 0):
         eng = efg.Engine(0)
         eng.set_option(_lib.OPT_STRICT_FP, strict)
+        eng.set_option(_lib.OPT_PATH, path)
         efg.load_problem(eng, prob)
         eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
         cp, rv, nz = eng.fetch_csc()
-        assert int(eng.stat(_lib.STAT_PATH)) == _lib.PATH_TWOPASS
+        assert int(eng.stat(_lib.STAT_PATH)) == path
         eng.vec_assemble(_lib.VFORM_HEAT_LOAD, prob.quad, [-6.0], prob.ndofs)
         F = eng.fetch_vec()
         eng.close()
@@ -164,8 +166,23 @@ def test_t4_example_end_to_end_through_the_mirrored_api():
     T[:nu] = spl.spsolve(K[:nu, :nu].tocsc(), F[:nu] - KT[:nu])
     err = np.abs(T[fesp.field.dofnums[:, 0] - 1] - tempf(xyz[:, 0], xyz[:, 1], xyz[:, 2])).mean()
     assert err <= 1e-9, err
-    with pytest.raises(_lib.EfgError):          # the tiled kernel has no 3-D elements
-        e = efg.Engine(0)
-        e.set_option(_lib.OPT_PATH, _lib.PATH_TILED)
-        efg.load_problem(e, prob)
-        e.assemble(prob.form.form_id, prob.quad, prob.form.params())
+
+
+def test_t4_larger_mesh_tiled_equals_twopass(oracle):
+    """40^3 cells = 384 000 tetrahedra (jittered): the tiled kernel (3-D Morton tiles, geometry blocks with a z plane) against the
+    two-pass path bit for bit in strict mode, and against the direct oracle."""
+    prob = efg.heat_problem(efg.T4, 40, True, quad=4)
+    out = {}
+    for path in (_lib.PATH_TWOPASS, _lib.PATH_TILED):
+        eng = efg.Engine(0)
+        eng.set_option(_lib.OPT_STRICT_FP, 1)
+        eng.set_option(_lib.OPT_PATH, path)
+        efg.load_problem(eng, prob)
+        eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+        out[path] = eng.fetch_csc()
+        assert int(eng.stat(_lib.STAT_PATH)) == path
+        eng.close()
+    a, b = out[_lib.PATH_TWOPASS], out[_lib.PATH_TILED]
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2].tobytes() == b[2].tobytes()
+    ocp, orv, onz = oracle.assemble_direct_parallel(efg.oracle_args(prob), prob.ndofs, prob.ndofs, [(prob.meshes[0].conn, prob.spaces[0].field.dofnums)])
+    assert np.array_equal(b[0], ocp) and np.array_equal(b[1], orv) and np.array_equal(b[2], onz)
