@@ -158,6 +158,17 @@ def test_t4_tables_match_the_reference_known_answers(oracle):
     for npts in (1, 4, 5):          # src/RefShapes.jl:232-259: every rule integrates a constant over the unit tetrahedron
         assert L.efo_quadrature_t4(npts, pc, w) == npts
         assert abs(sum(w[:npts]) - 1.0 / 6.0) < 1e-15
+    # test/test_refshapes.jl:94-115 (mrs6): the tetrahedron rules' points and weights
+    L.efo_quadrature_t4(1, pc, w)
+    assert np.allclose(pc[:3], [0.25, 0.25, 0.25]) and np.isclose(w[0], 0.16666666666666666)
+    L.efo_quadrature_t4(4, pc, w)
+    assert np.allclose(np.array(pc[:12]).reshape(4, 3), [[0.1381966, 0.1381966, 0.1381966], [0.5854102, 0.1381966, 0.1381966],
+                                                         [0.1381966, 0.5854102, 0.1381966], [0.1381966, 0.1381966, 0.5854102]])
+    assert np.allclose(w[:4], [0.041666666666666664] * 4)
+    L.efo_quadrature_t4(5, pc, w)
+    a6 = 0.16666666666666666
+    assert np.allclose(np.array(pc[:15]).reshape(5, 3), [[0.25, 0.25, 0.25], [0.5, a6, a6], [a6, 0.5, a6], [a6, a6, 0.5], [a6, a6, a6]])
+    assert np.allclose(w[:5], [-0.13333333333333333, 0.075, 0.075, 0.075, 0.075])
     N = (C.c_double * 4)()
     L.efo_bfun_t4.argtypes = [C.c_double] * 3 + [C.POINTER(C.c_double)]
     L.efo_bfun_t4(0.25, 0.25, 0.25, N)

@@ -430,3 +430,14 @@ def test_direct_accumulate_mode_rejects_unnumbered_dofs(oracle):
     efg.numberfreedofs(p.spaces[0])
     with pytest.raises(ValueError):
         oracle.assemble_direct(*efg.oracle_args(p), p.ndofs, p.ndofs)
+
+
+def test_gauss_rules_integrate_exp_like_the_reference(oracle):
+    """test/test_refshapes.jl:124-146 (mrs7): sum(exp.(param_coords) .* weights) of the interval rules, orders 1..5 (the orders
+    the oracle restates with the reference's literals; higher orders are Golub-Welsch in the reference).  The square rule is
+    the tensor product, so sum_ij w_ij exp(x_i) = 2 * the interval result."""
+    ref = [2.0, 2.3426960879097307, 2.350336928680011, 2.3504020921563744, 2.350402386462827]
+    for order, want in zip(range(1, 6), ref):
+        pc, w = oracle.quadrature(efg.Q4, order)
+        assert len(w) == order ** 2                                  # test/test_refshapes.jl:64-67 (mrs4)
+        assert np.isclose(float((np.exp(pc[:, 0]) * w).sum()) / 2.0, want, rtol=1e-8, atol=0)
