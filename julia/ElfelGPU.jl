@@ -154,6 +154,35 @@ function assemble!(v::SysvecAssemblerGPU, form::HeatLoadForm, elit::FEIterator, 
     return v
 end
 
+"""
+    assemble!(am, av, HeatForm(kappa), HeatLoadForm(Q), elit, qpit)
+
+K and F of ONE pass, like the reference's heat loops (`ke[i, j] += ...` and `fe[j] += N[j] * Q * JxW` in the same quadrature
+loop, `assemble!(am, ke); assemble!(av, fe)` per element: examples/heat/poisson/t3.jl:41-64).  `av` must share `am`'s
+context (`SysvecAssemblerGPU(0.0; like = am)`); then `finish!(am)`, `finish!(av)` as usual.
+"""
+function assemble!(a::SysmatAssemblerGPU, v::SysvecAssemblerGPU, form::HeatForm, vform::HeatLoadForm, elit::FEIterator, qpit::QPIterator)
+    v.owner === a || error("assemble!(am, av, ...): the vector assembler must share the matrix assembler's context (like = am)")
+    _check(a, ccall((:efg_set_option, LIB), Cint, (Ptr{Cvoid}, Cint, Int64), a.ctx, 5, 1))      # EFG_OPT_FUSE_LOAD (before the symbolic phase)
+    GC.@preserve elit begin
+        conn = reinterpret(Int64, elit._bir._v); xy = reinterpret(Float64, elit._geom.v)
+        _check(a, ccall((:efg_set_mesh, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Int64, Int64, Ptr{Int64}, Ptr{Float64}),
+                        a.ctx, 0, _kind(elit), length(elit), length(elit._geom), conn, xy))
+        dof = reinterpret(Int64, elit._fld0.dofnums)
+        _check(a, ccall((:efg_set_space, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Int64, Ptr{Int64}),
+                        a.ctx, 0, 0, 1, length(elit._fld0.dofnums), dof))
+        _check(a, ccall((:efg_start, LIB), Cint, (Ptr{Cvoid}, Int64, Int64), a.ctx, a.nrow, a.ncol))
+        nnz = Ref{Int64}(0)
+        _check(a, ccall((:efg_pattern, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ref{Int64}), a.ctx, 1, _rule(qpit, _kind(elit)), nnz))
+        a.nnz = nnz[]
+        a.colptr = Vector{Int64}(undef, a.ncol + 1); a.rowval = Vector{Int64}(undef, a.nnz); a.nzval = Vector{Float64}(undef, a.nnz)
+        _check(a, ccall((:efg_fetch_pattern_async, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}), a.ctx, a.colptr, a.rowval))
+        _check(a, ccall((:efg_numeric_with_load, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Float64), a.ctx, [form.kappa], 1, vform.Q))
+        a.loaded = Any[elit]
+    end
+    return a, v
+end
+
 "finish!(av) -- src/Assemblers.jl:230-232"
 function finish!(v::SysvecAssemblerGPU)
     F = Vector{Float64}(undef, v.ndofs)
