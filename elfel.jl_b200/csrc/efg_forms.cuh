@@ -21,6 +21,10 @@
                           // point instead of 4 operations); differences to the reference's rounding sequence are O(1e-16) relative
 #endif
 
+#ifndef TL_HEAT_NUM
+#define TL_HEAT_NUM 1     // default FP mode of the heat forms: undivided gradient numerators, one factor kappa*w/det per quadrature point
+#endif
+
 struct QTab {
     double w[EFG_MAXQ];
     double N[EFG_MAXQ][6];
@@ -115,6 +119,31 @@ __device__ __forceinline__ void geo_qp(const double (&X)[GK], const double (&Y)[
     for (int n = 0; n < BK; n++) {
         gx[n] = div(fsub<S>(fmul<S>(J11, tb.gp[q][n][0]), fmul<S>(J10, tb.gp[q][n][1])));
         gy[n] = div(fsub<S>(fmul<S>(J00, tb.gp[q][n][1]), fmul<S>(J01, tb.gp[q][n][0])));
+    }
+}
+
+// Default FP mode of the heat forms: the UNDIVIDED gradient numerators (J11*g0 - J10*g1, J00*g1 - J01*g0) and the determinant.
+// With c = kappa * w / det the entry sum_q dot(gradN_i, gradN_j) * kappa * JxW becomes sum_q (nx_i*c)*nx_j + (ny_i*c)*ny_j:
+// the per-gradient quotients by det disappear (8-12 DMUL per quadrature point).  The Jacobian itself is still the
+// uncontracted node-order sum (see geo_qp); differences to the reference's rounding sequence stay O(1e-16) relative.
+template <int GK, int BK, int BS = kind_slot(BK)>
+__device__ __forceinline__ void geo_qp_num(const double (&X)[GK], const double (&Y)[GK], int q,
+                                           double (&nx)[BK], double (&ny)[BK], double &det)
+{
+    const QTab &tg = c_tab[kind_slot(GK)];
+    const QTab &tb = c_tab[BS];
+    double J00 = __dmul_rn(X[0], tg.gp[q][0][0]), J01 = __dmul_rn(X[0], tg.gp[q][0][1]);
+    double J10 = __dmul_rn(Y[0], tg.gp[q][0][0]), J11 = __dmul_rn(Y[0], tg.gp[q][0][1]);
+#pragma unroll
+    for (int n = 1; n < GK; n++) {
+        J00 = __dadd_rn(J00, __dmul_rn(X[n], tg.gp[q][n][0])); J01 = __dadd_rn(J01, __dmul_rn(X[n], tg.gp[q][n][1]));
+        J10 = __dadd_rn(J10, __dmul_rn(Y[n], tg.gp[q][n][0])); J11 = __dadd_rn(J11, __dmul_rn(Y[n], tg.gp[q][n][1]));
+    }
+    det = __dsub_rn(__dmul_rn(J00, J11), __dmul_rn(J10, J01));
+#pragma unroll
+    for (int n = 0; n < BK; n++) {
+        nx[n] = J11 * tb.gp[q][n][0] - J10 * tb.gp[q][n][1];
+        ny[n] = J00 * tb.gp[q][n][1] - J01 * tb.gp[q][n][0];
     }
 }
 
@@ -248,6 +277,21 @@ template <int VK, int NQ_> struct HeatForm {
         double K[ND][ND];
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
+            if constexpr (!S && TL_FAST_ACC && TL_HEAT_NUM) {
+                double nx[BK], ny[BK], det;
+                geo_qp_num<GK, BK>(X, Y, q, nx, ny, det);
+                const SharedDivisor<false> div(det);
+                const double c = div(kappa * c_tab[kind_slot(GK)].w[q]);          // kappa * JxW / det^2
+                double sx[BK], sy[BK];
+#pragma unroll
+                for (int i = 0; i < ND; i++) { sx[i] = nx[i] * c; sy[i] = ny[i] * c; }
+#pragma unroll
+                for (int j = 0; j < ND; j++)
+#pragma unroll
+                    for (int i = 0; i <= j; i++)
+                        K[i][j] = q == 0 ? fma(sx[i], nx[j], sy[i] * ny[j]) : fma(sx[i], nx[j], fma(sy[i], ny[j], K[i][j]));
+                continue;
+            }
             double gx[BK], gy[BK], JxW;
             geo_qp<S, GK, BK>(X, Y, q, gx, gy, JxW);
             const double kJ = fmul<S>(kappa, JxW);
