@@ -25,6 +25,10 @@
 #define TL_HEAT_NUM 1     // default FP mode of the heat forms: undivided gradient numerators, one factor kappa*w/det per quadrature point
 #endif
 
+#ifndef TL_Q4_TENSOR
+#define TL_Q4_TENSOR 1    // FEH1_Q4 heat, default FP mode: Jacobian columns shared between the points of the tensor-product rule
+#endif
+
 struct QTab {
     double w[EFG_MAXQ];
     double N[EFG_MAXQ][6];
@@ -275,8 +279,55 @@ template <int VK, int NQ_> struct HeatForm {
     __device__ __forceinline__ static void element(const double (&X)[GK], const double (&Y)[GK], uint32_t m, Emit &emit) {
         const double kappa = c_prm[0];
         double K[ND][ND];
+        // FEH1_Q4 on the tensor-product Gauss rule (points i outer / j inner, src/RefShapes.jl:350-362), default FP mode: dN/dxi
+        // depends on eta only and dN/deta on xi only, so the first Jacobian column takes NP distinct values (one per j) and the
+        // second NP (one per i) instead of NP^2 each -- the same individually rounded node-order sums, computed once
+        constexpr bool Q4T = !S && TL_FAST_ACC && TL_HEAT_NUM && TL_Q4_TENSOR && VK == 4 && (NQ == 4 || NQ == 9);
+        constexpr int NP = NQ == 9 ? 3 : 2;
+        double A00[NP], A10[NP], B01[NP], B11[NP];
+        if constexpr (Q4T) {
+            const QTab &tg = c_tab[kind_slot(GK)];
+            {
+                {
+#pragma unroll
+                    for (int t = 0; t < NP; t++) {
+                        const int qa = t, qb = t * NP;          // (i = 0, j = t) and (i = t, j = 0)
+                        double a0 = __dmul_rn(X[0], tg.gp[qa][0][0]), a1 = __dmul_rn(Y[0], tg.gp[qa][0][0]);
+                        double b0 = __dmul_rn(X[0], tg.gp[qb][0][1]), b1 = __dmul_rn(Y[0], tg.gp[qb][0][1]);
+#pragma unroll
+                        for (int n = 1; n < GK; n++) {
+                            a0 = __dadd_rn(a0, __dmul_rn(X[n], tg.gp[qa][n][0])); a1 = __dadd_rn(a1, __dmul_rn(Y[n], tg.gp[qa][n][0]));
+                            b0 = __dadd_rn(b0, __dmul_rn(X[n], tg.gp[qb][n][1])); b1 = __dadd_rn(b1, __dmul_rn(Y[n], tg.gp[qb][n][1]));
+                        }
+                        A00[t] = a0; A10[t] = a1; B01[t] = b0; B11[t] = b1;
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
+            if constexpr (Q4T) {
+                const QTab &tg = c_tab[kind_slot(GK)];
+                const double J00 = A00[q % NP], J10 = A10[q % NP], J01 = B01[q / NP], J11 = B11[q / NP];
+                const double det = __dsub_rn(__dmul_rn(J00, J11), __dmul_rn(J10, J01));
+                double nx[BK], ny[BK];
+#pragma unroll
+                for (int n = 0; n < BK; n++) {
+                    nx[n] = J11 * tg.gp[q][n][0] - J10 * tg.gp[q][n][1];
+                    ny[n] = J00 * tg.gp[q][n][1] - J01 * tg.gp[q][n][0];
+                }
+                const SharedDivisor<false> div(det);
+                const double c = div(kappa * tg.w[q]);
+                double sx[BK], sy[BK];
+#pragma unroll
+                for (int i = 0; i < ND; i++) { sx[i] = nx[i] * c; sy[i] = ny[i] * c; }
+#pragma unroll
+                for (int j = 0; j < ND; j++)
+#pragma unroll
+                    for (int i = 0; i <= j; i++)
+                        K[i][j] = q == 0 ? fma(sx[i], nx[j], sy[i] * ny[j]) : fma(sx[i], nx[j], fma(sy[i], ny[j], K[i][j]));
+                continue;
+            }
             if constexpr (!S && TL_FAST_ACC && TL_HEAT_NUM) {
                 double nx[BK], ny[BK], det;
                 geo_qp_num<GK, BK>(X, Y, q, nx, ny, det);
