@@ -361,3 +361,28 @@ def test_deferred_coordinate_copy_gives_the_same_matrix(oracle):
             cp, rv, nz = eng.fetch_csc()
         eng.close()
         assert np.array_equal(cp, ocp) and np.array_equal(rv, orv) and np.array_equal(nz, onz), seq
+
+
+@pytest.mark.parametrize("host_widen", [0, 1], ids=["device-widened", "host-widened"])
+def test_row_indices_reach_the_host_identically_on_both_routes(oracle, host_widen):
+    """EFG_OPT_HOST_WIDEN: Int64 row indices widened on the device (many ranks per host) or sent as Int32 and widened in place by
+    library threads (one or two GPUs per host) -- the caller's SparseMatrixCSC arrays must come out the same, for the plain
+    fetch and for the overlapped pattern fetch, with page-locked and with pageable destinations."""
+    import torch
+    prob = efg.heat_problem(efg.T6, 61, True)
+    ocp, orv, onz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    eng = efg.Engine(0)
+    eng.set_option(_lib.OPT_HOST_WIDEN, host_widen)
+    eng.set_option(_lib.OPT_STRICT_FP, 1)
+    efg.load_problem(eng, prob)
+    nnz = eng.pattern(prob.form.form_id, prob.quad)
+    cp = torch.empty(prob.ndofs + 1, dtype=torch.int64).pin_memory()
+    rv = torch.full((nnz,), -7, dtype=torch.int64).pin_memory()
+    eng.fetch_pattern_async(cp, rv)
+    eng.numeric(prob.form.params())
+    nz = np.empty(nnz, dtype=np.float64)
+    eng.fetch_csc(None, None, nz)
+    assert np.array_equal(cp.numpy(), ocp) and np.array_equal(rv.numpy(), orv) and np.array_equal(nz, onz)
+    cp2, rv2, nz2 = eng.fetch_csc()                       # pageable numpy arrays, everything in one call
+    assert np.array_equal(cp2, ocp) and np.array_equal(rv2, orv) and np.array_equal(nz2, onz)
+    eng.close()
