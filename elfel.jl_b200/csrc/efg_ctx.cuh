@@ -150,6 +150,10 @@ template <class Fn> inline bool dispatch_form(int form, int vkind, int nq, Fn &&
         if (vkind == 4 && nq == 1) { fn(HeatForm<4, 1>{}); return true; }
         if (vkind == 4 && nq == 4) { fn(HeatForm<4, 4>{}); return true; }
         if (vkind == 4 && nq == 9) { fn(HeatForm<4, 9>{}); return true; }
+        // the less common rules: one instantiation per element kind with the number of points read at run time
+        if (vkind == 3 && (nq == 4 || nq == 6 || nq == 7 || nq == 9 || nq == 12 || nq == 13)) { fn(HeatForm<3, 0>{}); return true; }
+        if (vkind == 6 && (nq == 4 || nq == 6 || nq == 7 || nq == 9 || nq == 12 || nq == 13)) { fn(HeatForm<6, 0>{}); return true; }
+        if (vkind == 4 && (nq == 16 || nq == 25)) { fn(HeatForm<4, 0>{}); return true; }
         if (vkind == EFG_T4 && nq == 1) { fn(HeatFormT4<1>{}); return true; }
         if (vkind == EFG_T4 && nq == 4) { fn(HeatFormT4<4>{}); return true; }
         if (vkind == EFG_T4 && nq == 5) { fn(HeatFormT4<5>{}); return true; }

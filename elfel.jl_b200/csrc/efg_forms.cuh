@@ -10,7 +10,7 @@
 #include <utility>
 #include <type_traits>
 
-#define EFG_MAXQ 9
+#define EFG_MAXQ 25     // largest rule: Gauss order 5 on the square (25 points); triangles go up to 13 points
 // Default (non-strict) FP mode only -- the strict mode always performs the reference's operations one by one:
 #ifndef TL_DIV_CORR
 #define TL_DIV_CORR 0     // 1: quotients by the Jacobian determinant get a Markstein residual correction (correctly rounded in almost all cases);
@@ -30,6 +30,7 @@
 #endif
 
 struct QTab {
+    int npts, pad_;           // points of the active rule (read by the run-time-NQ instantiations, NQ_ = 0)
     double w[EFG_MAXQ];
     double N[EFG_MAXQ][6];
     double gp[EFG_MAXQ][6][2];
@@ -282,6 +283,10 @@ template <int VK, int NQ_> struct HeatForm {
         // FEH1_Q4 on the tensor-product Gauss rule (points i outer / j inner, src/RefShapes.jl:350-362), default FP mode: dN/dxi
         // depends on eta only and dN/deta on xi only, so the first Jacobian column takes NP distinct values (one per j) and the
         // second NP (one per i) instead of NP^2 each -- the same individually rounded node-order sums, computed once
+        // NQ_ = 0: the number of quadrature points is read from the table at run time (the less common rules: triangles with
+        // 4 / 6 / 7 / 9 / 12 / 13 points, Gauss orders 4 and 5 on the square -- src/RefShapes.jl:120-230, 85-110); same arithmetic,
+        // the loop is not unrolled
+        const int nq = NQ ? NQ : c_tab[kind_slot(GK)].npts;
         constexpr bool Q4T = !S && TL_FAST_ACC && TL_HEAT_NUM && TL_Q4_TENSOR && VK == 4 && (NQ == 4 || NQ == 9);
         constexpr int NP = NQ == 9 ? 3 : 2;
         double A00[NP], A10[NP], B01[NP], B11[NP];
@@ -305,7 +310,7 @@ template <int VK, int NQ_> struct HeatForm {
             }
         }
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
+        for (int q = 0; q < nq; q++) {
             if constexpr (Q4T) {
                 const QTab &tg = c_tab[kind_slot(GK)];
                 const double J00 = A00[q % NP], J10 = A10[q % NP], J01 = B01[q / NP], J11 = B11[q / NP];
@@ -377,7 +382,7 @@ template <int VK, int NQ_> struct HeatForm {
 #pragma unroll
             for (int j = 0; j < ND; j++) f[j] = 0.0;
 #pragma unroll
-            for (int q = 0; q < NQ; q++) {
+            for (int q = 0; q < nq; q++) {
                 double J00 = __dmul_rn(X[0], tg.gp[q][0][0]), J01 = __dmul_rn(X[0], tg.gp[q][0][1]);
                 double J10 = __dmul_rn(Y[0], tg.gp[q][0][0]), J11 = __dmul_rn(Y[0], tg.gp[q][0][1]);
 #pragma unroll

@@ -70,6 +70,7 @@ __global__ void __launch_bounds__(256) k_vec_heat_load(const int32_t *__restrict
                                                        double Q, double *__restrict__ fe)
 {
     const QTab &tg = c_tab[kind_slot(NEN)];
+    const int nq = NQ ? NQ : tg.npts;          // NQ = 0: the rule's size is read at run time (the less common rules)
     GRID_STRIDE(e, nel) {
         double X[NEN], Y[NEN];
         load_xy<NEN>(conn, xy, e, X, Y);
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) k_vec_heat_load(const int32_t *__restrict
 #pragma unroll
         for (int j = 0; j < NEN; j++) f[j] = 0.0;
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
+        for (int q = 0; q < nq; q++) {
             // _jac + Jacobian(Val{2}): src/FElements.jl:148-156,120-129 (node-order sum, first term assigned)
             double J00 = __dmul_rn(X[0], tg.gp[q][0][0]), J01 = __dmul_rn(X[0], tg.gp[q][0][1]);
             double J10 = __dmul_rn(Y[0], tg.gp[q][0][0]), J11 = __dmul_rn(Y[0], tg.gp[q][0][1]);
@@ -288,15 +289,16 @@ template <int NEN, int NQ>
 __global__ void __launch_bounds__(256) k_qp_locations(const int32_t *__restrict__ conn, const double2 *__restrict__ xy, int64_t nel, double *__restrict__ out)
 {
     const QTab &tg = c_tab[kind_slot(NEN)];
+    const int nq = NQ ? NQ : tg.npts;
     GRID_STRIDE(e, nel) {
         double X[NEN], Y[NEN];
         load_xy<NEN>(conn, xy, e, X, Y);
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
+        for (int q = 0; q < nq; q++) {
             double lx = __dmul_rn(X[0], tg.N[q][0]), ly = __dmul_rn(Y[0], tg.N[q][0]);
 #pragma unroll
             for (int i = 1; i < NEN; i++) { lx = __dadd_rn(lx, __dmul_rn(X[i], tg.N[q][i])); ly = __dadd_rn(ly, __dmul_rn(Y[i], tg.N[q][i])); }
-            reinterpret_cast<double2 *>(out)[e * NQ + q] = make_double2(lx, ly);
+            reinterpret_cast<double2 *>(out)[e * nq + q] = make_double2(lx, ly);
         }
     }
 }
@@ -312,6 +314,7 @@ __global__ void __launch_bounds__(256) k_l2_error_elem(const int32_t *__restrict
                                                        double *__restrict__ eout, int *__restrict__ err)
 {
     const QTab &tg = c_tab[kind_slot(NEN)];
+    const int nq = NQ ? NQ : tg.npts;
     GRID_STRIDE(e, nel) {
         double X[NEN], Y[NEN], v0[NEN], v1[NEN];
 #pragma unroll
@@ -335,7 +338,7 @@ __global__ void __launch_bounds__(256) k_l2_error_elem(const int32_t *__restrict
         }
         double acc = 0.0;
 #pragma unroll
-        for (int q = 0; q < NQ; q++) {
+        for (int q = 0; q < nq; q++) {
             double J00 = __dmul_rn(X[0], tg.gp[q][0][0]), J01 = __dmul_rn(X[0], tg.gp[q][0][1]);
             double J10 = __dmul_rn(Y[0], tg.gp[q][0][0]), J11 = __dmul_rn(Y[0], tg.gp[q][0][1]);
 #pragma unroll
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(256) k_l2_error_elem(const int32_t *__restrict
                 a0 = __dadd_rn(a0, __dmul_rn(b0, Nb));
                 if (NC > 1) a1 = __dadd_rn(a1, __dmul_rn(b1, Nb));
             }
-            const double *t = truth + (e * NQ + q) * NC;
+            const double *t = truth + (e * nq + q) * NC;
             const double d0 = __dsub_rn(a0, t[0]);
             double sq = __dmul_rn(d0, d0);
             if (NC > 1) { const double d1 = __dsub_rn(a1, t[1]); sq = __dadd_rn(sq, __dmul_rn(d1, d1)); }
@@ -387,5 +390,10 @@ template <class Fn> static bool vec_dispatch_kq(int kind, int npts, Fn &&fn)
     case 404: fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 4>{}); return true;
     case 409: fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 9>{}); return true;
     }
+    // the less common rules: the number of points is read from the table at run time (NQ = 0)
+    const bool tri_rule = npts == 4 || npts == 6 || npts == 7 || npts == 9 || npts == 12 || npts == 13;
+    if (kind == 3 && tri_rule) { fn(std::integral_constant<int, 3>{}, std::integral_constant<int, 0>{}); return true; }
+    if (kind == 6 && tri_rule) { fn(std::integral_constant<int, 6>{}, std::integral_constant<int, 0>{}); return true; }
+    if (kind == 4 && (npts == 16 || npts == 25)) { fn(std::integral_constant<int, 4>{}, std::integral_constant<int, 0>{}); return true; }
     return false;
 }

@@ -23,8 +23,71 @@ static int gauss1(int order, double *pc, double *w) // src/RefShapes.jl:91-106 (
     case 2: pc[0] = -0.577350269189626; pc[1] = 0.577350269189626; w[0] = 1.0; w[1] = 1.0; return 2;
     case 3: pc[0] = -0.774596669241483; pc[1] = 0.0; pc[2] = 0.774596669241483;
             w[0] = 0.5555555555555556; w[1] = 0.8888888888888889; w[2] = 0.5555555555555556; return 3;
+    case 4: pc[0] = -0.86113631159405; pc[1] = -0.33998104358486; pc[2] = 0.33998104358486; pc[3] = 0.86113631159405;
+            w[0] = 0.34785484513745; w[1] = 0.65214515486255; w[2] = 0.65214515486255; w[3] = 0.34785484513745; return 4;
+    case 5: pc[0] = -0.906179845938664; pc[1] = -0.538469310105683; pc[2] = 0.000000000000000;
+            pc[3] = 0.538469310105683; pc[4] = 0.906179845938664;
+            w[0] = 0.236926885056189; w[1] = 0.478628670499367; w[2] = 0.568888888888889;
+            w[3] = 0.478628670499367; w[4] = 0.236926885056189; return 5;
     }
-    return -1;
+    return -1;   // order > 5 is Golub-Welsch in the reference: out of scope
+}
+
+// the higher triangle rules of _triangle, src/RefShapes.jl:120-230: literal tables (incl. the reference's own digits), weights
+// divided by 2 where the source does
+static int triangle_rule_table(int npts, double (*pc)[2], double *w)
+{
+    static const double P4[4][2] = {{0.333333333333333, 0.333333333333333}, {0.200000000000000, 0.200000000000000},
+                                    {0.600000000000000, 0.200000000000000}, {0.200000000000000, 0.600000000000000}};
+    static const double W4[4] = {-0.281250000000000, 0.260416666666667, 0.260416666666667, 0.260416666666667};
+    static const double P6[6][2] = {{0.816847572980459, 0.091576213509771}, {0.091576213509771, 0.816847572980459},
+                                    {0.091576213509771, 0.091576213509771}, {0.108103018168070, 0.445948490915965},
+                                    {0.445948490915965, 0.108103018168070}, {0.445948490915965, 0.445948490915965}};
+    static const double W6[6] = {0.109951743655322, 0.109951743655322, 0.109951743655322, 0.223381589678011, 0.223381589678011, 0.223381589678011};
+    static const double P7[7][2] = {{0.101286507323456, 0.101286507323456}, {0.797426958353087, 0.101286507323456},
+                                    {0.101286507323456, 0.797426958353087}, {0.470142064105115, 0.470142064105115},
+                                    {0.059715871789770, 0.470142064105115}, {0.470142064105115, 0.059715871789770},
+                                    {0.333333333333333, 0.333333333333333}};
+    static const double W7[7] = {0.062969590272414, 0.062969590272414, 0.062969590272414, 0.066197076394253, 0.066197076394253,
+                                 0.066197076394253, 0.112500000000000};
+    static const double P9[9][2] = {{0.437525248383384, 0.437525248383384}, {0.124949503233232, 0.437525248383384},
+                                    {0.437525248383384, 0.124949503233232}, {0.165409927389841, 0.037477420750088},
+                                    {0.037477420750088, 0.165409927389841}, {0.797112651860071, 0.165409927389841},
+                                    {0.165409927389841, 0.797112651860071}, {0.037477420750088, 0.797112651860071},
+                                    {0.797112651860071, 0.037477420750088}};
+    static const double W9[9] = {0.205950504760887, 0.205950504760887, 0.205950504760887, 0.063691414286223, 0.063691414286223,
+                                 0.063691414286223, 0.063691414286223, 0.063691414286223, 0.063691414286223};
+    static const double P12[12][2] = {{0.063089014491502, 0.063089014491502}, {0.873821971016996, 0.063089014491502},
+                                      {0.063089014491502, 0.873821971016996}, {0.249286745170910, 0.249286745170910},
+                                      {0.501426509658179, 0.249286745170910}, {0.249286745170910, 0.501426509658179},
+                                      {0.310352451033785, 0.053145049844816}, {0.053145049844816, 0.310352451033785},
+                                      {0.636502499121399, 0.310352451033785}, {0.310352451033785, 0.636502499121399},
+                                      {0.053145049844816, 0.636502499121399}, {0.636502499121399, 0.053145049844816}};
+    static const double W12[12] = {0.050844906370207, 0.050844906370207, 0.050844906370207, 0.116786275726379, 0.116786275726379,
+                                   0.116786275726379, 0.082851075618374, 0.082851075618374, 0.082851075618374, 0.082851075618374,
+                                   0.082851075618374, 0.082851075618374};
+    static const double P13[13][2] = {{0.333333333333333, 0.333333333333333}, {0.479308067841923, 0.260345966079038},
+                                      {0.260345966079038, 0.479308067841923}, {0.260345966079038, 0.260345966079038},
+                                      {0.869739794195568, 0.065130102902216}, {0.065130102902216, 0.869739794195568},
+                                      {0.065130102902216, 0.065130102902216}, {0.638444188569809, 0.312865496004875},
+                                      {0.638444188569809, 0.048690315425316}, {0.312865496004875, 0.638444188569809},
+                                      {0.312865496004875, 0.048690315425316}, {0.048690315425316, 0.638444188569809},
+                                      {0.048690315425316, 0.312865496004875}};
+    static const double W13[13] = {-0.149570044467670, 0.175615257433204, 0.175615257433204, 0.175615257433204, 0.053347235608839,
+                                   0.053347235608839, 0.053347235608839, 0.077113760890257, 0.077113760890257, 0.077113760890257,
+                                   0.077113760890257, 0.077113760890257, 0.077113760890257};
+    const double (*P)[2] = nullptr; const double *W = nullptr; bool halve = false;
+    switch (npts) {
+    case 4: P = P4; W = W4; break;
+    case 6: P = P6; W = W6; halve = true; break;
+    case 7: P = P7; W = W7; break;
+    case 9: P = P9; W = W9; halve = true; break;
+    case 12: P = P12; W = W12; halve = true; break;
+    case 13: P = P13; W = W13; halve = true; break;
+    default: return -1;
+    }
+    for (int q = 0; q < npts; q++) { pc[q][0] = P[q][0]; pc[q][1] = P[q][1]; w[q] = halve ? W[q] / 2 : W[q]; }
+    return npts;
 }
 
 // returns npts; pc is npts x 2
@@ -39,10 +102,10 @@ static int quadrature_points(int kind, int rule, double (*pc)[2], double *w)
             pc[2][0] = 1.0 / 6; pc[2][1] = 1.0 / 6;
             w[0] = w[1] = w[2] = (1.0 / 3) / 2; return 3;
         }
-        return -1;
+        return triangle_rule_table(rule, pc, w);
     }
     if (kind == EFG_Q4) { // src/RefShapes.jl:350-362: i outer, j inner
-        double p1[3], w1[3];
+        double p1[5], w1[5];
         const int np = gauss1(rule, p1, w1);
         if (np < 0) return -1;
         int r = 0;
@@ -117,6 +180,7 @@ static int build_tables(int vkind, int rule, QTab (&h)[EFG_NTAB])
     if (vkind == EFG_T4) {     // src/FElements.jl:372-378: N = (1 - r - s - t, r, s, t)
         double pc3[EFG_MAXQ][3], w3[EFG_MAXQ];
         const int n3 = quadrature_points_t4(rule, pc3, w3);
+        h[EFG_TAB_T4].npts = n3 > 0 ? n3 : 0;
         for (int q = 0; q < n3; q++) {
             h[EFG_TAB_T4].w[q] = w3[q];
             h[EFG_TAB_T4].N[q][0] = (1 - pc3[q][0] - pc3[q][1] - pc3[q][2]); h[EFG_TAB_T4].N[q][1] = pc3[q][0];
@@ -132,6 +196,7 @@ static int build_tables(int vkind, int rule, QTab (&h)[EFG_NTAB])
     for (int k = 0; k < 5; k++) {
         const bool tri = kinds[k] != EFG_Q4, vtri = vkind != EFG_Q4;
         if (tri != vtri && kinds[k] != EFG_FE_L2) continue;
+        h[k].npts = npts;
         for (int q = 0; q < npts; q++) {
             h[k].w[q] = w[q];
             basis_tables(kinds[k], pc[q][0], pc[q][1], h[k].N[q], h[k].gp[q]);
@@ -974,7 +1039,13 @@ int efg_vec_assemble(efg_ctx *ctx, int vform, int quad, const double *params, in
     case EFG_T4 * 100 + 1: vec_numeric_heat_t4<1>(ctx, vd, Q); break;
     case EFG_T4 * 100 + 4: vec_numeric_heat_t4<4>(ctx, vd, Q); break;
     case EFG_T4 * 100 + 5: vec_numeric_heat_t4<5>(ctx, vd, Q); break;
-    default: efg_throw(EFG_ERR_INVALID, "the heat load vector is not available for element kind %d with rule %d", m0.kind, quad);
+    default: {
+        bool done = false;          // the less common rules: run-time number of points
+        vec_dispatch_kq(m0.kind, npts, [&](auto K, auto Qn) {
+            if constexpr (decltype(Qn)::value == 0) { vec_numeric_heat<decltype(K)::value, 0>(ctx, vd, Q); done = true; }
+        });
+        if (!done) efg_throw(EFG_ERR_INVALID, "the heat load vector is not available for element kind %d with rule %d", m0.kind, quad);
+    }
     }
     CUDA_CHECK(cudaEventRecord(ctx->ev1, ctx->stream));
     vd->vec_ms = elapsed_sync(ctx);

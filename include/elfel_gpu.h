@@ -176,8 +176,10 @@ int efg_set_column_range(efg_ctx *ctx, int64_t col_first, int64_t col_last);
  * columns in ascending order: colptr has (number of owned columns + 1) entries. */
 int efg_set_column_ranges(efg_ctx *ctx, int64_t nranges, const int64_t *col_firsts, const int64_t *col_lasts);
 
-/* Symbolic phase: CSC pattern + scatter maps on the device.  quad_rule: triangles npts (1|3),
- * squares Gauss order (1..3).  Cached until mesh/space/start/range/options change. */
+/* Symbolic phase: CSC pattern + scatter maps on the device.  quad_rule = the QPIterator settings: triangles npts
+ * (1 | 3 for every form; 4 | 6 | 7 | 9 | 12 | 13 for EFG_FORM_HEAT / EFG_VFORM_HEAT_LOAD / locations / error norms:
+ * src/RefShapes.jl:113-230), squares Gauss order (1..3; 4 | 5 for the heat forms: src/RefShapes.jl:85-110, 333-366),
+ * tetrahedra npts (1 | 4 | 5: src/RefShapes.jl:232-259).  Cached until mesh/space/start/range/options change. */
 int efg_symbolic(efg_ctx *ctx, int form_id, int quad_rule, int64_t *nnz_out);
 /* First half of efg_symbolic only: the CSC pattern (colptr / rowval / nnz); the scatter maps are built by the next
  * efg_symbolic / efg_numeric / efg_assemble call.  For callers that overlap: efg_pattern -> allocate the three output

@@ -95,7 +95,61 @@ int efo_quadrature(int elemkind, int rule, double *pc, double *w)
             w[0] = (1.0 / 3) / 2; w[1] = (1.0 / 3) / 2; w[2] = (1.0 / 3) / 2;
             return 3;
         }
-        return -1;
+        /* the higher rules of _triangle, src/RefShapes.jl:120-230: literal tables (weights divided by 2 where the source does) */
+        {
+            static const double P4[4][2] = {{0.333333333333333, 0.333333333333333}, {0.200000000000000, 0.200000000000000},
+                                            {0.600000000000000, 0.200000000000000}, {0.200000000000000, 0.600000000000000}};
+            static const double W4[4] = {-0.281250000000000, 0.260416666666667, 0.260416666666667, 0.260416666666667};
+            static const double P6[6][2] = {{0.816847572980459, 0.091576213509771}, {0.091576213509771, 0.816847572980459},
+                                            {0.091576213509771, 0.091576213509771}, {0.108103018168070, 0.445948490915965},
+                                            {0.445948490915965, 0.108103018168070}, {0.445948490915965, 0.445948490915965}};
+            static const double W6[6] = {0.109951743655322, 0.109951743655322, 0.109951743655322, 0.223381589678011, 0.223381589678011,
+                                         0.223381589678011};                                  /* ... / 2 */
+            static const double P7[7][2] = {{0.101286507323456, 0.101286507323456}, {0.797426958353087, 0.101286507323456},
+                                            {0.101286507323456, 0.797426958353087}, {0.470142064105115, 0.470142064105115},
+                                            {0.059715871789770, 0.470142064105115}, {0.470142064105115, 0.059715871789770},
+                                            {0.333333333333333, 0.333333333333333}};
+            static const double W7[7] = {0.062969590272414, 0.062969590272414, 0.062969590272414, 0.066197076394253, 0.066197076394253,
+                                         0.066197076394253, 0.112500000000000};
+            static const double P9[9][2] = {{0.437525248383384, 0.437525248383384}, {0.124949503233232, 0.437525248383384},
+                                            {0.437525248383384, 0.124949503233232}, {0.165409927389841, 0.037477420750088},
+                                            {0.037477420750088, 0.165409927389841}, {0.797112651860071, 0.165409927389841},
+                                            {0.165409927389841, 0.797112651860071}, {0.037477420750088, 0.797112651860071},
+                                            {0.797112651860071, 0.037477420750088}};
+            static const double W9[9] = {0.205950504760887, 0.205950504760887, 0.205950504760887, 0.063691414286223, 0.063691414286223,
+                                         0.063691414286223, 0.063691414286223, 0.063691414286223, 0.063691414286223};   /* ... ./ 2 */
+            static const double P12[12][2] = {{0.063089014491502, 0.063089014491502}, {0.873821971016996, 0.063089014491502},
+                                              {0.063089014491502, 0.873821971016996}, {0.249286745170910, 0.249286745170910},
+                                              {0.501426509658179, 0.249286745170910}, {0.249286745170910, 0.501426509658179},
+                                              {0.310352451033785, 0.053145049844816}, {0.053145049844816, 0.310352451033785},
+                                              {0.636502499121399, 0.310352451033785}, {0.310352451033785, 0.636502499121399},
+                                              {0.053145049844816, 0.636502499121399}, {0.636502499121399, 0.053145049844816}};
+            static const double W12[12] = {0.050844906370207, 0.050844906370207, 0.050844906370207, 0.116786275726379, 0.116786275726379,
+                                           0.116786275726379, 0.082851075618374, 0.082851075618374, 0.082851075618374, 0.082851075618374,
+                                           0.082851075618374, 0.082851075618374};               /* ... ./ 2 */
+            static const double P13[13][2] = {{0.333333333333333, 0.333333333333333}, {0.479308067841923, 0.260345966079038},
+                                              {0.260345966079038, 0.479308067841923}, {0.260345966079038, 0.260345966079038},
+                                              {0.869739794195568, 0.065130102902216}, {0.065130102902216, 0.869739794195568},
+                                              {0.065130102902216, 0.065130102902216}, {0.638444188569809, 0.312865496004875},
+                                              {0.638444188569809, 0.048690315425316}, {0.312865496004875, 0.638444188569809},
+                                              {0.312865496004875, 0.048690315425316}, {0.048690315425316, 0.638444188569809},
+                                              {0.048690315425316, 0.312865496004875}};
+            static const double W13[13] = {-0.149570044467670, 0.175615257433204, 0.175615257433204, 0.175615257433204, 0.053347235608839,
+                                           0.053347235608839, 0.053347235608839, 0.077113760890257, 0.077113760890257, 0.077113760890257,
+                                           0.077113760890257, 0.077113760890257, 0.077113760890257};   /* ... ' / 2 */
+            const double (*P)[2] = NULL; const double *W = NULL; int halve = 0;
+            switch (rule) {
+            case 4: P = P4; W = W4; break;
+            case 6: P = P6; W = W6; halve = 1; break;
+            case 7: P = P7; W = W7; break;
+            case 9: P = P9; W = W9; halve = 1; break;
+            case 12: P = P12; W = W12; halve = 1; break;
+            case 13: P = P13; W = W13; halve = 1; break;
+            default: return -1;
+            }
+            for (int q = 0; q < rule; q++) { pc[2 * q] = P[q][0]; pc[2 * q + 1] = P[q][1]; w[q] = halve ? W[q] / 2 : W[q]; }
+            return rule;
+        }
     } else if (elemkind == EFO_Q4) { /* src/RefShapes.jl:350-362 */
         double p1[5], w1[5];
         int np = gauss1(rule, p1, w1);

@@ -127,7 +127,7 @@ def test_call_order_and_bad_arguments():
     prob = efg.heat_problem(efg.T3, 4)
     efg.load_problem(eng, prob)
     with pytest.raises(efg.EfgError):
-        eng.assemble(_lib.FORM_HEAT, 7, [1.0])   # no such triangle rule
+        eng.assemble(_lib.FORM_HEAT, 5, [1.0])   # no such triangle rule ("Unknown number of integration points", src/RefShapes.jl:227)
     with pytest.raises(efg.EfgError):
         eng.assemble(_lib.FORM_ELASTICITY, 1, [1.0] * 9)   # space has 1 component
     bad = prob.meshes[0].conn.copy(); bad[0, 0] = 10 ** 6
@@ -386,3 +386,34 @@ def test_row_indices_reach_the_host_identically_on_both_routes(oracle, host_wide
     cp2, rv2, nz2 = eng.fetch_csc()                       # pageable numpy arrays, everything in one call
     assert np.array_equal(cp2, ocp) and np.array_equal(rv2, orv) and np.array_equal(nz2, onz)
     eng.close()
+
+
+@pytest.mark.parametrize("path", [_lib.PATH_TWOPASS, _lib.PATH_TILED], ids=["twopass", "tiled"])
+@pytest.mark.parametrize("kind,N,quad", [(efg.T3, 21, 4), (efg.T3, 17, 6), (efg.T3, 13, 7), (efg.T3, 19, 9), (efg.T3, 11, 12), (efg.T3, 15, 13),
+                                          (efg.T6, 14, 4), (efg.T6, 12, 6), (efg.T6, 10, 7), (efg.T6, 9, 12), (efg.T6, 11, 13),
+                                          (efg.Q4, 18, 4), (efg.Q4, 13, 5)])
+def test_heat_with_the_higher_quadrature_rules(oracle, kind, N, quad, path):
+    """The rules beyond the examples' (triangles with 4 ... 13 points, Gauss orders 4 and 5 on the square: src/RefShapes.jl:85-110,
+    120-230) run through one instantiation per element kind with the number of points read at run time; matrix and load vector
+    against the oracle like the common rules."""
+    prob = efg.heat_problem(kind, N, True, quad=quad)
+    ocp, orv, onz = oracle.assemble(*efg.oracle_args(prob), prob.ndofs, prob.ndofs)
+    oF = oracle.assemble_vec_heat(prob.quad, prob.meshes[0], prob.spaces[0].field.dofnums, 2.5, prob.ndofs)
+    for strict in (1, 0):
+        eng = efg.Engine(0)
+        eng.set_option(_lib.OPT_PATH, path)
+        eng.set_option(_lib.OPT_STRICT_FP, strict)
+        efg.load_problem(eng, prob)
+        eng.assemble(prob.form.form_id, prob.quad, prob.form.params())
+        cp, rv, nz = eng.fetch_csc()
+        eng.vec_assemble(_lib.VFORM_HEAT_LOAD, prob.quad, [2.5], prob.ndofs)
+        F = eng.fetch_vec()
+        loc = eng.qp_locations(0, prob.quad, prob.meshes[0].nel)
+        eng.close()
+        assert np.array_equal(cp, ocp) and np.array_equal(rv, orv)
+        assert F.tobytes() == oF.tobytes()
+        assert loc.tobytes() == oracle.qp_locations(prob.quad, prob.meshes[0]).tobytes()
+        if strict:
+            assert np.array_equal(nz, onz), f"max |d| = {np.abs(nz - onz).max()}"
+        else:
+            assert np.all(np.abs(nz - onz) <= ATOL + RTOL * np.abs(onz)), f"max |d| = {np.abs(nz - onz).max()}"

@@ -48,7 +48,7 @@ def test_load_vector_errors():
     with pytest.raises(_lib.EfgError):                       # unknown vector form / rule
         eng.vec_assemble(99, 1, [1.0], prob.ndofs)
     with pytest.raises(_lib.EfgError):
-        eng.vec_assemble(_lib.VFORM_HEAT_LOAD, 7, [1.0], prob.ndofs)
+        eng.vec_assemble(_lib.VFORM_HEAT_LOAD, 5, [1.0], prob.ndofs)     # no 5-point triangle rule
     eng.vec_assemble(_lib.VFORM_HEAT_LOAD, 1, [1.0], prob.ndofs)
     assert eng.fetch_vec().shape == (prob.ndofs,)
     eng.close()

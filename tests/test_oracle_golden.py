@@ -441,3 +441,22 @@ def test_gauss_rules_integrate_exp_like_the_reference(oracle):
         pc, w = oracle.quadrature(efg.Q4, order)
         assert len(w) == order ** 2                                  # test/test_refshapes.jl:64-67 (mrs4)
         assert np.isclose(float((np.exp(pc[:, 0]) * w).sum()) / 2.0, want, rtol=1e-8, atol=0)
+
+
+def test_higher_triangle_rules_as_in_the_reference(oracle):
+    """src/RefShapes.jl:120-230, test/test_refshapes.jl:74-88 (mrs5: npts in [1, 3, 4, 6, 7, 9, 12, 13]): the literal tables --
+    every rule sums to the triangle's area and integrates the monomials x^a y^b = a! b! / (a + b + 2)! up to its degree (to the
+    precision of the reference's own 15-digit literals: the 7-point rule is only good to 3e-9, one of its coordinates is mistyped
+    in the reference and restated as it is)."""
+    from math import factorial
+    degree = {1: 1, 3: 2, 4: 3, 6: 4, 7: 5, 9: 5, 12: 6, 13: 7}
+    for n, deg in degree.items():
+        pc, w = oracle.quadrature(efg.T3, n)
+        assert len(w) == n and pc.shape == (n, 2)
+        assert abs(w.sum() - 0.5) < 1e-14
+        for d in range(deg + 1):
+            for a in range(d + 1):
+                exact = factorial(a) * factorial(d - a) / factorial(d + 2)
+                assert abs(float((w * pc[:, 0] ** a * pc[:, 1] ** (d - a)).sum()) - exact) < 1e-8, (n, d, a)
+    with pytest.raises(ValueError):
+        oracle.quadrature(efg.T3, 5)            # "Unknown number of integration points"
