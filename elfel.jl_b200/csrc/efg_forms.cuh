@@ -30,10 +30,10 @@
 #endif
 
 struct QTab {
-    int npts, pad_;           // points of the active rule (read by the run-time-NQ instantiations, NQ_ = 0)
     double w[EFG_MAXQ];
     double N[EFG_MAXQ][6];
     double gp[EFG_MAXQ][6][2];
+    int npts, pad_;           // points of the active rule (read by the run-time-NQ instantiations, NQ_ = 0)
 };
 
 // slot 0: T3, 1: Q4, 2: T6 -- tables of the ACTIVE quadrature rule for each element kind
