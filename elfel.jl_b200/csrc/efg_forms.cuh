@@ -546,6 +546,7 @@ template <bool VECLAP_ALT> struct Stokes2Form {
         for (int m = 0; m < 3; m++) d[12 + m] = s.dof1[s.conn1[e * 3 + m]];
     }
     static constexpr bool SPLIT = true;
+    static constexpr int PAIR_COLS = 12;     // columns 0..11 pair up by node, 12..14 (pressure) are single
     __device__ __forceinline__ static int colnode(int J) { return J < 12 ? (J >> 1) : 0; }
     template <bool S> __device__ __forceinline__ static void column_rt(const Geo<6, 3> &G, int J, const double (&gjx)[3],
                                                                         const double (&gjy)[3], double (&out)[ND]) {
@@ -708,6 +709,40 @@ template <bool VECLAP_ALT> struct Stokes2Form {
                 acc = q == 0 ? t : fadd<S>(acc, t);
             }
             put(12 + m, acc);
+        }
+    }
+    // all owned pressure columns of one element in one sweep over the row nodes (bit m of tm: pressure dof m is owned); the
+    // row gradients are read once for up to three columns.  put(m, i, v) = row i of pressure column m.  Entry by entry the
+    // arithmetic of column_single_rt's pressure branch.
+    template <bool S, class Load, class Put>
+    __device__ __forceinline__ static void columns_tail_rt(Load &&g, uint32_t tm, Put &&put) {
+        constexpr int NQ_ = 3, BK_ = 6;
+        const QTab &tp = c_tab[kind_slot(3)];
+        double w[3][NQ_];
+#pragma unroll
+        for (int q = 0; q < NQ_; q++) {
+            const double jw = g(2 * NQ_ * BK_ + q);
+#pragma unroll
+            for (int m = 0; m < 3; m++) w[m][q] = fmul<S>(-jw, tp.N[q][m]);
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) {
+            double ax[NQ_], ay[NQ_];
+#pragma unroll
+            for (int q = 0; q < NQ_; q++) { ax[q] = g(q * BK_ + a); ay[q] = g(NQ_ * BK_ + q * BK_ + a); }
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                if (!(tm & (1u << m))) continue;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int q = 0; q < NQ_; q++) {
+                    const double t0 = fmul<S>(w[m][q], ax[q]), t1 = fmul<S>(w[m][q], ay[q]);
+                    a0 = q == 0 ? t0 : fadd<S>(a0, t0);
+                    a1 = q == 0 ? t1 : fadd<S>(a1, t1);
+                }
+                put(m, 2 * a, a0);
+                put(m, 2 * a + 1, a1);
+            }
         }
     }
     template <bool S, class Load, class Put>

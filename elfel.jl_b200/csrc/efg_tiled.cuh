@@ -97,6 +97,17 @@ __host__ __device__ static inline int tl_geo_block_bytes(int gk, int nelem, int 
 #define TL_PERSIST_SPLIT 0
 #endif
 template <class F> constexpr bool tl_persist() { return TL_GEO && (F::SPLIT ? TL_PERSIST_SPLIT : TL_PERSIST_NS); }
+#ifndef TL_GATHER_SELECT
+#define TL_GATHER_SELECT 0
+#endif
+#ifndef TL_TAIL_PASS
+#define TL_TAIL_PASS 1   // Stokes forms: pressure columns from their own item space (see tl_phase1b_pairs)
+#endif
+#ifndef TL_GEO_QSPLIT
+#define TL_GEO_QSPLIT 0  // vector forms, phase 1a: one thread per (element, quadrature point) instead of one per element: SLOWER
+                         // (elasticity 3.29 -> 3.52 ms, Stokes gen 1.444 -> 1.470): idle threads cost nothing while the co-resident CTA
+                         // runs, the repeated coordinate loads and run-time table indices do (profiles/r2_ab_cta_shapes_and_layouts.txt)
+#endif
 #ifndef TL_GEO_SPLIT
 #define TL_GEO_SPLIT 1  // vector forms: phase 1a reads the tile's geometry block too (the block sits behind the shared
                         // geometry/metadata area)
@@ -977,6 +988,27 @@ __device__ __forceinline__ void tl_geometry_to_smem_local(int le, int ne, const 
         Gs[(2 * NQ * BK + q) * ne + le] = JxW;
     }
 }
+// same, ONE quadrature point of one element per thread (TL_GEO_QSPLIT): a tile of a vector form has fewer elements than the CTA
+// has threads (32 owned + halo = 55-95 against 256 / 384), so phase 1a by element leaves three threads out of four idle
+// while the others run NQ Jacobians in a row.  Same arithmetic (geo_qp, bit for bit), items q-major so that all but two warps
+// read the reference-element tables at one q.  Measured slower than the per-element loop (see TL_GEO_QSPLIT): kept as the record.
+template <class F, bool S>
+__device__ __forceinline__ void tl_geometry_qp_to_smem_local(int le, int q, int ne, const uint16_t *__restrict__ c16, const double2 *__restrict__ sxy,
+                                                             double *__restrict__ Gs)
+{
+    constexpr int GK = F::GK, NQ = F::NQ, BK = F::BK;
+    double X[GK], Y[GK];
+#pragma unroll
+    for (int a = 0; a < GK; a++) { const double2 p = sxy[c16[le * GK + a]]; X[a] = p.x; Y[a] = p.y; }
+    double gx[BK], gy[BK], JxW;
+    geo_qp<S, GK, BK>(X, Y, q, gx, gy, JxW);
+#pragma unroll
+    for (int n = 0; n < BK; n++) {
+        Gs[(q * BK + n) * ne + le] = gx[n];
+        Gs[(NQ * BK + q * BK + n) * ne + le] = gy[n];
+    }
+    Gs[(2 * NQ * BK + q) * ne + le] = JxW;
+}
 template <class F, bool S>
 __device__ __forceinline__ void tl_column_to_stage(int qc, int le, int J, int ne, int nq, const double *__restrict__ Gs, double *__restrict__ stage)
 {
@@ -996,11 +1028,18 @@ __device__ __forceinline__ void tl_column_pair_to_stage(int qc0, int qc1, int le
 // gradients are read once for both).  Elements are ordered by their number of owned columns (descending), qbase[r] = first
 // staged column of "r-th owned column of an element", so pair rank p of element le covers staged columns qbase[2p] + le and
 // qbase[2p+1] + le.  Columns that do not pair up (a pressure dof, a node with one owned dof) take the single-column worker.
+// Forms whose trailing columns never pair up (the pressure dofs of the Stokes forms: F::PAIR_COLS leading columns come in node pairs)
+// get those columns from a second item space, (tail column k, tile element), walked after the pair items and from the LAST thread
+// down: a warp of pair items used to run the pair sweep AND the single-column code whenever one of its elements had a pressure dof
+// at that rank (partly owned halo elements) -- 9% of the Stokes gen kernel (profiles/r2_ab_cta_shapes_and_layouts.txt).
+template <class F, class = void> struct form_pair_cols { static constexpr int value = F::ND; };
+template <class F> struct form_pair_cols<F, std::void_t<decltype(F::PAIR_COLS)>> { static constexpr int value = TL_TAIL_PASS ? F::PAIR_COLS : F::ND; };
 template <class F, bool S, int BLOCK>
 __device__ __forceinline__ void tl_phase1b_pairs(const TileDescFull &td, const uint16_t *__restrict__ smask, int ne, int nq, const double *__restrict__ Gs,
                                                  double *__restrict__ stage, int tid)
 {
-    constexpr int NP = (F::ND + 1) / 2;
+    constexpr int PC = form_pair_cols<F>::value;      // columns below PC pair up by node; ranks >= PC hold tail columns only
+    constexpr int NP = (PC + 1) / 2;
     int total = 0;
 #pragma unroll
     for (int p = 0; p < NP; p++) total += (int)td.qbase[2 * p + 1] - (int)td.qbase[2 * p];
@@ -1014,8 +1053,10 @@ __device__ __forceinline__ void tl_phase1b_pairs(const TileDescFull &td, const u
         uint32_t mm = smask[le];
         for (int k = 0; k < 2 * p; k++) mm &= mm - 1;
         const int J0 = __ffs(mm) - 1;
+        if (PC < F::ND && J0 >= PC) continue;      // a tail column: second item space
         mm &= mm - 1;
-        const int J1 = mm ? __ffs(mm) - 1 : -1;
+        int J1 = mm ? __ffs(mm) - 1 : -1;
+        if (PC < F::ND && J1 >= PC) J1 = -1;
         const int qc0 = (int)td.qbase[2 * p] + le, qc1 = (int)td.qbase[2 * p + 1] + le;
         if (J1 == J0 + 1 && F::pairable(J0)) {
             tl_column_pair_to_stage<F, S>(qc0, qc1, le, J0, ne, nq, Gs, stage);
@@ -1023,6 +1064,29 @@ __device__ __forceinline__ void tl_phase1b_pairs(const TileDescFull &td, const u
             tl_column_to_stage<F, S>(qc0, le, J0, ne, nq, Gs, stage);
             if (J1 >= 0) tl_column_to_stage<F, S>(qc1, le, J1, ne, nq, Gs, stage);
         }
+    }
+    if constexpr (PC < F::ND) {
+#if TL_TAIL_PASS == 1      // one item per (tail column, element): 1.390 ms for Stokes gen against 1.444 without the second item space
+        for (int t = BLOCK - 1 - tid; t < (F::ND - PC) * ne; t += BLOCK) {
+            const int k = t / ne, le = t - k * ne, J = PC + k;
+            const uint32_t m = smask[le];
+            if (m & (1u << J)) tl_column_to_stage<F, S>((int)td.qbase[__popc(m & ((1u << J) - 1u))] + le, le, J, ne, nq, Gs, stage);
+        }
+#else                      // (2) one item per element, all its owned tail columns in one sweep over the row nodes: 1.452 ms -- fewer
+                           // instructions, but two warps with a long divergent item each are the CTA's critical path
+        static_assert(F::ND - PC == 3, "");
+        for (int le = BLOCK - 1 - tid; le < ne; le += BLOCK) {
+            const uint32_t m = smask[le], tm = m >> PC;
+            if (!tm) continue;
+            const int r0 = __popc(m & ((1u << PC) - 1u));
+            double *s0 = stage + (int)td.qbase[r0] + le;
+            double *s1 = stage + (int)td.qbase[r0 + (tm & 1u)] + le;
+            double *s2 = stage + (int)td.qbase[r0 + (tm & 1u) + ((tm >> 1) & 1u)] + le;
+            const double *ge = Gs + le;
+            F::template columns_tail_rt<S>([&](int k) { return ge[k * ne]; }, tm,
+                                           [&](int mcol, int i, double v) { (mcol == 0 ? s0 : (mcol == 1 ? s1 : s2))[i * nq] = v; });
+        }
+#endif
     }
 }
 
@@ -1053,9 +1117,16 @@ __device__ __forceinline__ void tl_gather_light(const TileDescFull &td, const do
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const uint32_t i0 = pk[u] & 0xFFFFu, i1 = pk[u] >> 16;
+#if TL_GATHER_SELECT   // loads always issued (index 0 when there is no contribution), selects instead of predicated loads
+            const bool h0 = i0 < 0xFFFEu, h1 = i1 < 0xFFFEu;
+            const double v0 = stage[h0 ? i0 : 0u], v1 = stage[h1 ? i1 : 0u];
+            acc[u] = h0 ? v0 : 0.0;
+            acc[u] = h1 ? __dadd_rn(acc[u], v1) : acc[u];
+#else
             acc[u] = 0.0;
             if (i0 < 0xFFFEu) acc[u] = stage[i0];
             if (i1 < 0xFFFEu) acc[u] = __dadd_rn(acc[u], stage[i1]);
+#endif
         }
 #pragma unroll
         for (int u = 0; u < U; u++)
@@ -1176,7 +1247,11 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
             const double2 *sxy = reinterpret_cast<const double2 *>(sgeo);
             const uint16_t *sc16 = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode));
             smask = reinterpret_cast<const uint16_t *>(sgeo + tl_geo_xy_bytes(td.nnode) + tl_geo_conn_bytes(GK, ne));
+#if TL_GEO_QSPLIT
+            for (int t = tid; t < F::NQ * ne; t += BLOCK) { const int q = t / ne; tl_geometry_qp_to_smem_local<F, S>(t - q * ne, q, ne, sc16, sxy, Gs); }
+#else
             for (int le = tid; le < ne; le += BLOCK) tl_geometry_to_smem_local<F, S>(le, ne, sc16, sxy, Gs);
+#endif
         } else {
             uint16_t *sm = reinterpret_cast<uint16_t *>(Gs + GSZ * ne);
             for (int le = tid; le < ne; le += BLOCK)
@@ -1357,9 +1432,12 @@ template <class F> __host__ __device__ constexpr int tl_block() { return F::SPLI
 #ifndef TL_MINB_SPLIT
 #define TL_MINB_SPLIT 2
 #endif
-template <class F> constexpr int tl_minb() { return F::SPLIT ? TL_MINB_SPLIT : (F::ND > 8 ? 2 : (F::ND <= 4 ? TL_MINB4 : TL_MINB)); }
+#ifndef TL_MINB_SPLIT15
+#define TL_MINB_SPLIT15 TL_MINB_SPLIT
+#endif
+template <class F> constexpr int tl_minb() { return F::SPLIT ? (F::ND >= 15 ? TL_MINB_SPLIT15 : TL_MINB_SPLIT) : (F::ND > 8 ? 2 : (F::ND <= 4 ? TL_MINB4 : TL_MINB)); }
 
-static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32};
+static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32, 24, 16};
 template <class F> __host__ __device__ constexpr int tl_items_1b() { return TL_PAIRS ? (F::ND + 1) / 2 : F::ND; }
 template <class F> static int tl_default_tile_elems()
 {
