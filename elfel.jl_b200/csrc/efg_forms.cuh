@@ -711,40 +711,6 @@ template <bool VECLAP_ALT> struct Stokes2Form {
             put(12 + m, acc);
         }
     }
-    // all owned pressure columns of one element in one sweep over the row nodes (bit m of tm: pressure dof m is owned); the
-    // row gradients are read once for up to three columns.  put(m, i, v) = row i of pressure column m.  Entry by entry the
-    // arithmetic of column_single_rt's pressure branch.
-    template <bool S, class Load, class Put>
-    __device__ __forceinline__ static void columns_tail_rt(Load &&g, uint32_t tm, Put &&put) {
-        constexpr int NQ_ = 3, BK_ = 6;
-        const QTab &tp = c_tab[kind_slot(3)];
-        double w[3][NQ_];
-#pragma unroll
-        for (int q = 0; q < NQ_; q++) {
-            const double jw = g(2 * NQ_ * BK_ + q);
-#pragma unroll
-            for (int m = 0; m < 3; m++) w[m][q] = fmul<S>(-jw, tp.N[q][m]);
-        }
-#pragma unroll
-        for (int a = 0; a < 6; a++) {
-            double ax[NQ_], ay[NQ_];
-#pragma unroll
-            for (int q = 0; q < NQ_; q++) { ax[q] = g(q * BK_ + a); ay[q] = g(NQ_ * BK_ + q * BK_ + a); }
-#pragma unroll
-            for (int m = 0; m < 3; m++) {
-                if (!(tm & (1u << m))) continue;
-                double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                for (int q = 0; q < NQ_; q++) {
-                    const double t0 = fmul<S>(w[m][q], ax[q]), t1 = fmul<S>(w[m][q], ay[q]);
-                    a0 = q == 0 ? t0 : fadd<S>(a0, t0);
-                    a1 = q == 0 ? t1 : fadd<S>(a1, t1);
-                }
-                put(m, 2 * a, a0);
-                put(m, 2 * a + 1, a1);
-            }
-        }
-    }
     template <bool S, class Load, class Put>
     __device__ __forceinline__ static void column_pair_rt(Load &&g, int nb, Put &&put) {
         constexpr int NQ_ = 3, BK_ = 6;

@@ -1066,27 +1066,14 @@ __device__ __forceinline__ void tl_phase1b_pairs(const TileDescFull &td, const u
         }
     }
     if constexpr (PC < F::ND) {
-#if TL_TAIL_PASS == 1      // one item per (tail column, element): 1.390 ms for Stokes gen against 1.444 without the second item space
+        // Measured alternatives (Stokes gen, 1.389 ms as written; 1.444 without the second item space): tail items confined to
+        // the warps without pair items, in rounds: 1.419; half a column per item: 1.406; one item per element sweeping all its
+        // tail columns: 1.452 (profiles/r2_ab_cta_shapes_and_layouts.txt).
         for (int t = BLOCK - 1 - tid; t < (F::ND - PC) * ne; t += BLOCK) {
             const int k = t / ne, le = t - k * ne, J = PC + k;
             const uint32_t m = smask[le];
             if (m & (1u << J)) tl_column_to_stage<F, S>((int)td.qbase[__popc(m & ((1u << J) - 1u))] + le, le, J, ne, nq, Gs, stage);
         }
-#else                      // (2) one item per element, all its owned tail columns in one sweep over the row nodes: 1.452 ms -- fewer
-                           // instructions, but two warps with a long divergent item each are the CTA's critical path
-        static_assert(F::ND - PC == 3, "");
-        for (int le = BLOCK - 1 - tid; le < ne; le += BLOCK) {
-            const uint32_t m = smask[le], tm = m >> PC;
-            if (!tm) continue;
-            const int r0 = __popc(m & ((1u << PC) - 1u));
-            double *s0 = stage + (int)td.qbase[r0] + le;
-            double *s1 = stage + (int)td.qbase[r0 + (tm & 1u)] + le;
-            double *s2 = stage + (int)td.qbase[r0 + (tm & 1u) + ((tm >> 1) & 1u)] + le;
-            const double *ge = Gs + le;
-            F::template columns_tail_rt<S>([&](int k) { return ge[k * ne]; }, tm,
-                                           [&](int mcol, int i, double v) { (mcol == 0 ? s0 : (mcol == 1 ? s1 : s2))[i * nq] = v; });
-        }
-#endif
     }
 }
 
