@@ -13,7 +13,7 @@ loudly if it is missing.
 """
 from .meshes import (Mesh, T3, Q4, T6, T4, T4block, T3block, Q4block, T6block, T6block_fast, T3toT6, T6toT3,
                      transform, boundary_nodes, vselect, jitter)
-from .fespaces import (FE, FEH1_T3, FEH1_T6, FEH1_Q4, FEH1_T3_BUBBLE, FEH1_T4, FEL2_T3, FEL2_Q4, bfun, edofmdim, FEField, FESpace, edofbfnum, edofcompnt,
+from .fespaces import (FE, FEH1_T3, FEH1_T6, FEH1_Q4, FEH1_T3_BUBBLE, FEH1_T4, FEL2_T3, FEL2_Q4, FEL2_T4, bfun, edofmdim, FEField, FESpace, edofbfnum, edofcompnt,
                        ndofsperel, setebc, numberfreedofs, numberdatadofs, numberdofs, nunknowns,
                        ndofs, highestfreedofnum, highestdatadofnum, gathersysvec, scattersysvec)
 from . import _lib

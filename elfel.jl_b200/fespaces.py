@@ -58,8 +58,17 @@ def FEL2_Q4():
     return FE(Q4, "FEL2_Q4", (0, 0, 1), 1)
 
 
+def FEL2_T4():
+    """src/FElements.jl:454-477: one constant basis function on the cell of a tetrahedron (ndofperfeat [0,0,0,1]; here the
+    third entry of ndofperfeat is the cell whatever its dimension).  The reference has no example that assembles with it
+    (test/test_felements.jl:117-135 checks its tables only); the space machinery (cell field, numbering) is the generic one."""
+    return FE(T4, "FEL2_T4", (0, 0, 1), 1)
+
+
 def bfun(fe: FE, pc):
-    """Scalar basis functions at parametric point pc (src/FElements.jl:239-246, 264-288, 306-320, 341-347, 412-414)."""
+    """Scalar basis functions at parametric point pc (src/FElements.jl:239-246, 264-288, 306-320, 341-347, 412-414, 470-472)."""
+    if fe.ndofperfeat[0] == 0:
+        return np.array([1.0])
     if fe.kind == T4:
         return np.array([1 - pc[0] - pc[1] - pc[2], pc[0], pc[1], pc[2]], dtype=np.float64)
     r, s = float(pc[0]), float(pc[1])

@@ -199,3 +199,18 @@ def test_t4_patch_test_on_a_distorted_mesh(oracle):
     nu = efg.nunknowns(fs)
     T[:nu] = spl.spsolve(K[:nu, :nu].tocsc(), -(K @ T)[:nu])
     assert np.abs(T[fs.field.dofnums[:, 0] - 1] - lin(xyz[:, 0], xyz[:, 1], xyz[:, 2])).max() < 1e-13
+
+
+def test_fel2_t4_tables_and_space():
+    # test/test_felements.jl:117-135 (mfes4): one dof on the cell, none on vertices / edges / faces; bfun == [1.0]
+    fe = efg.FEL2_T4()
+    assert fe.ndofperfeat == (0, 0, 1) and fe.nbf == 1 and fe.nen == 4
+    assert np.array_equal(efg.bfun(fe, [0.25, 0.25, 0.25]), [1.0])
+    # a space on a tetrahedral block: one term per cell, numbered like every other field (src/FESpaces.jl:67-88)
+    mesh = efg.T4block(1.0, 1.0, 1.0, 2, 2, 3)
+    fesp = efg.FESpace(mesh, fe, 1)
+    assert fesp.field is None and fesp.cellfield.nterms == mesh.nel == 6 * 2 * 2 * 3
+    assert efg.ndofsperel(fesp) == 1
+    efg.numberdofs([fesp])
+    assert efg.ndofs(fesp) == mesh.nel and efg.nunknowns(fesp) == mesh.nel
+    assert np.array_equal(np.sort(fesp.cellfield.dofnums[:, 0]), np.arange(1, mesh.nel + 1))
