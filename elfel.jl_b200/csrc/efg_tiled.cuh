@@ -1424,7 +1424,7 @@ template <class F> __host__ __device__ constexpr int tl_block() { return F::SPLI
 #endif
 template <class F> constexpr int tl_minb() { return F::SPLIT ? (F::ND >= 15 ? TL_MINB_SPLIT15 : TL_MINB_SPLIT) : (F::ND > 8 ? 2 : (F::ND <= 4 ? TL_MINB4 : TL_MINB)); }
 
-static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32, 24, 16};
+static const int TL_TILE_SIZES[] = {512, 384, 256, 192, 128, 96, 64, 56, 48, 40, 32};      // (smaller tiles only through EFG_OPT_TILE_ELEMS)
 template <class F> __host__ __device__ constexpr int tl_items_1b() { return TL_PAIRS ? (F::ND + 1) / 2 : F::ND; }
 template <class F> static int tl_default_tile_elems()
 {
