@@ -657,9 +657,10 @@ def main():
         sym_ms = eng.stat(_lib.STAT_SYMBOLIC_MS)
     else:
         ncl = eng.ncols_local
-        o_colptr = torch.empty(ncl + 1, dtype=torch.int64).pin_memory()
-        o_rowval = torch.empty(nnz, dtype=torch.int64).pin_memory()
-        o_nzval = torch.empty(nnz, dtype=torch.float64).pin_memory()
+        # (allocated pinned directly: .pin_memory() on a pageable tensor would allocate, copy and free another 12 GB here)
+        o_colptr = torch.empty(ncl + 1, dtype=torch.int64, pin_memory=True)
+        o_rowval = torch.empty(nnz, dtype=torch.int64, pin_memory=True)
+        o_nzval = torch.empty(nnz, dtype=torch.float64, pin_memory=True)
         d2h = 8 * (ncl + 1) + (4 if host_widen else 8) * nnz + 8 * nnz      # colptr Int64, rowval (Int32 when widened by host threads), nzval
         t0 = time.perf_counter()
         eng.fetch_pattern_async(o_colptr, o_rowval)
