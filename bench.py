@@ -594,7 +594,10 @@ def main():
         prob, col_range, nel_global = make_problem(efg, args.workload, n), None, None
     nel_global = nel_global or prob.nel
 
+    torch.cuda.synchronize()
+    t_create = time.perf_counter()
     eng = efg.Engine(local)
+    create_ms = 1e3 * (time.perf_counter() - t_create)       # efg_create: stream, events, the library's device module
     eng.set_option(_lib.OPT_PATH, args.path)
     eng.set_option(_lib.OPT_STRICT_FP, args.strict)
     eng.set_option(_lib.OPT_TILE_ELEMS, args.tile_elems)
@@ -718,7 +721,7 @@ def main():
                "what": "efg_set_mesh/_space (EFG_OPT_DEFER_XY: coordinates copied while the pattern kernels run) + efg_start + efg_pattern + efg_fetch_pattern_async + efg_numeric + efg_fetch_csc(nzval), pinned host buffers "
                        "(the sequence of the Julia shim's assemble!/finish!: structure copied out while tiles and values are computed)",
                "plain_sequence_ms": 1e3 * float(np.min(ps)),
-               "e2e_first_call": {"value": nel_global / first_s, "ms": 1e3 * first_s, "symbolic_ms": sym_ms,
+               "e2e_first_call": {"value": nel_global / first_s, "ms": 1e3 * first_s, "symbolic_ms": sym_ms, "efg_create_ms": create_ms,
                                   "what": "the same sequence as the first library call of the process (no warm-up; CUDA context creation excluded)"},
                "e2e_reassembly": {"value": nel_global / re_s, "ms": 1e3 * re_s, "d2h_bytes_per_step": int(8 * nnz),
                                   "what": "efg_numeric on the cached pattern + efg_fetch_csc(nzval only)"}}

@@ -454,6 +454,12 @@ int efg_create(int device, efg_ctx **out)
     }
     ctx->pool.stream = ctx->stream;
     tables_register(ctx);
+    // Bring the library's device module in now, like every handle-creating call of the CUDA libraries does: with CUDA's lazy
+    // loading it would otherwise be loaded by the first kernel launch, inside the caller's first assembly.
+    {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, (const void *)k_mailbox) != cudaSuccess) cudaGetLastError();
+    }
     *out = ctx;
     return EFG_OK;
 }

@@ -137,6 +137,7 @@ typedef struct efg_ctx efg_ctx;
 #define EFG_STAT_VEC_MS          10 /* device time of the last efg_vec_assemble numeric part (2 kernels) */
 #define EFG_STAT_SPMV_MS         11 /* device time of the last efg_spmv kernel */
 
+/* efg_create also brings the library's device module in (tens of ms), so that the first assembly does not pay for it. */
 int efg_create(int device, efg_ctx **out);
 int efg_destroy(efg_ctx *ctx);
 const char *efg_last_error(const efg_ctx *ctx);

@@ -1,0 +1,10 @@
+#!/bin/bash
+# EFG_TRACE of the first call in consecutive processes: which symbolic step carries the occasional extra time?
+mkdir -p gpurun_out
+for i in 1 2 3 4; do
+  EFG_TRACE=1 python bench.py --no-cpu --no-callers --no-others --no-config5 --no-widened --e2e-steps 1 --e2e-warmup 1 --steps 2 --warmup 3 2> gpurun_out/trace_$i.txt | python -c "
+import json,sys
+r=json.loads(sys.stdin.read().strip().splitlines()[-1]); e=r['e2e']
+print('process $i: first call %.1f ms (symbolic %.1f, efg_create %.1f), warm %.1f ms' % (e['e2e_first_call']['ms'], e['e2e_first_call']['symbolic_ms'], e['e2e_first_call'].get('efg_create_ms', -1), e['ms_per_step']))"
+  grep -n "efg trace" gpurun_out/trace_$i.txt | head -45 > gpurun_out/trace_first_$i.txt
+done
