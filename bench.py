@@ -722,7 +722,7 @@ def main():
                        "(the sequence of the Julia shim's assemble!/finish!: structure copied out while tiles and values are computed)",
                "plain_sequence_ms": 1e3 * float(np.min(ps)),
                "e2e_first_call": {"value": nel_global / first_s, "ms": 1e3 * first_s, "symbolic_ms": sym_ms, "efg_create_ms": create_ms,
-                                  "what": "the same sequence as the first library call of the process (no warm-up; CUDA context creation excluded)"},
+                                  "what": "the same sequence as the first library call of the process (no warm-up; CUDA context creation excluded; efg_create, which loads the library's device module, is outside and reported as efg_create_ms)"},
                "e2e_reassembly": {"value": nel_global / re_s, "ms": 1e3 * re_s, "d2h_bytes_per_step": int(8 * nnz),
                                   "what": "efg_numeric on the cached pattern + efg_fetch_csc(nzval only)"}}
         checksum = float(o_nzval.sum().item())
