@@ -100,6 +100,12 @@ template <class F> constexpr bool tl_persist() { return TL_GEO && (F::SPLIT ? TL
 #ifndef TL_GATHER_SELECT
 #define TL_GATHER_SELECT 0
 #endif
+#ifndef TL_U_SPLIT
+#define TL_U_SPLIT 3     // rows of slots in flight per warp in the light walk of the vector forms (elasticity: 4 / 3 / 2 rows -> 3.290 / 3.255 /
+#endif                   // 3.269 ms; their CTAs are at the register cap, fewer rows in flight leave more registers to phase 1)
+#ifndef TL_U_SPLIT15
+#define TL_U_SPLIT15 2   // the same for the 15-column Stokes forms (Stokes gen: 1.390 / 1.380 / 1.375 ms)
+#endif
 #ifndef TL_TAIL_PASS
 #define TL_TAIL_PASS 1   // Stokes forms: pressure columns from their own item space (see tl_phase1b_pairs)
 #endif
@@ -1081,12 +1087,11 @@ __device__ __forceinline__ void tl_phase1b_pairs(const TileDescFull &td, const u
 // Light nonzeros (1 or 2 contributions: all but the matrix diagonals of node patches): one packed word per nonzero
 // names both stage entries.  The slots are walked in rows of 32 (one per lane) that never straddle a run, TL_U rows in
 // flight per warp: destination = rowbase[row] + lane, no per-nonzero run tracking.
-template <int BLOCK>
+template <int BLOCK, int U = TL_U>
 __device__ __forceinline__ void tl_gather_light(const TileDescFull &td, const double *__restrict__ stage, const unsigned char *__restrict__ smeta,
                                                 double *__restrict__ nzval, int lane, int warp)
 {
     constexpr int NW = BLOCK / 32;
-    constexpr int U = TL_U;
     const uint32_t *spk = reinterpret_cast<const uint32_t *>(smeta);
     const int64_t *srow = reinterpret_cast<const int64_t *>(smeta + tl_meta_goff_bytes(td.nslot) + tl_meta_gidx_bytes(td.ncontrib));
     const int nrows = td.nslot >> 5;
@@ -1270,7 +1275,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_tl_numeric(const TileDescFull *
 
     // phase 2: every owned nonzero = left-to-right sum of its contributions (append order), stored once
     const uint32_t fdiag = (uint32_t)F::ND * (uint32_t)nq, foff = (uint32_t)tl_srows<F>() * (uint32_t)nq;
-    tl_gather_light<BLOCK>(td, stage, smeta, nzval, lane, warp);
+    tl_gather_light<BLOCK, F::SPLIT ? (F::ND >= 15 ? TL_U_SPLIT15 : TL_U_SPLIT) : TL_U>(td, stage, smeta, nzval, lane, warp);
     // The tile that will occupy a CTA slot about one wave later (pf_dist = CTAs resident on the device): its geometry
     // block (or connectivity) is pulled into L2 at the end of this CTA, so that tile's first load is an L2 hit.  The
     // descriptor is read here, not at kernel start, so nothing stays live across the two phases (no spills).
