@@ -104,7 +104,7 @@ template <class F> constexpr bool tl_persist() { return TL_GEO && (F::SPLIT ? TL
 #define TL_U_SPLIT 3     // rows of slots in flight per warp in the light walk of the vector forms (elasticity: 4 / 3 / 2 rows -> 3.290 / 3.255 /
 #endif                   // 3.269 ms; their CTAs are at the register cap, fewer rows in flight leave more registers to phase 1)
 #ifndef TL_U_SPLIT15
-#define TL_U_SPLIT15 2   // the same for the 15-column Stokes forms (Stokes gen: 1.390 / 1.380 / 1.375 ms)
+#define TL_U_SPLIT15 1   // the same for the 15-column Stokes forms (Stokes gen, 4 / 3 / 2 / 1 rows: 1.390 / 1.380 / 1.375 / 1.369 ms)
 #endif
 #ifndef TL_TAIL_PASS
 #define TL_TAIL_PASS 1   // Stokes forms: pressure columns from their own item space (see tl_phase1b_pairs)
